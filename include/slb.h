@@ -1,0 +1,287 @@
+/* slb.h — C ABI of the B200-native multi-target rasteriser ("slb" = stillleben-b200).
+ *
+ * This is the drop-in boundary for ONE path of AIS-Bonn/stillleben:
+ *     sl::RenderPass::render(Scene&)          (reference: src/render_pass.cpp:303-796)
+ * plus the result hand-off that follows it  (reference: src/cuda_interop.cpp:83-208,
+ *                                            python/src/py_magnum.cpp:17-46).
+ *
+ * The reference has no FFI for this path (it is a C++ class surface + pybind11),
+ * so every entry point below cites the reference C++ interface it replaces.  All functions
+ * are extern "C", take plain pointers and sizes, return an int status (SLB_OK == 0) and never
+ * throw; slb_last_error() gives the message.  No torch / Magnum / CUDA-runtime types appear in
+ * a signature: a CUDA stream is passed as void* (cudaStream_t), device buffers as void*.
+ *
+ * Conventions (identical to the reference):
+ *   - all matrices are 4x4 float32 COLUMN-MAJOR (Magnum::Matrix4 memory order)
+ *   - camera frame: +x right, +y down, +z forward; memory row r == GL window y == r
+ *   - vertex stream: 68-byte interleaved records produced by the reference's
+ *     consolidateMesh()  (reference: src/mesh_tools/consolidate.cpp:53-61)
+ */
+#ifndef SLB_H
+#define SLB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLB_ABI_VERSION 1
+#define SLB_NUM_LIGHTS 3          /* reference: include/stillleben/common.h:17 (NumLights)      */
+#define SLB_VERTEX_STRIDE 68      /* reference: src/mesh_tools/consolidate.cpp:53-61             */
+#define SLB_SHADOW_RES 2048       /* reference: src/render_pass.cpp:271                          */
+#define SLB_INVALID_COORD 3000.0f /* reference: src/render_pass.cpp:316 (clear value "invalid")  */
+
+/* status codes */
+enum {
+    SLB_OK = 0,
+    SLB_ERR_INVALID_ARGUMENT = 1, /* reference: std::invalid_argument -> Python ValueError        */
+    SLB_ERR_RUNTIME = 2,          /* reference: std::runtime_error / logic_error -> RuntimeError  */
+    SLB_ERR_CUDA = 3,             /* reference: std::abort() on CUDA/GL failure (cuda_interop.cpp:99) */
+    SLB_ERR_OUT_OF_MEMORY = 4
+};
+
+/* The eight colour attachments of the reference frame buffer, in attachment order
+ * (reference: src/shaders/common.glsl:14-21, src/render_pass.cpp:347-365). */
+enum {
+    SLB_TARGET_RGB = 0,          /* RGBA8   4 B/px  tone-mapped colour                              */
+    SLB_TARGET_COORD = 1,        /* RGBA32F 16 B/px xyz = object-frame point, w = camera z (depth)  */
+    SLB_TARGET_CLASS = 2,        /* R16UI   2 B/px                                                  */
+    SLB_TARGET_INSTANCE = 3,     /* R16UI   2 B/px                                                  */
+    SLB_TARGET_NORMAL = 4,       /* RGBA32F 16 B/px xyz = camera-space unit normal, w = N.V         */
+    SLB_TARGET_VERTEX_INDEX = 5, /* RGBA32UI 16 B/px xyz = three one-based vertex ids               */
+    SLB_TARGET_BARY = 6,         /* RGBA32F 16 B/px xyz = perspective-correct barycentrics          */
+    SLB_TARGET_CAM_COORD = 7,    /* RGBA32F 16 B/px (x,y,z,1) camera-frame point                    */
+    SLB_NUM_TARGETS = 8
+};
+#define SLB_TARGETS_SIX 0x1Fu /* rgb + coord/depth + class + instance + normals  = 40 B/px */
+#define SLB_TARGETS_ALL 0xFFu /* all eight attachments                           = 88 B/px */
+
+/* texture sampler enums (values follow glTF / GL numeric order loosely; own namespace) */
+enum {
+    SLB_WRAP_REPEAT = 0,
+    SLB_WRAP_CLAMP_TO_EDGE = 1,
+    SLB_WRAP_MIRRORED_REPEAT = 2,
+    SLB_WRAP_CLAMP_TO_BORDER = 3 /* border colour transparent black (context.cpp:597-599) */
+};
+enum {
+    SLB_FILTER_NEAREST = 0,
+    SLB_FILTER_LINEAR = 1,
+    SLB_FILTER_NEAREST_MIPMAP_NEAREST = 2,
+    SLB_FILTER_LINEAR_MIPMAP_NEAREST = 3,
+    SLB_FILTER_NEAREST_MIPMAP_LINEAR = 4,
+    SLB_FILTER_LINEAR_MIPMAP_LINEAR = 5
+};
+enum {
+    SLB_TEXTURE_2D = 0,  /* normalised coords + full mip chain  (reference: GL::Texture2D, mesh.cpp:656-663) */
+    SLB_TEXTURE_RECT = 1 /* pixel coords, clamp-to-border transparent (reference: GL::RectangleTexture, context.cpp:597-599) */
+};
+
+typedef struct slb_ctx slb_ctx;
+typedef struct slb_mesh slb_mesh;
+typedef struct slb_texture slb_texture;
+typedef struct slb_lightmap slb_lightmap;
+typedef struct slb_result slb_result;
+
+/* ---- context -------------------------------------------------------------------------- */
+
+/* Replaces sl::Context::CreateCUDA(device) (reference: src/context.cpp:411, python/src/py_context.cpp:34).
+ * EGL/GL bring-up disappears; this selects the CUDA device and creates the work stream. */
+int slb_ctx_create(int device, slb_ctx** out);
+void slb_ctx_destroy(slb_ctx* ctx);
+/* Last error message for ctx (or for the failed slb_ctx_create when ctx == NULL). */
+const char* slb_last_error(const slb_ctx* ctx);
+int slb_abi_version(void);
+int slb_ctx_device(const slb_ctx* ctx);
+/* Block until all work queued on the context's streams is done. */
+int slb_ctx_synchronize(slb_ctx* ctx);
+
+/* ---- assets --------------------------------------------------------------------------- */
+
+typedef struct slb_image {
+    const void* pixels; /* host OR device pointer (UVA); rows bottom-up exactly as the importers
+                           deliver them: texel (i,j) at pixels[(j*width+i)*channels] */
+    int32_t width, height;
+    int32_t channels; /* 3 or 4, uint8 (reference accepts RGB8/RGBA8 only: mesh.cpp:644-653) */
+    int32_t wrap_s, wrap_t;
+    int32_t min_filter, mag_filter;
+} slb_image;
+
+/* One draw of the reference's object->draw() loop (reference: src/object.cpp:101-140, Drawable). */
+typedef struct slb_submesh {
+    uint32_t index_offset; /* first index into the consolidated index buffer */
+    uint32_t index_count;  /* multiple of 3 */
+    int32_t material;      /* index into materials[], -1 = context default material (context.cpp:382-384) */
+    uint32_t reserved;
+} slb_submesh;
+
+/* What RenderShader::setMaterial() derives from Trade::MaterialData BEFORE the per-object
+ * override (reference: src/shaders/render_shader.cpp:332-418).  The importer-dependent
+ * defaulting (metallic 0.04 / roughness 0.5 / 1.0 with texture / glTF factor) is applied by
+ * the caller that parsed the file; the per-object override is applied inside the library. */
+typedef struct slb_material {
+    float base_color[4];
+    float emissive[4];
+    float metallic;
+    float roughness;
+    int32_t tex_base_color; /* index into images[] or -1 */
+    int32_t tex_normal;
+    int32_t tex_metallic_roughness;
+    int32_t tex_emissive;
+    int32_t tex_occlusion;
+    int32_t reserved;
+} slb_material;
+
+/* Replaces Mesh::loadVisual(): VBO/IBO/texture upload (reference: src/mesh.cpp:624-745).
+ * vertices: n_vertices * 68 bytes; indices: n_indices u32.  bbox_min/max = Mesh::m_bbox (mesh
+ * frame, before pretransform). Host or device source pointers are both accepted (UVA). */
+int slb_mesh_upload(slb_ctx* ctx, const void* vertices, uint32_t n_vertices, const uint32_t* indices,
+                    uint32_t n_indices, const slb_submesh* submeshes, uint32_t n_submeshes,
+                    const slb_material* materials, uint32_t n_materials, const slb_image* images,
+                    uint32_t n_images, const float bbox_min[3], const float bbox_max[3], slb_mesh** out);
+/* Replaces Mesh::recompileMesh()/updateVertexPositionsAndColors() (reference: src/mesh.cpp:763-855). */
+int slb_mesh_update_vertices(slb_ctx* ctx, slb_mesh* mesh, const void* vertices, uint32_t n_vertices);
+void slb_mesh_destroy(slb_ctx* ctx, slb_mesh* mesh);
+
+/* Replaces Context::loadTexture / loadTexture2D and the sl.Texture / sl.Texture2D constructors
+ * (reference: src/context.cpp:560-640, python/src/py_magnum.cpp:115-198). */
+int slb_texture_create(slb_ctx* ctx, const slb_image* image, int kind, slb_texture** out);
+void slb_texture_destroy(slb_ctx* ctx, slb_texture* tex);
+
+/* Light map = the four GPU objects LightMap::load() leaves behind (reference:
+ * src/light_map.cpp:266-611, include/stillleben/light_map.h:33-56):
+ *   env cube 512^2 RGBA32F (mip chain), irradiance cube 32^2, prefilter cube 128^2 x 5 mips,
+ *   BRDF LUT 512^2 RG (stored RGBA32F) + up to 3 directional lights parsed from the .ibl file.
+ * slb_lightmap_create runs the precompute on the device from a lat-long float RGB image
+ * (rows bottom-up, GL addressing), i.e. it replaces the cubemap_shader_* / brdf_shader passes. */
+typedef struct slb_lightmap_desc {
+    const float* equirect_rgb; /* host, width*height*3 float32 */
+    int32_t width, height;
+    int32_t n_lights;                        /* <= SLB_NUM_LIGHTS (light_map.cpp:328-346) */
+    float light_directions[SLB_NUM_LIGHTS][3];
+    float light_colors[SLB_NUM_LIGHTS][3];
+} slb_lightmap_desc;
+int slb_lightmap_create(slb_ctx* ctx, const slb_lightmap_desc* desc, slb_lightmap** out);
+/* Read back the precomputed maps (tests / oracle cross-checks). which: 0 env cube level 0
+ * (6*512*512*4), 1 irradiance (6*32*32*4), 2 prefilter all mips packed, 3 BRDF LUT (512*512*4). */
+int slb_lightmap_read(slb_ctx* ctx, const slb_lightmap* lm, int which, float* host_out, size_t n_floats);
+void slb_lightmap_destroy(slb_ctx* ctx, slb_lightmap* lm);
+
+/* ---- scene descriptor (everything RenderPass::render reads; SURVEY §8b "inputs") ------- */
+
+typedef struct slb_object_desc {
+    const slb_mesh* mesh;
+    float pose[16];         /* objectToWorld  = Object::pose()                 (render_pass.cpp:590) */
+    float pretransform[16]; /* meshToObject   = Mesh::pretransform()           (object.cpp:83)       */
+    uint32_t class_index;   /* Mesh::classIndex()    <= 65535                   (mesh.cpp:1083-1089)  */
+    uint32_t instance_index;/* Object::instanceIndex() <= 65535                 (object.cpp:376-382)  */
+    float metallic;         /* per-object override, < 0 = none                  (object.h:277-278)    */
+    float roughness;
+    int32_t casts_shadows;  /* Object::castsShadows()                           (render_pass.cpp:447) */
+    int32_t visible;        /* result of the DrawPredicate, evaluated by caller (render_pass.cpp:444,587) */
+    const slb_texture* sticker_texture; /* RECT texture or NULL                 (render_pass.cpp:605) */
+    float sticker_projection[16];       /* Object::stickerViewProjection()      (object.cpp:494-513)  */
+    float sticker_range[4];             /* min.x, min.y, size.x, size.y (raw Range2D)                 */
+} slb_object_desc;
+
+typedef struct slb_scene_desc {
+    int32_t width, height;  /* Scene::viewport() */
+    float projection[16];   /* camera().projectionMatrix()                      (scene.cpp:222-258)   */
+    float world_to_cam[16]; /* camera().cameraMatrix()                                                 */
+    /* manual lighting (ignored when light_map != NULL: render_shader.cpp:270-315) */
+    float light_directions[SLB_NUM_LIGHTS][3];
+    float light_colors[SLB_NUM_LIGHTS][3];
+    float ambient_light[3];
+    const slb_lightmap* light_map;
+    /* background plane (render_pass.cpp:545-582); drawn iff dot(size,size) > 0 */
+    float background_plane_size[2];
+    float background_plane_pose[16];
+    const slb_texture* background_plane_texture; /* TEXTURE_2D or NULL */
+    const slb_texture* background_image;         /* TEXTURE_RECT or NULL (render_pass.cpp:637-647) */
+    float manual_exposure;                       /* < 0 = auto exposure (tone_map_shader.frag:109-123) */
+    int32_t ssao_enabled;                        /* RenderPass::ssaoEnabled() (render_pass.h:150) */
+    const slb_object_desc* objects;
+    int32_t n_objects;
+} slb_scene_desc;
+
+/* ---- results --------------------------------------------------------------------------- */
+
+/* Replaces RenderPass::Result + CUDATexture/CUDAMapper (reference: include/stillleben/render_pass.h:48-78,
+ * include/stillleben/cuda_interop.h:17-69).  A result holds n_frames frames of the selected
+ * targets as dense linear device arrays [n_frames][height][width][channels] — the layout the
+ * reference's accessors produce with cudaMemcpy2DFromArray (py_magnum.cpp:17-30) — so map/unmap
+ * and the per-accessor copy disappear.
+ * external_ptrs: optional array of SLB_NUM_TARGETS device pointers owned by the caller (e.g.
+ * torch tensors); entries for targets in target_mask must then be non-NULL. NULL = library
+ * allocates. */
+int slb_result_create(slb_ctx* ctx, int32_t width, int32_t height, int32_t n_frames, uint32_t target_mask,
+                      void* const* external_ptrs, slb_result** out);
+/* Device pointer + bytes per pixel of every target (NULL / 0 for targets not in the mask). */
+int slb_result_ptrs(const slb_result* res, void* ptrs[SLB_NUM_TARGETS], size_t bytes_per_pixel[SLB_NUM_TARGETS]);
+/* Copy one target of frames [first_frame, first_frame + n_frames) to host memory (replaces the CPU
+ * branch of extract(), py_magnum.cpp:33-45). */
+int slb_result_read(slb_ctx* ctx, const slb_result* res, int target, int32_t first_frame, int32_t n_frames,
+                    void* host_out, size_t host_bytes);
+/* Pre-tone-map HDR colour (RGBA32F) of a frame, kept only if slb_ctx_set_option(KEEP_HDR) is on. */
+int slb_result_read_hdr(slb_ctx* ctx, const slb_result* res, int32_t frame, float* host_out, size_t n_floats);
+void slb_result_destroy(slb_ctx* ctx, slb_result* res);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+
+/* Replaces RenderPass::render(Scene&, result, depthBufferResult, predicate) for a BATCH of
+ * independent scenes (reference: src/render_pass.cpp:303; python/src/py_render_pass.cpp:252-258).
+ * Scene i is rendered into frame first_frame + i of `result`.  depth_peel (may be NULL) is the
+ * reference's depthBufferResult: frame first_frame + i of it supplies the previous layer's
+ * coord.w (render_shader.frag:229-233).  All scenes of one call must share width/height with
+ * the result.  Work is queued on `stream` (cudaStream_t as void*, NULL = the context's own
+ * stream); the call returns without synchronising. */
+int slb_render_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int32_t n_scenes, slb_result* result,
+                     int32_t first_frame, const slb_result* depth_peel, void* stream);
+
+/* Same path, host buffers end to end: renders n_scenes scenes in internal sub-batches and copies
+ * the selected targets into caller-provided HOST arrays host_ptrs[t] of layout
+ * [n_scenes][H][W][C] (pinned memory recommended), overlapping D2H copies of sub-batch k with
+ * the rendering of sub-batch k+1.  Synchronous: returns when host_ptrs are complete. */
+int slb_render_batch_host(slb_ctx* ctx, const slb_scene_desc* scenes, int32_t n_scenes, uint32_t target_mask,
+                          void* const host_ptrs[SLB_NUM_TARGETS]);
+
+/* ---- statistics / options ---------------------------------------------------------------- */
+
+typedef struct slb_stats {
+    uint64_t kernel_launches;  /* kernels launched by this library since ctx creation */
+    uint64_t frames_rendered;
+    uint64_t triangles_submitted;
+    uint64_t triangles_binned; /* (sub)triangle-tile pairs emitted by the binner, last batch */
+    uint64_t bytes_h2d;        /* descriptor uploads */
+    uint64_t bytes_d2h;
+    float last_kernel_ms[8];   /* when option TIME_KERNELS is on: setup-count, scan, setup-emit, raster,
+                                  shade/store, ssao, post, other — of the last slb_render_batch call */
+} slb_stats;
+int slb_ctx_get_stats(slb_ctx* ctx, slb_stats* out);
+
+enum {
+    SLB_OPT_TIME_KERNELS = 1, /* record per-kernel CUDA-event times (adds syncs; off by default) */
+    SLB_OPT_KEEP_HDR = 2,     /* keep the HDR colour buffer readable after render             */
+    SLB_OPT_MAX_SUBBATCH = 3  /* frames per internal sub-batch (default 32)                   */
+};
+int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value);
+
+/* ---- config 4: render-and-compare helpers (reference: python/src/diff.cu, bridge_diff.cpp) -- */
+
+/* valid[h,w] = 0 iff pixel is an object pixel and a 3x3 neighbour belongs to a different
+ * non-zero instance with smaller depth (reference: python/src/diff.cu:13-99).
+ * instance_index: int16 HxW, depth: float32 HxW, valid_out: uint8 HxW; all DEVICE pointers. */
+int slb_diff_sobel_valid_mask(slb_ctx* ctx, const int16_t* instance_index, const float* depth,
+                              uint8_t* valid_out, int32_t height, int32_t width, void* stream);
+/* 3x3 dilation of a per-object mask gated on the Sobel-valid mask, copying a neighbour's object
+ * coordinate into newly covered pixels (reference: python/src/diff.cu:101-193).
+ * mask/valid: uint8 HxW; coords: float32 HxWx3 (pixel stride coord_stride floats). */
+int slb_diff_dilate_object_mask(slb_ctx* ctx, const uint8_t* mask, const uint8_t* valid, const float* coords,
+                                int32_t coord_stride, uint8_t* mask_out, float* coords_out, int32_t height,
+                                int32_t width, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLB_H */
