@@ -148,6 +148,10 @@ void slb_mesh_destroy(slb_ctx* ctx, slb_mesh* mesh);
  * (reference: src/context.cpp:560-640, python/src/py_magnum.cpp:115-198). */
 int slb_texture_create(slb_ctx* ctx, const slb_image* image, int kind, slb_texture** out);
 void slb_texture_destroy(slb_ctx* ctx, slb_texture* tex);
+/* Read back mip level `level` as RGBA8 (host_out may be NULL to query the size). Returns the number of
+ * levels (> 0) or a negative/zero status on error. The mip chain is what glGenerateMipmap produces in
+ * the reference (src/mesh.cpp:661-663); tests pin it bit-exactly against the oracle. */
+int slb_texture_read_level(slb_ctx* ctx, const slb_texture* tex, int level, int32_t* width, int32_t* height, void* host_out);
 
 /* Light map = the four GPU objects LightMap::load() leaves behind (reference:
  * src/light_map.cpp:266-611, include/stillleben/light_map.h:33-56):
@@ -163,6 +167,12 @@ typedef struct slb_lightmap_desc {
     float light_colors[SLB_NUM_LIGHTS][3];
 } slb_lightmap_desc;
 int slb_lightmap_create(slb_ctx* ctx, const slb_lightmap_desc* desc, slb_lightmap** out);
+/* Same with explicit map sizes / sample count (values <= 0 select the reference's 512 / 32 / 128 / 512 and
+ * 1024 samples, src/light_map.cpp:381,451,510,580); reduced sizes keep parity tests fast. */
+int slb_lightmap_create_ex(slb_ctx* ctx, const slb_lightmap_desc* desc, int env_size, int irradiance_size, int prefilter_size,
+                           int lut_size, int n_samples, slb_lightmap** out);
+/* sizes[4] = env, irradiance, prefilter (level 0), LUT edge lengths */
+int slb_lightmap_sizes(const slb_lightmap* lm, int32_t sizes[4]);
 /* Read back the precomputed maps (tests / oracle cross-checks). which: 0 env cube level 0
  * (6*512*512*4), 1 irradiance (6*32*32*4), 2 prefilter all mips packed, 3 BRDF LUT (512*512*4). */
 int slb_lightmap_read(slb_ctx* ctx, const slb_lightmap* lm, int which, float* host_out, size_t n_floats);

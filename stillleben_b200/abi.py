@@ -118,7 +118,12 @@ PROTOTYPES = {
     "slb_mesh_destroy": (None, [C.c_void_p, C.c_void_p]),
     "slb_texture_create": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int, C.POINTER(C.c_void_p)]),
     "slb_texture_destroy": (None, [C.c_void_p, C.c_void_p]),
+    "slb_texture_read_level": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                          C.c_void_p]),
     "slb_lightmap_create": (C.c_int, [C.c_void_p, C.POINTER(LightmapDesc), C.POINTER(C.c_void_p)]),
+    "slb_lightmap_create_ex": (C.c_int, [C.c_void_p, C.POINTER(LightmapDesc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_void_p)]),
+    "slb_lightmap_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "slb_lightmap_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "slb_lightmap_destroy": (None, [C.c_void_p, C.c_void_p]),
     "slb_result_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_void_p),

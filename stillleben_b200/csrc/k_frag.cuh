@@ -1,0 +1,410 @@
+// k_frag.cuh — programmable stages of the reference as device functions:
+//   vertex stage     src/shaders/render_shader.vert:57-95
+//   geometry stage   src/shaders/render_shader.geom:13-35   (barycentric basis, flat vertex ids)
+//   fragment stage   src/shaders/render_shader.frag:225-412
+// plus the texture units they use (GL 4.5 core §8.14: LOD selection, bilinear / trilinear filtering,
+// wrap modes; §8.13: cube-map face selection, seamless filtering), written out explicitly in fp32
+// so the results do not depend on the 8-bit filter weights of the hardware texture path.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "k_contract.cuh"
+#include "slb_dev.h"
+
+namespace slbk {
+
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ f3 operator/(f3 a, f3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ f3 normalize3(f3 a) { float l = sqrtf(dot3(a, a)); return mk3(a.x / l, a.y / l, a.z / l); }
+__device__ __forceinline__ f3 max3(f3 a, f3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+__device__ __forceinline__ f3 mix3(f3 a, f3 b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+__device__ __forceinline__ float4 operator*(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// column-major 4x4 times (x,y,z,1)
+__device__ __forceinline__ float4 mul_m4_p(const float* __restrict__ m, float x, float y, float z, float w) {
+    return make_float4(m[0] * x + m[4] * y + m[8] * z + m[12] * w, m[1] * x + m[5] * y + m[9] * z + m[13] * w,
+                       m[2] * x + m[6] * y + m[10] * z + m[14] * w, m[3] * x + m[7] * y + m[11] * z + m[15] * w);
+}
+__device__ __forceinline__ f3 mul_m3(const float* __restrict__ m9, f3 v) {
+    return mk3(m9[0] * v.x + m9[3] * v.y + m9[6] * v.z, m9[1] * v.x + m9[4] * v.y + m9[7] * v.z,
+               m9[2] * v.x + m9[5] * v.y + m9[8] * v.z);
+}
+
+// ---------------------------------------------------------------------------------------------
+// texture units
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int wrap_index(int i, int n, int mode, bool& border) {
+    switch (mode) {
+        case SLB_WRAP_REPEAT: { int m = i % n; return m < 0 ? m + n : m; }
+        case SLB_WRAP_MIRRORED_REPEAT: { int p = 2 * n; int m = i % p; if (m < 0) m += p; return m < n ? m : p - 1 - m; }
+        case SLB_WRAP_CLAMP_TO_BORDER: if (i < 0 || i >= n) { border = true; return 0; } return i;
+        default: return min(max(i, 0), n - 1);
+    }
+}
+__device__ __forceinline__ float4 tex_fetch(const DTexture& t, int level, int lw, int lh, int x, int y) {
+    bool border = false;
+    int xi = wrap_index(x, lw, t.wrap_s, border);
+    int yi = wrap_index(y, lh, t.wrap_t, border);
+    if (border) return make_float4(0.f, 0.f, 0.f, 0.f);
+    uchar4 p = __ldg(reinterpret_cast<const uchar4*>(t.px) + t.level_off[level] + (size_t)yi * lw + xi);
+    return make_float4(p.x / 255.0f, p.y / 255.0f, p.z / 255.0f, p.w / 255.0f);
+}
+__device__ __forceinline__ float4 tex_sample_level(const DTexture& t, int level, float u, float v, bool normalised, bool linear) {
+    int lw = max(1, t.w >> level), lh = max(1, t.h >> level);
+    float xs = normalised ? u * (float)lw : u, ys = normalised ? v * (float)lh : v;
+    if (!linear) return tex_fetch(t, level, lw, lh, (int)floorf(xs), (int)floorf(ys));
+    float x = xs - 0.5f, y = ys - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = x - fx, b = y - fy;
+    int i0 = (int)fx, j0 = (int)fy;
+    float4 t00 = tex_fetch(t, level, lw, lh, i0, j0), t10 = tex_fetch(t, level, lw, lh, i0 + 1, j0);
+    float4 t01 = tex_fetch(t, level, lw, lh, i0, j0 + 1), t11 = tex_fetch(t, level, lw, lh, i0 + 1, j0 + 1);
+    return t00 * ((1 - a) * (1 - b)) + t10 * (a * (1 - b)) + t01 * ((1 - a) * b) + t11 * (a * b);
+}
+// texture2D() with implicit derivatives (du/dx etc. in normalised units per pixel)
+static __device__ float4 tex_sample_2d(const DTexture& t, float u, float v, float dudx, float dvdx, float dudy, float dvdy) {
+    const int max_level = t.n_levels - 1;
+    float W = (float)t.w, H = (float)t.h;
+    float rx = sqrtf(dudx * W * dudx * W + dvdx * H * dvdx * H);
+    float ry = sqrtf(dudy * W * dudy * W + dvdy * H * dvdy * H);
+    float rho = fmaxf(rx, ry);
+    float lambda = log2f(rho);
+    bool mag_linear = (t.mag_filter == SLB_FILTER_LINEAR);
+    int mf = t.min_filter;
+    float c = (mag_linear && (mf == SLB_FILTER_NEAREST_MIPMAP_NEAREST || mf == SLB_FILTER_NEAREST_MIPMAP_LINEAR)) ? 0.5f : 0.0f;
+    if (!(lambda > c)) return tex_sample_level(t, 0, u, v, true, mag_linear);
+    bool lin = (mf == SLB_FILTER_LINEAR || mf == SLB_FILTER_LINEAR_MIPMAP_NEAREST || mf == SLB_FILTER_LINEAR_MIPMAP_LINEAR);
+    if (mf == SLB_FILTER_NEAREST || mf == SLB_FILTER_LINEAR) return tex_sample_level(t, 0, u, v, true, lin);
+    if (mf == SLB_FILTER_NEAREST_MIPMAP_NEAREST || mf == SLB_FILTER_LINEAR_MIPMAP_NEAREST) {
+        int d = (lambda <= 0.5f) ? 0 : min((int)ceilf(lambda + 0.5f) - 1, max_level);
+        return tex_sample_level(t, d, u, v, true, lin);
+    }
+    float lc = fminf(lambda, (float)max_level);
+    int d1 = (int)floorf(lc);
+    int d2 = min(d1 + 1, max_level);
+    float f = lc - (float)d1;
+    float4 s1 = tex_sample_level(t, d1, u, v, true, lin);
+    if (d2 == d1 || f == 0.0f) return s1;
+    float4 s2 = tex_sample_level(t, d2, u, v, true, lin);
+    return s1 * (1.0f - f) + s2 * f;
+}
+__device__ __forceinline__ float4 tex_sample_rect(const DTexture& t, float x, float y) {
+    return tex_sample_level(t, 0, x, y, false, t.mag_filter == SLB_FILTER_LINEAR);
+}
+
+// cube maps: face order +X,-X,+Y,-Y,+Z,-Z (GL 4.5 table 8.19)
+__device__ __forceinline__ void cube_face_coords(f3 d, int& face, float& s, float& t) {
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    float sc, tc, ma;
+    if (ax >= ay && ax >= az) { if (d.x >= 0) { face = 0; sc = -d.z; tc = -d.y; } else { face = 1; sc = d.z; tc = -d.y; } ma = ax; }
+    else if (ay >= az)        { if (d.y >= 0) { face = 2; sc = d.x;  tc = d.z;  } else { face = 3; sc = d.x; tc = -d.z; } ma = ay; }
+    else                      { if (d.z >= 0) { face = 4; sc = d.x;  tc = -d.y; } else { face = 5; sc = -d.x; tc = -d.y; } ma = az; }
+    s = 0.5f * (sc / ma + 1.0f);
+    t = 0.5f * (tc / ma + 1.0f);
+}
+__device__ __forceinline__ f3 cube_face_dir(int face, float s, float t) {
+    float a = 2.0f * s - 1.0f, b = 2.0f * t - 1.0f;
+    switch (face) {
+        case 0: return mk3(1, -b, -a);
+        case 1: return mk3(-1, -b, a);
+        case 2: return mk3(a, 1, b);
+        case 3: return mk3(a, -1, -b);
+        case 4: return mk3(a, -b, 1);
+        default: return mk3(-a, -b, -1);
+    }
+}
+__device__ __forceinline__ float4 cube_tap(const DCubeLevel& l, int face, int x, int y) {
+    int n = l.size;
+    if (x < 0 || x >= n || y < 0 || y >= n) {   // seamless: re-project through the texel centre
+        f3 d = cube_face_dir(face, (x + 0.5f) / n, (y + 0.5f) / n);
+        float s, t; cube_face_coords(d, face, s, t);
+        x = min(max((int)floorf(s * n), 0), n - 1);
+        y = min(max((int)floorf(t * n), 0), n - 1);
+    }
+    return __ldg(l.px + ((size_t)face * n + y) * n + x);
+}
+__device__ __forceinline__ float4 cube_sample_level(const DCubeLevel& l, f3 dir) {
+    int face; float s, t; cube_face_coords(dir, face, s, t);
+    float x = s * l.size - 0.5f, y = t * l.size - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = x - fx, b = y - fy;
+    int i0 = (int)fx, j0 = (int)fy;
+    float4 t00 = cube_tap(l, face, i0, j0), t10 = cube_tap(l, face, i0 + 1, j0);
+    float4 t01 = cube_tap(l, face, i0, j0 + 1), t11 = cube_tap(l, face, i0 + 1, j0 + 1);
+    return t00 * ((1 - a) * (1 - b)) + t10 * (a * (1 - b)) + t01 * ((1 - a) * b) + t11 * (a * b);
+}
+__device__ __forceinline__ float4 cube_sample_lod(const DCubeLevel* levels, int n_levels, f3 dir, float lod) {
+    int max_level = n_levels - 1;
+    float lc = fminf(fmaxf(lod, 0.0f), (float)max_level);
+    int d1 = (int)floorf(lc);
+    int d2 = min(d1 + 1, max_level);
+    float f = lc - (float)d1;
+    float4 s1 = cube_sample_level(levels[d1], dir);
+    if (d2 == d1 || f == 0.0f) return s1;
+    float4 s2 = cube_sample_level(levels[d2], dir);
+    return s1 * (1.0f - f) + s2 * f;
+}
+__device__ __forceinline__ float4 lut_sample(const DLightMap& lm, float u, float v) {
+    int n = lm.lut_size;
+    float x = u * n - 0.5f, y = v * n - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = x - fx, b = y - fy;
+    int i0 = (int)fx, j0 = (int)fy;
+    auto at = [&](int xi, int yi) { xi = min(max(xi, 0), n - 1); yi = min(max(yi, 0), n - 1); return __ldg(lm.lut + (size_t)yi * n + xi); };
+    return at(i0, j0) * ((1 - a) * (1 - b)) + at(i0 + 1, j0) * (a * (1 - b)) + at(i0, j0 + 1) * ((1 - a) * b) + at(i0 + 1, j0 + 1) * (a * b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// vertex stage (render_shader.vert:57-95)
+// ---------------------------------------------------------------------------------------------
+struct VSOut {
+    float u, v;
+    f3 nW, tW, bW;
+    float4 objc;   // xyz object frame, w = camera z
+    f3 wc, cc;
+    float su, sv;  // sticker coordinates
+};
+__device__ __forceinline__ void vertex_stage(const DFrame& f, const DDraw& d, uint32_t vi, VSOut& o, uint32_t& vertex_id) {
+    float4 p4 = __ldg(d.pos4 + vi);
+    vertex_id = __float_as_uint(p4.w);
+    float4 a0 = __ldg(d.attr + 3 * (size_t)vi), a1 = __ldg(d.attr + 3 * (size_t)vi + 1), a2 = __ldg(d.attr + 3 * (size_t)vi + 2);
+    float4 oc4 = mul_m4_p(d.meshToObject, p4.x, p4.y, p4.z, 1.0f);
+    o.objc = make_float4(oc4.x / oc4.w, oc4.y / oc4.w, oc4.z / oc4.w, 1.0f);
+    float4 wc4 = mul_m4_p(d.objectToWorld, oc4.x, oc4.y, oc4.z, oc4.w);
+    o.wc = mk3(wc4.x / wc4.w, wc4.y / wc4.w, wc4.z / wc4.w);
+    float4 cc4 = mul_m4_p(f.V, wc4.x, wc4.y, wc4.z, wc4.w);
+    o.cc = mk3(cc4.x / cc4.w, cc4.y / cc4.w, cc4.z / cc4.w);
+    o.objc.w = o.cc.z;
+    f3 n = mk3(a0.z, a0.w, a1.x), t = mk3(a1.y, a1.z, a1.w);
+    o.nW = normalize3(mul_m3(d.normalToWorld, n));
+    o.tW = normalize3(mul_m3(d.normalToWorld, t));
+    o.bW = normalize3(cross3(o.nW, o.tW)) * a2.x;
+    o.u = a0.x; o.v = a0.y;
+    if (d.sticker) {
+        float4 sp = mul_m4_p(d.stickerProj, oc4.x, oc4.y, oc4.z, oc4.w);
+        o.su = (sp.x / sp.w - d.stickerRange[0]) / d.stickerRange[2];
+        o.sv = (sp.y / sp.w - d.stickerRange[1]) / d.stickerRange[3];
+    } else { o.su = -1.0f; o.sv = -1.0f; }
+}
+
+// perspective-correct barycentrics w.r.t. the ORIGINAL triangle at pixel (px,py) of a sub-triangle
+// (render_shader.geom:13-35: smooth-interpolated barycentric basis)
+__device__ __forceinline__ void subtri_bary(const SubTri& st, const PolyV& a, const PolyV& b, const PolyV& c, int px, int py,
+                                            float out[3]) {
+    long long w0, w1, w2; subtri_weights(st, px, py, w0, w1, w2);
+    float b0 = __ll2float_rn(w0) * st.inv2A, b1 = __ll2float_rn(w1) * st.inv2A, b2 = __ll2float_rn(w2) * st.inv2A;
+    float g0 = b0 * a.invw, g1 = b1 * b.invw, g2 = b2 * c.invw;
+    float s = g0 + g1 + g2;
+    float q0 = g0 / s, q1 = g1 / s, q2 = g2 / s;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) out[j] = q0 * a.b[j] + q1 * b.b[j] + q2 * c.b[j];
+}
+
+struct FragIn {
+    float u, v, u_dx, v_dx, u_dy, v_dy;   // uv at the pixel and the per-pixel finite differences
+    f3 nW, tW, bW; float4 objc; f3 wc, cc; float su, sv;
+    bool front;
+};
+struct FragOut { float4 color, objc, camc, normal; };
+
+#define SLB_LERP(field) (vs[0].field * bary[0] + vs[1].field * bary[1] + vs[2].field * bary[2])
+__device__ __forceinline__ void interpolate(const SubTri& st, const PrimSetup& ps, int k, const VSOut vs[3], int px, int py,
+                                            bool want_derivs, FragIn& in, float bary[3]) {
+    const PolyV &a = ps.v[0], &b = ps.v[k], &c = ps.v[k + 1];
+    subtri_bary(st, a, b, c, px, py, bary);
+    in.u = SLB_LERP(u); in.v = SLB_LERP(v);
+    in.nW = SLB_LERP(nW); in.tW = SLB_LERP(tW); in.bW = SLB_LERP(bW);
+    in.wc = SLB_LERP(wc); in.cc = SLB_LERP(cc);
+    in.objc = make_float4(SLB_LERP(objc.x), SLB_LERP(objc.y), SLB_LERP(objc.z), SLB_LERP(objc.w));
+    in.su = SLB_LERP(su); in.sv = SLB_LERP(sv);
+    in.front = st.twoA < 0;   // FrontFace = CW (render_pass.cpp:330)
+    in.u_dx = in.v_dx = in.u_dy = in.v_dy = 0.0f;
+    if (want_derivs) {
+        // dFdx/dFdy of the 2x2 quad: partner pixel evaluated on the same primitive (helper invocation)
+        float bx[3], by[3];
+        subtri_bary(st, a, b, c, px ^ 1, py, bx);
+        subtri_bary(st, a, b, c, px, py ^ 1, by);
+        float sgx = (px & 1) ? -1.0f : 1.0f, sgy = (py & 1) ? -1.0f : 1.0f;
+        float ux = vs[0].u * bx[0] + vs[1].u * bx[1] + vs[2].u * bx[2], vx = vs[0].v * bx[0] + vs[1].v * bx[1] + vs[2].v * bx[2];
+        float uy = vs[0].u * by[0] + vs[1].u * by[1] + vs[2].u * by[2], vy = vs[0].v * by[0] + vs[1].v * by[1] + vs[2].v * by[2];
+        in.u_dx = sgx * (ux - in.u); in.v_dx = sgx * (vx - in.v);
+        in.u_dy = sgy * (uy - in.u); in.v_dy = sgy * (vy - in.v);
+    }
+}
+
+__device__ __forceinline__ float4 sample_mat(const DTexture* t, const FragIn& in) {
+    return tex_sample_2d(*t, in.u, in.v, in.u_dx, in.v_dx, in.u_dy, in.v_dy);
+}
+__device__ __forceinline__ float4 to_linear(float4 c) { return make_float4(powf(c.x, 2.2f), powf(c.y, 2.2f), powf(c.z, 2.2f), c.w); }
+__device__ __forceinline__ bool draw_has_textures(const DDraw& d) { return d.tex[0] || d.tex[1] || d.tex[2] || d.tex[3] || d.tex[4]; }
+
+// base colour incl. alpha (render_shader.frag:237-246)
+__device__ __forceinline__ float4 base_color(const DDraw& d, const FragIn& in) {
+    float4 bc = make_float4(d.base_color[0], d.base_color[1], d.base_color[2], d.base_color[3]);
+    if (d.tex[0]) { float4 t = to_linear(sample_mat(d.tex[0], in)); bc = make_float4(bc.x * t.x, bc.y * t.y, bc.z * t.z, bc.w * t.w); }
+    return bc;
+}
+
+__device__ __forceinline__ float DistributionGGX(f3 N, f3 H, float roughness) {
+    float a = roughness * roughness, a2 = a * a;
+    float NdotH = fmaxf(dot3(N, H), 0.0f), NdotH2 = NdotH * NdotH;
+    float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
+    denom = 3.141592653589793f * denom * denom;
+    return a2 / denom;
+}
+__device__ __forceinline__ float GeometrySchlickGGX(float NdotV, float roughness) {
+    float r = roughness + 1.0f, k = (r * r) / 8.0f;
+    return NdotV / (NdotV * (1.0f - k) + k);
+}
+
+// sampler2DArrayShadow tap: linear filter of (ref <= stored), clamp-to-edge (render_shader.frag:321-337)
+__device__ __forceinline__ float shadow_tap(const uint32_t* __restrict__ map, float u, float v, float ref) {
+    const int N = SLB_SHADOW_RES;
+    ref = clampf(ref, 0.0f, 1.0f);
+    float x = u * N - 0.5f, y = v * N - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = x - fx, b = y - fy;
+    int i0 = (int)fx, j0 = (int)fy;
+    int i1 = min(max(i0 + 1, 0), N - 1), j1 = min(max(j0 + 1, 0), N - 1);
+    i0 = min(max(i0, 0), N - 1); j0 = min(max(j0, 0), N - 1);
+    auto cmp = [&](int i, int j) {
+        float stored = (float)min(__ldg(map + (size_t)j * N + i), 0xFFFFFFu) / 16777215.0f;
+        return ref <= stored ? 1.0f : 0.0f;
+    };
+    return cmp(i0, j0) * ((1 - a) * (1 - b)) + cmp(i1, j0) * (a * (1 - b)) + cmp(i0, j1) * ((1 - a) * b) + cmp(i1, j1) * (a * b);
+}
+
+// fragment stage (render_shader.frag:225-412); the discards are evaluated by the rasteriser
+__device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, const FragIn& in, FragOut& out) {
+    const float PI = 3.141592653589793f;
+    float4 baseColor = base_color(d, in);
+    if (d.sticker && in.su >= 0 && in.sv >= 0 && in.su < 1 && in.sv < 1) {
+        float4 sc = to_linear(tex_sample_rect(*d.sticker, in.su * d.sticker->w, in.sv * d.sticker->h));
+        float a = sc.w;
+        baseColor = make_float4(baseColor.x * (1 - a) + sc.x * a, baseColor.y * (1 - a) + sc.y * a, baseColor.z * (1 - a) + sc.z * a,
+                                baseColor.w * (1 - a) + sc.w * a);
+    }
+    f3 normal;
+    if (d.tex[1]) {
+        float4 t = sample_mat(d.tex[1], in);
+        normal = normalize3(in.tW * (t.x * 2.0f - 1.0f) + in.bW * (t.y * 2.0f - 1.0f) + in.nW * (t.z * 2.0f - 1.0f));
+    } else normal = in.nW;
+    if (!in.front) normal = -normal;
+
+    f3 camPos = mk3(f.camPos[0], f.camPos[1], f.camPos[2]);
+    f3 cameraDirection = normalize3(camPos - in.wc);
+    f3 I = -cameraDirection;
+    f3 reflDir = I - normal * (2.0f * dot3(normal, I));
+    float NoV = clampf(dot3(normal, cameraDirection), 1e-5f, 1.0f);
+
+    float roughness = d.roughness, metallic = d.metallic;
+    if (d.tex[2]) { float4 t = sample_mat(d.tex[2], in); roughness *= t.y; metallic *= t.z; }
+    roughness = fmaxf(roughness, 0.045f);
+    float occlusion = 1.0f;
+    if (d.tex[4]) occlusion = sample_mat(d.tex[4], in).x;
+    f3 emissive = mk3(d.emissive[0], d.emissive[1], d.emissive[2]);
+    if (d.tex[3]) { float4 t = to_linear(sample_mat(d.tex[3], in)); emissive = emissive * mk3(t.x, t.y, t.z); }
+
+    f3 color = mk3(0.f, 0.f, 0.f);
+    f3 bc = mk3(baseColor.x, baseColor.y, baseColor.z);
+    f3 c_diff = bc * (1.0f - 0.04f) * (1.0f - metallic);
+    f3 F0 = mix3(mk3(0.04f, 0.04f, 0.04f), bc, metallic);
+    f3 Fr = max3(mk3(1.0f - roughness, 1.0f - roughness, 1.0f - roughness), F0) - F0;
+    f3 k_S = F0 + Fr * powf(1.0f - NoV, 5.0f);
+
+    const float shadowMapScale = 1.0f / (float)SLB_SHADOW_RES;
+#pragma unroll 1
+    for (int i = 0; i < SLB_NUM_LIGHTS; ++i) {
+        if (!f.lightActive[i]) continue;
+        float4 pc = mul_m4_p(f.shadowMat[i], in.wc.x, in.wc.y, in.wc.z, 1.0f);
+        float pcx = 0.5f * (pc.x / pc.w) + 0.5f, pcy = 0.5f * (pc.y / pc.w) + 0.5f, pcz = 0.5f * (pc.z / pc.w) + 0.5f;
+        float inverseShadow = 0.0f;
+        const uint32_t* map = f.shadowMap[i];
+        for (int yy = 0; yy < 4; ++yy)
+            for (int xx = 0; xx < 4; ++xx)
+                inverseShadow += shadow_tap(map, pcx + (-1.5f + xx) * shadowMapScale, pcy + (-1.5f + yy) * shadowMapScale, pcz - 0.00003f);
+        inverseShadow /= 16.0f;
+
+        f3 L = normalize3(mk3(-f.lightDir[i][0], -f.lightDir[i][1], -f.lightDir[i][2]));
+        f3 H = normalize3(cameraDirection + L);
+        f3 radiance = mk3(f.lightCol[i][0], f.lightCol[i][1], f.lightCol[i][2]);
+        float NDF = DistributionGGX(normal, H, roughness);
+        float NdotL = fmaxf(dot3(normal, L), 0.0f);
+        float G = GeometrySchlickGGX(NdotL, roughness) * GeometrySchlickGGX(fmaxf(dot3(normal, cameraDirection), 0.0f), roughness);
+        f3 nominator = k_S * (NDF * G);
+        float denominator = 4.0f * NoV * NdotL;
+        f3 specular = nominator / fmaxf(denominator, 0.001f);
+        f3 kD = (mk3(1.f, 1.f, 1.f) - k_S) * (1.0f - metallic);
+        color = color + (kD * bc / PI + specular) * radiance * (inverseShadow * NdotL);
+    }
+    color = color + mk3(f.ambient[0], f.ambient[1], f.ambient[2]) * bc;
+
+    if (f.lm) {
+        const DLightMap& lm = *f.lm;
+        float4 fab = lut_sample(lm, NoV, roughness);
+        float4 rad = cube_sample_lod(lm.pre, 5, reflDir, roughness * 4.0f);
+        float4 irr = cube_sample_lod(&lm.irr, 1, normal, 0.0f);
+        f3 radiance = mk3(rad.x, rad.y, rad.z), irradiance = mk3(irr.x, irr.y, irr.z);
+        f3 one = mk3(1.f, 1.f, 1.f);
+        f3 FssEss = k_S * fab.x + mk3(fab.y, fab.y, fab.y);
+        float Ems = 1.0f - (fab.x + fab.y);
+        f3 F_avg = F0 + (one - F0) / 21.0f;
+        f3 FmsEms = FssEss * F_avg * Ems / (one - F_avg * Ems);
+        f3 k_D = c_diff * (one - FssEss - FmsEms);
+        f3 selfColor = FssEss * radiance + (FmsEms + k_D) * irradiance;
+        color = color + selfColor * occlusion;
+    }
+    color = color + emissive;
+
+    out.color = make_float4(color.x, color.y, color.z, baseColor.w);
+    out.objc = in.objc;
+    out.camc = make_float4(in.cc.x, in.cc.y, in.cc.z, 1.0f);
+    f3 nc = mk3(f.V[0] * normal.x + f.V[4] * normal.y + f.V[8] * normal.z, f.V[1] * normal.x + f.V[5] * normal.y + f.V[9] * normal.z,
+                f.V[2] * normal.x + f.V[6] * normal.y + f.V[10] * normal.z);
+    nc = normalize3(nc);
+    out.normal = make_float4(nc.x, nc.y, nc.z, dot3(normal, cameraDirection));
+}
+
+// tone map (tone_map_shader.frag:102-131): RGB -> Yxy, exposure, -> RGB, ACES, RGBA8 (linear: the
+// gamma line of the reference is overwritten)
+__device__ __forceinline__ float aces1(float x) {
+    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
+    float v = (x * (a * x + b)) / (x * (c * x + d) + e);
+    return (v != v) ? 0.0f : clampf(v, 0.0f, 1.0f);
+}
+__device__ __forceinline__ unsigned unorm8(float v) {
+    if (!(v == v)) return 0u;
+    return (unsigned)__float2int_rn(clampf(v, 0.0f, 1.0f) * 255.0f);
+}
+__device__ __forceinline__ uchar4 tone_map(float4 hdr, float manual_exposure, const float* avg) {
+    float X = 0.4124564f * hdr.x + 0.3575761f * hdr.y + 0.1804375f * hdr.z;
+    float Y = 0.2126729f * hdr.x + 0.7151522f * hdr.y + 0.0721750f * hdr.z;
+    float Z = 0.0193339f * hdr.x + 0.1191920f * hdr.y + 0.9503041f * hdr.z;
+    float inv = 1.0f / (X + Y + Z);
+    float yY = Y, yx = X * inv, yy = Y * inv;
+    if (manual_exposure >= 0) yY *= manual_exposure;
+    else {
+        float lum = 0.1f * (0.2125f * (avg[0] / avg[3]) + 0.7154f * (avg[1] / avg[3]) + 0.0721f * (avg[2] / avg[3]));
+        yY /= (9.6f * lum + 0.0001f);
+    }
+    float x2 = yY * yx / yy, y2 = yY, z2 = yY * (1.0f - yx - yy) / yy;
+    float r = 3.2404542f * x2 - 1.5371385f * y2 - 0.4985314f * z2;
+    float g = -0.9692660f * x2 + 1.8760108f * y2 + 0.0415560f * z2;
+    float b = 0.0556434f * x2 - 0.2040259f * y2 + 1.0572252f * z2;
+    return make_uchar4((unsigned char)unorm8(aces1(r)), (unsigned char)unorm8(aces1(g)), (unsigned char)unorm8(aces1(b)),
+                       (unsigned char)unorm8(hdr.w));
+}
+
+}  // namespace slbk

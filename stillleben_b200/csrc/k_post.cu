@@ -1,0 +1,166 @@
+// k_post.cu — full-screen passes that follow the geometry pass when they are enabled:
+//   background image / IBL sky box     reference: src/render_pass.cpp:637-660, src/shaders/background_*.{vert,frag}
+//   auto-exposure average (mip chain)  reference: src/render_pass.cpp:632-635, tone_map_shader.frag:114-122
+//   SSAO + bilateral blur/apply        reference: src/render_pass.cpp:662-694, ssao_shader.frag:20-57, ssao_apply_shader.frag:29-76
+//   tone map                           reference: src/render_pass.cpp:696-710, tone_map_shader.frag:102-131
+// When none of them is needed the shade kernel tone-maps in registers and these kernels never run.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "k_frag.cuh"
+#include "kernels.h"
+
+using namespace slbk;
+
+__constant__ float c_ssao_noise[16 * 3];
+__constant__ float c_ssao_kernel[64 * 3];
+
+// linear-filtered rectangle-texture read of an RGBA32F image (clamp-to-edge), z component only
+__device__ __forceinline__ float rect_linear_z(const float4* __restrict__ img, int W, int H, float xs, float ys) {
+    float x = xs - 0.5f, y = ys - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = x - fx, b = y - fy;
+    int i0 = (int)fx, j0 = (int)fy;
+    int i1 = min(max(i0 + 1, 0), W - 1), j1 = min(max(j0 + 1, 0), H - 1);
+    i0 = min(max(i0, 0), W - 1); j0 = min(max(j0, 0), H - 1);
+    float z00 = __ldg(&img[(size_t)j0 * W + i0].z), z10 = __ldg(&img[(size_t)j0 * W + i1].z);
+    float z01 = __ldg(&img[(size_t)j1 * W + i0].z), z11 = __ldg(&img[(size_t)j1 * W + i1].z);
+    return z00 * ((1 - a) * (1 - b)) + z10 * (a * (1 - b)) + z01 * ((1 - a) * b) + z11 * (a * b);
+}
+
+__global__ void __launch_bounds__(256) k_background(const DFrame* __restrict__ frames) {
+    const DFrame& f = frames[blockIdx.z];
+    const int W = f.W, H = f.H;
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (px >= W || py >= H) return;
+    const size_t p = (size_t)py * W + px;
+    const unsigned long long key = f.keys[p];
+    if (f.bg_image) {
+        // full-screen quad at z_ndc = 0 under depth func LESS: wins wherever stored depth24 > d24(0.5)
+        const uint32_t quad_d24 = __float2uint_rn(0.5f * 16777215.0f);
+        uint32_t d24 = (key == SLB_KEY_EMPTY) ? 0xFFFFFFu : (uint32_t)(key >> 40);
+        if (!(quad_d24 < d24)) return;
+        const DTexture& bg = *f.bg_image;
+        float tx = ((px + 0.5f) / W), ty = 1.0f - ((py + 0.5f) / H);
+        int ix = (int)(tx * bg.w), iy = (int)(ty * bg.h);
+        float4 c = tex_sample_rect(bg, (float)ix, (float)iy);
+        f.hdr[p] = make_float4(c.x, c.y, c.z, 0.0f);
+    } else if (f.lm) {
+        if (key != SLB_KEY_EMPTY) return;
+        float xn = 2.0f * (px + 0.5f) / W - 1.0f, yn = 2.0f * (py + 0.5f) / H - 1.0f;
+        float4 q = mul_m4_p(f.Pinv, xn, yn, 1.0f, 1.0f);
+        f3 dc = mk3(q.x / q.w, q.y / q.w, q.z / q.w);
+        f3 dw = mk3(f.V[0] * dc.x + f.V[1] * dc.y + f.V[2] * dc.z, f.V[4] * dc.x + f.V[5] * dc.y + f.V[6] * dc.z,
+                    f.V[8] * dc.x + f.V[9] * dc.y + f.V[10] * dc.z);
+        float4 c = cube_sample_lod(f.lm->env, f.lm->n_env, dw, 0.0f);
+        f.hdr[p] = make_float4(c.x, c.y, c.z, 0.0f);
+    }
+}
+
+// one glGenerateMipmap step of an RGBA32F image: 2x2 box for even sizes, polyphase box for odd sizes
+__device__ __forceinline__ void mip_taps(int sN, int dN, int i, int idx[3], float w[3]) {
+    if (sN == 1) { idx[0] = idx[1] = idx[2] = 0; w[0] = 1; w[1] = w[2] = 0; return; }
+    if ((sN & 1) == 0) { idx[0] = 2 * i; idx[1] = idx[2] = 2 * i + 1; w[0] = w[1] = 0.5f; w[2] = 0; return; }
+    idx[0] = 2 * i; idx[1] = 2 * i + 1; idx[2] = 2 * i + 2;
+    w[0] = (float)(dN - i) / sN; w[1] = (float)dN / sN; w[2] = (float)(i + 1) / sN;
+}
+__global__ void k_downsample(const float4* __restrict__ src, int sw, int sh, float4* __restrict__ dst, int dw, int dh, size_t src_stride,
+                             size_t dst_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const float4* s = src + blockIdx.z * src_stride;
+    int ix[3], iy[3]; float wx[3], wy[3];
+    mip_taps(sw, dw, x, ix, wx); mip_taps(sh, dh, y, iy, wy);
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) {
+            double w = (double)__fmul_rn(wy[b], wx[a]);
+            float4 v = s[(size_t)iy[b] * sw + ix[a]];
+            a0 += w * v.x; a1 += w * v.y; a2 += w * v.z; a3 += w * v.w;
+        }
+    dst[blockIdx.z * dst_stride + (size_t)y * dw + x] = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
+}
+
+__device__ __forceinline__ float smoothstep01(float x) { float t = clampf(x, 0.0f, 1.0f); return t * t * (3.0f - 2.0f * t); }
+
+__global__ void __launch_bounds__(256) k_ssao(const DFrame* __restrict__ frames) {
+    const DFrame& f = frames[blockIdx.z];
+    const int W = f.W, H = f.H;
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (px >= W || py >= H) return;
+    const size_t p = (size_t)py * W + px;
+    if (!f.ssao) { f.ao[p] = 1.0f; return; }
+    float4 c4 = f.scratch_cam[p], n4 = f.scratch_normal[p];
+    if (n4.x == 0 && n4.y == 0 && n4.z == 0) { f.ao[p] = 1.0f; return; }
+    f3 fragPos = mk3(c4.x, c4.y, c4.z);
+    f3 normal = normalize3(mk3(n4.x, n4.y, n4.z));
+    const float* nz = c_ssao_noise + ((py & 3) * 4 + (px & 3)) * 3;
+    f3 randomVec = normalize3(mk3(nz[0], nz[1], nz[2]));
+    f3 tangent = normalize3(randomVec - normal * dot3(randomVec, normal));
+    f3 bitangent = cross3(normal, tangent);
+    float occlusion = 0.0f;
+    for (int i = 0; i < 64; ++i) {
+        f3 s = mk3(c_ssao_kernel[i * 3], c_ssao_kernel[i * 3 + 1], c_ssao_kernel[i * 3 + 2]);
+        f3 samplePos = tangent * s.x + bitangent * s.y + normal * s.z;
+        samplePos = fragPos + samplePos * 0.1f;
+        float4 off = mul_m4_p(f.P, samplePos.x, samplePos.y, samplePos.z, 1.0f);
+        float ox = off.x / off.w * 0.5f + 0.5f, oy = off.y / off.w * 0.5f + 0.5f;
+        float sampleDepth = rect_linear_z(f.scratch_cam, W, H, ox * W, oy * H);
+        float rangeCheck = smoothstep01(0.1f / fabsf(fragPos.z - sampleDepth));
+        occlusion += (sampleDepth <= samplePos.z - 0.0025f ? 1.0f : 0.0f) * rangeCheck;
+    }
+    f.ao[p] = 1.0f - (occlusion / 64.0f);
+}
+
+__global__ void __launch_bounds__(256) k_ssao_apply_tonemap(const DFrame* __restrict__ frames) {
+    const DFrame& f = frames[blockIdx.z];
+    const int W = f.W, H = f.H;
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (px >= W || py >= H) return;
+    const size_t p = (size_t)py * W + px;
+    float4 hdr = f.hdr[p];
+    if (f.ssao) {
+        float center_d = rect_linear_z(f.scratch_cam, W, H, (float)px, (float)py);
+        float result = 0.0f, w_total = 0.0f;
+        const float BlurSigma = 3.0f * 0.5f, BlurFalloff = 1.0f / (2.0f * BlurSigma * BlurSigma);
+        for (int x = -2; x < 2; ++x)
+            for (int y = -2; y < 2; ++y) {
+                int ux = px + x, uy = py + y;
+                float c = (ux >= 0 && ux < W && uy >= 0 && uy < H) ? f.ao[(size_t)uy * W + ux] : 0.0f;
+                float dd = rect_linear_z(f.scratch_cam, W, H, (float)ux, (float)uy);
+                float r = sqrtf((float)(x * x + y * y));
+                float ddiff = (dd - center_d) * 300.0f;
+                float w = exp2f(-r * r * BlurFalloff - ddiff * ddiff);
+                w_total += w;
+                result += c * w;
+            }
+        float a = result / w_total;
+        hdr.x *= a; hdr.y *= a; hdr.z *= a;
+        f.hdr[p] = hdr;
+    }
+    if (f.out[SLB_TARGET_RGB]) reinterpret_cast<uchar4*>(f.out[SLB_TARGET_RGB])[p] = tone_map(hdr, f.manual_exposure, f.avg);
+}
+
+namespace slbk {
+
+void upload_ssao_tables(const float* noise16x3, const float* kernel64x3) {
+    cudaMemcpyToSymbol(c_ssao_noise, noise16x3, sizeof(float) * 48);
+    cudaMemcpyToSymbol(c_ssao_kernel, kernel64x3, sizeof(float) * 192);
+}
+static dim3 frame_grid(int n_frames, int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8, n_frames); }
+void launch_background(const DFrame* frames, int n_frames, int W, int H, cudaStream_t s) {
+    k_background<<<frame_grid(n_frames, W, H), 256, 0, s>>>(frames);
+}
+void launch_downsample(const float4* src, int sw, int sh, float4* dst, int n_frames, size_t src_stride, size_t dst_stride, cudaStream_t s) {
+    int dw = sw > 1 ? sw >> 1 : 1, dh = sh > 1 ? sh >> 1 : 1;
+    dim3 block(16, 16), grid((dw + 15) / 16, (dh + 15) / 16, n_frames);
+    k_downsample<<<grid, block, 0, s>>>(src, sw, sh, dst, dw, dh, src_stride, dst_stride);
+}
+void launch_ssao(const DFrame* frames, int n_frames, int W, int H, cudaStream_t s) {
+    k_ssao<<<frame_grid(n_frames, W, H), 256, 0, s>>>(frames);
+}
+void launch_ssao_apply_tonemap(const DFrame* frames, int n_frames, int W, int H, cudaStream_t s) {
+    k_ssao_apply_tonemap<<<frame_grid(n_frames, W, H), 256, 0, s>>>(frames);
+}
+
+}  // namespace slbk

@@ -1,0 +1,458 @@
+// k_render.cu — the per-frame hot path as sm_100a kernels:
+//   k_bin<false/true>   triangle setup + tile binning (count pass / emit pass)
+//   k_scan              exclusive scan of the per-tile counts
+//   k_raster            warp-per-tile fine raster: per-tile pair lists staged through TMA bulk copies
+//                       (cp.async.bulk + mbarrier) into shared memory, warp-ballot edge tests,
+//                       per-lane z-compare, 64-bit visibility keys
+//   k_shadow            depth-only pass of the shadow casters (atomicMin on d24)
+//   k_shade             vertex + fragment stage of the visible fragment of every pixel, fused tone
+//                       map, all render targets stored with 128-bit coalesced writes
+// Replaces steps 6-10 and 14 of sl::RenderPass::render (reference: src/render_pass.cpp:407-622,696-710).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "k_frag.cuh"
+#include "kernels.h"
+#include "slb_dev.h"
+
+using namespace slbk;
+
+// ---------------------------------------------------------------------------------------------
+// setup + binning
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t find_draw(const uint32_t* __restrict__ chunk_base, int n_draws, uint32_t chunk) {
+    int lo = 0, hi = n_draws - 1;   // last draw with chunk_base <= chunk
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(chunk_base + mid) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    return (uint32_t)lo;
+}
+
+// can any pixel centre of tile (tx,ty) be covered? (conservative: tests the most-inside corner per edge)
+__device__ __forceinline__ bool tile_may_overlap(const SubTri& t, int tx, int ty, int W, int H) {
+    int x0 = tx * SLB_TILE, y0 = ty * SLB_TILE;
+    int x1 = min(x0 + SLB_TILE - 1, W - 1), y1 = min(y0 + SLB_TILE - 1, H - 1);
+    // d(s*w0)/dpx = -s*(cy-by), d(s*w0)/dpy = s*(cx-bx), etc.
+    int cx, cy;
+    cx = ((long long)t.s * -(t.cy - t.by) > 0) ? x1 : x0; cy = ((long long)t.s * (t.cx - t.bx) > 0) ? y1 : y0;
+    if (t.s * edge_fn(t.bx, t.by, t.cx, t.cy, cx * 256 + 128, cy * 256 + 128) + t.bias0 < 0) return false;
+    cx = ((long long)t.s * -(t.ay - t.cy) > 0) ? x1 : x0; cy = ((long long)t.s * (t.ax - t.cx) > 0) ? y1 : y0;
+    if (t.s * edge_fn(t.cx, t.cy, t.ax, t.ay, cx * 256 + 128, cy * 256 + 128) + t.bias1 < 0) return false;
+    cx = ((long long)t.s * -(t.by - t.ay) > 0) ? x1 : x0; cy = ((long long)t.s * (t.bx - t.ax) > 0) ? y1 : y0;
+    if (t.s * edge_fn(t.ax, t.ay, t.bx, t.by, cx * 256 + 128, cy * 256 + 128) + t.bias2 < 0) return false;
+    return true;
+}
+
+struct BigEntry { PairRec rec; int tx0, ty0, ntx, nty; };
+#define SLB_BIG_QUEUE 48
+#define SLB_BIG_TILES 24   // sub-triangles touching more tiles than this are binned by the whole block
+
+template <bool EMIT>
+__device__ __forceinline__ void bin_pair(uint32_t tile, const PairRec& rec, uint32_t* __restrict__ tile_count,
+                                         const uint32_t* __restrict__ tile_off, PairRec* __restrict__ pairs, uint32_t capacity) {
+    if (EMIT) {
+        uint32_t slot = atomicSub(tile_count + tile, 1u) - 1u;   // the count pass left the tile's total here
+        uint32_t at = __ldg(tile_off + tile) + slot;
+        if (at < capacity) pairs[at] = rec;
+    } else {
+        atomicAdd(tile_count + tile, 1u);
+    }
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_bin(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws,
+                                                         const uint32_t* __restrict__ chunk_base, int n_draws,
+                                                         uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_off,
+                                                         PairRec* __restrict__ pairs, uint32_t capacity) {
+    __shared__ float s_mvp[16];
+    __shared__ uint32_t s_draw;
+    __shared__ BigEntry s_big[SLB_BIG_QUEUE];
+    __shared__ int s_nbig;
+    if (threadIdx.x == 0) { s_draw = find_draw(chunk_base, n_draws, blockIdx.x); s_nbig = 0; }
+    __syncthreads();
+    const uint32_t di = s_draw;
+    const DDraw& d = draws[di];
+    if (threadIdx.x < 16) s_mvp[threadIdx.x] = d.mvp[threadIdx.x];
+    __syncthreads();
+    const DFrame& f = frames[d.frame];
+    const int W = f.W, H = f.H, tiles_x = f.tiles_x;
+    const uint32_t tile_base = f.tile_base;
+    const uint32_t tri = (blockIdx.x - __ldg(chunk_base + di)) * SLB_SETUP_CHUNK + threadIdx.x;
+    if (tri < d.n_tris) {
+        const uint32_t* ip = d.idx + 3 * (size_t)tri;
+        uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+        float4 p0 = __ldg(d.pos4 + i0), p1 = __ldg(d.pos4 + i1), p2 = __ldg(d.pos4 + i2);
+        PrimSetup ps;
+        if (setup_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), W, H, ps)) {
+            for (int k = 1; k + 1 < ps.n; ++k) {
+                SubTri st;
+                if (!make_subtri(ps, k, st)) continue;
+                int px0, py0, px1, py1;
+                if (!subtri_pixel_bbox(st, W, H, px0, py0, px1, py1)) continue;
+                int tx0 = px0 / SLB_TILE, tx1 = px1 / SLB_TILE, ty0 = py0 / SLB_TILE, ty1 = py1 / SLB_TILE;
+                int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
+                PairRec rec;
+                rec.ax = st.ax; rec.ay = st.ay; rec.bx = st.bx; rec.by = st.by; rec.cx = st.cx; rec.cy = st.cy;
+                rec.az = st.az; rec.bz = st.bz; rec.cz = st.cz;
+                rec.seq = d.prim_base + tri;
+                rec.k_flags = (uint32_t)k | ((d.flags & DRAW_FRAG_TEST) ? 0x100u : 0u);
+                rec.draw = di;
+                if (ntx * nty == 1) {
+                    bin_pair<EMIT>(tile_base + ty0 * tiles_x + tx0, rec, tile_count, tile_off, pairs, capacity);
+                } else if (ntx * nty <= SLB_BIG_TILES) {
+                    const bool test = ntx * nty > 2;
+                    for (int ty = ty0; ty <= ty1; ++ty)
+                        for (int tx = tx0; tx <= tx1; ++tx)
+                            if (!test || tile_may_overlap(st, tx, ty, W, H))
+                                bin_pair<EMIT>(tile_base + ty * tiles_x + tx, rec, tile_count, tile_off, pairs, capacity);
+                } else {
+                    int q = atomicAdd(&s_nbig, 1);
+                    if (q < SLB_BIG_QUEUE) {
+                        s_big[q].rec = rec; s_big[q].tx0 = tx0; s_big[q].ty0 = ty0; s_big[q].ntx = ntx; s_big[q].nty = nty;
+                    } else {   // queue full: this thread walks the tiles itself
+                        for (int ty = ty0; ty <= ty1; ++ty)
+                            for (int tx = tx0; tx <= tx1; ++tx)
+                                if (tile_may_overlap(st, tx, ty, W, H))
+                                    bin_pair<EMIT>(tile_base + ty * tiles_x + tx, rec, tile_count, tile_off, pairs, capacity);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int nbig = min(s_nbig, SLB_BIG_QUEUE);
+    for (int q = 0; q < nbig; ++q) {   // large sub-triangles: all threads of the block share the tile walk
+        const BigEntry& e = s_big[q];
+        SubTri st;
+        make_subtri(e.rec.ax, e.rec.ay, e.rec.bx, e.rec.by, e.rec.cx, e.rec.cy, e.rec.az, e.rec.bz, e.rec.cz, st);
+        const int n = e.ntx * e.nty;
+        for (int i = threadIdx.x; i < n; i += SLB_SETUP_CHUNK) {
+            int tx = e.tx0 + i % e.ntx, ty = e.ty0 + i / e.ntx;
+            if (tile_may_overlap(st, tx, ty, W, H))
+                bin_pair<EMIT>(tile_base + ty * tiles_x + tx, e.rec, tile_count, tile_off, pairs, capacity);
+        }
+    }
+}
+
+// exclusive scan of n counts into off[0..n] (off[n] = total); one block
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ count, uint32_t* __restrict__ off, uint32_t n) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t per = (n + 1023u) / 1024u;
+    const uint32_t beg = min(n, threadIdx.x * per), end = min(n, beg + per);
+    uint32_t sum = 0;
+    for (uint32_t i = beg; i < end; ++i) sum += count[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int ofs = 1; ofs < 1024; ofs <<= 1) {   // Hillis-Steele inclusive scan of the partials
+        uint32_t v = (threadIdx.x >= ofs) ? s_part[threadIdx.x - ofs] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[threadIdx.x] - sum;
+    for (uint32_t i = beg; i < end; ++i) { off[i] = run; run += count[i]; }
+    if (threadIdx.x == 1023) off[n] = s_part[1023];
+}
+
+// ---------------------------------------------------------------------------------------------
+// fine raster
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// per-tile derived triangle data, written lane-parallel, read as shared-memory broadcasts
+struct __align__(16) TriDerived {
+    long long e0, e1;                 // s*w_i + bias_i at the tile's first pixel centre
+    long long e2; int dx0, dy0;       // per-pixel steps / 256
+    int dx1, dy1, dx2, dy2;
+    float az, dzb, dzc, inv2A;
+    int s_bias; uint32_t seq, k_flags, draw;
+};
+static_assert(sizeof(TriDerived) == 80, "TriDerived must be 80 bytes");
+
+#define SLB_RASTER_WARPS 8
+#define SLB_RASTER_CHUNK 32
+
+// fragment-stage discards that decide coverage: depth peel + alpha test (render_shader.frag:229-246)
+__device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint32_t tri, int k, int px, int py) {
+    const uint32_t* ip = d.idx + 3 * (size_t)tri;
+    uint32_t i[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
+    float4 p0 = __ldg(d.pos4 + i[0]), p1 = __ldg(d.pos4 + i[1]), p2 = __ldg(d.pos4 + i[2]);
+    PrimSetup ps;
+    if (!setup_prim(d.mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), f.W, f.H, ps))
+        return true;
+    SubTri st;
+    if (k + 1 >= ps.n || !make_subtri(ps, k, st)) return true;
+    VSOut vs[3]; uint32_t vid;
+    for (int j = 0; j < 3; ++j) vertex_stage(f, d, i[j], vs[j], vid);
+    FragIn in; float bary[3];
+    interpolate(st, ps, k, vs, px, py, d.tex[0] != nullptr, in, bary);
+    if (f.peel && in.objc.w - 0.00001f <= f.peel[((size_t)py * f.W + px) * 4 + 3]) return true;
+    if ((d.flags & DRAW_FRAG_TEST) && base_color(d, in).w < 0.5f) return true;
+    return false;
+}
+
+__global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws,
+                                                                   const uint32_t* __restrict__ tile_off,
+                                                                   const PairRec* __restrict__ pairs, uint32_t n_tiles,
+                                                                   uint32_t tiles_per_frame) {
+    __shared__ __align__(128) PairRec s_rec[SLB_RASTER_WARPS][2][SLB_RASTER_CHUNK];
+    __shared__ __align__(16) TriDerived s_der[SLB_RASTER_WARPS][SLB_RASTER_CHUNK];
+    __shared__ __align__(8) uint64_t s_bar[SLB_RASTER_WARPS][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * SLB_RASTER_WARPS + warp;
+    if (t >= n_tiles) return;
+    const uint32_t fi = t / tiles_per_frame, tl = t - fi * tiles_per_frame;
+    const DFrame& f = frames[fi];
+    const int W = f.W, H = f.H;
+    const int tx = tl % f.tiles_x, ty = tl / f.tiles_x;
+    const int lx = lane & 7, ly = lane >> 3;
+    const int px = tx * SLB_TILE + lx, py0 = ty * SLB_TILE + ly, py1 = py0 + 4;
+    const uint32_t beg = __ldg(tile_off + t), end = __ldg(tile_off + t + 1);
+    const uint32_t n = end - beg;
+    unsigned long long key0 = SLB_KEY_EMPTY, key1 = SLB_KEY_EMPTY;
+
+    if (n > 0) {
+        uint64_t* bar = s_bar[warp];
+        if (lane == 0) {
+            mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+        const uint32_t nchunks = (n + SLB_RASTER_CHUNK - 1) / SLB_RASTER_CHUNK;
+        if (lane == 0) {
+            uint32_t cnt = min(n, (uint32_t)SLB_RASTER_CHUNK);
+            mbar_expect_tx(&bar[0], cnt * (uint32_t)sizeof(PairRec));
+            bulk_g2s(&s_rec[warp][0][0], pairs + beg, cnt * (uint32_t)sizeof(PairRec), &bar[0]);
+        }
+        const int ox = (tx * SLB_TILE) * 256 + 128, oy = (ty * SLB_TILE) * 256 + 128;   // tile's first pixel centre
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            const int b = c & 1;
+            if (lane == 0 && c + 1 < nchunks) {   // prefetch the next chunk into the other buffer
+                uint32_t cnt = min(n - (c + 1) * SLB_RASTER_CHUNK, (uint32_t)SLB_RASTER_CHUNK);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bar[b ^ 1], cnt * (uint32_t)sizeof(PairRec));
+                bulk_g2s(&s_rec[warp][b ^ 1][0], pairs + beg + (size_t)(c + 1) * SLB_RASTER_CHUNK, cnt * (uint32_t)sizeof(PairRec),
+                         &bar[b ^ 1]);
+            }
+            mbar_wait(&bar[b], (c >> 1) & 1);
+            const int cnt = (int)min(n - c * SLB_RASTER_CHUNK, (uint32_t)SLB_RASTER_CHUNK);
+            // phase A: one triangle per lane -> edge functions at the tile origin
+            if (lane < cnt) {
+                const PairRec r = s_rec[warp][b][lane];
+                SubTri st;
+                make_subtri(r.ax, r.ay, r.bx, r.by, r.cx, r.cy, r.az, r.bz, r.cz, st);
+                TriDerived dv;
+                dv.e0 = st.s * edge_fn(st.bx, st.by, st.cx, st.cy, ox, oy) + st.bias0;
+                dv.e1 = st.s * edge_fn(st.cx, st.cy, st.ax, st.ay, ox, oy) + st.bias1;
+                dv.e2 = st.s * edge_fn(st.ax, st.ay, st.bx, st.by, ox, oy) + st.bias2;
+                dv.dx0 = -st.s * (st.cy - st.by); dv.dy0 = st.s * (st.cx - st.bx);
+                dv.dx1 = -st.s * (st.ay - st.cy); dv.dy1 = st.s * (st.ax - st.cx);
+                dv.dx2 = -st.s * (st.by - st.ay); dv.dy2 = st.s * (st.bx - st.ax);
+                dv.az = st.az; dv.dzb = __fsub_rn(st.bz, st.az); dv.dzc = __fsub_rn(st.cz, st.az); dv.inv2A = st.inv2A;
+                dv.s_bias = (st.s < 0 ? 1 : 0) | (st.bias1 ? 2 : 0) | (st.bias2 ? 4 : 0);
+                dv.seq = r.seq; dv.k_flags = r.k_flags; dv.draw = r.draw;
+                s_der[warp][lane] = dv;
+            }
+            __syncwarp();
+            // phase B: every lane tests its two pixels against each triangle of the chunk
+            for (int j = 0; j < cnt; ++j) {
+                const TriDerived& dv = s_der[warp][j];
+                long long e0 = dv.e0 + (long long)(dv.dx0 * lx + dv.dy0 * ly) * 256;
+                long long e1 = dv.e1 + (long long)(dv.dx1 * lx + dv.dy1 * ly) * 256;
+                long long e2 = dv.e2 + (long long)(dv.dx2 * lx + dv.dy2 * ly) * 256;
+                long long g0 = e0 + (long long)dv.dy0 * 1024, g1 = e1 + (long long)dv.dy1 * 1024, g2 = e2 + (long long)dv.dy2 * 1024;
+                const bool in0 = (e0 | e1 | e2) >= 0, in1 = (g0 | g1 | g2) >= 0;
+                if (__ballot_sync(0xffffffffu, in0 || in1) == 0) continue;
+                if (in0 || in1) {
+                    const int sb = dv.s_bias;
+                    const long long b1 = (sb & 2) ? -1 : 0, b2 = (sb & 4) ? -1 : 0;
+                    const bool neg = sb & 1;
+                    const unsigned long long lowkey = ((unsigned long long)dv.seq << 8) | (dv.k_flags & 0xffu);
+                    const float dzb = dv.dzb, dzc = dv.dzc, az = dv.az, inv2A = dv.inv2A;
+                    if (in0 && px < W && py0 < H) {
+                        long long w1 = e1 - b1, w2 = e2 - b2;
+                        if (neg) { w1 = -w1; w2 = -w2; }
+                        float q1 = __fmul_rn(__ll2float_rn(w1), inv2A), q2 = __fmul_rn(__ll2float_rn(w2), inv2A);
+                        float z = __fmaf_rn(q2, dzc, __fmaf_rn(q1, dzb, az));
+                        z = fminf(fmaxf(z, 0.0f), 1.0f);
+                        unsigned long long key = ((unsigned long long)__float2uint_rn(__fmul_rn(z, 16777215.0f)) << 40) | lowkey;
+                        if (key < key0) {
+                            if (!(dv.k_flags & 0x100u) ||
+                                !frag_discard(f, draws[dv.draw], dv.seq - draws[dv.draw].prim_base, dv.k_flags & 0xff, px, py0))
+                                key0 = key;
+                        }
+                    }
+                    if (in1 && px < W && py1 < H) {
+                        long long w1 = g1 - b1, w2 = g2 - b2;
+                        if (neg) { w1 = -w1; w2 = -w2; }
+                        float q1 = __fmul_rn(__ll2float_rn(w1), inv2A), q2 = __fmul_rn(__ll2float_rn(w2), inv2A);
+                        float z = __fmaf_rn(q2, dzc, __fmaf_rn(q1, dzb, az));
+                        z = fminf(fmaxf(z, 0.0f), 1.0f);
+                        unsigned long long key = ((unsigned long long)__float2uint_rn(__fmul_rn(z, 16777215.0f)) << 40) | lowkey;
+                        if (key < key1) {
+                            if (!(dv.k_flags & 0x100u) ||
+                                !frag_discard(f, draws[dv.draw], dv.seq - draws[dv.draw].prim_base, dv.k_flags & 0xff, px, py1))
+                                key1 = key;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (px < W) {
+        if (py0 < H) f.keys[(size_t)py0 * W + px] = key0;
+        if (py1 < H) f.keys[(size_t)py1 * W + px] = key1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shadow pass: depth only, front faces culled (render_pass.cpp:426-460, shadow_shader.vert:10-13)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_shadow(const DShadowDraw* __restrict__ sdraws,
+                                                            const uint32_t* __restrict__ chunk_base, int n_draws) {
+    __shared__ float s_mvp[16];
+    __shared__ uint32_t s_draw;
+    if (threadIdx.x == 0) s_draw = find_draw(chunk_base, n_draws, blockIdx.x);
+    __syncthreads();
+    const DShadowDraw& d = sdraws[s_draw];
+    if (threadIdx.x < 16) s_mvp[threadIdx.x] = d.mvp[threadIdx.x];
+    __syncthreads();
+    const uint32_t tri = (blockIdx.x - __ldg(chunk_base + s_draw)) * SLB_SETUP_CHUNK + threadIdx.x;
+    if (tri >= d.n_tris) return;
+    const int N = SLB_SHADOW_RES;
+    const uint32_t* ip = d.idx + 3 * (size_t)tri;
+    uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+    float4 p0 = __ldg(d.pos4 + i0), p1 = __ldg(d.pos4 + i1), p2 = __ldg(d.pos4 + i2);
+    PrimSetup ps;
+    if (!setup_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), N, N, ps)) return;
+    for (int k = 1; k + 1 < ps.n; ++k) {
+        SubTri st;
+        if (!make_subtri(ps, k, st)) continue;
+        if (st.twoA < 0) continue;   // cull FRONT faces
+        int px0, py0, px1, py1;
+        if (!subtri_pixel_bbox(st, N, N, px0, py0, px1, py1)) continue;
+        for (int py = py0; py <= py1; ++py)
+            for (int px = px0; px <= px1; ++px) {
+                long long w0, w1, w2; subtri_weights(st, px, py, w0, w1, w2);
+                if (!subtri_covers(st, w0, w1, w2)) continue;
+                atomicMin(d.map + (size_t)py * N + px, subtri_depth24(st, w1, w2));
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shade + multi-render-target store
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t find_draw_by_prim(const DDraw* __restrict__ draws, uint32_t lo, uint32_t hi, uint32_t seq) {
+    --hi;   // last draw in [lo, hi] with prim_base <= seq
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (draws[mid].prim_base <= seq) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) k_shade(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws) {
+    const DFrame& f = frames[blockIdx.z];
+    const int W = f.W, H = f.H;
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (px >= W || py >= H) return;
+    const size_t p = (size_t)py * W + px;
+    const unsigned long long key = f.keys[p];
+
+    float4 hdr = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 coord = make_float4(SLB_INVALID_COORD, SLB_INVALID_COORD, SLB_INVALID_COORD, SLB_INVALID_COORD);
+    float4 camc = coord;
+    float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bary4 = make_float4(0.f, 0.f, 0.f, 1.0f);
+    uint4 vidx = make_uint4(0u, 0u, 0u, 0u);
+    unsigned short cls = 0, inst = 0;
+
+    if (key != SLB_KEY_EMPTY) {
+        const uint32_t seq = (uint32_t)(key >> 8);
+        const int k = (int)(key & 0xffu);
+        const DDraw& d = draws[find_draw_by_prim(draws, f.draw_begin, f.draw_end, seq)];
+        const uint32_t tri = seq - d.prim_base;
+        const uint32_t* ip = d.idx + 3 * (size_t)tri;
+        uint32_t i[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
+        float4 p0 = __ldg(d.pos4 + i[0]), p1 = __ldg(d.pos4 + i[1]), p2 = __ldg(d.pos4 + i[2]);
+        PrimSetup ps;
+        SubTri st;
+        if (setup_prim(d.mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), W, H, ps) &&
+            k + 1 < ps.n && make_subtri(ps, k, st)) {
+            VSOut vs[3]; uint32_t vid[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) vertex_stage(f, d, i[j], vs[j], vid[j]);
+            FragIn in; float bary[3];
+            interpolate(st, ps, k, vs, px, py, draw_has_textures(d), in, bary);
+            FragOut o;
+            fragment_stage(f, d, in, o);
+            hdr = o.color; coord = o.objc; camc = o.camc; nrm = o.normal;
+            bary4 = make_float4(bary[0], bary[1], bary[2], 1.0f);
+            vidx = make_uint4(vid[0], vid[1], vid[2], 0u);
+            cls = (unsigned short)d.class_index; inst = (unsigned short)d.instance_index;
+        }
+    }
+    if (f.fused_tonemap) {
+        if (f.out[SLB_TARGET_RGB]) reinterpret_cast<uchar4*>(f.out[SLB_TARGET_RGB])[p] = tone_map(hdr, f.manual_exposure, nullptr);
+    } else {
+        f.hdr[p] = hdr;
+    }
+    if (f.out[SLB_TARGET_COORD]) reinterpret_cast<float4*>(f.out[SLB_TARGET_COORD])[p] = coord;
+    if (f.out[SLB_TARGET_CLASS]) reinterpret_cast<unsigned short*>(f.out[SLB_TARGET_CLASS])[p] = cls;
+    if (f.out[SLB_TARGET_INSTANCE]) reinterpret_cast<unsigned short*>(f.out[SLB_TARGET_INSTANCE])[p] = inst;
+    if (f.scratch_normal) f.scratch_normal[p] = nrm;   // == out[NORMAL] when that target is requested
+    if (f.out[SLB_TARGET_VERTEX_INDEX]) reinterpret_cast<uint4*>(f.out[SLB_TARGET_VERTEX_INDEX])[p] = vidx;
+    if (f.out[SLB_TARGET_BARY]) reinterpret_cast<float4*>(f.out[SLB_TARGET_BARY])[p] = bary4;
+    if (f.scratch_cam) f.scratch_cam[p] = camc;         // == out[CAM_COORD] when that target is requested
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+namespace slbk {
+
+void launch_bin(bool emit, const DFrame* frames, const DDraw* draws, const uint32_t* chunk_base, int n_draws, uint32_t n_chunks,
+                uint32_t* tile_count, const uint32_t* tile_off, PairRec* pairs, uint32_t capacity, cudaStream_t s) {
+    if (n_chunks == 0) return;
+    if (emit) k_bin<true><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(frames, draws, chunk_base, n_draws, tile_count, tile_off, pairs, capacity);
+    else k_bin<false><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(frames, draws, chunk_base, n_draws, tile_count, tile_off, pairs, capacity);
+}
+void launch_scan(const uint32_t* count, uint32_t* off, uint32_t n, cudaStream_t s) { k_scan<<<1, 1024, 0, s>>>(count, off, n); }
+void launch_raster(const DFrame* frames, const DDraw* draws, const uint32_t* tile_off, const PairRec* pairs, uint32_t n_tiles,
+                   uint32_t tiles_per_frame, cudaStream_t s) {
+    if (n_tiles == 0) return;
+    k_raster<<<(n_tiles + SLB_RASTER_WARPS - 1) / SLB_RASTER_WARPS, SLB_RASTER_WARPS * 32, 0, s>>>(frames, draws, tile_off, pairs, n_tiles,
+                                                                                                  tiles_per_frame);
+}
+void launch_shadow(const DShadowDraw* sdraws, const uint32_t* chunk_base, int n_draws, uint32_t n_chunks, cudaStream_t s) {
+    if (n_chunks == 0) return;
+    k_shadow<<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(sdraws, chunk_base, n_draws);
+}
+void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, cudaStream_t s) {
+    dim3 grid((W + 31) / 32, (H + 7) / 8, n_frames);
+    k_shade<<<grid, 256, 0, s>>>(frames, draws);
+}
+
+}  // namespace slbk

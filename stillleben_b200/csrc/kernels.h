@@ -1,0 +1,41 @@
+// kernels.h — host-callable launchers of the CUDA kernels (one per translation unit below).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "slb_dev.h"
+
+namespace slbk {
+
+// k_render.cu
+void launch_bin(bool emit, const DFrame* frames, const DDraw* draws, const uint32_t* chunk_base, int n_draws, uint32_t n_chunks,
+                uint32_t* tile_count, const uint32_t* tile_off, PairRec* pairs, uint32_t capacity, cudaStream_t s);
+void launch_scan(const uint32_t* count, uint32_t* off, uint32_t n, cudaStream_t s);
+void launch_raster(const DFrame* frames, const DDraw* draws, const uint32_t* tile_off, const PairRec* pairs, uint32_t n_tiles,
+                   uint32_t tiles_per_frame, cudaStream_t s);
+void launch_shadow(const DShadowDraw* sdraws, const uint32_t* chunk_base, int n_draws, uint32_t n_chunks, cudaStream_t s);
+void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, cudaStream_t s);
+
+// k_post.cu
+void upload_ssao_tables(const float* noise16x3, const float* kernel64x3);
+void launch_background(const DFrame* frames, int n_frames, int W, int H, cudaStream_t s);
+void launch_downsample(const float4* src, int sw, int sh, float4* dst, int n_frames, size_t src_stride, size_t dst_stride, cudaStream_t s);
+void launch_ssao(const DFrame* frames, int n_frames, int W, int H, cudaStream_t s);
+void launch_ssao_apply_tonemap(const DFrame* frames, int n_frames, int W, int H, cudaStream_t s);
+
+// k_assets.cu
+void launch_repack_vertices(const uint8_t* verts68, uint32_t n, float4* pos4, float4* attr, cudaStream_t s);
+void launch_expand_rgba(const uint8_t* src, int channels, uint8_t* dst, size_t n_texels, cudaStream_t s);
+void launch_mip_level(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh, cudaStream_t s);
+void launch_cube_mip(const float4* src, int ssize, float4* dst, cudaStream_t s);
+void launch_equirect_to_cube(const float* equirect, int ew, int eh, float4* cube, int size, cudaStream_t s);
+void launch_irradiance(const DLightMap* lm, float4* out, int size, float lod, cudaStream_t s);
+void launch_prefilter(const DLightMap* lm, float4* out, int size, float roughness, int n_samples, float env_resolution, cudaStream_t s);
+void launch_brdf_lut(float4* out, int size, int n_samples, cudaStream_t s);
+
+// k_diff.cu
+void launch_sobel_valid_mask(const int16_t* inst, const float* depth, uint8_t* valid, int H, int W, cudaStream_t s);
+void launch_dilate_object_mask(const uint8_t* mask, const uint8_t* valid, const float* coords, int coord_stride, uint8_t* mask_out,
+                               float* coords_out, int H, int W, cudaStream_t s);
+
+}  // namespace slbk

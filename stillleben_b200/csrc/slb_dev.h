@@ -1,0 +1,109 @@
+// slb_dev.h — plain-old-data records shared by the host marshalling code (slb_host.cu) and the
+// kernels. Everything here lives in HBM; layouts are chosen for the kernels, not for the caller:
+//   * vertex stream is split at upload into pos4[] (xyz + one-based vertex id, one 128-bit load in
+//     triangle setup) and attr[] (uv, normal, tangent: three 128-bit loads in the shade kernel);
+//     the reference's 68-byte interleaved record (src/mesh_tools/consolidate.cpp:53-61) is only the
+//     upload format,
+//   * textures are RGBA8 with the whole mip chain in one allocation,
+//   * per-batch scene state is two flat arrays (DFrame[], DDraw[]) uploaded with one copy.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/slb.h"
+
+#define SLB_TILE 8                 // fine-raster tile: 8x8 pixels, one warp, two pixels per lane
+#define SLB_SETUP_CHUNK 256        // triangles per block in the setup/bin kernels
+#define SLB_MAX_LEVELS 16
+
+struct DTexture {
+    const uint8_t* px;             // RGBA8, level l starts at texel level_off[l]
+    int32_t w, h, n_levels;
+    int32_t wrap_s, wrap_t, min_filter, mag_filter;
+    int32_t kind, has_alpha;
+    uint32_t level_off[SLB_MAX_LEVELS];
+};
+
+struct DCubeLevel { const float4* px; int32_t size; int32_t pad; };
+struct DLightMap {
+    DCubeLevel env[12]; int32_t n_env;
+    DCubeLevel irr;
+    DCubeLevel pre[5];
+    const float4* lut; int32_t lut_size;
+    int32_t n_lights;
+    float light_directions[SLB_NUM_LIGHTS][3];
+    float light_colors[SLB_NUM_LIGHTS][3];
+};
+
+struct DDraw {
+    const float4* pos4;            // xyz, w = __uint_as_float(one-based vertex id)
+    const float4* attr;            // 3 x float4 per vertex: (u,v,nx,ny) (nz,tx,ty,tz) (tw,0,0,0)
+    const uint32_t* idx;           // already offset to the sub-mesh's first index
+    uint32_t n_tris;
+    uint32_t prim_base;            // sequence number of triangle 0 within the frame (submission order)
+    uint32_t chunk_base;           // first setup chunk of this draw within the batch
+    uint32_t frame;                // frame index within the batch
+    float mvp[16];
+    float meshToObject[16], objectToWorld[16];
+    float normalToWorld[9];
+    float base_color[4], emissive[4];
+    float metallic, roughness;
+    const DTexture* tex[5];        // base, normal, metallic-roughness, emissive, occlusion
+    const DTexture* sticker;
+    float stickerProj[16];
+    float stickerRange[4];
+    uint32_t class_index, instance_index;
+    uint32_t flags;                // DRAW_*
+    uint32_t pad;
+};
+enum { DRAW_FRAG_TEST = 1u };      // coverage depends on the fragment stage (alpha test / depth peel)
+
+struct DShadowDraw {
+    const float4* pos4;
+    const uint32_t* idx;
+    uint32_t n_tris;
+    uint32_t chunk_base;
+    uint32_t* map;                 // SLB_SHADOW_RES^2 d24 values
+    uint32_t pad;
+    float mvp[16];
+};
+
+struct DFrame {
+    int32_t W, H, tiles_x, tiles_y;
+    uint32_t tile_base;            // first tile of this frame in the batch-wide tile arrays
+    uint32_t draw_begin, draw_end;
+    uint32_t n_prims;
+    float P[16], V[16], Pinv[16];
+    float camPos[3];
+    float manual_exposure;
+    float lightDir[SLB_NUM_LIGHTS][3], lightCol[SLB_NUM_LIGHTS][3];
+    int32_t lightActive[SLB_NUM_LIGHTS];
+    int32_t ssao;
+    float ambient[3];
+    int32_t fused_tonemap;         // 1: shade kernel tone-maps and stores rgb itself (no post passes needed)
+    float shadowMat[SLB_NUM_LIGHTS][16];
+    const uint32_t* shadowMap[SLB_NUM_LIGHTS];
+    const DLightMap* lm;
+    const float* peel;             // previous layer's coord target (HxWx4) or null
+    const DTexture* bg_image;
+    uint64_t* keys;                // H*W visibility keys
+    float4* hdr;                   // H*W pre-tone-map colour (post-pass path only)
+    float4* scratch_normal;        // used by SSAO when the normal / cam-coord targets are not requested
+    float4* scratch_cam;
+    float* ao;
+    float* avg;                    // 4 floats: 1x1 mip level for auto exposure
+    void* out[SLB_NUM_TARGETS];    // this frame's slice of each requested target (null = not requested)
+};
+
+// One (tile, sub-triangle) pair of the binner: the snapped sub-triangle itself, 48 bytes so that a
+// tile's list is a 16-byte-aligned contiguous run that cp.async.bulk can stage into shared memory.
+struct __align__(16) PairRec {
+    int32_t ax, ay, bx, by, cx, cy;   // 24.8 fixed-point window coordinates
+    float az, bz, cz;                 // window z in [0,1]
+    uint32_t seq;                     // primitive sequence number within the frame
+    uint32_t k_flags;                 // bits 0..7: fan index k of the sub-triangle; bit 8: needs fragment test
+    uint32_t draw;                    // index into DDraw[] (fragment-test path only)
+};
+static_assert(sizeof(PairRec) == 48, "PairRec must be 48 bytes");
+
+// visibility key: depth24 << 40 | seq << 8 | k   (min == GL_LESS + first draw wins on ties)
+#define SLB_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull

@@ -1,0 +1,1108 @@
+// slb_host.cu — the C ABI of include/slb.h: context, asset upload, result buffers and the host side
+// of the hot path (marshalling a batch of scene descriptors into DFrame/DDraw arrays and queueing
+// the kernels). Replaces the host part of sl::RenderPass::render (reference: src/render_pass.cpp:303-796)
+// and of Mesh::loadVisual / LightMap::load / CUDATexture (src/mesh.cpp:624-745, src/light_map.cpp:266-611,
+// src/cuda_interop.cpp:83-208). No exception crosses the boundary; every entry point returns a status.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/slb.h"
+#include "hostmath.h"
+#include "kernels.h"
+#include "slb_dev.h"
+
+using namespace slbk;
+
+// ---------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes, bool zero = false) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        if (zero) e = cudaMemset(p, 0, want);
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct slb_texture {
+    DTexture h; DTexture* d = nullptr; uint8_t* px = nullptr;
+};
+struct slb_mesh {
+    float4* pos4 = nullptr; float4* attr = nullptr; uint32_t* idx = nullptr;
+    uint32_t n_vertices = 0, n_indices = 0;
+    std::vector<slb_submesh> submeshes;
+    std::vector<slb_material> materials;
+    std::vector<slb_texture*> textures;
+    float bbox_min[3], bbox_max[3];
+};
+struct slb_lightmap {
+    DLightMap h; DLightMap* d = nullptr;
+    std::vector<void*> allocs;
+    int env_size = 0, irr_size = 0, pre_size = 0, lut_size = 0;
+};
+struct slb_result {
+    int32_t W = 0, H = 0, n_frames = 0; uint32_t mask = 0;
+    void* ptrs[SLB_NUM_TARGETS]; bool owned[SLB_NUM_TARGETS];
+    float4* hdr = nullptr;   // [n_frames][H][W], only with SLB_OPT_KEEP_HDR
+};
+static const size_t kTargetBpp[SLB_NUM_TARGETS] = {4, 16, 2, 2, 16, 16, 16, 16};
+
+enum { ST_SHADOW = 0, ST_COUNT, ST_SCAN, ST_EMIT, ST_RASTER, ST_SHADE, ST_SSAO, ST_POST, ST_N };
+
+struct slb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::string err;
+    bool time_kernels = false, keep_hdr = false;
+    int max_subbatch = 16;
+    slb_stats stats;
+    // assets owned by the context
+    slb_mesh* plane = nullptr;
+    // per-batch device arrays
+    DevBuf frames_d, draws_d, chunk_base_d, sdraws_d, schunk_base_d;
+    DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, ao, avg, mip_a, mip_b, shadow_maps;
+    // pinned staging
+    void* staging = nullptr; size_t staging_cap = 0;
+    uint32_t* total_pinned = nullptr;
+    // timing
+    struct Ev { int stage; cudaEvent_t a, b; };
+    std::vector<Ev> events;
+    std::vector<cudaEvent_t> event_pool;
+    // host-render slots
+    slb_result* slot[2] = {nullptr, nullptr};
+    cudaEvent_t slot_rendered[2] = {nullptr, nullptr}, slot_copied[2] = {nullptr, nullptr};
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(slb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? SLB_ERR_OUT_OF_MEMORY : SLB_ERR_CUDA,        \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                                \
+    } while (0)
+
+static int ensure_staging(slb_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->staging_cap) return SLB_OK;
+    if (ctx->staging) cudaFreeHost(ctx->staging);
+    ctx->staging = nullptr; ctx->staging_cap = 0;
+    size_t want = bytes + bytes / 2 + 4096;
+    CU(cudaHostAlloc(&ctx->staging, want, cudaHostAllocDefault));
+    ctx->staging_cap = want;
+    return SLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+static void ssao_tables(float* noise, float* kernel) {   // reference: src/shaders/ssao_shader.cpp:72-112
+    std::mt19937 random{0xdeadbeef};
+    std::uniform_real_distribution<float> rf(0.0f, 1.0f);
+    for (int i = 0; i < 16; ++i) { float a = 2.0f * rf(random) - 1.0f; float b = 2.0f * rf(random) - 1.0f; noise[i * 3] = a; noise[i * 3 + 1] = b; noise[i * 3 + 2] = 0.0f; }
+    for (int i = 0; i < 64; ++i) {
+        float a = 2.0f * rf(random) - 1.0f; float b = 2.0f * rf(random) - 1.0f; float c = rf(random);
+        hm::Vec3 s = hm::normalize(hm::v3(a, b, c)) * rf(random);
+        float scale = (float)i / 64.0f;
+        float t = scale * scale;
+        s = s * (0.1f * (1.0f - t) + 1.0f * t);
+        kernel[i * 3] = s.x; kernel[i * 3 + 1] = s.y; kernel[i * 3 + 2] = s.z;
+    }
+}
+
+extern "C" int slb_abi_version(void) { return SLB_ABI_VERSION; }
+
+extern "C" const char* slb_last_error(const slb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int slb_ctx_device(const slb_ctx* ctx) { return ctx ? ctx->device : -1; }
+
+extern "C" int slb_ctx_create(int device, slb_ctx** out) {
+    slb_ctx* ctx = nullptr;
+    if (!out) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(ctx, SLB_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_ctx_create: device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(ctx, SLB_ERR_RUNTIME, std::string("stillleben_b200 is built for sm_100a only; device is ") + prop.name);
+    slb_ctx* c = new slb_ctx;
+    c->device = device;
+    std::memset(&c->stats, 0, sizeof c->stats);
+    ctx = c;
+    cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    cudaError_t e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    cudaError_t e3 = cudaHostAlloc((void**)&c->total_pinned, 64, cudaHostAllocDefault);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { delete c; ctx = nullptr; return fail(ctx, SLB_ERR_CUDA, "slb_ctx_create: stream/pinned allocation failed"); }
+    float noise[48], kernel[192];
+    ssao_tables(noise, kernel);
+    upload_ssao_tables(noise, kernel);
+    // background plane: Magnum Primitives::planeSolid(TextureCoordinates) — strip (1,-1)(1,1)(-1,-1)(-1,1),
+    // +Z normal, no tangent / vertex-id attribute (contrib/magnum/src/Magnum/Primitives/Plane.cpp:36-60)
+    {
+        struct V68 { float pos[3], uv[2], color[4], tangent[4]; uint32_t id; float normal[3]; } v[4];
+        static_assert(sizeof(V68) == SLB_VERTEX_STRIDE, "vertex stride");
+        const float P[4][2] = {{1, -1}, {1, 1}, {-1, -1}, {-1, 1}};
+        const float U[4][2] = {{1, 0}, {1, 1}, {0, 0}, {0, 1}};
+        std::memset(v, 0, sizeof v);
+        for (int i = 0; i < 4; ++i) {
+            v[i].pos[0] = P[i][0]; v[i].pos[1] = P[i][1]; v[i].uv[0] = U[i][0]; v[i].uv[1] = U[i][1];
+            v[i].color[3] = 1.0f; v[i].tangent[3] = 1.0f; v[i].normal[2] = 1.0f; v[i].id = 0;
+        }
+        const uint32_t idx[6] = {0, 1, 2, 2, 1, 3};
+        slb_submesh sm = {0, 6, -1, 0};
+        const float bmin[3] = {-1, -1, 0}, bmax[3] = {1, 1, 0};
+        int rc = slb_mesh_upload(c, v, 4, idx, 6, &sm, 1, nullptr, 0, nullptr, 0, bmin, bmax, &c->plane);
+        if (rc != SLB_OK) { g_create_error = c->err; slb_ctx_destroy(c); return rc; }
+    }
+    *out = c;
+    return SLB_OK;
+}
+
+extern "C" int slb_ctx_synchronize(slb_ctx* ctx) {
+    if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    return SLB_OK;
+}
+
+extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->plane) slb_mesh_destroy(ctx, ctx->plane);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->slot[i]) slb_result_destroy(ctx, ctx->slot[i]);
+        if (ctx->slot_rendered[i]) cudaEventDestroy(ctx->slot_rendered[i]);
+        if (ctx->slot_copied[i]) cudaEventDestroy(ctx->slot_copied[i]);
+    }
+    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->sdraws_d, &ctx->schunk_base_d, &ctx->tile_count,
+                      &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->ao,
+                      &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& e : ctx->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->staging) cudaFreeHost(ctx->staging);
+    if (ctx->total_pinned) cudaFreeHost(ctx->total_pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+extern "C" int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value) {
+    if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
+    switch (option) {
+        case SLB_OPT_TIME_KERNELS: ctx->time_kernels = value != 0; return SLB_OK;
+        case SLB_OPT_KEEP_HDR: ctx->keep_hdr = value != 0; return SLB_OK;
+        case SLB_OPT_MAX_SUBBATCH:
+            if (value < 1 || value > 1024) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "SLB_OPT_MAX_SUBBATCH must be in [1, 1024]");
+            ctx->max_subbatch = (int)value;
+            for (int i = 0; i < 2; ++i) if (ctx->slot[i]) { slb_result_destroy(ctx, ctx->slot[i]); ctx->slot[i] = nullptr; }
+            return SLB_OK;
+        default: return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "unknown option");
+    }
+}
+
+extern "C" int slb_ctx_get_stats(slb_ctx* ctx, slb_stats* out) {
+    if (!ctx || !out) return SLB_ERR_INVALID_ARGUMENT;
+    *out = ctx->stats;
+    return SLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// textures / meshes
+// ---------------------------------------------------------------------------------------------
+static bool valid_image(const slb_image* im) {
+    return im && im->pixels && im->width > 0 && im->height > 0 && (im->channels == 3 || im->channels == 4) &&
+           im->wrap_s >= 0 && im->wrap_s <= 3 && im->wrap_t >= 0 && im->wrap_t <= 3 && im->min_filter >= 0 && im->min_filter <= 5 &&
+           (im->mag_filter == SLB_FILTER_NEAREST || im->mag_filter == SLB_FILTER_LINEAR);
+}
+
+extern "C" int slb_texture_create(slb_ctx* ctx, const slb_image* image, int kind, slb_texture** out) {
+    if (!ctx || !out) return SLB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!valid_image(image)) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_texture_create: unsupported image (RGB8/RGBA8 only)");
+    if (kind != SLB_TEXTURE_2D && kind != SLB_TEXTURE_RECT) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_texture_create: bad kind");
+    CU(cudaSetDevice(ctx->device));
+    slb_texture* t = new slb_texture;
+    std::memset(&t->h, 0, sizeof t->h);
+    t->h.w = image->width; t->h.h = image->height;
+    t->h.wrap_s = image->wrap_s; t->h.wrap_t = image->wrap_t; t->h.min_filter = image->min_filter; t->h.mag_filter = image->mag_filter;
+    t->h.kind = kind; t->h.has_alpha = image->channels == 4;
+    int lw = image->width, lh = image->height, nl = 0; size_t total = 0;
+    std::vector<int> ws, hs;
+    for (;;) {
+        t->h.level_off[nl] = (uint32_t)total; ws.push_back(lw); hs.push_back(lh);
+        total += (size_t)lw * lh; ++nl;
+        if (kind != SLB_TEXTURE_2D || (lw == 1 && lh == 1) || nl == SLB_MAX_LEVELS) break;
+        lw = lw > 1 ? lw >> 1 : 1; lh = lh > 1 ? lh >> 1 : 1;
+    }
+    t->h.n_levels = nl;
+    void* raw = nullptr;
+    size_t raw_bytes = (size_t)image->width * image->height * image->channels;
+    cudaError_t e = cudaMalloc((void**)&t->px, total * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&raw, raw_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&t->d, sizeof(DTexture));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(raw, image->pixels, raw_bytes, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) {
+        launch_expand_rgba((const uint8_t*)raw, image->channels, t->px, (size_t)image->width * image->height, ctx->stream);
+        for (int l = 1; l < nl; ++l)
+            launch_mip_level(t->px + (size_t)t->h.level_off[l - 1] * 4, ws[l - 1], hs[l - 1], t->px + (size_t)t->h.level_off[l] * 4, ws[l], hs[l], ctx->stream);
+        ctx->stats.kernel_launches += nl;
+        t->h.px = t->px;
+        e = cudaMemcpyAsync(t->d, &t->h, sizeof(DTexture), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (raw) cudaFree(raw);
+    if (e != cudaSuccess) {
+        if (t->px) cudaFree(t->px);
+        if (t->d) cudaFree(t->d);
+        delete t;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? SLB_ERR_OUT_OF_MEMORY : SLB_ERR_CUDA, std::string("slb_texture_create: ") + cudaGetErrorString(e));
+    }
+    *out = t;
+    return SLB_OK;
+}
+// read back one level as RGBA8 (tests pin the mip chain bit-exactly against the oracle)
+extern "C" int slb_texture_read_level(slb_ctx* ctx, const slb_texture* tex, int level, int32_t* w, int32_t* h, void* host_out) {
+    if (!ctx || !tex || level < 0 || level >= tex->h.n_levels) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_texture_read_level: bad level");
+    int lw = tex->h.w >> level, lh = tex->h.h >> level;
+    lw = lw > 0 ? lw : 1; lh = lh > 0 ? lh : 1;
+    if (w) *w = lw;
+    if (h) *h = lh;
+    if (host_out) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaMemcpy(host_out, tex->px + (size_t)tex->h.level_off[level] * 4, (size_t)lw * lh * 4, cudaMemcpyDeviceToHost));
+    }
+    return tex->h.n_levels;
+}
+
+extern "C" void slb_texture_destroy(slb_ctx* ctx, slb_texture* tex) {
+    if (!tex) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (tex->px) cudaFree(tex->px);
+    if (tex->d) cudaFree(tex->d);
+    delete tex;
+}
+
+extern "C" int slb_mesh_upload(slb_ctx* ctx, const void* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices,
+                               const slb_submesh* submeshes, uint32_t n_submeshes, const slb_material* materials, uint32_t n_materials,
+                               const slb_image* images, uint32_t n_images, const float bbox_min[3], const float bbox_max[3], slb_mesh** out) {
+    if (!ctx || !out) return SLB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!vertices || !indices || n_vertices == 0 || !submeshes || n_submeshes == 0 || !bbox_min || !bbox_max)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_mesh_upload: missing vertices / indices / submeshes / bbox");
+    for (uint32_t i = 0; i < n_submeshes; ++i) {
+        const slb_submesh& s = submeshes[i];
+        if (s.index_count % 3 != 0 || (uint64_t)s.index_offset + s.index_count > n_indices)
+            return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_mesh_upload: submesh index range invalid");
+        if (s.material >= (int32_t)n_materials) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_mesh_upload: submesh material out of range");
+    }
+    for (uint32_t i = 0; i < n_materials; ++i) {
+        const int32_t tx[5] = {materials[i].tex_base_color, materials[i].tex_normal, materials[i].tex_metallic_roughness,
+                               materials[i].tex_emissive, materials[i].tex_occlusion};
+        for (int k = 0; k < 5; ++k)
+            if (tx[k] >= (int32_t)n_images) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_mesh_upload: material texture index out of range");
+    }
+    CU(cudaSetDevice(ctx->device));
+    slb_mesh* m = new slb_mesh;
+    m->n_vertices = n_vertices; m->n_indices = n_indices;
+    m->submeshes.assign(submeshes, submeshes + n_submeshes);
+    if (n_materials) m->materials.assign(materials, materials + n_materials);
+    for (int k = 0; k < 3; ++k) { m->bbox_min[k] = bbox_min[k]; m->bbox_max[k] = bbox_max[k]; }
+    void* raw = nullptr;
+    cudaError_t e = cudaMalloc((void**)&m->pos4, (size_t)n_vertices * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->attr, (size_t)n_vertices * 3 * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->idx, (size_t)(n_indices ? n_indices : 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&raw, (size_t)n_vertices * SLB_VERTEX_STRIDE);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(raw, vertices, (size_t)n_vertices * SLB_VERTEX_STRIDE, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m->idx, indices, (size_t)n_indices * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) {
+        launch_repack_vertices((const uint8_t*)raw, n_vertices, m->pos4, m->attr, ctx->stream);
+        ctx->stats.kernel_launches += 1;
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (raw) cudaFree(raw);
+    int rc = SLB_OK;
+    if (e != cudaSuccess) rc = fail(ctx, e == cudaErrorMemoryAllocation ? SLB_ERR_OUT_OF_MEMORY : SLB_ERR_CUDA, std::string("slb_mesh_upload: ") + cudaGetErrorString(e));
+    // index range check on the host copy when the source is host memory is the caller's job; textures:
+    for (uint32_t i = 0; rc == SLB_OK && i < n_images; ++i) {
+        slb_texture* t = nullptr;
+        rc = slb_texture_create(ctx, &images[i], SLB_TEXTURE_2D, &t);
+        if (rc == SLB_OK) m->textures.push_back(t);
+    }
+    if (rc != SLB_OK) { std::string keep = ctx->err; slb_mesh_destroy(ctx, m); ctx->err = keep; return rc; }
+    *out = m;
+    return SLB_OK;
+}
+
+extern "C" int slb_mesh_update_vertices(slb_ctx* ctx, slb_mesh* mesh, const void* vertices, uint32_t n_vertices) {
+    if (!ctx || !mesh || !vertices) return SLB_ERR_INVALID_ARGUMENT;
+    if (n_vertices != mesh->n_vertices) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_mesh_update_vertices: vertex count must not change");
+    CU(cudaSetDevice(ctx->device));
+    void* raw = nullptr;
+    CU(cudaMalloc(&raw, (size_t)n_vertices * SLB_VERTEX_STRIDE));
+    cudaError_t e = cudaMemcpyAsync(raw, vertices, (size_t)n_vertices * SLB_VERTEX_STRIDE, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) {
+        launch_repack_vertices((const uint8_t*)raw, n_vertices, mesh->pos4, mesh->attr, ctx->stream);
+        ctx->stats.kernel_launches += 1;
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(raw);
+    if (e != cudaSuccess) return fail(ctx, SLB_ERR_CUDA, std::string("slb_mesh_update_vertices: ") + cudaGetErrorString(e));
+    return SLB_OK;
+}
+
+extern "C" void slb_mesh_destroy(slb_ctx* ctx, slb_mesh* mesh) {
+    if (!mesh) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    for (slb_texture* t : mesh->textures) slb_texture_destroy(ctx, t);
+    if (mesh->pos4) cudaFree(mesh->pos4);
+    if (mesh->attr) cudaFree(mesh->attr);
+    if (mesh->idx) cudaFree(mesh->idx);
+    delete mesh;
+}
+
+// ---------------------------------------------------------------------------------------------
+// light maps
+// ---------------------------------------------------------------------------------------------
+static int lightmap_finish(slb_ctx* ctx, slb_lightmap* lm) {
+    CU(cudaMemcpyAsync(lm->d, &lm->h, sizeof(DLightMap), cudaMemcpyHostToDevice, ctx->stream));
+    return SLB_OK;
+}
+static int lm_alloc(slb_ctx* ctx, slb_lightmap* lm, size_t bytes, void** out) {
+    CU(cudaMalloc(out, bytes));
+    lm->allocs.push_back(*out);
+    return SLB_OK;
+}
+static int lightmap_build_env_mips(slb_ctx* ctx, slb_lightmap* lm, float4* level0, int size) {
+    lm->h.n_env = 0;
+    float4* cur = level0; int s = size;
+    for (;;) {
+        lm->h.env[lm->h.n_env].px = cur; lm->h.env[lm->h.n_env].size = s; lm->h.n_env++;
+        if (s == 1 || lm->h.n_env == 12) break;
+        float4* nxt = nullptr;
+        int rc = lm_alloc(ctx, lm, (size_t)6 * (s / 2) * (s / 2) * sizeof(float4), (void**)&nxt);
+        if (rc != SLB_OK) return rc;
+        launch_cube_mip(cur, s, nxt, ctx->stream);
+        ctx->stats.kernel_launches += 1;
+        cur = nxt; s /= 2;
+    }
+    return SLB_OK;
+}
+
+// sizes <= 0 select the reference's (512 / 32 / 128 / 512, 1024 samples)
+extern "C" int slb_lightmap_create_ex(slb_ctx* ctx, const slb_lightmap_desc* desc, int env_size, int irr_size, int pre_size, int lut_size,
+                                      int n_samples, slb_lightmap** out) {
+    if (!ctx || !out) return SLB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!desc || !desc->equirect_rgb || desc->width <= 0 || desc->height <= 0 || desc->n_lights < 0 || desc->n_lights > SLB_NUM_LIGHTS)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_lightmap_create: bad descriptor");
+    env_size = env_size > 0 ? env_size : 512; irr_size = irr_size > 0 ? irr_size : 32; pre_size = pre_size > 0 ? pre_size : 128;
+    lut_size = lut_size > 0 ? lut_size : 512; n_samples = n_samples > 0 ? n_samples : 1024;
+    if ((env_size & (env_size - 1)) || (pre_size & (pre_size - 1)) || pre_size < 16)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_lightmap_create: cube sizes must be powers of two (prefilter >= 16)");
+    CU(cudaSetDevice(ctx->device));
+    slb_lightmap* lm = new slb_lightmap;
+    std::memset(&lm->h, 0, sizeof lm->h);
+    lm->env_size = env_size; lm->irr_size = irr_size; lm->pre_size = pre_size; lm->lut_size = lut_size;
+    lm->h.n_lights = desc->n_lights;
+    std::memcpy(lm->h.light_directions, desc->light_directions, sizeof lm->h.light_directions);
+    std::memcpy(lm->h.light_colors, desc->light_colors, sizeof lm->h.light_colors);
+    int rc = SLB_OK;
+    float* eq = nullptr; float4* env0 = nullptr; float4* irr = nullptr; float4* lut = nullptr;
+    size_t eq_bytes = (size_t)desc->width * desc->height * 3 * sizeof(float);
+    do {
+        if ((rc = lm_alloc(ctx, lm, sizeof(DLightMap), (void**)&lm->d)) != SLB_OK) break;
+        if ((rc = lm_alloc(ctx, lm, eq_bytes, (void**)&eq)) != SLB_OK) break;
+        if ((rc = lm_alloc(ctx, lm, (size_t)6 * env_size * env_size * sizeof(float4), (void**)&env0)) != SLB_OK) break;
+        if ((rc = lm_alloc(ctx, lm, (size_t)6 * irr_size * irr_size * sizeof(float4), (void**)&irr)) != SLB_OK) break;
+        if ((rc = lm_alloc(ctx, lm, (size_t)lut_size * lut_size * sizeof(float4), (void**)&lut)) != SLB_OK) break;
+        cudaError_t e = cudaMemcpyAsync(eq, desc->equirect_rgb, eq_bytes, cudaMemcpyDefault, ctx->stream);
+        if (e != cudaSuccess) { rc = fail(ctx, SLB_ERR_CUDA, cudaGetErrorString(e)); break; }
+        launch_equirect_to_cube(eq, desc->width, desc->height, env0, env_size, ctx->stream);
+        ctx->stats.kernel_launches += 1;
+        if ((rc = lightmap_build_env_mips(ctx, lm, env0, env_size)) != SLB_OK) break;
+        lm->h.irr.px = irr; lm->h.irr.size = irr_size;
+        lm->h.lut = lut; lm->h.lut_size = lut_size;
+        for (int mip = 0; mip < 5; ++mip) {
+            int n = pre_size >> mip;
+            float4* p = nullptr;
+            if ((rc = lm_alloc(ctx, lm, (size_t)6 * n * n * sizeof(float4), (void**)&p)) != SLB_OK) break;
+            lm->h.pre[mip].px = p; lm->h.pre[mip].size = n;
+        }
+        if (rc != SLB_OK) break;
+        if ((rc = lightmap_finish(ctx, lm)) != SLB_OK) break;   // env chain visible to the convolution kernels
+        launch_irradiance(lm->d, irr, irr_size, log2f((float)env_size / (float)irr_size), ctx->stream);
+        for (int mip = 0; mip < 5; ++mip)
+            launch_prefilter(lm->d, const_cast<float4*>(lm->h.pre[mip].px), lm->h.pre[mip].size, (float)mip / 4.0f, n_samples, (float)env_size, ctx->stream);
+        launch_brdf_lut(lut, lut_size, n_samples, ctx->stream);
+        ctx->stats.kernel_launches += 7;
+        cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+        if (e2 == cudaSuccess) e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) { rc = fail(ctx, SLB_ERR_CUDA, std::string("slb_lightmap_create: ") + cudaGetErrorString(e2)); break; }
+    } while (0);
+    if (rc != SLB_OK) { std::string keep = ctx->err; slb_lightmap_destroy(ctx, lm); ctx->err = keep; return rc; }
+    *out = lm;
+    return SLB_OK;
+}
+extern "C" int slb_lightmap_create(slb_ctx* ctx, const slb_lightmap_desc* desc, slb_lightmap** out) {
+    return slb_lightmap_create_ex(ctx, desc, 0, 0, 0, 0, 0, out);
+}
+
+extern "C" int slb_lightmap_read(slb_ctx* ctx, const slb_lightmap* lm, int which, float* host_out, size_t n_floats) {
+    if (!ctx || !lm || !host_out) return SLB_ERR_INVALID_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (which == 0 || which == 1 || which == 3) {
+        const void* src = which == 0 ? (const void*)lm->h.env[0].px : which == 1 ? (const void*)lm->h.irr.px : (const void*)lm->h.lut;
+        size_t n = which == 0 ? (size_t)6 * lm->env_size * lm->env_size * 4 : which == 1 ? (size_t)6 * lm->irr_size * lm->irr_size * 4
+                                                                                         : (size_t)lm->lut_size * lm->lut_size * 4;
+        if (n_floats < n) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_lightmap_read: buffer too small");
+        CU(cudaMemcpy(host_out, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+        return SLB_OK;
+    }
+    if (which == 2) {
+        size_t ofs = 0;
+        for (int mip = 0; mip < 5; ++mip) {
+            size_t n = (size_t)6 * lm->h.pre[mip].size * lm->h.pre[mip].size * 4;
+            if (n_floats < ofs + n) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_lightmap_read: buffer too small");
+            CU(cudaMemcpy(host_out + ofs, lm->h.pre[mip].px, n * sizeof(float), cudaMemcpyDeviceToHost));
+            ofs += n;
+        }
+        return SLB_OK;
+    }
+    return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_lightmap_read: which must be 0..3");
+}
+extern "C" int slb_lightmap_sizes(const slb_lightmap* lm, int32_t sizes[4]) {
+    if (!lm || !sizes) return SLB_ERR_INVALID_ARGUMENT;
+    sizes[0] = lm->env_size; sizes[1] = lm->irr_size; sizes[2] = lm->pre_size; sizes[3] = lm->lut_size;
+    return SLB_OK;
+}
+
+extern "C" void slb_lightmap_destroy(slb_ctx* ctx, slb_lightmap* lm) {
+    if (!lm) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    for (void* p : lm->allocs) cudaFree(p);
+    delete lm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------------------------
+extern "C" int slb_result_create(slb_ctx* ctx, int32_t width, int32_t height, int32_t n_frames, uint32_t target_mask,
+                                 void* const* external_ptrs, slb_result** out) {
+    if (!ctx || !out) return SLB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || n_frames <= 0 || (target_mask & ~SLB_TARGETS_ALL) || target_mask == 0)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_result_create: bad size or target mask");
+    CU(cudaSetDevice(ctx->device));
+    slb_result* r = new slb_result;
+    r->W = width; r->H = height; r->n_frames = n_frames; r->mask = target_mask;
+    for (int t = 0; t < SLB_NUM_TARGETS; ++t) { r->ptrs[t] = nullptr; r->owned[t] = false; }
+    for (int t = 0; t < SLB_NUM_TARGETS; ++t) {
+        if (!(target_mask & (1u << t))) continue;
+        if (external_ptrs) {
+            if (!external_ptrs[t]) { slb_result_destroy(ctx, r); return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_result_create: external pointer missing for a requested target"); }
+            r->ptrs[t] = external_ptrs[t];
+        } else {
+            cudaError_t e = cudaMalloc(&r->ptrs[t], (size_t)n_frames * width * height * kTargetBpp[t]);
+            if (e != cudaSuccess) { slb_result_destroy(ctx, r); return fail(ctx, SLB_ERR_OUT_OF_MEMORY, std::string("slb_result_create: ") + cudaGetErrorString(e)); }
+            r->owned[t] = true;
+        }
+    }
+    if (ctx->keep_hdr) {
+        cudaError_t e = cudaMalloc((void**)&r->hdr, (size_t)n_frames * width * height * sizeof(float4));
+        if (e != cudaSuccess) { slb_result_destroy(ctx, r); return fail(ctx, SLB_ERR_OUT_OF_MEMORY, "slb_result_create: hdr allocation failed"); }
+    }
+    *out = r;
+    return SLB_OK;
+}
+
+extern "C" int slb_result_ptrs(const slb_result* res, void* ptrs[SLB_NUM_TARGETS], size_t bytes_per_pixel[SLB_NUM_TARGETS]) {
+    if (!res) return SLB_ERR_INVALID_ARGUMENT;
+    for (int t = 0; t < SLB_NUM_TARGETS; ++t) {
+        if (ptrs) ptrs[t] = res->ptrs[t];
+        if (bytes_per_pixel) bytes_per_pixel[t] = res->ptrs[t] ? kTargetBpp[t] : 0;
+    }
+    return SLB_OK;
+}
+
+extern "C" int slb_result_read(slb_ctx* ctx, const slb_result* res, int target, int32_t first_frame, int32_t n_frames, void* host_out,
+                               size_t host_bytes) {
+    if (!ctx || !res || !host_out) return SLB_ERR_INVALID_ARGUMENT;
+    if (target < 0 || target >= SLB_NUM_TARGETS || !res->ptrs[target]) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_result_read: target not in the result");
+    if (first_frame < 0 || n_frames <= 0 || first_frame + n_frames > res->n_frames) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_result_read: frame range");
+    size_t per = (size_t)res->W * res->H * kTargetBpp[target];
+    if (host_bytes < per * n_frames) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_result_read: host buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(host_out, (const uint8_t*)res->ptrs[target] + per * first_frame, per * n_frames, cudaMemcpyDeviceToHost));
+    ctx->stats.bytes_d2h += per * n_frames;
+    return SLB_OK;
+}
+
+extern "C" int slb_result_read_hdr(slb_ctx* ctx, const slb_result* res, int32_t frame, float* host_out, size_t n_floats) {
+    if (!ctx || !res || !host_out) return SLB_ERR_INVALID_ARGUMENT;
+    if (!res->hdr) return fail(ctx, SLB_ERR_RUNTIME, "slb_result_read_hdr: result was created without SLB_OPT_KEEP_HDR");
+    if (frame < 0 || frame >= res->n_frames || n_floats < (size_t)res->W * res->H * 4) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_result_read_hdr: bad frame / size");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(host_out, res->hdr + (size_t)frame * res->W * res->H, (size_t)res->W * res->H * sizeof(float4), cudaMemcpyDeviceToHost));
+    return SLB_OK;
+}
+
+extern "C" void slb_result_destroy(slb_ctx* ctx, slb_result* res) {
+    if (!res) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); }
+    for (int t = 0; t < SLB_NUM_TARGETS; ++t) if (res->owned[t] && res->ptrs[t]) cudaFree(res->ptrs[t]);
+    if (res->hdr) cudaFree(res->hdr);
+    delete res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Batch {
+    std::vector<DFrame> frames;
+    std::vector<DDraw> draws;
+    std::vector<uint32_t> chunk_base;     // per draw (+1 sentinel)
+    std::vector<DShadowDraw> sdraws;
+    std::vector<uint32_t> schunk_base;
+    std::vector<int> frame_first_light_slot;   // index of the frame's first shadow map in the batch pool
+    uint32_t n_chunks = 0, n_schunks = 0, n_shadow_maps = 0;
+    uint64_t n_tris = 0;
+    bool fused = true, any_ssao = false, any_auto = false, any_bg = false;
+};
+
+static inline uint32_t chunks_of(uint32_t n_tris) { return (n_tris + SLB_SETUP_CHUNK - 1) / SLB_SETUP_CHUNK; }
+
+// reference: src/render_pass.cpp:69-129
+static void frustum_corners(const slb_scene_desc& sc, hm::Vec3 corners[8]) {
+    using namespace hm;
+    Mat4 P = load(sc.projection), V = load(sc.world_to_cam);
+    Mat4 Pinv = inverted(P);
+    float nearv = -1.0f, farv = 1.0f;
+    if (sc.n_objects > 0) {
+        float nearObj = std::numeric_limits<float>::infinity(), farObj = -nearObj;
+        for (int i = 0; i < sc.n_objects; ++i) {
+            const slb_object_desc& o = sc.objects[i];
+            const slb_mesh* m = o.mesh;
+            Mat4 pre = load(o.pretransform);
+            Vec3 lo = transform_point(pre, v3(m->bbox_min[0], m->bbox_min[1], m->bbox_min[2]));
+            Vec3 hi = transform_point(pre, v3(m->bbox_max[0], m->bbox_max[1], m->bbox_max[2]));
+            Vec3 center = (lo + hi) * 0.5f;
+            float radius = length(hi - lo) / 2;
+            Vec3 objInCam = transform_point(mul(V, load(o.pose)), center);
+            Vec3 np = transform_point(P, objInCam - v3(0, 0, radius));
+            Vec3 fp = transform_point(P, objInCam + v3(0, 0, radius));
+            nearObj = std::min(nearObj, np.z);
+            farObj = std::max(farObj, fp.z);
+        }
+        nearv = std::max(std::max(-1.0f, nearObj), nearv);
+        farv = std::min(farObj, farv);
+    }
+    const float hc[8][3] = {{-1, 1, nearv}, {1, 1, nearv}, {1, -1, nearv}, {-1, -1, nearv},
+                            {-1, 1, farv},  {1, 1, farv},  {1, -1, farv},  {-1, -1, farv}};
+    Mat4 camToWorld = inverted_rigid(V);
+    for (int i = 0; i < 8; ++i) {
+        float v[4] = {hc[i][0], hc[i][1], hc[i][2], 1.0f}, a[4], b[4];
+        mul4(Pinv, v, a); mul4(camToWorld, a, b);
+        corners[i] = v3(b[0] / b[3], b[1] / b[3], b[2] / b[3]);
+    }
+}
+// reference: src/render_pass.cpp:131-211
+static hm::Mat4 shadow_matrix(const slb_scene_desc& sc, const hm::Vec3 corners[8], hm::Vec3 lightDirection) {
+    using namespace hm;
+    Vec3 z = normalize(lightDirection);
+    Vec3 x = normalize(cross(z, v3(0, 0, 1)));
+    Vec3 y = normalize(cross(z, x));
+    Mat4 camToWorld = identity();
+    const float xs[3] = {x.x, x.y, x.z}, ys[3] = {y.x, y.y, y.z}, zs[3] = {z.x, z.y, z.z};
+    for (int r = 0; r < 3; ++r) { camToWorld.at(r, 0) = xs[r]; camToWorld.at(r, 1) = ys[r]; camToWorld.at(r, 2) = zs[r]; }
+    Mat4 worldToCam = inverted_rigid(camToWorld);
+    const float inf = std::numeric_limits<float>::infinity();
+    Vec3 mn = v3(inf, inf, inf), mx = v3(-inf, -inf, -inf);
+    for (int i = 0; i < 8; ++i) { Vec3 c = transform_point(worldToCam, corners[i]); mn = vmin(mn, c); mx = vmax(mx, c); }
+    float nearv = mn.z, farv = mx.z;
+    float meanZ = (nearv + farv) / 2.0f;
+    float spread = farv - meanZ;
+    farv = meanZ + 5.0f * spread;
+    nearv = meanZ - 5.0f * spread;
+    float L = mn.x, R = mx.x, T = mn.y, B = mx.y;
+    if (sc.n_objects > 0) {
+        Vec3 lo_all = v3(inf, inf, inf), hi_all = v3(-inf, -inf, -inf);
+        for (int i = 0; i < sc.n_objects; ++i) {
+            const slb_object_desc& o = sc.objects[i];
+            const slb_mesh* m = o.mesh;
+            Mat4 pre = load(o.pretransform);
+            Vec3 lo = transform_point(pre, v3(m->bbox_min[0], m->bbox_min[1], m->bbox_min[2]));
+            Vec3 hi = transform_point(pre, v3(m->bbox_max[0], m->bbox_max[1], m->bbox_max[2]));
+            float radius = length(hi - lo) / 2;
+            Vec3 c = transform_point(mul(worldToCam, load(o.pose)), (lo + hi) * 0.5f);
+            lo_all = vmin(lo_all, c - v3(radius, radius, radius));
+            hi_all = vmax(hi_all, c + v3(radius, radius, radius));
+        }
+        L = std::max(L, lo_all.x); R = std::min(R, hi_all.x);
+        T = std::max(T, lo_all.y); B = std::min(B, hi_all.y);
+    }
+    Mat4 Pm; std::memset(Pm.m, 0, sizeof Pm.m);
+    Pm.at(0, 0) = 2.0f / (R - L); Pm.at(1, 1) = 2.0f / (B - T); Pm.at(2, 2) = 2.0f / (farv - nearv);
+    Pm.at(0, 3) = -(R + L) / (R - L); Pm.at(1, 3) = -(B + T) / (B - T); Pm.at(2, 3) = -(farv + nearv) / (farv - nearv);
+    Pm.at(3, 3) = 1.0f;
+    return mul(Pm, worldToCam);
+}
+
+static void fill_material(DDraw& d, const slb_mesh* mesh, int material, float ovr_metallic, float ovr_roughness) {
+    for (int i = 0; i < 5; ++i) d.tex[i] = nullptr;
+    bool tex0_alpha = false;
+    if (mesh && material >= 0 && material < (int)mesh->materials.size()) {
+        const slb_material& m = mesh->materials[material];
+        std::memcpy(d.base_color, m.base_color, 16); std::memcpy(d.emissive, m.emissive, 16);
+        d.metallic = m.metallic; d.roughness = m.roughness;
+        const int32_t tx[5] = {m.tex_base_color, m.tex_normal, m.tex_metallic_roughness, m.tex_emissive, m.tex_occlusion};
+        for (int i = 0; i < 5; ++i)
+            if (tx[i] >= 0 && tx[i] < (int)mesh->textures.size()) d.tex[i] = mesh->textures[tx[i]]->d;
+        if (d.tex[0]) tex0_alpha = mesh->textures[tx[0]]->h.has_alpha != 0;
+    } else {   // context default material: 0x3bd267ff_srgbaf (reference: src/context.cpp:382-384)
+        d.base_color[0] = 0.04373503f; d.base_color[1] = 0.6444797f; d.base_color[2] = 0.13563333f; d.base_color[3] = 1.0f;
+        d.emissive[0] = d.emissive[1] = d.emissive[2] = d.emissive[3] = 0.0f;
+        d.metallic = 0.04f; d.roughness = 0.5f;
+    }
+    if (ovr_metallic >= 0.0f) d.metallic = ovr_metallic;      // render_shader.cpp:372-377
+    if (ovr_roughness >= 0.0f) d.roughness = ovr_roughness;
+    d.flags = (tex0_alpha || d.base_color[3] < 0.5f) ? DRAW_FRAG_TEST : 0u;
+}
+
+}  // namespace
+
+static int validate_scene(slb_ctx* ctx, const slb_scene_desc& sc, const slb_result* result) {
+    if (sc.width != result->W || sc.height != result->H) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_render_batch: scene viewport differs from the result size");
+    if (sc.n_objects < 0 || (sc.n_objects > 0 && !sc.objects)) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_render_batch: objects missing");
+    for (int i = 0; i < sc.n_objects; ++i) {
+        const slb_object_desc& o = sc.objects[i];
+        if (!o.mesh) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_render_batch: object without mesh");
+        if (o.class_index > 0xFFFFu) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "class index out of range (max 65535)");          // mesh.cpp:1083-1089
+        if (o.instance_index > 0xFFFFu) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "instance index out of range (max 65535)");    // object.cpp:376-382
+        if (o.sticker_texture && o.sticker_texture->h.kind != SLB_TEXTURE_RECT) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "sticker texture must be a RECT texture");
+    }
+    if (sc.background_image && sc.background_image->h.kind != SLB_TEXTURE_RECT) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "background image must be a RECT texture");
+    if (sc.background_plane_texture && sc.background_plane_texture->h.kind != SLB_TEXTURE_2D) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "plane texture must be a 2D texture");
+    return SLB_OK;
+}
+
+// marshal scenes [s0, s0+n) into a Batch (host arrays only; device pointers are patched in later)
+static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const slb_result* result, int first_frame,
+                        const slb_result* depth_peel, Batch& b) {
+    using namespace hm;
+    const int W = result->W, H = result->H;
+    const int tiles_x = (W + SLB_TILE - 1) / SLB_TILE, tiles_y = (H + SLB_TILE - 1) / SLB_TILE;
+    b.frames.resize(n);
+    for (int j = 0; j < n; ++j) {
+        const slb_scene_desc& sc = scenes[j];
+        DFrame& f = b.frames[j];
+        std::memset(&f, 0, sizeof f);
+        f.W = W; f.H = H; f.tiles_x = tiles_x; f.tiles_y = tiles_y;
+        f.tile_base = (uint32_t)j * tiles_x * tiles_y;
+        Mat4 P = load(sc.projection), V = load(sc.world_to_cam);
+        std::memcpy(f.P, P.m, 64); std::memcpy(f.V, V.m, 64);
+        Mat4 Pinv = inverted(P); std::memcpy(f.Pinv, Pinv.m, 64);
+        Mat4 camToWorld = inverted_rigid(V);
+        f.camPos[0] = camToWorld.at(0, 3); f.camPos[1] = camToWorld.at(1, 3); f.camPos[2] = camToWorld.at(2, 3);
+        f.manual_exposure = sc.manual_exposure;
+        f.ssao = sc.ssao_enabled ? 1 : 0;
+        const slb_lightmap* lm = sc.light_map;
+        f.lm = lm ? lm->d : nullptr;
+        bool anyLight = false;
+        for (int i = 0; i < SLB_NUM_LIGHTS; ++i) {
+            float dir[3] = {0, 0, 0}, col[3] = {0, 0, 0};
+            if (lm) {   // render_shader.cpp:270-296
+                if (i < lm->h.n_lights) { std::memcpy(dir, lm->h.light_directions[i], 12); std::memcpy(col, lm->h.light_colors[i], 12); }
+            } else { std::memcpy(dir, sc.light_directions[i], 12); std::memcpy(col, sc.light_colors[i], 12); }
+            std::memcpy(f.lightDir[i], dir, 12); std::memcpy(f.lightCol[i], col, 12);
+            bool colZero = col[0] == 0 && col[1] == 0 && col[2] == 0, dirZero = dir[0] == 0 && dir[1] == 0 && dir[2] == 0;
+            f.lightActive[i] = !(colZero || dirZero);
+            anyLight |= f.lightActive[i] != 0;
+        }
+        if (!lm) std::memcpy(f.ambient, sc.ambient_light, 12);
+        f.peel = depth_peel ? (const float*)depth_peel->ptrs[SLB_TARGET_COORD] + (size_t)(first_frame + j) * W * H * 4 : nullptr;
+        f.bg_image = sc.background_image ? sc.background_image->d : nullptr;
+        for (int t = 0; t < SLB_NUM_TARGETS; ++t)
+            f.out[t] = result->ptrs[t] ? (uint8_t*)result->ptrs[t] + (size_t)(first_frame + j) * W * H * kTargetBpp[t] : nullptr;
+        const bool fused = !f.ssao && f.manual_exposure >= 0 && !f.bg_image && !f.lm && !ctx->keep_hdr;
+        b.fused &= fused;
+        b.any_ssao |= f.ssao != 0; b.any_auto |= f.manual_exposure < 0; b.any_bg |= (f.bg_image || f.lm);
+
+        // ---- draw list in submission order (render_pass.cpp:545-622) ----
+        f.draw_begin = (uint32_t)b.draws.size();
+        uint32_t prim = 0;
+        const bool frag_all = f.peel != nullptr;
+        auto push_draw = [&](DDraw& d, uint32_t n_tris) {
+            d.n_tris = n_tris; d.prim_base = prim; prim += n_tris;
+            d.frame = (uint32_t)j;
+            d.chunk_base = b.n_chunks; b.n_chunks += chunks_of(n_tris);
+            Mat4 o2w = load(d.objectToWorld), m2o = load(d.meshToObject);
+            mvp(P, V, o2w, m2o, d.mvp);
+            normal_matrix(mul(o2w, m2o), d.normalToWorld);
+            if (frag_all) d.flags |= DRAW_FRAG_TEST;
+            b.n_tris += n_tris;
+            b.chunk_base.push_back(d.chunk_base);
+            b.draws.push_back(d);
+        };
+        if (sc.background_plane_size[0] * sc.background_plane_size[0] + sc.background_plane_size[1] * sc.background_plane_size[1] > 0) {
+            DDraw d; std::memset(&d, 0, sizeof d);
+            const slb_mesh* pm = ctx->plane;
+            d.pos4 = pm->pos4; d.attr = pm->attr; d.idx = pm->idx;
+            Mat4 scale = identity();
+            scale.at(0, 0) = sc.background_plane_size[0] / 2.0f; scale.at(1, 1) = sc.background_plane_size[1] / 2.0f;
+            Mat4 o2w = mul(load(sc.background_plane_pose), scale);
+            std::memcpy(d.objectToWorld, o2w.m, 64);
+            Mat4 I = identity(); std::memcpy(d.meshToObject, I.m, 64); std::memcpy(d.stickerProj, I.m, 64);
+            fill_material(d, nullptr, -1, -1.0f, -1.0f);
+            if (sc.background_plane_texture) {
+                d.base_color[0] = d.base_color[1] = d.base_color[2] = d.base_color[3] = 1.0f;
+                d.tex[0] = sc.background_plane_texture->d;
+                d.flags = sc.background_plane_texture->h.has_alpha ? DRAW_FRAG_TEST : 0u;
+            } else { d.base_color[0] = 0.0f; d.base_color[1] = 0.8f; d.base_color[2] = 0.0f; d.base_color[3] = 1.0f; }
+            d.stickerRange[2] = d.stickerRange[3] = 1e-6f;
+            push_draw(d, 2);
+        }
+        for (int i = 0; i < sc.n_objects; ++i) {
+            const slb_object_desc& o = sc.objects[i];
+            if (!o.visible) continue;
+            const slb_mesh* mesh = o.mesh;
+            for (const slb_submesh& sm : mesh->submeshes) {
+                DDraw d; std::memset(&d, 0, sizeof d);
+                d.pos4 = mesh->pos4; d.attr = mesh->attr; d.idx = mesh->idx + sm.index_offset;
+                std::memcpy(d.meshToObject, o.pretransform, 64); std::memcpy(d.objectToWorld, o.pose, 64);
+                fill_material(d, mesh, sm.material, o.metallic, o.roughness);
+                d.class_index = o.class_index; d.instance_index = o.instance_index;
+                d.sticker = o.sticker_texture ? o.sticker_texture->d : nullptr;
+                std::memcpy(d.stickerProj, o.sticker_projection, 64);
+                d.stickerRange[0] = o.sticker_range[0]; d.stickerRange[1] = o.sticker_range[1];
+                d.stickerRange[2] = std::max(1e-6f, o.sticker_range[2]); d.stickerRange[3] = std::max(1e-6f, o.sticker_range[3]);
+                push_draw(d, sm.index_count / 3);
+            }
+        }
+        f.draw_end = (uint32_t)b.draws.size();
+        f.n_prims = prim;
+
+        // ---- shadow pass set-up (render_pass.cpp:407-460) ----
+        b.frame_first_light_slot.push_back((int)b.n_shadow_maps);
+        if (anyLight) {
+            Vec3 corners[8]; frustum_corners(sc, corners);
+            for (int li = 0; li < SLB_NUM_LIGHTS; ++li) {
+                if (!f.lightActive[li]) continue;
+                Mat4 sm = shadow_matrix(sc, corners, v3(f.lightDir[li][0], f.lightDir[li][1], f.lightDir[li][2]));
+                std::memcpy(f.shadowMat[li], sm.m, 64);
+                const uint32_t slot = b.n_shadow_maps++;
+                f.shadowMap[li] = reinterpret_cast<const uint32_t*>((uintptr_t)slot);   // patched to a pointer once the pool is sized
+                for (int i = 0; i < sc.n_objects; ++i) {
+                    const slb_object_desc& o = sc.objects[i];
+                    if (!o.visible || !o.casts_shadows) continue;
+                    const slb_mesh* mesh = o.mesh;
+                    for (const slb_submesh& s : mesh->submeshes) {
+                        DShadowDraw sd; std::memset(&sd, 0, sizeof sd);
+                        sd.pos4 = mesh->pos4; sd.idx = mesh->idx + s.index_offset; sd.n_tris = s.index_count / 3;
+                        sd.chunk_base = b.n_schunks; b.n_schunks += chunks_of(sd.n_tris);
+                        sd.map = reinterpret_cast<uint32_t*>((uintptr_t)slot);
+                        mvp(sm, identity(), load(o.pose), load(o.pretransform), sd.mvp);
+                        b.schunk_base.push_back(sd.chunk_base);
+                        b.sdraws.push_back(sd);
+                    }
+                }
+            }
+        }
+    }
+    b.chunk_base.push_back(b.n_chunks);
+    b.schunk_base.push_back(b.n_schunks);
+}
+
+static cudaEvent_t get_event(slb_ctx* ctx) {
+    if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct StageTimer {
+    slb_ctx* ctx; cudaStream_t s; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(slb_ctx* c, cudaStream_t st, int stage_) : ctx(c), s(st), stage(stage_) {
+        if (ctx->time_kernels) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, s); }
+    }
+    ~StageTimer() { if (ctx->time_kernels) { cudaEventRecord(b, s); ctx->events.push_back({stage, a, b}); } }
+};
+
+static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, slb_result* result, int first_frame,
+                           const slb_result* depth_peel, cudaStream_t s) {
+    Batch b;
+    build_batch(ctx, scenes, n, result, first_frame, depth_peel, b);
+    const int W = result->W, H = result->H;
+    const size_t npx = (size_t)W * H;
+    const uint32_t tiles_per_frame = (uint32_t)b.frames[0].tiles_x * b.frames[0].tiles_y;
+    const uint32_t n_tiles = tiles_per_frame * (uint32_t)n;
+
+    // ---- device scratch ----
+    CU(ctx->frames_d.reserve(b.frames.size() * sizeof(DFrame)));
+    CU(ctx->draws_d.reserve((b.draws.size() + 1) * sizeof(DDraw)));
+    CU(ctx->chunk_base_d.reserve(b.chunk_base.size() * 4));
+    CU(ctx->sdraws_d.reserve((b.sdraws.size() + 1) * sizeof(DShadowDraw)));
+    CU(ctx->schunk_base_d.reserve(b.schunk_base.size() * 4));
+    CU(ctx->tile_count.reserve((size_t)n_tiles * 4, true));
+    CU(ctx->tile_off.reserve(((size_t)n_tiles + 1) * 4));
+    CU(ctx->keys.reserve(npx * n * 8));
+    CU(ctx->shadow_maps.reserve((size_t)b.n_shadow_maps * SLB_SHADOW_RES * SLB_SHADOW_RES * 4));
+    const bool post = !b.fused;
+    if (post) {
+        if (!result->hdr) CU(ctx->hdr.reserve(npx * n * 16));
+        CU(ctx->ao.reserve(npx * n * 4));
+        CU(ctx->avg.reserve((size_t)n * 16));
+        if (!result->ptrs[SLB_TARGET_NORMAL] && b.any_ssao) CU(ctx->scratch_normal.reserve(npx * n * 16));
+        if (!result->ptrs[SLB_TARGET_CAM_COORD] && b.any_ssao) CU(ctx->scratch_cam.reserve(npx * n * 16));
+        if (b.any_auto) { CU(ctx->mip_a.reserve((npx / 4 + W + H + 4) * n * 16)); CU(ctx->mip_b.reserve((npx / 16 + W + H + 4) * n * 16)); }
+    }
+    // ---- patch device pointers into the host arrays ----
+    uint32_t* smaps = ctx->shadow_maps.as<uint32_t>();
+    const size_t smap_elems = (size_t)SLB_SHADOW_RES * SLB_SHADOW_RES;
+    for (int j = 0; j < n; ++j) {
+        DFrame& f = b.frames[j];
+        f.keys = ctx->keys.as<uint64_t>() + npx * j;
+        f.fused_tonemap = b.fused ? 1 : 0;
+        for (int li = 0; li < SLB_NUM_LIGHTS; ++li)
+            f.shadowMap[li] = f.lightActive[li] ? smaps + smap_elems * (uintptr_t)f.shadowMap[li] : nullptr;
+        f.scratch_normal = (float4*)f.out[SLB_TARGET_NORMAL];
+        f.scratch_cam = (float4*)f.out[SLB_TARGET_CAM_COORD];
+        if (post) {
+            f.hdr = result->hdr ? result->hdr + npx * (first_frame + j) : ctx->hdr.as<float4>() + npx * j;
+            f.ao = ctx->ao.as<float>() + npx * j;
+            f.avg = ctx->avg.as<float>() + 4 * j;
+            if (!f.scratch_normal && b.any_ssao) f.scratch_normal = ctx->scratch_normal.as<float4>() + npx * j;
+            if (!f.scratch_cam && b.any_ssao) f.scratch_cam = ctx->scratch_cam.as<float4>() + npx * j;
+        }
+    }
+    for (DShadowDraw& sd : b.sdraws) sd.map = smaps + smap_elems * (uintptr_t)sd.map;
+
+    // ---- one staged upload ----
+    const size_t sz_f = b.frames.size() * sizeof(DFrame), sz_d = b.draws.size() * sizeof(DDraw), sz_c = b.chunk_base.size() * 4,
+                 sz_s = b.sdraws.size() * sizeof(DShadowDraw), sz_sc = b.schunk_base.size() * 4;
+    int rc = ensure_staging(ctx, sz_f + sz_d + sz_c + sz_s + sz_sc + 64);
+    if (rc != SLB_OK) return rc;
+    uint8_t* st = (uint8_t*)ctx->staging;
+    std::memcpy(st, b.frames.data(), sz_f);
+    std::memcpy(st + sz_f, b.draws.data(), sz_d);
+    std::memcpy(st + sz_f + sz_d, b.chunk_base.data(), sz_c);
+    std::memcpy(st + sz_f + sz_d + sz_c, b.sdraws.data(), sz_s);
+    std::memcpy(st + sz_f + sz_d + sz_c + sz_s, b.schunk_base.data(), sz_sc);
+    CU(cudaMemcpyAsync(ctx->frames_d.p, st, sz_f, cudaMemcpyHostToDevice, s));
+    if (sz_d) CU(cudaMemcpyAsync(ctx->draws_d.p, st + sz_f, sz_d, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->chunk_base_d.p, st + sz_f + sz_d, sz_c, cudaMemcpyHostToDevice, s));
+    if (sz_s) CU(cudaMemcpyAsync(ctx->sdraws_d.p, st + sz_f + sz_d + sz_c, sz_s, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->schunk_base_d.p, st + sz_f + sz_d + sz_c + sz_s, sz_sc, cudaMemcpyHostToDevice, s));
+    ctx->stats.bytes_h2d += sz_f + sz_d + sz_c + sz_s + sz_sc;
+
+    const DFrame* frames_d = ctx->frames_d.as<DFrame>();
+    const DDraw* draws_d = ctx->draws_d.as<DDraw>();
+
+    // ---- shadow pass ----
+    if (b.n_shadow_maps) {
+        StageTimer t(ctx, s, ST_SHADOW);
+        CU(cudaMemsetAsync(smaps, 0xFF, smap_elems * 4 * b.n_shadow_maps, s));
+        launch_shadow(ctx->sdraws_d.as<DShadowDraw>(), ctx->schunk_base_d.as<uint32_t>(), (int)b.sdraws.size(), b.n_schunks, s);
+        if (b.n_schunks) ctx->stats.kernel_launches += 1;
+    }
+    // ---- bin: count, scan, emit ----
+    {
+        StageTimer t(ctx, s, ST_COUNT);
+        launch_bin(false, frames_d, draws_d, ctx->chunk_base_d.as<uint32_t>(), (int)b.draws.size(), b.n_chunks, ctx->tile_count.as<uint32_t>(),
+                   ctx->tile_off.as<uint32_t>(), nullptr, 0, s);
+    }
+    {
+        StageTimer t(ctx, s, ST_SCAN);
+        launch_scan(ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), n_tiles, s);
+    }
+    CU(cudaMemcpyAsync(ctx->total_pinned, ctx->tile_off.as<uint32_t>() + n_tiles, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));   // the pair buffer is sized from the exact total
+    const uint32_t total_pairs = *ctx->total_pinned;
+    CU(ctx->pairs.reserve(((size_t)total_pairs + 1) * sizeof(PairRec)));
+    {
+        StageTimer t(ctx, s, ST_EMIT);
+        launch_bin(true, frames_d, draws_d, ctx->chunk_base_d.as<uint32_t>(), (int)b.draws.size(), b.n_chunks, ctx->tile_count.as<uint32_t>(),
+                   ctx->tile_off.as<uint32_t>(), ctx->pairs.as<PairRec>(), total_pairs, s);
+    }
+    {
+        StageTimer t(ctx, s, ST_RASTER);
+        launch_raster(frames_d, draws_d, ctx->tile_off.as<uint32_t>(), ctx->pairs.as<PairRec>(), n_tiles, tiles_per_frame, s);
+    }
+    {
+        StageTimer t(ctx, s, ST_SHADE);
+        launch_shade(frames_d, draws_d, n, W, H, s);
+    }
+    ctx->stats.kernel_launches += (b.n_chunks ? 2 : 0) + 3;
+    if (post) {
+        if (b.any_auto) {   // 1x1 level of the mip chain of the HDR target, taken before background / SSAO
+            StageTimer t(ctx, s, ST_POST);
+            const float4* src = result->hdr ? result->hdr + npx * first_frame : ctx->hdr.as<float4>();
+            size_t src_stride = npx;
+            int sw = W, sh = H; bool flip = false;
+            while (sw > 1 || sh > 1) {
+                int dw = sw > 1 ? sw >> 1 : 1, dh = sh > 1 ? sh >> 1 : 1;
+                const bool last = dw == 1 && dh == 1;
+                float4* dst = last ? ctx->avg.as<float4>() : (flip ? ctx->mip_b.as<float4>() : ctx->mip_a.as<float4>());
+                size_t dst_stride = last ? 1 : (size_t)dw * dh;
+                launch_downsample(src, sw, sh, dst, n, src_stride, dst_stride, s);
+                ctx->stats.kernel_launches += 1;
+                src = dst; src_stride = dst_stride; sw = dw; sh = dh; flip = !flip;
+            }
+            if (W == 1 && H == 1) CU(cudaMemcpyAsync(ctx->avg.p, src, (size_t)n * 16, cudaMemcpyDeviceToDevice, s));
+        }
+        if (b.any_bg) {
+            StageTimer t(ctx, s, ST_POST);
+            launch_background(frames_d, n, W, H, s);
+            ctx->stats.kernel_launches += 1;
+        }
+        if (b.any_ssao) {
+            StageTimer t(ctx, s, ST_SSAO);
+            launch_ssao(frames_d, n, W, H, s);
+            ctx->stats.kernel_launches += 1;
+        }
+        {
+            StageTimer t(ctx, s, ST_POST);
+            launch_ssao_apply_tonemap(frames_d, n, W, H, s);
+            ctx->stats.kernel_launches += 1;
+        }
+    }
+    CU(cudaGetLastError());
+    ctx->stats.frames_rendered += n;
+    ctx->stats.triangles_submitted += b.n_tris;
+    ctx->stats.triangles_binned = total_pairs;
+    return SLB_OK;
+}
+
+static void collect_times(slb_ctx* ctx) {
+    if (ctx->events.empty()) return;
+    float acc[ST_N] = {0};
+    for (auto& e : ctx->events) {
+        cudaEventSynchronize(e.b);
+        float ms = 0; cudaEventElapsedTime(&ms, e.a, e.b);
+        acc[e.stage] += ms;
+        ctx->event_pool.push_back(e.a); ctx->event_pool.push_back(e.b);
+    }
+    ctx->events.clear();
+    for (int i = 0; i < 8; ++i) ctx->stats.last_kernel_ms[i] = i < ST_N ? acc[i] : 0.0f;
+}
+
+extern "C" int slb_render_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int32_t n_scenes, slb_result* result, int32_t first_frame,
+                                const slb_result* depth_peel, void* stream) {
+    if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
+    if (!scenes || n_scenes <= 0 || !result) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_render_batch: scenes / result missing");
+    if (first_frame < 0 || first_frame + n_scenes > result->n_frames) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_render_batch: frame range exceeds the result");
+    if (depth_peel && (depth_peel->W != result->W || depth_peel->H != result->H || depth_peel->n_frames < first_frame + n_scenes ||
+                       !depth_peel->ptrs[SLB_TARGET_COORD]))
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_render_batch: depth-peel result must hold the coord target at the same size");
+    if (ctx->keep_hdr && !result->hdr) return fail(ctx, SLB_ERR_RUNTIME, "slb_render_batch: SLB_OPT_KEEP_HDR is on but the result was created without it");
+    for (int i = 0; i < n_scenes; ++i) { int rc = validate_scene(ctx, scenes[i], result); if (rc != SLB_OK) return rc; }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    for (int at = 0; at < n_scenes; at += ctx->max_subbatch) {
+        int n = std::min(ctx->max_subbatch, n_scenes - at);
+        int rc = render_subbatch(ctx, scenes + at, n, result, first_frame + at, depth_peel, s);
+        if (rc != SLB_OK) return rc;
+    }
+    if (ctx->time_kernels) collect_times(ctx);
+    return SLB_OK;
+}
+
+extern "C" int slb_render_batch_host(slb_ctx* ctx, const slb_scene_desc* scenes, int32_t n_scenes, uint32_t target_mask,
+                                     void* const host_ptrs[SLB_NUM_TARGETS]) {
+    if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
+    if (!scenes || n_scenes <= 0 || !host_ptrs || target_mask == 0 || (target_mask & ~SLB_TARGETS_ALL))
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_render_batch_host: bad arguments");
+    for (int t = 0; t < SLB_NUM_TARGETS; ++t)
+        if ((target_mask & (1u << t)) && !host_ptrs[t]) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_render_batch_host: host pointer missing for a requested target");
+    CU(cudaSetDevice(ctx->device));
+    const int W = scenes[0].width, H = scenes[0].height;
+    for (int i = 0; i < 2; ++i) {
+        slb_result* r = ctx->slot[i];
+        if (r && (r->W != W || r->H != H || r->mask != target_mask || r->n_frames != ctx->max_subbatch || (ctx->keep_hdr && !r->hdr))) {
+            slb_result_destroy(ctx, r); ctx->slot[i] = nullptr;
+        }
+        if (!ctx->slot[i]) { int rc = slb_result_create(ctx, W, H, ctx->max_subbatch, target_mask, nullptr, &ctx->slot[i]); if (rc != SLB_OK) return rc; }
+        if (!ctx->slot_rendered[i]) { CU(cudaEventCreateWithFlags(&ctx->slot_rendered[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&ctx->slot_copied[i], cudaEventDisableTiming)); }
+    }
+    for (int i = 0; i < n_scenes; ++i) { int rc = validate_scene(ctx, scenes[i], ctx->slot[0]); if (rc != SLB_OK) return rc; }
+    const size_t npx = (size_t)W * H;
+    int k = 0;
+    bool used[2] = {false, false};
+    for (int at = 0; at < n_scenes; at += ctx->max_subbatch, ++k) {
+        const int n = std::min(ctx->max_subbatch, n_scenes - at);
+        const int sl = k & 1;
+        if (used[sl]) CU(cudaStreamWaitEvent(ctx->stream, ctx->slot_copied[sl], 0));   // slot free again?
+        int rc = render_subbatch(ctx, scenes + at, n, ctx->slot[sl], 0, nullptr, ctx->stream);
+        if (rc != SLB_OK) return rc;
+        CU(cudaEventRecord(ctx->slot_rendered[sl], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->slot_rendered[sl], 0));
+        for (int t = 0; t < SLB_NUM_TARGETS; ++t) {
+            if (!(target_mask & (1u << t))) continue;
+            const size_t per = npx * kTargetBpp[t];
+            CU(cudaMemcpyAsync((uint8_t*)host_ptrs[t] + per * at, ctx->slot[sl]->ptrs[t], per * n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            ctx->stats.bytes_d2h += per * n;
+        }
+        CU(cudaEventRecord(ctx->slot_copied[sl], ctx->copy_stream));
+        used[sl] = true;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->time_kernels) collect_times(ctx);
+    return SLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// config 4 helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int slb_diff_sobel_valid_mask(slb_ctx* ctx, const int16_t* instance_index, const float* depth, uint8_t* valid_out,
+                                         int32_t height, int32_t width, void* stream) {
+    if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
+    if (!instance_index || !depth || !valid_out || height <= 0 || width <= 0) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_diff_sobel_valid_mask: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    launch_sobel_valid_mask(instance_index, depth, valid_out, height, width, stream ? (cudaStream_t)stream : ctx->stream);
+    ctx->stats.kernel_launches += 1;
+    CU(cudaGetLastError());
+    return SLB_OK;
+}
+extern "C" int slb_diff_dilate_object_mask(slb_ctx* ctx, const uint8_t* mask, const uint8_t* valid, const float* coords,
+                                           int32_t coord_stride, uint8_t* mask_out, float* coords_out, int32_t height, int32_t width,
+                                           void* stream) {
+    if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
+    if (!mask || !valid || !coords || !mask_out || !coords_out || coord_stride < 3 || height <= 0 || width <= 0)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_diff_dilate_object_mask: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    launch_dilate_object_mask(mask, valid, coords, coord_stride, mask_out, coords_out, height, width, stream ? (cudaStream_t)stream : ctx->stream);
+    ctx->stats.kernel_launches += 1;
+    CU(cudaGetLastError());
+    return SLB_OK;
+}
