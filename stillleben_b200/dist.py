@@ -1,0 +1,108 @@
+"""Multi-GPU plumbing: one process per GPU, scenes sharded by index, shared assets broadcast once.
+
+Scenes of a batch are independent (the reference treats GPUs as independent processes:
+python/src/py_context.cpp:12-52), so the only communication is ONE broadcast of the packed
+read-only asset arena (consolidated vertex / index buffers, material tables, texture images) from
+rank 0 at load time — NCCL over NVLink on the GPU box, gloo in the CPU tests.  There is no
+collective in the steady state.
+"""
+import json
+import os
+
+import numpy as np
+
+from . import abi
+from .desc import ImageData, MaterialData, MeshData
+
+
+def shard_range(n_items, rank, world_size):
+    """Contiguous block of scene indices owned by `rank` (blocks differ by at most one item)."""
+    base, rem = divmod(n_items, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+# ---- asset arena ------------------------------------------------------------------------------
+def pack_meshes(meshes):
+    """Serialise a list of MeshData into (header bytes, flat uint8 arena)."""
+    chunks, metas, off = [], [], 0
+
+    def put(a):
+        nonlocal off
+        a = np.ascontiguousarray(a)
+        b = a.view(np.uint8).reshape(-1)
+        pad = (-len(b)) % 256
+        chunks.append(b)
+        if pad:
+            chunks.append(np.zeros(pad, np.uint8))
+        at = off
+        off += len(b) + pad
+        return at, len(b)
+
+    for m in meshes:
+        meta = {"name": m.name, "submeshes": [tuple(int(x) for x in s) for s in m.submeshes],
+                "bbox_min": np.asarray(m.bbox_min, np.float32).tolist(), "bbox_max": np.asarray(m.bbox_max, np.float32).tolist(),
+                "vertices": put(m.vertices), "n_vertices": len(m.vertices), "indices": put(m.indices),
+                "materials": [vars(x).copy() for x in m.materials], "images": []}
+        for im in m.images:
+            meta["images"].append({"shape": list(im.pixels.shape), "data": put(im.pixels), "wrap_s": im.wrap_s,
+                                   "wrap_t": im.wrap_t, "min_filter": im.min_filter, "mag_filter": im.mag_filter,
+                                   "kind": im.kind})
+        metas.append(meta)
+    arena = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+    return json.dumps(metas).encode(), arena
+
+
+def unpack_meshes(header, arena):
+    metas = json.loads(bytes(header).decode())
+    out = []
+    for meta in metas:
+        vo, vn = meta["vertices"]
+        verts = arena[vo:vo + vn].view(abi.VERTEX_DTYPE).copy()
+        io_, in_ = meta["indices"]
+        idx = arena[io_:io_ + in_].view(np.uint32).copy()
+        images = []
+        for im in meta["images"]:
+            o, n = im["data"]
+            images.append(ImageData(arena[o:o + n].reshape(im["shape"]).copy(), im["wrap_s"], im["wrap_t"], im["min_filter"],
+                                    im["mag_filter"], im["kind"]))
+        mats = [MaterialData(**{k: tuple(v) if isinstance(v, list) else v for k, v in m.items()}) for m in meta["materials"]]
+        out.append(MeshData(verts, idx, [tuple(s) for s in meta["submeshes"]], mats, images,
+                            np.array(meta["bbox_min"], np.float32), np.array(meta["bbox_max"], np.float32), meta["name"]))
+    return out
+
+
+def broadcast_meshes(meshes, src=0, device=None):
+    """Broadcast the mesh pool from rank `src` to every rank (one collective for the arena).
+
+    `meshes` is only read on `src`; other ranks may pass None.  Works with any initialised
+    torch.distributed backend; with NCCL the arena travels GPU-to-GPU over NVLink."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return meshes
+    rank = dist.get_rank()
+    if rank == src:
+        header, arena = pack_meshes(meshes)
+        sizes = torch.tensor([len(header), len(arena)], dtype=torch.int64)
+    else:
+        header, arena = b"", None
+        sizes = torch.zeros(2, dtype=torch.int64)
+    dev = device if device is not None else torch.device("cpu")
+    sizes = sizes.to(dev)
+    dist.broadcast(sizes, src)
+    hn, an = int(sizes[0]), int(sizes[1])
+    payload = torch.empty(hn + an, dtype=torch.uint8, device=dev)
+    if rank == src:
+        payload[:hn] = torch.frombuffer(bytearray(header), dtype=torch.uint8).to(dev)
+        payload[hn:] = torch.from_numpy(arena).to(dev)
+    dist.broadcast(payload, src)
+    if rank == src:
+        return meshes
+    host = payload.cpu().numpy()
+    return unpack_meshes(host[:hn].tobytes(), host[hn:])
