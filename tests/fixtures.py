@@ -1,0 +1,177 @@
+"""Scenes shared by the CPU and GPU tests, built from the committed fixtures in tests/golden/."""
+import os
+
+import numpy as np
+
+from stillleben_b200 import abi, synth
+from stillleben_b200.desc import (ImageData, MaterialData, MeshData, ObjectSpec, SceneSpec, fov_projection, inverted_rigid,
+                                  look_at_pose)
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_cache = {}
+
+
+def load_mesh(name):
+    if name in _cache:
+        return _cache[name]
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    verts = np.ascontiguousarray(z["vertices"]).view(abi.VERTEX_DTYPE).reshape(-1)
+    mats = []
+    for r in z["materials"]:
+        mats.append(MaterialData(tuple(float(x) for x in r[0:4]), tuple(float(x) for x in r[4:8]), float(r[8]), float(r[9]),
+                                 int(r[10]), int(r[11]), int(r[12]), int(r[13]), int(r[14])))
+    images = []
+    i = 0
+    while f"image{i}" in z:
+        s = z[f"image{i}_sampler"]
+        images.append(ImageData(np.ascontiguousarray(z[f"image{i}"]), int(s[0]), int(s[1]), int(s[2]), int(s[3])))
+        i += 1
+    m = MeshData(verts, z["indices"], [tuple(int(x) for x in s) for s in z["submeshes"]], mats, images,
+                 z["bbox_min"].astype(np.float32), z["bbox_max"].astype(np.float32), name)
+    _cache[name] = m
+    return m
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def cube_test_scene(width=640, height=480):
+    """The reference's "vertex indices" test (tests/basic.cpp:375-453): cube.glb at the origin, 640x480,
+    camera at (4,0,0) looking at the origin; a light direction is set (chooseRandomLightDirection there,
+    a fixed one here) so the colour target is not black."""
+    cube = load_mesh("cube_glb_mesh")
+    pose = look_at_pose((4, 0, 0), (0, 0, 0))
+    ldir = np.zeros((3, 3), np.float32)
+    ldir[0] = np.array([-1, -1, -1], np.float32) / np.sqrt(3.0)
+    lcol = np.zeros((3, 3), np.float32)
+    lcol[0] = 3.0
+    return SceneSpec(width, height, fov_projection(width, height), inverted_rigid(pose), [ObjectSpec(cube, instance_index=1)],
+                     light_directions=ldir, light_colors=lcol, manual_exposure=1.0, ssao_enabled=False)
+
+
+def bunny_test_scene(width=640, height=480, lit=False):
+    """The reference's "render" test (tests/basic.cpp:108-261): bunny centred, scaled to diagonal 0.5,
+    placed at (0,0,minimumDistanceForObjectDiameter), instance index 0xFFFF, default (identity) camera
+    pose, default lights (none active), default SSAO on, auto exposure."""
+    bunny = load_mesh("bunny_mesh")
+    pre = synth.normalising_pretransform(bunny, 0.5)
+    P = fov_projection(width, height)
+    diag = 0.5
+    distance = max(P[0, 0] * diag / 2.0, P[1, 1] * diag / 2.0)     # src/pose.cpp:24-34
+    pose = np.eye(4, dtype=np.float32)
+    pose[2, 3] = distance
+    sc = SceneSpec(width, height, P, np.eye(4, dtype=np.float32),
+                   [ObjectSpec(bunny, pose=pose, pretransform=pre, class_index=1, instance_index=0xFFFF)],
+                   manual_exposure=-1.0, ssao_enabled=True)
+    if lit:     # not part of the reference test: a light so that the colour target is not black
+        sc.light_directions[0] = np.array([0.3, 0.5, 0.8], np.float32) / np.linalg.norm([0.3, 0.5, 0.8])
+        sc.light_colors[0] = 3.0
+        sc.ambient_light = (0.2, 0.2, 0.2)
+    return sc
+
+
+def small_tabletop_scene():
+    pool = synth.mesh_pool(5, nu=32, nv=16, tex_size=64)
+    return synth.tabletop_scene(pool, 4242, n_objects=6, width=160, height=120, intrinsics=None)
+
+
+# ---------------------------------------------------------------------------------------------
+# scene variants covering the edge cases of the path (used by the GPU parity tests)
+# ---------------------------------------------------------------------------------------------
+def small_pool():
+    if "pool" not in _cache:
+        _cache["pool"] = synth.mesh_pool(6, nu=48, nv=24, tex_size=64)
+    return _cache["pool"]
+
+
+def alpha_mesh():
+    """A textured blob whose RGBA texture has transparent holes -> exercises the alpha-test discard."""
+    if "alpha" not in _cache:
+        m = synth.shape_mesh("blob", 77, nu=48, nv=24, textured=True, tex_size=64)
+        rgb = m.images[0].pixels
+        yy, xx = np.mgrid[0:64, 0:64]
+        a = np.where(((xx // 8) + (yy // 8)) % 2 == 0, 255, 30).astype(np.uint8)
+        m.images[0] = ImageData(np.ascontiguousarray(np.dstack([rgb, a])))
+        _cache["alpha"] = m
+    return _cache["alpha"]
+
+
+def light_map_data():
+    from stillleben_b200.desc import LightMapData
+    if "lm" not in _cache:
+        eq, sun_dir = synth.procedural_equirect(128, 64, seed=7)
+        _cache["lm"] = LightMapData(eq, [sun_dir.tolist()], [[2.0, 1.9, 1.7]])
+    return _cache["lm"]
+
+
+def variant(name, width=320, height=240):
+    pool = small_pool()
+    base = dict(n_objects=6, width=width, height=height, intrinsics=None)
+    if name == "tabletop":
+        return synth.tabletop_scene(pool, 11, **base)
+    if name == "three_lights":
+        return synth.tabletop_scene(pool, 12, n_lights=3, **base)
+    if name == "ssao":
+        return synth.tabletop_scene(pool, 13, ssao=True, **base)
+    if name == "auto_exposure":
+        return synth.tabletop_scene(pool, 14, manual_exposure=-1.0, **base)
+    if name == "no_plane_no_light":
+        sc = synth.tabletop_scene(pool, 15, plane=False, n_lights=0, **base)
+        return sc
+    if name == "empty":
+        return synth.tabletop_scene(pool, 16, n_objects=0, width=width, height=height, intrinsics=None, plane=False)
+    if name == "ibl":
+        return synth.tabletop_scene(pool, 17, light_map=light_map_data(), ssao=True, **base)
+    if name == "alpha_test":
+        sc = synth.tabletop_scene(pool, 18, **base)
+        m = alpha_mesh()
+        for o in sc.objects[:3]:
+            o.mesh = m
+            o.pretransform = synth.normalising_pretransform(m, 0.3)
+        return sc
+    if name == "sticker":
+        sc = synth.tabletop_scene(pool, 19, **base)
+        st = ImageData(synth.procedural_texture(5, 32), kind=abi.TEXTURE_RECT)
+        o = sc.objects[0]
+        o.sticker_texture = st
+        d = float(np.linalg.norm(o.mesh.bbox_max - o.mesh.bbox_min)) * float(o.pretransform[0, 0])
+        proj = np.eye(4, dtype=np.float32)            # orthographic: (2x/d, 2y/d, z+2, 1)  
+        proj[0, 0] = proj[1, 1] = 2.0 / d
+        proj[2, 3] = 2.0
+        o.sticker_projection = proj
+        o.sticker_range = (-0.5, -0.5, 1.0, 1.0)
+        return sc
+    if name == "background_image":
+        sc = synth.tabletop_scene(pool, 20, plane=False, **base)
+        sc.background_image = ImageData(synth.procedural_texture(9, 96), kind=abi.TEXTURE_RECT, mag_filter=abi.FILTER_NEAREST)
+        return sc
+    if name == "plane_texture":
+        sc = synth.tabletop_scene(pool, 21, **base)
+        sc.background_plane_texture = ImageData(synth.procedural_texture(3, 128))
+        return sc
+    if name == "near_clip":
+        # camera 6 cm above the 3x3 m plane looking along it: the plane crosses the near plane and
+        # extends behind the camera -> homogeneous clipping + guard band
+        sc = synth.tabletop_scene(pool, 22, **base)
+        pose = look_at_pose((0.9, 0.1, 0.06), (0.0, 0.0, 0.10))
+        sc.world_to_cam = inverted_rigid(pose)
+        return sc
+    if name == "predicate":
+        sc = synth.tabletop_scene(pool, 23, **base)
+        sc.objects[1].visible = False
+        sc.objects[2].casts_shadows = False
+        return sc
+    if name == "id_limits":
+        sc = synth.tabletop_scene(pool, 24, **base)
+        sc.objects[0].instance_index = 65535
+        sc.objects[0].class_index = 65535
+        return sc
+    if name == "odd_viewport":
+        return synth.tabletop_scene(pool, 25, n_objects=5, width=203, height=117, intrinsics=None)
+    raise KeyError(name)
+
+
+VARIANTS = ["tabletop", "three_lights", "ssao", "auto_exposure", "no_plane_no_light", "empty", "ibl", "alpha_test", "sticker",
+            "background_image", "plane_texture", "near_clip", "predicate", "id_limits", "odd_viewport"]

@@ -1,0 +1,152 @@
+"""Parity proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs and against the committed golden fixtures. ID maps bit-exact; float targets within 1e-3 relative
+(tolerances in tests/parity.py); RGBA8 within 1 LSB. The colour targets may differ in a handful of
+pixels where a 4x4 PCF shadow tap sits exactly on its compare threshold (budget: 0.1 % of the pixels)."""
+import numpy as np
+import pytest
+
+import fixtures
+import oracle_util as ou
+import parity
+from stillleben_b200 import abi, lib
+
+pytestmark = pytest.mark.gpu
+
+OUTLIERS = dict(rgb_outlier_frac=1e-3, hdr_outlier_frac=1e-3)
+
+
+def render_gpu(ctx, scene, mask=abi.TARGETS_ALL, peel=None):
+    ctx.set_option(abi.OPT_KEEP_HDR, 1)
+    res = ctx.render([scene], target_mask=mask, depth_peel=peel)
+    ctx.synchronize()
+    out = res.frame_dict(0)
+    out["hdr"] = res.hdr(0)
+    ctx.set_option(abi.OPT_KEEP_HDR, 0)
+    return out, res
+
+
+def feed_gpu_lightmap_to_oracle(ctx, assets, scene):
+    """Both sides render with the SAME light-map textures (the precompute has its own parity test)."""
+    if scene.light_map is not None and id(scene.light_map) not in assets.lightmap_maps:
+        env0, irr, pre, lut = ctx.read_lightmap(scene.light_map)
+        assets.set_lightmap_maps(scene.light_map, env0, irr, pre, lut)
+
+
+@pytest.mark.parametrize("name", fixtures.VARIANTS)
+def test_variant_matches_oracle(gpu_ctx, name):
+    scene = fixtures.variant(name)
+    assets = ou.OracleAssets()
+    feed_gpu_lightmap_to_oracle(gpu_ctx, assets, scene)
+    gpu, _ = render_gpu(gpu_ctx, scene)
+    ref = ou.render(scene, assets)
+    parity.assert_parity(gpu, ref, **OUTLIERS)
+
+
+def test_config1_cube_plumbing(gpu_ctx):
+    from stillleben_b200 import synth
+    scene = synth.config1_scene()
+    gpu, _ = render_gpu(gpu_ctx, scene)
+    ref = ou.render(scene)
+    parity.assert_parity(gpu, ref)
+    assert len(np.unique(gpu["vertex_index"][..., :3])) == 5
+
+
+@pytest.mark.parametrize("golden,scene_fn", [("golden_cube", lambda: fixtures.cube_test_scene(320, 240)),
+                                              ("golden_bunny", lambda: fixtures.bunny_test_scene(320, 240, lit=True)),
+                                              ("golden_tabletop", fixtures.small_tabletop_scene)])
+def test_matches_committed_golden(gpu_ctx, golden, scene_fn):
+    gpu, _ = render_gpu(gpu_ctx, scene_fn())
+    ref = fixtures.load_golden(golden)
+    parity.assert_parity(gpu, ref, **OUTLIERS)
+
+
+def test_reference_known_answers_on_gpu(gpu_ctx):
+    # tests/basic.cpp:375-453 (cube) and :108-261 (bunny) asserted on the CUDA output
+    gpu, _ = render_gpu(gpu_ctx, fixtures.cube_test_scene())
+    vi = gpu["vertex_index"][..., :3].reshape(-1, 3)
+    assert tuple(vi[0]) == (0, 0, 0) and vi.max() > 10 and len(np.unique(vi)) == 5
+    fg = vi[:, 0] != 0
+    v = vi[fg]
+    assert (v[:, 0] != v[:, 1]).all() and (v[:, 0] != v[:, 2]).all() and (v[:, 1] != v[:, 2]).all()
+    np.testing.assert_allclose(gpu["barycentric"][..., :3].reshape(-1, 3)[fg].sum(-1), 1.0, rtol=1e-5)
+    gpu, _ = render_gpu(gpu_ctx, fixtures.bunny_test_scene())
+    n = 640 * 480
+    assert (gpu["rgb"][..., 3] != 0).sum() > 10
+    assert 10 < (gpu["class_index"] != 0).sum() < 0.5 * n
+    assert set(np.unique(gpu["instance_index"])) == {0, 65535}
+
+
+def test_depth_peel_second_layer(gpu_ctx):
+    # render_shader.frag:229-233: the second pass keeps only fragments behind the first layer
+    scene = fixtures.variant("tabletop")
+    first, res1 = render_gpu(gpu_ctx, scene)
+    second, _ = render_gpu(gpu_ctx, scene, peel=res1)
+    ref2 = ou.render(scene, peel=first["coord"])
+    parity.assert_parity(second, ref2, **OUTLIERS)
+    both = (first["vertex_index"][..., 0] != 0) & (second["vertex_index"][..., 0] != 0)
+    assert both.sum() > 100
+    assert (second["coord"][..., 3][both] > first["coord"][..., 3][both]).all()
+
+
+def test_six_target_subset_equals_full(gpu_ctx):
+    scene = fixtures.variant("three_lights")
+    res6 = gpu_ctx.render([scene], target_mask=abi.TARGETS_SIX)
+    res8 = gpu_ctx.render([scene], target_mask=abi.TARGETS_ALL)
+    gpu_ctx.synchronize()
+    a, b = res6.frame_dict(0), res8.frame_dict(0)
+    assert set(a) == {"rgb", "coord", "class_index", "instance_index", "normals"}
+    for k in a:
+        assert (a[k].view(np.uint8) == b[k].view(np.uint8)).all(), k
+
+
+def test_ragged_batch_equals_single_renders(gpu_ctx):
+    """Scenes with different object counts / features in one call; each frame equals its solo render, and
+    the result does not depend on how the batch is split into sub-batches."""
+    names = ["tabletop", "empty", "three_lights", "predicate", "no_plane_no_light", "alpha_test", "tabletop"]
+    scenes = [fixtures.variant(n) for n in names]
+    gpu_ctx.set_option(abi.OPT_MAX_SUBBATCH, 3)
+    batch = gpu_ctx.render(scenes, target_mask=abi.TARGETS_ALL)
+    gpu_ctx.synchronize()
+    gpu_ctx.set_option(abi.OPT_MAX_SUBBATCH, 16)
+    for i, sc in enumerate(scenes):
+        solo = gpu_ctx.render([sc], target_mask=abi.TARGETS_ALL)
+        gpu_ctx.synchronize()
+        a, b = batch.frame_dict(i), solo.frame_dict(0)
+        for k in a:
+            assert (a[k].view(np.uint8) == b[k].view(np.uint8)).all(), (names[i], k)
+
+
+def test_render_host_equals_device_path(gpu_ctx):
+    scenes = [fixtures.variant(n) for n in ("tabletop", "three_lights", "predicate")]
+    dev = gpu_ctx.render(scenes, target_mask=abi.TARGETS_SIX)
+    gpu_ctx.synchronize()
+    host = {}
+    for t, (dt, ch) in enumerate(abi.TARGET_FORMATS):
+        if abi.TARGETS_SIX & (1 << t):
+            host[t] = np.zeros((3, 240, 320, ch), dt)
+    gpu_ctx.set_option(abi.OPT_MAX_SUBBATCH, 2)     # forces two internal sub-batches and both staging slots
+    gpu_ctx.render_host(gpu_ctx.descs(scenes), host, abi.TARGETS_SIX)
+    gpu_ctx.set_option(abi.OPT_MAX_SUBBATCH, 16)
+    for t, a in host.items():
+        assert (a.view(np.uint8) == dev.numpy(t).view(np.uint8)).all(), abi.TARGET_NAMES[t]
+
+
+def test_full_hd_frame(gpu_ctx):
+    # config C5 geometry of the viewport: 1920x1080, IBL + SSAO + 3 shadow lights (small object count here)
+    from stillleben_b200 import synth
+    scene = synth.tabletop_scene(fixtures.small_pool(), 31, n_objects=8, width=1920, height=1080, intrinsics=None, n_lights=3, ssao=True)
+    gpu, _ = render_gpu(gpu_ctx, scene)
+    ref = ou.render(scene)
+    parity.assert_parity(gpu, ref, **OUTLIERS)
+
+
+def test_error_convention(gpu_ctx):
+    scene = fixtures.variant("tabletop")
+    scene.objects[0].instance_index = 70000          # object.cpp:376-382 -> std::invalid_argument -> ValueError
+    with pytest.raises(ValueError):
+        gpu_ctx.render([scene])
+    res = lib.Result(gpu_ctx, 64, 64, 1)
+    with pytest.raises(ValueError):                  # viewport mismatch
+        gpu_ctx.render([fixtures.variant("tabletop")], result=res)
+    with pytest.raises(ValueError):
+        lib.Result(gpu_ctx, 0, 64, 1)

@@ -1,0 +1,72 @@
+"""Host-side logic: camera matrices, descriptor marshalling, sharding and the asset arena."""
+import ctypes as C
+
+import numpy as np
+
+from stillleben_b200 import abi, desc, dist, synth
+
+
+def test_intrinsics_projection_matches_closed_form():
+    # SURVEY Appendix A.2 (src/scene.cpp:222-253)
+    fx, fy, cx, cy, W, H = 1066.778, 1067.487, 312.9869, 241.3109, 640, 480
+    P = desc.intrinsics_projection(fx, fy, cx, cy, W, H)
+    p = np.array([0.1, -0.05, 1.3, 1.0], np.float64)
+    c = P.astype(np.float64) @ p
+    ndc = c[:3] / c[3]
+    assert abs((ndc[0] * 0.5 + 0.5) * W - (fx * p[0] / p[2] + cx)) < 1e-3
+    assert abs((ndc[1] * 0.5 + 0.5) * H - (fy * p[1] / p[2] + cy)) < 1e-3
+    n, f = 0.1, 10.0
+    assert abs(ndc[2] - ((f + n) / (f - n) - 2 * f * n / ((f - n) * p[2]))) < 1e-5
+    assert c[3] == p[2]
+
+
+def test_look_at_is_rigid_and_points_forward():
+    m = desc.look_at_pose((4, 0, 0), (0, 0, 0))
+    np.testing.assert_allclose(m[:3, :3].T @ m[:3, :3], np.eye(3), atol=1e-6)
+    np.testing.assert_allclose(m[:3, 2], [-1, 0, 0], atol=1e-6)       # +z forward
+    inv = desc.inverted_rigid(m)
+    np.testing.assert_allclose(inv @ m, np.eye(4), atol=1e-6)
+
+
+def test_desc_batch_marshalling():
+    pool = synth.mesh_pool(2, nu=8, nv=4, tex_size=8)
+    sc = synth.tabletop_scene(pool, 1, n_objects=3)
+    sc.objects[1].instance_index = 0        # auto -> position in scene, 1-based (scene.cpp:285-287)
+    handles = {}
+    b = desc.DescBatch([sc], lambda o: handles.setdefault(id(o), 1000 + len(handles)))
+    d = b.scenes[0]
+    assert (d.width, d.height, d.n_objects) == (640, 480, 3)
+    assert d.objects[1].instance_index == 2
+    assert d.objects[0].mesh == handles[id(sc.objects[0].mesh)]
+    # column-major storage of a row-major numpy matrix
+    assert abs(d.projection[11] - sc.projection[3, 2]) < 1e-7 and d.projection[11] == 1.0
+    assert d.background_plane_size[0] == 3.0 and d.light_map is None
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 1024, 1025):
+        for w in (1, 2, 3, 8):
+            seen = []
+            for r in range(w):
+                lo, hi = dist.shard_range(n, r, w)
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))
+
+
+def test_asset_arena_round_trip():
+    pool = synth.mesh_pool(3, nu=16, nv=8, tex_size=16)
+    header, arena = dist.pack_meshes(pool)
+    back = dist.unpack_meshes(header, arena)
+    assert len(back) == len(pool)
+    for a, b in zip(pool, back):
+        assert (a.vertices == b.vertices).all() and (a.indices == b.indices).all()
+        assert a.submeshes == b.submeshes
+        assert all((x.pixels == y.pixels).all() for x, y in zip(a.images, b.images))
+        assert a.geometry_bytes() == b.geometry_bytes()
+
+
+def test_vertex_dtype_is_reference_layout():
+    # src/mesh_tools/consolidate.cpp:53-61
+    dt = abi.VERTEX_DTYPE
+    assert dt.itemsize == 68
+    assert [dt.fields[k][1] for k in ("position", "uv", "color", "tangent", "vertex_index", "normal")] == [0, 12, 20, 36, 52, 56]
