@@ -124,6 +124,32 @@ __device__ __forceinline__ bool setup_prim(const float* __restrict__ mvp, float3
     return true;
 }
 
+// Sub-triangle k of the (possibly clipped) primitive with its three vertices returned BY VALUE, so the
+// common unclipped case (k == 1) stays in registers; only the clipped case touches local arrays.
+static __device__ __noinline__ bool setup_subtri_clipped(const ClipV c[3], int need, float hw, float hh, int k, PolyV& a, PolyV& b,
+                                                         PolyV& cc) {
+    PrimSetup ps;
+    if (!setup_clipped(c, need, hw, hh, ps)) return false;
+    if (k < 1 || k + 1 >= ps.n) return false;
+    a = ps.v[0]; b = ps.v[k]; cc = ps.v[k + 1];
+    return true;
+}
+__device__ __forceinline__ bool setup_subtri(const float* __restrict__ mvp, float3 p0, float3 p1, float3 p2, int W, int H, int k,
+                                             PolyV& a, PolyV& b, PolyV& cc) {
+    ClipV c[3];
+    xform_clip(mvp, p0.x, p0.y, p0.z, c[0]);
+    xform_clip(mvp, p1.x, p1.y, p1.z, c[1]);
+    xform_clip(mvp, p2.x, p2.y, p2.z, c[2]);
+    if (frustum_code(c[0]) & frustum_code(c[1]) & frustum_code(c[2])) return false;
+    int need = need_mask(c[0]) | need_mask(c[1]) | need_mask(c[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { c[i].b[0] = c[i].b[1] = c[i].b[2] = 0.0f; c[i].b[i] = 1.0f; }
+    const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+    if (need) return setup_subtri_clipped(c, need, hw, hh, k, a, b, cc);
+    if (k != 1) return false;
+    return project_vertex(c[0], hw, hh, a) && project_vertex(c[1], hw, hh, b) && project_vertex(c[2], hw, hh, cc);
+}
+
 __device__ __forceinline__ long long edge_fn(int ax, int ay, int bx, int by, int px, int py) {
     return (long long)(bx - ax) * (long long)(py - ay) - (long long)(by - ay) * (long long)(px - ax);
 }

@@ -59,7 +59,8 @@ __device__ __forceinline__ float4 tex_fetch(const DTexture& t, int level, int lw
     int yi = wrap_index(y, lh, t.wrap_t, border);
     if (border) return make_float4(0.f, 0.f, 0.f, 0.f);
     uchar4 p = __ldg(reinterpret_cast<const uchar4*>(t.px) + t.level_off[level] + (size_t)yi * lw + xi);
-    return make_float4(p.x / 255.0f, p.y / 255.0f, p.z / 255.0f, p.w / 255.0f);
+    const float k = 1.0f / 255.0f;
+    return make_float4(p.x * k, p.y * k, p.z * k, p.w * k);
 }
 __device__ __forceinline__ float4 tex_sample_level(const DTexture& t, int level, float u, float v, bool normalised, bool linear) {
     int lw = max(1, t.w >> level), lh = max(1, t.h >> level);
@@ -220,9 +221,8 @@ struct FragIn {
 struct FragOut { float4 color, objc, camc, normal; };
 
 #define SLB_LERP(field) (vs[0].field * bary[0] + vs[1].field * bary[1] + vs[2].field * bary[2])
-__device__ __forceinline__ void interpolate(const SubTri& st, const PrimSetup& ps, int k, const VSOut vs[3], int px, int py,
-                                            bool want_derivs, FragIn& in, float bary[3]) {
-    const PolyV &a = ps.v[0], &b = ps.v[k], &c = ps.v[k + 1];
+__device__ __forceinline__ void interpolate(const SubTri& st, const PolyV& a, const PolyV& b, const PolyV& c, const VSOut vs[3],
+                                            int px, int py, bool want_derivs, FragIn& in, float bary[3]) {
     subtri_bary(st, a, b, c, px, py, bary);
     in.u = SLB_LERP(u); in.v = SLB_LERP(v);
     in.nW = SLB_LERP(nW); in.tW = SLB_LERP(tW); in.bW = SLB_LERP(bW);
@@ -247,7 +247,8 @@ __device__ __forceinline__ void interpolate(const SubTri& st, const PrimSetup& p
 __device__ __forceinline__ float4 sample_mat(const DTexture* t, const FragIn& in) {
     return tex_sample_2d(*t, in.u, in.v, in.u_dx, in.v_dx, in.u_dy, in.v_dy);
 }
-__device__ __forceinline__ float4 to_linear(float4 c) { return make_float4(powf(c.x, 2.2f), powf(c.y, 2.2f), powf(c.z, 2.2f), c.w); }
+__device__ __forceinline__ float pow22(float x) { return x > 0.0f ? exp2f(2.2f * __log2f(x)) : 0.0f; }
+__device__ __forceinline__ float4 to_linear(float4 c) { return make_float4(pow22(c.x), pow22(c.y), pow22(c.z), c.w); }
 __device__ __forceinline__ bool draw_has_textures(const DDraw& d) { return d.tex[0] || d.tex[1] || d.tex[2] || d.tex[3] || d.tex[4]; }
 
 // base colour incl. alpha (render_shader.frag:237-246)
@@ -269,20 +270,26 @@ __device__ __forceinline__ float GeometrySchlickGGX(float NdotV, float roughness
     return NdotV / (NdotV * (1.0f - k) + k);
 }
 
-// sampler2DArrayShadow tap: linear filter of (ref <= stored), clamp-to-edge (render_shader.frag:321-337)
-__device__ __forceinline__ float shadow_tap(const uint32_t* __restrict__ map, float u, float v, float ref) {
-    const int N = SLB_SHADOW_RES;
+// sampler2DArrayShadow (render_shader.frag:321-337): each tap is a linear filter of the comparison
+// `ref <= stored` with stored = d24 / 16777215. All 16 taps of a light share `ref`, so the comparison is
+// turned into an integer one ONCE: shadow_threshold() returns the smallest d24 whose float quotient
+// reaches ref (exact, the quotient is monotonic in d24) and every tap compares integers.
+__device__ __forceinline__ uint32_t shadow_threshold(float ref) {
+    if (!(ref == ref)) return 0x1000000u;              // NaN never passes
     ref = clampf(ref, 0.0f, 1.0f);
+    int d = max(0, (int)floorf(ref * 16777215.0f) - 2);
+    while (d <= 0xFFFFFF && __fdiv_rn((float)d, 16777215.0f) < ref) ++d;
+    return (uint32_t)d;
+}
+__device__ __forceinline__ float shadow_tap(const uint32_t* __restrict__ map, float u, float v, uint32_t thr) {
+    const int N = SLB_SHADOW_RES;
     float x = u * N - 0.5f, y = v * N - 0.5f;
     float fx = floorf(x), fy = floorf(y);
     float a = x - fx, b = y - fy;
     int i0 = (int)fx, j0 = (int)fy;
     int i1 = min(max(i0 + 1, 0), N - 1), j1 = min(max(j0 + 1, 0), N - 1);
     i0 = min(max(i0, 0), N - 1); j0 = min(max(j0, 0), N - 1);
-    auto cmp = [&](int i, int j) {
-        float stored = (float)min(__ldg(map + (size_t)j * N + i), 0xFFFFFFu) / 16777215.0f;
-        return ref <= stored ? 1.0f : 0.0f;
-    };
+    auto cmp = [&](int i, int j) { return min(__ldg(map + (size_t)j * N + i), 0xFFFFFFu) >= thr ? 1.0f : 0.0f; };
     return cmp(i0, j0) * ((1 - a) * (1 - b)) + cmp(i1, j0) * (a * (1 - b)) + cmp(i0, j1) * ((1 - a) * b) + cmp(i1, j1) * (a * b);
 }
 
@@ -322,7 +329,8 @@ __device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, 
     f3 c_diff = bc * (1.0f - 0.04f) * (1.0f - metallic);
     f3 F0 = mix3(mk3(0.04f, 0.04f, 0.04f), bc, metallic);
     f3 Fr = max3(mk3(1.0f - roughness, 1.0f - roughness, 1.0f - roughness), F0) - F0;
-    f3 k_S = F0 + Fr * powf(1.0f - NoV, 5.0f);
+    const float omv = 1.0f - NoV, omv2 = omv * omv;
+    f3 k_S = F0 + Fr * (omv2 * omv2 * omv);
 
     const float shadowMapScale = 1.0f / (float)SLB_SHADOW_RES;
 #pragma unroll 1
@@ -332,9 +340,10 @@ __device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, 
         float pcx = 0.5f * (pc.x / pc.w) + 0.5f, pcy = 0.5f * (pc.y / pc.w) + 0.5f, pcz = 0.5f * (pc.z / pc.w) + 0.5f;
         float inverseShadow = 0.0f;
         const uint32_t* map = f.shadowMap[i];
+        const uint32_t thr = shadow_threshold(pcz - 0.00003f);
         for (int yy = 0; yy < 4; ++yy)
             for (int xx = 0; xx < 4; ++xx)
-                inverseShadow += shadow_tap(map, pcx + (-1.5f + xx) * shadowMapScale, pcy + (-1.5f + yy) * shadowMapScale, pcz - 0.00003f);
+                inverseShadow += shadow_tap(map, pcx + (-1.5f + xx) * shadowMapScale, pcy + (-1.5f + yy) * shadowMapScale, thr);
         inverseShadow /= 16.0f;
 
         f3 L = normalize3(mk3(-f.lightDir[i][0], -f.lightDir[i][1], -f.lightDir[i][2]));

@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(256) k_background(const DFrame* __restrict__ f
         uint32_t d24 = (key == SLB_KEY_EMPTY) ? 0xFFFFFFu : (uint32_t)(key >> 40);
         if (!(quad_d24 < d24)) return;
         const DTexture& bg = *f.bg_image;
-        float tx = ((px + 0.5f) / W), ty = 1.0f - ((py + 0.5f) / H);
-        int ix = (int)(tx * bg.w), iy = (int)(ty * bg.h);
+        // exact division / multiplication: the texel index is a floor of this value
+        float tx = __fdiv_rn(px + 0.5f, (float)W), ty = __fsub_rn(1.0f, __fdiv_rn(py + 0.5f, (float)H));
+        int ix = (int)__fmul_rn(tx, (float)bg.w), iy = (int)__fmul_rn(ty, (float)bg.h);
         float4 c = tex_sample_rect(bg, (float)ix, (float)iy);
         f.hdr[p] = make_float4(c.x, c.y, c.z, 0.0f);
     } else if (f.lm) {

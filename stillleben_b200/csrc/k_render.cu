@@ -196,15 +196,15 @@ __device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint3
     const uint32_t* ip = d.idx + 3 * (size_t)tri;
     uint32_t i[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
     float4 p0 = __ldg(d.pos4 + i[0]), p1 = __ldg(d.pos4 + i[1]), p2 = __ldg(d.pos4 + i[2]);
-    PrimSetup ps;
-    if (!setup_prim(d.mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), f.W, f.H, ps))
+    PolyV a, b, c;
+    if (!setup_subtri(d.mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), f.W, f.H, k, a, b, c))
         return true;
     SubTri st;
-    if (k + 1 >= ps.n || !make_subtri(ps, k, st)) return true;
+    if (!make_subtri(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, st)) return true;
     VSOut vs[3]; uint32_t vid;
     for (int j = 0; j < 3; ++j) vertex_stage(f, d, i[j], vs[j], vid);
     FragIn in; float bary[3];
-    interpolate(st, ps, k, vs, px, py, d.tex[0] != nullptr, in, bary);
+    interpolate(st, a, b, c, vs, px, py, d.tex[0] != nullptr, in, bary);
     if (f.peel && in.objc.w - 0.00001f <= f.peel[((size_t)py * f.W + px) * 4 + 3]) return true;
     if ((d.flags & DRAW_FRAG_TEST) && base_color(d, in).w < 0.5f) return true;
     return false;
@@ -329,35 +329,93 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DFrame* 
 // ---------------------------------------------------------------------------------------------
 // shadow pass: depth only, front faces culled (render_pass.cpp:426-460, shadow_shader.vert:10-13)
 // ---------------------------------------------------------------------------------------------
+struct ShadowBig { int ax, ay, bx, by, cx, cy; float az, bz, cz; int px0, py0, px1, py1; };
+#define SLB_SHADOW_QUEUE 32
+#define SLB_SHADOW_BIG_AREA 1024   // bounding boxes above this many pixels are walked by the whole block
+
+// rasterise one sub-triangle into the d24 map: edge functions evaluated once at the first pixel of the
+// box and stepped exactly in 64-bit integers (same values as the contract's per-pixel evaluation)
+__device__ __forceinline__ void shadow_raster(const SubTri& st, uint32_t* __restrict__ map, int px0, int py0, int px1, int py1,
+                                              int start, int stride) {
+    const int N = SLB_SHADOW_RES;
+    const int cx0 = px0 * 256 + 128, cy0 = py0 * 256 + 128;
+    const long long r0 = st.s * edge_fn(st.bx, st.by, st.cx, st.cy, cx0, cy0) + st.bias0;
+    const long long r1 = st.s * edge_fn(st.cx, st.cy, st.ax, st.ay, cx0, cy0) + st.bias1;
+    const long long r2 = st.s * edge_fn(st.ax, st.ay, st.bx, st.by, cx0, cy0) + st.bias2;
+    const long long dx0 = (long long)(-st.s * (st.cy - st.by)) * 256, dy0 = (long long)(st.s * (st.cx - st.bx)) * 256;
+    const long long dx1 = (long long)(-st.s * (st.ay - st.cy)) * 256, dy1 = (long long)(st.s * (st.ax - st.cx)) * 256;
+    const long long dx2 = (long long)(-st.s * (st.by - st.ay)) * 256, dy2 = (long long)(st.s * (st.bx - st.ax)) * 256;
+    const float dzb = __fsub_rn(st.bz, st.az), dzc = __fsub_rn(st.cz, st.az);
+    auto plot = [&](long long e1, long long e2, int x, int y) {
+        long long w1 = e1 - st.bias1, w2 = e2 - st.bias2;
+        if (st.s < 0) { w1 = -w1; w2 = -w2; }
+        float q1 = __fmul_rn(__ll2float_rn(w1), st.inv2A), q2 = __fmul_rn(__ll2float_rn(w2), st.inv2A);
+        float z = __fmaf_rn(q2, dzc, __fmaf_rn(q1, dzb, st.az));
+        z = fminf(fmaxf(z, 0.0f), 1.0f);
+        atomicMin(map + (size_t)y * N + x, __float2uint_rn(__fmul_rn(z, 16777215.0f)));
+    };
+    if (stride == 1) {   // one thread walks the whole box: pure additions per pixel
+        long long a0 = r0, a1 = r1, a2 = r2;
+        for (int y = py0; y <= py1; ++y, a0 += dy0, a1 += dy1, a2 += dy2) {
+            long long e0 = a0, e1 = a1, e2 = a2;
+            for (int x = px0; x <= px1; ++x, e0 += dx0, e1 += dx1, e2 += dx2)
+                if ((e0 | e1 | e2) >= 0) plot(e1, e2, x, y);
+        }
+        return;
+    }
+    const int w = px1 - px0 + 1, n = w * (py1 - py0 + 1);
+    for (int i = start; i < n; i += stride) {
+        const int ix = i % w, iy = i / w;
+        const long long e0 = r0 + dx0 * ix + dy0 * iy, e1 = r1 + dx1 * ix + dy1 * iy, e2 = r2 + dx2 * ix + dy2 * iy;
+        if ((e0 | e1 | e2) >= 0) plot(e1, e2, px0 + ix, py0 + iy);
+    }
+}
+
 __global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_shadow(const DShadowDraw* __restrict__ sdraws,
                                                             const uint32_t* __restrict__ chunk_base, int n_draws) {
     __shared__ float s_mvp[16];
     __shared__ uint32_t s_draw;
-    if (threadIdx.x == 0) s_draw = find_draw(chunk_base, n_draws, blockIdx.x);
+    __shared__ ShadowBig s_big[SLB_SHADOW_QUEUE];
+    __shared__ int s_nbig;
+    if (threadIdx.x == 0) { s_draw = find_draw(chunk_base, n_draws, blockIdx.x); s_nbig = 0; }
     __syncthreads();
     const DShadowDraw& d = sdraws[s_draw];
     if (threadIdx.x < 16) s_mvp[threadIdx.x] = d.mvp[threadIdx.x];
     __syncthreads();
     const uint32_t tri = (blockIdx.x - __ldg(chunk_base + s_draw)) * SLB_SETUP_CHUNK + threadIdx.x;
-    if (tri >= d.n_tris) return;
     const int N = SLB_SHADOW_RES;
-    const uint32_t* ip = d.idx + 3 * (size_t)tri;
-    uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
-    float4 p0 = __ldg(d.pos4 + i0), p1 = __ldg(d.pos4 + i1), p2 = __ldg(d.pos4 + i2);
-    PrimSetup ps;
-    if (!setup_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), N, N, ps)) return;
-    for (int k = 1; k + 1 < ps.n; ++k) {
-        SubTri st;
-        if (!make_subtri(ps, k, st)) continue;
-        if (st.twoA < 0) continue;   // cull FRONT faces
-        int px0, py0, px1, py1;
-        if (!subtri_pixel_bbox(st, N, N, px0, py0, px1, py1)) continue;
-        for (int py = py0; py <= py1; ++py)
-            for (int px = px0; px <= px1; ++px) {
-                long long w0, w1, w2; subtri_weights(st, px, py, w0, w1, w2);
-                if (!subtri_covers(st, w0, w1, w2)) continue;
-                atomicMin(d.map + (size_t)py * N + px, subtri_depth24(st, w1, w2));
+    if (tri < d.n_tris) {
+        const uint32_t* ip = d.idx + 3 * (size_t)tri;
+        uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+        float4 p0 = __ldg(d.pos4 + i0), p1 = __ldg(d.pos4 + i1), p2 = __ldg(d.pos4 + i2);
+        PrimSetup ps;
+        if (setup_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), N, N, ps)) {
+            for (int k = 1; k + 1 < ps.n; ++k) {
+                SubTri st;
+                if (!make_subtri(ps, k, st)) continue;
+                if (st.twoA < 0) continue;   // cull FRONT faces (render_pass.cpp:428-429)
+                int px0, py0, px1, py1;
+                if (!subtri_pixel_bbox(st, N, N, px0, py0, px1, py1)) continue;
+                if ((px1 - px0 + 1) * (py1 - py0 + 1) > SLB_SHADOW_BIG_AREA) {
+                    int q = atomicAdd(&s_nbig, 1);
+                    if (q < SLB_SHADOW_QUEUE) {
+                        ShadowBig& e = s_big[q];
+                        e.ax = st.ax; e.ay = st.ay; e.bx = st.bx; e.by = st.by; e.cx = st.cx; e.cy = st.cy;
+                        e.az = st.az; e.bz = st.bz; e.cz = st.cz; e.px0 = px0; e.py0 = py0; e.px1 = px1; e.py1 = py1;
+                        continue;
+                    }
+                }
+                shadow_raster(st, d.map, px0, py0, px1, py1, 0, 1);
             }
+        }
+    }
+    __syncthreads();
+    const int nbig = min(s_nbig, SLB_SHADOW_QUEUE);
+    for (int q = 0; q < nbig; ++q) {
+        const ShadowBig& e = s_big[q];
+        SubTri st;
+        make_subtri(e.ax, e.ay, e.bx, e.by, e.cx, e.cy, e.az, e.bz, e.cz, st);
+        shadow_raster(st, d.map, e.px0, e.py0, e.px1, e.py1, threadIdx.x, SLB_SETUP_CHUNK);
     }
 }
 
@@ -397,15 +455,15 @@ __global__ void __launch_bounds__(256) k_shade(const DFrame* __restrict__ frames
         const uint32_t* ip = d.idx + 3 * (size_t)tri;
         uint32_t i[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
         float4 p0 = __ldg(d.pos4 + i[0]), p1 = __ldg(d.pos4 + i[1]), p2 = __ldg(d.pos4 + i[2]);
-        PrimSetup ps;
+        PolyV va, vb, vc;
         SubTri st;
-        if (setup_prim(d.mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), W, H, ps) &&
-            k + 1 < ps.n && make_subtri(ps, k, st)) {
+        if (setup_subtri(d.mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), W, H, k, va, vb, vc) &&
+            make_subtri(va.X, va.Y, vb.X, vb.Y, vc.X, vc.Y, va.z, vb.z, vc.z, st)) {
             VSOut vs[3]; uint32_t vid[3];
 #pragma unroll
             for (int j = 0; j < 3; ++j) vertex_stage(f, d, i[j], vs[j], vid[j]);
             FragIn in; float bary[3];
-            interpolate(st, ps, k, vs, px, py, draw_has_textures(d), in, bary);
+            interpolate(st, va, vb, vc, vs, px, py, draw_has_textures(d), in, bary);
             FragOut o;
             fragment_stage(f, d, in, o);
             hdr = o.color; coord = o.objc; camc = o.camc; nrm = o.normal;
