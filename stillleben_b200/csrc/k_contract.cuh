@@ -105,7 +105,7 @@ static __device__ __noinline__ bool setup_clipped(const ClipV c[3], int need, fl
 
 // clip + viewport + snap. Returns false if the primitive is culled.
 __device__ __forceinline__ bool setup_prim(const float* __restrict__ mvp, float3 p0, float3 p1, float3 p2, int W, int H,
-                                           PrimSetup& ps) {
+                                           PrimSetup& ps, bool* clipped = nullptr) {
     ClipV c[3];
     xform_clip(mvp, p0.x, p0.y, p0.z, c[0]);
     xform_clip(mvp, p1.x, p1.y, p1.z, c[1]);
@@ -116,6 +116,7 @@ __device__ __forceinline__ bool setup_prim(const float* __restrict__ mvp, float3
 #pragma unroll
     for (int i = 0; i < 3; ++i) { c[i].b[0] = c[i].b[1] = c[i].b[2] = 0.0f; c[i].b[i] = 1.0f; }
     const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+    if (clipped) *clipped = need != 0;
     if (need) return setup_clipped(c, need, hw, hh, ps);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -134,20 +135,33 @@ static __device__ __noinline__ bool setup_subtri_clipped(const ClipV c[3], int n
     a = ps.v[0]; b = ps.v[k]; cc = ps.v[k + 1];
     return true;
 }
-__device__ __forceinline__ bool setup_subtri(const float* __restrict__ mvp, float3 p0, float3 p1, float3 p2, int W, int H, int k,
-                                             PolyV& a, PolyV& b, PolyV& cc) {
+// Fast path of the per-pixel re-setup: returns 1 with (a,b,cc) filled when the primitive needs no clipping
+// (then k must be 1), 0 when it is culled, and -1 when it needs clipping (the caller then fetches the
+// binner's ClipRec or falls back to setup_subtri_clipped through resetup_clipped()).
+__device__ __forceinline__ int setup_subtri_fast(const float* __restrict__ mvp, float3 p0, float3 p1, float3 p2, int W, int H, int k,
+                                                 PolyV& a, PolyV& b, PolyV& cc) {
     ClipV c[3];
     xform_clip(mvp, p0.x, p0.y, p0.z, c[0]);
     xform_clip(mvp, p1.x, p1.y, p1.z, c[1]);
     xform_clip(mvp, p2.x, p2.y, p2.z, c[2]);
-    if (frustum_code(c[0]) & frustum_code(c[1]) & frustum_code(c[2])) return false;
+    if (frustum_code(c[0]) & frustum_code(c[1]) & frustum_code(c[2])) return 0;
     int need = need_mask(c[0]) | need_mask(c[1]) | need_mask(c[2]);
+    if (need) return -1;
+    if (k != 1) return 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { c[i].b[0] = c[i].b[1] = c[i].b[2] = 0.0f; c[i].b[i] = 1.0f; }
     const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
-    if (need) return setup_subtri_clipped(c, need, hw, hh, k, a, b, cc);
-    if (k != 1) return false;
-    return project_vertex(c[0], hw, hh, a) && project_vertex(c[1], hw, hh, b) && project_vertex(c[2], hw, hh, cc);
+    return (project_vertex(c[0], hw, hh, a) && project_vertex(c[1], hw, hh, b) && project_vertex(c[2], hw, hh, cc)) ? 1 : 0;
+}
+static __device__ __noinline__ bool resetup_clipped(const float* __restrict__ mvp, float3 p0, float3 p1, float3 p2, int W, int H, int k,
+                                                    PolyV& a, PolyV& b, PolyV& cc) {
+    ClipV c[3];
+    xform_clip(mvp, p0.x, p0.y, p0.z, c[0]);
+    xform_clip(mvp, p1.x, p1.y, p1.z, c[1]);
+    xform_clip(mvp, p2.x, p2.y, p2.z, c[2]);
+    int need = need_mask(c[0]) | need_mask(c[1]) | need_mask(c[2]);
+    for (int i = 0; i < 3; ++i) { c[i].b[0] = c[i].b[1] = c[i].b[2] = 0.0f; c[i].b[i] = 1.0f; }
+    return setup_subtri_clipped(c, need, 0.5f * (float)W, 0.5f * (float)H, k, a, b, cc);
 }
 
 __device__ __forceinline__ long long edge_fn(int ax, int ay, int bx, int by, int px, int py) {

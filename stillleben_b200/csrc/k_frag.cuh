@@ -25,7 +25,7 @@ __device__ __forceinline__ f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y
 __device__ __forceinline__ f3 operator/(f3 a, f3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
 __device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-__device__ __forceinline__ f3 normalize3(f3 a) { float l = sqrtf(dot3(a, a)); return mk3(a.x / l, a.y / l, a.z / l); }
+__device__ __forceinline__ f3 normalize3(f3 a) { float r = rsqrtf(dot3(a, a)); return mk3(a.x * r, a.y * r, a.z * r); }
 __device__ __forceinline__ f3 max3(f3 a, f3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
 __device__ __forceinline__ f3 mix3(f3 a, f3 b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
@@ -47,7 +47,7 @@ __device__ __forceinline__ f3 mul_m3(const float* __restrict__ m9, f3 v) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int wrap_index(int i, int n, int mode, bool& border) {
     switch (mode) {
-        case SLB_WRAP_REPEAT: { int m = i % n; return m < 0 ? m + n : m; }
+        case SLB_WRAP_REPEAT: { if ((n & (n - 1)) == 0) return i & (n - 1); int m = i % n; return m < 0 ? m + n : m; }
         case SLB_WRAP_MIRRORED_REPEAT: { int p = 2 * n; int m = i % p; if (m < 0) m += p; return m < n ? m : p - 1 - m; }
         case SLB_WRAP_CLAMP_TO_BORDER: if (i < 0 || i >= n) { border = true; return 0; } return i;
         default: return min(max(i, 0), n - 1);
@@ -172,7 +172,7 @@ __device__ __forceinline__ float4 lut_sample(const DLightMap& lm, float u, float
 // ---------------------------------------------------------------------------------------------
 struct VSOut {
     float u, v;
-    f3 nW, tW, bW;
+    f3 nW;
     float4 objc;   // xyz object frame, w = camera z
     f3 wc, cc;
     float su, sv;  // sticker coordinates
@@ -180,7 +180,7 @@ struct VSOut {
 __device__ __forceinline__ void vertex_stage(const DFrame& f, const DDraw& d, uint32_t vi, VSOut& o, uint32_t& vertex_id) {
     float4 p4 = __ldg(d.pos4 + vi);
     vertex_id = __float_as_uint(p4.w);
-    float4 a0 = __ldg(d.attr + 3 * (size_t)vi), a1 = __ldg(d.attr + 3 * (size_t)vi + 1), a2 = __ldg(d.attr + 3 * (size_t)vi + 2);
+    float4 a0 = __ldg(d.attr + 3 * (size_t)vi), a1 = __ldg(d.attr + 3 * (size_t)vi + 1);
     float4 oc4 = mul_m4_p(d.meshToObject, p4.x, p4.y, p4.z, 1.0f);
     o.objc = make_float4(oc4.x / oc4.w, oc4.y / oc4.w, oc4.z / oc4.w, 1.0f);
     float4 wc4 = mul_m4_p(d.objectToWorld, oc4.x, oc4.y, oc4.z, oc4.w);
@@ -188,16 +188,27 @@ __device__ __forceinline__ void vertex_stage(const DFrame& f, const DDraw& d, ui
     float4 cc4 = mul_m4_p(f.V, wc4.x, wc4.y, wc4.z, wc4.w);
     o.cc = mk3(cc4.x / cc4.w, cc4.y / cc4.w, cc4.z / cc4.w);
     o.objc.w = o.cc.z;
-    f3 n = mk3(a0.z, a0.w, a1.x), t = mk3(a1.y, a1.z, a1.w);
+    f3 n = mk3(a0.z, a0.w, a1.x);
     o.nW = normalize3(mul_m3(d.normalToWorld, n));
-    o.tW = normalize3(mul_m3(d.normalToWorld, t));
-    o.bW = normalize3(cross3(o.nW, o.tW)) * a2.x;
     o.u = a0.x; o.v = a0.y;
     if (d.sticker) {
         float4 sp = mul_m4_p(d.stickerProj, oc4.x, oc4.y, oc4.z, oc4.w);
         o.su = (sp.x / sp.w - d.stickerRange[0]) / d.stickerRange[2];
         o.sv = (sp.y / sp.w - d.stickerRange[1]) / d.stickerRange[3];
     } else { o.su = -1.0f; o.sv = -1.0f; }
+}
+
+// interpolated world-space tangent and bitangent (render_shader.vert:75-84) — only evaluated for draws with
+// a normal texture, so the common path does not carry them
+static __device__ __noinline__ void tangent_frame(const DDraw& d, const uint32_t vi[3], const float bary[3], f3& tW, f3& bW) {
+    tW = bW = mk3(0.f, 0.f, 0.f);
+    for (int j = 0; j < 3; ++j) {
+        float4 a0 = __ldg(d.attr + 3 * (size_t)vi[j]), a1 = __ldg(d.attr + 3 * (size_t)vi[j] + 1), a2 = __ldg(d.attr + 3 * (size_t)vi[j] + 2);
+        f3 n = normalize3(mul_m3(d.normalToWorld, mk3(a0.z, a0.w, a1.x)));
+        f3 t = normalize3(mul_m3(d.normalToWorld, mk3(a1.y, a1.z, a1.w)));
+        f3 b = normalize3(cross3(n, t)) * a2.x;
+        tW = tW + t * bary[j]; bW = bW + b * bary[j];
+    }
 }
 
 // perspective-correct barycentrics w.r.t. the ORIGINAL triangle at pixel (px,py) of a sub-triangle
@@ -213,32 +224,67 @@ __device__ __forceinline__ void subtri_bary(const SubTri& st, const PolyV& a, co
     for (int j = 0; j < 3; ++j) out[j] = q0 * a.b[j] + q1 * b.b[j] + q2 * c.b[j];
 }
 
+// The three snapped vertices of sub-triangle k of primitive `tri` of draw d: recomputed in registers when the
+// primitive is unclipped, fetched from the binner's ClipRec list when it was clipped.
+__device__ __forceinline__ bool fetch_subtri(const DFrame& f, const DDraw& d, uint32_t tri, uint32_t seq, int k, const uint32_t vi[3],
+                                             PolyV& a, PolyV& b, PolyV& c) {
+    float4 p0 = __ldg(d.pos4 + vi[0]), p1 = __ldg(d.pos4 + vi[1]), p2 = __ldg(d.pos4 + vi[2]);
+    const float3 q0 = make_float3(p0.x, p0.y, p0.z), q1 = make_float3(p1.x, p1.y, p1.z), q2 = make_float3(p2.x, p2.y, p2.z);
+    int r = setup_subtri_fast(d.mvp, q0, q1, q2, f.W, f.H, k, a, b, c);
+    if (r >= 0) return r == 1;
+    const uint32_t n = min(*f.clip_count, (uint32_t)SLB_MAX_CLIP);
+    for (uint32_t i = 0; i < n; ++i) {
+        const ClipRec& cr = f.clip[i];
+        if (cr.seq != seq) continue;
+        if (k < 1 || k + 1 >= cr.n) return false;
+        const DPolyV &va = cr.v[0], &vb = cr.v[k], &vc = cr.v[k + 1];
+        a.X = va.X; a.Y = va.Y; a.z = va.z; a.invw = va.invw; a.b[0] = va.b[0]; a.b[1] = va.b[1]; a.b[2] = va.b[2];
+        b.X = vb.X; b.Y = vb.Y; b.z = vb.z; b.invw = vb.invw; b.b[0] = vb.b[0]; b.b[1] = vb.b[1]; b.b[2] = vb.b[2];
+        c.X = vc.X; c.Y = vc.Y; c.z = vc.z; c.invw = vc.invw; c.b[0] = vc.b[0]; c.b[1] = vc.b[1]; c.b[2] = vc.b[2];
+        return true;
+    }
+    (void)tri;
+    return resetup_clipped(d.mvp, q0, q1, q2, f.W, f.H, k, a, b, c);
+}
+
 struct FragIn {
     float u, v, u_dx, v_dx, u_dy, v_dy;   // uv at the pixel and the per-pixel finite differences
-    f3 nW, tW, bW; float4 objc; f3 wc, cc; float su, sv;
+    f3 nW; float4 objc; f3 wc, cc; float su, sv;
     bool front;
 };
-struct FragOut { float4 color, objc, camc, normal; };
 
-#define SLB_LERP(field) (vs[0].field * bary[0] + vs[1].field * bary[1] + vs[2].field * bary[2])
-__device__ __forceinline__ void interpolate(const SubTri& st, const PolyV& a, const PolyV& b, const PolyV& c, const VSOut vs[3],
-                                            int px, int py, bool want_derivs, FragIn& in, float bary[3]) {
+// Runs the vertex stage on the three vertices and interpolates its outputs at pixel (px,py), one vertex at
+// a time so that only one VSOut is live (sum order ((v0*b0 + v1*b1) + v2*b2) as in the smooth varyings).
+// dFdx / dFdy of uv come from the 2x2 quad partner evaluated on the same primitive (helper invocation).
+__device__ __forceinline__ void shade_inputs(const DFrame& f, const DDraw& d, const SubTri& st, const PolyV& a, const PolyV& b,
+                                             const PolyV& c, const uint32_t vi[3], int px, int py, bool want_derivs, FragIn& in,
+                                             float bary[3], uint32_t vid[3]) {
     subtri_bary(st, a, b, c, px, py, bary);
-    in.u = SLB_LERP(u); in.v = SLB_LERP(v);
-    in.nW = SLB_LERP(nW); in.tW = SLB_LERP(tW); in.bW = SLB_LERP(bW);
-    in.wc = SLB_LERP(wc); in.cc = SLB_LERP(cc);
-    in.objc = make_float4(SLB_LERP(objc.x), SLB_LERP(objc.y), SLB_LERP(objc.z), SLB_LERP(objc.w));
-    in.su = SLB_LERP(su); in.sv = SLB_LERP(sv);
+    float bx[3] = {0.f, 0.f, 0.f}, by[3] = {0.f, 0.f, 0.f};
+    if (want_derivs) {
+        subtri_bary(st, a, b, c, px ^ 1, py, bx);
+        subtri_bary(st, a, b, c, px, py ^ 1, by);
+    }
+    float ux = 0.f, vx = 0.f, uy = 0.f, vy = 0.f;
+    in.u = in.v = in.su = in.sv = 0.f;
+    in.nW = in.wc = in.cc = mk3(0.f, 0.f, 0.f);
+    in.objc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        VSOut v;
+        vertex_stage(f, d, vi[j], v, vid[j]);
+        const float w = bary[j];
+        in.u += v.u * w; in.v += v.v * w;
+        in.nW = in.nW + v.nW * w;
+        in.wc = in.wc + v.wc * w; in.cc = in.cc + v.cc * w;
+        in.objc = in.objc + v.objc * w;
+        in.su += v.su * w; in.sv += v.sv * w;
+        ux += v.u * bx[j]; vx += v.v * bx[j]; uy += v.u * by[j]; vy += v.v * by[j];
+    }
     in.front = st.twoA < 0;   // FrontFace = CW (render_pass.cpp:330)
     in.u_dx = in.v_dx = in.u_dy = in.v_dy = 0.0f;
     if (want_derivs) {
-        // dFdx/dFdy of the 2x2 quad: partner pixel evaluated on the same primitive (helper invocation)
-        float bx[3], by[3];
-        subtri_bary(st, a, b, c, px ^ 1, py, bx);
-        subtri_bary(st, a, b, c, px, py ^ 1, by);
         float sgx = (px & 1) ? -1.0f : 1.0f, sgy = (py & 1) ? -1.0f : 1.0f;
-        float ux = vs[0].u * bx[0] + vs[1].u * bx[1] + vs[2].u * bx[2], vx = vs[0].v * bx[0] + vs[1].v * bx[1] + vs[2].v * bx[2];
-        float uy = vs[0].u * by[0] + vs[1].u * by[1] + vs[2].u * by[2], vy = vs[0].v * by[0] + vs[1].v * by[1] + vs[2].v * by[2];
         in.u_dx = sgx * (ux - in.u); in.v_dx = sgx * (vx - in.v);
         in.u_dy = sgy * (uy - in.u); in.v_dy = sgy * (vy - in.v);
     }
@@ -281,20 +327,33 @@ __device__ __forceinline__ uint32_t shadow_threshold(float ref) {
     while (d <= 0xFFFFFF && __fdiv_rn((float)d, 16777215.0f) < ref) ++d;
     return (uint32_t)d;
 }
-__device__ __forceinline__ float shadow_tap(const uint32_t* __restrict__ map, float u, float v, uint32_t thr) {
+// 4x4 PCF taps at offsets {-1.5,-0.5,0.5,1.5} texels, each a 2x2 bilinear filter of the comparison: the 16
+// taps share their fractional position, so the sum separates into weights (1-a, 1, 1, 1, a) x (1-b, 1, 1, 1, b)
+// over the 5x5 texel neighbourhood — 25 compares instead of 64 (clamp-to-edge per texel index).
+__device__ __forceinline__ float shadow_pcf16(const uint32_t* __restrict__ map, float u, float v, uint32_t thr) {
     const int N = SLB_SHADOW_RES;
-    float x = u * N - 0.5f, y = v * N - 0.5f;
+    float x = u * N - 2.0f, y = v * N - 2.0f;            // (u - 1.5/N) * N - 0.5
     float fx = floorf(x), fy = floorf(y);
     float a = x - fx, b = y - fy;
     int i0 = (int)fx, j0 = (int)fy;
-    int i1 = min(max(i0 + 1, 0), N - 1), j1 = min(max(j0 + 1, 0), N - 1);
-    i0 = min(max(i0, 0), N - 1); j0 = min(max(j0, 0), N - 1);
-    auto cmp = [&](int i, int j) { return min(__ldg(map + (size_t)j * N + i), 0xFFFFFFu) >= thr ? 1.0f : 0.0f; };
-    return cmp(i0, j0) * ((1 - a) * (1 - b)) + cmp(i1, j0) * (a * (1 - b)) + cmp(i0, j1) * ((1 - a) * b) + cmp(i1, j1) * (a * b);
+    const float wx[5] = {1.0f - a, 1.0f, 1.0f, 1.0f, a};
+    const float wy[5] = {1.0f - b, 1.0f, 1.0f, 1.0f, b};
+    float sum = 0.0f;
+#pragma unroll
+    for (int jj = 0; jj < 5; ++jj) {
+        const uint32_t* row = map + (size_t)min(max(j0 + jj, 0), N - 1) * N;
+        float r = 0.0f;
+#pragma unroll
+        for (int ii = 0; ii < 5; ++ii)
+            r += (min(__ldg(row + min(max(i0 + ii, 0), N - 1)), 0xFFFFFFu) >= thr) ? wx[ii] : 0.0f;
+        sum += r * wy[jj];
+    }
+    return sum * (1.0f / 16.0f);
 }
 
 // fragment stage (render_shader.frag:225-412); the discards are evaluated by the rasteriser
-__device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, const FragIn& in, FragOut& out) {
+__device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, const FragIn& in, const uint32_t vi[3],
+                                               const float bary[3], float4& out_color, float4& out_normal) {
     const float PI = 3.141592653589793f;
     float4 baseColor = base_color(d, in);
     if (d.sticker && in.su >= 0 && in.sv >= 0 && in.su < 1 && in.sv < 1) {
@@ -306,7 +365,9 @@ __device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, 
     f3 normal;
     if (d.tex[1]) {
         float4 t = sample_mat(d.tex[1], in);
-        normal = normalize3(in.tW * (t.x * 2.0f - 1.0f) + in.bW * (t.y * 2.0f - 1.0f) + in.nW * (t.z * 2.0f - 1.0f));
+        f3 tW, bW;
+        tangent_frame(d, vi, bary, tW, bW);
+        normal = normalize3(tW * (t.x * 2.0f - 1.0f) + bW * (t.y * 2.0f - 1.0f) + in.nW * (t.z * 2.0f - 1.0f));
     } else normal = in.nW;
     if (!in.front) normal = -normal;
 
@@ -332,19 +393,12 @@ __device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, 
     const float omv = 1.0f - NoV, omv2 = omv * omv;
     f3 k_S = F0 + Fr * (omv2 * omv2 * omv);
 
-    const float shadowMapScale = 1.0f / (float)SLB_SHADOW_RES;
 #pragma unroll 1
     for (int i = 0; i < SLB_NUM_LIGHTS; ++i) {
         if (!f.lightActive[i]) continue;
         float4 pc = mul_m4_p(f.shadowMat[i], in.wc.x, in.wc.y, in.wc.z, 1.0f);
         float pcx = 0.5f * (pc.x / pc.w) + 0.5f, pcy = 0.5f * (pc.y / pc.w) + 0.5f, pcz = 0.5f * (pc.z / pc.w) + 0.5f;
-        float inverseShadow = 0.0f;
-        const uint32_t* map = f.shadowMap[i];
-        const uint32_t thr = shadow_threshold(pcz - 0.00003f);
-        for (int yy = 0; yy < 4; ++yy)
-            for (int xx = 0; xx < 4; ++xx)
-                inverseShadow += shadow_tap(map, pcx + (-1.5f + xx) * shadowMapScale, pcy + (-1.5f + yy) * shadowMapScale, thr);
-        inverseShadow /= 16.0f;
+        const float inverseShadow = shadow_pcf16(f.shadowMap[i], pcx, pcy, shadow_threshold(pcz - 0.00003f));
 
         f3 L = normalize3(mk3(-f.lightDir[i][0], -f.lightDir[i][1], -f.lightDir[i][2]));
         f3 H = normalize3(cameraDirection + L);
@@ -377,13 +431,11 @@ __device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, 
     }
     color = color + emissive;
 
-    out.color = make_float4(color.x, color.y, color.z, baseColor.w);
-    out.objc = in.objc;
-    out.camc = make_float4(in.cc.x, in.cc.y, in.cc.z, 1.0f);
+    out_color = make_float4(color.x, color.y, color.z, baseColor.w);
     f3 nc = mk3(f.V[0] * normal.x + f.V[4] * normal.y + f.V[8] * normal.z, f.V[1] * normal.x + f.V[5] * normal.y + f.V[9] * normal.z,
                 f.V[2] * normal.x + f.V[6] * normal.y + f.V[10] * normal.z);
     nc = normalize3(nc);
-    out.normal = make_float4(nc.x, nc.y, nc.z, dot3(normal, cameraDirection));
+    out_normal = make_float4(nc.x, nc.y, nc.z, dot3(normal, cameraDirection));
 }
 
 // tone map (tone_map_shader.frag:102-131): RGB -> Yxy, exposure, -> RGB, ACES, RGBA8 (linear: the

@@ -84,7 +84,19 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_bin(const DFrame* __restric
         uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
         float4 p0 = __ldg(d.pos4 + i0), p1 = __ldg(d.pos4 + i1), p2 = __ldg(d.pos4 + i2);
         PrimSetup ps;
-        if (setup_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), W, H, ps)) {
+        bool clipped = false;
+        if (setup_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), W, H, ps, &clipped)) {
+            if (EMIT && clipped) {   // publish the clipped polygon once for the fragment test and the shade kernel
+                uint32_t slot = atomicAdd(f.clip_count, 1u);
+                if (slot < SLB_MAX_CLIP) {
+                    ClipRec& cr = f.clip[slot];
+                    cr.seq = d.prim_base + tri; cr.n = ps.n;
+                    for (int i = 0; i < ps.n; ++i) {
+                        cr.v[i].X = ps.v[i].X; cr.v[i].Y = ps.v[i].Y; cr.v[i].z = ps.v[i].z; cr.v[i].invw = ps.v[i].invw;
+                        cr.v[i].b[0] = ps.v[i].b[0]; cr.v[i].b[1] = ps.v[i].b[1]; cr.v[i].b[2] = ps.v[i].b[2];
+                    }
+                }
+            }
             for (int k = 1; k + 1 < ps.n; ++k) {
                 SubTri st;
                 if (!make_subtri(ps, k, st)) continue;
@@ -192,19 +204,16 @@ static_assert(sizeof(TriDerived) == 80, "TriDerived must be 80 bytes");
 #define SLB_RASTER_CHUNK 32
 
 // fragment-stage discards that decide coverage: depth peel + alpha test (render_shader.frag:229-246)
-__device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint32_t tri, int k, int px, int py) {
+__device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint32_t seq, int k, int px, int py) {
+    const uint32_t tri = seq - d.prim_base;
     const uint32_t* ip = d.idx + 3 * (size_t)tri;
-    uint32_t i[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
-    float4 p0 = __ldg(d.pos4 + i[0]), p1 = __ldg(d.pos4 + i[1]), p2 = __ldg(d.pos4 + i[2]);
+    const uint32_t vi[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
     PolyV a, b, c;
-    if (!setup_subtri(d.mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), f.W, f.H, k, a, b, c))
-        return true;
+    if (!fetch_subtri(f, d, tri, seq, k, vi, a, b, c)) return true;
     SubTri st;
     if (!make_subtri(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, st)) return true;
-    VSOut vs[3]; uint32_t vid;
-    for (int j = 0; j < 3; ++j) vertex_stage(f, d, i[j], vs[j], vid);
-    FragIn in; float bary[3];
-    interpolate(st, a, b, c, vs, px, py, d.tex[0] != nullptr, in, bary);
+    FragIn in; float bary[3]; uint32_t vid[3];
+    shade_inputs(f, d, st, a, b, c, vi, px, py, d.tex[0] != nullptr, in, bary, vid);
     if (f.peel && in.objc.w - 0.00001f <= f.peel[((size_t)py * f.W + px) * 4 + 3]) return true;
     if ((d.flags & DRAW_FRAG_TEST) && base_color(d, in).w < 0.5f) return true;
     return false;
@@ -298,7 +307,7 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DFrame* 
                         unsigned long long key = ((unsigned long long)__float2uint_rn(__fmul_rn(z, 16777215.0f)) << 40) | lowkey;
                         if (key < key0) {
                             if (!(dv.k_flags & 0x100u) ||
-                                !frag_discard(f, draws[dv.draw], dv.seq - draws[dv.draw].prim_base, dv.k_flags & 0xff, px, py0))
+                                !frag_discard(f, draws[dv.draw], dv.seq, dv.k_flags & 0xff, px, py0))
                                 key0 = key;
                         }
                     }
@@ -311,7 +320,7 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DFrame* 
                         unsigned long long key = ((unsigned long long)__float2uint_rn(__fmul_rn(z, 16777215.0f)) << 40) | lowkey;
                         if (key < key1) {
                             if (!(dv.k_flags & 0x100u) ||
-                                !frag_discard(f, draws[dv.draw], dv.seq - draws[dv.draw].prim_base, dv.k_flags & 0xff, px, py1))
+                                !frag_discard(f, draws[dv.draw], dv.seq, dv.k_flags & 0xff, px, py1))
                                 key1 = key;
                         }
                     }
@@ -438,52 +447,53 @@ __global__ void __launch_bounds__(256) k_shade(const DFrame* __restrict__ frames
     if (px >= W || py >= H) return;
     const size_t p = (size_t)py * W + px;
     const unsigned long long key = f.keys[p];
+    float4* const o_coord = reinterpret_cast<float4*>(f.out[SLB_TARGET_COORD]);
+    unsigned short* const o_cls = reinterpret_cast<unsigned short*>(f.out[SLB_TARGET_CLASS]);
+    unsigned short* const o_inst = reinterpret_cast<unsigned short*>(f.out[SLB_TARGET_INSTANCE]);
+    uint4* const o_vidx = reinterpret_cast<uint4*>(f.out[SLB_TARGET_VERTEX_INDEX]);
+    float4* const o_bary = reinterpret_cast<float4*>(f.out[SLB_TARGET_BARY]);
 
     float4 hdr = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 coord = make_float4(SLB_INVALID_COORD, SLB_INVALID_COORD, SLB_INVALID_COORD, SLB_INVALID_COORD);
-    float4 camc = coord;
     float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 bary4 = make_float4(0.f, 0.f, 0.f, 1.0f);
-    uint4 vidx = make_uint4(0u, 0u, 0u, 0u);
-    unsigned short cls = 0, inst = 0;
-
+    bool shaded = false;
     if (key != SLB_KEY_EMPTY) {
         const uint32_t seq = (uint32_t)(key >> 8);
         const int k = (int)(key & 0xffu);
         const DDraw& d = draws[find_draw_by_prim(draws, f.draw_begin, f.draw_end, seq)];
         const uint32_t tri = seq - d.prim_base;
         const uint32_t* ip = d.idx + 3 * (size_t)tri;
-        uint32_t i[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
-        float4 p0 = __ldg(d.pos4 + i[0]), p1 = __ldg(d.pos4 + i[1]), p2 = __ldg(d.pos4 + i[2]);
+        const uint32_t vi[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
         PolyV va, vb, vc;
         SubTri st;
-        if (setup_subtri(d.mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), W, H, k, va, vb, vc) &&
-            make_subtri(va.X, va.Y, vb.X, vb.Y, vc.X, vc.Y, va.z, vb.z, vc.z, st)) {
-            VSOut vs[3]; uint32_t vid[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) vertex_stage(f, d, i[j], vs[j], vid[j]);
-            FragIn in; float bary[3];
-            interpolate(st, va, vb, vc, vs, px, py, draw_has_textures(d), in, bary);
-            FragOut o;
-            fragment_stage(f, d, in, o);
-            hdr = o.color; coord = o.objc; camc = o.camc; nrm = o.normal;
-            bary4 = make_float4(bary[0], bary[1], bary[2], 1.0f);
-            vidx = make_uint4(vid[0], vid[1], vid[2], 0u);
-            cls = (unsigned short)d.class_index; inst = (unsigned short)d.instance_index;
+        if (fetch_subtri(f, d, tri, seq, k, vi, va, vb, vc) && make_subtri(va.X, va.Y, vb.X, vb.Y, vc.X, vc.Y, va.z, vb.z, vc.z, st)) {
+            FragIn in; float bary[3]; uint32_t vid[3];
+            shade_inputs(f, d, st, va, vb, vc, vi, px, py, draw_has_textures(d), in, bary, vid);
+            // geometry targets first: their registers are free before the lighting code runs
+            if (o_coord) o_coord[p] = in.objc;
+            if (o_cls) o_cls[p] = (unsigned short)d.class_index;
+            if (o_inst) o_inst[p] = (unsigned short)d.instance_index;
+            if (o_vidx) o_vidx[p] = make_uint4(vid[0], vid[1], vid[2], 0u);
+            if (o_bary) o_bary[p] = make_float4(bary[0], bary[1], bary[2], 1.0f);
+            if (f.scratch_cam) f.scratch_cam[p] = make_float4(in.cc.x, in.cc.y, in.cc.z, 1.0f);   // == out[CAM_COORD] when requested
+            fragment_stage(f, d, in, vi, bary, hdr, nrm);
+            shaded = true;
         }
+    }
+    if (!shaded) {   // clear values (render_pass.cpp:316,523-532)
+        const float4 inval = make_float4(SLB_INVALID_COORD, SLB_INVALID_COORD, SLB_INVALID_COORD, SLB_INVALID_COORD);
+        if (o_coord) o_coord[p] = inval;
+        if (o_cls) o_cls[p] = 0;
+        if (o_inst) o_inst[p] = 0;
+        if (o_vidx) o_vidx[p] = make_uint4(0u, 0u, 0u, 0u);
+        if (o_bary) o_bary[p] = make_float4(0.f, 0.f, 0.f, 1.0f);
+        if (f.scratch_cam) f.scratch_cam[p] = inval;
     }
     if (f.fused_tonemap) {
         if (f.out[SLB_TARGET_RGB]) reinterpret_cast<uchar4*>(f.out[SLB_TARGET_RGB])[p] = tone_map(hdr, f.manual_exposure, nullptr);
     } else {
         f.hdr[p] = hdr;
     }
-    if (f.out[SLB_TARGET_COORD]) reinterpret_cast<float4*>(f.out[SLB_TARGET_COORD])[p] = coord;
-    if (f.out[SLB_TARGET_CLASS]) reinterpret_cast<unsigned short*>(f.out[SLB_TARGET_CLASS])[p] = cls;
-    if (f.out[SLB_TARGET_INSTANCE]) reinterpret_cast<unsigned short*>(f.out[SLB_TARGET_INSTANCE])[p] = inst;
     if (f.scratch_normal) f.scratch_normal[p] = nrm;   // == out[NORMAL] when that target is requested
-    if (f.out[SLB_TARGET_VERTEX_INDEX]) reinterpret_cast<uint4*>(f.out[SLB_TARGET_VERTEX_INDEX])[p] = vidx;
-    if (f.out[SLB_TARGET_BARY]) reinterpret_cast<float4*>(f.out[SLB_TARGET_BARY])[p] = bary4;
-    if (f.scratch_cam) f.scratch_cam[p] = camc;         // == out[CAM_COORD] when that target is requested
 }
 
 // ---------------------------------------------------------------------------------------------

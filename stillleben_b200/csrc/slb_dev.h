@@ -67,6 +67,12 @@ struct DShadowDraw {
     float mvp[16];
 };
 
+// A primitive that needed polygon clipping, written once by the binner so that the raster's fragment test
+// and the shade kernel fetch the clipped, snapped polygon instead of re-clipping it per pixel.
+struct DPolyV { int32_t X, Y; float z, invw; float b[3]; };
+struct ClipRec { uint32_t seq; int32_t n; DPolyV v[10]; };
+#define SLB_MAX_CLIP 48            // per frame; primitives beyond this are re-clipped where they are used
+
 struct DFrame {
     int32_t W, H, tiles_x, tiles_y;
     uint32_t tile_base;            // first tile of this frame in the batch-wide tile arrays
@@ -85,6 +91,8 @@ struct DFrame {
     const DLightMap* lm;
     const float* peel;             // previous layer's coord target (HxWx4) or null
     const DTexture* bg_image;
+    ClipRec* clip;                 // SLB_MAX_CLIP records
+    uint32_t* clip_count;
     uint64_t* keys;                // H*W visibility keys
     float4* hdr;                   // H*W pre-tone-map colour (post-pass path only)
     float4* scratch_normal;        // used by SSAO when the normal / cam-coord targets are not requested

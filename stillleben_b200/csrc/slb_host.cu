@@ -75,6 +75,7 @@ struct slb_ctx {
     slb_mesh* plane = nullptr;
     // per-batch device arrays
     DevBuf frames_d, draws_d, chunk_base_d, sdraws_d, schunk_base_d;
+    DevBuf clip_recs, clip_counts;
     DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, ao, avg, mip_a, mip_b, shadow_maps;
     // pinned staging
     void* staging = nullptr; size_t staging_cap = 0;
@@ -202,7 +203,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
     }
     DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->sdraws_d, &ctx->schunk_base_d, &ctx->tile_count,
                       &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->ao,
-                      &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps};
+                      &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ctx->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -876,6 +877,8 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     CU(ctx->tile_count.reserve((size_t)n_tiles * 4, true));
     CU(ctx->tile_off.reserve(((size_t)n_tiles + 1) * 4));
     CU(ctx->keys.reserve(npx * n * 8));
+    CU(ctx->clip_recs.reserve((size_t)n * SLB_MAX_CLIP * sizeof(ClipRec)));
+    CU(ctx->clip_counts.reserve((size_t)n * 4));
     CU(ctx->shadow_maps.reserve((size_t)b.n_shadow_maps * SLB_SHADOW_RES * SLB_SHADOW_RES * 4));
     const bool post = !b.fused;
     if (post) {
@@ -892,6 +895,8 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     for (int j = 0; j < n; ++j) {
         DFrame& f = b.frames[j];
         f.keys = ctx->keys.as<uint64_t>() + npx * j;
+        f.clip = ctx->clip_recs.as<ClipRec>() + (size_t)j * SLB_MAX_CLIP;
+        f.clip_count = ctx->clip_counts.as<uint32_t>() + j;
         f.fused_tonemap = b.fused ? 1 : 0;
         for (int li = 0; li < SLB_NUM_LIGHTS; ++li)
             f.shadowMap[li] = f.lightActive[li] ? smaps + smap_elems * (uintptr_t)f.shadowMap[li] : nullptr;
@@ -928,6 +933,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     const DFrame* frames_d = ctx->frames_d.as<DFrame>();
     const DDraw* draws_d = ctx->draws_d.as<DDraw>();
 
+    CU(cudaMemsetAsync(ctx->clip_counts.p, 0, (size_t)n * 4, s));
     // ---- shadow pass ----
     if (b.n_shadow_maps) {
         StageTimer t(ctx, s, ST_SHADOW);
