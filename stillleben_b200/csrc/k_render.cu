@@ -190,18 +190,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 
-// per-tile derived triangle data, written lane-parallel, read as shared-memory broadcasts
-struct __align__(16) TriDerived {
-    long long e0, e1;                 // s*w_i + bias_i at the tile's first pixel centre
-    long long e2; int dx0, dy0;       // per-pixel steps / 256
-    int dx1, dy1, dx2, dy2;
-    float az, dzb, dzc, inv2A;
-    int s_bias; uint32_t seq, k_flags, draw;
-};
-static_assert(sizeof(TriDerived) == 80, "TriDerived must be 80 bytes");
-
 #define SLB_RASTER_WARPS 8
 #define SLB_RASTER_CHUNK 32
+#define SLB_RASTER_SMALL 16   // sub-triangles whose in-tile pixel box is at most this big are rasterised by ONE lane
 
 // fragment-stage discards that decide coverage: depth peel + alpha test (render_shader.frag:229-246)
 __device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint32_t seq, int k, int px, int py) {
@@ -219,12 +210,18 @@ __device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint3
     return false;
 }
 
+// One warp per 8x8 tile. The tile's PairRec run is staged through TMA bulk copies (double buffered, 32
+// records per stage). Each lane then owns one record of the stage: sub-triangles whose pixel box inside the
+// tile is small (the common case for 16k-triangle meshes) are walked by that lane alone, with per-lane
+// z-compare through a 64-bit atomicMin on the tile's key buffer in shared memory; the remaining (large)
+// records are found with a warp ballot and processed by the whole warp, two pixels per lane.
+template <bool FRAG>
 __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws,
                                                                    const uint32_t* __restrict__ tile_off,
                                                                    const PairRec* __restrict__ pairs, uint32_t n_tiles,
                                                                    uint32_t tiles_per_frame) {
     __shared__ __align__(128) PairRec s_rec[SLB_RASTER_WARPS][2][SLB_RASTER_CHUNK];
-    __shared__ __align__(16) TriDerived s_der[SLB_RASTER_WARPS][SLB_RASTER_CHUNK];
+    __shared__ unsigned long long s_key[SLB_RASTER_WARPS][SLB_TILE * SLB_TILE];
     __shared__ __align__(8) uint64_t s_bar[SLB_RASTER_WARPS][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x * SLB_RASTER_WARPS + warp;
@@ -233,11 +230,13 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DFrame* 
     const DFrame& f = frames[fi];
     const int W = f.W, H = f.H;
     const int tx = tl % f.tiles_x, ty = tl / f.tiles_x;
+    const int x_lo = tx * SLB_TILE, y_lo = ty * SLB_TILE;
+    const int x_hi = min(x_lo + SLB_TILE - 1, W - 1), y_hi = min(y_lo + SLB_TILE - 1, H - 1);
     const int lx = lane & 7, ly = lane >> 3;
-    const int px = tx * SLB_TILE + lx, py0 = ty * SLB_TILE + ly, py1 = py0 + 4;
     const uint32_t beg = __ldg(tile_off + t), end = __ldg(tile_off + t + 1);
     const uint32_t n = end - beg;
-    unsigned long long key0 = SLB_KEY_EMPTY, key1 = SLB_KEY_EMPTY;
+    unsigned long long* keys = s_key[warp];
+    keys[lane] = SLB_KEY_EMPTY; keys[lane + 32] = SLB_KEY_EMPTY;
 
     if (n > 0) {
         uint64_t* bar = s_bar[warp];
@@ -253,10 +252,9 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DFrame* 
             mbar_expect_tx(&bar[0], cnt * (uint32_t)sizeof(PairRec));
             bulk_g2s(&s_rec[warp][0][0], pairs + beg, cnt * (uint32_t)sizeof(PairRec), &bar[0]);
         }
-        const int ox = (tx * SLB_TILE) * 256 + 128, oy = (ty * SLB_TILE) * 256 + 128;   // tile's first pixel centre
         for (uint32_t c = 0; c < nchunks; ++c) {
             const int b = c & 1;
-            if (lane == 0 && c + 1 < nchunks) {   // prefetch the next chunk into the other buffer
+            if (lane == 0 && c + 1 < nchunks) {   // prefetch the next stage into the other buffer
                 uint32_t cnt = min(n - (c + 1) * SLB_RASTER_CHUNK, (uint32_t)SLB_RASTER_CHUNK);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&bar[b ^ 1], cnt * (uint32_t)sizeof(PairRec));
@@ -265,73 +263,83 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DFrame* 
             }
             mbar_wait(&bar[b], (c >> 1) & 1);
             const int cnt = (int)min(n - c * SLB_RASTER_CHUNK, (uint32_t)SLB_RASTER_CHUNK);
-            // phase A: one triangle per lane -> edge functions at the tile origin
+            // ---- one record per lane ----
+            bool big = false;
             if (lane < cnt) {
                 const PairRec r = s_rec[warp][b][lane];
                 SubTri st;
                 make_subtri(r.ax, r.ay, r.bx, r.by, r.cx, r.cy, r.az, r.bz, r.cz, st);
-                TriDerived dv;
-                dv.e0 = st.s * edge_fn(st.bx, st.by, st.cx, st.cy, ox, oy) + st.bias0;
-                dv.e1 = st.s * edge_fn(st.cx, st.cy, st.ax, st.ay, ox, oy) + st.bias1;
-                dv.e2 = st.s * edge_fn(st.ax, st.ay, st.bx, st.by, ox, oy) + st.bias2;
-                dv.dx0 = -st.s * (st.cy - st.by); dv.dy0 = st.s * (st.cx - st.bx);
-                dv.dx1 = -st.s * (st.ay - st.cy); dv.dy1 = st.s * (st.ax - st.cx);
-                dv.dx2 = -st.s * (st.by - st.ay); dv.dy2 = st.s * (st.bx - st.ax);
-                dv.az = st.az; dv.dzb = __fsub_rn(st.bz, st.az); dv.dzc = __fsub_rn(st.cz, st.az); dv.inv2A = st.inv2A;
-                dv.s_bias = (st.s < 0 ? 1 : 0) | (st.bias1 ? 2 : 0) | (st.bias2 ? 4 : 0);
-                dv.seq = r.seq; dv.k_flags = r.k_flags; dv.draw = r.draw;
-                s_der[warp][lane] = dv;
+                int px0, py0, px1, py1;
+                if (subtri_pixel_bbox(st, W, H, px0, py0, px1, py1)) {
+                    px0 = max(px0, x_lo); px1 = min(px1, x_hi); py0 = max(py0, y_lo); py1 = min(py1, y_hi);
+                    if (px0 <= px1 && py0 <= py1) {
+                        if ((px1 - px0 + 1) * (py1 - py0 + 1) > SLB_RASTER_SMALL) big = true;
+                        else {
+                            const int cx0 = px0 * 256 + 128, cy0 = py0 * 256 + 128;
+                            long long a0 = st.s * edge_fn(st.bx, st.by, st.cx, st.cy, cx0, cy0) + st.bias0;
+                            long long a1 = st.s * edge_fn(st.cx, st.cy, st.ax, st.ay, cx0, cy0) + st.bias1;
+                            long long a2 = st.s * edge_fn(st.ax, st.ay, st.bx, st.by, cx0, cy0) + st.bias2;
+                            const long long dx0 = (long long)(-st.s * (st.cy - st.by)) * 256, dy0 = (long long)(st.s * (st.cx - st.bx)) * 256;
+                            const long long dx1 = (long long)(-st.s * (st.ay - st.cy)) * 256, dy1 = (long long)(st.s * (st.ax - st.cx)) * 256;
+                            const long long dx2 = (long long)(-st.s * (st.by - st.ay)) * 256, dy2 = (long long)(st.s * (st.bx - st.ax)) * 256;
+                            const float dzb = __fsub_rn(st.bz, st.az), dzc = __fsub_rn(st.cz, st.az);
+                            const unsigned long long lowkey = ((unsigned long long)r.seq << 8) | (r.k_flags & 0xffu);
+                            for (int y = py0; y <= py1; ++y, a0 += dy0, a1 += dy1, a2 += dy2) {
+                                long long e0 = a0, e1 = a1, e2 = a2;
+                                for (int x = px0; x <= px1; ++x, e0 += dx0, e1 += dx1, e2 += dx2) {
+                                    if ((e0 | e1 | e2) < 0) continue;
+                                    long long w1 = e1 - st.bias1, w2 = e2 - st.bias2;
+                                    if (st.s < 0) { w1 = -w1; w2 = -w2; }
+                                    float q1 = __fmul_rn(__ll2float_rn(w1), st.inv2A), q2 = __fmul_rn(__ll2float_rn(w2), st.inv2A);
+                                    float z = __fmaf_rn(q2, dzc, __fmaf_rn(q1, dzb, st.az));
+                                    z = fminf(fmaxf(z, 0.0f), 1.0f);
+                                    const unsigned long long key = ((unsigned long long)__float2uint_rn(__fmul_rn(z, 16777215.0f)) << 40) | lowkey;
+                                    unsigned long long* slot = keys + (y - y_lo) * SLB_TILE + (x - x_lo);
+                                    if (FRAG) {
+                                        if ((r.k_flags & 0x100u) && (key >= *(volatile unsigned long long*)slot ||
+                                                                     frag_discard(f, draws[r.draw], r.seq, r.k_flags & 0xff, x, y)))
+                                            continue;
+                                    }
+                                    atomicMin(slot, key);
+                                }
+                            }
+                        }
+                    }
+                }
             }
+            unsigned bigmask = __ballot_sync(0xffffffffu, big);
             __syncwarp();
-            // phase B: every lane tests its two pixels against each triangle of the chunk
-            for (int j = 0; j < cnt; ++j) {
-                const TriDerived& dv = s_der[warp][j];
-                long long e0 = dv.e0 + (long long)(dv.dx0 * lx + dv.dy0 * ly) * 256;
-                long long e1 = dv.e1 + (long long)(dv.dx1 * lx + dv.dy1 * ly) * 256;
-                long long e2 = dv.e2 + (long long)(dv.dx2 * lx + dv.dy2 * ly) * 256;
-                long long g0 = e0 + (long long)dv.dy0 * 1024, g1 = e1 + (long long)dv.dy1 * 1024, g2 = e2 + (long long)dv.dy2 * 1024;
-                const bool in0 = (e0 | e1 | e2) >= 0, in1 = (g0 | g1 | g2) >= 0;
-                if (__ballot_sync(0xffffffffu, in0 || in1) == 0) continue;
-                if (in0 || in1) {
-                    const int sb = dv.s_bias;
-                    const long long b1 = (sb & 2) ? -1 : 0, b2 = (sb & 4) ? -1 : 0;
-                    const bool neg = sb & 1;
-                    const unsigned long long lowkey = ((unsigned long long)dv.seq << 8) | (dv.k_flags & 0xffu);
-                    const float dzb = dv.dzb, dzc = dv.dzc, az = dv.az, inv2A = dv.inv2A;
-                    if (in0 && px < W && py0 < H) {
-                        long long w1 = e1 - b1, w2 = e2 - b2;
-                        if (neg) { w1 = -w1; w2 = -w2; }
-                        float q1 = __fmul_rn(__ll2float_rn(w1), inv2A), q2 = __fmul_rn(__ll2float_rn(w2), inv2A);
-                        float z = __fmaf_rn(q2, dzc, __fmaf_rn(q1, dzb, az));
-                        z = fminf(fmaxf(z, 0.0f), 1.0f);
-                        unsigned long long key = ((unsigned long long)__float2uint_rn(__fmul_rn(z, 16777215.0f)) << 40) | lowkey;
-                        if (key < key0) {
-                            if (!(dv.k_flags & 0x100u) ||
-                                !frag_discard(f, draws[dv.draw], dv.seq, dv.k_flags & 0xff, px, py0))
-                                key0 = key;
-                        }
+            // ---- large records: the whole warp, two pixels per lane ----
+            while (bigmask) {
+                const int j = __ffs(bigmask) - 1;
+                bigmask &= bigmask - 1;
+                const PairRec& r = s_rec[warp][b][j];
+                SubTri st;
+                make_subtri(r.ax, r.ay, r.bx, r.by, r.cx, r.cy, r.az, r.bz, r.cz, st);
+                const unsigned long long lowkey = ((unsigned long long)r.seq << 8) | (r.k_flags & 0xffu);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int x = x_lo + lx, y = y_lo + ly + 4 * h;
+                    if (x > x_hi || y > y_hi) continue;
+                    long long w0, w1, w2; subtri_weights(st, x, y, w0, w1, w2);
+                    if (!subtri_covers(st, w0, w1, w2)) continue;
+                    const unsigned long long key = ((unsigned long long)subtri_depth24(st, w1, w2) << 40) | lowkey;
+                    unsigned long long* slot = keys + (ly + 4 * h) * SLB_TILE + lx;
+                    if (key >= *slot) continue;
+                    if (FRAG) {
+                        if ((r.k_flags & 0x100u) && frag_discard(f, draws[r.draw], r.seq, r.k_flags & 0xff, x, y)) continue;
                     }
-                    if (in1 && px < W && py1 < H) {
-                        long long w1 = g1 - b1, w2 = g2 - b2;
-                        if (neg) { w1 = -w1; w2 = -w2; }
-                        float q1 = __fmul_rn(__ll2float_rn(w1), inv2A), q2 = __fmul_rn(__ll2float_rn(w2), inv2A);
-                        float z = __fmaf_rn(q2, dzc, __fmaf_rn(q1, dzb, az));
-                        z = fminf(fmaxf(z, 0.0f), 1.0f);
-                        unsigned long long key = ((unsigned long long)__float2uint_rn(__fmul_rn(z, 16777215.0f)) << 40) | lowkey;
-                        if (key < key1) {
-                            if (!(dv.k_flags & 0x100u) ||
-                                !frag_discard(f, draws[dv.draw], dv.seq, dv.k_flags & 0xff, px, py1))
-                                key1 = key;
-                        }
-                    }
+                    *slot = key;
                 }
             }
             __syncwarp();
         }
     }
+    __syncwarp();
+    const int px = x_lo + lx;
     if (px < W) {
-        if (py0 < H) f.keys[(size_t)py0 * W + px] = key0;
-        if (py1 < H) f.keys[(size_t)py1 * W + px] = key1;
+        if (y_lo + ly < H) f.keys[(size_t)(y_lo + ly) * W + px] = keys[ly * SLB_TILE + lx];
+        if (y_lo + ly + 4 < H) f.keys[(size_t)(y_lo + ly + 4) * W + px] = keys[(ly + 4) * SLB_TILE + lx];
     }
 }
 
@@ -508,11 +516,12 @@ void launch_bin(bool emit, const DFrame* frames, const DDraw* draws, const uint3
     else k_bin<false><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(frames, draws, chunk_base, n_draws, tile_count, tile_off, pairs, capacity);
 }
 void launch_scan(const uint32_t* count, uint32_t* off, uint32_t n, cudaStream_t s) { k_scan<<<1, 1024, 0, s>>>(count, off, n); }
-void launch_raster(const DFrame* frames, const DDraw* draws, const uint32_t* tile_off, const PairRec* pairs, uint32_t n_tiles,
-                   uint32_t tiles_per_frame, cudaStream_t s) {
+void launch_raster(bool frag_test, const DFrame* frames, const DDraw* draws, const uint32_t* tile_off, const PairRec* pairs,
+                   uint32_t n_tiles, uint32_t tiles_per_frame, cudaStream_t s) {
     if (n_tiles == 0) return;
-    k_raster<<<(n_tiles + SLB_RASTER_WARPS - 1) / SLB_RASTER_WARPS, SLB_RASTER_WARPS * 32, 0, s>>>(frames, draws, tile_off, pairs, n_tiles,
-                                                                                                  tiles_per_frame);
+    const unsigned grid = (n_tiles + SLB_RASTER_WARPS - 1) / SLB_RASTER_WARPS;
+    if (frag_test) k_raster<true><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(frames, draws, tile_off, pairs, n_tiles, tiles_per_frame);
+    else k_raster<false><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(frames, draws, tile_off, pairs, n_tiles, tiles_per_frame);
 }
 void launch_shadow(const DShadowDraw* sdraws, const uint32_t* chunk_base, int n_draws, uint32_t n_chunks, cudaStream_t s) {
     if (n_chunks == 0) return;

@@ -601,7 +601,7 @@ struct Batch {
     std::vector<int> frame_first_light_slot;   // index of the frame's first shadow map in the batch pool
     uint32_t n_chunks = 0, n_schunks = 0, n_shadow_maps = 0;
     uint64_t n_tris = 0;
-    bool fused = true, any_ssao = false, any_auto = false, any_bg = false;
+    bool fused = true, any_ssao = false, any_auto = false, any_bg = false, any_frag_test = false;
 };
 
 static inline uint32_t chunks_of(uint32_t n_tris) { return (n_tris + SLB_SETUP_CHUNK - 1) / SLB_SETUP_CHUNK; }
@@ -774,6 +774,7 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
             mvp(P, V, o2w, m2o, d.mvp);
             normal_matrix(mul(o2w, m2o), d.normalToWorld);
             if (frag_all) d.flags |= DRAW_FRAG_TEST;
+            b.any_frag_test |= (d.flags & DRAW_FRAG_TEST) != 0;
             b.n_tris += n_tris;
             b.chunk_base.push_back(d.chunk_base);
             b.draws.push_back(d);
@@ -962,7 +963,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     }
     {
         StageTimer t(ctx, s, ST_RASTER);
-        launch_raster(frames_d, draws_d, ctx->tile_off.as<uint32_t>(), ctx->pairs.as<PairRec>(), n_tiles, tiles_per_frame, s);
+        launch_raster(b.any_frag_test, frames_d, draws_d, ctx->tile_off.as<uint32_t>(), ctx->pairs.as<PairRec>(), n_tiles, tiles_per_frame, s);
     }
     {
         StageTimer t(ctx, s, ST_SHADE);
