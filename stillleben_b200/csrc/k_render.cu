@@ -4,7 +4,7 @@
 //   k_raster            warp-per-tile fine raster: per-tile pair lists staged through TMA bulk copies
 //                       (cp.async.bulk + mbarrier) into shared memory, warp-ballot edge tests,
 //                       per-lane z-compare, 64-bit visibility keys
-//   k_shadow            depth-only pass of the shadow casters (atomicMin on d24)
+//   (shadow maps are extra depth-only VIEWS of the same three kernels: front faces culled, d24 output)
 //   k_shade             vertex + fragment stage of the visible fragment of every pixel, fused tone
 //                       map, all render targets stored with 128-bit coalesced writes
 // Replaces steps 6-10 and 14 of sl::RenderPass::render (reference: src/render_pass.cpp:407-622,696-710).
@@ -20,15 +20,6 @@ using namespace slbk;
 // ---------------------------------------------------------------------------------------------
 // setup + binning
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t find_draw(const uint32_t* __restrict__ chunk_base, int n_draws, uint32_t chunk) {
-    int lo = 0, hi = n_draws - 1;   // last draw with chunk_base <= chunk
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (__ldg(chunk_base + mid) <= chunk) lo = mid; else hi = mid - 1;
-    }
-    return (uint32_t)lo;
-}
-
 // can any pixel centre of tile (tx,ty) be covered? (conservative: tests the most-inside corner per edge)
 __device__ __forceinline__ bool tile_may_overlap(const SubTri& t, int tx, int ty, int W, int H) {
     int x0 = tx * SLB_TILE, y0 = ty * SLB_TILE;
@@ -61,24 +52,24 @@ __device__ __forceinline__ void bin_pair(uint32_t tile, const PairRec& rec, uint
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_bin(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws,
-                                                         const uint32_t* __restrict__ chunk_base, int n_draws,
-                                                         uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_off,
-                                                         PairRec* __restrict__ pairs, uint32_t capacity) {
+__global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_bin(const DView* __restrict__ views, const DFrame* __restrict__ frames,
+                                                         const DBinDraw* __restrict__ bdraws, const uint32_t* __restrict__ chunk_draw,
+                                                         uint32_t* __restrict__ tile_count,
+                                                         const uint32_t* __restrict__ tile_off, PairRec* __restrict__ pairs,
+                                                         uint32_t capacity) {
     __shared__ float s_mvp[16];
-    __shared__ uint32_t s_draw;
     __shared__ BigEntry s_big[SLB_BIG_QUEUE];
     __shared__ int s_nbig;
-    if (threadIdx.x == 0) { s_draw = find_draw(chunk_base, n_draws, blockIdx.x); s_nbig = 0; }
-    __syncthreads();
-    const uint32_t di = s_draw;
-    const DDraw& d = draws[di];
+    const uint32_t di = __ldg(chunk_draw + blockIdx.x);   // host-built table: setup chunk -> bin draw
+    const DBinDraw& d = bdraws[di];
     if (threadIdx.x < 16) s_mvp[threadIdx.x] = d.mvp[threadIdx.x];
+    if (threadIdx.x == 32) s_nbig = 0;
     __syncthreads();
-    const DFrame& f = frames[d.frame];
-    const int W = f.W, H = f.H, tiles_x = f.tiles_x;
-    const uint32_t tile_base = f.tile_base;
-    const uint32_t tri = (blockIdx.x - __ldg(chunk_base + di)) * SLB_SETUP_CHUNK + threadIdx.x;
+    const DView& v = views[d.view];
+    const int W = v.W, H = v.H, tiles_x = v.tiles_x;
+    const uint32_t tile_base = v.tile_base;
+    const bool shadow = v.shadow != 0;
+    const uint32_t tri = (blockIdx.x - d.chunk_base) * SLB_SETUP_CHUNK + threadIdx.x;
     if (tri < d.n_tris) {
         const uint32_t* ip = d.idx + 3 * (size_t)tri;
         uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
@@ -86,7 +77,8 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_bin(const DFrame* __restric
         PrimSetup ps;
         bool clipped = false;
         if (setup_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), W, H, ps, &clipped)) {
-            if (EMIT && clipped) {   // publish the clipped polygon once for the fragment test and the shade kernel
+            if (EMIT && clipped && !shadow) {   // publish the clipped polygon once for the fragment test and the shade kernel
+                const DFrame& f = frames[v.frame];
                 uint32_t slot = atomicAdd(f.clip_count, 1u);
                 if (slot < SLB_MAX_CLIP) {
                     ClipRec& cr = f.clip[slot];
@@ -100,6 +92,7 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_bin(const DFrame* __restric
             for (int k = 1; k + 1 < ps.n; ++k) {
                 SubTri st;
                 if (!make_subtri(ps, k, st)) continue;
+                if (shadow && st.twoA < 0) continue;   // shadow views cull FRONT faces (render_pass.cpp:428-429)
                 int px0, py0, px1, py1;
                 if (!subtri_pixel_bbox(st, W, H, px0, py0, px1, py1)) continue;
                 int tx0 = px0 / SLB_TILE, tx1 = px1 / SLB_TILE, ty0 = py0 / SLB_TILE, ty1 = py1 / SLB_TILE;
@@ -109,7 +102,7 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_bin(const DFrame* __restric
                 rec.az = st.az; rec.bz = st.bz; rec.cz = st.cz;
                 rec.seq = d.prim_base + tri;
                 rec.k_flags = (uint32_t)k | ((d.flags & DRAW_FRAG_TEST) ? 0x100u : 0u);
-                rec.draw = di;
+                rec.draw = d.draw;
                 if (ntx * nty == 1) {
                     bin_pair<EMIT>(tile_base + ty0 * tiles_x + tx0, rec, tile_count, tile_off, pairs, capacity);
                 } else if (ntx * nty <= SLB_BIG_TILES) {
@@ -147,24 +140,77 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_bin(const DFrame* __restric
     }
 }
 
-// exclusive scan of n counts into off[0..n] (off[n] = total); one block
-__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ count, uint32_t* __restrict__ off, uint32_t n) {
-    __shared__ uint32_t s_part[1024];
-    const uint32_t per = (n + 1023u) / 1024u;
-    const uint32_t beg = min(n, threadIdx.x * per), end = min(n, beg + per);
-    uint32_t sum = 0;
-    for (uint32_t i = beg; i < end; ++i) sum += count[i];
-    s_part[threadIdx.x] = sum;
+// Exclusive scan of the n tile counts into off[0..n] (off[n] = total pairs) fused with the compaction of the
+// non-empty tiles into active[]: the scanned value packs (pair count, non-empty flag) into 64 bits, so one scan
+// yields both the tile's pair offset and its slot in the active list. Three kernels: block-local scans of 4096
+// items, a scan of the block totals, and a fix-up pass that also writes the ActiveTile records.
+#define SLB_SCAN_ITEMS 4
+#define SLB_SCAN_BLOCK (1024 * SLB_SCAN_ITEMS)
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* s_warp, unsigned long long& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    for (int ofs = 1; ofs < 1024; ofs <<= 1) {   // Hillis-Steele inclusive scan of the partials
-        uint32_t v = (threadIdx.x >= ofs) ? s_part[threadIdx.x - ofs] : 0u;
+    if (warp == 0) {
+        unsigned long long w = s_warp[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return s_warp[warp] + inc - v;
+}
+__device__ __forceinline__ unsigned long long pack_count(uint32_t c) { return (unsigned long long)c | ((unsigned long long)(c != 0) << 32); }
+__global__ void __launch_bounds__(1024) k_scan_local(const uint32_t* __restrict__ count, unsigned long long* __restrict__ block_sums, uint32_t n) {
+    __shared__ unsigned long long s_warp[33];
+    const uint32_t base = blockIdx.x * SLB_SCAN_BLOCK + threadIdx.x * SLB_SCAN_ITEMS;
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < SLB_SCAN_ITEMS; ++i) sum += pack_count((base + i < n) ? count[base + i] : 0u);
+    unsigned long long total;
+    block_exclusive_scan(sum, s_warp, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(unsigned long long* __restrict__ block_sums, uint32_t n_blocks, uint32_t* __restrict__ totals) {
+    __shared__ unsigned long long s_warp[33];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t at = 0; at < n_blocks; at += 1024) {
+        uint32_t i = at + threadIdx.x;
+        unsigned long long v = i < n_blocks ? block_sums[i] : 0ull;
+        unsigned long long total;
+        unsigned long long ex = block_exclusive_scan(v, s_warp, total);
+        if (i < n_blocks) block_sums[i] = s_carry + ex;
         __syncthreads();
-        s_part[threadIdx.x] += v;
+        if (threadIdx.x == 0) s_carry += total;
         __syncthreads();
     }
-    uint32_t run = s_part[threadIdx.x] - sum;
-    for (uint32_t i = beg; i < end; ++i) { off[i] = run; run += count[i]; }
-    if (threadIdx.x == 1023) off[n] = s_part[1023];
+    if (threadIdx.x == 0) { totals[0] = (uint32_t)s_carry; totals[1] = (uint32_t)(s_carry >> 32); }   // pairs, active tiles
+}
+__global__ void __launch_bounds__(1024) k_scan_fix(const uint32_t* __restrict__ count, const unsigned long long* __restrict__ block_sums,
+                                                   uint32_t* __restrict__ off, ActiveTile* __restrict__ active, uint32_t n) {
+    __shared__ unsigned long long s_warp[33];
+    const uint32_t base = blockIdx.x * SLB_SCAN_BLOCK + threadIdx.x * SLB_SCAN_ITEMS;
+    uint32_t c[SLB_SCAN_ITEMS];
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < SLB_SCAN_ITEMS; ++i) { c[i] = (base + i < n) ? count[base + i] : 0u; sum += pack_count(c[i]); }
+    unsigned long long total;
+    unsigned long long run = block_sums[blockIdx.x] + block_exclusive_scan(sum, s_warp, total);
+#pragma unroll
+    for (int i = 0; i < SLB_SCAN_ITEMS; ++i) {
+        if (base + i < n) {
+            off[base + i] = (uint32_t)run;
+            if (c[i]) { ActiveTile a; a.tile = base + i; a.beg = (uint32_t)run; a.count = c[i]; a.pad = 0; active[(uint32_t)(run >> 32)] = a; }
+        }
+        run += pack_count(c[i]);
+    }
+    if (base <= n && n < base + SLB_SCAN_ITEMS) off[n] = (uint32_t)(run);   // run == total here only for the thread covering index n
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -216,25 +262,28 @@ __device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint3
 // z-compare through a 64-bit atomicMin on the tile's key buffer in shared memory; the remaining (large)
 // records are found with a warp ballot and processed by the whole warp, two pixels per lane.
 template <bool FRAG>
-__global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws,
-                                                                   const uint32_t* __restrict__ tile_off,
-                                                                   const PairRec* __restrict__ pairs, uint32_t n_tiles,
-                                                                   uint32_t tiles_per_frame) {
+__global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DView* __restrict__ views, const DFrame* __restrict__ frames,
+                                                                   const DDraw* __restrict__ draws, const ActiveTile* __restrict__ active,
+                                                                   const PairRec* __restrict__ pairs, const RasterGrid g) {
     __shared__ __align__(128) PairRec s_rec[SLB_RASTER_WARPS][2][SLB_RASTER_CHUNK];
     __shared__ unsigned long long s_key[SLB_RASTER_WARPS][SLB_TILE * SLB_TILE];
     __shared__ __align__(8) uint64_t s_bar[SLB_RASTER_WARPS][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t t = blockIdx.x * SLB_RASTER_WARPS + warp;
-    if (t >= n_tiles) return;
-    const uint32_t fi = t / tiles_per_frame, tl = t - fi * tiles_per_frame;
-    const DFrame& f = frames[fi];
-    const int W = f.W, H = f.H;
-    const int tx = tl % f.tiles_x, ty = tl / f.tiles_x;
+    const uint32_t at = blockIdx.x * SLB_RASTER_WARPS + warp;
+    if (at >= g.n_active) return;
+    const ActiveTile act = active[at];   // only non-empty tiles get a warp; the outputs were pre-filled with "empty"
+    const uint32_t t = act.tile;
+    uint32_t vi, tl;   // camera views come first in the tile index space, then the shadow views
+    if (t < g.n_cam_tiles) { vi = t / g.tiles_per_cam; tl = t - vi * g.tiles_per_cam; }
+    else { const uint32_t u = t - g.n_cam_tiles; vi = u / g.tiles_per_shadow; tl = u - vi * g.tiles_per_shadow; vi += g.n_cam_views; }
+    const DView& v = views[vi];
+    const DFrame& f = frames[v.frame];
+    const int W = v.W, H = v.H;
+    const int tx = tl % v.tiles_x, ty = tl / v.tiles_x;
     const int x_lo = tx * SLB_TILE, y_lo = ty * SLB_TILE;
     const int x_hi = min(x_lo + SLB_TILE - 1, W - 1), y_hi = min(y_lo + SLB_TILE - 1, H - 1);
     const int lx = lane & 7, ly = lane >> 3;
-    const uint32_t beg = __ldg(tile_off + t), end = __ldg(tile_off + t + 1);
-    const uint32_t n = end - beg;
+    const uint32_t beg = act.beg, n = act.count;
     unsigned long long* keys = s_key[warp];
     keys[lane] = SLB_KEY_EMPTY; keys[lane + 32] = SLB_KEY_EMPTY;
 
@@ -338,101 +387,16 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DFrame* 
     __syncwarp();
     const int px = x_lo + lx;
     if (px < W) {
-        if (y_lo + ly < H) f.keys[(size_t)(y_lo + ly) * W + px] = keys[ly * SLB_TILE + lx];
-        if (y_lo + ly + 4 < H) f.keys[(size_t)(y_lo + ly + 4) * W + px] = keys[(ly + 4) * SLB_TILE + lx];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// shadow pass: depth only, front faces culled (render_pass.cpp:426-460, shadow_shader.vert:10-13)
-// ---------------------------------------------------------------------------------------------
-struct ShadowBig { int ax, ay, bx, by, cx, cy; float az, bz, cz; int px0, py0, px1, py1; };
-#define SLB_SHADOW_QUEUE 32
-#define SLB_SHADOW_BIG_AREA 1024   // bounding boxes above this many pixels are walked by the whole block
-
-// rasterise one sub-triangle into the d24 map: edge functions evaluated once at the first pixel of the
-// box and stepped exactly in 64-bit integers (same values as the contract's per-pixel evaluation)
-__device__ __forceinline__ void shadow_raster(const SubTri& st, uint32_t* __restrict__ map, int px0, int py0, int px1, int py1,
-                                              int start, int stride) {
-    const int N = SLB_SHADOW_RES;
-    const int cx0 = px0 * 256 + 128, cy0 = py0 * 256 + 128;
-    const long long r0 = st.s * edge_fn(st.bx, st.by, st.cx, st.cy, cx0, cy0) + st.bias0;
-    const long long r1 = st.s * edge_fn(st.cx, st.cy, st.ax, st.ay, cx0, cy0) + st.bias1;
-    const long long r2 = st.s * edge_fn(st.ax, st.ay, st.bx, st.by, cx0, cy0) + st.bias2;
-    const long long dx0 = (long long)(-st.s * (st.cy - st.by)) * 256, dy0 = (long long)(st.s * (st.cx - st.bx)) * 256;
-    const long long dx1 = (long long)(-st.s * (st.ay - st.cy)) * 256, dy1 = (long long)(st.s * (st.ax - st.cx)) * 256;
-    const long long dx2 = (long long)(-st.s * (st.by - st.ay)) * 256, dy2 = (long long)(st.s * (st.bx - st.ax)) * 256;
-    const float dzb = __fsub_rn(st.bz, st.az), dzc = __fsub_rn(st.cz, st.az);
-    auto plot = [&](long long e1, long long e2, int x, int y) {
-        long long w1 = e1 - st.bias1, w2 = e2 - st.bias2;
-        if (st.s < 0) { w1 = -w1; w2 = -w2; }
-        float q1 = __fmul_rn(__ll2float_rn(w1), st.inv2A), q2 = __fmul_rn(__ll2float_rn(w2), st.inv2A);
-        float z = __fmaf_rn(q2, dzc, __fmaf_rn(q1, dzb, st.az));
-        z = fminf(fmaxf(z, 0.0f), 1.0f);
-        atomicMin(map + (size_t)y * N + x, __float2uint_rn(__fmul_rn(z, 16777215.0f)));
-    };
-    if (stride == 1) {   // one thread walks the whole box: pure additions per pixel
-        long long a0 = r0, a1 = r1, a2 = r2;
-        for (int y = py0; y <= py1; ++y, a0 += dy0, a1 += dy1, a2 += dy2) {
-            long long e0 = a0, e1 = a1, e2 = a2;
-            for (int x = px0; x <= px1; ++x, e0 += dx0, e1 += dx1, e2 += dx2)
-                if ((e0 | e1 | e2) >= 0) plot(e1, e2, x, y);
+        if (v.shadow) {   // depth-only view: the d24 plane the PCF lookup reads (cleared to 0xFFFFFF where nothing was drawn)
+            uint32_t* out = reinterpret_cast<uint32_t*>(v.out);
+            const unsigned long long k0 = keys[ly * SLB_TILE + lx], k1 = keys[(ly + 4) * SLB_TILE + lx];
+            if (y_lo + ly < H) out[(size_t)(y_lo + ly) * W + px] = k0 == SLB_KEY_EMPTY ? 0xFFFFFFu : (uint32_t)(k0 >> 40);
+            if (y_lo + ly + 4 < H) out[(size_t)(y_lo + ly + 4) * W + px] = k1 == SLB_KEY_EMPTY ? 0xFFFFFFu : (uint32_t)(k1 >> 40);
+        } else {
+            unsigned long long* out = reinterpret_cast<unsigned long long*>(v.out);
+            if (y_lo + ly < H) out[(size_t)(y_lo + ly) * W + px] = keys[ly * SLB_TILE + lx];
+            if (y_lo + ly + 4 < H) out[(size_t)(y_lo + ly + 4) * W + px] = keys[(ly + 4) * SLB_TILE + lx];
         }
-        return;
-    }
-    const int w = px1 - px0 + 1, n = w * (py1 - py0 + 1);
-    for (int i = start; i < n; i += stride) {
-        const int ix = i % w, iy = i / w;
-        const long long e0 = r0 + dx0 * ix + dy0 * iy, e1 = r1 + dx1 * ix + dy1 * iy, e2 = r2 + dx2 * ix + dy2 * iy;
-        if ((e0 | e1 | e2) >= 0) plot(e1, e2, px0 + ix, py0 + iy);
-    }
-}
-
-__global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_shadow(const DShadowDraw* __restrict__ sdraws,
-                                                            const uint32_t* __restrict__ chunk_base, int n_draws) {
-    __shared__ float s_mvp[16];
-    __shared__ uint32_t s_draw;
-    __shared__ ShadowBig s_big[SLB_SHADOW_QUEUE];
-    __shared__ int s_nbig;
-    if (threadIdx.x == 0) { s_draw = find_draw(chunk_base, n_draws, blockIdx.x); s_nbig = 0; }
-    __syncthreads();
-    const DShadowDraw& d = sdraws[s_draw];
-    if (threadIdx.x < 16) s_mvp[threadIdx.x] = d.mvp[threadIdx.x];
-    __syncthreads();
-    const uint32_t tri = (blockIdx.x - __ldg(chunk_base + s_draw)) * SLB_SETUP_CHUNK + threadIdx.x;
-    const int N = SLB_SHADOW_RES;
-    if (tri < d.n_tris) {
-        const uint32_t* ip = d.idx + 3 * (size_t)tri;
-        uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
-        float4 p0 = __ldg(d.pos4 + i0), p1 = __ldg(d.pos4 + i1), p2 = __ldg(d.pos4 + i2);
-        PrimSetup ps;
-        if (setup_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), N, N, ps)) {
-            for (int k = 1; k + 1 < ps.n; ++k) {
-                SubTri st;
-                if (!make_subtri(ps, k, st)) continue;
-                if (st.twoA < 0) continue;   // cull FRONT faces (render_pass.cpp:428-429)
-                int px0, py0, px1, py1;
-                if (!subtri_pixel_bbox(st, N, N, px0, py0, px1, py1)) continue;
-                if ((px1 - px0 + 1) * (py1 - py0 + 1) > SLB_SHADOW_BIG_AREA) {
-                    int q = atomicAdd(&s_nbig, 1);
-                    if (q < SLB_SHADOW_QUEUE) {
-                        ShadowBig& e = s_big[q];
-                        e.ax = st.ax; e.ay = st.ay; e.bx = st.bx; e.by = st.by; e.cx = st.cx; e.cy = st.cy;
-                        e.az = st.az; e.bz = st.bz; e.cz = st.cz; e.px0 = px0; e.py0 = py0; e.px1 = px1; e.py1 = py1;
-                        continue;
-                    }
-                }
-                shadow_raster(st, d.map, px0, py0, px1, py1, 0, 1);
-            }
-        }
-    }
-    __syncthreads();
-    const int nbig = min(s_nbig, SLB_SHADOW_QUEUE);
-    for (int q = 0; q < nbig; ++q) {
-        const ShadowBig& e = s_big[q];
-        SubTri st;
-        make_subtri(e.ax, e.ay, e.bx, e.by, e.cx, e.cy, e.az, e.bz, e.cz, st);
-        shadow_raster(st, d.map, e.px0, e.py0, e.px1, e.py1, threadIdx.x, SLB_SETUP_CHUNK);
     }
 }
 
@@ -509,23 +473,25 @@ __global__ void __launch_bounds__(256) k_shade(const DFrame* __restrict__ frames
 // ---------------------------------------------------------------------------------------------
 namespace slbk {
 
-void launch_bin(bool emit, const DFrame* frames, const DDraw* draws, const uint32_t* chunk_base, int n_draws, uint32_t n_chunks,
-                uint32_t* tile_count, const uint32_t* tile_off, PairRec* pairs, uint32_t capacity, cudaStream_t s) {
+void launch_bin(bool emit, const DView* views, const DFrame* frames, const DBinDraw* bdraws, const uint32_t* chunk_draw,
+                uint32_t n_chunks, uint32_t* tile_count, const uint32_t* tile_off, PairRec* pairs, uint32_t capacity, cudaStream_t s) {
     if (n_chunks == 0) return;
-    if (emit) k_bin<true><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(frames, draws, chunk_base, n_draws, tile_count, tile_off, pairs, capacity);
-    else k_bin<false><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(frames, draws, chunk_base, n_draws, tile_count, tile_off, pairs, capacity);
+    if (emit) k_bin<true><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tile_count, tile_off, pairs, capacity);
+    else k_bin<false><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tile_count, tile_off, pairs, capacity);
 }
-void launch_scan(const uint32_t* count, uint32_t* off, uint32_t n, cudaStream_t s) { k_scan<<<1, 1024, 0, s>>>(count, off, n); }
-void launch_raster(bool frag_test, const DFrame* frames, const DDraw* draws, const uint32_t* tile_off, const PairRec* pairs,
-                   uint32_t n_tiles, uint32_t tiles_per_frame, cudaStream_t s) {
-    if (n_tiles == 0) return;
-    const unsigned grid = (n_tiles + SLB_RASTER_WARPS - 1) / SLB_RASTER_WARPS;
-    if (frag_test) k_raster<true><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(frames, draws, tile_off, pairs, n_tiles, tiles_per_frame);
-    else k_raster<false><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(frames, draws, tile_off, pairs, n_tiles, tiles_per_frame);
+void launch_scan(const uint32_t* count, uint32_t* off, ActiveTile* active, unsigned long long* block_sums, uint32_t* totals, uint32_t n,
+                 cudaStream_t s) {
+    const uint32_t n_blocks = (n + 1 + SLB_SCAN_BLOCK - 1) / SLB_SCAN_BLOCK;   // n + 1: some thread must own index n (the total)
+    k_scan_local<<<n_blocks, 1024, 0, s>>>(count, block_sums, n);
+    k_scan_sums<<<1, 1024, 0, s>>>(block_sums, n_blocks, totals);
+    k_scan_fix<<<n_blocks, 1024, 0, s>>>(count, block_sums, off, active, n);
 }
-void launch_shadow(const DShadowDraw* sdraws, const uint32_t* chunk_base, int n_draws, uint32_t n_chunks, cudaStream_t s) {
-    if (n_chunks == 0) return;
-    k_shadow<<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(sdraws, chunk_base, n_draws);
+void launch_raster(bool frag_test, const DView* views, const DFrame* frames, const DDraw* draws, const ActiveTile* active,
+                   const PairRec* pairs, RasterGrid g, cudaStream_t s) {
+    if (g.n_active == 0) return;
+    const unsigned grid = (g.n_active + SLB_RASTER_WARPS - 1) / SLB_RASTER_WARPS;
+    if (frag_test) k_raster<true><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(views, frames, draws, active, pairs, g);
+    else k_raster<false><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(views, frames, draws, active, pairs, g);
 }
 void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, cudaStream_t s) {
     dim3 grid((W + 31) / 32, (H + 7) / 8, n_frames);

@@ -40,8 +40,8 @@ struct DDraw {
     const uint32_t* idx;           // already offset to the sub-mesh's first index
     uint32_t n_tris;
     uint32_t prim_base;            // sequence number of triangle 0 within the frame (submission order)
-    uint32_t chunk_base;           // first setup chunk of this draw within the batch
     uint32_t frame;                // frame index within the batch
+    uint32_t pad0;
     float mvp[16];
     float meshToObject[16], objectToWorld[16];
     float normalToWorld[9];
@@ -57,14 +57,26 @@ struct DDraw {
 };
 enum { DRAW_FRAG_TEST = 1u };      // coverage depends on the fragment stage (alpha test / depth peel)
 
-struct DShadowDraw {
+// What the binner needs of one draw. Camera views and shadow views go through the SAME setup / bin / raster
+// kernels: a shadow map is just another view with its own tile grid, front faces culled and depth-only output.
+struct DBinDraw {
     const float4* pos4;
     const uint32_t* idx;
     uint32_t n_tris;
-    uint32_t chunk_base;
-    uint32_t* map;                 // SLB_SHADOW_RES^2 d24 values
-    uint32_t pad;
+    uint32_t chunk_base;           // first setup chunk of this draw within the batch
+    uint32_t prim_base;            // sequence number of triangle 0 within its view
+    uint32_t view;                 // index into DView[]
+    uint32_t draw;                 // index into DDraw[] (camera views; used by the fragment-test path)
+    uint32_t flags;                // DRAW_*
     float mvp[16];
+};
+struct DView {
+    int32_t W, H, tiles_x, tiles_y;
+    uint32_t tile_base;            // first tile of this view in the batch-wide tile arrays
+    int32_t shadow;                // 1: cull front faces, write d24 only (render_pass.cpp:426-460)
+    uint32_t frame;                // DFrame index (camera views)
+    uint32_t pad;
+    void* out;                     // uint64 keys[H*W] (camera) or uint32 d24[H*W] (shadow)
 };
 
 // A primitive that needed polygon clipping, written once by the binner so that the raster's fragment test
@@ -75,7 +87,7 @@ struct ClipRec { uint32_t seq; int32_t n; DPolyV v[10]; };
 
 struct DFrame {
     int32_t W, H, tiles_x, tiles_y;
-    uint32_t tile_base;            // first tile of this frame in the batch-wide tile arrays
+    uint32_t pad1;
     uint32_t draw_begin, draw_end;
     uint32_t n_prims;
     float P[16], V[16], Pinv[16];
@@ -112,6 +124,9 @@ struct __align__(16) PairRec {
     uint32_t draw;                    // index into DDraw[] (fragment-test path only)
 };
 static_assert(sizeof(PairRec) == 48, "PairRec must be 48 bytes");
+
+// a non-empty tile: what one raster warp needs to start (written by the scan's fix-up pass)
+struct ActiveTile { uint32_t tile, beg, count, pad; };
 
 // visibility key: depth24 << 40 | seq << 8 | k   (min == GL_LESS + first draw wins on ties)
 #define SLB_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull

@@ -74,7 +74,7 @@ struct slb_ctx {
     // assets owned by the context
     slb_mesh* plane = nullptr;
     // per-batch device arrays
-    DevBuf frames_d, draws_d, chunk_base_d, sdraws_d, schunk_base_d;
+    DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals;
     DevBuf clip_recs, clip_counts;
     DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, ao, avg, mip_a, mip_b, shadow_maps;
     // pinned staging
@@ -201,7 +201,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
         if (ctx->slot_rendered[i]) cudaEventDestroy(ctx->slot_rendered[i]);
         if (ctx->slot_copied[i]) cudaEventDestroy(ctx->slot_copied[i]);
     }
-    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->sdraws_d, &ctx->schunk_base_d, &ctx->tile_count,
+    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->tile_count,
                       &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->ao,
                       &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts};
     for (DevBuf* b : bufs) b->release();
@@ -595,11 +595,10 @@ namespace {
 struct Batch {
     std::vector<DFrame> frames;
     std::vector<DDraw> draws;
-    std::vector<uint32_t> chunk_base;     // per draw (+1 sentinel)
-    std::vector<DShadowDraw> sdraws;
-    std::vector<uint32_t> schunk_base;
-    std::vector<int> frame_first_light_slot;   // index of the frame's first shadow map in the batch pool
-    uint32_t n_chunks = 0, n_schunks = 0, n_shadow_maps = 0;
+    std::vector<DView> views;             // camera views [0, n) then shadow views
+    std::vector<DBinDraw> bdraws;         // camera + shadow draws in creation order
+    std::vector<uint32_t> chunk_draw;     // setup chunk -> bin draw
+    uint32_t n_chunks = 0, n_shadow_maps = 0;
     uint64_t n_tris = 0;
     bool fused = true, any_ssao = false, any_auto = false, any_bg = false, any_frag_test = false;
 };
@@ -727,12 +726,18 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
     const int W = result->W, H = result->H;
     const int tiles_x = (W + SLB_TILE - 1) / SLB_TILE, tiles_y = (H + SLB_TILE - 1) / SLB_TILE;
     b.frames.resize(n);
+    b.views.resize(n);
     for (int j = 0; j < n; ++j) {
         const slb_scene_desc& sc = scenes[j];
         DFrame& f = b.frames[j];
         std::memset(&f, 0, sizeof f);
         f.W = W; f.H = H; f.tiles_x = tiles_x; f.tiles_y = tiles_y;
-        f.tile_base = (uint32_t)j * tiles_x * tiles_y;
+        {
+            DView& cv = b.views[j];
+            std::memset(&cv, 0, sizeof cv);
+            cv.W = W; cv.H = H; cv.tiles_x = tiles_x; cv.tiles_y = tiles_y;
+            cv.tile_base = (uint32_t)j * tiles_x * tiles_y; cv.shadow = 0; cv.frame = (uint32_t)j;
+        }
         Mat4 P = load(sc.projection), V = load(sc.world_to_cam);
         std::memcpy(f.P, P.m, 64); std::memcpy(f.V, V.m, 64);
         Mat4 Pinv = inverted(P); std::memcpy(f.Pinv, Pinv.m, 64);
@@ -769,14 +774,19 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
         auto push_draw = [&](DDraw& d, uint32_t n_tris) {
             d.n_tris = n_tris; d.prim_base = prim; prim += n_tris;
             d.frame = (uint32_t)j;
-            d.chunk_base = b.n_chunks; b.n_chunks += chunks_of(n_tris);
             Mat4 o2w = load(d.objectToWorld), m2o = load(d.meshToObject);
             mvp(P, V, o2w, m2o, d.mvp);
             normal_matrix(mul(o2w, m2o), d.normalToWorld);
             if (frag_all) d.flags |= DRAW_FRAG_TEST;
             b.any_frag_test |= (d.flags & DRAW_FRAG_TEST) != 0;
             b.n_tris += n_tris;
-            b.chunk_base.push_back(d.chunk_base);
+            DBinDraw bd; std::memset(&bd, 0, sizeof bd);
+            bd.pos4 = d.pos4; bd.idx = d.idx; bd.n_tris = n_tris; bd.prim_base = d.prim_base; bd.view = (uint32_t)j;
+            bd.draw = (uint32_t)b.draws.size(); bd.flags = d.flags;
+            std::memcpy(bd.mvp, d.mvp, 64);
+            bd.chunk_base = b.n_chunks; b.n_chunks += chunks_of(n_tris);
+            b.chunk_draw.insert(b.chunk_draw.end(), chunks_of(n_tris), (uint32_t)b.bdraws.size());
+            b.bdraws.push_back(bd);
             b.draws.push_back(d);
         };
         if (sc.background_plane_size[0] * sc.background_plane_size[0] + sc.background_plane_size[1] * sc.background_plane_size[1] > 0) {
@@ -817,35 +827,40 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
         f.draw_end = (uint32_t)b.draws.size();
         f.n_prims = prim;
 
-        // ---- shadow pass set-up (render_pass.cpp:407-460) ----
-        b.frame_first_light_slot.push_back((int)b.n_shadow_maps);
+        // ---- shadow views (render_pass.cpp:407-460): one 2048^2 depth-only view per active light ----
         if (anyLight) {
             Vec3 corners[8]; frustum_corners(sc, corners);
+            const int stiles = SLB_SHADOW_RES / SLB_TILE;
             for (int li = 0; li < SLB_NUM_LIGHTS; ++li) {
                 if (!f.lightActive[li]) continue;
                 Mat4 sm = shadow_matrix(sc, corners, v3(f.lightDir[li][0], f.lightDir[li][1], f.lightDir[li][2]));
                 std::memcpy(f.shadowMat[li], sm.m, 64);
                 const uint32_t slot = b.n_shadow_maps++;
                 f.shadowMap[li] = reinterpret_cast<const uint32_t*>((uintptr_t)slot);   // patched to a pointer once the pool is sized
+                DView sv; std::memset(&sv, 0, sizeof sv);
+                sv.W = sv.H = SLB_SHADOW_RES; sv.tiles_x = sv.tiles_y = stiles;
+                sv.tile_base = (uint32_t)n * tiles_x * tiles_y + slot * (uint32_t)(stiles * stiles);
+                sv.shadow = 1; sv.frame = (uint32_t)j;
+                const uint32_t view_index = (uint32_t)n + slot;
+                b.views.push_back(sv);
+                uint32_t sprim = 0;
                 for (int i = 0; i < sc.n_objects; ++i) {
                     const slb_object_desc& o = sc.objects[i];
                     if (!o.visible || !o.casts_shadows) continue;
                     const slb_mesh* mesh = o.mesh;
-                    for (const slb_submesh& s : mesh->submeshes) {
-                        DShadowDraw sd; std::memset(&sd, 0, sizeof sd);
-                        sd.pos4 = mesh->pos4; sd.idx = mesh->idx + s.index_offset; sd.n_tris = s.index_count / 3;
-                        sd.chunk_base = b.n_schunks; b.n_schunks += chunks_of(sd.n_tris);
-                        sd.map = reinterpret_cast<uint32_t*>((uintptr_t)slot);
-                        mvp(sm, identity(), load(o.pose), load(o.pretransform), sd.mvp);
-                        b.schunk_base.push_back(sd.chunk_base);
-                        b.sdraws.push_back(sd);
+                    for (const slb_submesh& sub : mesh->submeshes) {
+                        DBinDraw bd; std::memset(&bd, 0, sizeof bd);
+                        bd.pos4 = mesh->pos4; bd.idx = mesh->idx + sub.index_offset; bd.n_tris = sub.index_count / 3;
+                        bd.prim_base = sprim; sprim += bd.n_tris; bd.view = view_index;
+                        mvp(sm, identity(), load(o.pose), load(o.pretransform), bd.mvp);
+                        bd.chunk_base = b.n_chunks; b.n_chunks += chunks_of(bd.n_tris);
+                        b.chunk_draw.insert(b.chunk_draw.end(), chunks_of(bd.n_tris), (uint32_t)b.bdraws.size());
+                        b.bdraws.push_back(bd);
                     }
                 }
             }
         }
     }
-    b.chunk_base.push_back(b.n_chunks);
-    b.schunk_base.push_back(b.n_schunks);
 }
 
 static cudaEvent_t get_event(slb_ctx* ctx) {
@@ -866,17 +881,24 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     build_batch(ctx, scenes, n, result, first_frame, depth_peel, b);
     const int W = result->W, H = result->H;
     const size_t npx = (size_t)W * H;
-    const uint32_t tiles_per_frame = (uint32_t)b.frames[0].tiles_x * b.frames[0].tiles_y;
-    const uint32_t n_tiles = tiles_per_frame * (uint32_t)n;
+    const uint32_t tiles_per_cam = (uint32_t)b.frames[0].tiles_x * b.frames[0].tiles_y;
+    const uint32_t tiles_per_shadow = (uint32_t)(SLB_SHADOW_RES / SLB_TILE) * (SLB_SHADOW_RES / SLB_TILE);
+    RasterGrid grid;
+    grid.n_cam_tiles = tiles_per_cam * (uint32_t)n; grid.tiles_per_cam = tiles_per_cam; grid.n_cam_views = (uint32_t)n;
+    grid.tiles_per_shadow = tiles_per_shadow; grid.n_active = 0;
+    const uint32_t n_tiles = grid.n_cam_tiles + tiles_per_shadow * b.n_shadow_maps;
 
     // ---- device scratch ----
     CU(ctx->frames_d.reserve(b.frames.size() * sizeof(DFrame)));
     CU(ctx->draws_d.reserve((b.draws.size() + 1) * sizeof(DDraw)));
-    CU(ctx->chunk_base_d.reserve(b.chunk_base.size() * 4));
-    CU(ctx->sdraws_d.reserve((b.sdraws.size() + 1) * sizeof(DShadowDraw)));
-    CU(ctx->schunk_base_d.reserve(b.schunk_base.size() * 4));
+    CU(ctx->views_d.reserve(b.views.size() * sizeof(DView)));
+    CU(ctx->bdraws_d.reserve((b.bdraws.size() + 1) * sizeof(DBinDraw)));
+    CU(ctx->chunk_base_d.reserve((b.chunk_draw.size() + 1) * 4));
     CU(ctx->tile_count.reserve((size_t)n_tiles * 4, true));
     CU(ctx->tile_off.reserve(((size_t)n_tiles + 1) * 4));
+    CU(ctx->scan_sums.reserve(((size_t)n_tiles / 4096 + 2) * 8));
+    CU(ctx->active_tiles.reserve((size_t)n_tiles * sizeof(ActiveTile)));
+    CU(ctx->scan_totals.reserve(64));
     CU(ctx->keys.reserve(npx * n * 8));
     CU(ctx->clip_recs.reserve((size_t)n * SLB_MAX_CLIP * sizeof(ClipRec)));
     CU(ctx->clip_counts.reserve((size_t)n * 4));
@@ -896,6 +918,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     for (int j = 0; j < n; ++j) {
         DFrame& f = b.frames[j];
         f.keys = ctx->keys.as<uint64_t>() + npx * j;
+        b.views[j].out = f.keys;
         f.clip = ctx->clip_recs.as<ClipRec>() + (size_t)j * SLB_MAX_CLIP;
         f.clip_count = ctx->clip_counts.as<uint32_t>() + j;
         f.fused_tonemap = b.fused ? 1 : 0;
@@ -911,65 +934,70 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
             if (!f.scratch_cam && b.any_ssao) f.scratch_cam = ctx->scratch_cam.as<float4>() + npx * j;
         }
     }
-    for (DShadowDraw& sd : b.sdraws) sd.map = smaps + smap_elems * (uintptr_t)sd.map;
+    for (uint32_t sidx = 0; sidx < b.n_shadow_maps; ++sidx) b.views[n + sidx].out = smaps + smap_elems * sidx;
 
     // ---- one staged upload ----
-    const size_t sz_f = b.frames.size() * sizeof(DFrame), sz_d = b.draws.size() * sizeof(DDraw), sz_c = b.chunk_base.size() * 4,
-                 sz_s = b.sdraws.size() * sizeof(DShadowDraw), sz_sc = b.schunk_base.size() * 4;
-    int rc = ensure_staging(ctx, sz_f + sz_d + sz_c + sz_s + sz_sc + 64);
+    const size_t sz[5] = {b.frames.size() * sizeof(DFrame), b.draws.size() * sizeof(DDraw), b.views.size() * sizeof(DView),
+                          b.bdraws.size() * sizeof(DBinDraw), b.chunk_draw.size() * 4};
+    const void* src[5] = {b.frames.data(), b.draws.data(), b.views.data(), b.bdraws.data(), b.chunk_draw.data()};
+    void* dst[5] = {ctx->frames_d.p, ctx->draws_d.p, ctx->views_d.p, ctx->bdraws_d.p, ctx->chunk_base_d.p};
+    size_t total_sz = 0;
+    for (int i = 0; i < 5; ++i) total_sz += (sz[i] + 63) & ~(size_t)63;
+    int rc = ensure_staging(ctx, total_sz + 64);
     if (rc != SLB_OK) return rc;
-    uint8_t* st = (uint8_t*)ctx->staging;
-    std::memcpy(st, b.frames.data(), sz_f);
-    std::memcpy(st + sz_f, b.draws.data(), sz_d);
-    std::memcpy(st + sz_f + sz_d, b.chunk_base.data(), sz_c);
-    std::memcpy(st + sz_f + sz_d + sz_c, b.sdraws.data(), sz_s);
-    std::memcpy(st + sz_f + sz_d + sz_c + sz_s, b.schunk_base.data(), sz_sc);
-    CU(cudaMemcpyAsync(ctx->frames_d.p, st, sz_f, cudaMemcpyHostToDevice, s));
-    if (sz_d) CU(cudaMemcpyAsync(ctx->draws_d.p, st + sz_f, sz_d, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->chunk_base_d.p, st + sz_f + sz_d, sz_c, cudaMemcpyHostToDevice, s));
-    if (sz_s) CU(cudaMemcpyAsync(ctx->sdraws_d.p, st + sz_f + sz_d + sz_c, sz_s, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(ctx->schunk_base_d.p, st + sz_f + sz_d + sz_c + sz_s, sz_sc, cudaMemcpyHostToDevice, s));
-    ctx->stats.bytes_h2d += sz_f + sz_d + sz_c + sz_s + sz_sc;
-
+    {
+        uint8_t* st = (uint8_t*)ctx->staging;
+        size_t at = 0;
+        for (int i = 0; i < 5; ++i) {
+            if (sz[i]) {
+                std::memcpy(st + at, src[i], sz[i]);
+                CU(cudaMemcpyAsync(dst[i], st + at, sz[i], cudaMemcpyHostToDevice, s));
+            }
+            at += (sz[i] + 63) & ~(size_t)63;
+            ctx->stats.bytes_h2d += sz[i];
+        }
+    }
     const DFrame* frames_d = ctx->frames_d.as<DFrame>();
     const DDraw* draws_d = ctx->draws_d.as<DDraw>();
+    const DView* views_d = ctx->views_d.as<DView>();
+    const DBinDraw* bdraws_d = ctx->bdraws_d.as<DBinDraw>();
 
     CU(cudaMemsetAsync(ctx->clip_counts.p, 0, (size_t)n * 4, s));
-    // ---- shadow pass ----
-    if (b.n_shadow_maps) {
+    {   // "nothing drawn": keys = all ones, shadow d24 >= 0xFFFFFF; only non-empty tiles get a raster warp
         StageTimer t(ctx, s, ST_SHADOW);
-        CU(cudaMemsetAsync(smaps, 0xFF, smap_elems * 4 * b.n_shadow_maps, s));
-        launch_shadow(ctx->sdraws_d.as<DShadowDraw>(), ctx->schunk_base_d.as<uint32_t>(), (int)b.sdraws.size(), b.n_schunks, s);
-        if (b.n_schunks) ctx->stats.kernel_launches += 1;
+        CU(cudaMemsetAsync(ctx->keys.p, 0xFF, npx * n * 8, s));
+        if (b.n_shadow_maps) CU(cudaMemsetAsync(smaps, 0xFF, smap_elems * 4 * b.n_shadow_maps, s));
     }
-    // ---- bin: count, scan, emit ----
+    // ---- bin (camera + shadow views together): count, scan, emit ----
     {
         StageTimer t(ctx, s, ST_COUNT);
-        launch_bin(false, frames_d, draws_d, ctx->chunk_base_d.as<uint32_t>(), (int)b.draws.size(), b.n_chunks, ctx->tile_count.as<uint32_t>(),
-                   ctx->tile_off.as<uint32_t>(), nullptr, 0, s);
+        launch_bin(false, views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks,
+                   ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), nullptr, 0, s);
     }
     {
         StageTimer t(ctx, s, ST_SCAN);
-        launch_scan(ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), n_tiles, s);
+        launch_scan(ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->active_tiles.as<ActiveTile>(),
+                    ctx->scan_sums.as<unsigned long long>(), ctx->scan_totals.as<uint32_t>(), n_tiles, s);
     }
-    CU(cudaMemcpyAsync(ctx->total_pinned, ctx->tile_off.as<uint32_t>() + n_tiles, 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));   // the pair buffer is sized from the exact total
-    const uint32_t total_pairs = *ctx->total_pinned;
+    CU(cudaMemcpyAsync(ctx->total_pinned, ctx->scan_totals.p, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));   // the pair buffer and the raster grid are sized from the exact totals
+    const uint32_t total_pairs = ctx->total_pinned[0];
+    grid.n_active = ctx->total_pinned[1];
     CU(ctx->pairs.reserve(((size_t)total_pairs + 1) * sizeof(PairRec)));
     {
         StageTimer t(ctx, s, ST_EMIT);
-        launch_bin(true, frames_d, draws_d, ctx->chunk_base_d.as<uint32_t>(), (int)b.draws.size(), b.n_chunks, ctx->tile_count.as<uint32_t>(),
-                   ctx->tile_off.as<uint32_t>(), ctx->pairs.as<PairRec>(), total_pairs, s);
+        launch_bin(true, views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks,
+                   ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->pairs.as<PairRec>(), total_pairs, s);
     }
     {
         StageTimer t(ctx, s, ST_RASTER);
-        launch_raster(b.any_frag_test, frames_d, draws_d, ctx->tile_off.as<uint32_t>(), ctx->pairs.as<PairRec>(), n_tiles, tiles_per_frame, s);
+        launch_raster(b.any_frag_test, views_d, frames_d, draws_d, ctx->active_tiles.as<ActiveTile>(), ctx->pairs.as<PairRec>(), grid, s);
     }
     {
         StageTimer t(ctx, s, ST_SHADE);
         launch_shade(frames_d, draws_d, n, W, H, s);
     }
-    ctx->stats.kernel_launches += (b.n_chunks ? 2 : 0) + 3;
+    ctx->stats.kernel_launches += (b.n_chunks ? 2 : 0) + 5;
     if (post) {
         if (b.any_auto) {   // 1x1 level of the mip chain of the HDR target, taken before background / SSAO
             StageTimer t(ctx, s, ST_POST);
