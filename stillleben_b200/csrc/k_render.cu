@@ -51,12 +51,97 @@ __device__ __forceinline__ void bin_pair(uint32_t tile, const PairRec& rec, uint
     }
 }
 
+// bins one snapped sub-triangle; returns the number of (tile, sub-triangle) pairs it produced (big ones are queued
+// for the whole block and reported as 1)
+template <bool EMIT>
+__device__ __forceinline__ int bin_subtri(int ax, int ay, int bx, int by, int cx, int cy, float az, float bz, float cz, uint32_t seq,
+                                          uint32_t k_flags, uint32_t draw, bool shadow, int W, int H, int tiles_x, uint32_t tile_base,
+                                          uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_off,
+                                          PairRec* __restrict__ pairs, uint32_t capacity, BigEntry* s_big, int* s_nbig) {
+    // pixel box first: most rejected sub-triangles die here, before any 64-bit arithmetic
+    const int xmin = min(ax, min(bx, cx)), xmax = max(ax, max(bx, cx));
+    const int ymin = min(ay, min(by, cy)), ymax = max(ay, max(by, cy));
+    const int px0 = max(0, (xmin - 128 + 255) >> 8), px1 = min(W - 1, (xmax - 128) >> 8);
+    const int py0 = max(0, (ymin - 128 + 255) >> 8), py1 = min(H - 1, (ymax - 128) >> 8);
+    if (px0 > px1 || py0 > py1) return 0;
+    const long long twoA = edge_fn(ax, ay, bx, by, cx, cy);
+    if (twoA == 0) return 0;
+    if (shadow && twoA < 0) return 0;   // shadow views cull FRONT faces (render_pass.cpp:428-429)
+    const int tx0 = px0 / SLB_TILE, tx1 = px1 / SLB_TILE, ty0 = py0 / SLB_TILE, ty1 = py1 / SLB_TILE;
+    const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
+    PairRec rec;
+    rec.ax = ax; rec.ay = ay; rec.bx = bx; rec.by = by; rec.cx = cx; rec.cy = cy;
+    rec.az = az; rec.bz = bz; rec.cz = cz;
+    rec.seq = seq; rec.k_flags = k_flags; rec.draw = draw;
+    if (ntx * nty == 1) {
+        bin_pair<EMIT>(tile_base + ty0 * tiles_x + tx0, rec, tile_count, tile_off, pairs, capacity);
+        return 1;
+    }
+    if (ntx * nty == 2) {
+        bin_pair<EMIT>(tile_base + ty0 * tiles_x + tx0, rec, tile_count, tile_off, pairs, capacity);
+        bin_pair<EMIT>(tile_base + ty1 * tiles_x + tx1, rec, tile_count, tile_off, pairs, capacity);
+        return 2;
+    }
+    if (ntx * nty > SLB_BIG_TILES) {
+        int q = atomicAdd(s_nbig, 1);
+        if (q < SLB_BIG_QUEUE) {
+            s_big[q].rec = rec; s_big[q].tx0 = tx0; s_big[q].ty0 = ty0; s_big[q].ntx = ntx; s_big[q].nty = nty;
+            return 1;
+        }
+    }
+    SubTri st;
+    st.ax = ax; st.ay = ay; st.bx = bx; st.by = by; st.cx = cx; st.cy = cy;
+    st.s = twoA > 0 ? 1 : -1;
+    st.bias0 = top_left(cx - bx, cy - by, st.s) ? 0 : -1;
+    st.bias1 = top_left(ax - cx, ay - cy, st.s) ? 0 : -1;
+    st.bias2 = top_left(bx - ax, by - ay, st.s) ? 0 : -1;
+    int n = 0;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx)
+            if (tile_may_overlap(st, tx, ty, W, H)) {
+                bin_pair<EMIT>(tile_base + ty * tiles_x + tx, rec, tile_count, tile_off, pairs, capacity);
+                ++n;
+            }
+    return n;
+}
+
+// primitives that need polygon clipping (rare: the background plane, triangles crossing the near plane)
+template <bool EMIT>
+static __device__ __noinline__ int bin_clipped(const float* mvp, float3 p0, float3 p1, float3 p2, uint32_t seq, uint32_t flags,
+                                               uint32_t draw, bool shadow, const DFrame* fr, int W, int H, int tiles_x, uint32_t tile_base,
+                                               uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_off,
+                                               PairRec* __restrict__ pairs, uint32_t capacity, BigEntry* s_big, int* s_nbig) {
+    PrimSetup ps;
+    if (!setup_prim(mvp, p0, p1, p2, W, H, ps)) return 0;
+    if (EMIT && fr) {   // publish the clipped polygon once for the fragment test and the shade kernel
+        uint32_t slot = atomicAdd(fr->clip_count, 1u);
+        if (slot < SLB_MAX_CLIP) {
+            ClipRec& cr = fr->clip[slot];
+            cr.seq = seq; cr.n = ps.n;
+            for (int i = 0; i < ps.n; ++i) {
+                cr.v[i].X = ps.v[i].X; cr.v[i].Y = ps.v[i].Y; cr.v[i].z = ps.v[i].z; cr.v[i].invw = ps.v[i].invw;
+                cr.v[i].b[0] = ps.v[i].b[0]; cr.v[i].b[1] = ps.v[i].b[1]; cr.v[i].b[2] = ps.v[i].b[2];
+            }
+        }
+    }
+    int n = 0;
+    for (int k = 1; k + 1 < ps.n; ++k) {
+        const PolyV &a = ps.v[0], &b = ps.v[k], &c = ps.v[k + 1];
+        n += bin_subtri<EMIT>(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, (uint32_t)k | flags, draw, shadow, W, H, tiles_x, tile_base,
+                              tile_count, tile_off, pairs, capacity, s_big, s_nbig);
+    }
+    return n;
+}
+
+// Triangle setup + binning, one thread per triangle, one block per 256-triangle chunk of one draw. Pass 1 (EMIT =
+// false) counts pairs per tile and records, one bit per triangle, whether the triangle produced any pair; pass 2
+// (EMIT = true) skips the triangles whose bit is clear and writes the PairRecs into the tile segments.
 template <bool EMIT>
 __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_bin(const DView* __restrict__ views, const DFrame* __restrict__ frames,
-                                                         const DBinDraw* __restrict__ bdraws, const uint32_t* __restrict__ chunk_draw,
-                                                         uint32_t* __restrict__ tile_count,
-                                                         const uint32_t* __restrict__ tile_off, PairRec* __restrict__ pairs,
-                                                         uint32_t capacity) {
+                                                            const DBinDraw* __restrict__ bdraws, const uint32_t* __restrict__ chunk_draw,
+                                                            uint32_t* __restrict__ tri_mask, uint32_t* __restrict__ tile_count,
+                                                            const uint32_t* __restrict__ tile_off, PairRec* __restrict__ pairs,
+                                                            uint32_t capacity) {
     __shared__ float s_mvp[16];
     __shared__ BigEntry s_big[SLB_BIG_QUEUE];
     __shared__ int s_nbig;
@@ -70,60 +155,37 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_bin(const DView* __restr
     const uint32_t tile_base = v.tile_base;
     const bool shadow = v.shadow != 0;
     const uint32_t tri = (blockIdx.x - d.chunk_base) * SLB_SETUP_CHUNK + threadIdx.x;
-    if (tri < d.n_tris) {
+    const uint32_t mask_word = blockIdx.x * (SLB_SETUP_CHUNK / 32) + (threadIdx.x >> 5);
+    bool active = tri < d.n_tris;
+    if (EMIT) active = active && ((__ldg(tri_mask + mask_word) >> (threadIdx.x & 31)) & 1u);
+    int produced = 0;
+    if (active) {
         const uint32_t* ip = d.idx + 3 * (size_t)tri;
-        uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
-        float4 p0 = __ldg(d.pos4 + i0), p1 = __ldg(d.pos4 + i1), p2 = __ldg(d.pos4 + i2);
-        PrimSetup ps;
-        bool clipped = false;
-        if (setup_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), W, H, ps, &clipped)) {
-            if (EMIT && clipped && !shadow) {   // publish the clipped polygon once for the fragment test and the shade kernel
-                const DFrame& f = frames[v.frame];
-                uint32_t slot = atomicAdd(f.clip_count, 1u);
-                if (slot < SLB_MAX_CLIP) {
-                    ClipRec& cr = f.clip[slot];
-                    cr.seq = d.prim_base + tri; cr.n = ps.n;
-                    for (int i = 0; i < ps.n; ++i) {
-                        cr.v[i].X = ps.v[i].X; cr.v[i].Y = ps.v[i].Y; cr.v[i].z = ps.v[i].z; cr.v[i].invw = ps.v[i].invw;
-                        cr.v[i].b[0] = ps.v[i].b[0]; cr.v[i].b[1] = ps.v[i].b[1]; cr.v[i].b[2] = ps.v[i].b[2];
-                    }
-                }
-            }
-            for (int k = 1; k + 1 < ps.n; ++k) {
-                SubTri st;
-                if (!make_subtri(ps, k, st)) continue;
-                if (shadow && st.twoA < 0) continue;   // shadow views cull FRONT faces (render_pass.cpp:428-429)
-                int px0, py0, px1, py1;
-                if (!subtri_pixel_bbox(st, W, H, px0, py0, px1, py1)) continue;
-                int tx0 = px0 / SLB_TILE, tx1 = px1 / SLB_TILE, ty0 = py0 / SLB_TILE, ty1 = py1 / SLB_TILE;
-                int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
-                PairRec rec;
-                rec.ax = st.ax; rec.ay = st.ay; rec.bx = st.bx; rec.by = st.by; rec.cx = st.cx; rec.cy = st.cy;
-                rec.az = st.az; rec.bz = st.bz; rec.cz = st.cz;
-                rec.seq = d.prim_base + tri;
-                rec.k_flags = (uint32_t)k | ((d.flags & DRAW_FRAG_TEST) ? 0x100u : 0u);
-                rec.draw = d.draw;
-                if (ntx * nty == 1) {
-                    bin_pair<EMIT>(tile_base + ty0 * tiles_x + tx0, rec, tile_count, tile_off, pairs, capacity);
-                } else if (ntx * nty <= SLB_BIG_TILES) {
-                    const bool test = ntx * nty > 2;
-                    for (int ty = ty0; ty <= ty1; ++ty)
-                        for (int tx = tx0; tx <= tx1; ++tx)
-                            if (!test || tile_may_overlap(st, tx, ty, W, H))
-                                bin_pair<EMIT>(tile_base + ty * tiles_x + tx, rec, tile_count, tile_off, pairs, capacity);
-                } else {
-                    int q = atomicAdd(&s_nbig, 1);
-                    if (q < SLB_BIG_QUEUE) {
-                        s_big[q].rec = rec; s_big[q].tx0 = tx0; s_big[q].ty0 = ty0; s_big[q].ntx = ntx; s_big[q].nty = nty;
-                    } else {   // queue full: this thread walks the tiles itself
-                        for (int ty = ty0; ty <= ty1; ++ty)
-                            for (int tx = tx0; tx <= tx1; ++tx)
-                                if (tile_may_overlap(st, tx, ty, W, H))
-                                    bin_pair<EMIT>(tile_base + ty * tiles_x + tx, rec, tile_count, tile_off, pairs, capacity);
-                    }
-                }
+        const uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+        const float4 p0 = __ldg(d.pos4 + i0), p1 = __ldg(d.pos4 + i1), p2 = __ldg(d.pos4 + i2);
+        ClipV c0, c1, c2;
+        xform_clip(s_mvp, p0.x, p0.y, p0.z, c0);
+        xform_clip(s_mvp, p1.x, p1.y, p1.z, c1);
+        xform_clip(s_mvp, p2.x, p2.y, p2.z, c2);
+        if (!(frustum_code(c0) & frustum_code(c1) & frustum_code(c2))) {
+            const uint32_t seq = d.prim_base + tri;
+            const uint32_t flags = (d.flags & DRAW_FRAG_TEST) ? 0x100u : 0u;
+            if (need_mask(c0) | need_mask(c1) | need_mask(c2)) {
+                produced = bin_clipped<EMIT>(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z),
+                                             seq, flags, d.draw, shadow, shadow ? nullptr : &frames[v.frame], W, H, tiles_x, tile_base,
+                                             tile_count, tile_off, pairs, capacity, s_big, &s_nbig);
+            } else {
+                const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+                PolyV a, b, c;
+                if (project_vertex(c0, hw, hh, a) && project_vertex(c1, hw, hh, b) && project_vertex(c2, hw, hh, c))
+                    produced = bin_subtri<EMIT>(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, 1u | flags, d.draw, shadow, W, H, tiles_x,
+                                                tile_base, tile_count, tile_off, pairs, capacity, s_big, &s_nbig);
             }
         }
+    }
+    if (!EMIT) {
+        const unsigned m = __ballot_sync(0xffffffffu, produced > 0);
+        if ((threadIdx.x & 31) == 0) tri_mask[mask_word] = m;
     }
     __syncthreads();
     const int nbig = min(s_nbig, SLB_BIG_QUEUE);
@@ -238,7 +300,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 #define SLB_RASTER_WARPS 8
 #define SLB_RASTER_CHUNK 32
-#define SLB_RASTER_SMALL 16   // sub-triangles whose in-tile pixel box is at most this big are rasterised by ONE lane
+#define SLB_RASTER_SMALL 24   // sub-triangles whose in-tile pixel box is at most this big are rasterised by ONE lane
 
 // fragment-stage discards that decide coverage: depth peel + alpha test (render_shader.frag:229-246)
 __device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint32_t seq, int k, int px, int py) {
@@ -314,43 +376,75 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DView* _
             const int cnt = (int)min(n - c * SLB_RASTER_CHUNK, (uint32_t)SLB_RASTER_CHUNK);
             // ---- one record per lane ----
             bool big = false;
+            // edge functions (orientation-normalised, top-left bias folded in) at the tile's first pixel centre and
+            // their per-pixel steps; depth plane; low key bits — kept in registers for the warp-wide path below
+            long long E0 = 0, E1 = 0, E2 = 0;
+            int sx0 = 0, sy0 = 0, sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
+            float z_a = 0.f, z_b = 0.f, z_c = 0.f, inv2A = 0.f;
+            int sb = 0;
+            uint32_t r_seq = 0, r_kf = 0, r_draw = 0;
             if (lane < cnt) {
                 const PairRec r = s_rec[warp][b][lane];
-                SubTri st;
-                make_subtri(r.ax, r.ay, r.bx, r.by, r.cx, r.cy, r.az, r.bz, r.cz, st);
-                int px0, py0, px1, py1;
-                if (subtri_pixel_bbox(st, W, H, px0, py0, px1, py1)) {
-                    px0 = max(px0, x_lo); px1 = min(px1, x_hi); py0 = max(py0, y_lo); py1 = min(py1, y_hi);
-                    if (px0 <= px1 && py0 <= py1) {
-                        if ((px1 - px0 + 1) * (py1 - py0 + 1) > SLB_RASTER_SMALL) big = true;
-                        else {
-                            const int cx0 = px0 * 256 + 128, cy0 = py0 * 256 + 128;
-                            long long a0 = st.s * edge_fn(st.bx, st.by, st.cx, st.cy, cx0, cy0) + st.bias0;
-                            long long a1 = st.s * edge_fn(st.cx, st.cy, st.ax, st.ay, cx0, cy0) + st.bias1;
-                            long long a2 = st.s * edge_fn(st.ax, st.ay, st.bx, st.by, cx0, cy0) + st.bias2;
-                            const long long dx0 = (long long)(-st.s * (st.cy - st.by)) * 256, dy0 = (long long)(st.s * (st.cx - st.bx)) * 256;
-                            const long long dx1 = (long long)(-st.s * (st.ay - st.cy)) * 256, dy1 = (long long)(st.s * (st.ax - st.cx)) * 256;
-                            const long long dx2 = (long long)(-st.s * (st.by - st.ay)) * 256, dy2 = (long long)(st.s * (st.bx - st.ax)) * 256;
-                            const float dzb = __fsub_rn(st.bz, st.az), dzc = __fsub_rn(st.cz, st.az);
-                            const unsigned long long lowkey = ((unsigned long long)r.seq << 8) | (r.k_flags & 0xffu);
-                            for (int y = py0; y <= py1; ++y, a0 += dy0, a1 += dy1, a2 += dy2) {
-                                long long e0 = a0, e1 = a1, e2 = a2;
-                                for (int x = px0; x <= px1; ++x, e0 += dx0, e1 += dx1, e2 += dx2) {
-                                    if ((e0 | e1 | e2) < 0) continue;
-                                    long long w1 = e1 - st.bias1, w2 = e2 - st.bias2;
-                                    if (st.s < 0) { w1 = -w1; w2 = -w2; }
-                                    float q1 = __fmul_rn(__ll2float_rn(w1), st.inv2A), q2 = __fmul_rn(__ll2float_rn(w2), st.inv2A);
-                                    float z = __fmaf_rn(q2, dzc, __fmaf_rn(q1, dzb, st.az));
-                                    z = fminf(fmaxf(z, 0.0f), 1.0f);
-                                    const unsigned long long key = ((unsigned long long)__float2uint_rn(__fmul_rn(z, 16777215.0f)) << 40) | lowkey;
-                                    unsigned long long* slot = keys + (y - y_lo) * SLB_TILE + (x - x_lo);
-                                    if (FRAG) {
-                                        if ((r.k_flags & 0x100u) && (key >= *(volatile unsigned long long*)slot ||
-                                                                     frag_discard(f, draws[r.draw], r.seq, r.k_flags & 0xff, x, y)))
-                                            continue;
-                                    }
-                                    atomicMin(slot, key);
-                                }
+                r_seq = r.seq; r_kf = r.k_flags; r_draw = r.draw;
+                const int xmin = min(r.ax, min(r.bx, r.cx)), xmax = max(r.ax, max(r.bx, r.cx));
+                const int ymin = min(r.ay, min(r.by, r.cy)), ymax = max(r.ay, max(r.by, r.cy));
+                const int px0 = max(x_lo, (xmin - 128 + 255) >> 8), px1 = min(x_hi, (xmax - 128) >> 8);
+                const int py0 = max(y_lo, (ymin - 128 + 255) >> 8), py1 = min(y_hi, (ymax - 128) >> 8);
+                if (px0 <= px1 && py0 <= py1) {
+                    const long long twoA = edge_fn(r.ax, r.ay, r.bx, r.by, r.cx, r.cy);
+                    const int sg = twoA > 0 ? 1 : -1;
+                    inv2A = __fdiv_rn(1.0f, __ll2float_rn(twoA));
+                    const int bias0 = top_left(r.cx - r.bx, r.cy - r.by, sg) ? 0 : -1;
+                    const int bias1 = top_left(r.ax - r.cx, r.ay - r.cy, sg) ? 0 : -1;
+                    const int bias2 = top_left(r.bx - r.ax, r.by - r.ay, sg) ? 0 : -1;
+                    sx0 = -sg * (r.cy - r.by); sy0 = sg * (r.cx - r.bx);     // d(s*w_i)/dpx, d(s*w_i)/dpy in units of 1/256 px
+                    sx1 = -sg * (r.ay - r.cy); sy1 = sg * (r.ax - r.cx);
+                    sx2 = -sg * (r.by - r.ay); sy2 = sg * (r.bx - r.ax);
+                    z_a = r.az; z_b = __fsub_rn(r.bz, r.az); z_c = __fsub_rn(r.cz, r.az);
+                    sb = (sg < 0 ? 1 : 0) | (bias1 ? 2 : 0) | (bias2 ? 4 : 0);
+                    const unsigned long long lowkey = ((unsigned long long)r.seq << 8) | (r.k_flags & 0xffu);
+                    if ((px1 - px0 + 1) * (py1 - py0 + 1) > SLB_RASTER_SMALL) {
+                        big = true;
+                        const int ox = x_lo * 256 + 128, oy = y_lo * 256 + 128;
+                        E0 = sg * edge_fn(r.bx, r.by, r.cx, r.cy, ox, oy) + bias0;
+                        E1 = sg * edge_fn(r.cx, r.cy, r.ax, r.ay, ox, oy) + bias1;
+                        E2 = sg * edge_fn(r.ax, r.ay, r.bx, r.by, ox, oy) + bias2;
+                    } else {
+                        const int cx0 = px0 * 256 + 128, cy0 = py0 * 256 + 128;
+                        const long long a0 = sg * edge_fn(r.bx, r.by, r.cx, r.cy, cx0, cy0) + bias0;
+                        const long long a1 = sg * edge_fn(r.cx, r.cy, r.ax, r.ay, cx0, cy0) + bias1;
+                        const long long a2 = sg * edge_fn(r.ax, r.ay, r.bx, r.by, cx0, cy0) + bias2;
+                        auto plot = [&](long long w1, long long w2, int x, int y) {   // w_i = s*w_i + bias_i at a covered pixel
+                            w1 -= bias1; w2 -= bias2;
+                            if (sg < 0) { w1 = -w1; w2 = -w2; }
+                            float q1 = __fmul_rn(__ll2float_rn(w1), inv2A), q2 = __fmul_rn(__ll2float_rn(w2), inv2A);
+                            float z = __fmaf_rn(q2, z_c, __fmaf_rn(q1, z_b, z_a));
+                            z = fminf(fmaxf(z, 0.0f), 1.0f);
+                            const unsigned long long key = ((unsigned long long)__float2uint_rn(__fmul_rn(z, 16777215.0f)) << 40) | lowkey;
+                            unsigned long long* slot = keys + (y - y_lo) * SLB_TILE + (x - x_lo);
+                            if (key >= *(volatile unsigned long long*)slot) return;
+                            if (FRAG) {
+                                if ((r.k_flags & 0x100u) && frag_discard(f, draws[r.draw], r.seq, r.k_flags & 0xff, x, y)) return;
+                            }
+                            atomicMin(slot, key);
+                        };
+                        if (xmax - xmin < 16384 && ymax - ymin < 16384) {
+                            // the whole triangle is smaller than 64 px: every edge value inside its box fits 32 bits
+                            int e0r = (int)a0, e1r = (int)a1, e2r = (int)a2;
+                            const int dx0 = sx0 * 256, dy0 = sy0 * 256, dx1 = sx1 * 256, dy1 = sy1 * 256, dx2 = sx2 * 256, dy2 = sy2 * 256;
+                            for (int y = py0; y <= py1; ++y, e0r += dy0, e1r += dy1, e2r += dy2) {
+                                int e0 = e0r, e1 = e1r, e2 = e2r;
+                                for (int x = px0; x <= px1; ++x, e0 += dx0, e1 += dx1, e2 += dx2)
+                                    if ((e0 | e1 | e2) >= 0) plot((long long)e1, (long long)e2, x, y);
+                            }
+                        } else {
+                            const long long dx0 = (long long)sx0 * 256, dy0 = (long long)sy0 * 256, dx1 = (long long)sx1 * 256,
+                                            dy1 = (long long)sy1 * 256, dx2 = (long long)sx2 * 256, dy2 = (long long)sy2 * 256;
+                            long long e0r = a0, e1r = a1, e2r = a2;
+                            for (int y = py0; y <= py1; ++y, e0r += dy0, e1r += dy1, e2r += dy2) {
+                                long long e0 = e0r, e1 = e1r, e2 = e2r;
+                                for (int x = px0; x <= px1; ++x, e0 += dx0, e1 += dx1, e2 += dx2)
+                                    if ((e0 | e1 | e2) >= 0) plot(e1, e2, x, y);
                             }
                         }
                     }
@@ -358,25 +452,37 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DView* _
             }
             unsigned bigmask = __ballot_sync(0xffffffffu, big);
             __syncwarp();
-            // ---- large records: the whole warp, two pixels per lane ----
+            // ---- large records: the owning lane broadcasts its set-up, every lane tests its two pixels ----
             while (bigmask) {
                 const int j = __ffs(bigmask) - 1;
                 bigmask &= bigmask - 1;
-                const PairRec& r = s_rec[warp][b][j];
-                SubTri st;
-                make_subtri(r.ax, r.ay, r.bx, r.by, r.cx, r.cy, r.az, r.bz, r.cz, st);
-                const unsigned long long lowkey = ((unsigned long long)r.seq << 8) | (r.k_flags & 0xffu);
+                const long long b0 = __shfl_sync(0xffffffffu, E0, j), b1 = __shfl_sync(0xffffffffu, E1, j), b2 = __shfl_sync(0xffffffffu, E2, j);
+                const int tx0 = __shfl_sync(0xffffffffu, sx0, j), ty0 = __shfl_sync(0xffffffffu, sy0, j);
+                const int tx1 = __shfl_sync(0xffffffffu, sx1, j), ty1 = __shfl_sync(0xffffffffu, sy1, j);
+                const int tx2 = __shfl_sync(0xffffffffu, sx2, j), ty2 = __shfl_sync(0xffffffffu, sy2, j);
+                const float za = __shfl_sync(0xffffffffu, z_a, j), zb = __shfl_sync(0xffffffffu, z_b, j), zc = __shfl_sync(0xffffffffu, z_c, j);
+                const float i2a = __shfl_sync(0xffffffffu, inv2A, j);
+                const int sbj = __shfl_sync(0xffffffffu, sb, j);
+                const uint32_t seqj = __shfl_sync(0xffffffffu, r_seq, j), kfj = __shfl_sync(0xffffffffu, r_kf, j);
+                const uint32_t drawj = __shfl_sync(0xffffffffu, r_draw, j);
+                const unsigned long long lowkey = ((unsigned long long)seqj << 8) | (kfj & 0xffu);
+                const long long e0 = b0 + (long long)(tx0 * lx + ty0 * ly) * 256, e1 = b1 + (long long)(tx1 * lx + ty1 * ly) * 256,
+                                e2 = b2 + (long long)(tx2 * lx + ty2 * ly) * 256;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    const long long g0 = e0 + (long long)ty0 * (1024 * h), g1 = e1 + (long long)ty1 * (1024 * h), g2 = e2 + (long long)ty2 * (1024 * h);
                     const int x = x_lo + lx, y = y_lo + ly + 4 * h;
-                    if (x > x_hi || y > y_hi) continue;
-                    long long w0, w1, w2; subtri_weights(st, x, y, w0, w1, w2);
-                    if (!subtri_covers(st, w0, w1, w2)) continue;
-                    const unsigned long long key = ((unsigned long long)subtri_depth24(st, w1, w2) << 40) | lowkey;
+                    if ((g0 | g1 | g2) < 0 || x > x_hi || y > y_hi) continue;
+                    long long w1 = g1 - ((sbj & 2) ? -1 : 0), w2 = g2 - ((sbj & 4) ? -1 : 0);
+                    if (sbj & 1) { w1 = -w1; w2 = -w2; }
+                    float q1 = __fmul_rn(__ll2float_rn(w1), i2a), q2 = __fmul_rn(__ll2float_rn(w2), i2a);
+                    float z = __fmaf_rn(q2, zc, __fmaf_rn(q1, zb, za));
+                    z = fminf(fmaxf(z, 0.0f), 1.0f);
+                    const unsigned long long key = ((unsigned long long)__float2uint_rn(__fmul_rn(z, 16777215.0f)) << 40) | lowkey;
                     unsigned long long* slot = keys + (ly + 4 * h) * SLB_TILE + lx;
                     if (key >= *slot) continue;
                     if (FRAG) {
-                        if ((r.k_flags & 0x100u) && frag_discard(f, draws[r.draw], r.seq, r.k_flags & 0xff, x, y)) continue;
+                        if ((kfj & 0x100u) && frag_discard(f, draws[drawj], seqj, kfj & 0xff, x, y)) continue;
                     }
                     *slot = key;
                 }
@@ -474,10 +580,11 @@ __global__ void __launch_bounds__(256) k_shade(const DFrame* __restrict__ frames
 namespace slbk {
 
 void launch_bin(bool emit, const DView* views, const DFrame* frames, const DBinDraw* bdraws, const uint32_t* chunk_draw,
-                uint32_t n_chunks, uint32_t* tile_count, const uint32_t* tile_off, PairRec* pairs, uint32_t capacity, cudaStream_t s) {
+                uint32_t n_chunks, uint32_t* tri_mask, uint32_t* tile_count, const uint32_t* tile_off, PairRec* pairs, uint32_t capacity,
+                cudaStream_t s) {
     if (n_chunks == 0) return;
-    if (emit) k_bin<true><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tile_count, tile_off, pairs, capacity);
-    else k_bin<false><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tile_count, tile_off, pairs, capacity);
+    if (emit) k_bin<true><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tri_mask, tile_count, tile_off, pairs, capacity);
+    else k_bin<false><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tri_mask, tile_count, tile_off, pairs, capacity);
 }
 void launch_scan(const uint32_t* count, uint32_t* off, ActiveTile* active, unsigned long long* block_sums, uint32_t* totals, uint32_t n,
                  cudaStream_t s) {

@@ -9,7 +9,8 @@ namespace slbk {
 
 // k_render.cu
 void launch_bin(bool emit, const DView* views, const DFrame* frames, const DBinDraw* bdraws, const uint32_t* chunk_draw,
-                uint32_t n_chunks, uint32_t* tile_count, const uint32_t* tile_off, PairRec* pairs, uint32_t capacity, cudaStream_t s);
+                uint32_t n_chunks, uint32_t* tri_mask, uint32_t* tile_count, const uint32_t* tile_off, PairRec* pairs, uint32_t capacity,
+                cudaStream_t s);
 void launch_scan(const uint32_t* count, uint32_t* off, ActiveTile* active, unsigned long long* block_sums, uint32_t* totals, uint32_t n,
                  cudaStream_t s);
 struct RasterGrid { uint32_t n_active, n_cam_tiles, tiles_per_cam, n_cam_views, tiles_per_shadow; };

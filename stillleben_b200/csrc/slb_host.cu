@@ -74,7 +74,7 @@ struct slb_ctx {
     // assets owned by the context
     slb_mesh* plane = nullptr;
     // per-batch device arrays
-    DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals;
+    DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, tri_mask;
     DevBuf clip_recs, clip_counts;
     DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, ao, avg, mip_a, mip_b, shadow_maps;
     // pinned staging
@@ -201,7 +201,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
         if (ctx->slot_rendered[i]) cudaEventDestroy(ctx->slot_rendered[i]);
         if (ctx->slot_copied[i]) cudaEventDestroy(ctx->slot_copied[i]);
     }
-    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->tile_count,
+    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->tri_mask, &ctx->tile_count,
                       &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->ao,
                       &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts};
     for (DevBuf* b : bufs) b->release();
@@ -899,6 +899,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     CU(ctx->scan_sums.reserve(((size_t)n_tiles / 4096 + 2) * 8));
     CU(ctx->active_tiles.reserve((size_t)n_tiles * sizeof(ActiveTile)));
     CU(ctx->scan_totals.reserve(64));
+    CU(ctx->tri_mask.reserve(((size_t)b.n_chunks + 1) * (SLB_SETUP_CHUNK / 32) * 4));
     CU(ctx->keys.reserve(npx * n * 8));
     CU(ctx->clip_recs.reserve((size_t)n * SLB_MAX_CLIP * sizeof(ClipRec)));
     CU(ctx->clip_counts.reserve((size_t)n * 4));
@@ -971,7 +972,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     // ---- bin (camera + shadow views together): count, scan, emit ----
     {
         StageTimer t(ctx, s, ST_COUNT);
-        launch_bin(false, views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks,
+        launch_bin(false, views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks, ctx->tri_mask.as<uint32_t>(),
                    ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), nullptr, 0, s);
     }
     {
@@ -986,7 +987,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     CU(ctx->pairs.reserve(((size_t)total_pairs + 1) * sizeof(PairRec)));
     {
         StageTimer t(ctx, s, ST_EMIT);
-        launch_bin(true, views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks,
+        launch_bin(true, views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks, ctx->tri_mask.as<uint32_t>(),
                    ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->pairs.as<PairRec>(), total_pairs, s);
     }
     {
