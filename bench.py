@@ -187,13 +187,12 @@ def main():
     # ---- end to end: host descriptors in, all six targets back in pinned host memory ----
     e2e = None
     if not args.no_e2e:
-        chunk = min(128, n_local)
+        chunk = min(256, n_local)
         host = {}
         for tgt, (dt_, ch) in enumerate(abi.TARGET_FORMATS):
             if abi.TARGETS_SIX & (1 << tgt):
-                tdt = {np.uint8: torch.uint8, np.float32: torch.float32, np.uint16: torch.int16, np.uint32: torch.int32}[dt_]
-                host[tgt] = torch.empty((chunk, H, W, ch), dtype=tdt).pin_memory()
-        host_ptrs = {k: v.data_ptr() for k, v in host.items()}
+                host[tgt] = ctx.host_alloc((chunk, H, W, ch), dt_)          # page-locked (slb_host_alloc)
+        host_ptrs = {k: v.ctypes.data for k, v in host.items()}
         chunk_descs = [ctx.descs(scenes[a:a + chunk]) for a in range(0, n_local, chunk)]
         d2h = n_local * W * H * BYTES_PER_PX
         h2d0 = ctx.stats().bytes_h2d
@@ -214,7 +213,7 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": args.scenes * args.steps / float(t.item()), "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world,
-               "d2h_bytes_per_step": int(d2h) * world, "note": "slb_render_batch_host, pinned host buffers, 128-scene calls"}
+               "d2h_bytes_per_step": int(d2h) * world, "note": "slb_render_batch_host, page-locked host buffers (slb_host_alloc), 256-scene calls"}
 
     if rank != 0:
         if world > 1:

@@ -97,6 +97,12 @@ int slb_ctx_device(const slb_ctx* ctx);
 /* Block until all work queued on the context's streams is done. */
 int slb_ctx_synchronize(slb_ctx* ctx);
 
+/* Page-locked host memory for slb_render_batch_host destinations / upload sources (cudaHostAlloc): D2H copies
+ * into pageable memory cannot overlap with rendering. (New: the reference reads results with glGetTexImage into
+ * pageable Magnum::Image2D storage, python/src/py_magnum.cpp:33-45.) */
+int slb_host_alloc(slb_ctx* ctx, size_t bytes, void** out);
+void slb_host_free(slb_ctx* ctx, void* ptr);
+
 /* ---- assets --------------------------------------------------------------------------- */
 
 typedef struct slb_image {

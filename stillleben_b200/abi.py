@@ -111,6 +111,8 @@ PROTOTYPES = {
     "slb_abi_version": (C.c_int, []),
     "slb_ctx_device": (C.c_int, [C.c_void_p]),
     "slb_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "slb_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "slb_host_free": (None, [C.c_void_p, C.c_void_p]),
     "slb_mesh_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(Submesh),
                                    C.c_uint32, C.POINTER(Material), C.c_uint32, C.POINTER(Image), C.c_uint32,
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_void_p)]),

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <random>
@@ -156,7 +157,7 @@ extern "C" int slb_ctx_create(int device, slb_ctx** out) {
     ctx = c;
     cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-    cudaError_t e3 = cudaHostAlloc((void**)&c->total_pinned, 64, cudaHostAllocDefault);
+    cudaError_t e3 = cudaHostAlloc((void**)&c->total_pinned, 64, cudaHostAllocPortable | cudaHostAllocMapped);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { delete c; ctx = nullptr; return fail(ctx, SLB_ERR_CUDA, "slb_ctx_create: stream/pinned allocation failed"); }
     float noise[48], kernel[192];
     ssao_tables(noise, kernel);
@@ -232,6 +233,19 @@ extern "C" int slb_ctx_get_stats(slb_ctx* ctx, slb_stats* out) {
     if (!ctx || !out) return SLB_ERR_INVALID_ARGUMENT;
     *out = ctx->stats;
     return SLB_OK;
+}
+
+extern "C" int slb_host_alloc(slb_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out || bytes == 0) return SLB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return SLB_OK;
+}
+extern "C" void slb_host_free(slb_ctx* ctx, void* ptr) {
+    if (!ptr) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFreeHost(ptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -978,9 +992,10 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     {
         StageTimer t(ctx, s, ST_SCAN);
         launch_scan(ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->active_tiles.as<ActiveTile>(),
-                    ctx->scan_sums.as<unsigned long long>(), ctx->scan_totals.as<uint32_t>(), n_tiles, s);
+                    ctx->scan_sums.as<unsigned long long>(), ctx->total_pinned, n_tiles, s);
     }
-    CU(cudaMemcpyAsync(ctx->total_pinned, ctx->scan_totals.p, 8, cudaMemcpyDeviceToHost, s));
+    // The scan writes its two totals straight into page-locked host memory (UVA): a D2H memcpy here would queue
+    // behind the result copies of the previous sub-batch on the copy engine and serialise the pipeline.
     CU(cudaStreamSynchronize(s));   // the pair buffer and the raster grid are sized from the exact totals
     const uint32_t total_pairs = ctx->total_pinned[0];
     grid.n_active = ctx->total_pinned[1];
@@ -1094,12 +1109,17 @@ extern "C" int slb_render_batch_host(slb_ctx* ctx, const slb_scene_desc* scenes,
     const size_t npx = (size_t)W * H;
     int k = 0;
     bool used[2] = {false, false};
+    const bool dbg = getenv("SLB_DEBUG_TIMING") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now();
     for (int at = 0; at < n_scenes; at += ctx->max_subbatch, ++k) {
         const int n = std::min(ctx->max_subbatch, n_scenes - at);
         const int sl = k & 1;
         if (used[sl]) CU(cudaStreamWaitEvent(ctx->stream, ctx->slot_copied[sl], 0));   // slot free again?
+        const double t0 = now();
         int rc = render_subbatch(ctx, scenes + at, n, ctx->slot[sl], 0, nullptr, ctx->stream);
         if (rc != SLB_OK) return rc;
+        const double t1 = now();
         CU(cudaEventRecord(ctx->slot_rendered[sl], ctx->stream));
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->slot_rendered[sl], 0));
         for (int t = 0; t < SLB_NUM_TARGETS; ++t) {
@@ -1110,9 +1130,12 @@ extern "C" int slb_render_batch_host(slb_ctx* ctx, const slb_scene_desc* scenes,
         }
         CU(cudaEventRecord(ctx->slot_copied[sl], ctx->copy_stream));
         used[sl] = true;
+        if (dbg) fprintf(stderr, "[slb] sub-batch %d: render_subbatch host %.2f ms (from %.2f), copies queued at %.2f\n", k, t1 - t0, t0 - t_begin, now() - t_begin);
     }
+    if (dbg) fprintf(stderr, "[slb] all queued at %.2f ms\n", now() - t_begin);
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->copy_stream));
+    if (dbg) fprintf(stderr, "[slb] done at %.2f ms\n", now() - t_begin);
     if (ctx->time_kernels) collect_times(ctx);
     return SLB_OK;
 }

@@ -117,6 +117,7 @@ class Context:
         self.device = device
         self._handles = {}
         self._keep = []
+        self._pinned = []
         self.lightmap_sizes = (0, 0, 0, 0, 0)
 
     # ---- assets -------------------------------------------------------------------------------
@@ -232,6 +233,18 @@ class Context:
         if rc != abi.OK:
             _raise(self.lib, self.h, rc, "slb_render_batch_host")
 
+    def host_alloc(self, shape, dtype):
+        """numpy array over page-locked host memory (slb_host_alloc); freed with the context."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        rc = self.lib.slb_host_alloc(self.h, n, C.byref(p))
+        if rc != abi.OK:
+            _raise(self.lib, self.h, rc, "slb_host_alloc")
+        self._pinned.append(p.value)
+        buf = (C.c_uint8 * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
     def synchronize(self):
         rc = self.lib.slb_ctx_synchronize(self.h)
         if rc != abi.OK:
@@ -249,5 +262,8 @@ class Context:
 
     def close(self):
         if self.h:
+            for p in self._pinned:
+                self.lib.slb_host_free(self.h, p)
+            self._pinned = []
             self.lib.slb_ctx_destroy(self.h)
             self.h = None
