@@ -1,0 +1,595 @@
+"""Host-side mirror of the reference's Python surface for the render path.
+
+    from stillleben_b200 import sl          # instead of:  import stillleben as sl
+
+Same names, argument meanings, defaults, tensor dtypes / shapes and error behaviour as the pybind11 module
+of the reference for everything RenderPass::render reads or returns:
+  sl.init / sl.init_cuda            python/src/py_context.cpp:19-100
+  sl.Mesh                           python/src/py_mesh.cpp:314-525, src/mesh.cpp:1000-1089
+  sl.Object                         python/src/py_object.cpp:23-197
+  sl.Scene                          python/src/py_scene.cpp:48-425, src/scene.cpp:195-330,453-470
+  sl.LightMap                       python/src/py_light_map.cpp:19-52, src/light_map.cpp:62-152,266-376
+  sl.Texture / sl.Texture2D         python/src/py_magnum.cpp:115-198
+  sl.RenderPass / RenderPassResult  python/src/py_render_pass.cpp:92-279
+Matrices are 4x4 float tensors indexed m[row, col] (as the reference's toTorch<Matrix4>). Everything here is
+host logic over the C ABI (stillleben_b200.lib); rendering always runs in the CUDA library. Physics entry
+points raise RuntimeError: PhysX stays on the host and is not part of this build.
+"""
+import math
+import os
+import warnings
+
+import numpy as np
+import torch
+
+from . import abi, gltf
+from . import lib as _lib
+from .desc import (ImageData, LightMapData, MeshData, ObjectSpec, SceneSpec, fov_projection, intrinsics_projection,
+                   inverted_rigid, look_at_pose)
+
+_ctx = None
+_cuda_index = 0
+
+
+# ---------------------------------------------------------------------------------------------
+# context
+# ---------------------------------------------------------------------------------------------
+def init():
+    """sl.init(): the reference creates a GL context without CUDA interop; here rendering always runs on a
+    CUDA device, so this is init_cuda(0) with results returned as CPU tensors."""
+    _init(0, False)
+
+
+def init_cuda(device_index=0, use_cuda=True):
+    _init(device_index, use_cuda)
+
+
+_use_cuda = True
+
+
+def _init(device_index, use_cuda):
+    global _ctx, _cuda_index, _use_cuda
+    if _ctx is not None:
+        if device_index != _cuda_index or use_cuda != _use_cuda:      # py_context.cpp:36-44: only warns
+            warnings.warn("stillleben context was already created with different CUDA settings")
+        return
+    _ctx = _lib.Context(device_index)
+    _cuda_index, _use_cuda = device_index, use_cuda
+
+
+def _context():
+    if _ctx is None:
+        raise RuntimeError("Call sl::init() first")                   # py_context.cpp:69-75
+    return _ctx
+
+
+def _np44(m):
+    a = m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
+    a = np.asarray(a, np.float32)
+    if a.shape != (4, 4):
+        raise ValueError("expected a 4x4 matrix")
+    return a.copy()
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+
+# ---------------------------------------------------------------------------------------------
+# textures
+# ---------------------------------------------------------------------------------------------
+def _image_from(arg):
+    if isinstance(arg, (str, os.PathLike)):
+        from PIL import Image
+        img = Image.open(arg)
+        img = img.convert("RGBA" if "A" in img.getbands() else "RGB")
+        return np.ascontiguousarray(np.asarray(img)[::-1])            # row 0 = bottom row
+    t = arg.detach().cpu() if isinstance(arg, torch.Tensor) else torch.as_tensor(arg)
+    if t.dim() != 3 or t.shape[2] != 3 or t.dtype != torch.uint8:
+        raise ValueError("expected a HxWx3 uint8 CPU tensor")         # py_magnum.cpp:131-151
+    return np.ascontiguousarray(t.numpy())                            # tensor row 0 becomes GL row 0
+
+
+class Texture:
+    """Rectangle texture (pixel coordinates, clamp-to-border transparent): background image / sticker."""
+
+    def __init__(self, arg):
+        self.image = ImageData(_image_from(arg), wrap_s=abi.WRAP_CLAMP_TO_BORDER, wrap_t=abi.WRAP_CLAMP_TO_BORDER,
+                               min_filter=abi.FILTER_LINEAR, mag_filter=abi.FILTER_LINEAR, kind=abi.TEXTURE_RECT)
+
+
+class Texture2D:
+    """Normalised-coordinate texture with a full mip chain: background plane texture."""
+
+    def __init__(self, arg):
+        self.image = ImageData(_image_from(arg), wrap_s=abi.WRAP_REPEAT, wrap_t=abi.WRAP_REPEAT,
+                               min_filter=abi.FILTER_LINEAR_MIPMAP_LINEAR, mag_filter=abi.FILTER_LINEAR, kind=abi.TEXTURE_2D)
+
+
+# ---------------------------------------------------------------------------------------------
+# light map
+# ---------------------------------------------------------------------------------------------
+def _read_rgbe(path):
+    """Radiance .hdr reader (RLE + flat), returns float32 HxWx3 with row 0 = top."""
+    with open(path, "rb") as f:
+        data = f.read()
+    pos = data.index(b"\n\n") + 2
+    end = data.index(b"\n", pos)
+    dims = data[pos:end].split()
+    H, W = int(dims[1]), int(dims[3])
+    p = end + 1
+    out = np.zeros((H, W, 4), np.uint8)
+    buf = np.frombuffer(data, np.uint8)
+    for y in range(H):
+        if W >= 8 and W < 32768 and buf[p] == 2 and buf[p + 1] == 2 and (int(buf[p + 2]) << 8 | int(buf[p + 3])) == W:
+            p += 4
+            for c in range(4):
+                x = 0
+                while x < W:
+                    n = int(buf[p]); p += 1
+                    if n > 128:
+                        n -= 128
+                        out[y, x:x + n, c] = buf[p]; p += 1
+                    else:
+                        out[y, x:x + n, c] = buf[p:p + n]; p += n
+                    x += n
+        else:
+            out[y] = buf[p:p + 4 * W].reshape(W, 4); p += 4 * W
+    e = out[..., 3].astype(np.int32)
+    scale = np.where(e > 0, np.ldexp(1.0, e - 136), 0.0).astype(np.float32)
+    return out[..., :3].astype(np.float32) * scale[..., None]
+
+
+class LightMap:
+    """Image-based lighting: a lat-long HDR map (+ up to three directional lights from an sIBL .ibl file)."""
+
+    def __init__(self, path=None):
+        self.data = None
+        self.path = None
+        if path is not None:
+            self.load(path)
+
+    def load(self, path):
+        path = os.fspath(path)
+        lights_d, lights_c = [], []
+        img_path = path
+        if path.endswith(".ibl"):                                     # light_map.cpp:62-152: Corrade ini
+            sections, cur = {}, None
+            for line in open(path, errors="ignore"):
+                line = line.strip()
+                if line.startswith("[") and line.endswith("]"):
+                    cur = line[1:-1]; sections[cur] = {}
+                elif "=" in line and cur is not None:
+                    k, v = line.split("=", 1)
+                    sections[cur][k.strip()] = v.strip().strip('"')
+            ref = sections.get("Reflection", {})
+            if int(ref.get("REFmap", "1")) != 1:
+                raise RuntimeError("Only lat-long light maps are supported")
+            img_path = os.path.join(os.path.dirname(path), ref["REFfile"])
+            for sec, pre in (("Sun", "SUN"), ("Light1", "LIGHT"), ("Light2", "LIGHT")):
+                if sec not in sections:
+                    continue
+                s = sections[sec]
+                col = np.array([float(x) for x in s[pre + "color"].split(",")], np.float32) / 255.0 * float(s.get(pre + "multi", 1.0))
+                u, v = float(s[pre + "u"]), float(s[pre + "v"])
+                theta, phi = (u + 0.5) * 2.0 * math.pi, v * math.pi       # light_map.cpp:314-326
+                lights_d.append((-np.array([math.cos(phi) * math.sin(theta), math.sin(phi) * math.sin(theta), math.cos(theta)])).tolist())
+                lights_c.append(col.tolist())
+        if img_path.lower().endswith(".hdr"):
+            eq = _read_rgbe(img_path)
+        elif img_path.lower().endswith(".npy"):
+            eq = np.load(img_path).astype(np.float32)
+        else:
+            from PIL import Image
+            eq = np.asarray(Image.open(img_path).convert("RGB"), np.float32) / 255.0
+        self.data = LightMapData(np.ascontiguousarray(eq[::-1]), lights_d[:3], lights_c[:3])     # rows bottom-up
+        self.path = path
+        return True
+
+    @staticmethod
+    def from_equirect(equirect_bottom_up, light_directions=(), light_colors=()):
+        """Extension: build a light map from a float32 HxWx3 lat-long image (row 0 = bottom)."""
+        lm = LightMap()
+        lm.data = LightMapData(np.ascontiguousarray(equirect_bottom_up, np.float32), [list(d) for d in light_directions],
+                               [list(c) for c in light_colors])
+        return lm
+
+
+# ---------------------------------------------------------------------------------------------
+# mesh
+# ---------------------------------------------------------------------------------------------
+class _Range3D:
+    def __init__(self, lo, hi):
+        self.min, self.max = _t(lo), _t(hi)
+
+    @property
+    def center(self):
+        return (self.min + self.max) / 2
+
+    @property
+    def size(self):
+        return self.max - self.min
+
+    @property
+    def diagonal(self):
+        return float(torch.linalg.norm(self.size))
+
+
+class Mesh:
+    def __init__(self, filename, visual=True, physics=True, flags=None):
+        _context()
+        if isinstance(filename, MeshData):
+            self.data, self.filename = filename, filename.name
+        else:
+            self.filename = os.fspath(filename)
+            if not self.filename.lower().endswith((".gltf", ".glb")):
+                raise RuntimeError(f"Could not load mesh {self.filename}: only glTF / GLB is supported by this build")
+            self.data = gltf.load(self.filename)
+        self._scale = 1.0
+        self._rigid = np.eye(4, dtype=np.float32)
+        self._class_index = 1                                          # mesh.h:300
+        # physics=True is the reference default; V-HACD / PhysX cooking is skipped here (no PhysX in this build)
+
+    @staticmethod
+    def load_threaded(filenames, visual=True, physics=True, flags=None):
+        return [Mesh(f, visual, physics) for f in filenames]
+
+    @staticmethod
+    def from_data(mesh_data):
+        """Extension: wrap an in-memory consolidated mesh (stillleben_b200.desc.MeshData)."""
+        return Mesh(mesh_data)
+
+    # ---- pretransform (src/mesh.cpp:1000-1081) ----
+    @property
+    def pretransform(self):
+        s = np.eye(4, dtype=np.float32)
+        s[:3, :3] *= self._scale
+        return _t(s @ self._rigid)
+
+    @pretransform.setter
+    def pretransform(self, m):
+        m = _np44(m)
+        u, w, vt = np.linalg.svd(m[:3, :3].astype(np.float64))
+        if w.max() - w.min() > 1e-5:
+            raise ValueError("Scaling is not uniform")
+        self._scale = float((w.max() + w.min()) / 2.0)
+        self._rigid = np.eye(4, dtype=np.float32)
+        self._rigid[:3, :3] = (u @ vt).astype(np.float32)
+        self._rigid[:3, 3] = (1.0 / self._scale) * m[:3, 3]
+
+    def _pre_np(self):
+        return self.pretransform.numpy()
+
+    @property
+    def bbox(self):
+        p = self._pre_np().astype(np.float64)
+        lo = p[:3, :3] @ self.data.bbox_min + p[:3, 3]
+        hi = p[:3, :3] @ self.data.bbox_max + p[:3, 3]
+        return _Range3D(lo, hi)
+
+    def center_bbox(self):
+        c = (self.data.bbox_min + self.data.bbox_max) / 2
+        self._rigid[:3, 3] = -(self._rigid[:3, :3] @ c)
+
+    def scale_to_bbox_diagonal(self, target_diagonal, mode="exact"):
+        diag = float(np.linalg.norm(self.data.bbox_max - self.data.bbox_min))
+        scale = target_diagonal / diag
+        if mode == "exact":
+            self._scale = scale
+        elif mode == "order_of_magnitude":
+            self._scale = float(10.0 ** round(math.log10(scale)))
+        else:
+            raise ValueError("invalid value for mode argument")
+
+    @property
+    def class_index(self):
+        return self._class_index
+
+    @class_index.setter
+    def class_index(self, index):
+        if index < 0 or index > 0xFFFF:
+            raise ValueError("Mesh::setClassIndex(): out of range")    # mesh.cpp:1083-1089
+        self._class_index = int(index)
+
+    # ---- geometry access / editing (py_mesh.cpp:409-500) ----
+    @property
+    def points(self):
+        return torch.from_numpy(self.data.vertices["position"].copy())
+
+    @property
+    def normals(self):
+        return torch.from_numpy(self.data.vertices["normal"].copy())
+
+    @property
+    def colors(self):
+        return torch.from_numpy(self.data.vertices["color"].copy())
+
+    @property
+    def faces(self):
+        return torch.from_numpy(self.data.indices.astype(np.int32))
+
+    def set_new_positions(self, new_positions):
+        p = new_positions.detach().cpu().numpy().astype(np.float32)
+        if p.shape != self.data.vertices["position"].shape:
+            raise ValueError("new_positions must be N x 3")
+        self.data.vertices["position"] = p
+        self.data.bbox_min, self.data.bbox_max = p.min(axis=0), p.max(axis=0)
+        self._reupload()
+
+    def update_positions(self, vertex_indices, position_update):
+        idx = vertex_indices.detach().cpu().numpy().astype(np.int64) - 1      # vertex ids are one-based
+        self.data.vertices["position"][idx] += position_update.detach().cpu().numpy().astype(np.float32)
+        p = self.data.vertices["position"]
+        self.data.bbox_min, self.data.bbox_max = p.min(axis=0), p.max(axis=0)
+        self._reupload()
+
+    def _reupload(self):
+        ctx = _context()
+        if id(self.data) in ctx._handles:
+            ctx.update_vertices(self.data)
+
+
+# ---------------------------------------------------------------------------------------------
+# object
+# ---------------------------------------------------------------------------------------------
+class Object:
+    def __init__(self, mesh, options=None):
+        self.mesh = mesh
+        self._pose = np.eye(4, dtype=np.float32)
+        self._instance_index = 0
+        self.specular_color = torch.ones(4)
+        self.shininess = 80.0
+        self.metallic = -1.0                                           # object.h:277-278: < 0 = use the material's
+        self.roughness = -1.0
+        self.casts_shadows = True
+        self.sticker_rotation = torch.tensor([0.0, 0.0, 0.0, 1.0])    # quaternion x,y,z,w
+        self.sticker_range = torch.zeros(4)                            # min.x, min.y, max.x, max.y (Range2D)
+        self.sticker_texture = None
+        self.static = False
+        self.mass = 1.0
+
+    def pose(self):
+        return _t(self._pose)
+
+    def set_pose(self, pose):
+        self._pose = _np44(pose)
+
+    @property
+    def instance_index(self):
+        return self._instance_index
+
+    @instance_index.setter
+    def instance_index(self, index):
+        if index < 0 or index > 0xFFFF:
+            raise ValueError("Object::setInstanceIndex(): out of range")      # object.cpp:376-382
+        self._instance_index = int(index)
+
+    def _sticker_projection(self):
+        """object.cpp:494-513: orthographic (2x/d, 2y/d, z+2, 1) of the rotated object point, d = bbox diagonal."""
+        x, y, z, w = [float(v) for v in self.sticker_rotation]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], np.float32)
+        d = self.mesh.bbox.diagonal
+        proj = np.eye(4, dtype=np.float32)
+        proj[0, 0] = proj[1, 1] = 2.0 / d
+        proj[2, 3] = 2.0
+        rot = np.eye(4, dtype=np.float32)
+        rot[:3, :3] = R
+        return proj @ rot
+
+
+# ---------------------------------------------------------------------------------------------
+# scene
+# ---------------------------------------------------------------------------------------------
+class Scene:
+    def __init__(self, viewport_size):
+        _context()
+        self._W, self._H = int(viewport_size[0]), int(viewport_size[1])
+        self._projection = fov_projection(self._W, self._H)            # scene.cpp:138: 58 degree default
+        self._camera_pose = np.eye(4, dtype=np.float32)
+        self._objects = []
+        self._light_directions = torch.zeros(3, 3)
+        self._light_colors = torch.tensor([[300.0, 300.0, 300.0], [0, 0, 0], [0, 0, 0]])     # scene.h:225-230
+        self.ambient_light = torch.zeros(3)
+        self.light_map = None
+        self.background_image = None
+        self.background_color = torch.tensor([1.0, 1.0, 1.0, 1.0])
+        self.background_plane_pose = torch.eye(4)
+        self.background_plane_size = torch.zeros(2)
+        self.background_plane_texture = None
+        self.manual_exposure = -1.0                                    # scene.h:198: < 0 = auto exposure
+        self._rng = np.random.RandomState(0)
+
+    # ---- camera ----
+    @property
+    def viewport(self):
+        return (self._W, self._H)
+
+    def camera_pose(self):
+        return _t(self._camera_pose)
+
+    def set_camera_pose(self, pose):
+        self._camera_pose = _np44(pose)
+
+    def set_camera_look_at(self, position, look_at, up=(0.0, 0.0, 1.0)):
+        as3 = lambda v: np.asarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, np.float32)
+        self._camera_pose = look_at_pose(as3(position), as3(look_at), as3(up))
+
+    def set_camera_intrinsics(self, fx, fy, cx, cy):
+        self._projection = intrinsics_projection(fx, fy, cx, cy, self._W, self._H)
+
+    def set_camera_hfov(self, hfov):
+        self._projection = fov_projection(self._W, self._H, math.degrees(hfov))
+
+    def set_camera_projection(self, P):
+        self._projection = _np44(P)
+
+    def projection_matrix(self):
+        return _t(self._projection)
+
+    def min_dist_for_object_diameter(self, diameter):
+        P = self._projection
+        return float(max(P[0, 0] * diameter / 2.0, P[1, 1] * diameter / 2.0))      # src/pose.cpp:24-34
+
+    # ---- objects ----
+    def add_object(self, obj):
+        if obj.instance_index == 0:
+            obj.instance_index = len(self._objects) + 1                # scene.cpp:285-287
+        self._objects.append(obj)
+
+    def remove_object(self, obj):
+        self._objects.remove(obj)
+
+    @property
+    def objects(self):
+        return list(self._objects)
+
+    def load_visual(self):
+        ctx = _context()
+        for o in self._objects:
+            ctx.handle_of(o.mesh.data)
+
+    # ---- lights ----
+    @property
+    def light_directions(self):
+        return self._light_directions
+
+    @light_directions.setter
+    def light_directions(self, d):
+        self._light_directions.copy_(torch.as_tensor(d, dtype=torch.float32).reshape(3, 3))
+
+    @property
+    def light_colors(self):
+        return self._light_colors
+
+    @light_colors.setter
+    def light_colors(self, c):
+        self._light_colors.copy_(torch.as_tensor(c, dtype=torch.float32).reshape(3, 3))
+
+    @property
+    def light_position(self):
+        warnings.warn("light_position is deprecated, use light_directions instead.", DeprecationWarning)
+        return -self._light_directions[0]
+
+    @light_position.setter
+    def light_position(self, p):
+        warnings.warn("light_position is deprecated, use light_directions instead.", DeprecationWarning)
+        self._light_directions.zero_()
+        self._light_directions[0] = -torch.as_tensor(p, dtype=torch.float32)
+
+    def choose_random_light_direction(self):
+        # scene.cpp:453-470: from above and from the camera side, sampled in the camera frame
+        r = np.array([self._rng.normal(), -abs(self._rng.normal()), -abs(self._rng.normal())], np.float32)
+        r /= np.linalg.norm(r)
+        d_world = self._camera_pose[:3, :3] @ (-r)
+        self._light_directions.zero_()
+        self._light_directions[0] = torch.from_numpy(d_world.astype(np.float32))
+
+    def choose_random_light_position(self):
+        warnings.warn("choose_random_light_position() is deprecated", DeprecationWarning)     # py_scene.cpp:350-352: sets nothing
+
+    def simulate_tabletop_scene(self, *a, **k):
+        raise RuntimeError("physics is not available in this build (PhysX stays host-side, SURVEY §3.2)")
+
+    simulate = check_collisions = find_noncolliding_pose = load_physics = simulate_tabletop_scene
+
+    # ---- marshalling ----
+    def _spec(self, ssao_enabled, predicate):
+        objs = []
+        for o in self._objects:
+            visible = True if predicate is None else bool(predicate(o))
+            rng = [float(v) for v in o.sticker_range]
+            objs.append(ObjectSpec(o.mesh.data, pose=o._pose, pretransform=o.mesh._pre_np(), class_index=o.mesh.class_index,
+                                   instance_index=o.instance_index, metallic=float(o.metallic), roughness=float(o.roughness),
+                                   casts_shadows=bool(o.casts_shadows), visible=visible,
+                                   sticker_texture=o.sticker_texture.image if o.sticker_texture is not None else None,
+                                   sticker_projection=o._sticker_projection() if o.sticker_texture is not None else np.eye(4, dtype=np.float32),
+                                   sticker_range=(rng[0], rng[1], rng[2] - rng[0], rng[3] - rng[1])))
+        sc = SceneSpec(self._W, self._H, self._projection, inverted_rigid(self._camera_pose), objs,
+                       light_directions=self._light_directions.numpy().copy(), light_colors=self._light_colors.numpy().copy(),
+                       ambient_light=tuple(float(v) for v in self.ambient_light),
+                       light_map=self.light_map.data if self.light_map is not None else None,
+                       background_plane_size=tuple(float(v) for v in self.background_plane_size),
+                       background_plane_pose=_np44(self.background_plane_pose),
+                       background_plane_texture=self.background_plane_texture.image if self.background_plane_texture is not None else None,
+                       background_image=self.background_image.image if self.background_image is not None else None,
+                       manual_exposure=float(self.manual_exposure), ssao_enabled=bool(ssao_enabled))
+        return sc
+
+
+# ---------------------------------------------------------------------------------------------
+# render pass
+# ---------------------------------------------------------------------------------------------
+class RenderPassResult:
+    """Accessors return FRESH tensors (they outlive the result and the next render), on cuda:<device> after
+    init_cuda(use_cuda=True), on the CPU otherwise — same shapes and dtypes as py_render_pass.cpp:20-223."""
+
+    def __init__(self):
+        self._res = None
+
+    def _ensure(self, W, H):
+        ctx = _context()
+        if self._res is None or (self._res.W, self._res.H) != (W, H):
+            self._res = _lib.Result(ctx, W, H, 1, abi.TARGETS_ALL, torch_tensors=True)
+        return self._res
+
+    def _tensor(self, target):
+        if self._res is None:
+            raise RuntimeError("RenderPassResult is empty: render into it first")
+        _context().synchronize()
+        t = self._res.tensors[target][0].clone()
+        return t if _use_cuda else t.cpu()
+
+    def rgb(self):
+        return self._tensor(abi.TARGET_RGB)
+
+    def class_index(self):
+        return self._tensor(abi.TARGET_CLASS)
+
+    def instance_index(self):
+        return self._tensor(abi.TARGET_INSTANCE)
+
+    def coordinates(self):
+        return self._tensor(abi.TARGET_COORD)[:, :, 0:3]
+
+    def depth(self):
+        return self._tensor(abi.TARGET_COORD)[:, :, 3]
+
+    def coordDepth(self):
+        return self._tensor(abi.TARGET_COORD)
+
+    def normals(self):
+        return self._tensor(abi.TARGET_NORMAL)
+
+    def vertex_indices(self):
+        return self._tensor(abi.TARGET_VERTEX_INDEX)[:, :, 0:3]
+
+    def barycentric_coeffs(self):
+        return self._tensor(abi.TARGET_BARY)[:, :, 0:3]
+
+    def cam_coordinates(self):
+        return self._tensor(abi.TARGET_CAM_COORD)
+
+
+class RenderPass:
+    def __init__(self, shading="pbr"):
+        _context()
+        if shading not in ("pbr", "phong", "flat"):
+            raise ValueError("unknown shading type specified")        # py_render_pass.cpp:244
+        self.shading = shading            # stored, unused by the reference renderer too
+        self.ssao_enabled = True          # render_pass.h:150
+        self._result = RenderPassResult()
+
+    def render(self, scene, result=None, depth_peel=None, predicate=None):
+        ctx = _context()
+        res = result if result is not None else self._result       # a second render with result=None overwrites the first
+        r = res._ensure(scene._W, scene._H)
+        spec = scene._spec(self.ssao_enabled, predicate)
+        ctx.render([spec], result=r, depth_peel=depth_peel._res if depth_peel is not None else None)
+        return res
+
+
+def view(scene):
+    """The reference opens an X11 viewer; headless this returns immediately (SURVEY §3.2 caveat ii)."""
+    return None
