@@ -10,6 +10,7 @@
 // Replaces steps 6-10 and 14 of sl::RenderPass::render (reference: src/render_pass.cpp:407-622,696-710).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "k_frag.cuh"
 #include "kernels.h"
@@ -43,36 +44,47 @@ template <bool EMIT>
 __device__ __forceinline__ void bin_pair(uint32_t tile, const PairRec& rec, uint32_t* __restrict__ tile_count,
                                          const uint32_t* __restrict__ tile_off, PairRec* __restrict__ pairs, uint32_t capacity) {
     if (EMIT) {
-        uint32_t slot = atomicSub(tile_count + tile, 1u) - 1u;   // the count pass left the tile's total here
-        uint32_t at = __ldg(tile_off + tile) + slot;
+        // the scan left the END of the tile's segment in tile_count: one atomic yields the global slot
+        uint32_t at = atomicSub(tile_count + tile, 1u) - 1u;
         if (at < capacity) pairs[at] = rec;
     } else {
         atomicAdd(tile_count + tile, 1u);
     }
 }
 
-// bins one snapped sub-triangle; returns the number of (tile, sub-triangle) pairs it produced (big ones are queued
-// for the whole block and reported as 1)
+// Warp-aggregated variants: neighbouring triangles of a mesh mostly fall into the same tile, so the lanes of a
+// warp that target the same tile are grouped with __match_any_sync and only the group leader touches the
+// counter (one atomic per distinct tile per warp instead of one per lane). Must be called by converged lanes.
+__device__ __forceinline__ void count_pair_agg(uint32_t tile, bool valid, uint32_t* __restrict__ tile_count) {
+    const unsigned mask = __activemask();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(mask, valid ? tile : 0xFFFFFFFFu);
+    if (valid && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(tile_count + tile, (uint32_t)__popc(peers));
+}
+__device__ __forceinline__ void emit_pair_agg(uint32_t tile, bool valid, const PairRec& rec, uint32_t* __restrict__ tile_count,
+                                              PairRec* __restrict__ pairs, uint32_t capacity) {
+    const unsigned mask = __activemask();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(mask, valid ? tile : 0xFFFFFFFFu);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && lane == (unsigned)leader) base = atomicSub(tile_count + tile, (uint32_t)__popc(peers));   // old value = end of free space
+    base = __shfl_sync(mask, base, leader);
+    if (valid) {
+        const uint32_t at = base - 1u - (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        if (at < capacity) pairs[at] = rec;
+    }
+}
+
+// Tile walk of one snapped sub-triangle: COUNT pass (EMIT = false) increments the per-tile counters, EMIT pass
+// writes the PairRec into each tile's segment. Sub-triangles touching more than SLB_BIG_TILES tiles are queued
+// for the whole block. Returns the number of pairs produced (a queued one reports 1).
 template <bool EMIT>
-__device__ __forceinline__ int bin_subtri(int ax, int ay, int bx, int by, int cx, int cy, float az, float bz, float cz, uint32_t seq,
-                                          uint32_t k_flags, uint32_t draw, bool shadow, int W, int H, int tiles_x, uint32_t tile_base,
-                                          uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_off,
-                                          PairRec* __restrict__ pairs, uint32_t capacity, BigEntry* s_big, int* s_nbig) {
-    // pixel box first: most rejected sub-triangles die here, before any 64-bit arithmetic
-    const int xmin = min(ax, min(bx, cx)), xmax = max(ax, max(bx, cx));
-    const int ymin = min(ay, min(by, cy)), ymax = max(ay, max(by, cy));
-    const int px0 = max(0, (xmin - 128 + 255) >> 8), px1 = min(W - 1, (xmax - 128) >> 8);
-    const int py0 = max(0, (ymin - 128 + 255) >> 8), py1 = min(H - 1, (ymax - 128) >> 8);
-    if (px0 > px1 || py0 > py1) return 0;
-    const long long twoA = edge_fn(ax, ay, bx, by, cx, cy);
-    if (twoA == 0) return 0;
-    if (shadow && twoA < 0) return 0;   // shadow views cull FRONT faces (render_pass.cpp:428-429)
+__device__ __forceinline__ int bin_tiles(const PairRec& rec, long long twoA, int px0, int py0, int px1, int py1, int W, int H, int tiles_x,
+                                         uint32_t tile_base, uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_off,
+                                         PairRec* __restrict__ pairs, uint32_t capacity, BigEntry* s_big, int* s_nbig) {
     const int tx0 = px0 / SLB_TILE, tx1 = px1 / SLB_TILE, ty0 = py0 / SLB_TILE, ty1 = py1 / SLB_TILE;
     const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
-    PairRec rec;
-    rec.ax = ax; rec.ay = ay; rec.bx = bx; rec.by = by; rec.cx = cx; rec.cy = cy;
-    rec.az = az; rec.bz = bz; rec.cz = cz;
-    rec.seq = seq; rec.k_flags = k_flags; rec.draw = draw;
     if (ntx * nty == 1) {
         bin_pair<EMIT>(tile_base + ty0 * tiles_x + tx0, rec, tile_count, tile_off, pairs, capacity);
         return 1;
@@ -90,11 +102,11 @@ __device__ __forceinline__ int bin_subtri(int ax, int ay, int bx, int by, int cx
         }
     }
     SubTri st;
-    st.ax = ax; st.ay = ay; st.bx = bx; st.by = by; st.cx = cx; st.cy = cy;
+    st.ax = rec.ax; st.ay = rec.ay; st.bx = rec.bx; st.by = rec.by; st.cx = rec.cx; st.cy = rec.cy;
     st.s = twoA > 0 ? 1 : -1;
-    st.bias0 = top_left(cx - bx, cy - by, st.s) ? 0 : -1;
-    st.bias1 = top_left(ax - cx, ay - cy, st.s) ? 0 : -1;
-    st.bias2 = top_left(bx - ax, by - ay, st.s) ? 0 : -1;
+    st.bias0 = top_left(rec.cx - rec.bx, rec.cy - rec.by, st.s) ? 0 : -1;
+    st.bias1 = top_left(rec.ax - rec.cx, rec.ay - rec.cy, st.s) ? 0 : -1;
+    st.bias2 = top_left(rec.bx - rec.ax, rec.by - rec.ay, st.s) ? 0 : -1;
     int n = 0;
     for (int ty = ty0; ty <= ty1; ++ty)
         for (int tx = tx0; tx <= tx1; ++tx)
@@ -104,16 +116,64 @@ __device__ __forceinline__ int bin_subtri(int ax, int ay, int bx, int by, int cx
             }
     return n;
 }
-
-// primitives that need polygon clipping (rare: the background plane, triangles crossing the near plane)
+// the tail every bin kernel shares: the block walks the tiles of its queued large sub-triangles together
 template <bool EMIT>
-static __device__ __noinline__ int bin_clipped(const float* mvp, float3 p0, float3 p1, float3 p2, uint32_t seq, uint32_t flags,
-                                               uint32_t draw, bool shadow, const DFrame* fr, int W, int H, int tiles_x, uint32_t tile_base,
-                                               uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_off,
-                                               PairRec* __restrict__ pairs, uint32_t capacity, BigEntry* s_big, int* s_nbig) {
+__device__ __forceinline__ void bin_big_queue(const BigEntry* s_big, int nbig, const DView* __restrict__ views,
+                                              uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_off,
+                                              PairRec* __restrict__ pairs, uint32_t capacity) {
+    for (int q = 0; q < nbig; ++q) {
+        const BigEntry& e = s_big[q];
+        const DView& v = views[e.rec.k_flags >> 16];
+        SubTri st;
+        make_subtri(e.rec.ax, e.rec.ay, e.rec.bx, e.rec.by, e.rec.cx, e.rec.cy, e.rec.az, e.rec.bz, e.rec.cz, st);
+        const int n = e.ntx * e.nty;
+        for (int i = threadIdx.x; i < n; i += SLB_SETUP_CHUNK) {
+            int tx = e.tx0 + i % e.ntx, ty = e.ty0 + i / e.ntx;
+            if (tile_may_overlap(st, tx, ty, v.W, v.H))
+                bin_pair<EMIT>(v.tile_base + ty * v.tiles_x + tx, e.rec, tile_count, tile_off, pairs, capacity);
+        }
+    }
+}
+
+// pixel box of a snapped triangle inside a W x H viewport; false if it contains no pixel centre
+__device__ __forceinline__ bool pixel_box(int ax, int ay, int bx, int by, int cx, int cy, int W, int H, int& px0, int& py0, int& px1, int& py1) {
+    const int xmin = min(ax, min(bx, cx)), xmax = max(ax, max(bx, cx));
+    const int ymin = min(ay, min(by, cy)), ymax = max(ay, max(by, cy));
+    px0 = max(0, (xmin - 128 + 255) >> 8); px1 = min(W - 1, (xmax - 128) >> 8);
+    py0 = max(0, (ymin - 128 + 255) >> 8); py1 = min(H - 1, (ymax - 128) >> 8);
+    return px0 <= px1 && py0 <= py1;
+}
+
+// survivor test of one snapped sub-triangle (setup pass): fills `rec` and the tile range if it survives
+__device__ __forceinline__ bool survivor_test(int ax, int ay, int bx, int by, int cx, int cy, float az, float bz, float cz, uint32_t seq,
+                                              uint32_t k_flags, uint32_t draw, const DView& v, PairRec& rec, long long& twoA, int& px0,
+                                              int& py0, int& px1, int& py1) {
+    if (!pixel_box(ax, ay, bx, by, cx, cy, v.W, v.H, px0, py0, px1, py1)) return false;   // dies before any 64-bit arithmetic
+    twoA = edge_fn(ax, ay, bx, by, cx, cy);
+    if (twoA == 0) return false;
+    if (v.shadow && twoA < 0) return false;   // shadow views cull FRONT faces (render_pass.cpp:428-429)
+    rec.ax = ax; rec.ay = ay; rec.bx = bx; rec.by = by; rec.cx = cx; rec.cy = cy;
+    rec.az = az; rec.bz = bz; rec.cz = cz;
+    rec.seq = seq; rec.k_flags = k_flags; rec.draw = draw;
+    return true;
+}
+__device__ __forceinline__ bool setup_subtri_count(int ax, int ay, int bx, int by, int cx, int cy, float az, float bz, float cz, uint32_t seq,
+                                                   uint32_t k_flags, uint32_t draw, const DView& v, uint32_t* __restrict__ tile_count,
+                                                   BigEntry* s_big, int* s_nbig, PairRec& rec) {
+    long long twoA; int px0, py0, px1, py1;
+    if (!survivor_test(ax, ay, bx, by, cx, cy, az, bz, cz, seq, k_flags, draw, v, rec, twoA, px0, py0, px1, py1)) return false;
+    return bin_tiles<false>(rec, twoA, px0, py0, px1, py1, v.W, v.H, v.tiles_x, v.tile_base, tile_count, nullptr, nullptr, 0, s_big, s_nbig) > 0;
+}
+
+// primitives that need polygon clipping (rare: the background plane, triangles crossing the near plane): the
+// clipped polygon is published once for the fragment test / shade kernel; survivors are appended one by one
+static __device__ __noinline__ void setup_clipped_prim(const float* mvp, float3 p0, float3 p1, float3 p2, uint32_t seq, uint32_t flags,
+                                                       uint32_t draw, const DView& v, const DFrame* fr, uint32_t* __restrict__ tile_count,
+                                                       PairRec* __restrict__ survivors, uint32_t* __restrict__ counters, uint32_t surv_capacity,
+                                                       BigEntry* s_big, int* s_nbig) {
     PrimSetup ps;
-    if (!setup_prim(mvp, p0, p1, p2, W, H, ps)) return 0;
-    if (EMIT && fr) {   // publish the clipped polygon once for the fragment test and the shade kernel
+    if (!setup_prim(mvp, p0, p1, p2, v.W, v.H, ps)) return;
+    if (fr) {
         uint32_t slot = atomicAdd(fr->clip_count, 1u);
         if (slot < SLB_MAX_CLIP) {
             ClipRec& cr = fr->clip[slot];
@@ -124,42 +184,38 @@ static __device__ __noinline__ int bin_clipped(const float* mvp, float3 p0, floa
             }
         }
     }
-    int n = 0;
     for (int k = 1; k + 1 < ps.n; ++k) {
         const PolyV &a = ps.v[0], &b = ps.v[k], &c = ps.v[k + 1];
-        n += bin_subtri<EMIT>(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, (uint32_t)k | flags, draw, shadow, W, H, tiles_x, tile_base,
-                              tile_count, tile_off, pairs, capacity, s_big, s_nbig);
+        PairRec rec;
+        if (setup_subtri_count(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, (uint32_t)k | flags, draw, v, tile_count, s_big, s_nbig, rec)) {
+            uint32_t at = atomicAdd(&counters[0], 1u);
+            if (at < surv_capacity) survivors[at] = rec; else atomicExch(&counters[1], 1u);
+        }
     }
-    return n;
 }
 
-// Triangle setup + binning, one thread per triangle, one block per 256-triangle chunk of one draw. Pass 1 (EMIT =
-// false) counts pairs per tile and records, one bit per triangle, whether the triangle produced any pair; pass 2
-// (EMIT = true) skips the triangles whose bit is clear and writes the PairRecs into the tile segments.
-template <bool EMIT>
-__global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_bin(const DView* __restrict__ views, const DFrame* __restrict__ frames,
-                                                            const DBinDraw* __restrict__ bdraws, const uint32_t* __restrict__ chunk_draw,
-                                                            uint32_t* __restrict__ tri_mask, uint32_t* __restrict__ tile_count,
-                                                            const uint32_t* __restrict__ tile_off, PairRec* __restrict__ pairs,
-                                                            uint32_t capacity) {
+// PASS 1 — triangle setup: one thread per triangle, one block per 256-triangle chunk of one draw (camera or
+// shadow view). Transforms, clips, snaps (contract C1-C6), counts the (tile, sub-triangle) pairs per tile and
+// appends every surviving sub-triangle, already snapped, to the compact survivors[] array.
+__global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_setup(const DView* __restrict__ views, const DFrame* __restrict__ frames,
+                                                              const DBinDraw* __restrict__ bdraws, const uint32_t* __restrict__ chunk_draw,
+                                                              uint32_t* __restrict__ tile_count, PairRec* __restrict__ survivors,
+                                                              uint32_t* __restrict__ counters, uint32_t surv_capacity) {
     __shared__ float s_mvp[16];
     __shared__ BigEntry s_big[SLB_BIG_QUEUE];
     __shared__ int s_nbig;
+    __shared__ uint32_t s_wcount[SLB_SETUP_CHUNK / 32], s_base;
     const uint32_t di = __ldg(chunk_draw + blockIdx.x);   // host-built table: setup chunk -> bin draw
     const DBinDraw& d = bdraws[di];
     if (threadIdx.x < 16) s_mvp[threadIdx.x] = d.mvp[threadIdx.x];
     if (threadIdx.x == 32) s_nbig = 0;
     __syncthreads();
     const DView& v = views[d.view];
-    const int W = v.W, H = v.H, tiles_x = v.tiles_x;
-    const uint32_t tile_base = v.tile_base;
-    const bool shadow = v.shadow != 0;
     const uint32_t tri = (blockIdx.x - d.chunk_base) * SLB_SETUP_CHUNK + threadIdx.x;
-    const uint32_t mask_word = blockIdx.x * (SLB_SETUP_CHUNK / 32) + (threadIdx.x >> 5);
-    bool active = tri < d.n_tris;
-    if (EMIT) active = active && ((__ldg(tri_mask + mask_word) >> (threadIdx.x & 31)) & 1u);
-    int produced = 0;
-    if (active) {
+    PairRec rec;
+    bool has_rec = false;
+    uint32_t dt0 = 0xFFFFFFFFu, dt1 = 0xFFFFFFFFu;   // tiles of a one / two tile survivor
+    if (tri < d.n_tris) {
         const uint32_t* ip = d.idx + 3 * (size_t)tri;
         const uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
         const float4 p0 = __ldg(d.pos4 + i0), p1 = __ldg(d.pos4 + i1), p2 = __ldg(d.pos4 + i2);
@@ -169,36 +225,120 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_bin(const DView* __restr
         xform_clip(s_mvp, p2.x, p2.y, p2.z, c2);
         if (!(frustum_code(c0) & frustum_code(c1) & frustum_code(c2))) {
             const uint32_t seq = d.prim_base + tri;
-            const uint32_t flags = (d.flags & DRAW_FRAG_TEST) ? 0x100u : 0u;
+            const uint32_t flags = ((d.flags & DRAW_FRAG_TEST) ? 0x100u : 0u) | (d.view << 16);
             if (need_mask(c0) | need_mask(c1) | need_mask(c2)) {
-                produced = bin_clipped<EMIT>(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z),
-                                             seq, flags, d.draw, shadow, shadow ? nullptr : &frames[v.frame], W, H, tiles_x, tile_base,
-                                             tile_count, tile_off, pairs, capacity, s_big, &s_nbig);
+                setup_clipped_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), seq, flags,
+                                   d.draw, v, v.shadow ? nullptr : &frames[v.frame], tile_count, survivors, counters, surv_capacity, s_big, &s_nbig);
             } else {
-                const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+                const float hw = 0.5f * (float)v.W, hh = 0.5f * (float)v.H;
                 PolyV a, b, c;
-                if (project_vertex(c0, hw, hh, a) && project_vertex(c1, hw, hh, b) && project_vertex(c2, hw, hh, c))
-                    produced = bin_subtri<EMIT>(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, 1u | flags, d.draw, shadow, W, H, tiles_x,
-                                                tile_base, tile_count, tile_off, pairs, capacity, s_big, &s_nbig);
+                if (project_vertex(c0, hw, hh, a) && project_vertex(c1, hw, hh, b) && project_vertex(c2, hw, hh, c)) {
+                    long long twoA; int px0, py0, px1, py1;
+                    if (survivor_test(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, 1u | flags, d.draw, v, rec, twoA, px0, py0, px1, py1)) {
+                        const int tx0 = px0 / SLB_TILE, tx1 = px1 / SLB_TILE, ty0 = py0 / SLB_TILE, ty1 = py1 / SLB_TILE;
+                        if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= 2) {   // one or two tiles: counted warp-aggregated below
+                            has_rec = true;
+                            dt0 = v.tile_base + ty0 * v.tiles_x + tx0; dt1 = v.tile_base + ty1 * v.tiles_x + tx1;
+                        } else {
+                            has_rec = bin_tiles<false>(rec, twoA, px0, py0, px1, py1, v.W, v.H, v.tiles_x, v.tile_base, tile_count, nullptr, nullptr,
+                                                       0, s_big, &s_nbig) > 0;
+                        }
+                    }
+                }
             }
         }
     }
-    if (!EMIT) {
-        const unsigned m = __ballot_sync(0xffffffffu, produced > 0);
-        if ((threadIdx.x & 31) == 0) tri_mask[mask_word] = m;
+    count_pair_agg(dt0, dt0 != 0xFFFFFFFFu, tile_count);
+    count_pair_agg(dt1, dt1 != 0xFFFFFFFFu && dt1 != dt0, tile_count);
+    // compact the block's survivors: one global atomic per block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, has_rec);
+    if (lane == 0) s_wcount[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < SLB_SETUP_CHUNK / 32; ++w) { uint32_t c = s_wcount[w]; s_wcount[w] = total; total += c; }
+        s_base = total ? atomicAdd(&counters[0], total) : 0u;
     }
     __syncthreads();
-    const int nbig = min(s_nbig, SLB_BIG_QUEUE);
-    for (int q = 0; q < nbig; ++q) {   // large sub-triangles: all threads of the block share the tile walk
-        const BigEntry& e = s_big[q];
-        SubTri st;
-        make_subtri(e.rec.ax, e.rec.ay, e.rec.bx, e.rec.by, e.rec.cx, e.rec.cy, e.rec.az, e.rec.bz, e.rec.cz, st);
-        const int n = e.ntx * e.nty;
-        for (int i = threadIdx.x; i < n; i += SLB_SETUP_CHUNK) {
-            int tx = e.tx0 + i % e.ntx, ty = e.ty0 + i / e.ntx;
-            if (tile_may_overlap(st, tx, ty, W, H))
-                bin_pair<EMIT>(tile_base + ty * tiles_x + tx, e.rec, tile_count, tile_off, pairs, capacity);
+    if (has_rec) {
+        const uint32_t at = s_base + s_wcount[warp] + __popc(m & ((1u << lane) - 1u));
+        if (at < surv_capacity) survivors[at] = rec; else atomicExch(&counters[1], 1u);
+    }
+    bin_big_queue<false>(s_big, min(s_nbig, SLB_BIG_QUEUE), views, tile_count, nullptr, nullptr, 0);
+}
+
+// PASS 2 — emit: one thread per SURVIVOR (dense: no culled triangles, no vertex fetch, no transform). Records
+// touching one or two tiles are written directly; all others are queued in shared memory and their (record, tile)
+// work items are spread over the whole block, so no thread runs a long chain of dependent atomics.
+struct EmitEntry { PairRec rec; uint16_t tx0, ty0, ntx, nty; uint32_t n, sbits; };
+#define SLB_EMIT_QUEUE 160
+__global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_emit(const DView* __restrict__ views, const PairRec* __restrict__ survivors,
+                                                             uint32_t n_survivors, uint32_t* __restrict__ tile_count,
+                                                             PairRec* __restrict__ pairs, uint32_t capacity) {
+    __shared__ EmitEntry s_q[SLB_EMIT_QUEUE];
+    __shared__ uint32_t s_prefix[SLB_EMIT_QUEUE + 1];
+    __shared__ int s_nq;
+    if (threadIdx.x == 0) s_nq = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * SLB_SETUP_CHUNK + threadIdx.x;
+    PairRec rec;
+    uint32_t dt0 = 0xFFFFFFFFu, dt1 = 0xFFFFFFFFu;   // tiles of a one / two tile record
+    if (i < n_survivors) {
+        rec = survivors[i];
+        const DView& v = views[rec.k_flags >> 16];
+        int px0, py0, px1, py1;
+        pixel_box(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, v.W, v.H, px0, py0, px1, py1);
+        const int tx0 = px0 / SLB_TILE, tx1 = px1 / SLB_TILE, ty0 = py0 / SLB_TILE, ty1 = py1 / SLB_TILE;
+        const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
+        if (ntx * nty <= 2) {
+            dt0 = v.tile_base + ty0 * v.tiles_x + tx0; dt1 = v.tile_base + ty1 * v.tiles_x + tx1;
+        } else {
+            const long long twoA = edge_fn(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy);
+            const int sg = twoA > 0 ? 1 : -1;
+            const uint32_t sbits = (sg < 0 ? 1u : 0u) | (top_left(rec.cx - rec.bx, rec.cy - rec.by, sg) ? 0u : 2u) |
+                                   (top_left(rec.ax - rec.cx, rec.ay - rec.cy, sg) ? 0u : 4u) | (top_left(rec.bx - rec.ax, rec.by - rec.ay, sg) ? 0u : 8u);
+            const int q = atomicAdd(&s_nq, 1);
+            if (q < SLB_EMIT_QUEUE) {
+                EmitEntry& e = s_q[q];
+                e.rec = rec; e.tx0 = (uint16_t)tx0; e.ty0 = (uint16_t)ty0; e.ntx = (uint16_t)ntx; e.nty = (uint16_t)nty;
+                e.n = (uint32_t)(ntx * nty); e.sbits = sbits;
+            } else {   // queue full: walk the tiles alone
+                SubTri st;
+                st.ax = rec.ax; st.ay = rec.ay; st.bx = rec.bx; st.by = rec.by; st.cx = rec.cx; st.cy = rec.cy;
+                st.s = sg; st.bias0 = (sbits & 2) ? -1 : 0; st.bias1 = (sbits & 4) ? -1 : 0; st.bias2 = (sbits & 8) ? -1 : 0;
+                for (int ty = ty0; ty <= ty1; ++ty)
+                    for (int tx = tx0; tx <= tx1; ++tx)
+                        if (tile_may_overlap(st, tx, ty, v.W, v.H))
+                            bin_pair<true>(v.tile_base + ty * v.tiles_x + tx, rec, tile_count, nullptr, pairs, capacity);
+            }
         }
+    }
+    emit_pair_agg(dt0, dt0 != 0xFFFFFFFFu, rec, tile_count, pairs, capacity);
+    emit_pair_agg(dt1, dt1 != 0xFFFFFFFFu && dt1 != dt0, rec, tile_count, pairs, capacity);
+    __syncthreads();
+    const int nq = min(s_nq, SLB_EMIT_QUEUE);
+    if (nq == 0) return;
+    if (threadIdx.x == 0) {   // prefix sums of the per-entry tile counts (<= 160 entries)
+        uint32_t run = 0;
+        for (int q = 0; q < nq; ++q) { s_prefix[q] = run; run += s_q[q].n; }
+        s_prefix[nq] = run;
+    }
+    __syncthreads();
+    const uint32_t total = s_prefix[nq];
+    for (uint32_t w0 = 0; w0 < total; w0 += SLB_SETUP_CHUNK) {
+        const uint32_t w = w0 + threadIdx.x;
+        if (w >= total) { emit_pair_agg(0u, false, rec, tile_count, pairs, capacity); continue; }   // keeps the warp converged
+        int lo = 0, hi = nq - 1;   // last entry with prefix <= w
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_prefix[mid] <= w) lo = mid; else hi = mid - 1; }
+        const EmitEntry& e = s_q[lo];
+        const uint32_t k = w - s_prefix[lo];
+        const int tx = e.tx0 + (int)(k % e.ntx), ty = e.ty0 + (int)(k / e.ntx);
+        const DView& v = views[e.rec.k_flags >> 16];
+        SubTri st;
+        st.ax = e.rec.ax; st.ay = e.rec.ay; st.bx = e.rec.bx; st.by = e.rec.by; st.cx = e.rec.cx; st.cy = e.rec.cy;
+        st.s = (e.sbits & 1) ? -1 : 1; st.bias0 = (e.sbits & 2) ? -1 : 0; st.bias1 = (e.sbits & 4) ? -1 : 0; st.bias2 = (e.sbits & 8) ? -1 : 0;
+        emit_pair_agg(v.tile_base + ty * v.tiles_x + tx, tile_may_overlap(st, tx, ty, v.W, v.H), e.rec, tile_count, pairs, capacity);
     }
 }
 
@@ -237,7 +377,8 @@ __global__ void __launch_bounds__(1024) k_scan_local(const uint32_t* __restrict_
     block_exclusive_scan(sum, s_warp, total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
-__global__ void __launch_bounds__(1024) k_scan_sums(unsigned long long* __restrict__ block_sums, uint32_t n_blocks, uint32_t* __restrict__ totals) {
+__global__ void __launch_bounds__(1024) k_scan_sums(unsigned long long* __restrict__ block_sums, uint32_t n_blocks, uint32_t* __restrict__ totals,
+                                                    const uint32_t* __restrict__ counters) {
     __shared__ unsigned long long s_warp[33];
     __shared__ unsigned long long s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -252,9 +393,11 @@ __global__ void __launch_bounds__(1024) k_scan_sums(unsigned long long* __restri
         if (threadIdx.x == 0) s_carry += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { totals[0] = (uint32_t)s_carry; totals[1] = (uint32_t)(s_carry >> 32); }   // pairs, active tiles
+    if (threadIdx.x == 0) {   // pairs, active tiles, survivors, survivor overflow flag -> mapped host memory
+        totals[0] = (uint32_t)s_carry; totals[1] = (uint32_t)(s_carry >> 32); totals[2] = counters[0]; totals[3] = counters[1];
+    }
 }
-__global__ void __launch_bounds__(1024) k_scan_fix(const uint32_t* __restrict__ count, const unsigned long long* __restrict__ block_sums,
+__global__ void __launch_bounds__(1024) k_scan_fix(uint32_t* __restrict__ count, const unsigned long long* __restrict__ block_sums,
                                                    uint32_t* __restrict__ off, ActiveTile* __restrict__ active, uint32_t n) {
     __shared__ unsigned long long s_warp[33];
     const uint32_t base = blockIdx.x * SLB_SCAN_BLOCK + threadIdx.x * SLB_SCAN_ITEMS;
@@ -268,7 +411,10 @@ __global__ void __launch_bounds__(1024) k_scan_fix(const uint32_t* __restrict__ 
     for (int i = 0; i < SLB_SCAN_ITEMS; ++i) {
         if (base + i < n) {
             off[base + i] = (uint32_t)run;
-            if (c[i]) { ActiveTile a; a.tile = base + i; a.beg = (uint32_t)run; a.count = c[i]; a.pad = 0; active[(uint32_t)(run >> 32)] = a; }
+            if (c[i]) {
+                ActiveTile a; a.tile = base + i; a.beg = (uint32_t)run; a.count = c[i]; a.pad = 0; active[(uint32_t)(run >> 32)] = a;
+                count[base + i] = (uint32_t)run + c[i];   // becomes the emit pass's cursor (end of the segment)
+            }
         }
         run += pack_count(c[i]);
     }
@@ -518,10 +664,11 @@ __device__ __forceinline__ uint32_t find_draw_by_prim(const DDraw* __restrict__ 
     return lo;
 }
 
-__global__ void __launch_bounds__(256) k_shade(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws) {
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws) {
     const DFrame& f = frames[blockIdx.z];
     const int W = f.W, H = f.H;
-    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * (THREADS / 32) + (threadIdx.x >> 5);
     if (px >= W || py >= H) return;
     const size_t p = (size_t)py * W + px;
     const unsigned long long key = f.keys[p];
@@ -579,18 +726,22 @@ __global__ void __launch_bounds__(256) k_shade(const DFrame* __restrict__ frames
 // ---------------------------------------------------------------------------------------------
 namespace slbk {
 
-void launch_bin(bool emit, const DView* views, const DFrame* frames, const DBinDraw* bdraws, const uint32_t* chunk_draw,
-                uint32_t n_chunks, uint32_t* tri_mask, uint32_t* tile_count, const uint32_t* tile_off, PairRec* pairs, uint32_t capacity,
-                cudaStream_t s) {
+void launch_setup(const DView* views, const DFrame* frames, const DBinDraw* bdraws, const uint32_t* chunk_draw, uint32_t n_chunks,
+                  uint32_t* tile_count, PairRec* survivors, uint32_t* counters, uint32_t surv_capacity, cudaStream_t s) {
     if (n_chunks == 0) return;
-    if (emit) k_bin<true><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tri_mask, tile_count, tile_off, pairs, capacity);
-    else k_bin<false><<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tri_mask, tile_count, tile_off, pairs, capacity);
+    k_setup<<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tile_count, survivors, counters, surv_capacity);
 }
-void launch_scan(const uint32_t* count, uint32_t* off, ActiveTile* active, unsigned long long* block_sums, uint32_t* totals, uint32_t n,
-                 cudaStream_t s) {
+void launch_emit(const DView* views, const PairRec* survivors, uint32_t n_survivors, uint32_t* tile_count, PairRec* pairs,
+                 uint32_t capacity, cudaStream_t s) {
+    if (n_survivors == 0) return;
+    k_emit<<<(n_survivors + SLB_SETUP_CHUNK - 1) / SLB_SETUP_CHUNK, SLB_SETUP_CHUNK, 0, s>>>(views, survivors, n_survivors, tile_count, pairs,
+                                                                                           capacity);
+}
+void launch_scan(uint32_t* count, uint32_t* off, ActiveTile* active, unsigned long long* block_sums, uint32_t* totals,
+                 const uint32_t* counters, uint32_t n, cudaStream_t s) {
     const uint32_t n_blocks = (n + 1 + SLB_SCAN_BLOCK - 1) / SLB_SCAN_BLOCK;   // n + 1: some thread must own index n (the total)
     k_scan_local<<<n_blocks, 1024, 0, s>>>(count, block_sums, n);
-    k_scan_sums<<<1, 1024, 0, s>>>(block_sums, n_blocks, totals);
+    k_scan_sums<<<1, 1024, 0, s>>>(block_sums, n_blocks, totals, counters);
     k_scan_fix<<<n_blocks, 1024, 0, s>>>(count, block_sums, off, active, n);
 }
 void launch_raster(bool frag_test, const DView* views, const DFrame* frames, const DDraw* draws, const ActiveTile* active,
@@ -601,8 +752,8 @@ void launch_raster(bool frag_test, const DView* views, const DFrame* frames, con
     else k_raster<false><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(views, frames, draws, active, pairs, g);
 }
 void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, cudaStream_t s) {
-    dim3 grid((W + 31) / 32, (H + 7) / 8, n_frames);
-    k_shade<<<grid, 256, 0, s>>>(frames, draws);
+    // 256 threads = 32 x 8 pixels; (256, 2) = 128 registers measured fastest (tighter bounds spill, see profiles/)
+    k_shade<256, 2><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
 }
 
 }  // namespace slbk

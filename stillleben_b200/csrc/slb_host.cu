@@ -75,7 +75,7 @@ struct slb_ctx {
     // assets owned by the context
     slb_mesh* plane = nullptr;
     // per-batch device arrays
-    DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, tri_mask;
+    DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, survivors;
     DevBuf clip_recs, clip_counts;
     DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, ao, avg, mip_a, mip_b, shadow_maps;
     // pinned staging
@@ -202,7 +202,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
         if (ctx->slot_rendered[i]) cudaEventDestroy(ctx->slot_rendered[i]);
         if (ctx->slot_copied[i]) cudaEventDestroy(ctx->slot_copied[i]);
     }
-    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->tri_mask, &ctx->tile_count,
+    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->survivors, &ctx->tile_count,
                       &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->ao,
                       &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts};
     for (DevBuf* b : bufs) b->release();
@@ -913,7 +913,6 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     CU(ctx->scan_sums.reserve(((size_t)n_tiles / 4096 + 2) * 8));
     CU(ctx->active_tiles.reserve((size_t)n_tiles * sizeof(ActiveTile)));
     CU(ctx->scan_totals.reserve(64));
-    CU(ctx->tri_mask.reserve(((size_t)b.n_chunks + 1) * (SLB_SETUP_CHUNK / 32) * 4));
     CU(ctx->keys.reserve(npx * n * 8));
     CU(ctx->clip_recs.reserve((size_t)n * SLB_MAX_CLIP * sizeof(ClipRec)));
     CU(ctx->clip_counts.reserve((size_t)n * 4));
@@ -978,32 +977,49 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     const DBinDraw* bdraws_d = ctx->bdraws_d.as<DBinDraw>();
 
     CU(cudaMemsetAsync(ctx->clip_counts.p, 0, (size_t)n * 4, s));
+    CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, s));
     {   // "nothing drawn": keys = all ones, shadow d24 >= 0xFFFFFF; only non-empty tiles get a raster warp
         StageTimer t(ctx, s, ST_SHADOW);
         CU(cudaMemsetAsync(ctx->keys.p, 0xFF, npx * n * 8, s));
         if (b.n_shadow_maps) CU(cudaMemsetAsync(smaps, 0xFF, smap_elems * 4 * b.n_shadow_maps, s));
     }
-    // ---- bin (camera + shadow views together): count, scan, emit ----
-    {
-        StageTimer t(ctx, s, ST_COUNT);
-        launch_bin(false, views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks, ctx->tri_mask.as<uint32_t>(),
-                   ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), nullptr, 0, s);
+    // ---- setup (camera + shadow views together) -> scan -> emit ----
+    uint64_t total_bin_tris = 0;
+    for (const DBinDraw& bd : b.bdraws) total_bin_tris += bd.n_tris;
+    uint32_t total_pairs = 0, n_survivors = 0;
+    for (int attempt = 0;; ++attempt) {
+        const size_t want = (size_t)total_bin_tris + 4096;
+        if (ctx->survivors.cap < want * sizeof(PairRec)) CU(ctx->survivors.reserve(want * sizeof(PairRec)));
+        const uint32_t surv_capacity = (uint32_t)std::min<size_t>(ctx->survivors.cap / sizeof(PairRec), 0xFFFFFFF0u);
+        CU(cudaMemsetAsync(ctx->scan_totals.p, 0, 64, s));   // [0] survivor count, [1] overflow flag
+        {
+            StageTimer t(ctx, s, ST_COUNT);
+            launch_setup(views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks, ctx->tile_count.as<uint32_t>(),
+                         ctx->survivors.as<PairRec>(), ctx->scan_totals.as<uint32_t>(), surv_capacity, s);
+        }
+        {
+            StageTimer t(ctx, s, ST_SCAN);
+            launch_scan(ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->active_tiles.as<ActiveTile>(),
+                        ctx->scan_sums.as<unsigned long long>(), ctx->total_pinned, ctx->scan_totals.as<uint32_t>(), n_tiles, s);
+        }
+        // The scan writes its totals straight into page-locked host memory (UVA): a D2H memcpy here would queue
+        // behind the result copies of the previous sub-batch on the copy engine and serialise the pipeline.
+        CU(cudaStreamSynchronize(s));   // the pair buffer, the emit grid and the raster grid are sized from the exact totals
+        if (ctx->total_pinned[3] == 0) break;
+        // more clipped sub-triangles than triangles + 4096 (pathological): grow the survivor buffer and redo the pass
+        if (attempt == 4) return fail(ctx, SLB_ERR_RUNTIME, "slb_render_batch: survivor buffer overflow");
+        total_bin_tris = total_bin_tris * 2 + 65536;
+        CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, s));
+        CU(cudaMemsetAsync(ctx->clip_counts.p, 0, (size_t)n * 4, s));
     }
-    {
-        StageTimer t(ctx, s, ST_SCAN);
-        launch_scan(ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->active_tiles.as<ActiveTile>(),
-                    ctx->scan_sums.as<unsigned long long>(), ctx->total_pinned, n_tiles, s);
-    }
-    // The scan writes its two totals straight into page-locked host memory (UVA): a D2H memcpy here would queue
-    // behind the result copies of the previous sub-batch on the copy engine and serialise the pipeline.
-    CU(cudaStreamSynchronize(s));   // the pair buffer and the raster grid are sized from the exact totals
-    const uint32_t total_pairs = ctx->total_pinned[0];
+    total_pairs = ctx->total_pinned[0];
     grid.n_active = ctx->total_pinned[1];
+    n_survivors = ctx->total_pinned[2];
     CU(ctx->pairs.reserve(((size_t)total_pairs + 1) * sizeof(PairRec)));
     {
         StageTimer t(ctx, s, ST_EMIT);
-        launch_bin(true, views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks, ctx->tri_mask.as<uint32_t>(),
-                   ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->pairs.as<PairRec>(), total_pairs, s);
+        launch_emit(views_d, ctx->survivors.as<PairRec>(), n_survivors, ctx->tile_count.as<uint32_t>(), ctx->pairs.as<PairRec>(),
+                    total_pairs, s);
     }
     {
         StageTimer t(ctx, s, ST_RASTER);
