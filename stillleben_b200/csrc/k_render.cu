@@ -165,12 +165,25 @@ __device__ __forceinline__ bool setup_subtri_count(int ax, int ay, int bx, int b
     return bin_tiles<false>(rec, twoA, px0, py0, px1, py1, v.W, v.H, v.tiles_x, v.tile_base, tile_count, nullptr, nullptr, 0, s_big, s_nbig) > 0;
 }
 
+// Survivors of the tiled path. Ordinary ones are compacted into survivors[0 .. normal_cap); HUGE ones (more than
+// SLB_HUGE_TILES tiles: the background plane, close-up faces) go to survivors[normal_cap + i] and are emitted by
+// a kernel that gives each of them a whole block, so a handful of screen-filling triangles never serialises
+// on one thread block. counters: [0] ordinary survivors, [1] overflow flag, [2] huge survivors.
+#define SLB_HUGE_TILES 64
+struct SurvOut { PairRec* survivors; uint32_t* counters; uint32_t normal_cap, huge_cap; };
+__device__ __forceinline__ void append_huge(const SurvOut& so, const PairRec& rec) {
+    const uint32_t at = atomicAdd(&so.counters[2], 1u);
+    if (at < so.huge_cap) so.survivors[so.normal_cap + at] = rec; else atomicExch(&so.counters[1], 1u);
+}
+__device__ __forceinline__ int tiles_of_box(int px0, int py0, int px1, int py1) {
+    return (px1 / SLB_TILE - px0 / SLB_TILE + 1) * (py1 / SLB_TILE - py0 / SLB_TILE + 1);
+}
+
 // primitives that need polygon clipping (rare: the background plane, triangles crossing the near plane): the
 // clipped polygon is published once for the fragment test / shade kernel; survivors are appended one by one
 static __device__ __noinline__ void setup_clipped_prim(const float* mvp, float3 p0, float3 p1, float3 p2, uint32_t seq, uint32_t flags,
                                                        uint32_t draw, const DView& v, const DFrame* fr, uint32_t* __restrict__ tile_count,
-                                                       PairRec* __restrict__ survivors, uint32_t* __restrict__ counters, uint32_t surv_capacity,
-                                                       BigEntry* s_big, int* s_nbig) {
+                                                       const SurvOut& so, BigEntry* s_big, int* s_nbig) {
     PrimSetup ps;
     if (!setup_prim(mvp, p0, p1, p2, v.W, v.H, ps)) return;
     if (fr) {
@@ -188,8 +201,78 @@ static __device__ __noinline__ void setup_clipped_prim(const float* mvp, float3 
         const PolyV &a = ps.v[0], &b = ps.v[k], &c = ps.v[k + 1];
         PairRec rec;
         if (setup_subtri_count(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, (uint32_t)k | flags, draw, v, tile_count, s_big, s_nbig, rec)) {
-            uint32_t at = atomicAdd(&counters[0], 1u);
-            if (at < surv_capacity) survivors[at] = rec; else atomicExch(&counters[1], 1u);
+            int px0, py0, px1, py1;
+            pixel_box(a.X, a.Y, b.X, b.Y, c.X, c.Y, v.W, v.H, px0, py0, px1, py1);
+            if (tiles_of_box(px0, py0, px1, py1) > SLB_HUGE_TILES) { append_huge(so, rec); continue; }
+            uint32_t at = atomicAdd(&so.counters[0], 1u);
+            if (at < so.normal_cap) so.survivors[at] = rec; else atomicExch(&so.counters[1], 1u);
+        }
+    }
+}
+
+// Direct path for SMALL unclipped triangles (the bulk of a 16k-triangle mesh at table-top distance covers a
+// handful of pixels): rasterised by ONE thread right in the setup kernel, every covered pixel merged into the
+// view's output with a fire-and-forget L2 atomic (RED.MIN: u64 visibility key, or u32 d24 for a shadow view).
+// No survivor record, no per-tile pair, no raster warp. The result is the same minimum the tiled path takes,
+// so coverage, depth and ids stay bit-identical (contract C6/C7); all edge arithmetic fits 32 bits because the
+// triangle spans < 64 px (coordinates taken relative to vertex a).
+__device__ __forceinline__ void red_min_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.min.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_min_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// G = 1: the thread walks the triangle's pixel box alone.  G = 32: the warp walks it together, lane l taking the
+// box pixels l, l+32, ... in row-major order (mid-size triangles, e.g. a 16k-triangle mesh seen from a 2048^2
+// shadow view), so the cost per triangle is box/32 iterations instead of one iteration per touched tile.
+template <bool SHADOW, int G>
+__device__ __forceinline__ void raster_direct(int ax, int ay, int bx, int by, int cx, int cy, float az, float bz, float cz, uint32_t seq,
+                                              void* __restrict__ out, int W, int H, int lane) {
+    const int xmin = min(ax, min(bx, cx)), xmax = max(ax, max(bx, cx));
+    const int ymin = min(ay, min(by, cy)), ymax = max(ay, max(by, cy));
+    const int px0 = max(0, (xmin - 128 + 255) >> 8), px1 = min(W - 1, (xmax - 128) >> 8);
+    const int py0 = max(0, (ymin - 128 + 255) >> 8), py1 = min(H - 1, (ymax - 128) >> 8);
+    const int rbx = bx - ax, rby = by - ay, rcx = cx - ax, rcy = cy - ay;
+    const int twoA = rbx * rcy - rby * rcx;
+    const int sg = twoA > 0 ? 1 : -1;
+    const float inv2A = __fdiv_rn(1.0f, __int2float_rn(twoA));
+    const int bias0 = top_left(cx - bx, cy - by, sg) ? 0 : -1;
+    const int bias1 = top_left(ax - cx, ay - cy, sg) ? 0 : -1;
+    const int bias2 = top_left(bx - ax, by - ay, sg) ? 0 : -1;
+    const int qx = px0 * 256 + 128 - ax, qy = py0 * 256 + 128 - ay;
+    const int e0r = sg * ((rcx - rbx) * (qy - rby) - (rcy - rby) * (qx - rbx)) + bias0;   // s*edge(b,c,p) + bias at (px0, py0)
+    const int e1r = sg * (rcy * (qx - rcx) - rcx * (qy - rcy)) + bias1;                   // s*edge(c,a,p) + bias
+    const int e2r = sg * (rbx * qy - rby * qx) + bias2;                                   // s*edge(a,b,p) + bias
+    const int dx0 = -sg * (rcy - rby) * 256, dy0 = sg * (rcx - rbx) * 256;
+    const int dx1 = sg * rcy * 256, dy1 = -sg * rcx * 256;
+    const int dx2 = -sg * rby * 256, dy2 = sg * rbx * 256;
+    const float zb = __fsub_rn(bz, az), zc = __fsub_rn(cz, az);
+    const unsigned long long lowkey = ((unsigned long long)seq << 8) | 1ull;
+    auto plot = [&](int e1, int e2, int x, int y) {   // contract C7 on a covered pixel, merged with RED.MIN
+        const int w1 = sg * (e1 - bias1), w2 = sg * (e2 - bias2);
+        const float q1 = __fmul_rn(__int2float_rn(w1), inv2A), q2 = __fmul_rn(__int2float_rn(w2), inv2A);
+        float z = __fmaf_rn(q2, zc, __fmaf_rn(q1, zb, az));
+        z = fminf(fmaxf(z, 0.0f), 1.0f);
+        const uint32_t d24 = __float2uint_rn(__fmul_rn(z, 16777215.0f));
+        if (SHADOW) red_min_u32(reinterpret_cast<uint32_t*>(out) + (size_t)y * W + x, d24);
+        else red_min_u64(reinterpret_cast<unsigned long long*>(out) + (size_t)y * W + x, ((unsigned long long)d24 << 40) | lowkey);
+    };
+    if (G == 1) {
+        int f0 = e0r, f1 = e1r, f2 = e2r;
+        for (int y = py0; y <= py1; ++y, f0 += dy0, f1 += dy1, f2 += dy2) {
+            int e0 = f0, e1 = f1, e2 = f2;
+            for (int x = px0; x <= px1; ++x, e0 += dx0, e1 += dx1, e2 += dx2)
+                if ((e0 | e1 | e2) >= 0) plot(e1, e2, x, y);
+        }
+    } else {
+        const int bw = px1 - px0 + 1, n = bw * (py1 - py0 + 1);
+        const int qstep = G / bw, rstep = G - qstep * bw;   // advancing G pixels in row-major order = (qstep rows, rstep columns)
+        int x = lane % bw, y = lane / bw;
+        for (int i = lane; i < n; i += G) {
+            const int e0 = e0r + x * dx0 + y * dy0, e1 = e1r + x * dx1 + y * dy1, e2 = e2r + x * dx2 + y * dy2;
+            if ((e0 | e1 | e2) >= 0) plot(e1, e2, px0 + x, py0 + y);
+            x += rstep; y += qstep;
+            if (x >= bw) { x -= bw; ++y; }
         }
     }
 }
@@ -199,16 +282,18 @@ static __device__ __noinline__ void setup_clipped_prim(const float* mvp, float3 
 // appends every surviving sub-triangle, already snapped, to the compact survivors[] array.
 __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_setup(const DView* __restrict__ views, const DFrame* __restrict__ frames,
                                                               const DBinDraw* __restrict__ bdraws, const uint32_t* __restrict__ chunk_draw,
-                                                              uint32_t* __restrict__ tile_count, PairRec* __restrict__ survivors,
-                                                              uint32_t* __restrict__ counters, uint32_t surv_capacity) {
+                                                              uint32_t* __restrict__ tile_count, const SurvOut so, int direct_max, int warp_max) {
     __shared__ float s_mvp[16];
     __shared__ BigEntry s_big[SLB_BIG_QUEUE];
     __shared__ int s_nbig;
     __shared__ uint32_t s_wcount[SLB_SETUP_CHUNK / 32], s_base;
+    __shared__ int s_dq[10][SLB_SETUP_CHUNK];   // direct-path queue (structure of arrays: conflict-free)
+    __shared__ int s_ndirect, s_nmid, s_mid_next;
     const uint32_t di = __ldg(chunk_draw + blockIdx.x);   // host-built table: setup chunk -> bin draw
     const DBinDraw& d = bdraws[di];
     if (threadIdx.x < 16) s_mvp[threadIdx.x] = d.mvp[threadIdx.x];
     if (threadIdx.x == 32) s_nbig = 0;
+    if (threadIdx.x == 33) { s_ndirect = 0; s_nmid = 0; s_mid_next = 0; }
     __syncthreads();
     const DView& v = views[d.view];
     const uint32_t tri = (blockIdx.x - d.chunk_base) * SLB_SETUP_CHUNK + threadIdx.x;
@@ -228,7 +313,7 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_setup(const DView* __res
             const uint32_t flags = ((d.flags & DRAW_FRAG_TEST) ? 0x100u : 0u) | (d.view << 16);
             if (need_mask(c0) | need_mask(c1) | need_mask(c2)) {
                 setup_clipped_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), seq, flags,
-                                   d.draw, v, v.shadow ? nullptr : &frames[v.frame], tile_count, survivors, counters, surv_capacity, s_big, &s_nbig);
+                                   d.draw, v, v.shadow ? nullptr : &frames[v.frame], tile_count, so, s_big, &s_nbig);
             } else {
                 const float hw = 0.5f * (float)v.W, hh = 0.5f * (float)v.H;
                 PolyV a, b, c;
@@ -236,12 +321,22 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_setup(const DView* __res
                     long long twoA; int px0, py0, px1, py1;
                     if (survivor_test(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, 1u | flags, d.draw, v, rec, twoA, px0, py0, px1, py1)) {
                         const int tx0 = px0 / SLB_TILE, tx1 = px1 / SLB_TILE, ty0 = py0 / SLB_TILE, ty1 = py1 / SLB_TILE;
-                        if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= 2) {   // one or two tiles: counted warp-aggregated below
+                        const int ext_x = max(a.X, max(b.X, c.X)) - min(a.X, min(b.X, c.X)), ext_y = max(a.Y, max(b.Y, c.Y)) - min(a.Y, min(b.Y, c.Y));
+                        if (!(flags & 0x100u) && ext_x < 16384 && ext_y < 16384 && (px1 - px0 + 1) * (py1 - py0 + 1) <= warp_max) {
+                            // small / mid-size triangle: queued for the direct path below (never becomes a survivor). Small
+                            // ones fill the queue from the front (one thread each), mid-size ones from the back (one warp each).
+                            const bool small = (px1 - px0 + 1) * (py1 - py0 + 1) <= direct_max;
+                            const int q = small ? atomicAdd(&s_ndirect, 1) : SLB_SETUP_CHUNK - 1 - atomicAdd(&s_nmid, 1);
+                            s_dq[0][q] = a.X; s_dq[1][q] = a.Y; s_dq[2][q] = b.X; s_dq[3][q] = b.Y; s_dq[4][q] = c.X; s_dq[5][q] = c.Y;
+                            s_dq[6][q] = __float_as_int(a.z); s_dq[7][q] = __float_as_int(b.z); s_dq[8][q] = __float_as_int(c.z);
+                            s_dq[9][q] = (int)seq;
+                        } else if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= 2) {   // one or two tiles: counted warp-aggregated below
                             has_rec = true;
                             dt0 = v.tile_base + ty0 * v.tiles_x + tx0; dt1 = v.tile_base + ty1 * v.tiles_x + tx1;
                         } else {
                             has_rec = bin_tiles<false>(rec, twoA, px0, py0, px1, py1, v.W, v.H, v.tiles_x, v.tile_base, tile_count, nullptr, nullptr,
                                                        0, s_big, &s_nbig) > 0;
+                            if (has_rec && (tx1 - tx0 + 1) * (ty1 - ty0 + 1) > SLB_HUGE_TILES) { append_huge(so, rec); has_rec = false; }
                         }
                     }
                 }
@@ -258,14 +353,34 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_setup(const DView* __res
     if (threadIdx.x == 0) {
         uint32_t total = 0;
         for (int w = 0; w < SLB_SETUP_CHUNK / 32; ++w) { uint32_t c = s_wcount[w]; s_wcount[w] = total; total += c; }
-        s_base = total ? atomicAdd(&counters[0], total) : 0u;
+        s_base = total ? atomicAdd(&so.counters[0], total) : 0u;
     }
     __syncthreads();
     if (has_rec) {
         const uint32_t at = s_base + s_wcount[warp] + __popc(m & ((1u << lane) - 1u));
-        if (at < surv_capacity) survivors[at] = rec; else atomicExch(&counters[1], 1u);
+        if (at < so.normal_cap) so.survivors[at] = rec; else atomicExch(&so.counters[1], 1u);
     }
     bin_big_queue<false>(s_big, min(s_nbig, SLB_BIG_QUEUE), views, tile_count, nullptr, nullptr, 0);
+    // direct path: the block's small triangles, densely packed, one per thread ...
+#define SLB_DQ(q) s_dq[0][q], s_dq[1][q], s_dq[2][q], s_dq[3][q], s_dq[4][q], s_dq[5][q], __int_as_float(s_dq[6][q]), \
+                  __int_as_float(s_dq[7][q]), __int_as_float(s_dq[8][q]), (uint32_t)s_dq[9][q]
+    if ((int)threadIdx.x < s_ndirect) {
+        const int q = threadIdx.x;
+        if (v.shadow) raster_direct<true, 1>(SLB_DQ(q), v.out, v.W, v.H, 0);
+        else raster_direct<false, 1>(SLB_DQ(q), v.out, v.W, v.H, 0);
+    }
+    // ... then the mid-size ones, one per warp, handed out dynamically
+    const int nmid = s_nmid;
+    for (;;) {
+        int m = 0;
+        if (lane == 0) m = atomicAdd(&s_mid_next, 1);
+        m = __shfl_sync(0xffffffffu, m, 0);
+        if (m >= nmid) break;
+        const int q = SLB_SETUP_CHUNK - 1 - m;
+        if (v.shadow) raster_direct<true, 32>(SLB_DQ(q), v.out, v.W, v.H, lane);
+        else raster_direct<false, 32>(SLB_DQ(q), v.out, v.W, v.H, lane);
+    }
+#undef SLB_DQ
 }
 
 // PASS 2 — emit: one thread per SURVIVOR (dense: no culled triangles, no vertex fetch, no transform). Records
@@ -342,6 +457,23 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_emit(const DView* __rest
     }
 }
 
+// PASS 2b — one block per HUGE survivor: the block's threads stride over the tiles of its bounding box.
+__global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_emit_huge(const DView* __restrict__ views, const PairRec* __restrict__ huge,
+                                                               uint32_t* __restrict__ tile_count, PairRec* __restrict__ pairs, uint32_t capacity) {
+    const PairRec rec = huge[blockIdx.x];
+    const DView& v = views[rec.k_flags >> 16];
+    int px0, py0, px1, py1;
+    pixel_box(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, v.W, v.H, px0, py0, px1, py1);
+    const int tx0 = px0 / SLB_TILE, ty0 = py0 / SLB_TILE;
+    const int ntx = px1 / SLB_TILE - tx0 + 1, nty = py1 / SLB_TILE - ty0 + 1;
+    SubTri st;
+    make_subtri(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, rec.az, rec.bz, rec.cz, st);
+    for (int i = threadIdx.x; i < ntx * nty; i += SLB_SETUP_CHUNK) {
+        const int tx = tx0 + i % ntx, ty = ty0 + i / ntx;
+        if (tile_may_overlap(st, tx, ty, v.W, v.H)) bin_pair<true>(v.tile_base + ty * v.tiles_x + tx, rec, tile_count, nullptr, pairs, capacity);
+    }
+}
+
 // Exclusive scan of the n tile counts into off[0..n] (off[n] = total pairs) fused with the compaction of the
 // non-empty tiles into active[]: the scanned value packs (pair count, non-empty flag) into 64 bits, so one scan
 // yields both the tile's pair offset and its slot in the active list. Three kernels: block-local scans of 4096
@@ -394,7 +526,7 @@ __global__ void __launch_bounds__(1024) k_scan_sums(unsigned long long* __restri
         __syncthreads();
     }
     if (threadIdx.x == 0) {   // pairs, active tiles, survivors, survivor overflow flag -> mapped host memory
-        totals[0] = (uint32_t)s_carry; totals[1] = (uint32_t)(s_carry >> 32); totals[2] = counters[0]; totals[3] = counters[1];
+        totals[0] = (uint32_t)s_carry; totals[1] = (uint32_t)(s_carry >> 32); totals[2] = counters[0]; totals[3] = counters[1]; totals[4] = counters[2];
     }
 }
 __global__ void __launch_bounds__(1024) k_scan_fix(uint32_t* __restrict__ count, const unsigned long long* __restrict__ block_sums,
@@ -493,7 +625,23 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DView* _
     const int lx = lane & 7, ly = lane >> 3;
     const uint32_t beg = act.beg, n = act.count;
     unsigned long long* keys = s_key[warp];
-    keys[lane] = SLB_KEY_EMPTY; keys[lane + 32] = SLB_KEY_EMPTY;
+    {   // start from what the setup kernel's direct path already merged into this tile of the output
+        const int gx = x_lo + lx;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int gy = y_lo + ly + 4 * h;
+            unsigned long long k0 = SLB_KEY_EMPTY;
+            if (gx < W && gy < H) {
+                if (v.shadow) {
+                    const uint32_t g0 = reinterpret_cast<const uint32_t*>(v.out)[(size_t)gy * W + gx];
+                    if (g0 <= 0xFFFFFFu) k0 = (unsigned long long)g0 << 40;
+                } else {
+                    k0 = reinterpret_cast<const unsigned long long*>(v.out)[(size_t)gy * W + gx];
+                }
+            }
+            keys[lane + 32 * h] = k0;
+        }
+    }
 
     if (n > 0) {
         uint64_t* bar = s_bar[warp];
@@ -727,15 +875,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
 namespace slbk {
 
 void launch_setup(const DView* views, const DFrame* frames, const DBinDraw* bdraws, const uint32_t* chunk_draw, uint32_t n_chunks,
-                  uint32_t* tile_count, PairRec* survivors, uint32_t* counters, uint32_t surv_capacity, cudaStream_t s) {
+                  uint32_t* tile_count, PairRec* survivors, uint32_t* counters, uint32_t normal_cap, uint32_t huge_cap, int direct_max,
+                  int warp_max, cudaStream_t s) {
     if (n_chunks == 0) return;
-    k_setup<<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tile_count, survivors, counters, surv_capacity);
+    SurvOut so;
+    so.survivors = survivors; so.counters = counters; so.normal_cap = normal_cap; so.huge_cap = huge_cap;
+    k_setup<<<n_chunks, SLB_SETUP_CHUNK, 0, s>>>(views, frames, bdraws, chunk_draw, tile_count, so, direct_max, max(direct_max, warp_max));
 }
-void launch_emit(const DView* views, const PairRec* survivors, uint32_t n_survivors, uint32_t* tile_count, PairRec* pairs,
-                 uint32_t capacity, cudaStream_t s) {
-    if (n_survivors == 0) return;
-    k_emit<<<(n_survivors + SLB_SETUP_CHUNK - 1) / SLB_SETUP_CHUNK, SLB_SETUP_CHUNK, 0, s>>>(views, survivors, n_survivors, tile_count, pairs,
-                                                                                           capacity);
+void launch_emit(const DView* views, const PairRec* survivors, uint32_t n_survivors, const PairRec* huge, uint32_t n_huge,
+                 uint32_t* tile_count, PairRec* pairs, uint32_t capacity, cudaStream_t s) {
+    if (n_survivors)
+        k_emit<<<(n_survivors + SLB_SETUP_CHUNK - 1) / SLB_SETUP_CHUNK, SLB_SETUP_CHUNK, 0, s>>>(views, survivors, n_survivors, tile_count, pairs,
+                                                                                               capacity);
+    if (n_huge) k_emit_huge<<<n_huge, SLB_SETUP_CHUNK, 0, s>>>(views, huge, tile_count, pairs, capacity);
 }
 void launch_scan(uint32_t* count, uint32_t* off, ActiveTile* active, unsigned long long* block_sums, uint32_t* totals,
                  const uint32_t* counters, uint32_t n, cudaStream_t s) {

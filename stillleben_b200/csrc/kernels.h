@@ -9,9 +9,10 @@ namespace slbk {
 
 // k_render.cu
 void launch_setup(const DView* views, const DFrame* frames, const DBinDraw* bdraws, const uint32_t* chunk_draw, uint32_t n_chunks,
-                  uint32_t* tile_count, PairRec* survivors, uint32_t* counters, uint32_t surv_capacity, cudaStream_t s);
-void launch_emit(const DView* views, const PairRec* survivors, uint32_t n_survivors, uint32_t* tile_count, PairRec* pairs,
-                 uint32_t capacity, cudaStream_t s);
+                  uint32_t* tile_count, PairRec* survivors, uint32_t* counters, uint32_t normal_cap, uint32_t huge_cap, int direct_max,
+                  int warp_max, cudaStream_t s);
+void launch_emit(const DView* views, const PairRec* survivors, uint32_t n_survivors, const PairRec* huge, uint32_t n_huge,
+                 uint32_t* tile_count, PairRec* pairs, uint32_t capacity, cudaStream_t s);
 void launch_scan(uint32_t* count, uint32_t* off, ActiveTile* active, unsigned long long* block_sums, uint32_t* totals,
                  const uint32_t* counters, uint32_t n, cudaStream_t s);
 struct RasterGrid { uint32_t n_active, n_cam_tiles, tiles_per_cam, n_cam_views, tiles_per_shadow; };

@@ -71,6 +71,9 @@ struct slb_ctx {
     std::string err;
     bool time_kernels = false, keep_hdr = false;
     int max_subbatch = 16;
+    // largest pixel box (in pixels) the setup kernel rasterises directly with one thread / with one warp; larger
+    // triangles take the tiled path (tunables: env SLB_DIRECT_MAX, SLB_WARP_MAX)
+    int direct_max = 128, warp_max = 4096;
     slb_stats stats;
     // assets owned by the context
     slb_mesh* plane = nullptr;
@@ -154,6 +157,8 @@ extern "C" int slb_ctx_create(int device, slb_ctx** out) {
     slb_ctx* c = new slb_ctx;
     c->device = device;
     std::memset(&c->stats, 0, sizeof c->stats);
+    if (const char* dm = getenv("SLB_DIRECT_MAX")) c->direct_max = atoi(dm);
+    if (const char* wm = getenv("SLB_WARP_MAX")) c->warp_max = atoi(wm);
     ctx = c;
     cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
@@ -986,16 +991,19 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     // ---- setup (camera + shadow views together) -> scan -> emit ----
     uint64_t total_bin_tris = 0;
     for (const DBinDraw& bd : b.bdraws) total_bin_tris += bd.n_tris;
-    uint32_t total_pairs = 0, n_survivors = 0;
+    uint32_t total_pairs = 0, n_survivors = 0, n_huge = 0, normal_cap = 0;
     for (int attempt = 0;; ++attempt) {
-        const size_t want = (size_t)total_bin_tris + 4096;
+        // ordinary survivors in [0, normal_cap), huge ones (whole block each in the emit pass) in the last fifth
+        const size_t want = (size_t)total_bin_tris + total_bin_tris / 4 + 8192;
         if (ctx->survivors.cap < want * sizeof(PairRec)) CU(ctx->survivors.reserve(want * sizeof(PairRec)));
         const uint32_t surv_capacity = (uint32_t)std::min<size_t>(ctx->survivors.cap / sizeof(PairRec), 0xFFFFFFF0u);
-        CU(cudaMemsetAsync(ctx->scan_totals.p, 0, 64, s));   // [0] survivor count, [1] overflow flag
+        const uint32_t huge_cap = surv_capacity / 5;
+        normal_cap = surv_capacity - huge_cap;
+        CU(cudaMemsetAsync(ctx->scan_totals.p, 0, 64, s));   // [0] survivor count, [1] overflow flag, [2] huge survivor count
         {
             StageTimer t(ctx, s, ST_COUNT);
             launch_setup(views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks, ctx->tile_count.as<uint32_t>(),
-                         ctx->survivors.as<PairRec>(), ctx->scan_totals.as<uint32_t>(), surv_capacity, s);
+                         ctx->survivors.as<PairRec>(), ctx->scan_totals.as<uint32_t>(), normal_cap, huge_cap, ctx->direct_max, ctx->warp_max, s);
         }
         {
             StageTimer t(ctx, s, ST_SCAN);
@@ -1015,11 +1023,12 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     total_pairs = ctx->total_pinned[0];
     grid.n_active = ctx->total_pinned[1];
     n_survivors = ctx->total_pinned[2];
+    n_huge = ctx->total_pinned[4];
     CU(ctx->pairs.reserve(((size_t)total_pairs + 1) * sizeof(PairRec)));
     {
         StageTimer t(ctx, s, ST_EMIT);
-        launch_emit(views_d, ctx->survivors.as<PairRec>(), n_survivors, ctx->tile_count.as<uint32_t>(), ctx->pairs.as<PairRec>(),
-                    total_pairs, s);
+        launch_emit(views_d, ctx->survivors.as<PairRec>(), n_survivors, ctx->survivors.as<PairRec>() + normal_cap, n_huge,
+                    ctx->tile_count.as<uint32_t>(), ctx->pairs.as<PairRec>(), total_pairs, s);
     }
     {
         StageTimer t(ctx, s, ST_RASTER);
@@ -1029,7 +1038,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
         StageTimer t(ctx, s, ST_SHADE);
         launch_shade(frames_d, draws_d, n, W, H, s);
     }
-    ctx->stats.kernel_launches += (b.n_chunks ? 2 : 0) + 5;
+    ctx->stats.kernel_launches += (b.n_chunks ? 1 : 0) + 3 + (n_survivors ? 1 : 0) + (n_huge ? 1 : 0) + (grid.n_active ? 1 : 0) + 1;
     if (post) {
         if (b.any_auto) {   // 1x1 level of the mip chain of the HDR target, taken before background / SSAO
             StageTimer t(ctx, s, ST_POST);
