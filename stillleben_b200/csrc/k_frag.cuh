@@ -211,40 +211,41 @@ static __device__ __noinline__ void tangent_frame(const DDraw& d, const uint32_t
     }
 }
 
-// perspective-correct barycentrics w.r.t. the ORIGINAL triangle at pixel (px,py) of a sub-triangle
-// (render_shader.geom:13-35: smooth-interpolated barycentric basis)
-__device__ __forceinline__ void subtri_bary(const SubTri& st, const PolyV& a, const PolyV& b, const PolyV& c, int px, int py,
-                                            float out[3]) {
-    long long w0, w1, w2; subtri_weights(st, px, py, w0, w1, w2);
+// perspective-correct barycentrics w.r.t. the ORIGINAL triangle from the three edge-function values of a
+// sub-triangle (render_shader.geom:13-35: smooth-interpolated barycentric basis). `unit_basis`: the sub-triangle
+// IS the unclipped primitive, its vertices carry the basis (1,0,0),(0,1,0),(0,0,1) and the combination is the identity.
+__device__ __forceinline__ void bary_from_weights(const SubTri& st, const PolyV& a, const PolyV& b, const PolyV& c, long long w0,
+                                                  long long w1, long long w2, bool unit_basis, float out[3]) {
     float b0 = __ll2float_rn(w0) * st.inv2A, b1 = __ll2float_rn(w1) * st.inv2A, b2 = __ll2float_rn(w2) * st.inv2A;
     float g0 = b0 * a.invw, g1 = b1 * b.invw, g2 = b2 * c.invw;
     float s = g0 + g1 + g2;
     float q0 = g0 / s, q1 = g1 / s, q2 = g2 / s;
+    if (unit_basis) { out[0] = q0; out[1] = q1; out[2] = q2; return; }
 #pragma unroll
     for (int j = 0; j < 3; ++j) out[j] = q0 * a.b[j] + q1 * b.b[j] + q2 * c.b[j];
 }
 
 // The three snapped vertices of sub-triangle k of primitive `tri` of draw d: recomputed in registers when the
-// primitive is unclipped, fetched from the binner's ClipRec list when it was clipped.
-__device__ __forceinline__ bool fetch_subtri(const DFrame& f, const DDraw& d, uint32_t tri, uint32_t seq, int k, const uint32_t vi[3],
-                                             PolyV& a, PolyV& b, PolyV& c) {
-    float4 p0 = __ldg(d.pos4 + vi[0]), p1 = __ldg(d.pos4 + vi[1]), p2 = __ldg(d.pos4 + vi[2]);
-    const float3 q0 = make_float3(p0.x, p0.y, p0.z), q1 = make_float3(p1.x, p1.y, p1.z), q2 = make_float3(p2.x, p2.y, p2.z);
+// primitive is unclipped (returns 1), fetched from the binner's ClipRec list when it was clipped (returns 2);
+// 0 = culled. pm[] receives the three mesh-space vertices (xyz + one-based vertex id in w).
+__device__ __forceinline__ int fetch_subtri(const DFrame& f, const DDraw& d, uint32_t seq, int k, const uint32_t vi[3], float4 pm[3],
+                                            PolyV& a, PolyV& b, PolyV& c) {
+    pm[0] = __ldg(d.pos4 + vi[0]); pm[1] = __ldg(d.pos4 + vi[1]); pm[2] = __ldg(d.pos4 + vi[2]);
+    const float3 q0 = make_float3(pm[0].x, pm[0].y, pm[0].z), q1 = make_float3(pm[1].x, pm[1].y, pm[1].z), q2 = make_float3(pm[2].x, pm[2].y, pm[2].z);
     int r = setup_subtri_fast(d.mvp, q0, q1, q2, f.W, f.H, k, a, b, c);
-    if (r >= 0) return r == 1;
+    if (r >= 0) return r;
     const uint32_t n = min(*f.clip_count, (uint32_t)SLB_MAX_CLIP);
     for (uint32_t i = 0; i < n; ++i) {
         const ClipRec& cr = f.clip[i];
         if (cr.seq != seq) continue;
-        if (k < 1 || k + 1 >= cr.n) return false;
+        if (k < 1 || k + 1 >= cr.n) return 0;
         const DPolyV &va = cr.v[0], &vb = cr.v[k], &vc = cr.v[k + 1];
         a.X = va.X; a.Y = va.Y; a.z = va.z; a.invw = va.invw; a.b[0] = va.b[0]; a.b[1] = va.b[1]; a.b[2] = va.b[2];
         b.X = vb.X; b.Y = vb.Y; b.z = vb.z; b.invw = vb.invw; b.b[0] = vb.b[0]; b.b[1] = vb.b[1]; b.b[2] = vb.b[2];
         c.X = vc.X; c.Y = vc.Y; c.z = vc.z; c.invw = vc.invw; c.b[0] = vc.b[0]; c.b[1] = vc.b[1]; c.b[2] = vc.b[2];
-        return true;
+        return 2;
     }
-    (void)tri;
-    return resetup_clipped(d.mvp, q0, q1, q2, f.W, f.H, k, a, b, c);
+    return resetup_clipped(d.mvp, q0, q1, q2, f.W, f.H, k, a, b, c) ? 2 : 0;
 }
 
 struct FragIn {
@@ -253,33 +254,79 @@ struct FragIn {
     bool front;
 };
 
-// Runs the vertex stage on the three vertices and interpolates its outputs at pixel (px,py), one vertex at
-// a time so that only one VSOut is live (sum order ((v0*b0 + v1*b1) + v2*b2) as in the smooth varyings).
-// dFdx / dFdy of uv come from the 2x2 quad partner evaluated on the same primitive (helper invocation).
-__device__ __forceinline__ void shade_inputs(const DFrame& f, const DDraw& d, const SubTri& st, const PolyV& a, const PolyV& b,
-                                             const PolyV& c, const uint32_t vi[3], int px, int py, bool want_derivs, FragIn& in,
-                                             float bary[3], uint32_t vid[3]) {
-    subtri_bary(st, a, b, c, px, py, bary);
-    float bx[3] = {0.f, 0.f, 0.f}, by[3] = {0.f, 0.f, 0.f};
-    if (want_derivs) {
-        subtri_bary(st, a, b, c, px ^ 1, py, bx);
-        subtri_bary(st, a, b, c, px, py ^ 1, by);
-    }
-    float ux = 0.f, vx = 0.f, uy = 0.f, vy = 0.f;
-    in.u = in.v = in.su = in.sv = 0.f;
-    in.nW = in.wc = in.cc = mk3(0.f, 0.f, 0.f);
+// General vertex-stage path (a transformation with a projective last row): the vertex stage runs on the three
+// vertices and its outputs are interpolated, one vertex at a time (sum order ((v0*b0 + v1*b1) + v2*b2)).
+static __device__ __noinline__ void interpolate_general(const DFrame& f, const DDraw& d, const uint32_t vi[3], const float bary[3],
+                                                        FragIn& in) {
+    in.su = in.sv = 0.f;
+    in.wc = in.cc = mk3(0.f, 0.f, 0.f);
     in.objc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
     for (int j = 0; j < 3; ++j) {
-        VSOut v;
-        vertex_stage(f, d, vi[j], v, vid[j]);
+        VSOut v; uint32_t id;
+        vertex_stage(f, d, vi[j], v, id);
         const float w = bary[j];
-        in.u += v.u * w; in.v += v.v * w;
-        in.nW = in.nW + v.nW * w;
         in.wc = in.wc + v.wc * w; in.cc = in.cc + v.cc * w;
         in.objc = in.objc + v.objc * w;
         in.su += v.su * w; in.sv += v.sv * w;
-        ux += v.u * bx[j]; vx += v.v * bx[j]; uy += v.u * by[j]; vy += v.v * by[j];
+    }
+}
+
+// Inputs of the fragment stage at pixel (px,py): the interpolated outputs of the vertex stage
+// (render_shader.vert:57-95). For affine transformation chains (every rigid / scaled pose: DRAW_AFFINE) the
+// positions are interpolated in the mesh frame and transformed ONCE — mathematically identical because the
+// weights sum to one, and a third of the arithmetic; normals and sticker coordinates are non-linear per vertex
+// and stay per vertex. dFdx / dFdy of uv come from the 2x2 quad partner evaluated on the same primitive
+// (helper invocation); its edge-function values are the pixel's own plus / minus one exact integer step.
+__device__ __forceinline__ void shade_inputs(const DFrame& f, const DDraw& d, const SubTri& st, const PolyV& a, const PolyV& b,
+                                             const PolyV& c, const uint32_t vi[3], const float4 pm[3], bool unit_basis, int px, int py,
+                                             bool want_derivs, FragIn& in, float bary[3], uint32_t vid[3]) {
+    long long w0, w1, w2; subtri_weights(st, px, py, w0, w1, w2);
+    bary_from_weights(st, a, b, c, w0, w1, w2, unit_basis, bary);
+    float bx[3] = {0.f, 0.f, 0.f}, by[3] = {0.f, 0.f, 0.f};
+    if (want_derivs) {
+        const long long sx = (px & 1) ? -256 : 256, sy = (py & 1) ? -256 : 256;   // towards the quad partner
+        bary_from_weights(st, a, b, c, w0 - sx * (st.cy - st.by), w1 - sx * (st.ay - st.cy), w2 - sx * (st.by - st.ay), unit_basis, bx);
+        bary_from_weights(st, a, b, c, w0 + sy * (st.cx - st.bx), w1 + sy * (st.ax - st.cx), w2 + sy * (st.bx - st.ax), unit_basis, by);
+    }
+    float ux = 0.f, vx = 0.f, uy = 0.f, vy = 0.f;
+    in.u = in.v = 0.f;
+    in.nW = mk3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {   // uv and the (per-vertex normalised) world-space normal
+        vid[j] = __float_as_uint(pm[j].w);
+        const float4 a0 = __ldg(d.attr + 3 * (size_t)vi[j]), a1 = __ldg(d.attr + 3 * (size_t)vi[j] + 1);
+        const float w = bary[j];
+        in.u += a0.x * w; in.v += a0.y * w;
+        in.nW = in.nW + normalize3(mul_m3(d.normalToWorld, mk3(a0.z, a0.w, a1.x))) * w;
+        ux += a0.x * bx[j]; vx += a0.y * bx[j]; uy += a0.x * by[j]; vy += a0.y * by[j];
+    }
+    if (d.flags & DRAW_AFFINE) {
+        const float mx = pm[0].x * bary[0] + pm[1].x * bary[1] + pm[2].x * bary[2];
+        const float my = pm[0].y * bary[0] + pm[1].y * bary[1] + pm[2].y * bary[2];
+        const float mz = pm[0].z * bary[0] + pm[1].z * bary[1] + pm[2].z * bary[2];
+        const float* M = d.meshToObject;
+        const float ox = M[0] * mx + M[4] * my + M[8] * mz + M[12], oy = M[1] * mx + M[5] * my + M[9] * mz + M[13],
+                    oz = M[2] * mx + M[6] * my + M[10] * mz + M[14];
+        const float* O = d.objectToWorld;
+        in.wc = mk3(O[0] * ox + O[4] * oy + O[8] * oz + O[12], O[1] * ox + O[5] * oy + O[9] * oz + O[13],
+                    O[2] * ox + O[6] * oy + O[10] * oz + O[14]);
+        const float* V = f.V;
+        in.cc = mk3(V[0] * in.wc.x + V[4] * in.wc.y + V[8] * in.wc.z + V[12], V[1] * in.wc.x + V[5] * in.wc.y + V[9] * in.wc.z + V[13],
+                    V[2] * in.wc.x + V[6] * in.wc.y + V[10] * in.wc.z + V[14]);
+        in.objc = make_float4(ox, oy, oz, in.cc.z);
+        in.su = in.sv = -1.0f;
+        if (d.sticker) {   // projective per vertex (render_shader.vert:86-92), then interpolated
+            in.su = in.sv = 0.f;
+            for (int j = 0; j < 3; ++j) {
+                const float qx = M[0] * pm[j].x + M[4] * pm[j].y + M[8] * pm[j].z + M[12], qy = M[1] * pm[j].x + M[5] * pm[j].y + M[9] * pm[j].z + M[13],
+                            qz = M[2] * pm[j].x + M[6] * pm[j].y + M[10] * pm[j].z + M[14];
+                const float4 sp = mul_m4_p(d.stickerProj, qx, qy, qz, 1.0f);
+                in.su += (sp.x / sp.w - d.stickerRange[0]) / d.stickerRange[2] * bary[j];
+                in.sv += (sp.y / sp.w - d.stickerRange[1]) / d.stickerRange[3] * bary[j];
+            }
+        }
+    } else {
+        interpolate_general(f, d, vi, bary, in);
     }
     in.front = st.twoA < 0;   // FrontFace = CW (render_pass.cpp:330)
     in.u_dx = in.v_dx = in.u_dy = in.v_dy = 0.0f;

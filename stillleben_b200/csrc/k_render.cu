@@ -586,11 +586,13 @@ __device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint3
     const uint32_t* ip = d.idx + 3 * (size_t)tri;
     const uint32_t vi[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
     PolyV a, b, c;
-    if (!fetch_subtri(f, d, tri, seq, k, vi, a, b, c)) return true;
+    float4 pm[3];
+    const int how = fetch_subtri(f, d, seq, k, vi, pm, a, b, c);
+    if (!how) return true;
     SubTri st;
     if (!make_subtri(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, st)) return true;
     FragIn in; float bary[3]; uint32_t vid[3];
-    shade_inputs(f, d, st, a, b, c, vi, px, py, d.tex[0] != nullptr, in, bary, vid);
+    shade_inputs(f, d, st, a, b, c, vi, pm, how == 1, px, py, d.tex[0] != nullptr, in, bary, vid);
     if (f.peel && in.objc.w - 0.00001f <= f.peel[((size_t)py * f.W + px) * 4 + 3]) return true;
     if ((d.flags & DRAW_FRAG_TEST) && base_color(d, in).w < 0.5f) return true;
     return false;
@@ -832,15 +834,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
     if (key != SLB_KEY_EMPTY) {
         const uint32_t seq = (uint32_t)(key >> 8);
         const int k = (int)(key & 0xffu);
-        const DDraw& d = draws[find_draw_by_prim(draws, f.draw_begin, f.draw_end, seq)];
+        // the draw is encoded in the sequence number when the frame's draws fit (host: build_batch), else searched
+        const DDraw& d = draws[f.seq_shift ? f.draw_begin + (seq >> f.seq_shift) : find_draw_by_prim(draws, f.draw_begin, f.draw_end, seq)];
         const uint32_t tri = seq - d.prim_base;
         const uint32_t* ip = d.idx + 3 * (size_t)tri;
         const uint32_t vi[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
         PolyV va, vb, vc;
         SubTri st;
-        if (fetch_subtri(f, d, tri, seq, k, vi, va, vb, vc) && make_subtri(va.X, va.Y, vb.X, vb.Y, vc.X, vc.Y, va.z, vb.z, vc.z, st)) {
+        float4 pm[3];
+        const int how = fetch_subtri(f, d, seq, k, vi, pm, va, vb, vc);
+        if (how && make_subtri(va.X, va.Y, vb.X, vb.Y, vc.X, vc.Y, va.z, vb.z, vc.z, st)) {
             FragIn in; float bary[3]; uint32_t vid[3];
-            shade_inputs(f, d, st, va, vb, vc, vi, px, py, draw_has_textures(d), in, bary, vid);
+            shade_inputs(f, d, st, va, vb, vc, vi, pm, how == 1, px, py, draw_has_textures(d), in, bary, vid);
             // geometry targets first: their registers are free before the lighting code runs
             if (o_coord) o_coord[p] = in.objc;
             if (o_cls) o_cls[p] = (unsigned short)d.class_index;
@@ -905,7 +910,14 @@ void launch_raster(bool frag_test, const DView* views, const DFrame* frames, con
 }
 void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, cudaStream_t s) {
     // 256 threads = 32 x 8 pixels; (256, 2) = 128 registers measured fastest (tighter bounds spill, see profiles/)
-    k_shade<256, 2><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
+    static const int variant = getenv("SLB_SHADE_VARIANT") ? atoi(getenv("SLB_SHADE_VARIANT")) : 3;
+    switch (variant) {
+        case 1: k_shade<128, 4><<<dim3((W + 31) / 32, (H + 3) / 4, n_frames), 128, 0, s>>>(frames, draws); break;
+        case 2: k_shade<128, 5><<<dim3((W + 31) / 32, (H + 3) / 4, n_frames), 128, 0, s>>>(frames, draws); break;
+        case 3: k_shade<256, 3><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws); break;
+        case 4: k_shade<64, 10><<<dim3((W + 31) / 32, (H + 1) / 2, n_frames), 64, 0, s>>>(frames, draws); break;
+        default: k_shade<256, 2><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
+    }
 }
 
 }  // namespace slbk

@@ -39,7 +39,7 @@ struct DDraw {
     const float4* attr;            // 3 x float4 per vertex: (u,v,nx,ny) (nz,tx,ty,tz) (tw,0,0,0)
     const uint32_t* idx;           // already offset to the sub-mesh's first index
     uint32_t n_tris;
-    uint32_t prim_base;            // sequence number of triangle 0 within the frame (submission order)
+    uint32_t prim_base;            // sequence number of triangle 0 within the frame (increasing in submission order)
     uint32_t frame;                // frame index within the batch
     uint32_t pad0;
     float mvp[16];
@@ -55,7 +55,10 @@ struct DDraw {
     uint32_t flags;                // DRAW_*
     uint32_t pad;
 };
-enum { DRAW_FRAG_TEST = 1u };      // coverage depends on the fragment stage (alpha test / depth peel)
+enum {
+    DRAW_FRAG_TEST = 1u,           // coverage depends on the fragment stage (alpha test / depth peel)
+    DRAW_AFFINE = 2u               // meshToObject, objectToWorld and the view matrix all have the last row (0,0,0,1)
+};
 
 // What the binner needs of one draw. Camera views and shadow views go through the SAME setup / bin / raster
 // kernels: a shadow map is just another view with its own tile grid, front faces culled and depth-only output.
@@ -87,7 +90,7 @@ struct ClipRec { uint32_t seq; int32_t n; DPolyV v[10]; };
 
 struct DFrame {
     int32_t W, H, tiles_x, tiles_y;
-    uint32_t pad1;
+    uint32_t seq_shift;            // > 0: sequence number = (draw - draw_begin) << seq_shift | triangle (order preserving); 0: prim_base search
     uint32_t draw_begin, draw_end;
     uint32_t n_prims;
     float P[16], V[16], Pinv[16];

@@ -797,6 +797,8 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
             mvp(P, V, o2w, m2o, d.mvp);
             normal_matrix(mul(o2w, m2o), d.normalToWorld);
             if (frag_all) d.flags |= DRAW_FRAG_TEST;
+            auto affine = [](const float* m) { return m[3] == 0.0f && m[7] == 0.0f && m[11] == 0.0f && m[15] == 1.0f; };
+            if (affine(d.meshToObject) && affine(d.objectToWorld) && affine(f.V)) d.flags |= DRAW_AFFINE;
             b.any_frag_test |= (d.flags & DRAW_FRAG_TEST) != 0;
             b.n_tris += n_tris;
             DBinDraw bd; std::memset(&bd, 0, sizeof bd);
@@ -845,6 +847,23 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
         }
         f.draw_end = (uint32_t)b.draws.size();
         f.n_prims = prim;
+        {   // Encode the draw in the sequence number when it fits 32 bits: seq = local draw << shift | triangle keeps the
+            // submission order (all the visibility key needs) and saves the shade kernel its search over prim_base.
+            uint32_t max_tris = 1;
+            for (uint32_t di = f.draw_begin; di < f.draw_end; ++di) max_tris = std::max(max_tris, b.draws[di].n_tris);
+            uint32_t shift = 1;
+            while (shift < 32 && (1ull << shift) < max_tris) ++shift;
+            const uint64_t n_draws = f.draw_end - f.draw_begin;
+            f.seq_shift = 0;
+            if (n_draws && shift < 32 && ((n_draws - 1) << shift) + max_tris <= 0xFFFFFFFFull) {
+                f.seq_shift = shift;
+                const size_t bd0 = b.bdraws.size() - n_draws;   // this frame's camera bin draws were pushed together with its draws
+                for (uint32_t li = 0; li < n_draws; ++li) {
+                    b.draws[f.draw_begin + li].prim_base = li << shift;
+                    b.bdraws[bd0 + li].prim_base = li << shift;
+                }
+            }
+        }
 
         // ---- shadow views (render_pass.cpp:407-460): one 2048^2 depth-only view per active light ----
         if (anyLight) {
