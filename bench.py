@@ -226,7 +226,7 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
     sub = ctx.stats()
-    n_sub = -(-n_local // (args.subbatch or 16))
+    n_sub = -(-n_local // (args.subbatch or 64))
     shade_ms_per_launch = stage_ms[5] / (args.steps * n_sub)
     frames_per_launch = n_local / n_sub
     alg_bytes = frames_per_launch * W * H * BYTES_PER_PX
@@ -237,7 +237,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"C3: fixed batch of {args.scenes} scenes x {N_OBJECTS} objects ({POOL}-mesh pool, 16384 tris each), "
                                    f"{W}x{H}, six targets (40 B/px), 1 shadow light + ambient, exposure 1, SSAO off",
-                       "scenes_per_gpu": n_local, "subbatch": args.subbatch or 16,
+                       "scenes_per_gpu": n_local, "subbatch": args.subbatch or 64,
                        "l2": "outputs per step (%.1f GB) exceed L2; no flush needed" % (n_local * W * H * BYTES_PER_PX / 1e9)},
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "stage_ms_per_step": {n: float(v / args.steps) for n, v in zip(names, stage_ms)},

@@ -279,7 +279,7 @@ int slb_ctx_get_stats(slb_ctx* ctx, slb_stats* out);
 enum {
     SLB_OPT_TIME_KERNELS = 1, /* record per-kernel CUDA-event times (adds syncs; off by default) */
     SLB_OPT_KEEP_HDR = 2,     /* keep the HDR colour buffer readable after render             */
-    SLB_OPT_MAX_SUBBATCH = 3  /* frames per internal sub-batch (default 32)                   */
+    SLB_OPT_MAX_SUBBATCH = 3  /* frames per internal sub-batch (default 64)                   */
 };
 int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value);
 

@@ -225,19 +225,17 @@ __device__ __forceinline__ void bary_from_weights(const SubTri& st, const PolyV&
     for (int j = 0; j < 3; ++j) out[j] = q0 * a.b[j] + q1 * b.b[j] + q2 * c.b[j];
 }
 
-// The three snapped vertices of sub-triangle k of primitive `tri` of draw d: recomputed in registers when the
-// primitive is unclipped (returns 1), fetched from the binner's ClipRec list when it was clipped (returns 2);
-// 0 = culled. pm[] receives the three mesh-space vertices (xyz + one-based vertex id in w).
-__device__ __forceinline__ int fetch_subtri(const DFrame& f, const DDraw& d, uint32_t seq, int k, const uint32_t vi[3], float4 pm[3],
+// The three snapped vertices of one sub-triangle of a primitive of draw d. `kbyte` is the low byte of the
+// visibility key: fan index k in bits 0..2 and, for a clipped primitive, the slot + 1 of the ClipRec the setup
+// kernel published in bits 3..7 — the clipped, snapped polygon is then read back instead of re-clipped
+// (returns 2). Unclipped primitives are re-set-up in registers (returns 1); 0 = culled. pm[] receives the three
+// mesh-space vertices (xyz + one-based vertex id in w).
+__device__ __forceinline__ int fetch_subtri(const DFrame& f, const DDraw& d, uint32_t seq, int kbyte, const uint32_t vi[3], float4 pm[3],
                                             PolyV& a, PolyV& b, PolyV& c) {
     pm[0] = __ldg(d.pos4 + vi[0]); pm[1] = __ldg(d.pos4 + vi[1]); pm[2] = __ldg(d.pos4 + vi[2]);
-    const float3 q0 = make_float3(pm[0].x, pm[0].y, pm[0].z), q1 = make_float3(pm[1].x, pm[1].y, pm[1].z), q2 = make_float3(pm[2].x, pm[2].y, pm[2].z);
-    int r = setup_subtri_fast(d.mvp, q0, q1, q2, f.W, f.H, k, a, b, c);
-    if (r >= 0) return r;
-    const uint32_t n = min(*f.clip_count, (uint32_t)SLB_MAX_CLIP);
-    for (uint32_t i = 0; i < n; ++i) {
-        const ClipRec& cr = f.clip[i];
-        if (cr.seq != seq) continue;
+    const int k = kbyte & 7, slot = kbyte >> 3;
+    if (slot) {
+        const ClipRec& cr = f.clip[slot - 1];
         if (k < 1 || k + 1 >= cr.n) return 0;
         const DPolyV &va = cr.v[0], &vb = cr.v[k], &vc = cr.v[k + 1];
         a.X = va.X; a.Y = va.Y; a.z = va.z; a.invw = va.invw; a.b[0] = va.b[0]; a.b[1] = va.b[1]; a.b[2] = va.b[2];
@@ -245,6 +243,10 @@ __device__ __forceinline__ int fetch_subtri(const DFrame& f, const DDraw& d, uin
         c.X = vc.X; c.Y = vc.Y; c.z = vc.z; c.invw = vc.invw; c.b[0] = vc.b[0]; c.b[1] = vc.b[1]; c.b[2] = vc.b[2];
         return 2;
     }
+    const float3 q0 = make_float3(pm[0].x, pm[0].y, pm[0].z), q1 = make_float3(pm[1].x, pm[1].y, pm[1].z), q2 = make_float3(pm[2].x, pm[2].y, pm[2].z);
+    int r = setup_subtri_fast(d.mvp, q0, q1, q2, f.W, f.H, k, a, b, c);
+    if (r >= 0) return r;
+    (void)seq;   // clipped, but the frame's ClipRec table was full: clip again
     return resetup_clipped(d.mvp, q0, q1, q2, f.W, f.H, k, a, b, c) ? 2 : 0;
 }
 

@@ -169,7 +169,7 @@ __device__ __forceinline__ bool setup_subtri_count(int ax, int ay, int bx, int b
 // SLB_HUGE_TILES tiles: the background plane, close-up faces) go to survivors[normal_cap + i] and are emitted by
 // a kernel that gives each of them a whole block, so a handful of screen-filling triangles never serialises
 // on one thread block. counters: [0] ordinary survivors, [1] overflow flag, [2] huge survivors.
-#define SLB_HUGE_TILES 64
+#define SLB_HUGE_TILES 2
 struct SurvOut { PairRec* survivors; uint32_t* counters; uint32_t normal_cap, huge_cap; };
 __device__ __forceinline__ void append_huge(const SurvOut& so, const PairRec& rec) {
     const uint32_t at = atomicAdd(&so.counters[2], 1u);
@@ -186,9 +186,11 @@ static __device__ __noinline__ void setup_clipped_prim(const float* mvp, float3 
                                                        const SurvOut& so, BigEntry* s_big, int* s_nbig) {
     PrimSetup ps;
     if (!setup_prim(mvp, p0, p1, p2, v.W, v.H, ps)) return;
+    uint32_t slot_bits = 0;   // (ClipRec slot + 1) << 3, carried in the key so the consumers index the record directly
     if (fr) {
         uint32_t slot = atomicAdd(fr->clip_count, 1u);
         if (slot < SLB_MAX_CLIP) {
+            slot_bits = (slot + 1u) << 3;
             ClipRec& cr = fr->clip[slot];
             cr.seq = seq; cr.n = ps.n;
             for (int i = 0; i < ps.n; ++i) {
@@ -200,7 +202,7 @@ static __device__ __noinline__ void setup_clipped_prim(const float* mvp, float3 
     for (int k = 1; k + 1 < ps.n; ++k) {
         const PolyV &a = ps.v[0], &b = ps.v[k], &c = ps.v[k + 1];
         PairRec rec;
-        if (setup_subtri_count(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, (uint32_t)k | flags, draw, v, tile_count, s_big, s_nbig, rec)) {
+        if (setup_subtri_count(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, (uint32_t)k | slot_bits | flags, draw, v, tile_count, s_big, s_nbig, rec)) {
             int px0, py0, px1, py1;
             pixel_box(a.X, a.Y, b.X, b.Y, c.X, c.Y, v.W, v.H, px0, py0, px1, py1);
             if (tiles_of_box(px0, py0, px1, py1) > SLB_HUGE_TILES) { append_huge(so, rec); continue; }
@@ -458,7 +460,8 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_emit(const DView* __rest
 }
 
 // PASS 2b — one block per HUGE survivor: the block's threads stride over the tiles of its bounding box.
-__global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_emit_huge(const DView* __restrict__ views, const PairRec* __restrict__ huge,
+#define SLB_HUGE_THREADS 64
+__global__ void __launch_bounds__(SLB_HUGE_THREADS) k_emit_huge(const DView* __restrict__ views, const PairRec* __restrict__ huge,
                                                                uint32_t* __restrict__ tile_count, PairRec* __restrict__ pairs, uint32_t capacity) {
     const PairRec rec = huge[blockIdx.x];
     const DView& v = views[rec.k_flags >> 16];
@@ -468,7 +471,7 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK) k_emit_huge(const DView* __re
     const int ntx = px1 / SLB_TILE - tx0 + 1, nty = py1 / SLB_TILE - ty0 + 1;
     SubTri st;
     make_subtri(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, rec.az, rec.bz, rec.cz, st);
-    for (int i = threadIdx.x; i < ntx * nty; i += SLB_SETUP_CHUNK) {
+    for (int i = threadIdx.x; i < ntx * nty; i += SLB_HUGE_THREADS) {
         const int tx = tx0 + i % ntx, ty = ty0 + i / ntx;
         if (tile_may_overlap(st, tx, ty, v.W, v.H)) bin_pair<true>(v.tile_base + ty * v.tiles_x + tx, rec, tile_count, nullptr, pairs, capacity);
     }
@@ -581,7 +584,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #define SLB_RASTER_SMALL 24   // sub-triangles whose in-tile pixel box is at most this big are rasterised by ONE lane
 
 // fragment-stage discards that decide coverage: depth peel + alpha test (render_shader.frag:229-246)
-__device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint32_t seq, int k, int px, int py) {
+__device__ __noinline__ bool frag_discard(const DFrame& f, const DDraw& d, uint32_t seq, int k /* low key byte */, int px, int py) {
     const uint32_t tri = seq - d.prim_base;
     const uint32_t* ip = d.idx + 3 * (size_t)tri;
     const uint32_t vi[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
@@ -892,7 +895,7 @@ void launch_emit(const DView* views, const PairRec* survivors, uint32_t n_surviv
     if (n_survivors)
         k_emit<<<(n_survivors + SLB_SETUP_CHUNK - 1) / SLB_SETUP_CHUNK, SLB_SETUP_CHUNK, 0, s>>>(views, survivors, n_survivors, tile_count, pairs,
                                                                                                capacity);
-    if (n_huge) k_emit_huge<<<n_huge, SLB_SETUP_CHUNK, 0, s>>>(views, huge, tile_count, pairs, capacity);
+    if (n_huge) k_emit_huge<<<n_huge, SLB_HUGE_THREADS, 0, s>>>(views, huge, tile_count, pairs, capacity);
 }
 void launch_scan(uint32_t* count, uint32_t* off, ActiveTile* active, unsigned long long* block_sums, uint32_t* totals,
                  const uint32_t* counters, uint32_t n, cudaStream_t s) {

@@ -86,7 +86,7 @@ struct DView {
 // and the shade kernel fetch the clipped, snapped polygon instead of re-clipping it per pixel.
 struct DPolyV { int32_t X, Y; float z, invw; float b[3]; };
 struct ClipRec { uint32_t seq; int32_t n; DPolyV v[10]; };
-#define SLB_MAX_CLIP 48            // per frame; primitives beyond this are re-clipped where they are used
+#define SLB_MAX_CLIP 31            // per frame (slot + 1 fits 5 bits of the key); primitives beyond this are re-clipped where they are used
 
 struct DFrame {
     int32_t W, H, tiles_x, tiles_y;
@@ -123,7 +123,8 @@ struct __align__(16) PairRec {
     int32_t ax, ay, bx, by, cx, cy;   // 24.8 fixed-point window coordinates
     float az, bz, cz;                 // window z in [0,1]
     uint32_t seq;                     // primitive sequence number within the frame
-    uint32_t k_flags;                 // bits 0..7: fan index k of the sub-triangle; bit 8: needs fragment test
+    uint32_t k_flags;                 // bits 0..2: fan index k of the sub-triangle (1..7); bits 3..7: ClipRec slot + 1 of a clipped
+                                      // primitive (0: unclipped / not published); bit 8: needs fragment test; bits 16..: view
     uint32_t draw;                    // index into DDraw[] (fragment-test path only)
 };
 static_assert(sizeof(PairRec) == 48, "PairRec must be 48 bytes");
@@ -131,5 +132,5 @@ static_assert(sizeof(PairRec) == 48, "PairRec must be 48 bytes");
 // a non-empty tile: what one raster warp needs to start (written by the scan's fix-up pass)
 struct ActiveTile { uint32_t tile, beg, count, pad; };
 
-// visibility key: depth24 << 40 | seq << 8 | k   (min == GL_LESS + first draw wins on ties)
+// visibility key: depth24 << 40 | seq << 8 | (clip slot + 1) << 3 | k   (min == GL_LESS + first draw wins on ties)
 #define SLB_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull

@@ -70,7 +70,7 @@ struct slb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     std::string err;
     bool time_kernels = false, keep_hdr = false;
-    int max_subbatch = 16;
+    int max_subbatch = 64;
     // largest pixel box (in pixels) the setup kernel rasterises directly with one thread / with one warp; larger
     // triangles take the tiled path (tunables: env SLB_DIRECT_MAX, SLB_WARP_MAX)
     int direct_max = 128, warp_max = 4096;
@@ -1156,8 +1156,9 @@ extern "C" int slb_render_batch_host(slb_ctx* ctx, const slb_scene_desc* scenes,
     const bool dbg = getenv("SLB_DEBUG_TIMING") != nullptr;
     auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_begin = now();
-    for (int at = 0; at < n_scenes; at += ctx->max_subbatch, ++k) {
-        const int n = std::min(ctx->max_subbatch, n_scenes - at);
+    for (int at = 0, n = 0; at < n_scenes; at += n, ++k) {
+        // the first sub-batch is short so that the device->host copies (the bottleneck of this entry point) start early
+        n = std::min(k == 0 ? std::min(ctx->max_subbatch, 16) : ctx->max_subbatch, n_scenes - at);
         const int sl = k & 1;
         if (used[sl]) CU(cudaStreamWaitEvent(ctx->stream, ctx->slot_copied[sl], 0));   // slot free again?
         const double t0 = now();
