@@ -226,6 +226,11 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
     sub = ctx.stats()
+    traffic = None                                        # DRAM bytes of one k_shade launch from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = (tj["dram_read_bytes_per_launch"] + tj["dram_write_bytes_per_launch"]) / tj["frames_per_launch"]
     n_sub = -(-n_local // (args.subbatch or 64))
     shade_ms_per_launch = stage_ms[5] / (args.steps * n_sub)
     frames_per_launch = n_local / n_sub
@@ -242,7 +247,9 @@ def main():
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "stage_ms_per_step": {n: float(v / args.steps) for n, v in zip(names, stage_ms)},
             "roofline": {"bound": "hbm", "kernel": "k_shade (shade + MRT store)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic * frames_per_launch if traffic else None,
+                         "traffic_source": "profiles/traffic.json (ncu --set full, dram read + write bytes per k_shade launch, scaled to this launch size)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": shade_ms_per_launch},
             "triangles_per_frame": int(sub.triangles_submitted / max(1, sub.frames_rendered))}
     if e2e:

@@ -279,7 +279,13 @@ int slb_ctx_get_stats(slb_ctx* ctx, slb_stats* out);
 enum {
     SLB_OPT_TIME_KERNELS = 1, /* record per-kernel CUDA-event times (adds syncs; off by default) */
     SLB_OPT_KEEP_HDR = 2,     /* keep the HDR colour buffer readable after render             */
-    SLB_OPT_MAX_SUBBATCH = 3  /* frames per internal sub-batch (default 64)                   */
+    SLB_OPT_MAX_SUBBATCH = 3, /* frames per internal sub-batch (default 64)                   */
+    /* Raster path selection (tuning / testing; results are bit-identical for every setting):
+     * triangles whose pixel box holds at most DIRECT_MAX pixels are rasterised by one thread of the
+     * setup kernel, up to WARP_MAX pixels by one warp of it; larger ones take the tiled path. 0/0 =
+     * everything through the tiled path. Defaults 128 / 4096. */
+    SLB_OPT_DIRECT_MAX = 4,
+    SLB_OPT_WARP_MAX = 5
 };
 int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value);
 

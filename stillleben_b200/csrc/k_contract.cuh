@@ -44,6 +44,14 @@ __device__ __forceinline__ int need_mask(const ClipV& v) {
     return need;
 }
 
+// All three vertices inside the true frustum (codes == 0) and finite: then no clip plane of C4 can be violated
+// (-w <= x <= w implies w >= 0 and 16 w +- x >= 0, ...), so need_mask() is known to be 0 without evaluating its
+// 18 plane distances. Non-finite coordinates compare false everywhere, so they are sent to the full test.
+__device__ __forceinline__ bool inside_frustum(int codes, const ClipV& a, const ClipV& b, const ClipV& c) {
+    const float sum = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) + ((c.x + c.y) + (c.z + c.w));
+    return codes == 0 && (sum - sum) == 0.0f;
+}
+
 static __device__ __noinline__ int clip_poly(const ClipV* in, int n, int plane, ClipV* out) {
     int m = 0;
     for (int i = 0; i < n; ++i) {
@@ -73,7 +81,7 @@ static __device__ __noinline__ int clip_poly(const ClipV* in, int n, int plane, 
 // C5: perspective divide, viewport transform, snap to 1/256 pixel (round-to-nearest-even)
 __device__ __forceinline__ bool project_vertex(const ClipV& v, float hw, float hh, PolyV& o) {
     if (!(v.w > 0.0f)) return false;
-    float invw = __fdiv_rn(1.0f, v.w);
+    float invw = __frcp_rn(v.w);   // correctly rounded 1/w (== __fdiv_rn(1, w))
     float xw = __fmaf_rn(__fmul_rn(v.x, invw), hw, hw);
     float yw = __fmaf_rn(__fmul_rn(v.y, invw), hh, hh);
     o.X = __float2int_rn(__fmul_rn(xw, 256.0f));
@@ -144,9 +152,9 @@ __device__ __forceinline__ int setup_subtri_fast(const float* __restrict__ mvp, 
     xform_clip(mvp, p0.x, p0.y, p0.z, c[0]);
     xform_clip(mvp, p1.x, p1.y, p1.z, c[1]);
     xform_clip(mvp, p2.x, p2.y, p2.z, c[2]);
-    if (frustum_code(c[0]) & frustum_code(c[1]) & frustum_code(c[2])) return 0;
-    int need = need_mask(c[0]) | need_mask(c[1]) | need_mask(c[2]);
-    if (need) return -1;
+    const int f0 = frustum_code(c[0]), f1 = frustum_code(c[1]), f2 = frustum_code(c[2]);
+    if (f0 & f1 & f2) return 0;
+    if (!inside_frustum(f0 | f1 | f2, c[0], c[1], c[2]) && (need_mask(c[0]) | need_mask(c[1]) | need_mask(c[2]))) return -1;
     if (k != 1) return 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { c[i].b[0] = c[i].b[1] = c[i].b[2] = 0.0f; c[i].b[i] = 1.0f; }
@@ -187,7 +195,7 @@ __device__ __forceinline__ bool make_subtri(int ax, int ay, int bx, int by, int 
     t.twoA = edge_fn(ax, ay, bx, by, cx, cy);
     if (t.twoA == 0) return false;
     t.s = t.twoA > 0 ? 1 : -1;
-    t.inv2A = __fdiv_rn(1.0f, __ll2float_rn(t.twoA));
+    t.inv2A = __frcp_rn(__ll2float_rn(t.twoA));
     t.bias0 = top_left(cx - bx, cy - by, t.s) ? 0 : -1;   // w0 <-> edge b->c
     t.bias1 = top_left(ax - cx, ay - cy, t.s) ? 0 : -1;   // w1 <-> edge c->a
     t.bias2 = top_left(bx - ax, by - ay, t.s) ? 0 : -1;   // w2 <-> edge a->b

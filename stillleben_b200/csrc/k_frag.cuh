@@ -53,14 +53,17 @@ __device__ __forceinline__ int wrap_index(int i, int n, int mode, bool& border) 
         default: return min(max(i, 0), n - 1);
     }
 }
+__device__ __forceinline__ float4 tex_load(const DTexture& t, int level, int lw, int xi, int yi) {
+    uchar4 p = __ldg(reinterpret_cast<const uchar4*>(t.px) + t.level_off[level] + (size_t)yi * lw + xi);
+    const float k = 1.0f / 255.0f;
+    return make_float4(p.x * k, p.y * k, p.z * k, p.w * k);
+}
 __device__ __forceinline__ float4 tex_fetch(const DTexture& t, int level, int lw, int lh, int x, int y) {
     bool border = false;
     int xi = wrap_index(x, lw, t.wrap_s, border);
     int yi = wrap_index(y, lh, t.wrap_t, border);
     if (border) return make_float4(0.f, 0.f, 0.f, 0.f);
-    uchar4 p = __ldg(reinterpret_cast<const uchar4*>(t.px) + t.level_off[level] + (size_t)yi * lw + xi);
-    const float k = 1.0f / 255.0f;
-    return make_float4(p.x * k, p.y * k, p.z * k, p.w * k);
+    return tex_load(t, level, lw, xi, yi);
 }
 __device__ __forceinline__ float4 tex_sample_level(const DTexture& t, int level, float u, float v, bool normalised, bool linear) {
     int lw = max(1, t.w >> level), lh = max(1, t.h >> level);
@@ -70,8 +73,16 @@ __device__ __forceinline__ float4 tex_sample_level(const DTexture& t, int level,
     float fx = floorf(x), fy = floorf(y);
     float a = x - fx, b = y - fy;
     int i0 = (int)fx, j0 = (int)fy;
-    float4 t00 = tex_fetch(t, level, lw, lh, i0, j0), t10 = tex_fetch(t, level, lw, lh, i0 + 1, j0);
-    float4 t01 = tex_fetch(t, level, lw, lh, i0, j0 + 1), t11 = tex_fetch(t, level, lw, lh, i0 + 1, j0 + 1);
+    float4 t00, t10, t01, t11;
+    if (t.wrap_s == SLB_WRAP_REPEAT && t.wrap_t == SLB_WRAP_REPEAT && !(lw & (lw - 1)) && !(lh & (lh - 1))) {
+        // the common case (glTF default wrap, power-of-two levels): four masks instead of eight mode switches
+        const int x0 = i0 & (lw - 1), x1 = (i0 + 1) & (lw - 1), y0 = j0 & (lh - 1), y1 = (j0 + 1) & (lh - 1);
+        t00 = tex_load(t, level, lw, x0, y0); t10 = tex_load(t, level, lw, x1, y0);
+        t01 = tex_load(t, level, lw, x0, y1); t11 = tex_load(t, level, lw, x1, y1);
+    } else {
+        t00 = tex_fetch(t, level, lw, lh, i0, j0); t10 = tex_fetch(t, level, lw, lh, i0 + 1, j0);
+        t01 = tex_fetch(t, level, lw, lh, i0, j0 + 1); t11 = tex_fetch(t, level, lw, lh, i0 + 1, j0 + 1);
+    }
     return t00 * ((1 - a) * (1 - b)) + t10 * (a * (1 - b)) + t01 * ((1 - a) * b) + t11 * (a * b);
 }
 // texture2D() with implicit derivatives (du/dx etc. in normalised units per pixel)

@@ -237,7 +237,7 @@ __device__ __forceinline__ void raster_direct(int ax, int ay, int bx, int by, in
     const int rbx = bx - ax, rby = by - ay, rcx = cx - ax, rcy = cy - ay;
     const int twoA = rbx * rcy - rby * rcx;
     const int sg = twoA > 0 ? 1 : -1;
-    const float inv2A = __fdiv_rn(1.0f, __int2float_rn(twoA));
+    const float inv2A = __frcp_rn(__int2float_rn(twoA));
     const int bias0 = top_left(cx - bx, cy - by, sg) ? 0 : -1;
     const int bias1 = top_left(ax - cx, ay - cy, sg) ? 0 : -1;
     const int bias2 = top_left(bx - ax, by - ay, sg) ? 0 : -1;
@@ -310,10 +310,11 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_setup(const DView* __res
         xform_clip(s_mvp, p0.x, p0.y, p0.z, c0);
         xform_clip(s_mvp, p1.x, p1.y, p1.z, c1);
         xform_clip(s_mvp, p2.x, p2.y, p2.z, c2);
-        if (!(frustum_code(c0) & frustum_code(c1) & frustum_code(c2))) {
+        const int fc0 = frustum_code(c0), fc1 = frustum_code(c1), fc2 = frustum_code(c2);
+        if (!(fc0 & fc1 & fc2)) {
             const uint32_t seq = d.prim_base + tri;
             const uint32_t flags = ((d.flags & DRAW_FRAG_TEST) ? 0x100u : 0u) | (d.view << 16);
-            if (need_mask(c0) | need_mask(c1) | need_mask(c2)) {
+            if (!inside_frustum(fc0 | fc1 | fc2, c0, c1, c2) && (need_mask(c0) | need_mask(c1) | need_mask(c2))) {
                 setup_clipped_prim(s_mvp, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z), make_float3(p2.x, p2.y, p2.z), seq, flags,
                                    d.draw, v, v.shadow ? nullptr : &frames[v.frame], tile_count, so, s_big, &s_nbig);
             } else {
@@ -327,6 +328,7 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_setup(const DView* __res
                         if (!(flags & 0x100u) && ext_x < 16384 && ext_y < 16384 && (px1 - px0 + 1) * (py1 - py0 + 1) <= warp_max) {
                             // small / mid-size triangle: queued for the direct path below (never becomes a survivor). Small
                             // ones fill the queue from the front (one thread each), mid-size ones from the back (one warp each).
+                            // (Counting-sorting the small ones by box size to even out the warps was measured: no gain.)
                             const bool small = (px1 - px0 + 1) * (py1 - py0 + 1) <= direct_max;
                             const int q = small ? atomicAdd(&s_ndirect, 1) : SLB_SETUP_CHUNK - 1 - atomicAdd(&s_nmid, 1);
                             s_dq[0][q] = a.X; s_dq[1][q] = a.Y; s_dq[2][q] = b.X; s_dq[3][q] = b.Y; s_dq[4][q] = c.X; s_dq[5][q] = c.Y;
@@ -692,7 +694,7 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DView* _
                 if (px0 <= px1 && py0 <= py1) {
                     const long long twoA = edge_fn(r.ax, r.ay, r.bx, r.by, r.cx, r.cy);
                     const int sg = twoA > 0 ? 1 : -1;
-                    inv2A = __fdiv_rn(1.0f, __ll2float_rn(twoA));
+                    inv2A = __frcp_rn(__ll2float_rn(twoA));
                     const int bias0 = top_left(r.cx - r.bx, r.cy - r.by, sg) ? 0 : -1;
                     const int bias1 = top_left(r.ax - r.cx, r.ay - r.cy, sg) ? 0 : -1;
                     const int bias2 = top_left(r.bx - r.ax, r.by - r.ay, sg) ? 0 : -1;
@@ -913,12 +915,16 @@ void launch_raster(bool frag_test, const DView* views, const DFrame* frames, con
 }
 void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, cudaStream_t s) {
     // 256 threads = 32 x 8 pixels; (256, 2) = 128 registers measured fastest (tighter bounds spill, see profiles/)
-    static const int variant = getenv("SLB_SHADE_VARIANT") ? atoi(getenv("SLB_SHADE_VARIANT")) : 3;
+    static const int variant = getenv("SLB_SHADE_VARIANT") ? atoi(getenv("SLB_SHADE_VARIANT")) : 5;
     switch (variant) {
         case 1: k_shade<128, 4><<<dim3((W + 31) / 32, (H + 3) / 4, n_frames), 128, 0, s>>>(frames, draws); break;
         case 2: k_shade<128, 5><<<dim3((W + 31) / 32, (H + 3) / 4, n_frames), 128, 0, s>>>(frames, draws); break;
         case 3: k_shade<256, 3><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws); break;
         case 4: k_shade<64, 10><<<dim3((W + 31) / 32, (H + 1) / 2, n_frames), 64, 0, s>>>(frames, draws); break;
+        case 5: k_shade<256, 4><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws); break;
+        case 6: k_shade<128, 7><<<dim3((W + 31) / 32, (H + 3) / 4, n_frames), 128, 0, s>>>(frames, draws); break;
+        case 7: k_shade<128, 6><<<dim3((W + 31) / 32, (H + 3) / 4, n_frames), 128, 0, s>>>(frames, draws); break;
+        case 8: k_shade<128, 8><<<dim3((W + 31) / 32, (H + 3) / 4, n_frames), 128, 0, s>>>(frames, draws); break;
         default: k_shade<256, 2><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
     }
 }

@@ -230,6 +230,11 @@ extern "C" int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value) {
             ctx->max_subbatch = (int)value;
             for (int i = 0; i < 2; ++i) if (ctx->slot[i]) { slb_result_destroy(ctx, ctx->slot[i]); ctx->slot[i] = nullptr; }
             return SLB_OK;
+        case SLB_OPT_DIRECT_MAX:
+        case SLB_OPT_WARP_MAX:
+            if (value < 0 || value > 4096) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "SLB_OPT_DIRECT_MAX / SLB_OPT_WARP_MAX must be in [0, 4096]");
+            (option == SLB_OPT_DIRECT_MAX ? ctx->direct_max : ctx->warp_max) = (int)value;
+            return SLB_OK;
         default: return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "unknown option");
     }
 }

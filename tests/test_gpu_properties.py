@@ -85,3 +85,21 @@ def test_sampled_frames_match_oracle(batch):
     for i in (0, 7, 19):
         ref = ou.render(scenes[i], assets, want_hdr=False)
         parity.assert_parity(res.frame_dict(i), ref, rgb_outlier_frac=1e-3)
+
+
+def test_raster_paths_agree_bit_exactly(gpu_ctx, batch):
+    """The visibility result is the per-pixel minimum key whichever way a triangle is rasterised: all tiled
+    (0/0), all small ones by one thread (4096/4096), all by one warp (0/4096), the default mix — every
+    target of every frame must come out byte-identical (SLB_OPT_DIRECT_MAX / SLB_OPT_WARP_MAX)."""
+    pool, scenes, res = batch
+    ref = [digest(res, i) for i in range(6)]
+    try:
+        for direct_max, warp_max in ((0, 0), (4096, 4096), (0, 4096), (16, 256)):
+            gpu_ctx.set_option(abi.OPT_DIRECT_MAX, direct_max)
+            gpu_ctx.set_option(abi.OPT_WARP_MAX, warp_max)
+            again = gpu_ctx.render(scenes[:6], target_mask=abi.TARGETS_ALL)
+            gpu_ctx.synchronize()
+            assert [digest(again, i) for i in range(6)] == ref, (direct_max, warp_max)
+    finally:
+        gpu_ctx.set_option(abi.OPT_DIRECT_MAX, 128)
+        gpu_ctx.set_option(abi.OPT_WARP_MAX, 4096)
