@@ -303,6 +303,20 @@ int slb_diff_dilate_object_mask(slb_ctx* ctx, const uint8_t* mask, const uint8_t
                                 int32_t coord_stride, uint8_t* mask_out, float* coords_out, int32_t height,
                                 int32_t width, void* stream);
 
+/* Fused render-and-compare backward: gradient of an objective w.r.t. the locally linearised object poses
+ * T(alpha,beta,gamma,a,b,c) = T0 [[1,-gamma,beta,a],[gamma,1,-alpha,b],[-beta,alpha,1,c],[0,0,0,1]]
+ * from dObjective/dImage. Replaces the per-object Python loop of the reference
+ * (python/stillleben/diff.py:73-127 compute_image_space_gradients, :355-523
+ * backpropagate_gradient_to_poses; masks as python/src/diff.cu) with one pass over the pixels.
+ * rgb: uint8 HxWx4, instance_index: int16 HxW, coord_depth: float32 HxWx4 (object xyz, w = depth),
+ * grad_image: float32 3xHxW, grad_out: float32 n_objects x 6 — all DEVICE pointers.
+ * projection (16 floats) and poses (n_objects x 16), column-major as in slb_scene_desc, and
+ * instance_ids (n_objects) are HOST arrays. */
+int slb_diff_pose_grad(slb_ctx* ctx, const uint8_t* rgb, const int16_t* instance_index, const float* coord_depth,
+                       const float* grad_image, const float* projection, const float* poses,
+                       const int32_t* instance_ids, int32_t n_objects, float* grad_out, int32_t height,
+                       int32_t width, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

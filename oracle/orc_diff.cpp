@@ -56,3 +56,82 @@ void orc_diff_dilate_object_mask(const uint8_t* mask, const uint8_t* valid, cons
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Render-and-compare backward (reference: python/stillleben/diff.py:73-127 compute_image_space_gradients,
+// :355-523 backpropagate_gradient_to_poses). Literal float32 restatement of the tensor program, object by
+// object, pixel by pixel, with the products taken in the order of its bmm chain:
+//   grad_x[c] = -(rgb[c][x+1] - rgb[c][x-1]) / (2/W*2), grad_y likewise with H (zero padded), zeroed where
+//     the sobel-valid mask is false                                                           (:101-124)
+//   mask, coords = dilate_object_mask(instance == idx, valid, coordinates)                   (:401-411)
+//   y = T0 (coords, 1);  den = P[2,:] . y  (the reference really uses row 2)     (:431-443)
+//   g_coord[j][i] = P[j,i] / den - P[2,i] / den^2 * (P[j,:] . y)
+//   g_pose[i][k] = (T0 G_k x)[i] for the six generators alpha, beta, gamma, a, b, c           (:446-483)
+//   out[obj][k] = sum_pixels sum_c grad_in[c] * ((g_xy[c][:] g_coord) g_pose)[k]               (:485-521)
+// Matrices are row-major here (P[r*4+c], T0[r*4+c]) as torch holds them.
+extern "C" void orc_diff_pose_grad(const uint8_t* rgb /* HxWx4 */, const int16_t* inst, const float* coord /* HxWx4, w = depth */,
+                                   const float* grad_img /* 3xHxW */, const float* P, const float* poses /* n_obj x 16 */,
+                                   const int32_t* instance_ids, int n_obj, float* out /* n_obj x 6 */, int H, int W) {
+    const size_t N = (size_t)H * W;
+    uint8_t* valid = new uint8_t[N];
+    float* depth = new float[N];
+    for (size_t p = 0; p < N; ++p) depth[p] = coord[p * 4 + 3];
+    orc_diff_sobel_valid_mask(inst, depth, valid, H, W);
+    float* gx = new float[3 * N];
+    float* gy = new float[3 * N];
+    const float sx = 2.0f / (float)W * 2.0f, sy = 2.0f / (float)H * 2.0f;   // "sobel /= 2 / _w * 2"
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < H; ++r)
+            for (int x = 0; x < W; ++x) {
+                const size_t p = (size_t)r * W + x;
+                auto px = [&](int rr, int xx) -> float {
+                    if (rr < 0 || rr >= H || xx < 0 || xx >= W) return 0.0f;
+                    return (float)rgb[((size_t)rr * W + xx) * 4 + c] / 255.0f;
+                };
+                float dx = -1.0f / sx * px(r, x - 1) + 1.0f / sx * px(r, x + 1);
+                float dy = -1.0f / sy * px(r - 1, x) + 1.0f / sy * px(r + 1, x);
+                gx[c * N + p] = valid[p] ? -dx : 0.0f;
+                gy[c * N + p] = valid[p] ? -dy : 0.0f;
+            }
+    uint8_t* mask = new uint8_t[N];
+    uint8_t* mask_d = new uint8_t[N];
+    float* oc = new float[3 * N];
+    for (int o = 0; o < n_obj; ++o) {
+        const float* T = poses + 16 * o;
+        for (size_t p = 0; p < N; ++p) mask[p] = (int32_t)inst[p] == instance_ids[o];
+        orc_diff_dilate_object_mask(mask, valid, coord, 4, mask_d, oc, H, W);
+        double acc[6] = {0, 0, 0, 0, 0, 0};   // torch sums N x 6 floats pairwise; double keeps the oracle order-free
+        for (size_t p = 0; p < N; ++p) {
+            if (!mask_d[p]) continue;
+            const float x[4] = {oc[p * 3], oc[p * 3 + 1], oc[p * 3 + 2], 1.0f};
+            float y[4];
+            for (int r = 0; r < 4; ++r) y[r] = T[r * 4] * x[0] + T[r * 4 + 1] * x[1] + T[r * 4 + 2] * x[2] + T[r * 4 + 3] * x[3];
+            float Py[3];
+            for (int r = 0; r < 3; ++r) Py[r] = P[r * 4] * y[0] + P[r * 4 + 1] * y[1] + P[r * 4 + 2] * y[2] + P[r * 4 + 3] * y[3];
+            float gcoord[2][3];
+            for (int j = 0; j < 2; ++j)
+                for (int i = 0; i < 3; ++i)
+                    gcoord[j][i] = P[j * 4 + i] * (1.0f / Py[2]) + (P[2 * 4 + i] * (-1.0f / (Py[2] * Py[2]))) * Py[j];
+            // generators applied to x, then T0; homogeneous row dropped
+            const float gen[6][4] = {{0.0f, -x[2], x[1], 0.0f}, {x[2], 0.0f, -x[0], 0.0f}, {-x[1], x[0], 0.0f, 0.0f},
+                                     {x[3], 0.0f, 0.0f, 0.0f},  {0.0f, x[3], 0.0f, 0.0f},  {0.0f, 0.0f, x[3], 0.0f}};
+            float gpose[3][6];
+            for (int k = 0; k < 6; ++k)
+                for (int i = 0; i < 3; ++i)
+                    gpose[i][k] = T[i * 4] * gen[k][0] + T[i * 4 + 1] * gen[k][1] + T[i * 4 + 2] * gen[k][2] + T[i * 4 + 3] * gen[k][3];
+            float A[3][3];   // g_xy [3x2] @ g_coord [2x3]
+            for (int c = 0; c < 3; ++c)
+                for (int i = 0; i < 3; ++i) A[c][i] = gx[c * N + p] * gcoord[0][i] + gy[c * N + p] * gcoord[1][i];
+            for (int k = 0; k < 6; ++k) {
+                float g = 0.0f;
+                for (int c = 0; c < 3; ++c) {
+                    float Bck = A[c][0] * gpose[0][k] + A[c][1] * gpose[1][k] + A[c][2] * gpose[2][k];
+                    g += grad_img[c * N + p] * Bck;
+                }
+                acc[k] += (double)g;
+            }
+        }
+        for (int k = 0; k < 6; ++k) out[o * 6 + k] = (float)acc[k];
+    }
+    delete[] valid; delete[] depth; delete[] gx; delete[] gy; delete[] mask; delete[] mask_d; delete[] oc;
+}

@@ -144,6 +144,8 @@ PROTOTYPES = {
                                              C.c_void_p]),
     "slb_diff_dilate_object_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                                C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "slb_diff_pose_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 

@@ -42,4 +42,8 @@ void launch_sobel_valid_mask(const int16_t* inst, const float* depth, uint8_t* v
 void launch_dilate_object_mask(const uint8_t* mask, const uint8_t* valid, const float* coords, int coord_stride, uint8_t* mask_out,
                                float* coords_out, int H, int W, cudaStream_t s);
 
+size_t pose_grad_partial_floats(int n_obj, int H, int W);
+void launch_pose_grad(const uint8_t* rgb, const int16_t* inst, const float* coord, const float* grad_img, const float* params, int n_obj,
+                      float* partial, float* out, int H, int W, cudaStream_t s);
+
 }  // namespace slbk

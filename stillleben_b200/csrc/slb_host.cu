@@ -79,7 +79,7 @@ struct slb_ctx {
     slb_mesh* plane = nullptr;
     // per-batch device arrays
     DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, survivors;
-    DevBuf clip_recs, clip_counts;
+    DevBuf clip_recs, clip_counts, diff_params, diff_partial;
     DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, ao, avg, mip_a, mip_b, shadow_maps;
     // pinned staging
     void* staging = nullptr; size_t staging_cap = 0;
@@ -207,7 +207,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
         if (ctx->slot_rendered[i]) cudaEventDestroy(ctx->slot_rendered[i]);
         if (ctx->slot_copied[i]) cudaEventDestroy(ctx->slot_copied[i]);
     }
-    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->survivors, &ctx->tile_count,
+    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->survivors, &ctx->diff_params, &ctx->diff_partial, &ctx->tile_count,
                       &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->ao,
                       &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts};
     for (DevBuf* b : bufs) b->release();
@@ -1212,6 +1212,39 @@ extern "C" int slb_diff_dilate_object_mask(slb_ctx* ctx, const uint8_t* mask, co
     CU(cudaSetDevice(ctx->device));
     launch_dilate_object_mask(mask, valid, coords, coord_stride, mask_out, coords_out, height, width, stream ? (cudaStream_t)stream : ctx->stream);
     ctx->stats.kernel_launches += 1;
+    CU(cudaGetLastError());
+    return SLB_OK;
+}
+
+extern "C" int slb_diff_pose_grad(slb_ctx* ctx, const uint8_t* rgb, const int16_t* instance_index, const float* coord_depth,
+                                  const float* grad_image, const float* projection, const float* poses, const int32_t* instance_ids,
+                                  int32_t n_objects, float* grad_out, int32_t height, int32_t width, void* stream) {
+    if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
+    if (!rgb || !instance_index || !coord_depth || !grad_image || !projection || !grad_out || n_objects < 0 || height <= 0 || width <= 0 ||
+        (n_objects > 0 && (!poses || !instance_ids)))
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_diff_pose_grad: bad arguments");
+    if (n_objects == 0) return SLB_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    // parameter block: P (row-major), then per object T0 (row-major) + instance id
+    const size_t n_par = 16 + (size_t)17 * n_objects;
+    std::vector<float> par(n_par);
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) par[r * 4 + c] = projection[c * 4 + r];
+    for (int o = 0; o < n_objects; ++o) {
+        float* T = par.data() + 16 + (size_t)17 * o;
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) T[r * 4 + c] = poses[(size_t)o * 16 + c * 4 + r];
+        const int32_t id = (int32_t)(int16_t)instance_ids[o];   // the instance target is read as int16 (py_render_pass.cpp:103-127)
+        std::memcpy(T + 16, &id, 4);
+    }
+    CU(ctx->diff_params.reserve(n_par * sizeof(float)));
+    CU(ctx->diff_partial.reserve(pose_grad_partial_floats(n_objects, height, width) * sizeof(float)));
+    // pageable source: the copy is staged by the runtime before the call returns, so `par` may go out of scope
+    CU(cudaMemcpyAsync(ctx->diff_params.p, par.data(), n_par * sizeof(float), cudaMemcpyHostToDevice, s));
+    launch_pose_grad(rgb, instance_index, coord_depth, grad_image, ctx->diff_params.as<float>(), n_objects, ctx->diff_partial.as<float>(),
+                     grad_out, height, width, s);
+    ctx->stats.kernel_launches += 2;
     CU(cudaGetLastError());
     return SLB_OK;
 }

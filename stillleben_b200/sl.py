@@ -593,3 +593,6 @@ class RenderPass:
 def view(scene):
     """The reference opens an X11 viewer; headless this returns immediately (SURVEY §3.2 caveat ii)."""
     return None
+
+
+from . import diff  # noqa: E402,F401  (sl.diff.backpropagate_gradient_to_poses etc., as the reference's stillleben.diff)
