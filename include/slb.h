@@ -317,6 +317,37 @@ int slb_diff_pose_grad(slb_ctx* ctx, const uint8_t* rgb, const int16_t* instance
                        const int32_t* instance_ids, int32_t n_objects, float* grad_out, int32_t height,
                        int32_t width, void* stream);
 
+/* ---- camera noise model (reference: python/stillleben/camera_model.py) ---------------------- */
+
+enum {                          /* stages of process_deterministic, in order (camera_model.py:224-262) */
+    SLB_CAM_CHROMATIC = 1,      /* chromatic_aberration :46-73  */
+    SLB_CAM_BLUR = 2,           /* blur(blur_sigma) if blur_sigma > 0 :106-119 */
+    SLB_CAM_EXPOSURE = 4,       /* exposure :121-131 */
+    SLB_CAM_NOISE = 8,          /* noise(a, b) if do_noise :133-161 */
+    SLB_CAM_CLAMP = 16,         /* clamp to [0,1] :249 */
+    SLB_CAM_HUE = 32,           /* color_jitter :163-222 */
+    SLB_CAM_POST_BLUR = 64,     /* blur(0.4) + clamp :253-260 */
+    SLB_CAM_ALL = 127
+};
+typedef struct slb_camera_params {
+    float chromatic_translation[3][2]; /* (tx, ty) per channel, normalised [-1,1] image units */
+    float chromatic_scaling[3];
+    float blur_sigma;
+    float exposure_deltaS;
+    int32_t do_noise;
+    float noise_a, noise_b;            /* var = a * y (Poissonian part), std b (Gaussian part) */
+    float hue_shift;                   /* -0.5 .. 0.5 */
+    uint32_t stages;                   /* SLB_CAM_* mask; SLB_CAM_ALL = process_deterministic */
+    uint64_t seed;                     /* counter-RNG seed of the noise stage */
+} slb_camera_params;
+
+/* Applies the camera model to n images of H x W pixels in one launch pair. in_format 0: planar float32
+ * [n][3][H][W] in [0,1] (what the reference takes); 1: RGBA8 [n][H][W][4] (the render target, /255 folded in).
+ * out: planar float32 [n][3][H][W]. in / out are DEVICE pointers (out may not alias in); params is a HOST
+ * array of n records. */
+int slb_camera_model(slb_ctx* ctx, const void* in, int32_t in_format, float* out, int32_t n_images, int32_t height,
+                     int32_t width, const slb_camera_params* params, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,9 +144,20 @@ PROTOTYPES = {
                                              C.c_void_p]),
     "slb_diff_dilate_object_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                                C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "slb_camera_model": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_void_p]),
     "slb_diff_pose_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }
+
+
+CAM_CHROMATIC, CAM_BLUR, CAM_EXPOSURE, CAM_NOISE, CAM_CLAMP, CAM_HUE, CAM_POST_BLUR, CAM_ALL = 1, 2, 4, 8, 16, 32, 64, 127
+
+
+class CameraParams(C.Structure):
+    _fields_ = [("chromatic_translation", (C.c_float * 2) * 3), ("chromatic_scaling", C.c_float * 3), ("blur_sigma", C.c_float),
+                ("exposure_deltaS", C.c_float), ("do_noise", C.c_int32), ("noise_a", C.c_float), ("noise_b", C.c_float),
+                ("hue_shift", C.c_float), ("stages", C.c_uint32), ("seed", C.c_uint64)]
 
 
 def bind(lib):

@@ -46,4 +46,9 @@ size_t pose_grad_partial_floats(int n_obj, int H, int W);
 void launch_pose_grad(const uint8_t* rgb, const int16_t* inst, const float* coord, const float* grad_img, const float* params, int n_obj,
                       float* partial, float* out, int H, int W, cudaStream_t s);
 
+// k_camera.cu
+void launch_camera_stage1(const float* in_f, const uint8_t* in_u8, float* out, const slb_camera_params* params, int n, int H, int W,
+                          cudaStream_t s);
+void launch_camera_stage2(const float* in, float* out, float sigma, int n, int H, int W, cudaStream_t s);
+
 }  // namespace slbk

@@ -79,7 +79,7 @@ struct slb_ctx {
     slb_mesh* plane = nullptr;
     // per-batch device arrays
     DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, survivors;
-    DevBuf clip_recs, clip_counts, diff_params, diff_partial;
+    DevBuf clip_recs, clip_counts, diff_params, diff_partial, cam_params, cam_mid;
     DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, ao, avg, mip_a, mip_b, shadow_maps;
     // pinned staging
     void* staging = nullptr; size_t staging_cap = 0;
@@ -207,7 +207,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
         if (ctx->slot_rendered[i]) cudaEventDestroy(ctx->slot_rendered[i]);
         if (ctx->slot_copied[i]) cudaEventDestroy(ctx->slot_copied[i]);
     }
-    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->survivors, &ctx->diff_params, &ctx->diff_partial, &ctx->tile_count,
+    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->survivors, &ctx->diff_params, &ctx->diff_partial, &ctx->cam_params, &ctx->cam_mid, &ctx->tile_count,
                       &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->ao,
                       &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts};
     for (DevBuf* b : bufs) b->release();
@@ -1245,6 +1245,34 @@ extern "C" int slb_diff_pose_grad(slb_ctx* ctx, const uint8_t* rgb, const int16_
     launch_pose_grad(rgb, instance_index, coord_depth, grad_image, ctx->diff_params.as<float>(), n_objects, ctx->diff_partial.as<float>(),
                      grad_out, height, width, s);
     ctx->stats.kernel_launches += 2;
+    CU(cudaGetLastError());
+    return SLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// camera noise model
+// ---------------------------------------------------------------------------------------------
+extern "C" int slb_camera_model(slb_ctx* ctx, const void* in, int32_t in_format, float* out, int32_t n_images, int32_t height,
+                                int32_t width, const slb_camera_params* params, void* stream) {
+    if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
+    if (!in || !out || !params || n_images <= 0 || height <= 0 || width <= 0 || (in_format != 0 && in_format != 1) || (const void*)out == in)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_camera_model: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const size_t img_floats = (size_t)3 * height * width;
+    bool any_post = false;
+    for (int i = 0; i < n_images; ++i) any_post |= (params[i].stages & SLB_CAM_POST_BLUR) != 0;
+    for (int i = 0; i < n_images; ++i)
+        if (((params[i].stages & SLB_CAM_POST_BLUR) != 0) != any_post)
+            return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_camera_model: SLB_CAM_POST_BLUR must be set for all images of a call or for none");
+    CU(ctx->cam_params.reserve((size_t)n_images * sizeof(slb_camera_params)));
+    CU(cudaMemcpyAsync(ctx->cam_params.p, params, (size_t)n_images * sizeof(slb_camera_params), cudaMemcpyHostToDevice, s));
+    float* mid = out;
+    if (any_post) { CU(ctx->cam_mid.reserve((size_t)n_images * img_floats * sizeof(float))); mid = ctx->cam_mid.as<float>(); }
+    launch_camera_stage1(in_format == 0 ? (const float*)in : nullptr, in_format == 1 ? (const uint8_t*)in : nullptr, mid,
+                         ctx->cam_params.as<slb_camera_params>(), n_images, height, width, s);
+    if (any_post) launch_camera_stage2(mid, out, 0.4f, n_images, height, width, s);
+    ctx->stats.kernel_launches += any_post ? 2 : 1;
     CU(cudaGetLastError());
     return SLB_OK;
 }

@@ -44,6 +44,7 @@ int main(void) {
          sizeof(slb_object_desc), sizeof(slb_scene_desc), sizeof(slb_stats));
   printf("%zu %zu %zu\n", __builtin_offsetof(slb_scene_desc, objects), __builtin_offsetof(slb_object_desc, sticker_range),
          __builtin_offsetof(slb_scene_desc, manual_exposure));
+  printf("%zu %zu %zu\n", sizeof(slb_camera_params), __builtin_offsetof(slb_camera_params, stages), __builtin_offsetof(slb_camera_params, seed));
   return 0; }'''
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "t.c")
@@ -54,7 +55,8 @@ int main(void) {
     sizes = [int(x) for x in out]
     mirror = [C.sizeof(abi.Image), C.sizeof(abi.Submesh), C.sizeof(abi.Material), C.sizeof(abi.LightmapDesc),
               C.sizeof(abi.ObjectDesc), C.sizeof(abi.SceneDesc), C.sizeof(abi.Stats),
-              abi.SceneDesc.objects.offset, abi.ObjectDesc.sticker_range.offset, abi.SceneDesc.manual_exposure.offset]
+              abi.SceneDesc.objects.offset, abi.ObjectDesc.sticker_range.offset, abi.SceneDesc.manual_exposure.offset,
+              C.sizeof(abi.CameraParams), abi.CameraParams.stages.offset, abi.CameraParams.seed.offset]
     assert sizes == mirror
 
 
