@@ -87,7 +87,9 @@ __device__ __forceinline__ float smoothstep01(float x) { float t = clampf(x, 0.0
 __global__ void __launch_bounds__(256) k_ssao(const DFrame* __restrict__ frames) {
     const DFrame& f = frames[blockIdx.z];
     const int W = f.W, H = f.H;
-    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    // a warp covers an 8x4 pixel block: the 64 taps of neighbouring pixels land in neighbouring texels
+    const int wq = threadIdx.x >> 5, lq = threadIdx.x & 31;
+    const int px = blockIdx.x * 32 + (wq & 3) * 8 + (lq & 7), py = blockIdx.y * 8 + (wq >> 2) * 4 + (lq >> 3);
     if (px >= W || py >= H) return;
     const size_t p = (size_t)py * W + px;
     if (!f.ssao) { f.ao[p] = 1.0f; return; }
@@ -99,16 +101,31 @@ __global__ void __launch_bounds__(256) k_ssao(const DFrame* __restrict__ frames)
     f3 randomVec = normalize3(mk3(nz[0], nz[1], nz[2]));
     f3 tangent = normalize3(randomVec - normal * dot3(randomVec, normal));
     f3 bitangent = cross3(normal, tangent);
+    // offset = P (fragPos + 0.1 TBN s) is linear in the kernel sample s: project the frame once, not every sample
+    // (rows x, y, w of P; ssao_shader.frag:38-44)
+    const float* P = f.P;
+    float base[3], ct[3], cb[3], cn[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int row = r == 2 ? 3 : r;
+        base[r] = P[row] * fragPos.x + P[4 + row] * fragPos.y + P[8 + row] * fragPos.z + P[12 + row];
+        ct[r] = 0.1f * (P[row] * tangent.x + P[4 + row] * tangent.y + P[8 + row] * tangent.z);
+        cb[r] = 0.1f * (P[row] * bitangent.x + P[4 + row] * bitangent.y + P[8 + row] * bitangent.z);
+        cn[r] = 0.1f * (P[row] * normal.x + P[4 + row] * normal.y + P[8 + row] * normal.z);
+    }
+    const float zt = 0.1f * tangent.z, zb = 0.1f * bitangent.z, zn = 0.1f * normal.z;
+    const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
     float occlusion = 0.0f;
+#pragma unroll 4
     for (int i = 0; i < 64; ++i) {
-        f3 s = mk3(c_ssao_kernel[i * 3], c_ssao_kernel[i * 3 + 1], c_ssao_kernel[i * 3 + 2]);
-        f3 samplePos = tangent * s.x + bitangent * s.y + normal * s.z;
-        samplePos = fragPos + samplePos * 0.1f;
-        float4 off = mul_m4_p(f.P, samplePos.x, samplePos.y, samplePos.z, 1.0f);
-        float ox = off.x / off.w * 0.5f + 0.5f, oy = off.y / off.w * 0.5f + 0.5f;
-        float sampleDepth = rect_linear_z(f.scratch_cam, W, H, ox * W, oy * H);
+        const float sx = c_ssao_kernel[i * 3], sy = c_ssao_kernel[i * 3 + 1], sz = c_ssao_kernel[i * 3 + 2];
+        const float ox = base[0] + ct[0] * sx + cb[0] * sy + cn[0] * sz, oy = base[1] + ct[1] * sx + cb[1] * sy + cn[1] * sz;
+        const float ow = base[2] + ct[2] * sx + cb[2] * sy + cn[2] * sz;
+        const float sample_z = fragPos.z + zt * sx + zb * sy + zn * sz;
+        const float inv = 1.0f / ow;
+        float sampleDepth = rect_linear_z(f.scratch_cam, W, H, ox * inv * hw + hw, oy * inv * hh + hh);
         float rangeCheck = smoothstep01(0.1f / fabsf(fragPos.z - sampleDepth));
-        occlusion += (sampleDepth <= samplePos.z - 0.0025f ? 1.0f : 0.0f) * rangeCheck;
+        occlusion += (sampleDepth <= sample_z - 0.0025f ? 1.0f : 0.0f) * rangeCheck;
     }
     f.ao[p] = 1.0f - (occlusion / 64.0f);
 }
