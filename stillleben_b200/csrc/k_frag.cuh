@@ -257,8 +257,12 @@ __device__ __forceinline__ int fetch_subtri(const DFrame& f, const DDraw& d, uin
     const float3 q0 = make_float3(pm[0].x, pm[0].y, pm[0].z), q1 = make_float3(pm[1].x, pm[1].y, pm[1].z), q2 = make_float3(pm[2].x, pm[2].y, pm[2].z);
     int r = setup_subtri_fast(d.mvp, q0, q1, q2, f.W, f.H, k, a, b, c);
     if (r >= 0) return r;
-    (void)seq;   // clipped, but the frame's ClipRec table was full: clip again
-    return resetup_clipped(d.mvp, q0, q1, q2, f.W, f.H, k, a, b, c) ? 2 : 0;
+    (void)seq;   // clipped, but the frame's ClipRec table was full: clip again. Temporaries: the out-of-line call takes
+    // addresses, and a, b, c must stay in registers on the hot path.
+    PolyV ta, tb, tc;
+    if (!resetup_clipped(d.mvp, q0, q1, q2, f.W, f.H, k, ta, tb, tc)) return 0;
+    a = ta; b = tb; c = tc;
+    return 2;
 }
 
 struct FragIn {
@@ -338,8 +342,12 @@ __device__ __forceinline__ void shade_inputs(const DFrame& f, const DDraw& d, co
                 in.sv += (sp.y / sp.w - d.stickerRange[1]) / d.stickerRange[3] * bary[j];
             }
         }
-    } else {
-        interpolate_general(f, d, vi, bary, in);
+    } else {   // rare: copies, so that the out-of-line call does not pin `in`, `vi`, `bary` to local memory
+        FragIn tmp;
+        const uint32_t vi2[3] = {vi[0], vi[1], vi[2]};
+        const float b2[3] = {bary[0], bary[1], bary[2]};
+        interpolate_general(f, d, vi2, b2, tmp);
+        in.wc = tmp.wc; in.cc = tmp.cc; in.objc = tmp.objc; in.su = tmp.su; in.sv = tmp.sv;
     }
     in.front = st.twoA < 0;   // FrontFace = CW (render_pass.cpp:330)
     in.u_dx = in.v_dx = in.u_dy = in.v_dy = 0.0f;
@@ -426,7 +434,13 @@ __device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, 
     if (d.tex[1]) {
         float4 t = sample_mat(d.tex[1], in);
         f3 tW, bW;
-        tangent_frame(d, vi, bary, tW, bW);
+        {
+            const uint32_t vi2[3] = {vi[0], vi[1], vi[2]};
+            const float b2[3] = {bary[0], bary[1], bary[2]};
+            f3 t2, bb2;
+            tangent_frame(d, vi2, b2, t2, bb2);   // out of line: operate on copies (see shade_inputs)
+            tW = t2; bW = bb2;
+        }
         normal = normalize3(tW * (t.x * 2.0f - 1.0f) + bW * (t.y * 2.0f - 1.0f) + in.nW * (t.z * 2.0f - 1.0f));
     } else normal = in.nW;
     if (!in.front) normal = -normal;

@@ -347,8 +347,10 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_setup(const DView* __res
             }
         }
     }
-    count_pair_agg(dt0, dt0 != 0xFFFFFFFFu, tile_count);
-    count_pair_agg(dt1, dt1 != 0xFFFFFFFFu && dt1 != dt0, tile_count);
+    if (__any_sync(0xffffffffu, dt0 != 0xFFFFFFFFu)) {   // rare now that small triangles take the direct path: skip the match
+        count_pair_agg(dt0, dt0 != 0xFFFFFFFFu, tile_count);
+        count_pair_agg(dt1, dt1 != 0xFFFFFFFFu && dt1 != dt0, tile_count);
+    }
     // compact the block's survivors: one global atomic per block
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(0xffffffffu, has_rec);
