@@ -837,11 +837,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
     if (px >= W || py >= H) return;
     const size_t p = (size_t)py * W + px;
     const unsigned long long key = f.keys[p];
-    float4* const o_coord = reinterpret_cast<float4*>(f.out[SLB_TARGET_COORD]);
-    unsigned short* const o_cls = reinterpret_cast<unsigned short*>(f.out[SLB_TARGET_CLASS]);
-    unsigned short* const o_inst = reinterpret_cast<unsigned short*>(f.out[SLB_TARGET_INSTANCE]);
-    uint4* const o_vidx = reinterpret_cast<uint4*>(f.out[SLB_TARGET_VERTEX_INDEX]);
-    float4* const o_bary = reinterpret_cast<float4*>(f.out[SLB_TARGET_BARY]);
+    // the target pointers are fetched where they are used (not held in registers across the set-up code)
+    auto store_geometry = [&](float4 coord, unsigned short cls, unsigned short inst, uint4 vidx, float4 bary4, float4 cam) {
+        if (float4* o = reinterpret_cast<float4*>(f.out[SLB_TARGET_COORD])) o[p] = coord;
+        if (unsigned short* o = reinterpret_cast<unsigned short*>(f.out[SLB_TARGET_CLASS])) o[p] = cls;
+        if (unsigned short* o = reinterpret_cast<unsigned short*>(f.out[SLB_TARGET_INSTANCE])) o[p] = inst;
+        if (uint4* o = reinterpret_cast<uint4*>(f.out[SLB_TARGET_VERTEX_INDEX])) o[p] = vidx;
+        if (float4* o = reinterpret_cast<float4*>(f.out[SLB_TARGET_BARY])) o[p] = bary4;
+        if (f.scratch_cam) f.scratch_cam[p] = cam;   // == out[CAM_COORD] when requested
+    };
 
     float4 hdr = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -862,24 +866,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
             FragIn in; float bary[3]; uint32_t vid[3];
             shade_inputs(f, d, st, va, vb, vc, vi, pm, how == 1, px, py, draw_has_textures(d), in, bary, vid);
             // geometry targets first: their registers are free before the lighting code runs
-            if (o_coord) o_coord[p] = in.objc;
-            if (o_cls) o_cls[p] = (unsigned short)d.class_index;
-            if (o_inst) o_inst[p] = (unsigned short)d.instance_index;
-            if (o_vidx) o_vidx[p] = make_uint4(vid[0], vid[1], vid[2], 0u);
-            if (o_bary) o_bary[p] = make_float4(bary[0], bary[1], bary[2], 1.0f);
-            if (f.scratch_cam) f.scratch_cam[p] = make_float4(in.cc.x, in.cc.y, in.cc.z, 1.0f);   // == out[CAM_COORD] when requested
+            store_geometry(in.objc, (unsigned short)d.class_index, (unsigned short)d.instance_index, make_uint4(vid[0], vid[1], vid[2], 0u),
+                           make_float4(bary[0], bary[1], bary[2], 1.0f), make_float4(in.cc.x, in.cc.y, in.cc.z, 1.0f));
             fragment_stage(f, d, in, vi, bary, hdr, nrm);
             shaded = true;
         }
     }
     if (!shaded) {   // clear values (render_pass.cpp:316,523-532)
         const float4 inval = make_float4(SLB_INVALID_COORD, SLB_INVALID_COORD, SLB_INVALID_COORD, SLB_INVALID_COORD);
-        if (o_coord) o_coord[p] = inval;
-        if (o_cls) o_cls[p] = 0;
-        if (o_inst) o_inst[p] = 0;
-        if (o_vidx) o_vidx[p] = make_uint4(0u, 0u, 0u, 0u);
-        if (o_bary) o_bary[p] = make_float4(0.f, 0.f, 0.f, 1.0f);
-        if (f.scratch_cam) f.scratch_cam[p] = inval;
+        store_geometry(inval, 0, 0, make_uint4(0u, 0u, 0u, 0u), make_float4(0.f, 0.f, 0.f, 1.0f), inval);
     }
     if (f.fused_tonemap) {
         if (f.out[SLB_TARGET_RGB]) reinterpret_cast<uchar4*>(f.out[SLB_TARGET_RGB])[p] = tone_map(hdr, f.manual_exposure, nullptr);
