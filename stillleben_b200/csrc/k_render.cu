@@ -183,7 +183,8 @@ __device__ __forceinline__ int tiles_of_box(int px0, int py0, int px1, int py1) 
 // clipped polygon is published once for the fragment test / shade kernel; survivors are appended one by one
 static __device__ __noinline__ void setup_clipped_prim(const float* mvp, float3 p0, float3 p1, float3 p2, uint32_t seq, uint32_t flags,
                                                        uint32_t draw, const DView& v, const DFrame* fr, uint32_t* __restrict__ tile_count,
-                                                       const SurvOut& so, BigEntry* s_big, int* s_nbig) {
+                                                       const SurvOut so /* by value: a reference would pin the kernel's copy to local memory */,
+                                                       BigEntry* s_big, int* s_nbig) {
     PrimSetup ps;
     if (!setup_prim(mvp, p0, p1, p2, v.W, v.H, ps)) return;
     uint32_t slot_bits = 0;   // (ClipRec slot + 1) << 3, carried in the key so the consumers index the record directly
@@ -282,7 +283,7 @@ __device__ __forceinline__ void raster_direct(int ax, int ay, int bx, int by, in
 // PASS 1 — triangle setup: one thread per triangle, one block per 256-triangle chunk of one draw (camera or
 // shadow view). Transforms, clips, snaps (contract C1-C6), counts the (tile, sub-triangle) pairs per tile and
 // appends every surviving sub-triangle, already snapped, to the compact survivors[] array.
-__global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_setup(const DView* __restrict__ views, const DFrame* __restrict__ frames,
+__global__ void __launch_bounds__(SLB_SETUP_CHUNK, 5) k_setup(const DView* __restrict__ views, const DFrame* __restrict__ frames,
                                                               const DBinDraw* __restrict__ bdraws, const uint32_t* __restrict__ chunk_draw,
                                                               uint32_t* __restrict__ tile_count, const SurvOut so, int direct_max, int warp_max) {
     __shared__ float s_mvp[16];
