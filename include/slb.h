@@ -348,6 +348,18 @@ typedef struct slb_camera_params {
 int slb_camera_model(slb_ctx* ctx, const void* in, int32_t in_format, float* out, int32_t n_images, int32_t height,
                      int32_t width, const slb_camera_params* params, void* stream);
 
+/* ---- batched PNG encoder (reference: src/image_saver.cpp, python/src/py_image_saver.cpp:37-99) -------- */
+
+/* Upper bound of one encoded file for an image of the given shape. */
+size_t slb_png_bound(int32_t height, int32_t width, int32_t channels, int32_t bytes_per_channel);
+/* Encodes n images of identical shape into n complete PNG files in DEVICE memory. images: n contiguous
+ * HxWxC arrays, uint8 (C = 1, 3, 4: grey, RGB, RGBA) or, with bytes_per_channel = 2, 16-bit HxW (C = 1) as the
+ * reference's binding accepts them; row 0 is the top row of the file. File i is written to
+ * out + i * out_stride (out_stride >= slb_png_bound(...)) and its size to sizes[i]; images / out / sizes are
+ * DEVICE pointers. */
+int slb_png_encode(slb_ctx* ctx, const void* images, int32_t n_images, int32_t height, int32_t width, int32_t channels,
+                   int32_t bytes_per_channel, uint8_t* out, size_t out_stride, uint32_t* sizes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

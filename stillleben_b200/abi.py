@@ -146,6 +146,9 @@ PROTOTYPES = {
                                                C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "slb_camera_model": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                     C.c_void_p]),
+    "slb_png_bound": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "slb_png_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+                                  C.c_void_p, C.c_void_p]),
     "slb_diff_pose_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }

@@ -1,0 +1,222 @@
+// k_png.cu — batched PNG encoder on the device (reference: src/image_saver.cpp + python/src/py_image_saver.cpp:37-99,
+// a pool of CPU threads each running libpng through Magnum's AnyImageConverter; SURVEY 8(f-4): "at > 10 k fps the
+// saver becomes the bottleneck"). Every image of a batch becomes a complete, standard PNG file in device memory:
+//   k_png_rows      one thread per (image, scanline): PNG filter 1 (Sub) + deflate with the fixed Huffman code and
+//                   run matches at distance 1 / bytes-per-pixel, written as one byte-aligned deflate block per
+//                   scanline (fixed block, end-of-block, empty stored block = a zlib "sync flush"), plus the
+//                   scanline's Adler-32 partial sums and the CRC-32 of its compressed bytes;
+//   k_png_finalize  one thread per image: scanline offsets, Adler-32 / CRC-32 combination (GF(2) polynomial
+//                   arithmetic as in zlib's crc32_combine), signature, IHDR, IDAT header / trailer, IEND;
+//   k_png_gather    one block per (image, scanline): moves the scanline's bytes to their place in the file.
+// Formats as the reference's binding accepts them: uint8 HxW, HxWx3, HxWx4 and 16-bit HxW (big-endian samples).
+// Row 0 of the tensor is the top row of the file (the binding's flipud + Magnum's bottom-up rows cancel).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace {
+
+#define PNG_POLY 0xEDB88320u
+
+__constant__ uint32_t c_crc_table[256];
+__constant__ uint32_t c_x2n[32];               // x^(2^k) mod P, reflected (zlib crc32.c x2n_table)
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+
+__device__ __forceinline__ uint32_t multmodp(uint32_t a, uint32_t b) {   // a(x) * b(x) mod P, reflected bit order
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
+        m >>= 1;
+        b = (b & 1) ? (b >> 1) ^ PNG_POLY : b >> 1;
+    }
+    return p;
+}
+__device__ __forceinline__ uint32_t x2nmodp(uint64_t n, unsigned k) {    // x^(n * 2^k) mod P
+    uint32_t p = 1u << 31;
+    while (n) { if (n & 1) p = multmodp(c_x2n[k & 31], p); n >>= 1; ++k; }
+    return p;
+}
+__device__ __forceinline__ uint32_t crc_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) { return multmodp(x2nmodp(len2, 3), crc1) ^ crc2; }
+__device__ __forceinline__ uint32_t crc_bytes(uint32_t crc, const uint8_t* p, size_t n) {
+    crc = ~crc;
+    for (size_t i = 0; i < n; ++i) crc = c_crc_table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    return ~crc;
+}
+__device__ __forceinline__ uint32_t rev_bits(uint32_t v, int n) { return __brev(v) >> (32 - n); }
+
+struct BitWriter {   // LSB-first bit packing into the scanline's byte range
+    uint8_t* out; size_t pos; uint64_t acc; int nbits;
+    __device__ __forceinline__ void put(uint32_t v, int n) {
+        acc |= (uint64_t)v << nbits; nbits += n;
+        while (nbits >= 8) { out[pos++] = (uint8_t)acc; acc >>= 8; nbits -= 8; }
+    }
+    __device__ __forceinline__ void align() { if (nbits) { out[pos++] = (uint8_t)acc; acc = 0; nbits = 0; } }
+};
+__device__ __forceinline__ void put_literal(BitWriter& w, uint32_t lit) {        // RFC 1951 3.2.6
+    if (lit < 144) w.put(rev_bits(0x30 + lit, 8), 8); else w.put(rev_bits(0x190 + (lit - 144), 9), 9);
+}
+__device__ __forceinline__ void put_match(BitWriter& w, int len, int dist) {     // dist in 1..4: codes 0..3, no extra bits
+    int c = 0;
+    while (c < 28 && (int)c_len_base[c + 1] <= len) ++c;
+    const int sym = 257 + c;
+    if (sym < 280) w.put(rev_bits(sym - 256, 7), 7); else w.put(rev_bits(0xC0 + (sym - 280), 8), 8);
+    if (c_len_extra[c]) w.put((uint32_t)(len - c_len_base[c]), c_len_extra[c]);
+    w.put(rev_bits((uint32_t)(dist - 1), 5), 5);
+}
+
+struct RowInfo { uint32_t bytes, crc, adler_a; uint64_t adler_b; };
+
+// sample byte b of pixel x of the scanline as the PNG stores it (16-bit samples big-endian)
+__device__ __forceinline__ uint8_t raw_byte(const uint8_t* row, int i, int bpc) { return bpc == 2 ? row[i ^ 1] : row[i]; }
+
+__global__ void __launch_bounds__(128) k_png_rows(const uint8_t* __restrict__ images, int n, int H, int W, int channels, int bpc,
+                                                  uint8_t* __restrict__ rows_out, size_t row_bound, RowInfo* __restrict__ info) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n * H) return;
+    const int bpp = channels * bpc;
+    const size_t row_bytes = (size_t)W * bpp;
+    const uint8_t* row = images + t * row_bytes;
+    BitWriter w;
+    w.out = rows_out + t * row_bound; w.pos = 0; w.acc = 0; w.nbits = 0;
+    w.put(0u, 1); w.put(1u, 2);                               // BFINAL = 0, BTYPE = 01 (fixed Huffman)
+    // filtered scanline: filter-type byte 1 (Sub), then raw[i] - raw[i - bpp]
+    uint64_t sa = 1, sb = (uint64_t)(row_bytes + 1) * 1;     // Adler partial sums of this scanline (filter byte = 1 first)
+    put_literal(w, 1u);
+    const size_t len = row_bytes;
+    auto filt = [&](size_t i) -> uint32_t {
+        const uint32_t cur = raw_byte(row, (int)i, bpc), left = i >= (size_t)bpp ? raw_byte(row, (int)(i - bpp), bpc) : 0u;
+        return (cur - left) & 0xffu;
+    };
+    size_t i = 0;
+    while (i < len) {
+        const uint32_t v = filt(i);
+        // run matches: the filtered bytes repeat with period 1 (flat colour) or period bpp (constant gradient)
+        int best = 0, dist = 0;
+        if (i >= 1) {
+            for (int d = 1; d <= bpp; d += (bpp > 1 ? bpp - 1 : 1)) {
+                if (i < (size_t)d) continue;
+                int l = 0;
+                while (l < 258 && i + l < len && filt(i + l) == filt(i + l - d)) ++l;
+                if (l > best) { best = l; dist = d; }
+                if (bpp == 1) break;
+            }
+        }
+        if (best >= 4) {
+            put_match(w, best, dist);
+            for (int k = 0; k < best; ++k) { const uint32_t b = filt(i + k); sa += b; sb += (uint64_t)(len - (i + k)) * b; }
+            i += best;
+        } else {
+            put_literal(w, v);
+            sa += v; sb += (uint64_t)(len - i) * v;
+            ++i;
+        }
+    }
+    w.put(0u, 7);                                             // end of block (symbol 256)
+    w.put(0u, 1); w.put(0u, 2); w.align();                    // empty stored block: byte alignment ("sync flush")
+    w.out[w.pos++] = 0x00; w.out[w.pos++] = 0x00; w.out[w.pos++] = 0xFF; w.out[w.pos++] = 0xFF;
+    RowInfo ri;
+    ri.bytes = (uint32_t)w.pos;
+    ri.crc = crc_bytes(0u, w.out, w.pos);
+    ri.adler_a = (uint32_t)(sa % 65521u);                     // includes the +1 of the filter byte, not Adler's initial 1
+    ri.adler_b = sb % 65521u;
+    info[t] = ri;
+}
+
+__device__ __forceinline__ void put_be32(uint8_t* p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
+
+__global__ void k_png_finalize(const RowInfo* __restrict__ info, int n, int H, int W, int channels, int bpc, uint8_t* __restrict__ out,
+                               size_t out_stride, uint32_t* __restrict__ sizes, uint32_t* __restrict__ row_offset) {
+    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= n) return;
+    uint8_t* f = out + (size_t)img * out_stride;
+    const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    for (int i = 0; i < 8; ++i) f[i] = sig[i];
+    // IHDR
+    put_be32(f + 8, 13u);
+    uint8_t* ih = f + 12;
+    ih[0] = 'I'; ih[1] = 'H'; ih[2] = 'D'; ih[3] = 'R';
+    put_be32(ih + 4, (uint32_t)W); put_be32(ih + 8, (uint32_t)H);
+    ih[12] = (uint8_t)(8 * bpc);
+    ih[13] = channels == 1 ? 0 : channels == 3 ? 2 : 6;       // colour type: grey, RGB, RGBA
+    ih[14] = 0; ih[15] = 0; ih[16] = 0;
+    put_be32(f + 29, crc_bytes(0u, ih, 17));
+    // IDAT: zlib header, the scanline blocks, final empty stored block, Adler-32
+    uint8_t* idat = f + 33;                                   // length field at +0, type at +4, data from +8
+    idat[4] = 'I'; idat[5] = 'D'; idat[6] = 'A'; idat[7] = 'T';
+    idat[8] = 0x78; idat[9] = 0x01;
+    uint32_t crc = crc_bytes(0u, idat + 4, 6);
+    uint32_t off = 10;                                        // next free byte relative to idat
+    const size_t row_len = (size_t)W * channels * bpc + 1;
+    uint64_t A = 1, B = 0;
+    for (int r = 0; r < H; ++r) {
+        const RowInfo ri = info[(size_t)img * H + r];
+        row_offset[(size_t)img * H + r] = 33u + off;
+        off += ri.bytes;
+        crc = crc_combine(crc, ri.crc, ri.bytes);
+        // the row's partial sums were taken with A starting at 0: A' = A + a, B' = B + len * A + b
+        B = (B + (row_len % 65521u) * A + ri.adler_b) % 65521u;
+        A = (A + ri.adler_a) % 65521u;
+    }
+    uint8_t* tail = idat + off;
+    tail[0] = 0x01; tail[1] = 0x00; tail[2] = 0x00; tail[3] = 0xFF; tail[4] = 0xFF;   // BFINAL = 1 stored, empty
+    put_be32(tail + 5, (uint32_t)((B << 16) | A));
+    crc = crc_combine(crc, crc_bytes(0u, tail, 9), 9);
+    put_be32(tail + 9, crc);
+    put_be32(idat, off + 9 - 8);                              // IDAT data length
+    uint8_t* iend = tail + 13;
+    put_be32(iend, 0u);
+    iend[4] = 'I'; iend[5] = 'E'; iend[6] = 'N'; iend[7] = 'D';
+    put_be32(iend + 8, 0xAE426082u);
+    sizes[img] = 33u + off + 13u + 12u;
+}
+
+__global__ void __launch_bounds__(128) k_png_gather(const uint8_t* __restrict__ rows_out, size_t row_bound, const RowInfo* __restrict__ info,
+                                                    const uint32_t* __restrict__ row_offset, int H, uint8_t* __restrict__ out, size_t out_stride) {
+    const size_t t = blockIdx.x;                              // image * H + row
+    const uint32_t nbytes = info[t].bytes;
+    const uint8_t* src = rows_out + t * row_bound;
+    uint8_t* dst = out + (t / H) * out_stride + row_offset[t];
+    for (uint32_t i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace
+
+namespace slbk {
+
+void png_upload_tables() {
+    uint32_t table[256];
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ PNG_POLY : c >> 1;
+        table[i] = c;
+    }
+    cudaMemcpyToSymbol(c_crc_table, table, sizeof table);
+    // x^(2^k) mod P by repeated squaring (host copy of multmodp)
+    auto mul = [](uint32_t a, uint32_t b) {
+        uint32_t m = 1u << 31, p = 0;
+        for (;;) {
+            if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
+            m >>= 1;
+            b = (b & 1) ? (b >> 1) ^ PNG_POLY : b >> 1;
+        }
+        return p;
+    };
+    uint32_t x2n[32], p = 1u << 30;
+    x2n[0] = p;
+    for (int k = 1; k < 32; ++k) x2n[k] = p = mul(p, p);
+    cudaMemcpyToSymbol(c_x2n, x2n, sizeof x2n);
+}
+size_t png_row_bound(int W, int channels, int bpc) { return (((size_t)W * channels * bpc + 1) * 9 + 7) / 8 + 16; }
+size_t png_file_bound(int H, int W, int channels, int bpc) { return 33 + 10 + (size_t)H * png_row_bound(W, channels, bpc) + 13 + 12 + 16; }
+size_t png_row_info_bytes() { return sizeof(RowInfo); }
+void launch_png_encode(const uint8_t* images, int n, int H, int W, int channels, int bpc, uint8_t* rows_scratch, void* row_info,
+                       uint32_t* row_offset, uint8_t* out, size_t out_stride, uint32_t* sizes, cudaStream_t s) {
+    const size_t rows = (size_t)n * H, rb = png_row_bound(W, channels, bpc);
+    k_png_rows<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(images, n, H, W, channels, bpc, rows_scratch, rb, (RowInfo*)row_info);
+    k_png_finalize<<<(n + 63) / 64, 64, 0, s>>>((const RowInfo*)row_info, n, H, W, channels, bpc, out, out_stride, sizes, row_offset);
+    k_png_gather<<<(unsigned)rows, 128, 0, s>>>(rows_scratch, rb, (const RowInfo*)row_info, row_offset, H, out, out_stride);
+}
+
+}  // namespace slbk

@@ -51,4 +51,12 @@ void launch_camera_stage1(const float* in_f, const uint8_t* in_u8, float* out, c
                           cudaStream_t s);
 void launch_camera_stage2(const float* in, float* out, float sigma, int n, int H, int W, cudaStream_t s);
 
+// k_png.cu
+void png_upload_tables();
+size_t png_row_bound(int W, int channels, int bpc);
+size_t png_file_bound(int H, int W, int channels, int bpc);
+size_t png_row_info_bytes();
+void launch_png_encode(const uint8_t* images, int n, int H, int W, int channels, int bpc, uint8_t* rows_scratch, void* row_info,
+                       uint32_t* row_offset, uint8_t* out, size_t out_stride, uint32_t* sizes, cudaStream_t s);
+
 }  // namespace slbk

@@ -79,7 +79,8 @@ struct slb_ctx {
     slb_mesh* plane = nullptr;
     // per-batch device arrays
     DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, survivors;
-    DevBuf clip_recs, clip_counts, diff_params, diff_partial, cam_params, cam_mid;
+    DevBuf clip_recs, clip_counts, diff_params, diff_partial, cam_params, cam_mid, png_rows, png_info, png_offsets;
+    bool png_tables = false;
     DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, ao, avg, mip_a, mip_b, shadow_maps;
     // pinned staging
     void* staging = nullptr; size_t staging_cap = 0;
@@ -207,7 +208,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
         if (ctx->slot_rendered[i]) cudaEventDestroy(ctx->slot_rendered[i]);
         if (ctx->slot_copied[i]) cudaEventDestroy(ctx->slot_copied[i]);
     }
-    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->survivors, &ctx->diff_params, &ctx->diff_partial, &ctx->cam_params, &ctx->cam_mid, &ctx->tile_count,
+    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->survivors, &ctx->diff_params, &ctx->diff_partial, &ctx->cam_params, &ctx->cam_mid, &ctx->png_rows, &ctx->png_info, &ctx->png_offsets, &ctx->tile_count,
                       &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->ao,
                       &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts};
     for (DevBuf* b : bufs) b->release();
@@ -1273,6 +1274,38 @@ extern "C" int slb_camera_model(slb_ctx* ctx, const void* in, int32_t in_format,
                          ctx->cam_params.as<slb_camera_params>(), n_images, height, width, s);
     if (any_post) launch_camera_stage2(mid, out, 0.4f, n_images, height, width, s);
     ctx->stats.kernel_launches += any_post ? 2 : 1;
+    CU(cudaGetLastError());
+    return SLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched PNG encoder
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t slb_png_bound(int32_t height, int32_t width, int32_t channels, int32_t bytes_per_channel) {
+    if (height <= 0 || width <= 0 || channels <= 0 || bytes_per_channel <= 0) return 0;
+    return png_file_bound(height, width, channels, bytes_per_channel);
+}
+extern "C" int slb_png_encode(slb_ctx* ctx, const void* images, int32_t n_images, int32_t height, int32_t width, int32_t channels,
+                              int32_t bytes_per_channel, uint8_t* out, size_t out_stride, uint32_t* sizes, void* stream) {
+    if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
+    if (!images || !out || !sizes || n_images <= 0 || height <= 0 || width <= 0)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_png_encode: bad arguments");
+    const bool ok8 = bytes_per_channel == 1 && (channels == 1 || channels == 3 || channels == 4);
+    const bool ok16 = bytes_per_channel == 2 && channels == 1;
+    if (!ok8 && !ok16)   // py_image_saver.cpp:50-95
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_png_encode: images must be uint8 HxW, HxWx3, HxWx4 or 16-bit HxW");
+    if (out_stride < png_file_bound(height, width, channels, bytes_per_channel))
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_png_encode: out_stride is smaller than slb_png_bound()");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    if (!ctx->png_tables) { png_upload_tables(); ctx->png_tables = true; }
+    const size_t rows = (size_t)n_images * height;
+    CU(ctx->png_rows.reserve(rows * png_row_bound(width, channels, bytes_per_channel)));
+    CU(ctx->png_info.reserve(rows * png_row_info_bytes()));
+    CU(ctx->png_offsets.reserve(rows * 4));
+    launch_png_encode((const uint8_t*)images, n_images, height, width, channels, bytes_per_channel, ctx->png_rows.as<uint8_t>(), ctx->png_info.p,
+                      ctx->png_offsets.as<uint32_t>(), out, out_stride, sizes, s);
+    ctx->stats.kernel_launches += 3;
     CU(cudaGetLastError());
     return SLB_OK;
 }
