@@ -6,7 +6,7 @@ Magnum's AnyImageConverter). The reference's exact bytes are libpng's and are no
 IS defined is the decoded image: row 0 of the tensor is the top row, uint8 HxW / HxWx3 / HxWx4 or 16-bit HxW.
 So parity = (a) this restatement decodes, with an independent decoder (PIL, zlib), to exactly the input pixels,
 and (b) the kernels produce exactly these bytes. Stream layout: PNG filter 1 (Sub) on every scanline; one
-fixed-Huffman deflate block per scanline with run matches (length >= 4) at distance 1 or bytes-per-pixel,
+fixed-Huffman deflate block per 512-byte scanline segment with run matches (length >= 4) at distance 1 or bytes-per-pixel,
 followed by an empty stored block (byte alignment); a final empty stored block; zlib header 78 01.
 Pure-Python loops: small images only.
 """
@@ -62,35 +62,42 @@ def put_match(w, length, dist):
     w.put(rev(dist - 1, 5), 5)
 
 
+SEG = 512       # data bytes per deflate block (k_png.cu: PNG_SEG)
+
+
 def encode_row(raw, bpp):
-    """raw: the scanline's bytes as PNG stores them. Returns the byte-aligned deflate block(s) of the scanline."""
+    """raw: the scanline's bytes as PNG stores them. Returns the scanline's byte-aligned deflate blocks (one per
+    SEG-byte segment, no match reaches back across a segment start) and its filtered bytes."""
     n = len(raw)
     f = [(raw[i] - (raw[i - bpp] if i >= bpp else 0)) & 0xFF for i in range(n)]
-    w = BitWriter()
-    w.put(0, 1); w.put(1, 2)
-    put_literal(w, 1)
-    i = 0
-    while i < n:
-        best, dist = 0, 0
-        if i >= 1:
+    out = bytearray()
+    for beg in range(0, max(n, 1), SEG):
+        end = min(beg + SEG, n)
+        w = BitWriter()
+        w.put(0, 1); w.put(1, 2)
+        if beg == 0:
+            put_literal(w, 1)
+        i = beg
+        while i < end:
+            best, dist = 0, 0
             for d in ([1] if bpp == 1 else [1, bpp]):
-                if i < d:
+                if i < beg + d:
                     continue
                 l = 0
-                while l < 258 and i + l < n and f[i + l] == f[i + l - d]:
+                while l < 258 and i + l < end and f[i + l] == f[i + l - d]:
                     l += 1
                 if l > best:
                     best, dist = l, d
-        if best >= 4:
-            put_match(w, best, dist)
-            i += best
-        else:
-            put_literal(w, f[i])
-            i += 1
-    w.put(0, 7)
-    w.put(0, 1); w.put(0, 2); w.align()
-    w.out += b"\x00\x00\xff\xff"
-    return bytes(w.out), bytes([1] + f)
+            if best >= 4:
+                put_match(w, best, dist)
+                i += best
+            else:
+                put_literal(w, f[i])
+                i += 1
+        w.put(0, 7)
+        w.put(0, 1); w.put(0, 2); w.align()
+        out += w.out + b"\x00\x00\xff\xff"
+    return bytes(out), bytes([1] + f)
 
 
 def chunk(kind, data):

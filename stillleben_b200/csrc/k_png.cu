@@ -1,13 +1,14 @@
 // k_png.cu — batched PNG encoder on the device (reference: src/image_saver.cpp + python/src/py_image_saver.cpp:37-99,
 // a pool of CPU threads each running libpng through Magnum's AnyImageConverter; SURVEY 8(f-4): "at > 10 k fps the
 // saver becomes the bottleneck"). Every image of a batch becomes a complete, standard PNG file in device memory:
-//   k_png_rows      one thread per (image, scanline): PNG filter 1 (Sub) + deflate with the fixed Huffman code and
-//                   run matches at distance 1 / bytes-per-pixel, written as one byte-aligned deflate block per
-//                   scanline (fixed block, end-of-block, empty stored block = a zlib "sync flush"), plus the
-//                   scanline's Adler-32 partial sums and the CRC-32 of its compressed bytes;
-//   k_png_finalize  one thread per image: scanline offsets, Adler-32 / CRC-32 combination (GF(2) polynomial
-//                   arithmetic as in zlib's crc32_combine), signature, IHDR, IDAT header / trailer, IEND;
-//   k_png_gather    one block per (image, scanline): moves the scanline's bytes to their place in the file.
+//   k_png_rows      one thread per (image, scanline, 512-byte segment): PNG filter 1 (Sub) + deflate with the fixed
+//                   Huffman code and run matches at distance 1 / bytes-per-pixel, written as one byte-aligned
+//                   deflate block per segment (fixed block, end-of-block, empty stored block = a zlib "sync
+//                   flush"), plus the block's Adler-32 partial sums and the CRC-32 of its compressed bytes;
+//   k_png_finalize  one block per image: block offsets (prefix sum), ordered tree combination of the Adler-32 /
+//                   CRC-32 parts (GF(2) polynomial arithmetic as in zlib's crc32_combine), signature, IHDR, IDAT
+//                   header / trailer, IEND;
+//   k_png_gather    one block per deflate block: moves its bytes to their place in the file.
 // Formats as the reference's binding accepts them: uint8 HxW, HxWx3, HxWx4 and 16-bit HxW (big-endian samples).
 // Row 0 of the tensor is the top row of the file (the binding's flipud + Magnum's bottom-up rows cancel).
 #include <cuda_runtime.h>
@@ -66,50 +67,55 @@ __device__ __forceinline__ void put_match(BitWriter& w, int len, int dist) {    
     w.put(rev_bits((uint32_t)(dist - 1), 5), 5);
 }
 
-struct RowInfo { uint32_t bytes, crc, adler_a; uint64_t adler_b; };
+struct RowInfo { uint32_t bytes, crc, adler_a, len; uint64_t adler_b; };
 
 // sample byte b of pixel x of the scanline as the PNG stores it (16-bit samples big-endian)
 __device__ __forceinline__ uint8_t raw_byte(const uint8_t* row, int i, int bpc) { return bpc == 2 ? row[i ^ 1] : row[i]; }
 
-__global__ void __launch_bounds__(128) k_png_rows(const uint8_t* __restrict__ images, int n, int H, int W, int channels, int bpc,
-                                                  uint8_t* __restrict__ rows_out, size_t row_bound, RowInfo* __restrict__ info) {
+// one thread per (image, scanline, segment): a scanline is cut into segments of PNG_SEG data bytes, each its own
+// byte-aligned deflate block, so that a batch of 64 VGA frames exposes > 100 k independent encoders
+#define PNG_SEG 512
+__global__ void __launch_bounds__(128) k_png_rows(const uint8_t* __restrict__ images, int n, int H, int W, int channels, int bpc, int n_seg,
+                                                  uint8_t* __restrict__ rows_out, size_t seg_bound, RowInfo* __restrict__ info) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)n * H) return;
+    if (t >= (size_t)n * H * n_seg) return;
+    const size_t rowi = t / n_seg;
+    const int seg = (int)(t - rowi * n_seg);
     const int bpp = channels * bpc;
     const size_t row_bytes = (size_t)W * bpp;
-    const uint8_t* row = images + t * row_bytes;
+    const uint8_t* row = images + rowi * row_bytes;
+    const size_t beg = (size_t)seg * PNG_SEG, end = min(beg + (size_t)PNG_SEG, row_bytes);
     BitWriter w;
-    w.out = rows_out + t * row_bound; w.pos = 0; w.acc = 0; w.nbits = 0;
+    w.out = rows_out + t * seg_bound; w.pos = 0; w.acc = 0; w.nbits = 0;
     w.put(0u, 1); w.put(1u, 2);                               // BFINAL = 0, BTYPE = 01 (fixed Huffman)
-    // filtered scanline: filter-type byte 1 (Sub), then raw[i] - raw[i - bpp]
-    uint64_t sa = 1, sb = (uint64_t)(row_bytes + 1) * 1;     // Adler partial sums of this scanline (filter byte = 1 first)
-    put_literal(w, 1u);
-    const size_t len = row_bytes;
+    // filtered scanline: filter-type byte 1 (Sub) in front of the first segment, then raw[i] - raw[i - bpp]
+    const size_t seg_len = (end - beg) + (seg == 0 ? 1 : 0);  // filtered bytes this block carries
+    uint64_t sa = 0, sb = 0;                                  // Adler partial sums of this block
+    if (seg == 0) { put_literal(w, 1u); sa = 1; sb = seg_len; }
     auto filt = [&](size_t i) -> uint32_t {
         const uint32_t cur = raw_byte(row, (int)i, bpc), left = i >= (size_t)bpp ? raw_byte(row, (int)(i - bpp), bpc) : 0u;
         return (cur - left) & 0xffu;
     };
-    size_t i = 0;
-    while (i < len) {
+    size_t i = beg;
+    while (i < end) {
         const uint32_t v = filt(i);
-        // run matches: the filtered bytes repeat with period 1 (flat colour) or period bpp (constant gradient)
+        // run matches inside the segment: the filtered bytes repeat with period 1 (flat colour) or bpp (constant gradient)
         int best = 0, dist = 0;
-        if (i >= 1) {
-            for (int d = 1; d <= bpp; d += (bpp > 1 ? bpp - 1 : 1)) {
-                if (i < (size_t)d) continue;
+        for (int d = 1; d <= bpp; d += (bpp > 1 ? bpp - 1 : 1)) {
+            if (i >= beg + (size_t)d) {
                 int l = 0;
-                while (l < 258 && i + l < len && filt(i + l) == filt(i + l - d)) ++l;
+                while (l < 258 && i + l < end && filt(i + l) == filt(i + l - d)) ++l;
                 if (l > best) { best = l; dist = d; }
-                if (bpp == 1) break;
             }
+            if (bpp == 1) break;
         }
         if (best >= 4) {
             put_match(w, best, dist);
-            for (int k = 0; k < best; ++k) { const uint32_t b = filt(i + k); sa += b; sb += (uint64_t)(len - (i + k)) * b; }
+            for (int k = 0; k < best; ++k) { const uint32_t b = filt(i + k); sa += b; sb += (uint64_t)(end - (i + k)) * b; }
             i += best;
         } else {
             put_literal(w, v);
-            sa += v; sb += (uint64_t)(len - i) * v;
+            sa += v; sb += (uint64_t)(end - i) * v;
             ++i;
         }
     }
@@ -119,21 +125,66 @@ __global__ void __launch_bounds__(128) k_png_rows(const uint8_t* __restrict__ im
     RowInfo ri;
     ri.bytes = (uint32_t)w.pos;
     ri.crc = crc_bytes(0u, w.out, w.pos);
-    ri.adler_a = (uint32_t)(sa % 65521u);                     // includes the +1 of the filter byte, not Adler's initial 1
+    ri.adler_a = (uint32_t)(sa % 65521u);                     // sums over this block's bytes only (Adler's initial 1 comes later)
     ri.adler_b = sb % 65521u;
+    ri.len = (uint32_t)seg_len;
     info[t] = ri;
 }
 
 __device__ __forceinline__ void put_be32(uint8_t* p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
 
-__global__ void k_png_finalize(const RowInfo* __restrict__ info, int n, int H, int W, int channels, int bpc, uint8_t* __restrict__ out,
-                               size_t out_stride, uint32_t* __restrict__ sizes, uint32_t* __restrict__ row_offset) {
-    const int img = blockIdx.x * blockDim.x + threadIdx.x;
-    if (img >= n) return;
+// One block per image. CRC-32 and Adler-32 of a concatenation are associative combinations of the parts
+// ((crc, length) and (sum, weighted sum, length) monoids), so the image's deflate blocks are reduced by a tree in
+// shared memory; their file offsets are a prefix sum of their sizes.
+#define PNG_FIN_THREADS 256
+__global__ void __launch_bounds__(PNG_FIN_THREADS) k_png_finalize(const RowInfo* __restrict__ info, int H, int W, int channels, int bpc,
+                                                                  int n_seg, uint8_t* __restrict__ out, size_t out_stride,
+                                                                  uint32_t* __restrict__ sizes, uint32_t* __restrict__ row_offset) {
+    __shared__ uint32_t s_crc[PNG_FIN_THREADS], s_bytes[PNG_FIN_THREADS], s_a[PNG_FIN_THREADS], s_b[PNG_FIN_THREADS];
+    __shared__ uint64_t s_len[PNG_FIN_THREADS];
+    __shared__ uint32_t s_base[PNG_FIN_THREADS];
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int n_blocks = H * n_seg;
+    const int per = (n_blocks + PNG_FIN_THREADS - 1) / PNG_FIN_THREADS;
+    const int b0 = min(tid * per, n_blocks), b1 = min(b0 + per, n_blocks);
+    const RowInfo* my = info + (size_t)img * n_blocks;
+    // sequential combination of this thread's run of blocks
+    uint32_t crc = 0, bytes = 0; uint64_t a = 0, b = 0, len = 0;
+    for (int r = b0; r < b1; ++r) {
+        const RowInfo ri = my[r];
+        crc = bytes ? crc_combine(crc, ri.crc, ri.bytes) : ri.crc;
+        bytes += ri.bytes;
+        b = (b + (uint64_t)ri.len % 65521u * a + ri.adler_b) % 65521u;
+        a = (a + ri.adler_a) % 65521u;
+        len += ri.len;
+    }
+    s_crc[tid] = crc; s_bytes[tid] = bytes; s_a[tid] = (uint32_t)a; s_b[tid] = (uint32_t)b; s_len[tid] = len;
+    __syncthreads();
+    if (tid == 0) {   // exclusive prefix of the byte counts (256 adds)
+        uint32_t run = 0;
+        for (int t = 0; t < PNG_FIN_THREADS; ++t) { s_base[t] = run; run += s_bytes[t]; }
+    }
+    __syncthreads();
+    {   // file offsets of this thread's blocks: 33 (signature + IHDR) + 10 (IDAT length, type, zlib header) + prefix
+        uint32_t off = 43u + s_base[tid];
+        for (int r = b0; r < b1; ++r) { row_offset[(size_t)img * n_blocks + r] = off; off += my[r].bytes; }
+    }
+    // ordered tree reduction: element t absorbs element t + stride (which follows it in the stream)
+    for (int stride = 1; stride < PNG_FIN_THREADS; stride <<= 1) {
+        if ((tid & (2 * stride - 1)) == 0) {
+            const int o = tid + stride;
+            if (s_bytes[o]) s_crc[tid] = s_bytes[tid] ? crc_combine(s_crc[tid], s_crc[o], s_bytes[o]) : s_crc[o];
+            s_bytes[tid] += s_bytes[o];
+            s_b[tid] = (uint32_t)((s_b[tid] + (s_len[o] % 65521u) * s_a[tid] + s_b[o]) % 65521u);
+            s_a[tid] = (s_a[tid] + s_a[o]) % 65521u;
+            s_len[tid] += s_len[o];
+        }
+        __syncthreads();
+    }
+    if (tid != 0) return;
     uint8_t* f = out + (size_t)img * out_stride;
     const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     for (int i = 0; i < 8; ++i) f[i] = sig[i];
-    // IHDR
     put_be32(f + 8, 13u);
     uint8_t* ih = f + 12;
     ih[0] = 'I'; ih[1] = 'H'; ih[2] = 'D'; ih[3] = 'R';
@@ -142,42 +193,33 @@ __global__ void k_png_finalize(const RowInfo* __restrict__ info, int n, int H, i
     ih[13] = channels == 1 ? 0 : channels == 3 ? 2 : 6;       // colour type: grey, RGB, RGBA
     ih[14] = 0; ih[15] = 0; ih[16] = 0;
     put_be32(f + 29, crc_bytes(0u, ih, 17));
-    // IDAT: zlib header, the scanline blocks, final empty stored block, Adler-32
+    // IDAT: zlib header, the deflate blocks, final empty stored block, Adler-32
     uint8_t* idat = f + 33;                                   // length field at +0, type at +4, data from +8
     idat[4] = 'I'; idat[5] = 'D'; idat[6] = 'A'; idat[7] = 'T';
     idat[8] = 0x78; idat[9] = 0x01;
-    uint32_t crc = crc_bytes(0u, idat + 4, 6);
-    uint32_t off = 10;                                        // next free byte relative to idat
-    const size_t row_len = (size_t)W * channels * bpc + 1;
-    uint64_t A = 1, B = 0;
-    for (int r = 0; r < H; ++r) {
-        const RowInfo ri = info[(size_t)img * H + r];
-        row_offset[(size_t)img * H + r] = 33u + off;
-        off += ri.bytes;
-        crc = crc_combine(crc, ri.crc, ri.bytes);
-        // the row's partial sums were taken with A starting at 0: A' = A + a, B' = B + len * A + b
-        B = (B + (row_len % 65521u) * A + ri.adler_b) % 65521u;
-        A = (A + ri.adler_a) % 65521u;
-    }
-    uint8_t* tail = idat + off;
+    const uint32_t body = s_bytes[0];
+    uint32_t c = crc_combine(crc_bytes(0u, idat + 4, 6), s_crc[0], body);
+    const uint32_t A = (1u + s_a[0]) % 65521u, B = (uint32_t)((s_len[0] % 65521u + s_b[0]) % 65521u);   // Adler starts at A = 1, B = 0
+    uint8_t* tail = idat + 10 + body;
     tail[0] = 0x01; tail[1] = 0x00; tail[2] = 0x00; tail[3] = 0xFF; tail[4] = 0xFF;   // BFINAL = 1 stored, empty
-    put_be32(tail + 5, (uint32_t)((B << 16) | A));
-    crc = crc_combine(crc, crc_bytes(0u, tail, 9), 9);
-    put_be32(tail + 9, crc);
-    put_be32(idat, off + 9 - 8);                              // IDAT data length
+    put_be32(tail + 5, (B << 16) | A);
+    c = crc_combine(c, crc_bytes(0u, tail, 9), 9);
+    put_be32(tail + 9, c);
+    put_be32(idat, 2u + body + 9u);                           // IDAT data length
     uint8_t* iend = tail + 13;
     put_be32(iend, 0u);
     iend[4] = 'I'; iend[5] = 'E'; iend[6] = 'N'; iend[7] = 'D';
     put_be32(iend + 8, 0xAE426082u);
-    sizes[img] = 33u + off + 13u + 12u;
+    sizes[img] = 43u + body + 13u + 12u;
 }
 
-__global__ void __launch_bounds__(128) k_png_gather(const uint8_t* __restrict__ rows_out, size_t row_bound, const RowInfo* __restrict__ info,
-                                                    const uint32_t* __restrict__ row_offset, int H, uint8_t* __restrict__ out, size_t out_stride) {
-    const size_t t = blockIdx.x;                              // image * H + row
+__global__ void __launch_bounds__(128) k_png_gather(const uint8_t* __restrict__ rows_out, size_t seg_bound, const RowInfo* __restrict__ info,
+                                                    const uint32_t* __restrict__ row_offset, int blocks_per_image, uint8_t* __restrict__ out,
+                                                    size_t out_stride) {
+    const size_t t = blockIdx.x;                              // (image * H + row) * n_seg + segment
     const uint32_t nbytes = info[t].bytes;
-    const uint8_t* src = rows_out + t * row_bound;
-    uint8_t* dst = out + (t / H) * out_stride + row_offset[t];
+    const uint8_t* src = rows_out + t * seg_bound;
+    uint8_t* dst = out + (t / blocks_per_image) * out_stride + row_offset[t];
     for (uint32_t i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = src[i];
 }
 
@@ -208,15 +250,19 @@ void png_upload_tables() {
     for (int k = 1; k < 32; ++k) x2n[k] = p = mul(p, p);
     cudaMemcpyToSymbol(c_x2n, x2n, sizeof x2n);
 }
-size_t png_row_bound(int W, int channels, int bpc) { return (((size_t)W * channels * bpc + 1) * 9 + 7) / 8 + 16; }
-size_t png_file_bound(int H, int W, int channels, int bpc) { return 33 + 10 + (size_t)H * png_row_bound(W, channels, bpc) + 13 + 12 + 16; }
+int png_segments(int W, int channels, int bpc) { return (int)(((size_t)W * channels * bpc + PNG_SEG - 1) / PNG_SEG); }
+size_t png_seg_bound() { return ((size_t)(PNG_SEG + 1) * 9 + 7) / 8 + 16; }
+size_t png_file_bound(int H, int W, int channels, int bpc) {
+    return 33 + 10 + (size_t)H * png_segments(W, channels, bpc) * png_seg_bound() + 13 + 12 + 16;
+}
 size_t png_row_info_bytes() { return sizeof(RowInfo); }
 void launch_png_encode(const uint8_t* images, int n, int H, int W, int channels, int bpc, uint8_t* rows_scratch, void* row_info,
                        uint32_t* row_offset, uint8_t* out, size_t out_stride, uint32_t* sizes, cudaStream_t s) {
-    const size_t rows = (size_t)n * H, rb = png_row_bound(W, channels, bpc);
-    k_png_rows<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(images, n, H, W, channels, bpc, rows_scratch, rb, (RowInfo*)row_info);
-    k_png_finalize<<<(n + 63) / 64, 64, 0, s>>>((const RowInfo*)row_info, n, H, W, channels, bpc, out, out_stride, sizes, row_offset);
-    k_png_gather<<<(unsigned)rows, 128, 0, s>>>(rows_scratch, rb, (const RowInfo*)row_info, row_offset, H, out, out_stride);
+    const int n_seg = png_segments(W, channels, bpc);
+    const size_t blocks = (size_t)n * H * n_seg, sb = png_seg_bound();
+    k_png_rows<<<(unsigned)((blocks + 127) / 128), 128, 0, s>>>(images, n, H, W, channels, bpc, n_seg, rows_scratch, sb, (RowInfo*)row_info);
+    k_png_finalize<<<n, PNG_FIN_THREADS, 0, s>>>((const RowInfo*)row_info, H, W, channels, bpc, n_seg, out, out_stride, sizes, row_offset);
+    k_png_gather<<<(unsigned)blocks, 128, 0, s>>>(rows_scratch, sb, (const RowInfo*)row_info, row_offset, H * n_seg, out, out_stride);
 }
 
 }  // namespace slbk

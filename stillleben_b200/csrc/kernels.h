@@ -53,7 +53,8 @@ void launch_camera_stage2(const float* in, float* out, float sigma, int n, int H
 
 // k_png.cu
 void png_upload_tables();
-size_t png_row_bound(int W, int channels, int bpc);
+int png_segments(int W, int channels, int bpc);
+size_t png_seg_bound();
 size_t png_file_bound(int H, int W, int channels, int bpc);
 size_t png_row_info_bytes();
 void launch_png_encode(const uint8_t* images, int n, int H, int W, int channels, int bpc, uint8_t* rows_scratch, void* row_info,

@@ -1299,8 +1299,8 @@ extern "C" int slb_png_encode(slb_ctx* ctx, const void* images, int32_t n_images
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     if (!ctx->png_tables) { png_upload_tables(); ctx->png_tables = true; }
-    const size_t rows = (size_t)n_images * height;
-    CU(ctx->png_rows.reserve(rows * png_row_bound(width, channels, bytes_per_channel)));
+    const size_t rows = (size_t)n_images * height * png_segments(width, channels, bytes_per_channel);   // deflate blocks
+    CU(ctx->png_rows.reserve(rows * png_seg_bound()));
     CU(ctx->png_info.reserve(rows * png_row_info_bytes()));
     CU(ctx->png_offsets.reserve(rows * 4));
     launch_png_encode((const uint8_t*)images, n_images, height, width, channels, bytes_per_channel, ctx->png_rows.as<uint8_t>(), ctx->png_info.p,
