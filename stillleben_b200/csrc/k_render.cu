@@ -390,78 +390,26 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 5) k_setup(const DView* __res
 #undef SLB_DQ
 }
 
-// PASS 2 — emit: one thread per SURVIVOR (dense: no culled triangles, no vertex fetch, no transform). Records
-// touching one or two tiles are written directly; all others are queued in shared memory and their (record, tile)
-// work items are spread over the whole block, so no thread runs a long chain of dependent atomics.
-struct EmitEntry { PairRec rec; uint16_t tx0, ty0, ntx, nty; uint32_t n, sbits; };
-#define SLB_EMIT_QUEUE 160
+// PASS 2 — emit: one thread per ordinary SURVIVOR (dense: no culled triangles, no vertex fetch, no transform). Ordinary
+// survivors touch one or two tiles (everything larger went to the huge list, PASS 2b), so each thread writes its record
+// into at most two tile segments, with one atomic per distinct tile per warp.
 __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 4) k_emit(const DView* __restrict__ views, const PairRec* __restrict__ survivors,
                                                              uint32_t n_survivors, uint32_t* __restrict__ tile_count,
                                                              PairRec* __restrict__ pairs, uint32_t capacity) {
-    __shared__ EmitEntry s_q[SLB_EMIT_QUEUE];
-    __shared__ uint32_t s_prefix[SLB_EMIT_QUEUE + 1];
-    __shared__ int s_nq;
-    if (threadIdx.x == 0) s_nq = 0;
-    __syncthreads();
+    static_assert(SLB_HUGE_TILES == 2, "k_emit handles one- and two-tile records only");
     const uint32_t i = blockIdx.x * SLB_SETUP_CHUNK + threadIdx.x;
     PairRec rec;
-    uint32_t dt0 = 0xFFFFFFFFu, dt1 = 0xFFFFFFFFu;   // tiles of a one / two tile record
+    uint32_t dt0 = 0xFFFFFFFFu, dt1 = 0xFFFFFFFFu;
     if (i < n_survivors) {
         rec = survivors[i];
         const DView& v = views[rec.k_flags >> 16];
         int px0, py0, px1, py1;
         pixel_box(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, v.W, v.H, px0, py0, px1, py1);
         const int tx0 = px0 / SLB_TILE, tx1 = px1 / SLB_TILE, ty0 = py0 / SLB_TILE, ty1 = py1 / SLB_TILE;
-        const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
-        if (ntx * nty <= 2) {
-            dt0 = v.tile_base + ty0 * v.tiles_x + tx0; dt1 = v.tile_base + ty1 * v.tiles_x + tx1;
-        } else {
-            const long long twoA = edge_fn(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy);
-            const int sg = twoA > 0 ? 1 : -1;
-            const uint32_t sbits = (sg < 0 ? 1u : 0u) | (top_left(rec.cx - rec.bx, rec.cy - rec.by, sg) ? 0u : 2u) |
-                                   (top_left(rec.ax - rec.cx, rec.ay - rec.cy, sg) ? 0u : 4u) | (top_left(rec.bx - rec.ax, rec.by - rec.ay, sg) ? 0u : 8u);
-            const int q = atomicAdd(&s_nq, 1);
-            if (q < SLB_EMIT_QUEUE) {
-                EmitEntry& e = s_q[q];
-                e.rec = rec; e.tx0 = (uint16_t)tx0; e.ty0 = (uint16_t)ty0; e.ntx = (uint16_t)ntx; e.nty = (uint16_t)nty;
-                e.n = (uint32_t)(ntx * nty); e.sbits = sbits;
-            } else {   // queue full: walk the tiles alone
-                SubTri st;
-                st.ax = rec.ax; st.ay = rec.ay; st.bx = rec.bx; st.by = rec.by; st.cx = rec.cx; st.cy = rec.cy;
-                st.s = sg; st.bias0 = (sbits & 2) ? -1 : 0; st.bias1 = (sbits & 4) ? -1 : 0; st.bias2 = (sbits & 8) ? -1 : 0;
-                for (int ty = ty0; ty <= ty1; ++ty)
-                    for (int tx = tx0; tx <= tx1; ++tx)
-                        if (tile_may_overlap(st, tx, ty, v.W, v.H))
-                            bin_pair<true>(v.tile_base + ty * v.tiles_x + tx, rec, tile_count, nullptr, pairs, capacity);
-            }
-        }
+        dt0 = v.tile_base + ty0 * v.tiles_x + tx0; dt1 = v.tile_base + ty1 * v.tiles_x + tx1;   // equal for a one-tile record
     }
     emit_pair_agg(dt0, dt0 != 0xFFFFFFFFu, rec, tile_count, pairs, capacity);
     emit_pair_agg(dt1, dt1 != 0xFFFFFFFFu && dt1 != dt0, rec, tile_count, pairs, capacity);
-    __syncthreads();
-    const int nq = min(s_nq, SLB_EMIT_QUEUE);
-    if (nq == 0) return;
-    if (threadIdx.x == 0) {   // prefix sums of the per-entry tile counts (<= 160 entries)
-        uint32_t run = 0;
-        for (int q = 0; q < nq; ++q) { s_prefix[q] = run; run += s_q[q].n; }
-        s_prefix[nq] = run;
-    }
-    __syncthreads();
-    const uint32_t total = s_prefix[nq];
-    for (uint32_t w0 = 0; w0 < total; w0 += SLB_SETUP_CHUNK) {
-        const uint32_t w = w0 + threadIdx.x;
-        if (w >= total) { emit_pair_agg(0u, false, rec, tile_count, pairs, capacity); continue; }   // keeps the warp converged
-        int lo = 0, hi = nq - 1;   // last entry with prefix <= w
-        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_prefix[mid] <= w) lo = mid; else hi = mid - 1; }
-        const EmitEntry& e = s_q[lo];
-        const uint32_t k = w - s_prefix[lo];
-        const int tx = e.tx0 + (int)(k % e.ntx), ty = e.ty0 + (int)(k / e.ntx);
-        const DView& v = views[e.rec.k_flags >> 16];
-        SubTri st;
-        st.ax = e.rec.ax; st.ay = e.rec.ay; st.bx = e.rec.bx; st.by = e.rec.by; st.cx = e.rec.cx; st.cy = e.rec.cy;
-        st.s = (e.sbits & 1) ? -1 : 1; st.bias0 = (e.sbits & 2) ? -1 : 0; st.bias1 = (e.sbits & 4) ? -1 : 0; st.bias2 = (e.sbits & 8) ? -1 : 0;
-        emit_pair_agg(v.tile_base + ty * v.tiles_x + tx, tile_may_overlap(st, tx, ty, v.W, v.H), e.rec, tile_count, pairs, capacity);
-    }
 }
 
 // PASS 2b — one block per HUGE survivor: the block's threads stride over the tiles of its bounding box.
