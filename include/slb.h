@@ -285,7 +285,10 @@ enum {
      * setup kernel, up to WARP_MAX pixels by one warp of it; larger ones take the tiled path. 0/0 =
      * everything through the tiled path. Defaults 128 / 4096. */
     SLB_OPT_DIRECT_MAX = 4,
-    SLB_OPT_WARP_MAX = 5
+    SLB_OPT_WARP_MAX = 5,
+    /* 1 (default): sub-batches that use no normal / metallic-roughness / emissive / occlusion textures, stickers,
+     * light maps or projective transformations run the lean instantiation of the shade kernel; 0: always the full one. */
+    SLB_OPT_LEAN_SHADE = 6
 };
 int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value);
 

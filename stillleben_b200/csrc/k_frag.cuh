@@ -294,6 +294,7 @@ static __device__ __noinline__ void interpolate_general(const DFrame& f, const D
 // weights sum to one, and a third of the arithmetic; normals and sticker coordinates are non-linear per vertex
 // and stay per vertex. dFdx / dFdy of uv come from the 2x2 quad partner evaluated on the same primitive
 // (helper invocation); its edge-function values are the pixel's own plus / minus one exact integer step.
+template <bool LEAN = false>
 __device__ __forceinline__ void shade_inputs(const DFrame& f, const DDraw& d, const SubTri& st, const PolyV& a, const PolyV& b,
                                              const PolyV& c, const uint32_t vi[3], const float4 pm[3], bool unit_basis, int px, int py,
                                              bool want_derivs, FragIn& in, float bary[3], uint32_t vid[3]) {
@@ -317,7 +318,7 @@ __device__ __forceinline__ void shade_inputs(const DFrame& f, const DDraw& d, co
         in.nW = in.nW + normalize3(mul_m3(d.normalToWorld, mk3(a0.z, a0.w, a1.x))) * w;
         ux += a0.x * bx[j]; vx += a0.y * bx[j]; uy += a0.x * by[j]; vy += a0.y * by[j];
     }
-    if (d.flags & DRAW_AFFINE) {
+    if (LEAN || (d.flags & DRAW_AFFINE)) {
         const float mx = pm[0].x * bary[0] + pm[1].x * bary[1] + pm[2].x * bary[2];
         const float my = pm[0].y * bary[0] + pm[1].y * bary[1] + pm[2].y * bary[2];
         const float mz = pm[0].z * bary[0] + pm[1].z * bary[1] + pm[2].z * bary[2];
@@ -332,7 +333,7 @@ __device__ __forceinline__ void shade_inputs(const DFrame& f, const DDraw& d, co
                     V[2] * in.wc.x + V[6] * in.wc.y + V[10] * in.wc.z + V[14]);
         in.objc = make_float4(ox, oy, oz, in.cc.z);
         in.su = in.sv = -1.0f;
-        if (d.sticker) {   // projective per vertex (render_shader.vert:86-92), then interpolated
+        if (!LEAN && d.sticker) {   // projective per vertex (render_shader.vert:86-92), then interpolated
             in.su = in.sv = 0.f;
             for (int j = 0; j < 3; ++j) {
                 const float qx = M[0] * pm[j].x + M[4] * pm[j].y + M[8] * pm[j].z + M[12], qy = M[1] * pm[j].x + M[5] * pm[j].y + M[9] * pm[j].z + M[13],
@@ -342,7 +343,7 @@ __device__ __forceinline__ void shade_inputs(const DFrame& f, const DDraw& d, co
                 in.sv += (sp.y / sp.w - d.stickerRange[1]) / d.stickerRange[3] * bary[j];
             }
         }
-    } else {   // rare: copies, so that the out-of-line call does not pin `in`, `vi`, `bary` to local memory
+    } else if (!LEAN) {   // rare: copies, so that the out-of-line call does not pin `in`, `vi`, `bary` to local memory
         FragIn tmp;
         const uint32_t vi2[3] = {vi[0], vi[1], vi[2]};
         const float b2[3] = {bary[0], bary[1], bary[2]};
@@ -420,18 +421,22 @@ __device__ __forceinline__ float shadow_pcf16(const uint32_t* __restrict__ map, 
 }
 
 // fragment stage (render_shader.frag:225-412); the discards are evaluated by the rasteriser
+// LEAN = the sub-batch uses none of: normal / metallic-roughness / emissive / occlusion textures, stickers, light maps,
+// projective transformation chains (decided on the host per sub-batch). The lean instantiation compiles those paths
+// out: fewer live registers in the common case (base-colour textures, analytic lights, PCF shadows).
+template <bool LEAN = false>
 __device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, const FragIn& in, const uint32_t vi[3],
                                                const float bary[3], float4& out_color, float4& out_normal) {
     const float PI = 3.141592653589793f;
     float4 baseColor = base_color(d, in);
-    if (d.sticker && in.su >= 0 && in.sv >= 0 && in.su < 1 && in.sv < 1) {
+    if (!LEAN && d.sticker && in.su >= 0 && in.sv >= 0 && in.su < 1 && in.sv < 1) {
         float4 sc = to_linear(tex_sample_rect(*d.sticker, in.su * d.sticker->w, in.sv * d.sticker->h));
         float a = sc.w;
         baseColor = make_float4(baseColor.x * (1 - a) + sc.x * a, baseColor.y * (1 - a) + sc.y * a, baseColor.z * (1 - a) + sc.z * a,
                                 baseColor.w * (1 - a) + sc.w * a);
     }
     f3 normal;
-    if (d.tex[1]) {
+    if (!LEAN && d.tex[1]) {
         float4 t = sample_mat(d.tex[1], in);
         f3 tW, bW;
         {
@@ -452,12 +457,12 @@ __device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, 
     float NoV = clampf(dot3(normal, cameraDirection), 1e-5f, 1.0f);
 
     float roughness = d.roughness, metallic = d.metallic;
-    if (d.tex[2]) { float4 t = sample_mat(d.tex[2], in); roughness *= t.y; metallic *= t.z; }
+    if (!LEAN && d.tex[2]) { float4 t = sample_mat(d.tex[2], in); roughness *= t.y; metallic *= t.z; }
     roughness = fmaxf(roughness, 0.045f);
     float occlusion = 1.0f;
-    if (d.tex[4]) occlusion = sample_mat(d.tex[4], in).x;
+    if (!LEAN && d.tex[4]) occlusion = sample_mat(d.tex[4], in).x;
     f3 emissive = mk3(d.emissive[0], d.emissive[1], d.emissive[2]);
-    if (d.tex[3]) { float4 t = to_linear(sample_mat(d.tex[3], in)); emissive = emissive * mk3(t.x, t.y, t.z); }
+    if (!LEAN && d.tex[3]) { float4 t = to_linear(sample_mat(d.tex[3], in)); emissive = emissive * mk3(t.x, t.y, t.z); }
 
     f3 color = mk3(0.f, 0.f, 0.f);
     f3 bc = mk3(baseColor.x, baseColor.y, baseColor.z);
@@ -488,7 +493,7 @@ __device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, 
     }
     color = color + mk3(f.ambient[0], f.ambient[1], f.ambient[2]) * bc;
 
-    if (f.lm) {
+    if (!LEAN && f.lm) {
         const DLightMap& lm = *f.lm;
         float4 fab = lut_sample(lm, NoV, roughness);
         float4 rad = cube_sample_lod(lm.pre, 5, reflDir, roughness * 4.0f);

@@ -770,7 +770,7 @@ __device__ __forceinline__ uint32_t find_draw_by_prim(const DDraw* __restrict__ 
     return lo;
 }
 
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, bool LEAN>
 __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws) {
     const DFrame& f = frames[blockIdx.z];
     const int W = f.W, H = f.H;
@@ -813,11 +813,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
         const int how = fetch_subtri(f, d, seq, k, vi, pm, va, vb, vc);
         if (how && make_subtri(va.X, va.Y, vb.X, vb.Y, vc.X, vc.Y, va.z, vb.z, vc.z, st)) {
             FragIn in; float bary[3]; uint32_t vid[3];
-            shade_inputs(f, d, st, va, vb, vc, vi, pm, how == 1, px, py, draw_has_textures(d), in, bary, vid);
+            shade_inputs<LEAN>(f, d, st, va, vb, vc, vi, pm, how == 1, px, py, LEAN ? d.tex[0] != nullptr : draw_has_textures(d), in, bary, vid);
             // geometry targets first: their registers are free before the lighting code runs
             store_geometry(in.objc, (unsigned short)d.class_index, (unsigned short)d.instance_index, make_uint4(vid[0], vid[1], vid[2], 0u),
                            make_float4(bary[0], bary[1], bary[2], 1.0f), make_float4(in.cc.x, in.cc.y, in.cc.z, 1.0f));
-            fragment_stage(f, d, in, vi, bary, hdr, nrm);
+            fragment_stage<LEAN>(f, d, in, vi, bary, hdr, nrm);
             shaded = true;
         }
     }
@@ -867,11 +867,13 @@ void launch_raster(bool frag_test, const DView* views, const DFrame* frames, con
     if (frag_test) k_raster<true><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(views, frames, draws, active, pairs, g);
     else k_raster<false><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(views, frames, draws, active, pairs, g);
 }
-void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, cudaStream_t s) {
+void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, bool lean, cudaStream_t s) {
     // 256 threads = 32 x 8 pixels. Launch bounds measured on B200 (ms per 1024-frame step): (256,2) 118 regs 43.8,
     // (128,5) 96 regs 39.4, (256,3) 80 regs 36.3, (256,4) 64 regs 33.4 — the kernel is latency bound, occupancy wins
     // even with ~150 B of spills.
-    k_shade<256, 4><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
+    // `lean`: no material textures beyond base colour, no stickers, no light map, affine chains only (see fragment_stage)
+    if (lean) k_shade<256, 4, true><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
+    else k_shade<256, 4, false><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
 }
 
 }  // namespace slbk

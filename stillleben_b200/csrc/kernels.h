@@ -18,7 +18,7 @@ void launch_scan(uint32_t* count, uint32_t* off, ActiveTile* active, unsigned lo
 struct RasterGrid { uint32_t n_active, n_cam_tiles, tiles_per_cam, n_cam_views, tiles_per_shadow; };
 void launch_raster(bool frag_test, const DView* views, const DFrame* frames, const DDraw* draws, const ActiveTile* active,
                    const PairRec* pairs, RasterGrid g, cudaStream_t s);
-void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, cudaStream_t s);
+void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, bool lean, cudaStream_t s);
 
 // k_post.cu
 void upload_ssao_tables(const float* noise16x3, const float* kernel64x3);

@@ -74,6 +74,7 @@ struct slb_ctx {
     // largest pixel box (in pixels) the setup kernel rasterises directly with one thread / with one warp; larger
     // triangles take the tiled path (tunables: env SLB_DIRECT_MAX, SLB_WARP_MAX)
     int direct_max = 128, warp_max = 4096;
+    bool lean_shade = true;
     slb_stats stats;
     // assets owned by the context
     slb_mesh* plane = nullptr;
@@ -236,6 +237,7 @@ extern "C" int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value) {
             if (value < 0 || value > 4096) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "SLB_OPT_DIRECT_MAX / SLB_OPT_WARP_MAX must be in [0, 4096]");
             (option == SLB_OPT_DIRECT_MAX ? ctx->direct_max : ctx->warp_max) = (int)value;
             return SLB_OK;
+        case SLB_OPT_LEAN_SHADE: ctx->lean_shade = value != 0; return SLB_OK;
         default: return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -626,6 +628,7 @@ struct Batch {
     uint32_t n_chunks = 0, n_shadow_maps = 0;
     uint64_t n_tris = 0;
     bool fused = true, any_ssao = false, any_auto = false, any_bg = false, any_frag_test = false;
+    bool lean = true;                     // no draw needs the full-featured shade kernel (launch_shade)
 };
 
 static inline uint32_t chunks_of(uint32_t n_tris) { return (n_tris + SLB_SETUP_CHUNK - 1) / SLB_SETUP_CHUNK; }
@@ -805,6 +808,7 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
             if (frag_all) d.flags |= DRAW_FRAG_TEST;
             auto affine = [](const float* m) { return m[3] == 0.0f && m[7] == 0.0f && m[11] == 0.0f && m[15] == 1.0f; };
             if (affine(d.meshToObject) && affine(d.objectToWorld) && affine(f.V)) d.flags |= DRAW_AFFINE;
+            b.lean &= (d.flags & DRAW_AFFINE) && !d.tex[1] && !d.tex[2] && !d.tex[3] && !d.tex[4] && !d.sticker && !f.lm;
             b.any_frag_test |= (d.flags & DRAW_FRAG_TEST) != 0;
             b.n_tris += n_tris;
             DBinDraw bd; std::memset(&bd, 0, sizeof bd);
@@ -1061,7 +1065,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     }
     {
         StageTimer t(ctx, s, ST_SHADE);
-        launch_shade(frames_d, draws_d, n, W, H, s);
+        launch_shade(frames_d, draws_d, n, W, H, b.lean && ctx->lean_shade, s);
     }
     ctx->stats.kernel_launches += (b.n_chunks ? 1 : 0) + 3 + (n_survivors ? 1 : 0) + (n_huge ? 1 : 0) + (grid.n_active ? 1 : 0) + 1;
     if (post) {

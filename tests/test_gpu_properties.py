@@ -103,3 +103,25 @@ def test_raster_paths_agree_bit_exactly(gpu_ctx, batch):
     finally:
         gpu_ctx.set_option(abi.OPT_DIRECT_MAX, 128)
         gpu_ctx.set_option(abi.OPT_WARP_MAX, 4096)
+
+
+def test_lean_and_full_shade_kernels_agree(gpu_ctx, batch):
+    """Sub-batches without material textures / stickers / light maps run a lean instantiation of the shade kernel
+    (SLB_OPT_LEAN_SHADE): ids identical, float targets equal up to contraction differences, colour within 1 LSB."""
+    pool, scenes, res = batch
+    try:
+        gpu_ctx.set_option(abi.OPT_LEAN_SHADE, 0)
+        full = gpu_ctx.render(scenes[:4], target_mask=abi.TARGETS_ALL)
+        gpu_ctx.synchronize()
+    finally:
+        gpu_ctx.set_option(abi.OPT_LEAN_SHADE, 1)
+    for i in range(4):
+        a, b = res.frame_dict(i), full.frame_dict(i)
+        st = parity.compare(a, b)
+        for name, s_ in st.items():
+            if name in parity.EXACT:
+                assert s_["mismatch"] == 0, (name, s_)
+            elif name == "rgb":
+                assert s_["over1"] == 0, s_
+            else:
+                assert s_["bad"] == 0 and s_["max_abs"] < 1e-4 * 3000, (name, s_)
