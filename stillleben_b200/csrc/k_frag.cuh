@@ -390,11 +390,23 @@ __device__ __forceinline__ float GeometrySchlickGGX(float NdotV, float roughness
 // turned into an integer one ONCE: shadow_threshold() returns the smallest d24 whose float quotient
 // reaches ref (exact, the quotient is monotonic in d24) and every tap compares integers.
 __device__ __forceinline__ uint32_t shadow_threshold(float ref) {
-    if (!(ref == ref)) return 0x1000000u;              // NaN never passes
-    ref = clampf(ref, 0.0f, 1.0f);
-    int d = max(0, (int)floorf(ref * 16777215.0f) - 2);
-    while (d <= 0xFFFFFF && __fdiv_rn((float)d, 16777215.0f) < ref) ++d;
-    return (uint32_t)d;
+    // Closed form of "smallest d24 with fl32(d24 / 16777215) >= ref": the rounded quotient reaches ref exactly when
+    // d24 / C lies at or above the midpoint between ref and its float predecessor (on the midpoint itself only if
+    // ties-to-even lands on ref, i.e. ref's mantissa is even). With midpoint = P * 2^-s (P odd, < 2^25) this is
+    // d24 >= ceil(C * P / 2^s) in 64-bit integers — no division, no search loop. NaN never passes (0x1000000).
+    if (!(ref == ref)) return 0x1000000u;
+    const uint32_t bits = __float_as_uint(clampf(ref, 0.0f, 1.0f)) & 0x7FFFFFFFu;
+    if (bits == 0u) return 0u;
+    const uint32_t e = bits >> 23, m = bits & 0x7FFFFFu;
+    uint32_t P; int s; bool odd;
+    if (e == 0u) { P = 2u * m - 1u; s = 150; odd = m & 1u; }                                  // denormal
+    else if (m) { const uint32_t M = m | 0x800000u; P = 2u * M - 1u; s = 151 - (int)e; odd = M & 1u; }
+    else { P = 0x1FFFFFFu; s = 152 - (int)e; odd = false; }                                  // power of two: the predecessor is half as far
+    if (s >= 62) return 1u;
+    const unsigned long long N = 16777215ull * P, mask = (1ull << s) - 1ull;
+    uint32_t d = (uint32_t)((N + mask) >> s);
+    if ((N & mask) == 0ull && odd) ++d;
+    return d;
 }
 // 4x4 PCF taps at offsets {-1.5,-0.5,0.5,1.5} texels, each a 2x2 bilinear filter of the comparison: the 16
 // taps share their fractional position, so the sum separates into weights (1-a, 1, 1, 1, a) x (1-b, 1, 1, 1, b)
@@ -414,10 +426,10 @@ __device__ __forceinline__ float shadow_pcf16(const uint32_t* __restrict__ map, 
         float r = 0.0f;
 #pragma unroll
         for (int ii = 0; ii < 5; ++ii)
-            r += (min(__ldg(row + min(max(i0 + ii, 0), N - 1)), 0xFFFFFFu) >= thr) ? wx[ii] : 0.0f;
+            r += (__ldg(row + min(max(i0 + ii, 0), N - 1)) >= thr) ? wx[ii] : 0.0f;   // untouched texels hold 0xFFFFFFFF: lit
         sum += r * wy[jj];
     }
-    return sum * (1.0f / 16.0f);
+    return thr > 0xFFFFFFu ? 0.0f : sum * (1.0f / 16.0f);   // NaN reference: no tap passes
 }
 
 // fragment stage (render_shader.frag:225-412); the discards are evaluated by the rasteriser
