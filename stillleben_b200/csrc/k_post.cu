@@ -15,16 +15,17 @@ using namespace slbk;
 __constant__ float c_ssao_noise[16 * 3];
 __constant__ float c_ssao_kernel[64 * 3];
 
-// linear-filtered rectangle-texture read of an RGBA32F image (clamp-to-edge), z component only
-__device__ __forceinline__ float rect_linear_z(const float4* __restrict__ img, int W, int H, float xs, float ys) {
+// linear-filtered rectangle-texture read of the z component of the camCoordinates image (clamp-to-edge), served
+// from the dense z plane the shade kernel writes next to it
+__device__ __forceinline__ float rect_linear_z(const float* __restrict__ img, int W, int H, float xs, float ys) {
     float x = xs - 0.5f, y = ys - 0.5f;
     float fx = floorf(x), fy = floorf(y);
     float a = x - fx, b = y - fy;
     int i0 = (int)fx, j0 = (int)fy;
     int i1 = min(max(i0 + 1, 0), W - 1), j1 = min(max(j0 + 1, 0), H - 1);
     i0 = min(max(i0, 0), W - 1); j0 = min(max(j0, 0), H - 1);
-    float z00 = __ldg(&img[(size_t)j0 * W + i0].z), z10 = __ldg(&img[(size_t)j0 * W + i1].z);
-    float z01 = __ldg(&img[(size_t)j1 * W + i0].z), z11 = __ldg(&img[(size_t)j1 * W + i1].z);
+    float z00 = __ldg(&img[(size_t)j0 * W + i0]), z10 = __ldg(&img[(size_t)j0 * W + i1]);
+    float z01 = __ldg(&img[(size_t)j1 * W + i0]), z11 = __ldg(&img[(size_t)j1 * W + i1]);
     return z00 * ((1 - a) * (1 - b)) + z10 * (a * (1 - b)) + z01 * ((1 - a) * b) + z11 * (a * b);
 }
 
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256) k_ssao(const DFrame* __restrict__ frames)
         const float ow = base[2] + ct[2] * sx + cb[2] * sy + cn[2] * sz;
         const float sample_z = fragPos.z + zt * sx + zb * sy + zn * sz;
         const float inv = 1.0f / ow;
-        float sampleDepth = rect_linear_z(f.scratch_cam, W, H, ox * inv * hw + hw, oy * inv * hh + hh);
+        float sampleDepth = rect_linear_z(f.zplane, W, H, ox * inv * hw + hw, oy * inv * hh + hh);
         float rangeCheck = smoothstep01(0.1f / fabsf(fragPos.z - sampleDepth));
         occlusion += (sampleDepth <= sample_z - 0.0025f ? 1.0f : 0.0f) * rangeCheck;
     }
@@ -138,14 +139,14 @@ __global__ void __launch_bounds__(256) k_ssao_apply_tonemap(const DFrame* __rest
     const size_t p = (size_t)py * W + px;
     float4 hdr = f.hdr[p];
     if (f.ssao) {
-        float center_d = rect_linear_z(f.scratch_cam, W, H, (float)px, (float)py);
+        float center_d = rect_linear_z(f.zplane, W, H, (float)px, (float)py);
         float result = 0.0f, w_total = 0.0f;
         const float BlurSigma = 3.0f * 0.5f, BlurFalloff = 1.0f / (2.0f * BlurSigma * BlurSigma);
         for (int x = -2; x < 2; ++x)
             for (int y = -2; y < 2; ++y) {
                 int ux = px + x, uy = py + y;
                 float c = (ux >= 0 && ux < W && uy >= 0 && uy < H) ? f.ao[(size_t)uy * W + ux] : 0.0f;
-                float dd = rect_linear_z(f.scratch_cam, W, H, (float)ux, (float)uy);
+                float dd = rect_linear_z(f.zplane, W, H, (float)ux, (float)uy);
                 float r = sqrtf((float)(x * x + y * y));
                 float ddiff = (dd - center_d) * 300.0f;
                 float w = exp2f(-r * r * BlurFalloff - ddiff * ddiff);

@@ -794,6 +794,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
         if (uint4* o = reinterpret_cast<uint4*>(f.out[SLB_TARGET_VERTEX_INDEX])) o[p] = vidx;
         if (float4* o = reinterpret_cast<float4*>(f.out[SLB_TARGET_BARY])) o[p] = bary4;
         if (f.scratch_cam) f.scratch_cam[p] = cam;   // == out[CAM_COORD] when requested
+        if (f.zplane) f.zplane[p] = cam.z;
     };
 
     float4 hdr = make_float4(0.f, 0.f, 0.f, 0.f);

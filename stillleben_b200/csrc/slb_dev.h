@@ -112,6 +112,7 @@ struct DFrame {
     float4* hdr;                   // H*W pre-tone-map colour (post-pass path only)
     float4* scratch_normal;        // used by SSAO when the normal / cam-coord targets are not requested
     float4* scratch_cam;
+    float* zplane;                 // camera-space z of every pixel as a dense plane (SSAO taps: 8 pixels per 32-byte sector instead of 2)
     float* ao;
     float* avg;                    // 4 floats: 1x1 mip level for auto exposure
     void* out[SLB_NUM_TARGETS];    // this frame's slice of each requested target (null = not requested)

@@ -82,7 +82,7 @@ struct slb_ctx {
     DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, survivors;
     DevBuf clip_recs, clip_counts, diff_params, diff_partial, cam_params, cam_mid, png_rows, png_info, png_offsets;
     bool png_tables = false;
-    DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, ao, avg, mip_a, mip_b, shadow_maps;
+    DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, zplane, ao, avg, mip_a, mip_b, shadow_maps;
     // pinned staging
     void* staging = nullptr; size_t staging_cap = 0;
     uint32_t* total_pinned = nullptr;
@@ -210,7 +210,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
         if (ctx->slot_copied[i]) cudaEventDestroy(ctx->slot_copied[i]);
     }
     DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->survivors, &ctx->diff_params, &ctx->diff_partial, &ctx->cam_params, &ctx->cam_mid, &ctx->png_rows, &ctx->png_info, &ctx->png_offsets, &ctx->tile_count,
-                      &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->ao,
+                      &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->zplane, &ctx->ao,
                       &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ctx->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -958,6 +958,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
         CU(ctx->avg.reserve((size_t)n * 16));
         if (!result->ptrs[SLB_TARGET_NORMAL] && b.any_ssao) CU(ctx->scratch_normal.reserve(npx * n * 16));
         if (!result->ptrs[SLB_TARGET_CAM_COORD] && b.any_ssao) CU(ctx->scratch_cam.reserve(npx * n * 16));
+        if (b.any_ssao) CU(ctx->zplane.reserve(npx * n * 4));
         if (b.any_auto) { CU(ctx->mip_a.reserve((npx / 4 + W + H + 4) * n * 16)); CU(ctx->mip_b.reserve((npx / 16 + W + H + 4) * n * 16)); }
     }
     // ---- patch device pointers into the host arrays ----
@@ -980,6 +981,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
             f.avg = ctx->avg.as<float>() + 4 * j;
             if (!f.scratch_normal && b.any_ssao) f.scratch_normal = ctx->scratch_normal.as<float4>() + npx * j;
             if (!f.scratch_cam && b.any_ssao) f.scratch_cam = ctx->scratch_cam.as<float4>() + npx * j;
+            if (b.any_ssao) f.zplane = ctx->zplane.as<float>() + npx * j;
         }
     }
     for (uint32_t sidx = 0; sidx < b.n_shadow_maps; ++sidx) b.views[n + sidx].out = smaps + smap_elems * sidx;
