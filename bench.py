@@ -130,6 +130,7 @@ def main():
     from stillleben_b200 import dist as sdist
 
     rank, world, local = sdist.env_rank_world()
+    numa_node = sdist.bind_to_gpu_numa_node(local) if world > 1 else None   # host buffers next to the rank's GPU
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -243,7 +244,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"C3: fixed batch of {args.scenes} scenes x {N_OBJECTS} objects ({POOL}-mesh pool, 16384 tris each), "
                                    f"{W}x{H}, six targets (40 B/px), 1 shadow light + ambient, exposure 1, SSAO off",
-                       "scenes_per_gpu": n_local, "subbatch": args.subbatch or 64,
+                       "scenes_per_gpu": n_local, "subbatch": args.subbatch or 64, "rank0_numa_node": numa_node,
                        "l2": "outputs per step (%.1f GB) exceed L2; no flush needed" % (n_local * W * H * BYTES_PER_PX / 1e9)},
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "stage_ms_per_step": {n: float(v / args.steps) for n, v in zip(names, stage_ms)},

@@ -101,4 +101,19 @@ inline void mvp(const Mat4& P, const Mat4& V, const Mat4& world, const Mat4& pre
     for (int i = 0; i < 16; ++i) out[i] = (float)r[i];
 }
 
+// The same products with the double-precision operands kept by the caller (the frame's P and V and an object's
+// world * pre are shared by many draws): bit-identical to mvp(). `v == nullptr` stands for V = identity, whose
+// product is exact and is skipped.
+inline void to_double(const Mat4& a, double* o) { for (int i = 0; i < 16; ++i) o[i] = a.m[i]; }
+inline void world_pre_d(const Mat4& world, const Mat4& pre, double* mw) {
+    double w[16], m[16];
+    to_double(world, w); to_double(pre, m);
+    mul44d(w, m, mw);
+}
+inline void mvp_d(const double* p, const double* v, const double* mw, float* out) {
+    double mc[16], r[16];
+    if (v) { mul44d(v, mw, mc); mul44d(p, mc, r); } else mul44d(p, mw, r);
+    for (int i = 0; i < 16; ++i) out[i] = (float)r[i];
+}
+
 }  // namespace hm

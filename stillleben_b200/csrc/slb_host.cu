@@ -620,6 +620,12 @@ extern "C" void slb_result_destroy(slb_ctx* ctx, slb_result* res) {
 namespace {
 
 struct Batch {
+    void clear() {   // keeps the capacity of every array: a context marshals thousands of sub-batches
+        frames.clear(); draws.clear(); views.clear(); bdraws.clear(); chunk_draw.clear(); world_pre.clear();
+        n_chunks = n_shadow_maps = 0; n_tris = 0;
+        fused = true; any_ssao = any_auto = any_bg = any_frag_test = false; lean = true;
+    }
+    std::vector<double> world_pre;        // per (object, sub-mesh) of the current frame: world * pre in double (shared by its views)
     std::vector<DFrame> frames;
     std::vector<DDraw> draws;
     std::vector<DView> views;             // camera views [0, n) then shadow views
@@ -755,6 +761,16 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
     const int tiles_x = (W + SLB_TILE - 1) / SLB_TILE, tiles_y = (H + SLB_TILE - 1) / SLB_TILE;
     b.frames.resize(n);
     b.views.resize(n);
+    {   // exact sizes up front: no reallocation while the draw lists grow
+        size_t n_draws = 0, n_bdraws = 0, n_chunks = 0;
+        for (int j = 0; j < n; ++j) {
+            size_t subs = 0, chunks = 0;
+            for (int i = 0; i < scenes[j].n_objects; ++i)
+                for (const slb_submesh& sm : scenes[j].objects[i].mesh->submeshes) { ++subs; chunks += chunks_of(sm.index_count / 3); }
+            n_draws += subs + 1; n_bdraws += subs * (1 + SLB_NUM_LIGHTS) + 1; n_chunks += chunks * (1 + SLB_NUM_LIGHTS) + 1;
+        }
+        b.draws.reserve(n_draws); b.bdraws.reserve(n_bdraws); b.chunk_draw.reserve(n_chunks);
+    }
     for (int j = 0; j < n; ++j) {
         const slb_scene_desc& sc = scenes[j];
         DFrame& f = b.frames[j];
@@ -767,6 +783,9 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
             cv.tile_base = (uint32_t)j * tiles_x * tiles_y; cv.shadow = 0; cv.frame = (uint32_t)j;
         }
         Mat4 P = load(sc.projection), V = load(sc.world_to_cam);
+        double Pd[16], Vd[16];
+        to_double(P, Pd); to_double(V, Vd);
+        b.world_pre.clear();
         std::memcpy(f.P, P.m, 64); std::memcpy(f.V, V.m, 64);
         Mat4 Pinv = inverted(P); std::memcpy(f.Pinv, Pinv.m, 64);
         Mat4 camToWorld = inverted_rigid(V);
@@ -803,7 +822,10 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
             d.n_tris = n_tris; d.prim_base = prim; prim += n_tris;
             d.frame = (uint32_t)j;
             Mat4 o2w = load(d.objectToWorld), m2o = load(d.meshToObject);
-            mvp(P, V, o2w, m2o, d.mvp);
+            double mw[16];
+            world_pre_d(o2w, m2o, mw);                       // kept for this object's shadow views (same operands, same bits)
+            b.world_pre.insert(b.world_pre.end(), mw, mw + 16);
+            mvp_d(Pd, Vd, mw, d.mvp);
             normal_matrix(mul(o2w, m2o), d.normalToWorld);
             if (frag_all) d.flags |= DRAW_FRAG_TEST;
             auto affine = [](const float* m) { return m[3] == 0.0f && m[7] == 0.0f && m[11] == 0.0f && m[15] == 1.0f; };
@@ -892,15 +914,22 @@ static void build_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, const
                 const uint32_t view_index = (uint32_t)n + slot;
                 b.views.push_back(sv);
                 uint32_t sprim = 0;
+                double smd[16];
+                to_double(sm, smd);
+                size_t wp = (f.draw_end - f.draw_begin) - [&] {   // first world * pre entry of an object: after the plane's, if drawn
+                    size_t subs = 0;
+                    for (int i = 0; i < sc.n_objects; ++i) if (sc.objects[i].visible) subs += sc.objects[i].mesh->submeshes.size();
+                    return subs; }();
                 for (int i = 0; i < sc.n_objects; ++i) {
                     const slb_object_desc& o = sc.objects[i];
-                    if (!o.visible || !o.casts_shadows) continue;
+                    if (!o.visible) continue;
                     const slb_mesh* mesh = o.mesh;
+                    if (!o.casts_shadows) { wp += mesh->submeshes.size(); continue; }
                     for (const slb_submesh& sub : mesh->submeshes) {
                         DBinDraw bd; std::memset(&bd, 0, sizeof bd);
                         bd.pos4 = mesh->pos4; bd.idx = mesh->idx + sub.index_offset; bd.n_tris = sub.index_count / 3;
                         bd.prim_base = sprim; sprim += bd.n_tris; bd.view = view_index;
-                        mvp(sm, identity(), load(o.pose), load(o.pretransform), bd.mvp);
+                        mvp_d(smd, nullptr, b.world_pre.data() + 16 * wp++, bd.mvp);   // == mvp(sm, identity, pose, pretransform)
                         bd.chunk_base = b.n_chunks; b.n_chunks += chunks_of(bd.n_tris);
                         b.chunk_draw.insert(b.chunk_draw.end(), chunks_of(bd.n_tris), (uint32_t)b.bdraws.size());
                         b.bdraws.push_back(bd);
@@ -925,7 +954,8 @@ struct StageTimer {
 
 static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, slb_result* result, int first_frame,
                            const slb_result* depth_peel, cudaStream_t s) {
-    Batch b;
+    static thread_local Batch b;   // arrays keep their capacity from one sub-batch to the next
+    b.clear();
     build_batch(ctx, scenes, n, result, first_frame, depth_peel, b);
     const int W = result->W, H = result->H;
     const size_t npx = (size_t)W * H;

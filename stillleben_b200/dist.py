@@ -106,3 +106,40 @@ def broadcast_meshes(meshes, src=0, device=None):
         return meshes
     host = payload.cpu().numpy()
     return unpack_meshes(host[:hn].tobytes(), host[hn:])
+
+
+# ---- host placement ---------------------------------------------------------------------------
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated.
+
+    With one process per GPU the descriptor marshalling and — more importantly — the page-locked result buffers of
+    `slb_render_batch_host` should live next to the GPU: first-touch places them on the node of the allocating
+    CPU, and a device->host copy into the other socket's memory crosses the inter-socket link that all remote
+    GPUs share. Returns the NUMA node used, or None when the topology cannot be read (then nothing changes)."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        node_path = f"/sys/bus/pci/devices/{bus}/numa_node"
+        node = int(open(node_path).read().strip())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
