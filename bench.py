@@ -134,6 +134,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     # ---- load: rank 0 builds the pool, ONE broadcast of the asset arena ----
     pool = synth.mesh_pool(POOL) if rank == 0 else None
