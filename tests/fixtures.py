@@ -168,10 +168,25 @@ def variant(name, width=320, height=240):
         sc.objects[0].instance_index = 65535
         sc.objects[0].class_index = 65535
         return sc
+    if name == "multi_submesh":
+        # one mesh drawn as two sub-meshes with different materials (per-sub-mesh draws, shared vertex buffer); one of
+        # its instances does not cast shadows, another object is hidden: exercises the draw / shadow-draw bookkeeping
+        sc = synth.tabletop_scene(pool, 26, n_lights=2, **base)
+        src = sc.objects[0].mesh
+        n_idx = len(src.indices)
+        cut = (n_idx // 6) * 3
+        mats = [src.materials[0], MaterialData(base_color=(0.9, 0.2, 0.1, 1.0), metallic=0.3, roughness=0.7)]
+        two = MeshData(src.vertices, src.indices, [(0, cut, 0), (cut, n_idx - cut, 1)], mats, list(src.images), name="two_materials")
+        for k in (0, 2, 4):
+            sc.objects[k].mesh = two
+            sc.objects[k].pretransform = synth.normalising_pretransform(two, 0.25)
+        sc.objects[2].casts_shadows = False
+        sc.objects[3].visible = False
+        return sc
     if name == "odd_viewport":
         return synth.tabletop_scene(pool, 25, n_objects=5, width=203, height=117, intrinsics=None)
     raise KeyError(name)
 
 
 VARIANTS = ["tabletop", "three_lights", "ssao", "auto_exposure", "no_plane_no_light", "empty", "ibl", "alpha_test", "sticker",
-            "background_image", "plane_texture", "near_clip", "predicate", "id_limits", "odd_viewport"]
+            "background_image", "plane_texture", "near_clip", "predicate", "id_limits", "odd_viewport", "multi_submesh"]
