@@ -288,7 +288,11 @@ enum {
     SLB_OPT_WARP_MAX = 5,
     /* 1 (default): sub-batches that use no normal / metallic-roughness / emissive / occlusion textures, stickers,
      * light maps or projective transformations run the lean instantiation of the shade kernel; 0: always the full one. */
-    SLB_OPT_LEAN_SHADE = 6
+    SLB_OPT_LEAN_SHADE = 6,
+    /* 1 (default): the first few huge sub-triangles of a camera view (the background plane, close-up faces) are
+     * resolved per pixel inside the shade kernel instead of being tile-binned; 0: everything large is tile-binned.
+     * Results are bit-identical. */
+    SLB_OPT_HUGE_IN_SHADE = 7
 };
 int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value);
 

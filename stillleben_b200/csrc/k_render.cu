@@ -175,6 +175,25 @@ __device__ __forceinline__ void append_huge(const SurvOut& so, const PairRec& re
     const uint32_t at = atomicAdd(&so.counters[2], 1u);
     if (at < so.huge_cap) so.survivors[so.normal_cap + at] = rec; else atomicExch(&so.counters[1], 1u);
 }
+// Camera views resolve their first SLB_HUGE_PER_VIEW huge sub-triangles (the background plane, close-up faces) per
+// pixel in the shade kernel: no tile counting, no pairs, no raster warp for them. Returns false when the view has no
+// slot left (or the feature is off): the caller then sends the record down the tiled path; both routes merge by min.
+// (out of line and by value: rare, and the caller's record must not be pinned to local memory)
+static __device__ __noinline__ bool claim_huge_slot(HugeRec* huge, uint32_t* huge_n, const PairRec rec, int px0, int py0, int px1, int py1) {
+    if (!huge || (rec.k_flags & 0x100u)) return false;   // fragment-tested draws need the raster's discard logic
+    const uint32_t slot = atomicAdd(huge_n, 1u);
+    if (slot >= SLB_HUGE_PER_VIEW) return false;
+    SubTri st;
+    make_subtri(rec.ax, rec.ay, rec.bx, rec.by, rec.cx, rec.cy, rec.az, rec.bz, rec.cz, st);
+    HugeRec h;
+    h.ax = st.ax; h.ay = st.ay; h.bx = st.bx; h.by = st.by; h.cx = st.cx; h.cy = st.cy;
+    h.az = st.az; h.bz = st.bz; h.cz = st.cz; h.s = st.s; h.inv2A = st.inv2A;
+    h.bias0 = st.bias0; h.bias1 = st.bias1; h.bias2 = st.bias2;
+    h.seq = rec.seq; h.kbyte = rec.k_flags & 0xffu;
+    h.px0 = (int16_t)px0; h.py0 = (int16_t)py0; h.px1 = (int16_t)px1; h.py1 = (int16_t)py1;
+    huge[slot] = h;
+    return true;
+}
 __device__ __forceinline__ int tiles_of_box(int px0, int py0, int px1, int py1) {
     return (px1 / SLB_TILE - px0 / SLB_TILE + 1) * (py1 / SLB_TILE - py0 / SLB_TILE + 1);
 }
@@ -203,10 +222,13 @@ static __device__ __noinline__ void setup_clipped_prim(const float* mvp, float3 
     for (int k = 1; k + 1 < ps.n; ++k) {
         const PolyV &a = ps.v[0], &b = ps.v[k], &c = ps.v[k + 1];
         PairRec rec;
-        if (setup_subtri_count(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, (uint32_t)k | slot_bits | flags, draw, v, tile_count, s_big, s_nbig, rec)) {
-            int px0, py0, px1, py1;
-            pixel_box(a.X, a.Y, b.X, b.Y, c.X, c.Y, v.W, v.H, px0, py0, px1, py1);
-            if (tiles_of_box(px0, py0, px1, py1) > SLB_HUGE_TILES) { append_huge(so, rec); continue; }
+        long long twoA; int px0, py0, px1, py1;
+        if (!survivor_test(a.X, a.Y, b.X, b.Y, c.X, c.Y, a.z, b.z, c.z, seq, (uint32_t)k | slot_bits | flags, draw, v, rec, twoA, px0, py0, px1, py1))
+            continue;
+        const bool huge = tiles_of_box(px0, py0, px1, py1) > SLB_HUGE_TILES;
+        if (huge && claim_huge_slot(v.huge, v.huge_n, rec, px0, py0, px1, py1)) continue;   // resolved in the shade kernel
+        if (bin_tiles<false>(rec, twoA, px0, py0, px1, py1, v.W, v.H, v.tiles_x, v.tile_base, tile_count, nullptr, nullptr, 0, s_big, s_nbig) > 0) {
+            if (huge) { append_huge(so, rec); continue; }
             uint32_t at = atomicAdd(&so.counters[0], 1u);
             if (at < so.normal_cap) so.survivors[at] = rec; else atomicExch(&so.counters[1], 1u);
         }
@@ -338,10 +360,10 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 5) k_setup(const DView* __res
                         } else if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= 2) {   // one or two tiles: counted warp-aggregated below
                             has_rec = true;
                             dt0 = v.tile_base + ty0 * v.tiles_x + tx0; dt1 = v.tile_base + ty1 * v.tiles_x + tx1;
-                        } else {
+                        } else if (!claim_huge_slot(v.huge, v.huge_n, rec, px0, py0, px1, py1)) {   // more than two tiles: huge
                             has_rec = bin_tiles<false>(rec, twoA, px0, py0, px1, py1, v.W, v.H, v.tiles_x, v.tile_base, tile_count, nullptr, nullptr,
                                                        0, s_big, &s_nbig) > 0;
-                            if (has_rec && (tx1 - tx0 + 1) * (ty1 - ty0 + 1) > SLB_HUGE_TILES) { append_huge(so, rec); has_rec = false; }
+                            if (has_rec) { append_huge(so, rec); has_rec = false; }
                         }
                     }
                 }
@@ -785,7 +807,24 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
     const int px = blockIdx.x * 32 + (wq % WPR) * WW + (lq % WW), py = blockIdx.y * 8 + (wq / WPR) * WH + (lq / WW);
     if (px >= W || py >= H) return;
     const size_t p = (size_t)py * W + px;
-    const unsigned long long key = f.keys[p];
+    unsigned long long key = f.keys[p];
+    if (f.huge) {   // huge sub-triangles of this view: coverage (C6) and depth (C7) evaluated here, merged by minimum
+        const int nh = min((int)__ldg(f.huge_n), SLB_HUGE_PER_VIEW);
+        for (int i = 0; i < nh; ++i) {
+            const HugeRec& h = f.huge[i];
+            if (px < h.px0 || px > h.px1 || py < h.py0 || py > h.py1) continue;
+            SubTri st;
+            st.ax = h.ax; st.ay = h.ay; st.bx = h.bx; st.by = h.by; st.cx = h.cx; st.cy = h.cy;
+            st.az = h.az; st.bz = h.bz; st.cz = h.cz; st.s = h.s; st.inv2A = h.inv2A;
+            st.bias0 = h.bias0; st.bias1 = h.bias1; st.bias2 = h.bias2; st.twoA = h.s;
+            long long w0, w1, w2;
+            subtri_weights(st, px, py, w0, w1, w2);
+            if (!subtri_covers(st, w0, w1, w2)) continue;
+            const unsigned long long cand = ((unsigned long long)subtri_depth24(st, w1, w2) << 40) | ((unsigned long long)h.seq << 8) | h.kbyte;
+            key = min(key, cand);
+        }
+        if (nh && !f.fused_tonemap) f.keys[p] = key;   // the post passes (sky box / background image) test coverage on the keys
+    }
     // the target pointers are fetched where they are used (not held in registers across the set-up code)
     auto store_geometry = [&](float4 coord, unsigned short cls, unsigned short inst, uint4 vidx, float4 bary4, float4 cam) {
         if (float4* o = reinterpret_cast<float4*>(f.out[SLB_TARGET_COORD])) o[p] = coord;

@@ -73,6 +73,20 @@ struct DBinDraw {
     uint32_t flags;                // DRAW_*
     float mvp[16];
 };
+// A huge sub-triangle of a camera view that is resolved per pixel inside the shade kernel instead of going through
+// count / scan / emit / raster: its prepared edge set-up (k_contract.cuh SubTri, 64 B), key bits and pixel box.
+#define SLB_HUGE_PER_VIEW 8        // more than this many per view: the rest takes the tiled path (both merge by minimum)
+struct __align__(16) HugeRec {
+    int32_t ax, ay, bx, by, cx, cy;
+    float az, bz, cz;
+    int32_t s;                     // orientation sign
+    float inv2A;
+    int32_t bias0, bias1, bias2;
+    uint32_t seq, kbyte;
+    int16_t px0, py0, px1, py1;    // pixel box (inclusive)
+};
+static_assert(sizeof(HugeRec) == 80, "HugeRec must be 80 bytes");
+
 struct DView {
     int32_t W, H, tiles_x, tiles_y;
     uint32_t tile_base;            // first tile of this view in the batch-wide tile arrays
@@ -80,6 +94,8 @@ struct DView {
     uint32_t frame;                // DFrame index (camera views)
     uint32_t pad;
     void* out;                     // uint64 keys[H*W] (camera) or uint32 d24[H*W] (shadow)
+    HugeRec* huge;                 // camera views: SLB_HUGE_PER_VIEW slots (null: feature off / shadow view)
+    uint32_t* huge_n;              // how many were claimed (may exceed the capacity: the excess went to the tiled path)
 };
 
 // A primitive that needed polygon clipping, written once by the binner so that the raster's fragment test
@@ -108,6 +124,8 @@ struct DFrame {
     const DTexture* bg_image;
     ClipRec* clip;                 // SLB_MAX_CLIP records
     uint32_t* clip_count;
+    const HugeRec* huge;           // this frame's huge sub-triangles, resolved per pixel by the shade kernel
+    const uint32_t* huge_n;
     uint64_t* keys;                // H*W visibility keys
     float4* hdr;                   // H*W pre-tone-map colour (post-pass path only)
     float4* scratch_normal;        // used by SSAO when the normal / cam-coord targets are not requested

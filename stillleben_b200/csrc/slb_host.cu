@@ -75,12 +75,13 @@ struct slb_ctx {
     // triangles take the tiled path (tunables: env SLB_DIRECT_MAX, SLB_WARP_MAX)
     int direct_max = 128, warp_max = 4096;
     bool lean_shade = true;
+    bool huge_in_shade = true;   // camera views resolve their first SLB_HUGE_PER_VIEW huge sub-triangles in the shade kernel
     slb_stats stats;
     // assets owned by the context
     slb_mesh* plane = nullptr;
     // per-batch device arrays
     DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, survivors;
-    DevBuf clip_recs, clip_counts, diff_params, diff_partial, cam_params, cam_mid, png_rows, png_info, png_offsets;
+    DevBuf clip_recs, clip_counts, huge_recs, huge_counts, diff_params, diff_partial, cam_params, cam_mid, png_rows, png_info, png_offsets;
     bool png_tables = false;
     DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, zplane, ao, avg, mip_a, mip_b, shadow_maps;
     // pinned staging
@@ -211,7 +212,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
     }
     DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->survivors, &ctx->diff_params, &ctx->diff_partial, &ctx->cam_params, &ctx->cam_mid, &ctx->png_rows, &ctx->png_info, &ctx->png_offsets, &ctx->tile_count,
                       &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->zplane, &ctx->ao,
-                      &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts};
+                      &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts, &ctx->huge_recs, &ctx->huge_counts};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ctx->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -238,6 +239,7 @@ extern "C" int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value) {
             (option == SLB_OPT_DIRECT_MAX ? ctx->direct_max : ctx->warp_max) = (int)value;
             return SLB_OK;
         case SLB_OPT_LEAN_SHADE: ctx->lean_shade = value != 0; return SLB_OK;
+        case SLB_OPT_HUGE_IN_SHADE: ctx->huge_in_shade = value != 0; return SLB_OK;
         default: return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -980,6 +982,8 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     CU(ctx->keys.reserve(npx * n * 8));
     CU(ctx->clip_recs.reserve((size_t)n * SLB_MAX_CLIP * sizeof(ClipRec)));
     CU(ctx->clip_counts.reserve((size_t)n * 4));
+    CU(ctx->huge_recs.reserve((size_t)n * SLB_HUGE_PER_VIEW * sizeof(HugeRec)));
+    CU(ctx->huge_counts.reserve((size_t)n * 4));
     CU(ctx->shadow_maps.reserve((size_t)b.n_shadow_maps * SLB_SHADOW_RES * SLB_SHADOW_RES * 4));
     const bool post = !b.fused;
     if (post) {
@@ -1000,6 +1004,10 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
         b.views[j].out = f.keys;
         f.clip = ctx->clip_recs.as<ClipRec>() + (size_t)j * SLB_MAX_CLIP;
         f.clip_count = ctx->clip_counts.as<uint32_t>() + j;
+        if (ctx->huge_in_shade) {
+            f.huge = ctx->huge_recs.as<HugeRec>() + (size_t)j * SLB_HUGE_PER_VIEW; f.huge_n = ctx->huge_counts.as<uint32_t>() + j;
+            b.views[j].huge = ctx->huge_recs.as<HugeRec>() + (size_t)j * SLB_HUGE_PER_VIEW; b.views[j].huge_n = ctx->huge_counts.as<uint32_t>() + j;
+        }
         f.fused_tonemap = b.fused ? 1 : 0;
         for (int li = 0; li < SLB_NUM_LIGHTS; ++li)
             f.shadowMap[li] = f.lightActive[li] ? smaps + smap_elems * (uintptr_t)f.shadowMap[li] : nullptr;
@@ -1043,6 +1051,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     const DBinDraw* bdraws_d = ctx->bdraws_d.as<DBinDraw>();
 
     CU(cudaMemsetAsync(ctx->clip_counts.p, 0, (size_t)n * 4, s));
+    CU(cudaMemsetAsync(ctx->huge_counts.p, 0, (size_t)n * 4, s));
     CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, s));
     {   // "nothing drawn": keys = all ones, shadow d24 >= 0xFFFFFF; only non-empty tiles get a raster warp
         StageTimer t(ctx, s, ST_SHADOW);
@@ -1080,6 +1089,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
         total_bin_tris = total_bin_tris * 2 + 65536;
         CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, s));
         CU(cudaMemsetAsync(ctx->clip_counts.p, 0, (size_t)n * 4, s));
+        CU(cudaMemsetAsync(ctx->huge_counts.p, 0, (size_t)n * 4, s));
     }
     total_pairs = ctx->total_pinned[0];
     grid.n_active = ctx->total_pinned[1];

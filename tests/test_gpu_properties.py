@@ -94,15 +94,17 @@ def test_raster_paths_agree_bit_exactly(gpu_ctx, batch):
     pool, scenes, res = batch
     ref = [digest(res, i) for i in range(6)]
     try:
-        for direct_max, warp_max in ((0, 0), (4096, 4096), (0, 4096), (16, 256)):
+        for direct_max, warp_max, huge in ((0, 0, 0), (4096, 4096, 1), (0, 4096, 0), (16, 256, 1), (128, 4096, 0), (0, 0, 1)):
             gpu_ctx.set_option(abi.OPT_DIRECT_MAX, direct_max)
             gpu_ctx.set_option(abi.OPT_WARP_MAX, warp_max)
+            gpu_ctx.set_option(abi.OPT_HUGE_IN_SHADE, huge)          # huge triangles per pixel in the shade kernel / tile-binned
             again = gpu_ctx.render(scenes[:6], target_mask=abi.TARGETS_ALL)
             gpu_ctx.synchronize()
-            assert [digest(again, i) for i in range(6)] == ref, (direct_max, warp_max)
+            assert [digest(again, i) for i in range(6)] == ref, (direct_max, warp_max, huge)
     finally:
         gpu_ctx.set_option(abi.OPT_DIRECT_MAX, 128)
         gpu_ctx.set_option(abi.OPT_WARP_MAX, 4096)
+        gpu_ctx.set_option(abi.OPT_HUGE_IN_SHADE, 1)
 
 
 def test_lean_and_full_shade_kernels_agree(gpu_ctx, batch):
