@@ -805,13 +805,26 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
     constexpr int WW = SLB_WARP_W, WH = 32 / WW, WPR = 32 / WW;   // warp block width / height, warps per block row
     const int wq = threadIdx.x >> 5, lq = threadIdx.x & 31;
     const int px = blockIdx.x * 32 + (wq % WPR) * WW + (lq % WW), py = blockIdx.y * 8 + (wq / WPR) * WH + (lq / WW);
+    // huge sub-triangles of this view (resolved per pixel below): staged once per block, only those whose pixel box
+    // meets the block's 32x8 pixels
+    __shared__ HugeRec s_huge[SLB_HUGE_PER_VIEW];
+    __shared__ int s_nh;
+    if (threadIdx.x == 0) s_nh = 0;
+    __syncthreads();
+    if (f.huge && threadIdx.x < SLB_HUGE_PER_VIEW && (int)threadIdx.x < min((int)__ldg(f.huge_n), SLB_HUGE_PER_VIEW)) {
+        const HugeRec h = f.huge[threadIdx.x];
+        const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * 8;
+        if (h.px1 >= bx0 && h.px0 <= bx0 + 31 && h.py1 >= by0 && h.py0 <= by0 + 7) s_huge[atomicAdd(&s_nh, 1)] = h;
+    }
+    __syncthreads();
     if (px >= W || py >= H) return;
     const size_t p = (size_t)py * W + px;
     unsigned long long key = f.keys[p];
-    if (f.huge) {   // huge sub-triangles of this view: coverage (C6) and depth (C7) evaluated here, merged by minimum
-        const int nh = min((int)__ldg(f.huge_n), SLB_HUGE_PER_VIEW);
+    {   // coverage (C6) and depth (C7) of the staged huge sub-triangles at this pixel, merged by minimum (every covering
+        // record is evaluated, exactly as the tiled path would: snapped fan triangles may overlap in degenerate cases)
+        const int nh = s_nh;
         for (int i = 0; i < nh; ++i) {
-            const HugeRec& h = f.huge[i];
+            const HugeRec& h = s_huge[i];
             if (px < h.px0 || px > h.px1 || py < h.py0 || py > h.py1) continue;
             SubTri st;
             st.ax = h.ax; st.ay = h.ay; st.bx = h.bx; st.by = h.by; st.cx = h.cx; st.cy = h.cy;

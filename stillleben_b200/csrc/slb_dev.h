@@ -75,7 +75,7 @@ struct DBinDraw {
 };
 // A huge sub-triangle of a camera view that is resolved per pixel inside the shade kernel instead of going through
 // count / scan / emit / raster: its prepared edge set-up (k_contract.cuh SubTri, 64 B), key bits and pixel box.
-#define SLB_HUGE_PER_VIEW 8        // more than this many per view: the rest takes the tiled path (both merge by minimum)
+#define SLB_HUGE_PER_VIEW 16       // more than this many per view: the rest takes the tiled path (both merge by minimum)
 struct __align__(16) HugeRec {
     int32_t ax, ay, bx, by, cx, cy;
     float az, bz, cz;
