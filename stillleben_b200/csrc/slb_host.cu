@@ -72,7 +72,7 @@ struct slb_ctx {
     bool time_kernels = false, keep_hdr = false;
     int max_subbatch = 64;
     // largest pixel box (in pixels) the setup kernel rasterises directly with one thread / with one warp; larger
-    // triangles take the tiled path (tunables: env SLB_DIRECT_MAX, SLB_WARP_MAX)
+    // triangles take the tiled path (SLB_OPT_DIRECT_MAX, SLB_OPT_WARP_MAX)
     int direct_max = 128, warp_max = 4096;
     bool lean_shade = true;
     bool huge_in_shade = true;   // camera views resolve their first SLB_HUGE_PER_VIEW huge sub-triangles in the shade kernel
@@ -160,8 +160,6 @@ extern "C" int slb_ctx_create(int device, slb_ctx** out) {
     slb_ctx* c = new slb_ctx;
     c->device = device;
     std::memset(&c->stats, 0, sizeof c->stats);
-    if (const char* dm = getenv("SLB_DIRECT_MAX")) c->direct_max = atoi(dm);
-    if (const char* wm = getenv("SLB_WARP_MAX")) c->warp_max = atoi(wm);
     ctx = c;
     cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
