@@ -252,7 +252,7 @@ __device__ __forceinline__ void red_min_u64(unsigned long long* p, unsigned long
 // shadow view), so the cost per triangle is box/32 iterations instead of one iteration per touched tile.
 template <bool SHADOW, int G>
 __device__ __forceinline__ void raster_direct(int ax, int ay, int bx, int by, int cx, int cy, float az, float bz, float cz, uint32_t seq,
-                                              void* __restrict__ out, int W, int H, int lane) {
+                                              void* __restrict__ out, int W, int H, int lane, uint32_t tagbits) {
     const int xmin = min(ax, min(bx, cx)), xmax = max(ax, max(bx, cx));
     const int ymin = min(ay, min(by, cy)), ymax = max(ay, max(by, cy));
     const int px0 = max(0, (xmin - 128 + 255) >> 8), px1 = min(W - 1, (xmax - 128) >> 8);
@@ -279,7 +279,7 @@ __device__ __forceinline__ void raster_direct(int ax, int ay, int bx, int by, in
         float z = __fmaf_rn(q2, zc, __fmaf_rn(q1, zb, az));
         z = fminf(fmaxf(z, 0.0f), 1.0f);
         const uint32_t d24 = __float2uint_rn(__fmul_rn(z, 16777215.0f));
-        if (SHADOW) red_min_u32(reinterpret_cast<uint32_t*>(out) + (size_t)y * W + x, d24);
+        if (SHADOW) red_min_u32(reinterpret_cast<uint32_t*>(out) + (size_t)y * W + x, tagbits | d24);   // generation tag above the depth
         else red_min_u64(reinterpret_cast<unsigned long long*>(out) + (size_t)y * W + x, ((unsigned long long)d24 << 40) | lowkey);
     };
     if (G == 1) {
@@ -395,8 +395,8 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 5) k_setup(const DView* __res
                   __int_as_float(s_dq[7][q]), __int_as_float(s_dq[8][q]), (uint32_t)s_dq[9][q]
     if ((int)threadIdx.x < s_ndirect) {
         const int q = threadIdx.x;
-        if (v.shadow) raster_direct<true, 1>(SLB_DQ(q), v.out, v.W, v.H, 0);
-        else raster_direct<false, 1>(SLB_DQ(q), v.out, v.W, v.H, 0);
+        if (v.shadow) raster_direct<true, 1>(SLB_DQ(q), v.out, v.W, v.H, 0, v.tagbits);
+        else raster_direct<false, 1>(SLB_DQ(q), v.out, v.W, v.H, 0, 0u);
     }
     // ... then the mid-size ones, one per warp, handed out dynamically
     const int nmid = s_nmid;
@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 5) k_setup(const DView* __res
         m = __shfl_sync(0xffffffffu, m, 0);
         if (m >= nmid) break;
         const int q = SLB_SETUP_CHUNK - 1 - m;
-        if (v.shadow) raster_direct<true, 32>(SLB_DQ(q), v.out, v.W, v.H, lane);
-        else raster_direct<false, 32>(SLB_DQ(q), v.out, v.W, v.H, lane);
+        if (v.shadow) raster_direct<true, 32>(SLB_DQ(q), v.out, v.W, v.H, lane, v.tagbits);
+        else raster_direct<false, 32>(SLB_DQ(q), v.out, v.W, v.H, lane, 0u);
     }
 #undef SLB_DQ
 }
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DView* _
             if (gx < W && gy < H) {
                 if (v.shadow) {
                     const uint32_t g0 = reinterpret_cast<const uint32_t*>(v.out)[(size_t)gy * W + gx];
-                    if (g0 <= 0xFFFFFFu) k0 = (unsigned long long)g0 << 40;
+                    if ((g0 & 0xFF000000u) == v.tagbits) k0 = (unsigned long long)(g0 & 0xFFFFFFu) << 40;   // written in this generation
                 } else {
                     k0 = reinterpret_cast<const unsigned long long*>(v.out)[(size_t)gy * W + gx];
                 }
@@ -770,8 +770,8 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DView* _
         if (v.shadow) {   // depth-only view: the d24 plane the PCF lookup reads (cleared to 0xFFFFFF where nothing was drawn)
             uint32_t* out = reinterpret_cast<uint32_t*>(v.out);
             const unsigned long long k0 = keys[ly * SLB_TILE + lx], k1 = keys[(ly + 4) * SLB_TILE + lx];
-            if (y_lo + ly < H) out[(size_t)(y_lo + ly) * W + px] = k0 == SLB_KEY_EMPTY ? 0xFFFFFFu : (uint32_t)(k0 >> 40);
-            if (y_lo + ly + 4 < H) out[(size_t)(y_lo + ly + 4) * W + px] = k1 == SLB_KEY_EMPTY ? 0xFFFFFFu : (uint32_t)(k1 >> 40);
+            if (y_lo + ly < H) out[(size_t)(y_lo + ly) * W + px] = v.tagbits | (k0 == SLB_KEY_EMPTY ? 0xFFFFFFu : (uint32_t)(k0 >> 40));
+            if (y_lo + ly + 4 < H) out[(size_t)(y_lo + ly + 4) * W + px] = v.tagbits | (k1 == SLB_KEY_EMPTY ? 0xFFFFFFu : (uint32_t)(k1 >> 40));
         } else {
             unsigned long long* out = reinterpret_cast<unsigned long long*>(v.out);
             if (y_lo + ly < H) out[(size_t)(y_lo + ly) * W + px] = keys[ly * SLB_TILE + lx];

@@ -92,8 +92,8 @@ struct DView {
     uint32_t tile_base;            // first tile of this view in the batch-wide tile arrays
     int32_t shadow;                // 1: cull front faces, write d24 only (render_pass.cpp:426-460)
     uint32_t frame;                // DFrame index (camera views)
-    uint32_t pad;
-    void* out;                     // uint64 keys[H*W] (camera) or uint32 d24[H*W] (shadow)
+    uint32_t tagbits;              // shadow views: generation tag << 24, stored above every d24 (see DFrame::shadow_tagbits)
+    void* out;                     // uint64 keys[H*W] (camera) or uint32 tag | d24 [H*W] (shadow)
     HugeRec* huge;                 // camera views: SLB_HUGE_PER_VIEW slots (null: feature off / shadow view)
     uint32_t* huge_n;              // how many were claimed (may exceed the capacity: the excess went to the tiled path)
 };
@@ -117,6 +117,11 @@ struct DFrame {
     int32_t ssao;
     float ambient[3];
     int32_t fused_tonemap;         // 1: shade kernel tone-maps and stores rgb itself (no post passes needed)
+    // Shadow-map texels are tag << 24 | d24 with tag = 255 - generation, the generation counting the sub-batches that
+    // reused the map pool since its last clear. Newer generations are SMALLER, so RED.MIN lets this sub-batch's depths
+    // replace stale ones, and a texel nobody wrote this time compares >= any threshold of the current tag — "lit",
+    // exactly like a cleared texel. The 1 GB memset per sub-batch is needed only once every 255 sub-batches.
+    uint32_t shadow_tagbits;
     float shadowMat[SLB_NUM_LIGHTS][16];
     const uint32_t* shadowMap[SLB_NUM_LIGHTS];
     const DLightMap* lm;

@@ -75,6 +75,8 @@ struct slb_ctx {
     // triangles take the tiled path (SLB_OPT_DIRECT_MAX, SLB_OPT_WARP_MAX)
     int direct_max = 128, warp_max = 4096;
     bool lean_shade = true;
+    uint32_t shadow_gen = 255;   // generation of the shadow-map pool (DFrame::shadow_tagbits); 255 = clear before the next use
+    void* shadow_pool_at = nullptr; size_t shadow_pool_cap = 0;
     bool huge_in_shade = true;   // camera views resolve their first SLB_HUGE_PER_VIEW huge sub-triangles in the shade kernel
     slb_stats stats;
     // assets owned by the context
@@ -1020,7 +1022,18 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
             if (b.any_ssao) f.zplane = ctx->zplane.as<float>() + npx * j;
         }
     }
-    for (uint32_t sidx = 0; sidx < b.n_shadow_maps; ++sidx) b.views[n + sidx].out = smaps + smap_elems * sidx;
+    // generation tag of the shadow maps of this sub-batch: a real clear only when the pool moved / grew or the 8-bit
+    // generation wraps
+    const bool pool_changed = ctx->shadow_maps.p != ctx->shadow_pool_at || ctx->shadow_maps.cap != ctx->shadow_pool_cap;
+    bool clear_shadow_pool = false;
+    if (b.n_shadow_maps) {
+        if (pool_changed || ctx->shadow_gen >= 255) { clear_shadow_pool = true; ctx->shadow_gen = 0; }
+        ctx->shadow_pool_at = ctx->shadow_maps.p; ctx->shadow_pool_cap = ctx->shadow_maps.cap;
+        ++ctx->shadow_gen;
+    }
+    const uint32_t shadow_tagbits = (255u - ctx->shadow_gen) << 24;
+    for (int j = 0; j < n; ++j) b.frames[j].shadow_tagbits = shadow_tagbits;
+    for (uint32_t sidx = 0; sidx < b.n_shadow_maps; ++sidx) { b.views[n + sidx].out = smaps + smap_elems * sidx; b.views[n + sidx].tagbits = shadow_tagbits; }
 
     // ---- one staged upload ----
     const size_t sz[5] = {b.frames.size() * sizeof(DFrame), b.draws.size() * sizeof(DDraw), b.views.size() * sizeof(DView),
@@ -1054,7 +1067,7 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     {   // "nothing drawn": keys = all ones, shadow d24 >= 0xFFFFFF; only non-empty tiles get a raster warp
         StageTimer t(ctx, s, ST_SHADOW);
         CU(cudaMemsetAsync(ctx->keys.p, 0xFF, npx * n * 8, s));
-        if (b.n_shadow_maps) CU(cudaMemsetAsync(smaps, 0xFF, smap_elems * 4 * b.n_shadow_maps, s));
+        if (clear_shadow_pool) CU(cudaMemsetAsync(ctx->shadow_maps.p, 0xFF, ctx->shadow_maps.cap, s));   // whole pool: every slot starts stale
     }
     // ---- setup (camera + shadow views together) -> scan -> emit ----
     uint64_t total_bin_tris = 0;

@@ -127,3 +127,24 @@ def test_lean_and_full_shade_kernels_agree(gpu_ctx, batch):
                 assert s_["over1"] == 0, s_
             else:
                 assert s_["bad"] == 0 and s_["max_abs"] < 1e-4 * 3000, (name, s_)
+
+
+def test_shadow_map_generations_wrap(gpu_ctx):
+    """Shadow-map texels carry an 8-bit generation tag instead of being cleared for every sub-batch
+    (DFrame::shadow_tagbits); after 255 sub-batches the pool is really cleared and the count restarts. Rendering
+    the same scenes through > 2 x 255 single-scene sub-batches must keep producing identical frames."""
+    import fixtures
+    a, b = fixtures.small_tabletop_scene(), fixtures.variant("three_lights", 160, 120)
+    gpu_ctx.set_option(abi.OPT_MAX_SUBBATCH, 1)
+    try:
+        ref = gpu_ctx.render([a, b], target_mask=abi.TARGETS_SIX)
+        gpu_ctx.synchronize()
+        want = [hashlib.sha256(ref.numpy(abi.TARGET_RGB, i, 1).tobytes() + ref.numpy(abi.TARGET_COORD, i, 1).tobytes()).hexdigest() for i in range(2)]
+        for it in range(270):                       # 540 sub-batches with 1 or 3 shadow maps each
+            res = gpu_ctx.render([a, b], result=ref)
+            if it % 30 == 0 or it > 250:
+                gpu_ctx.synchronize()
+                got = [hashlib.sha256(res.numpy(abi.TARGET_RGB, i, 1).tobytes() + res.numpy(abi.TARGET_COORD, i, 1).tobytes()).hexdigest() for i in range(2)]
+                assert got == want, it
+    finally:
+        gpu_ctx.set_option(abi.OPT_MAX_SUBBATCH, 64)
