@@ -183,10 +183,21 @@ def variant(name, width=320, height=240):
         sc.objects[2].casts_shadows = False
         sc.objects[3].visible = False
         return sc
+    if name == "low_poly_closeup":
+        # a 64-triangle blob filling the view: several dozen huge triangles per frame -> the first 16 are resolved in the
+        # shade kernel, the rest fall back to the tiled path, a few are medium / small (warp and thread paths)
+        m = synth.shape_mesh("blob", 5, nu=8, nv=4, textured=True, tex_size=64)
+        sc = synth.tabletop_scene(pool, 27, n_objects=2, width=width, height=height, intrinsics=None)
+        for k, o in enumerate(sc.objects):
+            o.mesh = m
+            o.pretransform = synth.normalising_pretransform(m, 1.1 - 0.5 * k)
+            o.pose = np.eye(4, dtype=np.float32)
+            o.pose[:3, 3] = (0.15 * k, -0.1 * k, 0.35 + 0.2 * k)
+        return sc
     if name == "odd_viewport":
         return synth.tabletop_scene(pool, 25, n_objects=5, width=203, height=117, intrinsics=None)
     raise KeyError(name)
 
 
 VARIANTS = ["tabletop", "three_lights", "ssao", "auto_exposure", "no_plane_no_light", "empty", "ibl", "alpha_test", "sticker",
-            "background_image", "plane_texture", "near_clip", "predicate", "id_limits", "odd_viewport", "multi_submesh"]
+            "background_image", "plane_texture", "near_clip", "predicate", "id_limits", "odd_viewport", "multi_submesh", "low_poly_closeup"]
