@@ -27,7 +27,7 @@ struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     cudaError_t reserve(size_t bytes, bool zero = false) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p) { cudaDeviceSynchronize(); cudaFree(p); }   // growth is rare; queued work of an earlier sub-batch may still use the old block
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -65,6 +65,43 @@ static const size_t kTargetBpp[SLB_NUM_TARGETS] = {4, 16, 2, 2, 16, 16, 16, 16};
 
 enum { ST_SHADOW = 0, ST_COUNT, ST_SCAN, ST_EMIT, ST_RASTER, ST_SHADE, ST_SSAO, ST_POST, ST_N };
 
+// Everything one sub-batch owns on the device and in pinned host memory. A context has TWO sets, so that the
+// host can marshal, upload and queue the set-up of sub-batch k+1 while it waits for the scan totals of sub-batch k
+// (slb_render_batch): the one host synchronisation per sub-batch no longer idles the GPU.
+struct Pending {   // a sub-batch whose first phase (clear, set-up, scan) is queued and whose second phase is not
+    bool active = false;
+    int n = 0, W = 0, H = 0, first_frame = 0;
+    size_t npx = 0;
+    RasterGrid grid;
+    uint32_t n_tiles = 0, normal_cap = 0, huge_cap = 0;
+    uint64_t total_bin_tris = 0;
+    slb_result* result = nullptr;
+    bool post = false;
+};
+struct Scratch {
+    DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, survivors;
+    DevBuf clip_recs, clip_counts, huge_recs, huge_counts;
+    DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, zplane, ao, avg, mip_a, mip_b, shadow_maps;
+    void* staging = nullptr; size_t staging_cap = 0;   // pinned
+    uint32_t* total_pinned = nullptr;                   // mapped pinned: the scan writes its totals here
+    uint32_t shadow_gen = 255;   // generation of the shadow-map pool (DFrame::shadow_tagbits); 255 = clear before the next use
+    void* shadow_pool_at = nullptr; size_t shadow_pool_cap = 0;
+    void* batch = nullptr; void (*batch_delete)(void*) = nullptr;   // host arrays of the sub-batch (Batch, defined below)
+    cudaEvent_t scanned = nullptr;
+    Pending pending;
+    void release() {
+        DevBuf* bufs[] = {&frames_d, &draws_d, &chunk_base_d, &views_d, &bdraws_d, &scan_sums, &active_tiles, &scan_totals, &survivors, &clip_recs,
+                          &clip_counts, &huge_recs, &huge_counts, &tile_count, &tile_off, &pairs, &keys, &hdr, &scratch_normal, &scratch_cam,
+                          &zplane, &ao, &avg, &mip_a, &mip_b, &shadow_maps};
+        for (DevBuf* b : bufs) b->release();
+        if (staging) cudaFreeHost(staging);
+        if (total_pinned) cudaFreeHost(total_pinned);
+        if (batch && batch_delete) batch_delete(batch);
+        if (scanned) cudaEventDestroy(scanned);
+        staging = nullptr; total_pinned = nullptr; batch = nullptr; scanned = nullptr;
+    }
+};
+
 struct slb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -75,20 +112,13 @@ struct slb_ctx {
     // triangles take the tiled path (SLB_OPT_DIRECT_MAX, SLB_OPT_WARP_MAX)
     int direct_max = 128, warp_max = 4096;
     bool lean_shade = true;
-    uint32_t shadow_gen = 255;   // generation of the shadow-map pool (DFrame::shadow_tagbits); 255 = clear before the next use
-    void* shadow_pool_at = nullptr; size_t shadow_pool_cap = 0;
     bool huge_in_shade = true;   // camera views resolve their first SLB_HUGE_PER_VIEW huge sub-triangles in the shade kernel
     slb_stats stats;
     // assets owned by the context
     slb_mesh* plane = nullptr;
-    // per-batch device arrays
-    DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, survivors;
-    DevBuf clip_recs, clip_counts, huge_recs, huge_counts, diff_params, diff_partial, cam_params, cam_mid, png_rows, png_info, png_offsets;
+    Scratch scr[2];
+    DevBuf diff_params, diff_partial, cam_params, cam_mid, png_rows, png_info, png_offsets;
     bool png_tables = false;
-    DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, zplane, ao, avg, mip_a, mip_b, shadow_maps;
-    // pinned staging
-    void* staging = nullptr; size_t staging_cap = 0;
-    uint32_t* total_pinned = nullptr;
     // timing
     struct Ev { int stage; cudaEvent_t a, b; };
     std::vector<Ev> events;
@@ -97,7 +127,6 @@ struct slb_ctx {
     slb_result* slot[2] = {nullptr, nullptr};
     cudaEvent_t slot_rendered[2] = {nullptr, nullptr}, slot_copied[2] = {nullptr, nullptr};
 };
-
 static thread_local std::string g_create_error;
 
 static int fail(slb_ctx* ctx, int code, const std::string& msg) {
@@ -112,13 +141,13 @@ static int fail(slb_ctx* ctx, int code, const std::string& msg) {
                         std::string(#call) + ": " + cudaGetErrorString(e__));                                \
     } while (0)
 
-static int ensure_staging(slb_ctx* ctx, size_t bytes) {
-    if (bytes <= ctx->staging_cap) return SLB_OK;
-    if (ctx->staging) cudaFreeHost(ctx->staging);
-    ctx->staging = nullptr; ctx->staging_cap = 0;
-    size_t want = bytes + bytes / 2 + 4096;
-    CU(cudaHostAlloc(&ctx->staging, want, cudaHostAllocDefault));
-    ctx->staging_cap = want;
+static int ensure_staging(slb_ctx* ctx, Scratch& S, size_t bytes) {
+    if (bytes <= S.staging_cap) return SLB_OK;
+    if (S.staging) cudaFreeHost(S.staging);
+    S.staging = nullptr; S.staging_cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    CU(cudaHostAlloc(&S.staging, want, cudaHostAllocDefault));
+    S.staging_cap = want;
     return SLB_OK;
 }
 
@@ -165,8 +194,12 @@ extern "C" int slb_ctx_create(int device, slb_ctx** out) {
     ctx = c;
     cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-    cudaError_t e3 = cudaHostAlloc((void**)&c->total_pinned, 64, cudaHostAllocPortable | cudaHostAllocMapped);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { delete c; ctx = nullptr; return fail(ctx, SLB_ERR_CUDA, "slb_ctx_create: stream/pinned allocation failed"); }
+    cudaError_t e3 = cudaSuccess;
+    for (Scratch& S : c->scr) {
+        if (e3 == cudaSuccess) e3 = cudaHostAlloc((void**)&S.total_pinned, 64, cudaHostAllocPortable | cudaHostAllocMapped);
+        if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&S.scanned, cudaEventDisableTiming);
+    }
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { for (Scratch& S : c->scr) S.release(); delete c; ctx = nullptr; return fail(ctx, SLB_ERR_CUDA, "slb_ctx_create: stream/pinned allocation failed"); }
     float noise[48], kernel[192];
     ssao_tables(noise, kernel);
     upload_ssao_tables(noise, kernel);
@@ -210,14 +243,11 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
         if (ctx->slot_rendered[i]) cudaEventDestroy(ctx->slot_rendered[i]);
         if (ctx->slot_copied[i]) cudaEventDestroy(ctx->slot_copied[i]);
     }
-    DevBuf* bufs[] = {&ctx->frames_d, &ctx->draws_d, &ctx->chunk_base_d, &ctx->views_d, &ctx->bdraws_d, &ctx->scan_sums, &ctx->active_tiles, &ctx->scan_totals, &ctx->survivors, &ctx->diff_params, &ctx->diff_partial, &ctx->cam_params, &ctx->cam_mid, &ctx->png_rows, &ctx->png_info, &ctx->png_offsets, &ctx->tile_count,
-                      &ctx->tile_off, &ctx->pairs, &ctx->keys, &ctx->hdr, &ctx->scratch_normal, &ctx->scratch_cam, &ctx->zplane, &ctx->ao,
-                      &ctx->avg, &ctx->mip_a, &ctx->mip_b, &ctx->shadow_maps, &ctx->clip_recs, &ctx->clip_counts, &ctx->huge_recs, &ctx->huge_counts};
+    for (Scratch& S : ctx->scr) S.release();
+    DevBuf* bufs[] = {&ctx->diff_params, &ctx->diff_partial, &ctx->cam_params, &ctx->cam_mid, &ctx->png_rows, &ctx->png_info, &ctx->png_offsets};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ctx->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    if (ctx->staging) cudaFreeHost(ctx->staging);
-    if (ctx->total_pinned) cudaFreeHost(ctx->total_pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -954,9 +984,14 @@ struct StageTimer {
     ~StageTimer() { if (ctx->time_kernels) { cudaEventRecord(b, s); ctx->events.push_back({stage, a, b}); } }
 };
 
-static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, slb_result* result, int first_frame,
+static int subbatch_setup_scan(slb_ctx* ctx, Scratch& S, cudaStream_t s);
+// Phase 1 of a sub-batch on scratch set `set`: marshal, upload, clear, set-up (with the direct raster paths), scan.
+// Ends with the event the second phase waits on before it reads the scan totals.
+static int subbatch_phase1(slb_ctx* ctx, int set, const slb_scene_desc* scenes, int n, slb_result* result, int first_frame,
                            const slb_result* depth_peel, cudaStream_t s) {
-    static thread_local Batch b;   // arrays keep their capacity from one sub-batch to the next
+    Scratch& S = ctx->scr[set];
+    if (!S.batch) { S.batch = new Batch; S.batch_delete = [](void* p) { delete static_cast<Batch*>(p); }; }
+    Batch& b = *static_cast<Batch*>(S.batch);   // arrays keep their capacity from one sub-batch to the next
     b.clear();
     build_batch(ctx, scenes, n, result, first_frame, depth_peel, b);
     const int W = result->W, H = result->H;
@@ -969,44 +1004,44 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     const uint32_t n_tiles = grid.n_cam_tiles + tiles_per_shadow * b.n_shadow_maps;
 
     // ---- device scratch ----
-    CU(ctx->frames_d.reserve(b.frames.size() * sizeof(DFrame)));
-    CU(ctx->draws_d.reserve((b.draws.size() + 1) * sizeof(DDraw)));
-    CU(ctx->views_d.reserve(b.views.size() * sizeof(DView)));
-    CU(ctx->bdraws_d.reserve((b.bdraws.size() + 1) * sizeof(DBinDraw)));
-    CU(ctx->chunk_base_d.reserve((b.chunk_draw.size() + 1) * 4));
-    CU(ctx->tile_count.reserve((size_t)n_tiles * 4, true));
-    CU(ctx->tile_off.reserve(((size_t)n_tiles + 1) * 4));
-    CU(ctx->scan_sums.reserve(((size_t)n_tiles / 4096 + 2) * 8));
-    CU(ctx->active_tiles.reserve((size_t)n_tiles * sizeof(ActiveTile)));
-    CU(ctx->scan_totals.reserve(64));
-    CU(ctx->keys.reserve(npx * n * 8));
-    CU(ctx->clip_recs.reserve((size_t)n * SLB_MAX_CLIP * sizeof(ClipRec)));
-    CU(ctx->clip_counts.reserve((size_t)n * 4));
-    CU(ctx->huge_recs.reserve((size_t)n * SLB_HUGE_PER_VIEW * sizeof(HugeRec)));
-    CU(ctx->huge_counts.reserve((size_t)n * 4));
-    CU(ctx->shadow_maps.reserve((size_t)b.n_shadow_maps * SLB_SHADOW_RES * SLB_SHADOW_RES * 4));
+    CU(S.frames_d.reserve(b.frames.size() * sizeof(DFrame)));
+    CU(S.draws_d.reserve((b.draws.size() + 1) * sizeof(DDraw)));
+    CU(S.views_d.reserve(b.views.size() * sizeof(DView)));
+    CU(S.bdraws_d.reserve((b.bdraws.size() + 1) * sizeof(DBinDraw)));
+    CU(S.chunk_base_d.reserve((b.chunk_draw.size() + 1) * 4));
+    CU(S.tile_count.reserve((size_t)n_tiles * 4, true));
+    CU(S.tile_off.reserve(((size_t)n_tiles + 1) * 4));
+    CU(S.scan_sums.reserve(((size_t)n_tiles / 4096 + 2) * 8));
+    CU(S.active_tiles.reserve((size_t)n_tiles * sizeof(ActiveTile)));
+    CU(S.scan_totals.reserve(64));
+    CU(S.keys.reserve(npx * n * 8));
+    CU(S.clip_recs.reserve((size_t)n * SLB_MAX_CLIP * sizeof(ClipRec)));
+    CU(S.clip_counts.reserve((size_t)n * 4));
+    CU(S.huge_recs.reserve((size_t)n * SLB_HUGE_PER_VIEW * sizeof(HugeRec)));
+    CU(S.huge_counts.reserve((size_t)n * 4));
+    CU(S.shadow_maps.reserve((size_t)b.n_shadow_maps * SLB_SHADOW_RES * SLB_SHADOW_RES * 4));
     const bool post = !b.fused;
     if (post) {
-        if (!result->hdr) CU(ctx->hdr.reserve(npx * n * 16));
-        CU(ctx->ao.reserve(npx * n * 4));
-        CU(ctx->avg.reserve((size_t)n * 16));
-        if (!result->ptrs[SLB_TARGET_NORMAL] && b.any_ssao) CU(ctx->scratch_normal.reserve(npx * n * 16));
-        if (!result->ptrs[SLB_TARGET_CAM_COORD] && b.any_ssao) CU(ctx->scratch_cam.reserve(npx * n * 16));
-        if (b.any_ssao) CU(ctx->zplane.reserve(npx * n * 4));
-        if (b.any_auto) { CU(ctx->mip_a.reserve((npx / 4 + W + H + 4) * n * 16)); CU(ctx->mip_b.reserve((npx / 16 + W + H + 4) * n * 16)); }
+        if (!result->hdr) CU(S.hdr.reserve(npx * n * 16));
+        CU(S.ao.reserve(npx * n * 4));
+        CU(S.avg.reserve((size_t)n * 16));
+        if (!result->ptrs[SLB_TARGET_NORMAL] && b.any_ssao) CU(S.scratch_normal.reserve(npx * n * 16));
+        if (!result->ptrs[SLB_TARGET_CAM_COORD] && b.any_ssao) CU(S.scratch_cam.reserve(npx * n * 16));
+        if (b.any_ssao) CU(S.zplane.reserve(npx * n * 4));
+        if (b.any_auto) { CU(S.mip_a.reserve((npx / 4 + W + H + 4) * n * 16)); CU(S.mip_b.reserve((npx / 16 + W + H + 4) * n * 16)); }
     }
     // ---- patch device pointers into the host arrays ----
-    uint32_t* smaps = ctx->shadow_maps.as<uint32_t>();
+    uint32_t* smaps = S.shadow_maps.as<uint32_t>();
     const size_t smap_elems = (size_t)SLB_SHADOW_RES * SLB_SHADOW_RES;
     for (int j = 0; j < n; ++j) {
         DFrame& f = b.frames[j];
-        f.keys = ctx->keys.as<uint64_t>() + npx * j;
+        f.keys = S.keys.as<uint64_t>() + npx * j;
         b.views[j].out = f.keys;
-        f.clip = ctx->clip_recs.as<ClipRec>() + (size_t)j * SLB_MAX_CLIP;
-        f.clip_count = ctx->clip_counts.as<uint32_t>() + j;
+        f.clip = S.clip_recs.as<ClipRec>() + (size_t)j * SLB_MAX_CLIP;
+        f.clip_count = S.clip_counts.as<uint32_t>() + j;
         if (ctx->huge_in_shade) {
-            f.huge = ctx->huge_recs.as<HugeRec>() + (size_t)j * SLB_HUGE_PER_VIEW; f.huge_n = ctx->huge_counts.as<uint32_t>() + j;
-            b.views[j].huge = ctx->huge_recs.as<HugeRec>() + (size_t)j * SLB_HUGE_PER_VIEW; b.views[j].huge_n = ctx->huge_counts.as<uint32_t>() + j;
+            f.huge = S.huge_recs.as<HugeRec>() + (size_t)j * SLB_HUGE_PER_VIEW; f.huge_n = S.huge_counts.as<uint32_t>() + j;
+            b.views[j].huge = S.huge_recs.as<HugeRec>() + (size_t)j * SLB_HUGE_PER_VIEW; b.views[j].huge_n = S.huge_counts.as<uint32_t>() + j;
         }
         f.fused_tonemap = b.fused ? 1 : 0;
         for (int li = 0; li < SLB_NUM_LIGHTS; ++li)
@@ -1014,24 +1049,24 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
         f.scratch_normal = (float4*)f.out[SLB_TARGET_NORMAL];
         f.scratch_cam = (float4*)f.out[SLB_TARGET_CAM_COORD];
         if (post) {
-            f.hdr = result->hdr ? result->hdr + npx * (first_frame + j) : ctx->hdr.as<float4>() + npx * j;
-            f.ao = ctx->ao.as<float>() + npx * j;
-            f.avg = ctx->avg.as<float>() + 4 * j;
-            if (!f.scratch_normal && b.any_ssao) f.scratch_normal = ctx->scratch_normal.as<float4>() + npx * j;
-            if (!f.scratch_cam && b.any_ssao) f.scratch_cam = ctx->scratch_cam.as<float4>() + npx * j;
-            if (b.any_ssao) f.zplane = ctx->zplane.as<float>() + npx * j;
+            f.hdr = result->hdr ? result->hdr + npx * (first_frame + j) : S.hdr.as<float4>() + npx * j;
+            f.ao = S.ao.as<float>() + npx * j;
+            f.avg = S.avg.as<float>() + 4 * j;
+            if (!f.scratch_normal && b.any_ssao) f.scratch_normal = S.scratch_normal.as<float4>() + npx * j;
+            if (!f.scratch_cam && b.any_ssao) f.scratch_cam = S.scratch_cam.as<float4>() + npx * j;
+            if (b.any_ssao) f.zplane = S.zplane.as<float>() + npx * j;
         }
     }
     // generation tag of the shadow maps of this sub-batch: a real clear only when the pool moved / grew or the 8-bit
     // generation wraps
-    const bool pool_changed = ctx->shadow_maps.p != ctx->shadow_pool_at || ctx->shadow_maps.cap != ctx->shadow_pool_cap;
+    const bool pool_changed = S.shadow_maps.p != S.shadow_pool_at || S.shadow_maps.cap != S.shadow_pool_cap;
     bool clear_shadow_pool = false;
     if (b.n_shadow_maps) {
-        if (pool_changed || ctx->shadow_gen >= 255) { clear_shadow_pool = true; ctx->shadow_gen = 0; }
-        ctx->shadow_pool_at = ctx->shadow_maps.p; ctx->shadow_pool_cap = ctx->shadow_maps.cap;
-        ++ctx->shadow_gen;
+        if (pool_changed || S.shadow_gen >= 255) { clear_shadow_pool = true; S.shadow_gen = 0; }
+        S.shadow_pool_at = S.shadow_maps.p; S.shadow_pool_cap = S.shadow_maps.cap;
+        ++S.shadow_gen;
     }
-    const uint32_t shadow_tagbits = (255u - ctx->shadow_gen) << 24;
+    const uint32_t shadow_tagbits = (255u - S.shadow_gen) << 24;
     for (int j = 0; j < n; ++j) b.frames[j].shadow_tagbits = shadow_tagbits;
     for (uint32_t sidx = 0; sidx < b.n_shadow_maps; ++sidx) { b.views[n + sidx].out = smaps + smap_elems * sidx; b.views[n + sidx].tagbits = shadow_tagbits; }
 
@@ -1039,13 +1074,13 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     const size_t sz[5] = {b.frames.size() * sizeof(DFrame), b.draws.size() * sizeof(DDraw), b.views.size() * sizeof(DView),
                           b.bdraws.size() * sizeof(DBinDraw), b.chunk_draw.size() * 4};
     const void* src[5] = {b.frames.data(), b.draws.data(), b.views.data(), b.bdraws.data(), b.chunk_draw.data()};
-    void* dst[5] = {ctx->frames_d.p, ctx->draws_d.p, ctx->views_d.p, ctx->bdraws_d.p, ctx->chunk_base_d.p};
+    void* dst[5] = {S.frames_d.p, S.draws_d.p, S.views_d.p, S.bdraws_d.p, S.chunk_base_d.p};
     size_t total_sz = 0;
     for (int i = 0; i < 5; ++i) total_sz += (sz[i] + 63) & ~(size_t)63;
-    int rc = ensure_staging(ctx, total_sz + 64);
+    int rc = ensure_staging(ctx, S, total_sz + 64);
     if (rc != SLB_OK) return rc;
     {
-        uint8_t* st = (uint8_t*)ctx->staging;
+        uint8_t* st = (uint8_t*)S.staging;
         size_t at = 0;
         for (int i = 0; i < 5; ++i) {
             if (sz[i]) {
@@ -1056,65 +1091,94 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
             ctx->stats.bytes_h2d += sz[i];
         }
     }
-    const DFrame* frames_d = ctx->frames_d.as<DFrame>();
-    const DDraw* draws_d = ctx->draws_d.as<DDraw>();
-    const DView* views_d = ctx->views_d.as<DView>();
-    const DBinDraw* bdraws_d = ctx->bdraws_d.as<DBinDraw>();
-
-    CU(cudaMemsetAsync(ctx->clip_counts.p, 0, (size_t)n * 4, s));
-    CU(cudaMemsetAsync(ctx->huge_counts.p, 0, (size_t)n * 4, s));
-    CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, s));
+    CU(cudaMemsetAsync(S.clip_counts.p, 0, (size_t)n * 4, s));
+    CU(cudaMemsetAsync(S.huge_counts.p, 0, (size_t)n * 4, s));
+    CU(cudaMemsetAsync(S.tile_count.p, 0, (size_t)n_tiles * 4, s));
     {   // "nothing drawn": keys = all ones, shadow d24 >= 0xFFFFFF; only non-empty tiles get a raster warp
         StageTimer t(ctx, s, ST_SHADOW);
-        CU(cudaMemsetAsync(ctx->keys.p, 0xFF, npx * n * 8, s));
-        if (clear_shadow_pool) CU(cudaMemsetAsync(ctx->shadow_maps.p, 0xFF, ctx->shadow_maps.cap, s));   // whole pool: every slot starts stale
+        CU(cudaMemsetAsync(S.keys.p, 0xFF, npx * n * 8, s));
+        if (clear_shadow_pool) CU(cudaMemsetAsync(S.shadow_maps.p, 0xFF, S.shadow_maps.cap, s));   // whole pool: every slot starts stale
     }
-    // ---- setup (camera + shadow views together) -> scan -> emit ----
-    uint64_t total_bin_tris = 0;
-    for (const DBinDraw& bd : b.bdraws) total_bin_tris += bd.n_tris;
-    uint32_t total_pairs = 0, n_survivors = 0, n_huge = 0, normal_cap = 0;
+    // ---- setup (camera + shadow views together) -> scan ----
+    Pending& P = S.pending;
+    P.active = true; P.n = n; P.W = W; P.H = H; P.first_frame = first_frame; P.npx = npx; P.grid = grid; P.n_tiles = n_tiles;
+    P.result = result; P.post = post;
+    P.total_bin_tris = 0;
+    for (const DBinDraw& bd : b.bdraws) P.total_bin_tris += bd.n_tris;
+    return subbatch_setup_scan(ctx, S, s);
+}
+
+// set-up + scan of the sub-batch pending on S (also the retry after a survivor-buffer overflow)
+static int subbatch_setup_scan(slb_ctx* ctx, Scratch& S, cudaStream_t s) {
+    Pending& P = S.pending;
+    Batch& b = *static_cast<Batch*>(S.batch);
+    // ordinary survivors in [0, normal_cap), huge ones (whole block each in the emit pass) in the last fifth
+    const size_t want = (size_t)P.total_bin_tris + P.total_bin_tris / 4 + 8192;
+    if (S.survivors.cap < want * sizeof(PairRec)) CU(S.survivors.reserve(want * sizeof(PairRec)));
+    const uint32_t surv_capacity = (uint32_t)std::min<size_t>(S.survivors.cap / sizeof(PairRec), 0xFFFFFFF0u);
+    P.huge_cap = surv_capacity / 5;
+    P.normal_cap = surv_capacity - P.huge_cap;
+    CU(cudaMemsetAsync(S.scan_totals.p, 0, 64, s));   // [0] survivor count, [1] overflow flag, [2] huge survivor count
+    {
+        StageTimer t(ctx, s, ST_COUNT);
+        launch_setup(S.views_d.as<DView>(), S.frames_d.as<DFrame>(), S.bdraws_d.as<DBinDraw>(), S.chunk_base_d.as<uint32_t>(), b.n_chunks,
+                     S.tile_count.as<uint32_t>(), S.survivors.as<PairRec>(), S.scan_totals.as<uint32_t>(), P.normal_cap, P.huge_cap,
+                     ctx->direct_max, ctx->warp_max, s);
+    }
+    {
+        StageTimer t(ctx, s, ST_SCAN);
+        launch_scan(S.tile_count.as<uint32_t>(), S.tile_off.as<uint32_t>(), S.active_tiles.as<ActiveTile>(),
+                    S.scan_sums.as<unsigned long long>(), S.total_pinned, S.scan_totals.as<uint32_t>(), P.n_tiles, s);
+    }
+    // The scan writes its totals straight into page-locked host memory (UVA): a D2H memcpy here would queue
+    // behind the result copies of the previous sub-batch on the copy engine and serialise the pipeline.
+    CU(cudaEventRecord(S.scanned, s));
+    return SLB_OK;
+}
+
+// Phase 2: wait for the scan totals (the pair buffer, the emit grid and the raster grid are sized from them), then
+// emit -> raster -> shade -> post passes.
+static int subbatch_phase2(slb_ctx* ctx, int set, cudaStream_t s) {
+    Scratch& S = ctx->scr[set];
+    Pending& P = S.pending;
+    if (!P.active) return SLB_OK;
+    P.active = false;
+    Batch& b = *static_cast<Batch*>(S.batch);
+    const int n = P.n, W = P.W, H = P.H, first_frame = P.first_frame;
+    const size_t npx = P.npx;
+    slb_result* result = P.result;
+    const bool post = P.post;
+    RasterGrid grid = P.grid;
+    const DFrame* frames_d = S.frames_d.as<DFrame>();
+    const DDraw* draws_d = S.draws_d.as<DDraw>();
+    const DView* views_d = S.views_d.as<DView>();
     for (int attempt = 0;; ++attempt) {
-        // ordinary survivors in [0, normal_cap), huge ones (whole block each in the emit pass) in the last fifth
-        const size_t want = (size_t)total_bin_tris + total_bin_tris / 4 + 8192;
-        if (ctx->survivors.cap < want * sizeof(PairRec)) CU(ctx->survivors.reserve(want * sizeof(PairRec)));
-        const uint32_t surv_capacity = (uint32_t)std::min<size_t>(ctx->survivors.cap / sizeof(PairRec), 0xFFFFFFF0u);
-        const uint32_t huge_cap = surv_capacity / 5;
-        normal_cap = surv_capacity - huge_cap;
-        CU(cudaMemsetAsync(ctx->scan_totals.p, 0, 64, s));   // [0] survivor count, [1] overflow flag, [2] huge survivor count
-        {
-            StageTimer t(ctx, s, ST_COUNT);
-            launch_setup(views_d, frames_d, bdraws_d, ctx->chunk_base_d.as<uint32_t>(), b.n_chunks, ctx->tile_count.as<uint32_t>(),
-                         ctx->survivors.as<PairRec>(), ctx->scan_totals.as<uint32_t>(), normal_cap, huge_cap, ctx->direct_max, ctx->warp_max, s);
-        }
-        {
-            StageTimer t(ctx, s, ST_SCAN);
-            launch_scan(ctx->tile_count.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->active_tiles.as<ActiveTile>(),
-                        ctx->scan_sums.as<unsigned long long>(), ctx->total_pinned, ctx->scan_totals.as<uint32_t>(), n_tiles, s);
-        }
-        // The scan writes its totals straight into page-locked host memory (UVA): a D2H memcpy here would queue
-        // behind the result copies of the previous sub-batch on the copy engine and serialise the pipeline.
-        CU(cudaStreamSynchronize(s));   // the pair buffer, the emit grid and the raster grid are sized from the exact totals
-        if (ctx->total_pinned[3] == 0) break;
-        // more clipped sub-triangles than triangles + 4096 (pathological): grow the survivor buffer and redo the pass
+        CU(cudaEventSynchronize(S.scanned));
+        if (S.total_pinned[3] == 0) break;
+        // more clipped sub-triangles than triangles + 8192 (pathological): grow the survivor buffer and redo the pass
         if (attempt == 4) return fail(ctx, SLB_ERR_RUNTIME, "slb_render_batch: survivor buffer overflow");
-        total_bin_tris = total_bin_tris * 2 + 65536;
-        CU(cudaMemsetAsync(ctx->tile_count.p, 0, (size_t)n_tiles * 4, s));
-        CU(cudaMemsetAsync(ctx->clip_counts.p, 0, (size_t)n * 4, s));
-        CU(cudaMemsetAsync(ctx->huge_counts.p, 0, (size_t)n * 4, s));
+        P.total_bin_tris = P.total_bin_tris * 2 + 65536;
+        CU(cudaMemsetAsync(S.tile_count.p, 0, (size_t)P.n_tiles * 4, s));
+        CU(cudaMemsetAsync(S.clip_counts.p, 0, (size_t)n * 4, s));
+        CU(cudaMemsetAsync(S.huge_counts.p, 0, (size_t)n * 4, s));
+        int rc = subbatch_setup_scan(ctx, S, s);
+        if (rc != SLB_OK) return rc;
     }
-    total_pairs = ctx->total_pinned[0];
-    grid.n_active = ctx->total_pinned[1];
-    n_survivors = ctx->total_pinned[2];
-    n_huge = ctx->total_pinned[4];
-    CU(ctx->pairs.reserve(((size_t)total_pairs + 1) * sizeof(PairRec)));
+    const uint32_t normal_cap = P.normal_cap;
+    uint32_t total_pairs = 0, n_survivors = 0, n_huge = 0;
+    total_pairs = S.total_pinned[0];
+    grid.n_active = S.total_pinned[1];
+    n_survivors = S.total_pinned[2];
+    n_huge = S.total_pinned[4];
+    CU(S.pairs.reserve(((size_t)total_pairs + 1) * sizeof(PairRec)));
     {
         StageTimer t(ctx, s, ST_EMIT);
-        launch_emit(views_d, ctx->survivors.as<PairRec>(), n_survivors, ctx->survivors.as<PairRec>() + normal_cap, n_huge,
-                    ctx->tile_count.as<uint32_t>(), ctx->pairs.as<PairRec>(), total_pairs, s);
+        launch_emit(views_d, S.survivors.as<PairRec>(), n_survivors, S.survivors.as<PairRec>() + normal_cap, n_huge,
+                    S.tile_count.as<uint32_t>(), S.pairs.as<PairRec>(), total_pairs, s);
     }
     {
         StageTimer t(ctx, s, ST_RASTER);
-        launch_raster(b.any_frag_test, views_d, frames_d, draws_d, ctx->active_tiles.as<ActiveTile>(), ctx->pairs.as<PairRec>(), grid, s);
+        launch_raster(b.any_frag_test, views_d, frames_d, draws_d, S.active_tiles.as<ActiveTile>(), S.pairs.as<PairRec>(), grid, s);
     }
     {
         StageTimer t(ctx, s, ST_SHADE);
@@ -1124,19 +1188,19 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     if (post) {
         if (b.any_auto) {   // 1x1 level of the mip chain of the HDR target, taken before background / SSAO
             StageTimer t(ctx, s, ST_POST);
-            const float4* src = result->hdr ? result->hdr + npx * first_frame : ctx->hdr.as<float4>();
+            const float4* src = result->hdr ? result->hdr + npx * first_frame : S.hdr.as<float4>();
             size_t src_stride = npx;
             int sw = W, sh = H; bool flip = false;
             while (sw > 1 || sh > 1) {
                 int dw = sw > 1 ? sw >> 1 : 1, dh = sh > 1 ? sh >> 1 : 1;
                 const bool last = dw == 1 && dh == 1;
-                float4* dst = last ? ctx->avg.as<float4>() : (flip ? ctx->mip_b.as<float4>() : ctx->mip_a.as<float4>());
+                float4* dst = last ? S.avg.as<float4>() : (flip ? S.mip_b.as<float4>() : S.mip_a.as<float4>());
                 size_t dst_stride = last ? 1 : (size_t)dw * dh;
                 launch_downsample(src, sw, sh, dst, n, src_stride, dst_stride, s);
                 ctx->stats.kernel_launches += 1;
                 src = dst; src_stride = dst_stride; sw = dw; sh = dh; flip = !flip;
             }
-            if (W == 1 && H == 1) CU(cudaMemcpyAsync(ctx->avg.p, src, (size_t)n * 16, cudaMemcpyDeviceToDevice, s));
+            if (W == 1 && H == 1) CU(cudaMemcpyAsync(S.avg.p, src, (size_t)n * 16, cudaMemcpyDeviceToDevice, s));
         }
         if (b.any_bg) {
             StageTimer t(ctx, s, ST_POST);
@@ -1159,6 +1223,14 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     ctx->stats.triangles_submitted += b.n_tris;
     ctx->stats.triangles_binned = total_pairs;
     return SLB_OK;
+}
+
+// the two phases back to back (one sub-batch at a time: slb_render_batch_host)
+static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, slb_result* result, int first_frame,
+                           const slb_result* depth_peel, cudaStream_t s) {
+    int rc = subbatch_phase1(ctx, 0, scenes, n, result, first_frame, depth_peel, s);
+    if (rc != SLB_OK) return rc;
+    return subbatch_phase2(ctx, 0, s);
 }
 
 static void collect_times(slb_ctx* ctx) {
@@ -1186,10 +1258,20 @@ extern "C" int slb_render_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int3
     for (int i = 0; i < n_scenes; ++i) { int rc = validate_scene(ctx, scenes[i], result); if (rc != SLB_OK) return rc; }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    for (int at = 0; at < n_scenes; at += ctx->max_subbatch) {
-        int n = std::min(ctx->max_subbatch, n_scenes - at);
-        int rc = render_subbatch(ctx, scenes + at, n, result, first_frame + at, depth_peel, s);
-        if (rc != SLB_OK) return rc;
+    // Software pipeline over the two scratch sets: the first phase of sub-batch k+1 (marshal, upload, clear, set-up,
+    // scan) is queued BEFORE the host waits for the scan totals of sub-batch k, so the GPU always has work while the
+    // host sizes and queues the second phase (emit, raster, shade). Stream order: P1(0) P1(1) P2(0) P1(2) P2(1) ...
+    int k = 0, rc = SLB_OK;
+    for (int at = 0; at < n_scenes && rc == SLB_OK; at += ctx->max_subbatch, ++k) {
+        const int n = std::min(ctx->max_subbatch, n_scenes - at);
+        rc = subbatch_phase1(ctx, k & 1, scenes + at, n, result, first_frame + at, depth_peel, s);
+        if (rc == SLB_OK && k > 0) rc = subbatch_phase2(ctx, (k - 1) & 1, s);
+    }
+    if (rc == SLB_OK && k > 0) rc = subbatch_phase2(ctx, (k - 1) & 1, s);
+    if (rc != SLB_OK) {   // leave no half-issued sub-batch behind
+        cudaStreamSynchronize(s);
+        ctx->scr[0].pending.active = ctx->scr[1].pending.active = false;
+        return rc;
     }
     if (ctx->time_kernels) collect_times(ctx);
     return SLB_OK;
