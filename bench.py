@@ -133,13 +133,23 @@ def main():
     numa_node = sdist.bind_to_gpu_numa_node(local) if world > 1 else None   # host buffers next to the rank's GPU
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
     # ---- load: rank 0 builds the pool, ONE broadcast of the asset arena ----
-    pool = synth.mesh_pool(POOL) if rank == 0 else None
-    pool = sdist.broadcast_meshes(pool, 0, dev)
+    # NCCL logs its version banner to stdout when the first communicator comes up: keep fd 1 pointed at stderr until
+    # then, so that rank 0's stdout carries exactly ONE JSON line.
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+        pool = synth.mesh_pool(POOL) if rank == 0 else None
+        pool = sdist.broadcast_meshes(pool, 0, dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     ctx = lib.Context(local)
     if args.subbatch:
         ctx.set_option(abi.OPT_MAX_SUBBATCH, args.subbatch)
