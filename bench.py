@@ -184,9 +184,9 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         step()
-        stage_ms += np.array(list(ctx.stats().last_kernel_ms))
     ev1.record()
     barrier()
+    stage_ms += np.array(list(ctx.stats().last_kernel_ms))    # stage events of the whole timed region, read after it
     sampler.stop_flag = True
     ms = ev0.elapsed_time(ev1)
     launches = ctx.stats().kernel_launches - launches0

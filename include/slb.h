@@ -271,8 +271,8 @@ typedef struct slb_stats {
     uint64_t triangles_binned; /* (sub)triangle-tile pairs emitted by the binner, last batch */
     uint64_t bytes_h2d;        /* descriptor uploads */
     uint64_t bytes_d2h;
-    float last_kernel_ms[8];   /* when option TIME_KERNELS is on: setup-count, scan, setup-emit, raster,
-                                  shade/store, ssao, post, other — of the last slb_render_batch call */
+    float last_kernel_ms[8];   /* when option TIME_KERNELS is on: clears, setup, scan, emit, raster, shade/store, ssao,
+                                  post — summed over the render calls since the previous slb_ctx_get_stats */
 } slb_stats;
 int slb_ctx_get_stats(slb_ctx* ctx, slb_stats* out);
 

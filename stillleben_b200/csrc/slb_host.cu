@@ -274,8 +274,10 @@ extern "C" int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value) {
     }
 }
 
+static void collect_times(slb_ctx* ctx);
 extern "C" int slb_ctx_get_stats(slb_ctx* ctx, slb_stats* out) {
     if (!ctx || !out) return SLB_ERR_INVALID_ARGUMENT;
+    collect_times(ctx);   // waits for the stage events recorded since the previous call (SLB_OPT_TIME_KERNELS)
     *out = ctx->stats;
     return SLB_OK;
 }
@@ -1233,6 +1235,8 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
     return subbatch_phase2(ctx, 0, s);
 }
 
+// Stage times are recorded as events on the stream and only read here, on demand: no synchronisation inside the
+// render calls, so timing a run does not drain the sub-batch pipeline between calls.
 static void collect_times(slb_ctx* ctx) {
     if (ctx->events.empty()) return;
     float acc[ST_N] = {0};
@@ -1273,7 +1277,6 @@ extern "C" int slb_render_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int3
         ctx->scr[0].pending.active = ctx->scr[1].pending.active = false;
         return rc;
     }
-    if (ctx->time_kernels) collect_times(ctx);
     return SLB_OK;
 }
 
@@ -1326,7 +1329,6 @@ extern "C" int slb_render_batch_host(slb_ctx* ctx, const slb_scene_desc* scenes,
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->copy_stream));
     if (dbg) fprintf(stderr, "[slb] done at %.2f ms\n", now() - t_begin);
-    if (ctx->time_kernels) collect_times(ctx);
     return SLB_OK;
 }
 

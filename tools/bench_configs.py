@@ -32,10 +32,10 @@ def run(ctx, scenes, W, H, mask, label, steps=3, subbatch=None):
     e0.record()
     for _ in range(steps):
         ctx.render(scenes, result=res, descs=descs)
-        stage += np.array(list(ctx.stats().last_kernel_ms))
     ctx.synchronize()
     e1.record()
     torch.cuda.synchronize()
+    stage += np.array(list(ctx.stats().last_kernel_ms))
     ctx.set_option(abi.OPT_TIME_KERNELS, 0)
     ms = e0.elapsed_time(e1) / steps
     print(json.dumps({"config": label, "frames_per_s": len(scenes) / ms * 1e3, "ms_per_frame": ms / len(scenes),
