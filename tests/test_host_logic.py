@@ -70,3 +70,14 @@ def test_vertex_dtype_is_reference_layout():
     dt = abi.VERTEX_DTYPE
     assert dt.itemsize == 68
     assert [dt.fields[k][1] for k in ("position", "uv", "color", "tangent", "vertex_index", "normal")] == [0, 12, 20, 36, 52, 56]
+
+
+def test_cpulist_parser_and_numa_binding_are_harmless_without_a_gpu():
+    from stillleben_b200 import dist
+    assert dist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert dist._parse_cpulist("") == set()
+    import os
+    before = os.sched_getaffinity(0)
+    assert dist.bind_to_gpu_numa_node(0) in (None, 0, 1, 2, 3, 4, 5, 6, 7)     # no GPU here: None, and nothing changes
+    if dist.bind_to_gpu_numa_node(0) is None:
+        assert os.sched_getaffinity(0) == before
