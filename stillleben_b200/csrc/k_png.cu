@@ -13,6 +13,7 @@
 // Row 0 of the tensor is the top row of the file (the binding's flipud + Magnum's bottom-up rows cancel).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -129,6 +130,186 @@ __global__ void __launch_bounds__(128) k_png_rows(const uint8_t* __restrict__ im
     ri.adler_b = sb % 65521u;
     ri.len = (uint32_t)seg_len;
     info[t] = ri;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-per-segment encoder: the same greedy parse and the same bytes as k_png_rows, computed in parallel.
+//   1. every lane filters 16 bytes of the segment into shared memory;
+//   2. run lengths at distance 1 and bpp for every position: "next mismatch" by a per-lane backward walk + a warp
+//      suffix-min over the lanes; best(i), nxt(i) = i + (best >= 4 ? best : 1);
+//   3. the greedy token starts are the orbit of position 0 under nxt: pointer jumping (10 doubling rounds);
+//   4. token bit lengths -> warp prefix sum -> every lane ORs its tokens into the block image in shared memory;
+//   5. CRC-32 of the block by right-aligned per-lane chunks (the register of a chunk is shifted into place with one
+//      multiplication by x^(8 c m) from a table), Adler-32 partial sums by a warp reduction.
+// A byte-serial thread per segment runs at 4 of 32 lanes (profiles/r01_d_aux_kernels.md); this keeps all lanes busy.
+#define PNG_WARPS 8
+#define PNG_MAX_CHUNK 20                                 // ceil(max block bytes / 32)
+__constant__ uint32_t c_pow[PNG_MAX_CHUNK + 1][32];      // x^(8 c m) mod P, reflected: shifts a CRC register over c*m bytes
+struct SegShared {
+    uint8_t f[PNG_SEG + 16];
+    uint16_t jump[PNG_SEG + 2];
+    uint16_t len[PNG_SEG + 2];                            // best match length at the position (0..258), bit 15: distance is bpp
+    uint8_t mark[PNG_SEG + 2];
+    uint32_t out[160];
+};
+__device__ __forceinline__ void or_bits(uint32_t* out, uint32_t bitpos, uint32_t v, int nbits) {
+    const uint32_t w = bitpos >> 5, sh = bitpos & 31;
+    atomicOr(out + w, v << sh);
+    if (sh + nbits > 32) atomicOr(out + w + 1, v >> (32 - sh));
+}
+__global__ void __launch_bounds__(PNG_WARPS * 32) k_png_rows_warp(const uint8_t* __restrict__ images, int n_images, int H, int W, int channels,
+                                                                  int bpc, int n_seg, uint8_t* __restrict__ rows_out, size_t seg_bound,
+                                                                  RowInfo* __restrict__ info) {
+    __shared__ SegShared s_all[PNG_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t t = (size_t)blockIdx.x * PNG_WARPS + warp;
+    if (t >= (size_t)n_images * H * n_seg) return;
+    SegShared& S = s_all[warp];
+    const size_t rowi = t / n_seg;
+    const int seg = (int)(t - rowi * n_seg);
+    const int bpp = channels * bpc;
+    const size_t row_bytes = (size_t)W * bpp;
+    const uint8_t* row = images + rowi * row_bytes;
+    const int beg = seg * PNG_SEG, n = (int)min((size_t)PNG_SEG, row_bytes - (size_t)beg);   // data bytes of this block
+    // 1. filtered bytes
+    for (int r = lane; r < n; r += 32) {
+        const int i = beg + r;
+        const uint32_t cur = raw_byte(row, i, bpc), left = i >= bpp ? raw_byte(row, i - bpp, bpc) : 0u;
+        S.f[r] = (uint8_t)(cur - left);
+    }
+    for (int w = lane; w < 160; w += 32) S.out[w] = 0u;
+    __syncwarp();
+    // 2. run lengths: nz_d[r] = first position j >= r where f[j] != f[j - d] (or j < d, or j == n)
+    const int r0 = lane * 16;
+    int best_len[16];
+    {
+        int nz1 = PNG_SEG + 1, nzb = PNG_SEG + 1;   // first mismatch inside this lane's 16 positions
+        for (int k = 15; k >= 0; --k) {
+            const int r = r0 + k;
+            if (r >= n) { nz1 = nzb = min(r, n); continue; }
+            if (r < 1 || S.f[r] != S.f[r - 1]) nz1 = r;
+            if (r < bpp || S.f[r] != S.f[r - bpp]) nzb = r;
+        }
+        // suffix-min over the lanes: the first mismatch at or after the START of lane l's block
+        int s1 = nz1, sb_ = nzb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_down_sync(0xffffffffu, s1, o), b = __shfl_down_sync(0xffffffffu, sb_, o);
+            if (lane + o < 32) { s1 = min(s1, a); sb_ = min(sb_, b); }
+        }
+        int c1 = __shfl_down_sync(0xffffffffu, s1, 1), cb = __shfl_down_sync(0xffffffffu, sb_, 1);   // first mismatch after this lane's block
+        if (lane == 31) { c1 = n; cb = n; }
+        c1 = min(c1, n); cb = min(cb, n);
+        for (int k = 15; k >= 0; --k) {
+            const int r = r0 + k;
+            best_len[k] = 0;
+            if (r >= n) continue;
+            if (r < 1 || S.f[r] != S.f[r - 1]) c1 = r;
+            if (r < bpp || S.f[r] != S.f[r - bpp]) cb = r;
+            const int l1 = min(258, c1 - r), lb = bpp > 1 ? min(258, cb - r) : 0;
+            int best = l1, far = 0;
+            if (lb > l1) { best = lb; far = 1; }
+            best_len[k] = best;
+            S.len[r] = (uint16_t)(best | (far << 15));
+            S.jump[r] = (uint16_t)min(n, r + (best >= 4 ? best : 1));
+            S.mark[r] = r == 0 ? 1 : 0;
+        }
+        if (lane == 0) { S.jump[n] = (uint16_t)n; S.mark[n] = 0; }
+    }
+    __syncwarp();
+    // 3. orbit of position 0 under nxt by pointer jumping
+    for (int round = 0; round < 10; ++round) {
+        int nj[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int r = r0 + k;
+            nj[k] = n;
+            if (r < n) {
+                const int j = S.jump[r];
+                if (S.mark[r]) S.mark[j] = 1;
+                nj[k] = S.jump[j];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if (r0 + k < n) S.jump[r0 + k] = (uint16_t)nj[k];
+        __syncwarp();
+    }
+    // 4. token codes and bit offsets
+    uint32_t code[16]; uint8_t nb[16];
+    int local_bits = 0;
+    uint32_t sa = 0; unsigned long long sbw = 0;      // Adler partial sums over this lane's filtered bytes
+    const int L = n + (seg == 0 ? 1 : 0);              // filtered bytes this block carries
+    const int first = seg == 0 ? 1 : 0;                // index of data byte 0 inside the block
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int r = r0 + k;
+        nb[k] = 0; code[k] = 0;
+        if (r >= n) continue;
+        const uint32_t v = S.f[r];
+        sa += v; sbw += (unsigned long long)(L - (r + first)) * v;
+        if (!S.mark[r]) continue;
+        const int len = best_len[k];
+        if (len >= 4) {
+            int c = 0;
+            while (c < 28 && (int)c_len_base[c + 1] <= len) ++c;
+            const int sym = 257 + c;
+            uint32_t bits; int nbits;
+            if (sym < 280) { bits = rev_bits(sym - 256, 7); nbits = 7; } else { bits = rev_bits(0xC0 + (sym - 280), 8); nbits = 8; }
+            const int eb = c_len_extra[c];
+            if (eb) { bits |= (uint32_t)(len - c_len_base[c]) << nbits; nbits += eb; }
+            const int dist = (S.len[r] >> 15) ? bpp : 1;
+            bits |= rev_bits((uint32_t)(dist - 1), 5) << nbits; nbits += 5;
+            code[k] = bits; nb[k] = (uint8_t)nbits;
+        } else if (v < 144) { code[k] = rev_bits(0x30 + v, 8); nb[k] = 8; }
+        else { code[k] = rev_bits(0x190 + (v - 144), 9); nb[k] = 9; }
+        local_bits += nb[k];
+    }
+    int inc = local_bits;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += a; }
+    const int total_bits = __shfl_sync(0xffffffffu, inc, 31);
+    const int head_bits = 3 + (seg == 0 ? 8 : 0);
+    uint32_t bitpos = (uint32_t)(head_bits + inc - local_bits);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) if (nb[k]) { or_bits(S.out, bitpos, code[k], nb[k]); bitpos += nb[k]; }
+    if (lane == 0) {
+        or_bits(S.out, 0u, 2u, 3);                                             // BFINAL = 0, BTYPE = 01
+        if (seg == 0) or_bits(S.out, 3u, rev_bits(0x30 + 1, 8), 8);            // filter-type byte 1 as a literal
+    }
+    // end of block (7 zero bits), empty stored block header (3 zero bits), pad to a byte, 00 00 FF FF
+    const int nbytes = (head_bits + total_bits + 10 + 7) >> 3;
+    const int total = nbytes + 4;
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t o = (uint32_t)(nbytes + 2) * 8u;
+        or_bits(S.out, o, 0xFFFFu, 16);
+    }
+    __syncwarp();
+    // 5. copy out, CRC-32, Adler-32
+    const uint8_t* ob = reinterpret_cast<const uint8_t*>(S.out);
+    uint8_t* dst = rows_out + t * seg_bound;
+    for (int i = lane; i < total; i += 32) dst[i] = ob[i];
+    const int c = (total + 31) >> 5;                                           // chunk bytes per lane, right aligned
+    const int stop = total - (31 - lane) * c, start = stop - c;
+    uint32_t reg = (start <= 0 && stop > 0) ? 0xFFFFFFFFu : 0u;                // the chunk holding byte 0 carries the initial register
+    for (int i = max(start, 0); i < stop; ++i) reg = c_crc_table[(reg ^ ob[i]) & 0xff] ^ (reg >> 8);
+    if (stop <= 0) reg = 0u;
+    uint32_t shifted = multmodp(c_pow[c][31 - lane], reg);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) shifted ^= __shfl_xor_sync(0xffffffffu, shifted, o);
+    if (seg == 0 && lane == 0) { sa += 1u; sbw += (unsigned long long)L; }      // the filter byte (value 1, first in the block)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sbw += __shfl_xor_sync(0xffffffffu, sbw, o); }
+    if (lane == 0) {
+        RowInfo ri;
+        ri.bytes = (uint32_t)total;
+        ri.crc = ~shifted;
+        ri.adler_a = sa % 65521u;
+        ri.adler_b = sbw % 65521u;
+        ri.len = (uint32_t)L;
+        info[t] = ri;
+    }
 }
 
 __device__ __forceinline__ void put_be32(uint8_t* p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
@@ -249,6 +430,16 @@ void png_upload_tables() {
     x2n[0] = p;
     for (int k = 1; k < 32; ++k) x2n[k] = p = mul(p, p);
     cudaMemcpyToSymbol(c_x2n, x2n, sizeof x2n);
+    // x^(8 c m) for the warp encoder's chunk shifts: x^8 by squaring x three times, then powers by multiplication
+    static uint32_t pw[PNG_MAX_CHUNK + 1][32];
+    const uint32_t x8 = x2n[3];
+    for (int c = 0; c <= PNG_MAX_CHUNK; ++c) {
+        uint32_t xc = 1u << 31;                                   // x^0
+        for (int i = 0; i < c; ++i) xc = mul(xc, x8);             // x^(8 c)
+        uint32_t acc = 1u << 31;
+        for (int m = 0; m < 32; ++m) { pw[c][m] = acc; acc = mul(acc, xc); }
+    }
+    cudaMemcpyToSymbol(c_pow, pw, sizeof pw);
 }
 int png_segments(int W, int channels, int bpc) { return (int)(((size_t)W * channels * bpc + PNG_SEG - 1) / PNG_SEG); }
 size_t png_seg_bound() { return ((size_t)(PNG_SEG + 1) * 9 + 7) / 8 + 16; }
@@ -260,7 +451,9 @@ void launch_png_encode(const uint8_t* images, int n, int H, int W, int channels,
                        uint32_t* row_offset, uint8_t* out, size_t out_stride, uint32_t* sizes, cudaStream_t s) {
     const int n_seg = png_segments(W, channels, bpc);
     const size_t blocks = (size_t)n * H * n_seg, sb = png_seg_bound();
-    k_png_rows<<<(unsigned)((blocks + 127) / 128), 128, 0, s>>>(images, n, H, W, channels, bpc, n_seg, rows_scratch, sb, (RowInfo*)row_info);
+    static const bool serial = getenv("SLB_PNG_SERIAL") != nullptr;   // the byte-serial reference encoder (same bytes)
+    if (serial) k_png_rows<<<(unsigned)((blocks + 127) / 128), 128, 0, s>>>(images, n, H, W, channels, bpc, n_seg, rows_scratch, sb, (RowInfo*)row_info);
+    else k_png_rows_warp<<<(unsigned)((blocks + PNG_WARPS - 1) / PNG_WARPS), PNG_WARPS * 32, 0, s>>>(images, n, H, W, channels, bpc, n_seg, rows_scratch, sb, (RowInfo*)row_info);
     k_png_finalize<<<n, PNG_FIN_THREADS, 0, s>>>((const RowInfo*)row_info, H, W, channels, bpc, n_seg, out, out_stride, sizes, row_offset);
     k_png_gather<<<(unsigned)blocks, 128, 0, s>>>(rows_scratch, sb, (const RowInfo*)row_info, row_offset, H * n_seg, out, out_stride);
 }
