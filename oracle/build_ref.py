@@ -1,0 +1,66 @@
+"""Recipe for oracle/_ref/: pieces of the REFERENCE ITSELF compiled from the sources where they lie under
+/root/reference (never copied into this repo), used to pin the oracle restatement (tests/test_oracle_ref.py) and to
+generate the committed golden fixtures (tests/golden/make_ref_golden.py). Test infrastructure only.
+
+  diff      python/src/diff.cu + bridge_diff.cpp  -> oracle/_ref/diff/libstillleben_diff_python.so
+            (a self-contained torch extension: torch/extension.h only; CPU and CUDA branches)
+  meshtool  src/mesh_tools/{consolidate,compute_tangents}.cpp + GL-less Corrade/Magnum/CgltfImporter from contrib/
+            -> oracle/_ref/meshtool (dumps the reference's own consolidated 68-byte vertex stream)
+  glsl      src/shaders/*.{vert,frag,glsl} compiled VERBATIM as C++ behind oracle/glsl_compat.h
+            -> oracle/_ref/libglslref.so
+
+Usage: python oracle/build_ref.py [diff] [meshtool] [glsl]   (no argument = everything that is not built yet)
+Outputs only into oracle/_ref/ (git-ignored, not gpurun-ignored). Needs /root/reference; a no-op without it.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("SLB_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+
+
+def build_diff(force=False):
+    """The reference's torch extension for config 4 (python/src/diff.cu:13-193, bridge_diff.cpp:13-176)."""
+    out = os.path.join(OUT, "diff")
+    so = os.path.join(out, "libstillleben_diff_python.so")
+    if os.path.exists(so) and not force:
+        return so
+    os.makedirs(out, exist_ok=True)
+    from torch.utils import cpp_extension
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    cpp_extension.load(
+        name="libstillleben_diff_python",
+        sources=[os.path.join(REF, "python/src/bridge_diff.cpp"), os.path.join(REF, "python/src/diff.cu")],
+        extra_include_paths=[os.path.join(REF, "python/src")],
+        extra_cuda_cflags=["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"],
+        build_directory=out, is_python_module=False, verbose=False, with_cuda=True)
+    return so
+
+
+def load_diff():
+    """Import oracle/_ref/diff/libstillleben_diff_python.so (the prebuilt file; /root/reference is not needed)."""
+    import importlib.util
+    import torch  # noqa: F401  (libtorch must be loaded first)
+    so = os.path.join(OUT, "diff", "libstillleben_diff_python.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("libstillleben_diff_python", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main(argv):
+    if not os.path.isdir(REF):
+        print("oracle/build_ref.py: no reference tree at", REF, "- keeping prebuilt oracle/_ref as is")
+        return 0
+    want = argv or ["diff", "meshtool", "glsl"]
+    if "diff" in want:
+        print("diff ->", build_diff(force="--force" in argv))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main([a for a in sys.argv[1:]]))

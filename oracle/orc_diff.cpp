@@ -11,9 +11,58 @@
 
 static inline int clampi(int v, int n) { v = v > 0 ? v : 0; return v < n - 1 ? v : n - 1; }
 
+// The reference ships TWO implementations of both mask functions and they differ: the CUDA kernels
+// (diff.cu, the branch the product follows: the module is CUDA-only, diff.py:5-9) treat every pixel, with a
+// clamped 3x3 window walked column-offset-outer; the CPU branch of the bridge (bridge_diff.cpp:36-63,105-152)
+// skips the one-pixel image border (valid stays 1, dilated mask / coordinates stay 0 there), walks the window
+// row-offset-outer, and writes the neighbour's coordinate only when the pixel really is dilated.
+// variant 0 = CUDA kernels (default), 1 = CPU branch. The CPU branch exists so that the restatement can be pinned
+// against oracle/_ref/diff (the reference's own extension) in a container without a GPU.
+static int g_variant = 0;
+
 extern "C" {
 
+void orc_diff_set_variant(int v) { g_variant = v; }
+
+static void sobel_valid_mask_cpu_branch(const int16_t* inst, const float* depth, uint8_t* valid, int H, int W) {
+    for (size_t p = 0; p < (size_t)H * W; ++p) valid[p] = 1;
+    for (int h = 1; h < H - 1; ++h)
+        for (int w = 1; w < W - 1; ++w) {
+            int16_t cur = inst[(size_t)h * W + w];
+            if (cur == 0) continue;
+            float d = depth[(size_t)h * W + w];
+            for (int x = -1; x <= 1; ++x)
+                for (int y = -1; y <= 1; ++y) {
+                    size_t q = (size_t)(h + x) * W + (w + y);
+                    if (inst[q] != cur && inst[q] != 0 && depth[q] < d) valid[(size_t)h * W + w] = 0;
+                }
+        }
+}
+static void dilate_object_mask_cpu_branch(const uint8_t* mask, const uint8_t* valid, const float* coords, int cs, uint8_t* mask_out,
+                                          float* coords_out, int H, int W) {
+    for (size_t p = 0; p < (size_t)H * W; ++p) { mask_out[p] = 0; coords_out[p * 3] = coords_out[p * 3 + 1] = coords_out[p * 3 + 2] = 0.0f; }
+    for (int h = 1; h < H - 1; ++h)
+        for (int w = 1; w < W - 1; ++w) {
+            size_t p = (size_t)h * W + w;
+            mask_out[p] = mask[p];
+            for (int k = 0; k < 3; ++k) coords_out[p * 3 + k] = coords[p * cs + k];
+            if (mask[p] != 0) continue;
+            bool allValid = true, allBackground = true;
+            float c3[3] = {0, 0, 0};
+            for (int x = -1; x <= 1; ++x)
+                for (int y = -1; y <= 1; ++y) {
+                    size_t q = (size_t)(h + x) * W + (w + y);
+                    if (mask[q] != 0) { allBackground = false; for (int k = 0; k < 3; ++k) c3[k] = coords[q * cs + k]; }
+                    if (valid[q] == 0) { allValid = false; break; }
+                }
+            if (allBackground || !allValid) continue;
+            mask_out[p] = 1;
+            for (int k = 0; k < 3; ++k) coords_out[p * 3 + k] = c3[k];
+        }
+}
+
 void orc_diff_sobel_valid_mask(const int16_t* inst, const float* depth, uint8_t* valid, int H, int W) {
+    if (g_variant == 1) { sobel_valid_mask_cpu_branch(inst, depth, valid, H, W); return; }
     for (int r = 0; r < H; ++r)
         for (int c = 0; c < W; ++c) {
             uint8_t ok = 1;
@@ -32,6 +81,7 @@ void orc_diff_sobel_valid_mask(const int16_t* inst, const float* depth, uint8_t*
 
 void orc_diff_dilate_object_mask(const uint8_t* mask, const uint8_t* valid, const float* coords, int coord_stride,
                                  uint8_t* mask_out, float* coords_out /* HxWx3 dense */, int H, int W) {
+    if (g_variant == 1) { dilate_object_mask_cpu_branch(mask, valid, coords, coord_stride, mask_out, coords_out, H, W); return; }
     for (int r = 0; r < H; ++r)
         for (int c = 0; c < W; ++c) {
             size_t p = (size_t)r * W + c;

@@ -111,3 +111,41 @@ def test_gradient_sign_like_the_reference_test_grad():
         assert delta.shape == (1, 6)
         assert float(delta[0][param]) > 0, (param, delta)
         obj.set_pose(gt_pose)
+
+
+def _ref_ext():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import build_ref
+    ext = build_ref.load_diff()
+    if ext is None:
+        pytest.skip("oracle/_ref/diff not built")
+    return ext
+
+
+@pytest.mark.parametrize("seed,H,W", [(0, 64, 96), (1, 480, 640), (2, 32, 32)])
+def test_mask_kernels_match_the_reference_cuda_kernels(gpu_ctx, seed, H, W):
+    """python/src/diff.cu (the reference's own kernels, compiled for sm_100a into oracle/_ref/diff) run on the same device
+    maps as k_sobel_valid / k_dilate and the oracle: all three must agree bit for bit. Sizes are multiples of the
+    reference's 32x32 blocks — for other sizes its halo load leaves shared memory uninitialised at the right / bottom
+    image edge (diff.cu:36-64: only block-boundary threads load the halo)."""
+    ext = _ref_ext()
+    sl.init_cuda(0)
+    dev = torch.device("cuda", 0)
+    rgb, inst, coord4, grad, P, poses, ids = diff_ref.synthetic_inputs(seed, H=H, W=W)
+    inst_t, depth_t = torch.from_numpy(inst).to(dev), torch.from_numpy(np.ascontiguousarray(coord4[..., 3])).to(dev)
+    coord_t = torch.from_numpy(np.ascontiguousarray(coord4[..., :3])).to(dev)
+    valid_ref = ext.generate_sobel_valid_mask(inst_t, depth_t)
+    valid_mine = diff.generate_sobel_valid_mask(inst_t, depth_t)
+    valid_orc = diff_ref.masks(inst, np.ascontiguousarray(coord4[..., 3])).astype(bool)
+    assert torch.equal(valid_ref, valid_mine)
+    assert np.array_equal(valid_ref.cpu().numpy(), valid_orc)
+    assert (~valid_orc).sum() > 0
+    for idx in ids[:-1]:
+        mask_t = inst_t == int(idx)
+        m_ref, c_ref = ext.dilate_object_mask(mask_t, valid_ref, coord_t)
+        m_mine, c_mine = diff.dilate_object_mask(mask_t, valid_mine, coord_t)
+        m_orc, c_orc = diff_ref.dilate((inst == idx).astype(np.uint8), valid_orc.astype(np.uint8), coord4)
+        assert torch.equal(m_ref, m_mine) and np.array_equal(m_ref.cpu().numpy(), m_orc)
+        assert torch.equal(c_ref, c_mine) and np.array_equal(c_ref.cpu().numpy(), c_orc)
