@@ -52,13 +52,31 @@ def load_diff():
     return mod
 
 
+def build_meshtool(force=False):
+    """The reference's mesh front end: src/mesh_tools/{consolidate,compute_tangents}.cpp + vendored GL-less
+    Corrade / Magnum / CgltfImporter (oracle/build_magnum.sh), driven by oracle/ref_meshtool.cpp."""
+    exe = os.path.join(OUT, "meshtool")
+    if os.path.exists(exe) and not force:
+        return exe
+    prefix = subprocess.check_output(["bash", os.path.join(HERE, "build_magnum.sh")], text=True).strip().splitlines()[-1]
+    libs = [f"{prefix}/lib/magnum/importers/lib{n}.a" for n in ("CgltfImporter", "StbImageImporter", "AnyImageImporter")]
+    libs += [f"{prefix}/lib/lib{n}.a" for n in ("MagnumMeshTools", "MagnumTrade", "Magnum", "CorradePluginManager", "CorradeUtility")]
+    os.makedirs(OUT, exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", f"-I{prefix}/include", f"-I{REF}/include", os.path.join(HERE, "ref_meshtool.cpp"),
+                           os.path.join(REF, "src/mesh_tools/consolidate.cpp"), os.path.join(REF, "src/mesh_tools/compute_tangents.cpp"),
+                           "-o", exe] + libs + ["-ldl"])
+    return exe
+
+
 def main(argv):
     if not os.path.isdir(REF):
         print("oracle/build_ref.py: no reference tree at", REF, "- keeping prebuilt oracle/_ref as is")
         return 0
-    want = argv or ["diff", "meshtool", "glsl"]
+    want = [a for a in argv if not a.startswith("-")] or ["diff", "meshtool", "glsl"]
     if "diff" in want:
         print("diff ->", build_diff(force="--force" in argv))
+    if "meshtool" in want:
+        print("meshtool ->", build_meshtool(force="--force" in argv))
     return 0
 
 

@@ -1,8 +1,8 @@
 """Generates the committed fixtures under tests/golden/ (run in the build container, where
 /root/reference exists; the GPU box only reads the .npz files):
 
-  cube_glb_mesh.npz      the reference's tests/cube.glb after consolidation (stillleben_b200.gltf)
-  bunny_mesh.npz         the reference's tests/stanford_bunny/scene.gltf, texture reduced to 256^2
+  (cube_glb_mesh.npz / bunny_mesh.npz: the reference's two test assets after the reference's OWN consolidation — written by
+   make_ref_golden.py, run it first)
   golden_cube.npz        oracle output for the reference's "vertex indices" test scene (tests/basic.cpp:375-453) at 320x240
   golden_bunny.npz       oracle output for the reference's "render" test scene (tests/basic.cpp:108-261) at 320x240, lit
   golden_tabletop.npz    oracle output of a small procedural table-top scene (regression pin)
@@ -44,14 +44,7 @@ def save_frame(path, frame):
 
 
 def main():
-    cube = gltf.load(os.path.join(REF, "cube.glb"))
-    save_mesh(os.path.join(HERE, "cube_glb_mesh.npz"), cube)
-    bunny = gltf.load(os.path.join(REF, "stanford_bunny", "scene.gltf"))
-    from PIL import Image
-    for im in bunny.images:      # 2048^2 RGB -> 256^2 keeps the fixture small
-        im.pixels = np.ascontiguousarray(np.asarray(Image.fromarray(im.pixels).resize((256, 256), Image.BOX)))
-    save_mesh(os.path.join(HERE, "bunny_mesh.npz"), bunny)
-
+    # cube_glb_mesh.npz / bunny_mesh.npz are written by make_ref_golden.py from the REFERENCE's own consolidation
     assets = ou.OracleAssets()
     for name, scene in (("golden_cube", fixtures.cube_test_scene(320, 240)), ("golden_bunny", fixtures.bunny_test_scene(320, 240, lit=True)),
                         ("golden_tabletop", fixtures.small_tabletop_scene())):

@@ -5,10 +5,12 @@ the vectors do). Needs oracle/_ref (python oracle/build_ref.py) and /root/refere
                     plain tensors) driving the reference's compiled extension oracle/_ref/diff (python/src/bridge_diff.cpp,
                     CPU branch — no GPU here): compute_image_space_gradients, dilate_object_mask per object,
                     backpropagate_gradient_to_poses, apply_pose_delta.
-  cube_glb_ref.npz / bunny_ref.npz
-                    the reference's src/mesh_tools/consolidate.cpp + compute_tangents.cpp run through oracle/_ref/meshtool
-                    on the reference's two test assets: the consolidated 68-byte vertex stream, indices, sub-mesh table,
-                    importer material attributes.
+  cube_glb_mesh.npz / bunny_mesh.npz / kitchen_sink_mesh.npz / pbr_patch_mesh.npz
+                    the reference's src/mesh_tools/consolidate.cpp + compute_tangents.cpp + vendored CgltfImporter run through
+                    oracle/_ref/meshtool on the reference's two test assets and on tests/golden/assets/*.glb: the
+                    consolidated 68-byte vertex stream, indices, sub-mesh table, materials as RenderShader::setMaterial
+                    resolves them, textures with sampler state. tests/test_oracle_ref.py asserts stillleben_b200/gltf.py
+                    reproduces them byte for byte.
 
     python tests/golden/make_ref_golden.py [diff] [mesh]
 """
@@ -134,16 +136,46 @@ def make_diff():
     print("wrote golden_diff.npz")
 
 
+# Magnum sampler enums of the dump -> the ABI's (GL-style) enums
+_WRAP = {0: 0, 1: 2, 2: 1, 3: 3}              # Repeat, MirroredRepeat, ClampToEdge, ClampToBorder -> abi.WRAP_*
+_MINF = {(0, 0): 0, (1, 0): 1, (0, 1): 2, (1, 1): 3, (0, 2): 4, (1, 2): 5}     # (filter, mipmap) -> abi.FILTER_*
+
+
+def ref_dump_to_mesh_npz(d, max_image=None):
+    """The dump of oracle/_ref/meshtool in the fixture format of tests/fixtures.load_mesh (textures -> images with their
+    sampler state, one per glTF texture, as Mesh::loadVisual creates one GL texture per TextureData: mesh.cpp:633-663)."""
+    from PIL import Image
+    pos = d["vertices"].view(np.float32).reshape(len(d["vertices"]), -1)[:, :3]
+    out = {"vertices": d["vertices"], "indices": d["indices"], "submeshes": d["submeshes"],
+           "bbox_min": pos.min(0).astype(np.float32), "bbox_max": pos.max(0).astype(np.float32),
+           "materials": d["materials"][:, :15]}
+    for t, (img, minf, mip, magf, ws, wt) in enumerate(d["textures"]):
+        px = d[f"image{img}"]
+        if max_image and px.shape[0] > max_image:        # keeps the fixture small (the bunny's 2048^2 texture)
+            px = np.ascontiguousarray(np.asarray(Image.fromarray(px).resize((max_image, max_image), Image.BOX)))
+        out[f"image{t}"] = px
+        out[f"image{t}_sampler"] = np.array([_WRAP[int(ws)], _WRAP[int(wt)], _MINF[(int(minf), int(mip))], int(magf)])
+    return out
+
+
 def make_mesh():
+    import hashlib
+    import ref_meshdump
     tool = os.path.join(ROOT, "oracle", "_ref", "meshtool")
     assert os.path.exists(tool), "run python oracle/build_ref.py meshtool first"
-    for src, dst in (("tests/cube.glb", "cube_glb_ref.npz"), ("tests/stanford_bunny/scene.gltf", "bunny_ref.npz")):
+    jobs = [(os.path.join(REF, "tests/cube.glb"), "cube_glb_mesh.npz", None),
+            (os.path.join(REF, "tests/stanford_bunny/scene.gltf"), "bunny_mesh.npz", 256),
+            (os.path.join(HERE, "assets/kitchen_sink.glb"), "kitchen_sink_mesh.npz", None),
+            (os.path.join(HERE, "assets/pbr_patch.glb"), "pbr_patch_mesh.npz", None)]
+    for src, dst, max_image in jobs:
         tmp = os.path.join("/tmp", dst + ".bin")
-        subprocess.check_call([tool, os.path.join(REF, src), tmp])
-        import ref_meshdump
+        subprocess.check_call([tool, src, tmp])
         d = ref_meshdump.read(tmp)
-        np.savez_compressed(os.path.join(HERE, dst), **d)
-        print("wrote", dst, {k: getattr(v, "shape", v) for k, v in d.items()})
+        out = ref_dump_to_mesh_npz(d, max_image)
+        for k in [k for k in d if k.startswith("image")]:          # full-size image digests (the bunny texture is reduced above)
+            out["sha256_" + k] = np.frombuffer(hashlib.sha256(d[k].tobytes()).digest(), np.uint8)
+        np.savez_compressed(os.path.join(HERE, dst), **out)
+        print("wrote", dst, {k: v.shape for k, v in out.items() if not k.startswith("sha")})
 
 
 if __name__ == "__main__":

@@ -112,3 +112,70 @@ def test_masks_match_reference_extension_live(cpu_branch, seed, H, W):
         m, oc = diff_ref.dilate((inst == idx).astype(np.uint8), valid, coord4)
         assert np.array_equal(m, m_ref.numpy())
         assert np.array_equal(oc, c_ref.numpy())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mesh front end: stillleben_b200/gltf.py against the reference's own consolidation (oracle/_ref/meshtool -> *_mesh.npz)
+# ---------------------------------------------------------------------------------------------------------------------
+def _assert_same_mesh(mine, ref, full_images=True):
+    assert np.array_equal(mine.vertices.view(np.uint8).reshape(len(mine.vertices), -1), ref.vertices.view(np.uint8).reshape(len(ref.vertices), -1))
+    assert np.array_equal(mine.indices, ref.indices)
+    assert [tuple(s) for s in mine.submeshes] == [tuple(s) for s in ref.submeshes]
+    assert len(mine.materials) == len(ref.materials)
+    for a, b in zip(mine.materials, ref.materials):
+        np.testing.assert_array_equal(np.float32(a.base_color), np.float32(b.base_color))
+        np.testing.assert_array_equal(np.float32(a.emissive), np.float32(b.emissive))
+        assert np.float32(a.metallic) == np.float32(b.metallic) and np.float32(a.roughness) == np.float32(b.roughness)
+        assert (a.tex_base_color, a.tex_normal, a.tex_metallic_roughness, a.tex_emissive, a.tex_occlusion) == \
+               (b.tex_base_color, b.tex_normal, b.tex_metallic_roughness, b.tex_emissive, b.tex_occlusion)
+    assert len(mine.images) == len(ref.images)
+    for a, b in zip(mine.images, ref.images):
+        assert (a.wrap_s, a.wrap_t, a.min_filter, a.mag_filter) == (b.wrap_s, b.wrap_t, b.min_filter, b.mag_filter)
+        if full_images:
+            assert np.array_equal(a.pixels, b.pixels)
+    np.testing.assert_array_equal(mine.bbox_min, ref.bbox_min)
+    np.testing.assert_array_equal(mine.bbox_max, ref.bbox_max)
+
+
+@pytest.mark.parametrize("asset", ["kitchen_sink", "pbr_patch"])
+def test_gltf_front_end_matches_reference_consolidation(asset):
+    """Byte for byte: 68-byte vertices (node transforms baked in Magnum's float32 order, computed tangents, colours, zero
+    initialisation), indices, sub-mesh table in Object::loadVisual order, materials as RenderShader::setMaterial resolves
+    them (incl. the importer dropping factors equal to the glTF default), one texture per glTF texture with its sampler."""
+    from stillleben_b200 import gltf
+    mine = gltf.load(os.path.join(fixtures.GOLDEN, "assets", asset + ".glb"))
+    _assert_same_mesh(mine, fixtures.load_mesh(asset + "_mesh"))
+
+
+@pytest.mark.parametrize("path,fixture", [("tests/cube.glb", "cube_glb_mesh"), ("tests/stanford_bunny/scene.gltf", "bunny_mesh")])
+def test_gltf_front_end_matches_reference_on_its_own_assets(path, fixture):
+    import hashlib
+    from stillleben_b200 import gltf
+    src = os.path.join("/root/reference", path)
+    if not os.path.exists(src):
+        pytest.skip("the reference's test assets are not on this machine")
+    mine = gltf.load(src)
+    _assert_same_mesh(mine, fixtures.load_mesh(fixture), full_images=False)
+    z = np.load(os.path.join(fixtures.GOLDEN, fixture + ".npz"))
+    for i, im in enumerate(mine.images):     # full-size image bytes as the reference's StbImageImporter delivers them (bottom-up rows)
+        assert hashlib.sha256(im.pixels.tobytes()).digest() == z[f"sha256_image{i}"].tobytes()
+
+
+def test_gltf_without_normals_is_an_error_like_in_the_reference(tmp_path):
+    """The reference aborts on such a mesh (consolidate.cpp:84-87, verified with oracle/_ref/meshtool); here: ValueError."""
+    import json
+    from stillleben_b200 import gltf
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    idx = np.array([0, 1, 2], np.uint16)
+    blob = pos.tobytes() + idx.tobytes() + b"\0\0"
+    import base64
+    js = {"asset": {"version": "2.0"}, "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+          "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 6}],
+          "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}, {"bufferView": 1, "componentType": 5123, "count": 3, "type": "SCALAR"}],
+          "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}], "nodes": [{"mesh": 0}], "scenes": [{"nodes": [0]}], "scene": 0}
+    p = tmp_path / "no_normals.gltf"
+    p.write_text(json.dumps(js))
+    with pytest.raises(ValueError, match="NORMAL"):
+        gltf.load(str(p))
+    m = gltf.load(str(p), generate_missing_normals=True)
+    np.testing.assert_allclose(m.vertices["normal"], [[0, 0, 1]] * 3, atol=1e-6)
