@@ -81,6 +81,78 @@ static float geometry_schlick_ibl(float NdotV, float roughness) {
     return NdotV / (NdotV * (1.0f - k) + k);
 }
 
+// ---- the four fragment programs, one output texel each (WorldPos = un-normalised cube-face position) ----
+static V3 equirect_texel(const slb_lightmap_desc* d, V3 world_pos) {      // cubemap_shader_equirectangular.frag:10-27
+    V3 v = normalize(world_pos);
+    float u = std::atan2(v.y, v.x) * 0.1591f + 0.5f;
+    float w = std::asin(v.z) * 0.3183f + 0.5f;
+    return equirect_sample(d->equirect_rgb, d->width, d->height, u, w);
+}
+static V3 irradiance_texel(const std::vector<CubeLevel>& env, V3 world_pos, float lod) {   // cubemap_shader_irradiance.frag:14-45
+    V3 N = normalize(world_pos);
+    V3 irradiance(0.0f);
+    V3 up(0, 1, 0);
+    V3 right = cross(up, N);
+    up = cross(N, right);
+    const float sampleDelta = 0.020f;
+    float nrSamples = 0.0f;
+    for (float phi = 0.0f; phi < 2.0f * PI; phi += sampleDelta)
+        for (float theta = 0.0f; theta < 0.5f * PI; theta += sampleDelta) {
+            V3 ts(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta));
+            V3 sv = right * ts.x + up * ts.y + N * ts.z;
+            V4 c = sample_cube_lod(env, sv, lod);
+            irradiance += V3(c.x, c.y, c.z) * std::cos(theta) * std::sin(theta);
+            nrSamples += 1.0f;
+        }
+    return irradiance * PI * (1.0f / nrSamples);
+}
+static V3 prefilter_texel(const std::vector<CubeLevel>& env, V3 world_pos, float roughness, int n_samples, int env_size) {   // cubemap_shader_prefilter.frag:77-114
+    V3 N = normalize(world_pos);
+    V3 R = N, V = R;
+    V3 color(0.0f);
+    float totalWeight = 0.0f;
+    for (uint32_t i = 0; i < (uint32_t)n_samples; ++i) {
+        float xi_x = (float)i / (float)n_samples, xi_y = radical_inverse(i);
+        V3 H = importance_sample_ggx(xi_x, xi_y, N, roughness);
+        V3 L = normalize(H * (2.0f * dot(V, H)) - V);
+        float NdotL = std::max(dot(N, L), 0.0f);
+        if (NdotL > 0.0f) {
+            float D = distribution_ggx(N, H, roughness);
+            float NdotH = std::max(dot(N, H), 0.0f);
+            float HdotV = std::max(dot(H, V), 0.0f);
+            float pdf = D * NdotH / (4.0f * HdotV) + 0.0001f;
+            float resolution = (float)env_size;
+            float saTexel = 4.0f * PI / (6.0f * resolution * resolution);
+            float saSample = 1.0f / ((float)n_samples * pdf + 0.0001f);
+            float mipLevel = roughness == 0.0f ? 0.0f : 0.5f * std::log2(saSample / saTexel);
+            V4 c = sample_cube_lod(env, L, mipLevel);
+            color += V3(c.x, c.y, c.z) * NdotL;
+            totalWeight += NdotL;
+        }
+    }
+    return color / totalWeight;
+}
+static void brdf_texel(float NdotV, float roughness, int n_samples, float& A, float& B) {   // brdf_shader.frag:74-118
+    V3 V(std::sqrt(1.0f - NdotV * NdotV), 0.0f, NdotV);
+    A = 0.0f; B = 0.0f;
+    V3 N(0, 0, 1);
+    for (uint32_t i = 0; i < (uint32_t)n_samples; ++i) {
+        float xi_x = (float)i / (float)n_samples, xi_y = radical_inverse(i);
+        V3 H = importance_sample_ggx(xi_x, xi_y, N, roughness);
+        V3 L = normalize(H * (2.0f * dot(V, H)) - V);
+        float NdotL = std::max(L.z, 0.0f), NdotH = std::max(H.z, 0.0f), VdotH = std::max(dot(V, H), 0.0f);
+        if (NdotL > 0.0f) {
+            float G = geometry_schlick_ibl(std::max(dot(N, L), 0.0f), roughness) *
+                      geometry_schlick_ibl(std::max(dot(N, V), 0.0f), roughness);
+            float G_Vis = (G * VdotH) / (NdotH * NdotV);
+            float Fc = std::pow(1.0f - VdotH, 5.0f);
+            A += (1.0f - Fc) * G_Vis;
+            B += Fc * G_Vis;
+        }
+    }
+    A /= (float)n_samples; B /= (float)n_samples;
+}
+
 LightMap* lightmap_create(const slb_lightmap_desc* d, int env_size, int irr_size, int pre_size, int lut_size,
                           int n_samples) {
     LightMap* lm = new LightMap;
@@ -98,10 +170,7 @@ LightMap* lightmap_create(const slb_lightmap_desc* d, int env_size, int irr_size
         for (int f = 0; f < 6; ++f)
             for (int y = 0; y < env_size; ++y)
                 for (int x = 0; x < env_size; ++x) {
-                    V3 v = normalize(face_dir(f, (x + 0.5f) / env_size, (y + 0.5f) / env_size));
-                    float u = std::atan2(v.y, v.x) * 0.1591f + 0.5f;
-                    float w = std::asin(v.z) * 0.3183f + 0.5f;
-                    V3 c = equirect_sample(d->equirect_rgb, d->width, d->height, u, w);
+                    V3 c = equirect_texel(d, face_dir(f, (x + 0.5f) / env_size, (y + 0.5f) / env_size));
                     float* p = &l0.px[(((size_t)f * env_size + y) * env_size + x) * 4];
                     p[0] = c.x; p[1] = c.y; p[2] = c.z; p[3] = 1.0f;
                 }
@@ -117,22 +186,7 @@ LightMap* lightmap_create(const slb_lightmap_desc* d, int env_size, int irr_size
         for (int f = 0; f < 6; ++f)
             for (int y = 0; y < irr_size; ++y)
                 for (int x = 0; x < irr_size; ++x) {
-                    V3 N = normalize(face_dir(f, (x + 0.5f) / irr_size, (y + 0.5f) / irr_size));
-                    V3 irradiance(0.0f);
-                    V3 up(0, 1, 0);
-                    V3 right = cross(up, N);
-                    up = cross(N, right);
-                    const float sampleDelta = 0.020f;
-                    float nrSamples = 0.0f;
-                    for (float phi = 0.0f; phi < 2.0f * PI; phi += sampleDelta)
-                        for (float theta = 0.0f; theta < 0.5f * PI; theta += sampleDelta) {
-                            V3 ts(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta));
-                            V3 sv = right * ts.x + up * ts.y + N * ts.z;
-                            V4 c = sample_cube_lod(lm->env, sv, lod);
-                            irradiance += V3(c.x, c.y, c.z) * (std::cos(theta) * std::sin(theta));
-                            nrSamples += 1.0f;
-                        }
-                    irradiance = irradiance * PI * (1.0f / nrSamples);
+                    V3 irradiance = irradiance_texel(lm->env, face_dir(f, (x + 0.5f) / irr_size, (y + 0.5f) / irr_size), lod);
                     float* p = &l0.px[(((size_t)f * irr_size + y) * irr_size + x) * 4];
                     p[0] = irradiance.x; p[1] = irradiance.y; p[2] = irradiance.z; p[3] = 1.0f;
                 }
@@ -150,30 +204,7 @@ LightMap* lightmap_create(const slb_lightmap_desc* d, int env_size, int irr_size
             for (int f = 0; f < 6; ++f)
                 for (int y = 0; y < n; ++y)
                     for (int x = 0; x < n; ++x) {
-                        V3 N = normalize(face_dir(f, (x + 0.5f) / n, (y + 0.5f) / n));
-                        V3 R = N, V = R;
-                        V3 color(0.0f);
-                        float totalWeight = 0.0f;
-                        for (uint32_t i = 0; i < (uint32_t)n_samples; ++i) {
-                            float xi_x = (float)i / (float)n_samples, xi_y = radical_inverse(i);
-                            V3 H = importance_sample_ggx(xi_x, xi_y, N, roughness);
-                            V3 L = normalize(H * (2.0f * dot(V, H)) - V);
-                            float NdotL = std::max(dot(N, L), 0.0f);
-                            if (NdotL > 0.0f) {
-                                float D = distribution_ggx(N, H, roughness);
-                                float NdotH = std::max(dot(N, H), 0.0f);
-                                float HdotV = std::max(dot(H, V), 0.0f);
-                                float pdf = D * NdotH / (4.0f * HdotV) + 0.0001f;
-                                float resolution = (float)env_size;
-                                float saTexel = 4.0f * PI / (6.0f * resolution * resolution);
-                                float saSample = 1.0f / ((float)n_samples * pdf + 0.0001f);
-                                float mipLevel = roughness == 0.0f ? 0.0f : 0.5f * std::log2(saSample / saTexel);
-                                V4 c = sample_cube_lod(lm->env, L, mipLevel);
-                                color += V3(c.x, c.y, c.z) * NdotL;
-                                totalWeight += NdotL;
-                            }
-                        }
-                        color = color / totalWeight;
+                        V3 color = prefilter_texel(lm->env, face_dir(f, (x + 0.5f) / n, (y + 0.5f) / n), roughness, n_samples, env_size);
                         float* p = &l.px[(((size_t)f * n + y) * n + x) * 4];
                         p[0] = color.x; p[1] = color.y; p[2] = color.z; p[3] = 1.0f;
                     }
@@ -189,24 +220,7 @@ LightMap* lightmap_create(const slb_lightmap_desc* d, int env_size, int irr_size
         for (int y = 0; y < lut_size; ++y)
             for (int x = 0; x < lut_size; ++x) {
                 float NdotV = (x + 0.5f) / lut_size, roughness = (y + 0.5f) / lut_size;
-                V3 V(std::sqrt(1.0f - NdotV * NdotV), 0.0f, NdotV);
-                float A = 0.0f, B = 0.0f;
-                V3 N(0, 0, 1);
-                for (uint32_t i = 0; i < (uint32_t)n_samples; ++i) {
-                    float xi_x = (float)i / (float)n_samples, xi_y = radical_inverse(i);
-                    V3 H = importance_sample_ggx(xi_x, xi_y, N, roughness);
-                    V3 L = normalize(H * (2.0f * dot(V, H)) - V);
-                    float NdotL = std::max(L.z, 0.0f), NdotH = std::max(H.z, 0.0f), VdotH = std::max(dot(V, H), 0.0f);
-                    if (NdotL > 0.0f) {
-                        float G = geometry_schlick_ibl(std::max(dot(N, L), 0.0f), roughness) *
-                                  geometry_schlick_ibl(std::max(dot(N, V), 0.0f), roughness);
-                        float G_Vis = (G * VdotH) / (NdotH * NdotV);
-                        float Fc = std::pow(1.0f - VdotH, 5.0f);
-                        A += (1.0f - Fc) * G_Vis;
-                        B += Fc * G_Vis;
-                    }
-                }
-                A /= (float)n_samples; B /= (float)n_samples;
+                float A, B; brdf_texel(NdotV, roughness, n_samples, A, B);
                 float* p = &l0[((size_t)y * lut_size + x) * 4];
                 p[0] = A; p[1] = B; p[2] = 0.0f; p[3] = 1.0f;
             }
@@ -267,5 +281,31 @@ void orc_lightmap_sizes(const void* h, int sizes[4]) {
     sizes[0] = lm->env[0].size; sizes[1] = lm->irradiance[0].size; sizes[2] = lm->prefilter[0].size; sizes[3] = lm->lut_size;
 }
 void orc_lightmap_destroy(void* h) { delete (LightMap*)h; }
+
+// per-texel test hooks (see orc_test_hooks.h): which = 0 equirect -> cube, 1 irradiance, 2 prefilter; world_pos: n x 3
+// cube-face positions; `lm` supplies the environment cube for 1 and 2, `d` the equirect image for 0
+void orc_test_lightmap_texels(int which, const slb_lightmap_desc* d, const void* lm_h, const float* world_pos, int n, float roughness,
+                              int n_samples, float irradiance_lod, float* rgb_out) {
+    const LightMap* lm = (const LightMap*)lm_h;
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < n; ++i) {
+        V3 wp(world_pos[3 * i], world_pos[3 * i + 1], world_pos[3 * i + 2]), c;
+        if (which == 0) c = equirect_texel(d, wp);
+        else if (which == 1) c = irradiance_texel(lm->env, wp, irradiance_lod);
+        else c = prefilter_texel(lm->env, wp, roughness, n_samples, lm->env[0].size);
+        rgb_out[3 * i] = c.x; rgb_out[3 * i + 1] = c.y; rgb_out[3 * i + 2] = c.z;
+    }
+}
+void orc_test_brdf_lut(const float* ndotv_roughness, int n, int n_samples, float* ab_out) {
+    for (int i = 0; i < n; ++i) brdf_texel(ndotv_roughness[2 * i], ndotv_roughness[2 * i + 1], n_samples, ab_out[2 * i], ab_out[2 * i + 1]);
+}
+// filtered cube look-up of an oracle light map: which = 0 env, 1 irradiance, 2 prefilter (the harness binds the compiled
+// reference shaders' samplerCube to this)
+void orc_test_cube_sample(const void* lm_h, int which, const float* dir, float lod, float* rgba) {
+    const LightMap* lm = (const LightMap*)lm_h;
+    const std::vector<CubeLevel>& cube = which == 0 ? lm->env : (which == 1 ? lm->irradiance : lm->prefilter);
+    V4 c = sample_cube_lod(cube, V3(dir[0], dir[1], dir[2]), lod);
+    rgba[0] = c.x; rgba[1] = c.y; rgba[2] = c.z; rgba[3] = c.w;
+}
 
 }  // extern "C"

@@ -13,8 +13,10 @@
 // Fixed-function stages (clip, viewport, rasterise, depth) follow the GL 4.5 core spec
 // §13.5-13.6, §14.6, §17.3 under the NUMERICAL CONTRACT written in DESIGN.md §"Raster contract":
 // 8 sub-pixel bits, top-left rule in (x, row) coordinates, 24-bit depth, LESS, first draw wins.
-// PARITY STATUS: parity unpinned beyond the reference's weak pins (see orc_core.h).
+// PARITY STATUS: programmable stages pinned on the reference's GLSL text compiled as C++ (tests/test_glsl_ref.py); the GL
+// fixed function follows the written contract (see orc_core.h).
 #include "orc_core.h"
+#include "orc_test_hooks.h"
 
 #include <cstdio>
 #include <limits>
@@ -609,6 +611,94 @@ static inline uint8_t unorm8(float v) {
     return (uint8_t)std::lrintf(v * 255.0f);
 }
 
+
+// tone map of one pixel (tone_map_shader.frag:102-131); avg = texel (0,0) of the last mip level (auto exposure only)
+static void tone_map_pixel(const float* hdr4, float manual_exposure, const float avg[4], uint8_t* rgba8) {
+    V3 c(hdr4[0], hdr4[1], hdr4[2]);
+    V3 xyz(0.4124564f * c.x + 0.3575761f * c.y + 0.1804375f * c.z, 0.2126729f * c.x + 0.7151522f * c.y + 0.0721750f * c.z,
+           0.0193339f * c.x + 0.1191920f * c.y + 0.9503041f * c.z);
+    float inv = 1.0f / (xyz.x + xyz.y + xyz.z);
+    V3 Yxy(xyz.y, xyz.x * inv, xyz.y * inv);
+    if (manual_exposure >= 0) Yxy.x *= manual_exposure;
+    else {
+        float lum = 0.1f * (0.2125f * (avg[0] / avg[3]) + 0.7154f * (avg[1] / avg[3]) + 0.0721f * (avg[2] / avg[3]));
+        Yxy.x /= (9.6f * lum + 0.0001f);
+    }
+    V3 x2(Yxy.x * Yxy.y / Yxy.z, Yxy.x, Yxy.x * (1.0f - Yxy.y - Yxy.z) / Yxy.z);
+    V3 r(3.2404542f * x2.x - 1.5371385f * x2.y - 0.4985314f * x2.z, -0.9692660f * x2.x + 1.8760108f * x2.y + 0.0415560f * x2.z,
+         0.0556434f * x2.x - 0.2040259f * x2.y + 1.0572252f * x2.z);
+    V3 a = aces(r);
+    rgba8[0] = unorm8(a.x); rgba8[1] = unorm8(a.y); rgba8[2] = unorm8(a.z); rgba8[3] = unorm8(hdr4[3]);
+}
+
+// SSAO (ssao_shader.frag:20-57) over a whole frame: camc / normals are the HxWx4 float targets, P the projection
+static void ssao_pass(const float* camc, const float* normals, int W, int H, const M4& P, float* ao, int n_threads) {
+    V3 noise[16], kernel[64]; ssao_tables(noise, kernel);
+    #pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads)
+    for (int py = 0; py < H; ++py)
+        for (int px = 0; px < W; ++px) {
+            size_t p = (size_t)py * W + px;
+            V3 fragPos(camc[p * 4], camc[p * 4 + 1], camc[p * 4 + 2]);
+            V3 nrm(normals[p * 4], normals[p * 4 + 1], normals[p * 4 + 2]);
+            if (nrm.x == 0 && nrm.y == 0 && nrm.z == 0) { ao[p] = 1.0f; continue; }  // background: NaN path -> no occlusion
+            V3 normal = normalize(nrm);
+            V3 randomVec = normalize(noise[(py & 3) * 4 + (px & 3)]);
+            V3 tangent = normalize(randomVec - normal * dot(randomVec, normal));
+            V3 bitangent = cross(normal, tangent);
+            float occlusion = 0.0f;
+            for (int i = 0; i < 64; ++i) {
+                V3 s = kernel[i];
+                V3 samplePos = tangent * s.x + bitangent * s.y + normal * s.z;
+                samplePos = fragPos + samplePos * 0.1f;
+                V4 off = mul(P, V4(samplePos, 1.0f));
+                float ox = off.x / off.w * 0.5f + 0.5f, oy = off.y / off.w * 0.5f + 0.5f;
+                float sampleDepth = rect_linear(camc, W, H, ox * W, oy * H).z;
+                float rangeCheck = smoothstep01(0.1f / std::fabs(fragPos.z - sampleDepth));
+                occlusion += (sampleDepth <= samplePos.z - 0.0025f ? 1.0f : 0.0f) * rangeCheck;
+            }
+            ao[p] = 1.0f - (occlusion / 64.0f);
+        }
+}
+// bilateral blur + apply (ssao_apply_shader.frag:29-76): out rgb = hdr rgb * blurred ao, alpha untouched
+static void ssao_apply_pass(const float* hdr, const float* ao, const float* camc, int W, int H, float* outc, int n_threads) {
+    #pragma omp parallel for num_threads(n_threads)
+    for (int py = 0; py < H; ++py)
+        for (int px = 0; px < W; ++px) {
+            size_t p = (size_t)py * W + px;
+            float center_d = rect_linear(camc, W, H, (float)px, (float)py).z;
+            float result = 0.0f, w_total = 0.0f;
+            const float BlurSigma = 3.0f * 0.5f, BlurFalloff = 1.0f / (2.0f * BlurSigma * BlurSigma);
+            for (int x = -2; x < 2; ++x)
+                for (int y = -2; y < 2; ++y) {
+                    int ux = px + x, uy = py + y;
+                    float c = (ux >= 0 && ux < W && uy >= 0 && uy < H) ? ao[(size_t)uy * W + ux] : 0.0f;  // texelFetch out of range -> 0
+                    float dd = rect_linear(camc, W, H, (float)ux, (float)uy).z;
+                    float r = std::sqrt((float)(x * x + y * y));
+                    float ddiff = (dd - center_d) * 300.0f;
+                    float w = std::exp2(-r * r * BlurFalloff - ddiff * ddiff);
+                    w_total += w;
+                    result += c * w;
+                }
+            float a = result / w_total;
+            outc[p * 4 + 0] = hdr[p * 4 + 0] * a; outc[p * 4 + 1] = hdr[p * 4 + 1] * a; outc[p * 4 + 2] = hdr[p * 4 + 2] * a;
+            outc[p * 4 + 3] = hdr[p * 4 + 3];
+        }
+}
+// direction the sky box is sampled with at NDC (xn, yn): the cube position interpolated over the cube faces == the view
+// ray in the un-translated world frame, R^T (Pinv ndc)  (background_cube_shader.vert:14-20)
+static V3 skybox_dir(const M4& Pinv, const M4& V, float xn, float yn) {
+    V4 q = mul(Pinv, V4(xn, yn, 1.0f, 1.0f));
+    V3 dc(q.x / q.w, q.y / q.w, q.z / q.w);
+    return V3(V.at(0, 0) * dc.x + V.at(1, 0) * dc.y + V.at(2, 0) * dc.z, V.at(0, 1) * dc.x + V.at(1, 1) * dc.y + V.at(2, 1) * dc.z,
+              V.at(0, 2) * dc.x + V.at(1, 2) * dc.y + V.at(2, 2) * dc.z);
+}
+// background image texel for pixel (px, py) (background_shader.vert:12-14, .frag:10-16)
+static V4 background_image_texel(const Texture& bg, int px, int py, int W, int H) {
+    float tx = ((px + 0.5f) / W), ty = 1.0f - ((py + 0.5f) / H);   // textureCoords = (x_ndc, -y_ndc)/2 + 0.5 at the pixel centre
+    int ix = (int)(tx * bg.w), iy = (int)(ty * bg.h);              // ivec2(textureCoords * texSize)
+    return sample_texture_rect_linear(bg, (float)ix, (float)iy);
+}
+
 }  // namespace orc
 
 using namespace orc;
@@ -892,10 +982,7 @@ int orc_render(const slb_scene_desc* scp, const float* peel, void* const out[SLB
                 size_t p = (size_t)py * W + px;
                 uint32_t d24 = (keys[p] == ~0ull) ? 0xFFFFFFu : (uint32_t)(keys[p] >> 32);
                 if (!(quad_d24 < d24)) continue;
-                // textureCoords = (x_ndc, -y_ndc)/2 + 0.5 interpolated at the pixel centre
-                float tx = ((px + 0.5f) / W), ty = 1.0f - ((py + 0.5f) / H);
-                int ix = (int)(tx * bg->w), iy = (int)(ty * bg->h);   // ivec2(textureCoords * texSize)
-                V4 c = sample_texture_rect_linear(*bg, (float)ix, (float)iy);
+                V4 c = background_image_texel(*bg, px, py, W, H);
                 hdr[p * 4 + 0] = c.x; hdr[p * 4 + 1] = c.y; hdr[p * 4 + 2] = c.z; hdr[p * 4 + 3] = 0.0f;
             }
     } else if (f.lm) {
@@ -906,14 +993,7 @@ int orc_render(const slb_scene_desc* scp, const float* peel, void* const out[SLB
             for (int px = 0; px < W; ++px) {
                 size_t p = (size_t)py * W + px;
                 if (keys[p] != ~0ull) continue;
-                // cube position interpolated over the cube faces == direction of the view ray in
-                // the (un-translated) world frame: dir = R^T * (Pinv * ndc)
-                float xn = 2.0f * (px + 0.5f) / W - 1.0f, yn = 2.0f * (py + 0.5f) / H - 1.0f;
-                V4 q = mul(Pinv, V4(xn, yn, 1.0f, 1.0f));
-                V3 dc(q.x / q.w, q.y / q.w, q.z / q.w);
-                V3 dw(f.V.at(0, 0) * dc.x + f.V.at(1, 0) * dc.y + f.V.at(2, 0) * dc.z,
-                      f.V.at(0, 1) * dc.x + f.V.at(1, 1) * dc.y + f.V.at(2, 1) * dc.z,
-                      f.V.at(0, 2) * dc.x + f.V.at(1, 2) * dc.y + f.V.at(2, 2) * dc.z);
+                V3 dw = skybox_dir(Pinv, f.V, 2.0f * (px + 0.5f) / W - 1.0f, 2.0f * (py + 0.5f) / H - 1.0f);
                 V4 c = sample_cube_lod(f.lm->env, dw, 0.0f);
                 hdr[p * 4 + 0] = c.x; hdr[p * 4 + 1] = c.y; hdr[p * 4 + 2] = c.z; hdr[p * 4 + 3] = 0.0f;
             }
@@ -921,77 +1001,16 @@ int orc_render(const slb_scene_desc* scp, const float* peel, void* const out[SLB
 
     // ---- SSAO (render_pass.cpp:662-694) ----
     if (sc.ssao_enabled) {
-        V3 noise[16], kernel[64]; ssao_tables(noise, kernel);
         std::vector<float> ao((size_t)W * H, 1.0f);
-        #pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads)
-        for (int py = 0; py < H; ++py)
-            for (int px = 0; px < W; ++px) {
-                size_t p = (size_t)py * W + px;
-                V3 fragPos(camc[p * 4], camc[p * 4 + 1], camc[p * 4 + 2]);
-                V3 nrm(normals[p * 4], normals[p * 4 + 1], normals[p * 4 + 2]);
-                if (nrm.x == 0 && nrm.y == 0 && nrm.z == 0) { ao[p] = 1.0f; continue; }  // background: NaN path -> no occlusion
-                V3 normal = normalize(nrm);
-                V3 randomVec = normalize(noise[(py & 3) * 4 + (px & 3)]);
-                V3 tangent = normalize(randomVec - normal * dot(randomVec, normal));
-                V3 bitangent = cross(normal, tangent);
-                float occlusion = 0.0f;
-                for (int i = 0; i < 64; ++i) {
-                    V3 s = kernel[i];
-                    V3 samplePos = tangent * s.x + bitangent * s.y + normal * s.z;
-                    samplePos = fragPos + samplePos * 0.1f;
-                    V4 off = mul(f.P, V4(samplePos, 1.0f));
-                    float ox = off.x / off.w * 0.5f + 0.5f, oy = off.y / off.w * 0.5f + 0.5f;
-                    float sampleDepth = rect_linear(camc.data(), W, H, ox * W, oy * H).z;
-                    float rangeCheck = smoothstep01(0.1f / std::fabs(fragPos.z - sampleDepth));
-                    occlusion += (sampleDepth <= samplePos.z - 0.0025f ? 1.0f : 0.0f) * rangeCheck;
-                }
-                ao[p] = 1.0f - (occlusion / 64.0f);
-            }
-        // bilateral blur + apply (ssao_apply_shader.frag:29-76)
+        ssao_pass(camc.data(), normals.data(), W, H, f.P, ao.data(), n_threads);
         std::vector<float> outc = hdr;
-        #pragma omp parallel for num_threads(n_threads)
-        for (int py = 0; py < H; ++py)
-            for (int px = 0; px < W; ++px) {
-                size_t p = (size_t)py * W + px;
-                float center_d = rect_linear(camc.data(), W, H, (float)px, (float)py).z;
-                float result = 0.0f, w_total = 0.0f;
-                const float BlurSigma = 3.0f * 0.5f, BlurFalloff = 1.0f / (2.0f * BlurSigma * BlurSigma);
-                for (int x = -2; x < 2; ++x)
-                    for (int y = -2; y < 2; ++y) {
-                        int ux = px + x, uy = py + y;
-                        float c = (ux >= 0 && ux < W && uy >= 0 && uy < H) ? ao[(size_t)uy * W + ux] : 0.0f;  // texelFetch out of range -> 0
-                        float dd = rect_linear(camc.data(), W, H, (float)ux, (float)uy).z;
-                        float r = std::sqrt((float)(x * x + y * y));
-                        float ddiff = (dd - center_d) * 300.0f;
-                        float w = std::exp2(-r * r * BlurFalloff - ddiff * ddiff);
-                        w_total += w;
-                        result += c * w;
-                    }
-                float a = result / w_total;
-                outc[p * 4 + 0] = hdr[p * 4 + 0] * a; outc[p * 4 + 1] = hdr[p * 4 + 1] * a; outc[p * 4 + 2] = hdr[p * 4 + 2] * a;
-            }
+        ssao_apply_pass(hdr.data(), ao.data(), camc.data(), W, H, outc.data(), n_threads);
         hdr.swap(outc);
     }
 
     // ---- tone map (tone_map_shader.frag:102-131) ----
     std::vector<uint8_t> rgb((size_t)W * H * 4);
-    for (size_t p = 0; p < (size_t)W * H; ++p) {
-        V3 c(hdr[p * 4], hdr[p * 4 + 1], hdr[p * 4 + 2]);
-        V3 xyz(0.4124564f * c.x + 0.3575761f * c.y + 0.1804375f * c.z, 0.2126729f * c.x + 0.7151522f * c.y + 0.0721750f * c.z,
-               0.0193339f * c.x + 0.1191920f * c.y + 0.9503041f * c.z);
-        float inv = 1.0f / (xyz.x + xyz.y + xyz.z);
-        V3 Yxy(xyz.y, xyz.x * inv, xyz.y * inv);
-        if (sc.manual_exposure >= 0) Yxy.x *= sc.manual_exposure;
-        else {
-            float lum = 0.1f * (0.2125f * (avg[0] / avg[3]) + 0.7154f * (avg[1] / avg[3]) + 0.0721f * (avg[2] / avg[3]));
-            Yxy.x /= (9.6f * lum + 0.0001f);
-        }
-        V3 x2(Yxy.x * Yxy.y / Yxy.z, Yxy.x, Yxy.x * (1.0f - Yxy.y - Yxy.z) / Yxy.z);
-        V3 r(3.2404542f * x2.x - 1.5371385f * x2.y - 0.4985314f * x2.z, -0.9692660f * x2.x + 1.8760108f * x2.y + 0.0415560f * x2.z,
-             0.0556434f * x2.x - 0.2040259f * x2.y + 1.0572252f * x2.z);
-        V3 a = aces(r);
-        rgb[p * 4 + 0] = unorm8(a.x); rgb[p * 4 + 1] = unorm8(a.y); rgb[p * 4 + 2] = unorm8(a.z); rgb[p * 4 + 3] = unorm8(hdr[p * 4 + 3]);
-    }
+    for (size_t p = 0; p < (size_t)W * H; ++p) tone_map_pixel(&hdr[p * 4], sc.manual_exposure, avg, &rgb[p * 4]);
 
     if (out) {
         if (out[SLB_TARGET_RGB]) std::memcpy(out[SLB_TARGET_RGB], rgb.data(), rgb.size());
@@ -1005,6 +1024,108 @@ int orc_render(const slb_scene_desc* scp, const float* peel, void* const out[SLB
     }
     if (hdr_out) std::memcpy(hdr_out, hdr.data(), hdr.size() * 4);
     return 0;
+}
+
+// =======================================================================================
+// Per-stage test hooks (oracle/orc_test_hooks.h): the restatement's vertex / fragment / post stages on caller-supplied
+// inputs, so that tests/test_glsl_ref.py can hold them against the reference's GLSL compiled as C++ (oracle/_ref/libglslref.so).
+// =======================================================================================
+void orc_test_vertex(const orc_vert_uniforms* u, const void* verts68, int n, orc_vert_out* out) {
+    Frame f; Draw d;
+    f.V = M4::from(u->world_to_cam); f.P = M4::from(u->projection);
+    d.meshToObject = M4::from(u->mesh_to_object); d.objectToWorld = M4::from(u->object_to_world);
+    std::memcpy(d.normalToWorld, u->normal_to_world, sizeof d.normalToWorld);
+    d.stickerProj = M4::from(u->sticker_projection);
+    for (int k = 0; k < 4; ++k) d.stickerRange[k] = u->sticker_range[k];
+    const Vertex68* v = (const Vertex68*)verts68;
+    for (int i = 0; i < n; ++i) {
+        VSOut o; vertex_stage(f, d, v[i], o);
+        orc_vert_out& r = out[i];
+        std::memset(&r, 0, sizeof r);
+        r.uv[0] = o.uv.x; r.uv[1] = o.uv.y;
+        for (int k = 0; k < 3; ++k) { r.normal_w[k] = o.nW[k]; r.tangent_w[k] = o.tW[k]; r.bitangent_w[k] = o.bW[k]; r.world[k] = o.wc[k]; r.cam[k] = o.cc[k]; }
+        for (int k = 0; k < 4; ++k) r.objc[k] = o.objc[k];
+        r.sticker[0] = o.sticker.x; r.sticker[1] = o.sticker.y;
+        r.vertex_id = v[i].vertex_index;
+        // clip position as the raster front end computes it (contract C2/C3: mvp formed once, one fma chain per row)
+        float mvp[16]; make_mvp(f.P, f.V, d.objectToWorld, d.meshToObject, mvp);
+        ClipV c; xform_clip(mvp, v[i].pos, c);
+        r.position[0] = c.x; r.position[1] = c.y; r.position[2] = c.z; r.position[3] = c.w;
+    }
+}
+
+void orc_test_fragment(const orc_frag_uniforms* u, const orc_frag_in* in, int n, orc_frag_out* out) {
+    Frame f; Draw d;
+    f.W = u->width; f.H = u->height; f.peel = u->peel;
+    f.V = M4::from(u->world_to_cam);
+    f.camPos = V3(u->cam_position[0], u->cam_position[1], u->cam_position[2]);
+    f.lm = u->light_map_available ? (const LightMap*)u->light_map : nullptr;
+    for (int i = 0; i < SLB_NUM_LIGHTS; ++i) {
+        f.lightDir[i] = V3(u->light_directions[3 * i], u->light_directions[3 * i + 1], u->light_directions[3 * i + 2]);
+        f.lightCol[i] = V3(u->light_colors[3 * i], u->light_colors[3 * i + 1], u->light_colors[3 * i + 2]);
+        bool colZero = f.lightCol[i].x == 0 && f.lightCol[i].y == 0 && f.lightCol[i].z == 0;
+        bool dirZero = f.lightDir[i].x == 0 && f.lightDir[i].y == 0 && f.lightDir[i].z == 0;
+        f.lightActive[i] = !(colZero || dirZero);
+        f.shadowMat[i] = M4::from(u->shadow_matrices + 16 * i);
+        if (u->shadow_map[i]) f.shadowMap[i].assign(u->shadow_map[i], u->shadow_map[i] + (size_t)SLB_SHADOW_RES * SLB_SHADOW_RES);
+        else f.shadowMap[i].assign((size_t)SLB_SHADOW_RES * SLB_SHADOW_RES, 0xFFFFFFu);
+    }
+    f.ambient = V3(u->ambient[0], u->ambient[1], u->ambient[2]);
+    std::memcpy(d.mat.base_color, u->material, 16); std::memcpy(d.mat.emissive, u->material + 4, 16);
+    d.mat.metallic = u->material[9]; d.mat.roughness = u->material[10];
+    for (int i = 0; i < 5; ++i) d.tex[i] = (u->available_textures & (1u << i)) ? (const Texture*)u->tex[i] : nullptr;
+    d.alpha_tested = (d.tex[0] && d.tex[0]->has_alpha) || d.mat.base_color[3] < 0.5f;
+    d.class_index = u->class_index; d.instance_index = u->instance_index;
+    d.sticker = (const Texture*)u->sticker;
+    for (int i = 0; i < n; ++i) {
+        const orc_frag_in& s = in[i];
+        FragIn fi;
+        fi.uv = V2{s.uv[0], s.uv[1]}; fi.uv_dx = V2{s.uv_dx[0], s.uv_dx[1]}; fi.uv_dy = V2{s.uv_dy[0], s.uv_dy[1]};
+        fi.nW = V3(s.normal_w[0], s.normal_w[1], s.normal_w[2]); fi.tW = V3(s.tangent_w[0], s.tangent_w[1], s.tangent_w[2]);
+        fi.bW = V3(s.bitangent_w[0], s.bitangent_w[1], s.bitangent_w[2]);
+        fi.objc = V4(s.objc[0], s.objc[1], s.objc[2], s.objc[3]);
+        fi.wc = V3(s.world[0], s.world[1], s.world[2]); fi.cc = V3(s.cam[0], s.cam[1], s.cam[2]);
+        fi.sticker = V2{s.sticker[0], s.sticker[1]};
+        fi.front = s.front_facing != 0;
+        orc_frag_out& o = out[i];
+        std::memset(&o, 0, sizeof o);
+        // the two discards, evaluated where the raster stage of orc_render evaluates them (render_shader.frag:229-246)
+        const int px = (int)s.frag_x, py = (int)s.frag_y;
+        const float prev = f.peel ? f.peel[((size_t)py * f.W + px) * 4 + 3] : 0.0f;   // no peel layer bound: a zero texture (render_pass.cpp:395-402)
+        if (fi.objc.w - 0.00001f <= prev) { o.discarded = 1; continue; }
+        if (d.alpha_tested && base_color(d, fi).w < 0.5f) { o.discarded = 1; continue; }
+        FragOut fo; fragment_stage(f, d, fi, fo);
+        for (int k = 0; k < 4; ++k) { o.color[k] = fo.color[k]; o.objc[k] = fo.objc[k]; o.camc[k] = fo.camc[k]; o.normal[k] = fo.normal[k]; }
+        o.class_index = fo.cls; o.instance_index = fo.inst;
+        for (int k = 0; k < 3; ++k) { o.vertex_ids[k] = s.vertex_ids[k]; o.bary[k] = s.bary[k]; }   // flat / smooth pass-through (render_shader.geom)
+    }
+}
+
+void orc_test_tonemap(const float* hdr, int n, float manual_exposure, const float* avg, uint8_t* rgba8) {
+    for (int i = 0; i < n; ++i) tone_map_pixel(hdr + 4 * (size_t)i, manual_exposure, avg, rgba8 + 4 * (size_t)i);
+}
+void orc_test_ssao(const float* camc, const float* normals, int W, int H, const float* projection, float* ao) {
+    ssao_pass(camc, normals, W, H, M4::from(projection), ao, omp_get_max_threads());
+}
+void orc_test_ssao_apply(const float* hdr, const float* ao, const float* camc, int W, int H, float* out) {
+    ssao_apply_pass(hdr, ao, camc, W, H, out, omp_get_max_threads());
+}
+void orc_test_ssao_tables(float* noise16x3, float* kernel64x3) {
+    V3 noise[16], kernel[64]; ssao_tables(noise, kernel);
+    for (int i = 0; i < 16; ++i) for (int k = 0; k < 3; ++k) noise16x3[3 * i + k] = noise[i][k];
+    for (int i = 0; i < 64; ++i) for (int k = 0; k < 3; ++k) kernel64x3[3 * i + k] = kernel[i][k];
+}
+void orc_test_skybox_dir(const float* projection, const float* world_to_cam, const float* ndc_xy, int n, float* dir) {
+    M4 Pinv = inverted(M4::from(projection)), V = M4::from(world_to_cam);
+    for (int i = 0; i < n; ++i) { V3 d = skybox_dir(Pinv, V, ndc_xy[2 * i], ndc_xy[2 * i + 1]); dir[3 * i] = d.x; dir[3 * i + 1] = d.y; dir[3 * i + 2] = d.z; }
+}
+void orc_test_background_image(const void* tex, int W, int H, float* out /* HxWx4 */) {
+    const Texture& bg = *(const Texture*)tex;
+    for (int py = 0; py < H; ++py)
+        for (int px = 0; px < W; ++px) {
+            V4 c = background_image_texel(bg, px, py, W, H);
+            float* o = out + ((size_t)py * W + px) * 4; o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = 0.0f;
+        }
 }
 
 }  // extern "C"
