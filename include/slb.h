@@ -11,6 +11,12 @@
  * throw; slb_last_error() gives the message.  No torch / Magnum / CUDA-runtime types appear in
  * a signature: a CUDA stream is passed as void* (cudaStream_t), device buffers as void*.
  *
+ * Streams: every entry point with a `stream` argument queues its work there (NULL = the context's own stream). The
+ * per-context scratch is shared between calls, so the library ORDERS calls itself: the stream of a call first waits for
+ * whatever the previous call on this context queued, whatever stream that used. Calls that read back, update or destroy
+ * (slb_result_read*, slb_mesh_*, slb_*_destroy, slb_ctx_synchronize) wait for the context's own stream and for the stream
+ * of the latest call. A context must not be used from two host threads at once.
+ *
  * Conventions (identical to the reference):
  *   - all matrices are 4x4 float32 COLUMN-MAJOR (Magnum::Matrix4 memory order)
  *   - camera frame: +x right, +y down, +z forward; memory row r == GL window y == r
@@ -146,8 +152,27 @@ int slb_mesh_upload(slb_ctx* ctx, const void* vertices, uint32_t n_vertices, con
                     uint32_t n_indices, const slb_submesh* submeshes, uint32_t n_submeshes,
                     const slb_material* materials, uint32_t n_materials, const slb_image* images,
                     uint32_t n_images, const float bbox_min[3], const float bbox_max[3], slb_mesh** out);
-/* Replaces Mesh::recompileMesh()/updateVertexPositionsAndColors() (reference: src/mesh.cpp:763-855). */
+/* Replaces Mesh::recompileMesh() (reference: src/mesh.cpp:818-821): re-upload of the whole 68-byte stream, nothing
+ * recomputed. */
 int slb_mesh_update_vertices(slb_ctx* ctx, slb_mesh* mesh, const void* vertices, uint32_t n_vertices);
+/* Replaces Mesh::updateVertexPositionsAndColors / updateVertexPositions / updateVertexColors (reference:
+ * src/mesh.cpp:747-761,823-855; python/src/py_mesh.cpp:100-212): point[id-1] += position_update[i] (n x 3 floats, may be
+ * NULL), colour[id-1] += color_update[i] (n x 4 floats, may be NULL); vertex_ids are the ONE-BASED vertex ids the
+ * vertex-index target reports. After a position update the vertex normals are recomputed like Mesh::recomputeNormals
+ * (area-weighted face normals, src/mesh.cpp:763-816) — on the device, the vertex stream never leaves HBM. The bounding
+ * box is NOT updated (the reference keeps the load-time box). The arrays may be host or device memory. */
+int slb_mesh_update_positions_and_colors(slb_ctx* ctx, slb_mesh* mesh, const int32_t* vertex_ids, uint32_t n,
+                                         const float* position_update, const float* color_update, void* stream);
+/* Replaces Mesh::setVertexPositions (reference: src/mesh.cpp:857-870): all positions replaced, normals recomputed.
+ * SLB_ERR_INVALID_ARGUMENT if n_vertices differs ("Number of new vertices should match the existing mesh vertices"). */
+int slb_mesh_set_positions(slb_ctx* ctx, slb_mesh* mesh, const float* positions, uint32_t n_vertices, void* stream);
+/* Replaces Mesh::setVertexColors (reference: src/mesh.cpp:872-885). */
+int slb_mesh_set_colors(slb_ctx* ctx, slb_mesh* mesh, const float* colors, uint32_t n_vertices, void* stream);
+/* Replaces Mesh::recomputeNormals (reference: src/mesh.cpp:763-816). */
+int slb_mesh_recompute_normals(slb_ctx* ctx, slb_mesh* mesh, void* stream);
+/* The current 68-byte vertex stream (Mesh::meshPoints / meshNormals / meshColors views, reference: src/mesh.cpp:930-998);
+ * vertices_out: n_vertices * 68 bytes of host or device memory. Synchronous. */
+int slb_mesh_read_vertices(slb_ctx* ctx, const slb_mesh* mesh, void* vertices_out, uint32_t n_vertices);
 void slb_mesh_destroy(slb_ctx* ctx, slb_mesh* mesh);
 
 /* Replaces Context::loadTexture / loadTexture2D and the sl.Texture / sl.Texture2D constructors

@@ -735,6 +735,46 @@ void orc_mesh_update_vertices(void* mesh, const void* vertices, uint32_t n_verti
     m->verts.resize(n_vertices);
     std::memcpy(m->verts.data(), vertices, (size_t)n_vertices * sizeof(Vertex68));
 }
+// Mesh::recomputeNormals (reference: src/mesh.cpp:763-816), literally: per face cross = (v1 - v2) x (v1 - v3), area = |cross|,
+// normal = cross.normalized() (= cross * (1 / length), Magnum Vector::normalized); per vertex the sum of normal * area over
+// its faces in ascending face order, normalised. A zero-area face yields NaN (0 * inf) and poisons its vertices, as there.
+void orc_mesh_recompute_normals(void* mesh) {
+    Mesh* m = (Mesh*)mesh;
+    const size_t nf = m->indices.size() / 3, nv = m->verts.size();
+    std::vector<V3> fn(nf);
+    auto dot_rn = [](V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; };
+    for (size_t f = 0; f < nf; ++f) {
+        const float* p1 = m->verts[m->indices[3 * f]].pos; const float* p2 = m->verts[m->indices[3 * f + 1]].pos; const float* p3 = m->verts[m->indices[3 * f + 2]].pos;
+        V3 a(p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]), b(p1[0] - p3[0], p1[1] - p3[1], p1[2] - p3[2]);
+        V3 c(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+        float area = std::sqrt(dot_rn(c, c));
+        float inv = 1.0f / area;
+        fn[f] = V3((c.x * inv) * area, (c.y * inv) * area, (c.z * inv) * area);
+    }
+    std::vector<V3> acc(nv, V3(0.0f));
+    for (size_t f = 0; f < nf; ++f)
+        for (int k = 0; k < 3; ++k) { V3& n = acc[m->indices[3 * f + k]]; n = V3(n.x + fn[f].x, n.y + fn[f].y, n.z + fn[f].z); }
+    for (size_t v = 0; v < nv; ++v) {
+        float inv = 1.0f / std::sqrt(dot_rn(acc[v], acc[v]));
+        m->verts[v].normal[0] = acc[v].x * inv; m->verts[v].normal[1] = acc[v].y * inv; m->verts[v].normal[2] = acc[v].z * inv;
+    }
+}
+// Mesh::updateVertexPositionsAndColors (reference: src/mesh.cpp:823-855); ids are one-based. Returns -1 on a bad id.
+int orc_mesh_update_positions_and_colors(void* mesh, const int32_t* ids, uint32_t n, const float* dpos, const float* dcol) {
+    Mesh* m = (Mesh*)mesh;
+    for (uint32_t i = 0; i < n; ++i) {
+        int32_t v = ids[i] - 1;
+        if (v < 0 || (size_t)v >= m->verts.size()) return -1;
+        if (dpos) for (int k = 0; k < 3; ++k) m->verts[v].pos[k] = m->verts[v].pos[k] + dpos[3 * (size_t)i + k];
+        if (dcol) for (int k = 0; k < 4; ++k) m->verts[v].color[k] = m->verts[v].color[k] + dcol[4 * (size_t)i + k];
+    }
+    if (dpos && n) orc_mesh_recompute_normals(mesh);
+    return 0;
+}
+void orc_mesh_read_vertices(const void* mesh, void* out68) {
+    const Mesh* m = (const Mesh*)mesh;
+    std::memcpy(out68, m->verts.data(), m->verts.size() * sizeof(Vertex68));
+}
 void orc_mesh_destroy(void* m) { delete (Mesh*)m; }
 
 void* orc_texture_create(const slb_image* image, int kind) {

@@ -117,6 +117,11 @@ PROTOTYPES = {
                                    C.c_uint32, C.POINTER(Material), C.c_uint32, C.POINTER(Image), C.c_uint32,
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_void_p)]),
     "slb_mesh_update_vertices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "slb_mesh_update_positions_and_colors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "slb_mesh_set_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "slb_mesh_set_colors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "slb_mesh_recompute_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "slb_mesh_read_vertices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "slb_mesh_destroy": (None, [C.c_void_p, C.c_void_p]),
     "slb_texture_create": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int, C.POINTER(C.c_void_p)]),
     "slb_texture_destroy": (None, [C.c_void_p, C.c_void_p]),

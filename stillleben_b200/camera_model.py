@@ -21,6 +21,13 @@ __all__ = ["chromatic_aberration", "blur", "exposure", "noise", "color_jitter", 
            "process_batch", "random_parameters"]
 
 
+def _stream(ctx):
+    """torch's CURRENT stream on the context's device: the library work is ordered after the torch ops that produced the
+    inputs (stack / to / contiguous) instead of racing them on a private stream."""
+    import torch
+    return torch.cuda.current_stream(torch.device("cuda", ctx.device)).cuda_stream
+
+
 def _params(stages, chromatic_translation=None, chromatic_scaling=None, blur_sigma=0.0, exposure_deltaS=0.0, do_noise=False,
             noise_a=0.0, noise_b=0.0, hue_shift=0.0, seed=None):
     p = abi.CameraParams()
@@ -46,7 +53,7 @@ def _run(images, params, u8=False):
     H, W = (x.shape[1], x.shape[2]) if u8 else (x.shape[2], x.shape[3])
     out = torch.empty((n, 3, H, W), dtype=torch.float32, device=dev)
     arr = (abi.CameraParams * n)(*params)
-    rc = ctx.lib.slb_camera_model(ctx.h, x.data_ptr(), 1 if u8 else 0, out.data_ptr(), n, H, W, arr, None)
+    rc = ctx.lib.slb_camera_model(ctx.h, x.data_ptr(), 1 if u8 else 0, out.data_ptr(), n, H, W, arr, _stream(ctx))
     if rc != 0:
         raise RuntimeError(ctx.lib.slb_last_error(ctx.h).decode())
     ctx.synchronize()

@@ -12,7 +12,8 @@
 using namespace slbk;
 
 // 68-byte interleaved record {pos3, uv2, color4, tangent4, id, normal3} -> pos4[] + attr[3]
-__global__ void k_repack(const uint8_t* __restrict__ v68, uint32_t n, float4* __restrict__ pos4, float4* __restrict__ attr) {
+__global__ void k_repack(const uint8_t* __restrict__ v68, uint32_t n, float4* __restrict__ pos4, float4* __restrict__ attr,
+                         float4* __restrict__ col4) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* v = reinterpret_cast<const float*>(v68 + (size_t)i * SLB_VERTEX_STRIDE);   // 68 = 17 words: 4-byte aligned
@@ -20,6 +21,88 @@ __global__ void k_repack(const uint8_t* __restrict__ v68, uint32_t n, float4* __
     attr[3 * (size_t)i + 0] = make_float4(v[3], v[4], v[14], v[15]);                        // u, v, nx, ny
     attr[3 * (size_t)i + 1] = make_float4(v[16], v[9], v[10], v[11]);                       // nz, tx, ty, tz
     attr[3 * (size_t)i + 2] = make_float4(v[12], 0.f, 0.f, 0.f);                            // tw
+    col4[i] = make_float4(v[5], v[6], v[7], v[8]);   // vertex colours: never read by the renderer, kept for Mesh::colors / update_colors
+}
+// the inverse: pos4[] + attr[] + col4[] -> the 68-byte record (read-back for Mesh::points / normals / colors accessors)
+__global__ void k_unpack(const float4* __restrict__ pos4, const float4* __restrict__ attr, const float4* __restrict__ col4, uint32_t n,
+                         uint8_t* __restrict__ v68) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* v = reinterpret_cast<float*>(v68 + (size_t)i * SLB_VERTEX_STRIDE);
+    const float4 p = pos4[i], a0 = attr[3 * (size_t)i], a1 = attr[3 * (size_t)i + 1], a2 = attr[3 * (size_t)i + 2], c = col4[i];
+    v[0] = p.x; v[1] = p.y; v[2] = p.z; v[13] = p.w;
+    v[3] = a0.x; v[4] = a0.y; v[14] = a0.z; v[15] = a0.w;
+    v[16] = a1.x; v[9] = a1.y; v[10] = a1.z; v[11] = a1.w; v[12] = a2.x;
+    v[5] = c.x; v[6] = c.y; v[7] = c.z; v[8] = c.w;
+}
+// largest index value of an index buffer (upload-time validation: an index >= n_vertices would be an out-of-bounds read in
+// every kernel that dereferences pos4[idx])
+__global__ void k_index_max(const uint32_t* __restrict__ idx, uint32_t n, uint32_t* __restrict__ out) {
+    uint32_t m = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, idx[i]);
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// ---- vertex edit path (reference: Mesh::updateVertexPositionsAndColors / setVertexPositions / recomputeNormals,
+// src/mesh.cpp:763-878) ----
+// point[id-1] += update (ids are one-based vertex ids, mesh.cpp:830-835); colour likewise (:845-850). err: out-of-range id seen.
+__global__ void k_vertex_delta(const int32_t* __restrict__ ids, uint32_t n, const float* __restrict__ dpos, const float* __restrict__ dcol,
+                               float4* __restrict__ pos4, float4* __restrict__ col4, uint32_t n_vertices, uint32_t* __restrict__ err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t v = ids[i] - 1;
+    if (v < 0 || (uint32_t)v >= n_vertices) { atomicExch(err, 1u); return; }
+    if (dpos) {   // float atomics: a vertex listed twice accumulates both updates (the reference does so sequentially)
+        atomicAdd(&pos4[v].x, dpos[3 * (size_t)i]); atomicAdd(&pos4[v].y, dpos[3 * (size_t)i + 1]); atomicAdd(&pos4[v].z, dpos[3 * (size_t)i + 2]);
+    }
+    if (dcol) {
+        atomicAdd(&col4[v].x, dcol[4 * (size_t)i]); atomicAdd(&col4[v].y, dcol[4 * (size_t)i + 1]);
+        atomicAdd(&col4[v].z, dcol[4 * (size_t)i + 2]); atomicAdd(&col4[v].w, dcol[4 * (size_t)i + 3]);
+    }
+}
+__global__ void k_set_positions(const float* __restrict__ p3, uint32_t n, float4* __restrict__ pos4) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pos4[i].x = p3[3 * (size_t)i]; pos4[i].y = p3[3 * (size_t)i + 1]; pos4[i].z = p3[3 * (size_t)i + 2];
+}
+__global__ void k_set_colors(const float* __restrict__ c4, uint32_t n, float4* __restrict__ col4) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    col4[i] = make_float4(c4[4 * (size_t)i], c4[4 * (size_t)i + 1], c4[4 * (size_t)i + 2], c4[4 * (size_t)i + 3]);
+}
+// recomputeNormals pass 1 (mesh.cpp:776-803): per face, cross = (v1 - v2) x (v1 - v3), area = |cross|, normal = cross.normalized();
+// stored: normal * area. Explicit round-to-nearest intrinsics (no fma contraction): bit-identical with the oracle's twin,
+// incl. the NaN a zero-area face produces (0 * inf), which the reference propagates into the vertex normal.
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+__global__ void k_face_normals(const float4* __restrict__ pos4, const uint32_t* __restrict__ idx, uint32_t n_faces, float4* __restrict__ face_n) {
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_faces) return;
+    const float4 v1 = pos4[idx[3 * (size_t)f]], v2 = pos4[idx[3 * (size_t)f + 1]], v3 = pos4[idx[3 * (size_t)f + 2]];
+    const float ax = __fsub_rn(v1.x, v2.x), ay = __fsub_rn(v1.y, v2.y), az = __fsub_rn(v1.z, v2.z);
+    const float bx = __fsub_rn(v1.x, v3.x), by = __fsub_rn(v1.y, v3.y), bz = __fsub_rn(v1.z, v3.z);
+    const float cx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(by, az)), cy = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(bz, ax)),
+                cz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(bx, ay));
+    const float area = __fsqrt_rn(dot3_rn(cx, cy, cz, cx, cy, cz));
+    const float inv = __fdiv_rn(1.0f, area);                     // Vector::normalized() = *this * lengthInverted()
+    face_n[f] = make_float4(__fmul_rn(__fmul_rn(cx, inv), area), __fmul_rn(__fmul_rn(cy, inv), area), __fmul_rn(__fmul_rn(cz, inv), area), 0.f);
+}
+// pass 2 (mesh.cpp:805-818): per vertex, sum of its faces' (normal * area) in ascending face order, normalised; written into the
+// normal slot of the attribute stream
+__global__ void k_vertex_normals(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj_face, const float4* __restrict__ face_n,
+                                 uint32_t n_vertices, float4* __restrict__ attr) {
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_vertices) return;
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    for (uint32_t k = adj_off[v]; k < adj_off[v + 1]; ++k) {
+        const float4 fn = face_n[adj_face[k]];
+        nx = __fadd_rn(nx, fn.x); ny = __fadd_rn(ny, fn.y); nz = __fadd_rn(nz, fn.z);
+    }
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(dot3_rn(nx, ny, nz, nx, ny, nz)));
+    nx = __fmul_rn(nx, inv); ny = __fmul_rn(ny, inv); nz = __fmul_rn(nz, inv);
+    attr[3 * (size_t)v].z = nx; attr[3 * (size_t)v].w = ny; attr[3 * (size_t)v + 1].x = nz;
 }
 
 __global__ void k_expand_rgba(const uint8_t* __restrict__ src, int channels, uint8_t* __restrict__ dst, size_t n) {
@@ -189,8 +272,29 @@ __global__ void k_brdf_lut(float4* __restrict__ out, int size, int n_samples) {
 
 namespace slbk {
 
-void launch_repack_vertices(const uint8_t* verts68, uint32_t n, float4* pos4, float4* attr, cudaStream_t s) {
-    if (n) k_repack<<<(n + 255) / 256, 256, 0, s>>>(verts68, n, pos4, attr);
+void launch_repack_vertices(const uint8_t* verts68, uint32_t n, float4* pos4, float4* attr, float4* col4, cudaStream_t s) {
+    if (n) k_repack<<<(n + 255) / 256, 256, 0, s>>>(verts68, n, pos4, attr, col4);
+}
+void launch_unpack_vertices(const float4* pos4, const float4* attr, const float4* col4, uint32_t n, uint8_t* verts68, cudaStream_t s) {
+    if (n) k_unpack<<<(n + 255) / 256, 256, 0, s>>>(pos4, attr, col4, n, verts68);
+}
+void launch_index_max(const uint32_t* idx, uint32_t n, uint32_t* out, cudaStream_t s) {
+    if (n) k_index_max<<<min((n + 255) / 256, 1184u), 256, 0, s>>>(idx, n, out);
+}
+void launch_vertex_delta(const int32_t* ids, uint32_t n, const float* dpos, const float* dcol, float4* pos4, float4* col4, uint32_t n_vertices,
+                         uint32_t* err, cudaStream_t s) {
+    if (n) k_vertex_delta<<<(n + 255) / 256, 256, 0, s>>>(ids, n, dpos, dcol, pos4, col4, n_vertices, err);
+}
+void launch_set_positions(const float* p3, uint32_t n, float4* pos4, cudaStream_t s) {
+    if (n) k_set_positions<<<(n + 255) / 256, 256, 0, s>>>(p3, n, pos4);
+}
+void launch_set_colors(const float* c4, uint32_t n, float4* col4, cudaStream_t s) {
+    if (n) k_set_colors<<<(n + 255) / 256, 256, 0, s>>>(c4, n, col4);
+}
+void launch_recompute_normals(const float4* pos4, const uint32_t* idx, uint32_t n_faces, const uint32_t* adj_off, const uint32_t* adj_face,
+                              float4* face_n, uint32_t n_vertices, float4* attr, cudaStream_t s) {
+    if (n_faces) k_face_normals<<<(n_faces + 255) / 256, 256, 0, s>>>(pos4, idx, n_faces, face_n);
+    if (n_vertices) k_vertex_normals<<<(n_vertices + 255) / 256, 256, 0, s>>>(adj_off, adj_face, face_n, n_vertices, attr);
 }
 void launch_expand_rgba(const uint8_t* src, int channels, uint8_t* dst, size_t n_texels, cudaStream_t s) {
     if (n_texels) k_expand_rgba<<<(unsigned)((n_texels + 255) / 256), 256, 0, s>>>(src, channels, dst, n_texels);

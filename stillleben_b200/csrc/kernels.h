@@ -28,7 +28,15 @@ void launch_ssao(const DFrame* frames, int n_frames, int W, int H, cudaStream_t 
 void launch_ssao_apply_tonemap(const DFrame* frames, int n_frames, int W, int H, cudaStream_t s);
 
 // k_assets.cu
-void launch_repack_vertices(const uint8_t* verts68, uint32_t n, float4* pos4, float4* attr, cudaStream_t s);
+void launch_repack_vertices(const uint8_t* verts68, uint32_t n, float4* pos4, float4* attr, float4* col4, cudaStream_t s);
+void launch_unpack_vertices(const float4* pos4, const float4* attr, const float4* col4, uint32_t n, uint8_t* verts68, cudaStream_t s);
+void launch_index_max(const uint32_t* idx, uint32_t n, uint32_t* out, cudaStream_t s);
+void launch_vertex_delta(const int32_t* ids, uint32_t n, const float* dpos, const float* dcol, float4* pos4, float4* col4, uint32_t n_vertices,
+                         uint32_t* err, cudaStream_t s);
+void launch_set_positions(const float* p3, uint32_t n, float4* pos4, cudaStream_t s);
+void launch_set_colors(const float* c4, uint32_t n, float4* col4, cudaStream_t s);
+void launch_recompute_normals(const float4* pos4, const uint32_t* idx, uint32_t n_faces, const uint32_t* adj_off, const uint32_t* adj_face,
+                              float4* face_n, uint32_t n_vertices, float4* attr, cudaStream_t s);
 void launch_expand_rgba(const uint8_t* src, int channels, uint8_t* dst, size_t n_texels, cudaStream_t s);
 void launch_mip_level(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh, cudaStream_t s);
 void launch_cube_mip(const float4* src, int ssize, float4* dst, cudaStream_t s);

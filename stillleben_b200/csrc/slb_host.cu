@@ -45,6 +45,9 @@ struct slb_texture {
 };
 struct slb_mesh {
     float4* pos4 = nullptr; float4* attr = nullptr; uint32_t* idx = nullptr;
+    float4* col4 = nullptr;                                   // vertex colours (never read by the renderer)
+    // vertex-edit path (built on first use): vertex -> faces adjacency in ascending face order (CSR), per-face scratch
+    uint32_t* adj_off = nullptr; uint32_t* adj_face = nullptr; float4* face_n = nullptr;
     uint32_t n_vertices = 0, n_indices = 0;
     std::vector<slb_submesh> submeshes;
     std::vector<slb_material> materials;
@@ -105,6 +108,11 @@ struct Scratch {
 struct slb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // All per-context scratch (two Scratch sets, shadow pool + generation tags, staging, diff / camera / PNG buffers) is
+    // shared between calls, so calls are ORDERED even when they name different streams: enter_stream() makes the
+    // stream of an entry point wait for everything the previous entry point queued. last_stream = where that was.
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t order_event = nullptr;
     std::string err;
     bool time_kernels = false, keep_hdr = false;
     int max_subbatch = 64;
@@ -123,11 +131,29 @@ struct slb_ctx {
     struct Ev { int stage; cudaEvent_t a, b; };
     std::vector<Ev> events;
     std::vector<cudaEvent_t> event_pool;
+    float time_acc[16] = {0};   // stage times already drained from `events` (bounded: see StageTimer)
     // host-render slots
     slb_result* slot[2] = {nullptr, nullptr};
     cudaEvent_t slot_rendered[2] = {nullptr, nullptr}, slot_copied[2] = {nullptr, nullptr};
 };
 static thread_local std::string g_create_error;
+
+// The stream an entry point queues its work on (NULL = the context's own), ordered after the previous entry point's work.
+static cudaStream_t enter_stream(slb_ctx* ctx, void* stream) {
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    if (ctx->last_stream && s != ctx->last_stream && ctx->order_event) {
+        cudaEventRecord(ctx->order_event, ctx->last_stream);
+        cudaStreamWaitEvent(s, ctx->order_event, 0);
+    }
+    ctx->last_stream = s;
+    return s;
+}
+// Wait for everything queued through this context, on whichever stream it went (read-back, destroy, update paths).
+static cudaError_t sync_ctx(slb_ctx* ctx) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (ctx->last_stream && ctx->last_stream != ctx->stream) { cudaError_t e2 = cudaStreamSynchronize(ctx->last_stream); if (e == cudaSuccess) e = e2; }
+    return e;
+}
 
 static int fail(slb_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg; else g_create_error = msg;
@@ -194,7 +220,7 @@ extern "C" int slb_ctx_create(int device, slb_ctx** out) {
     ctx = c;
     cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-    cudaError_t e3 = cudaSuccess;
+    cudaError_t e3 = cudaEventCreateWithFlags(&c->order_event, cudaEventDisableTiming);
     for (Scratch& S : c->scr) {
         if (e3 == cudaSuccess) e3 = cudaHostAlloc((void**)&S.total_pinned, 64, cudaHostAllocPortable | cudaHostAllocMapped);
         if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&S.scanned, cudaEventDisableTiming);
@@ -228,7 +254,7 @@ extern "C" int slb_ctx_create(int device, slb_ctx** out) {
 extern "C" int slb_ctx_synchronize(slb_ctx* ctx) {
     if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
     CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(sync_ctx(ctx));
     CU(cudaStreamSynchronize(ctx->copy_stream));
     return SLB_OK;
 }
@@ -248,6 +274,7 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ctx->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->order_event) cudaEventDestroy(ctx->order_event);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -338,7 +365,7 @@ extern "C" int slb_texture_create(slb_ctx* ctx, const slb_image* image, int kind
         t->h.px = t->px;
         e = cudaMemcpyAsync(t->d, &t->h, sizeof(DTexture), cudaMemcpyHostToDevice, ctx->stream);
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = sync_ctx(ctx);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (raw) cudaFree(raw);
     if (e != cudaSuccess) {
@@ -366,7 +393,7 @@ extern "C" int slb_texture_read_level(slb_ctx* ctx, const slb_texture* tex, int 
 
 extern "C" void slb_texture_destroy(slb_ctx* ctx, slb_texture* tex) {
     if (!tex) return;
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx) { cudaSetDevice(ctx->device); sync_ctx(ctx); }
     if (tex->px) cudaFree(tex->px);
     if (tex->d) cudaFree(tex->d);
     delete tex;
@@ -400,20 +427,28 @@ extern "C" int slb_mesh_upload(slb_ctx* ctx, const void* vertices, uint32_t n_ve
     void* raw = nullptr;
     cudaError_t e = cudaMalloc((void**)&m->pos4, (size_t)n_vertices * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc((void**)&m->attr, (size_t)n_vertices * 3 * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->col4, (size_t)n_vertices * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc((void**)&m->idx, (size_t)(n_indices ? n_indices : 1) * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&raw, (size_t)n_vertices * SLB_VERTEX_STRIDE);
+    if (e == cudaSuccess) e = cudaMalloc(&raw, (size_t)n_vertices * SLB_VERTEX_STRIDE + sizeof(uint32_t));
+    uint32_t* d_max = raw ? reinterpret_cast<uint32_t*>((uint8_t*)raw + (size_t)n_vertices * SLB_VERTEX_STRIDE) : nullptr;   // 68 n is 4-byte aligned
+    uint32_t h_max = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(raw, vertices, (size_t)n_vertices * SLB_VERTEX_STRIDE, cudaMemcpyDefault, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(m->idx, indices, (size_t)n_indices * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_max, 0, sizeof(uint32_t), ctx->stream);
     if (e == cudaSuccess) {
-        launch_repack_vertices((const uint8_t*)raw, n_vertices, m->pos4, m->attr, ctx->stream);
-        ctx->stats.kernel_launches += 1;
-        e = cudaStreamSynchronize(ctx->stream);
+        launch_repack_vertices((const uint8_t*)raw, n_vertices, m->pos4, m->attr, m->col4, ctx->stream);
+        launch_index_max(m->idx, n_indices, d_max, ctx->stream);
+        ctx->stats.kernel_launches += 2;
+        e = cudaMemcpyAsync(&h_max, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = sync_ctx(ctx);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (raw) cudaFree(raw);
     int rc = SLB_OK;
     if (e != cudaSuccess) rc = fail(ctx, e == cudaErrorMemoryAllocation ? SLB_ERR_OUT_OF_MEMORY : SLB_ERR_CUDA, std::string("slb_mesh_upload: ") + cudaGetErrorString(e));
-    // index range check on the host copy when the source is host memory is the caller's job; textures:
+    // every kernel dereferences pos4[idx] / attr[idx] unchecked: reject an index buffer that points past the vertices
+    else if (n_indices && h_max >= n_vertices) rc = fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_mesh_upload: index value out of range (>= n_vertices)");
+    // textures:
     for (uint32_t i = 0; rc == SLB_OK && i < n_images; ++i) {
         slb_texture* t = nullptr;
         rc = slb_texture_create(ctx, &images[i], SLB_TEXTURE_2D, &t);
@@ -432,22 +467,131 @@ extern "C" int slb_mesh_update_vertices(slb_ctx* ctx, slb_mesh* mesh, const void
     CU(cudaMalloc(&raw, (size_t)n_vertices * SLB_VERTEX_STRIDE));
     cudaError_t e = cudaMemcpyAsync(raw, vertices, (size_t)n_vertices * SLB_VERTEX_STRIDE, cudaMemcpyDefault, ctx->stream);
     if (e == cudaSuccess) {
-        launch_repack_vertices((const uint8_t*)raw, n_vertices, mesh->pos4, mesh->attr, ctx->stream);
+        launch_repack_vertices((const uint8_t*)raw, n_vertices, mesh->pos4, mesh->attr, mesh->col4, ctx->stream);
         ctx->stats.kernel_launches += 1;
-        e = cudaStreamSynchronize(ctx->stream);
+        e = sync_ctx(ctx);
     }
     cudaFree(raw);
     if (e != cudaSuccess) return fail(ctx, SLB_ERR_CUDA, std::string("slb_mesh_update_vertices: ") + cudaGetErrorString(e));
     return SLB_OK;
 }
 
+// vertex -> faces adjacency in ascending face order (the summation order of Mesh::recomputeNormals, mesh.cpp:776-816),
+// built once per mesh on the host from the resident index buffer
+static int mesh_build_adjacency(slb_ctx* ctx, slb_mesh* m) {
+    if (m->adj_off) return SLB_OK;
+    std::vector<uint32_t> idx(m->n_indices), off(m->n_vertices + 1, 0u), faces(m->n_indices);
+    CU(cudaMemcpy(idx.data(), m->idx, (size_t)m->n_indices * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < m->n_indices; ++i) off[idx[i] + 1]++;
+    for (uint32_t v = 0; v < m->n_vertices; ++v) off[v + 1] += off[v];
+    std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+    for (uint32_t i = 0; i < m->n_indices; ++i) faces[cur[idx[i]]++] = i / 3;     // face order ascending; a face listing a vertex twice counts twice
+    CU(cudaMalloc((void**)&m->adj_off, off.size() * sizeof(uint32_t)));
+    CU(cudaMalloc((void**)&m->adj_face, (faces.size() ? faces.size() : 1) * sizeof(uint32_t)));
+    CU(cudaMalloc((void**)&m->face_n, (size_t)(m->n_indices / 3 ? m->n_indices / 3 : 1) * sizeof(float4)));
+    CU(cudaMemcpy(m->adj_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->adj_face, faces.data(), faces.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return SLB_OK;
+}
+static cudaStream_t mesh_stream(slb_ctx* ctx, void* stream) { return enter_stream(ctx, stream); }
+
+extern "C" int slb_mesh_recompute_normals(slb_ctx* ctx, slb_mesh* mesh, void* stream) {
+    if (!ctx || !mesh) return SLB_ERR_INVALID_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    int rc = mesh_build_adjacency(ctx, mesh);
+    if (rc != SLB_OK) return rc;
+    cudaStream_t s = mesh_stream(ctx, stream);
+    launch_recompute_normals(mesh->pos4, mesh->idx, mesh->n_indices / 3, mesh->adj_off, mesh->adj_face, mesh->face_n, mesh->n_vertices, mesh->attr, s);
+    ctx->stats.kernel_launches += 2;
+    CU(cudaGetLastError());
+    return SLB_OK;
+}
+
+extern "C" int slb_mesh_update_positions_and_colors(slb_ctx* ctx, slb_mesh* mesh, const int32_t* vertex_ids, uint32_t n,
+                                                    const float* position_update, const float* color_update, void* stream) {
+    if (!ctx || !mesh || (n && !vertex_ids)) return SLB_ERR_INVALID_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = mesh_stream(ctx, stream);
+    if (n && (position_update || color_update)) {
+        // the three arrays may live in host or device memory (UVA): stage them on the device
+        const size_t b_ids = (size_t)n * 4, b_pos = position_update ? (size_t)n * 12 : 0, b_col = color_update ? (size_t)n * 16 : 0;
+        uint8_t* stage = nullptr;
+        CU(cudaMallocAsync((void**)&stage, b_ids + b_pos + b_col + 4, s));
+        uint32_t* d_err = reinterpret_cast<uint32_t*>(stage + b_ids + b_pos + b_col);
+        CU(cudaMemcpyAsync(stage, vertex_ids, b_ids, cudaMemcpyDefault, s));
+        if (b_pos) CU(cudaMemcpyAsync(stage + b_ids, position_update, b_pos, cudaMemcpyDefault, s));
+        if (b_col) CU(cudaMemcpyAsync(stage + b_ids + b_pos, color_update, b_col, cudaMemcpyDefault, s));
+        CU(cudaMemsetAsync(d_err, 0, 4, s));
+        launch_vertex_delta(reinterpret_cast<const int32_t*>(stage), n, b_pos ? reinterpret_cast<const float*>(stage + b_ids) : nullptr,
+                            b_col ? reinterpret_cast<const float*>(stage + b_ids + b_pos) : nullptr, mesh->pos4, mesh->col4, mesh->n_vertices, d_err, s);
+        ctx->stats.kernel_launches += 1;
+        uint32_t h_err = 0;
+        CU(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaFreeAsync(stage, s));
+        CU(cudaStreamSynchronize(s));
+        if (h_err) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_mesh_update_positions_and_colors: vertex id out of range (ids are one-based)");
+    }
+    if (position_update && n) return slb_mesh_recompute_normals(ctx, mesh, stream);    // mesh.cpp:840-841
+    return SLB_OK;
+}
+
+extern "C" int slb_mesh_set_positions(slb_ctx* ctx, slb_mesh* mesh, const float* positions, uint32_t n_vertices, void* stream) {
+    if (!ctx || !mesh || !positions) return SLB_ERR_INVALID_ARGUMENT;
+    if (n_vertices != mesh->n_vertices)   // mesh.cpp:862-863
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "Number of new vertices should match the existing mesh vertices");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = mesh_stream(ctx, stream);
+    float* stage = nullptr;
+    CU(cudaMallocAsync((void**)&stage, (size_t)n_vertices * 12, s));
+    CU(cudaMemcpyAsync(stage, positions, (size_t)n_vertices * 12, cudaMemcpyDefault, s));
+    launch_set_positions(stage, n_vertices, mesh->pos4, s);
+    ctx->stats.kernel_launches += 1;
+    CU(cudaFreeAsync(stage, s));
+    return slb_mesh_recompute_normals(ctx, mesh, stream);                                // mesh.cpp:868
+}
+
+extern "C" int slb_mesh_set_colors(slb_ctx* ctx, slb_mesh* mesh, const float* colors, uint32_t n_vertices, void* stream) {
+    if (!ctx || !mesh || !colors) return SLB_ERR_INVALID_ARGUMENT;
+    if (n_vertices != mesh->n_vertices)   // mesh.cpp:878-879
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "Number of new vertices should match the existing mesh vertices for vertex color update");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = mesh_stream(ctx, stream);
+    float* stage = nullptr;
+    CU(cudaMallocAsync((void**)&stage, (size_t)n_vertices * 16, s));
+    CU(cudaMemcpyAsync(stage, colors, (size_t)n_vertices * 16, cudaMemcpyDefault, s));
+    launch_set_colors(stage, n_vertices, mesh->col4, s);
+    ctx->stats.kernel_launches += 1;
+    CU(cudaFreeAsync(stage, s));
+    return SLB_OK;
+}
+
+extern "C" int slb_mesh_read_vertices(slb_ctx* ctx, const slb_mesh* mesh, void* vertices_out, uint32_t n_vertices) {
+    if (!ctx || !mesh || !vertices_out) return SLB_ERR_INVALID_ARGUMENT;
+    if (n_vertices != mesh->n_vertices) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_mesh_read_vertices: vertex count mismatch");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());      // edits may have been queued on a caller stream
+    uint8_t* raw = nullptr;
+    CU(cudaMalloc((void**)&raw, (size_t)n_vertices * SLB_VERTEX_STRIDE));
+    launch_unpack_vertices(mesh->pos4, mesh->attr, mesh->col4, n_vertices, raw, ctx->stream);
+    ctx->stats.kernel_launches += 1;
+    cudaError_t e = cudaMemcpyAsync(vertices_out, raw, (size_t)n_vertices * SLB_VERTEX_STRIDE, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = sync_ctx(ctx);
+    cudaFree(raw);
+    if (e != cudaSuccess) return fail(ctx, SLB_ERR_CUDA, std::string("slb_mesh_read_vertices: ") + cudaGetErrorString(e));
+    return SLB_OK;
+}
+
 extern "C" void slb_mesh_destroy(slb_ctx* ctx, slb_mesh* mesh) {
     if (!mesh) return;
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx) { cudaSetDevice(ctx->device); sync_ctx(ctx); }
     for (slb_texture* t : mesh->textures) slb_texture_destroy(ctx, t);
     if (mesh->pos4) cudaFree(mesh->pos4);
     if (mesh->attr) cudaFree(mesh->attr);
     if (mesh->idx) cudaFree(mesh->idx);
+    if (mesh->col4) cudaFree(mesh->col4);
+    if (mesh->adj_off) cudaFree(mesh->adj_off);
+    if (mesh->adj_face) cudaFree(mesh->adj_face);
+    if (mesh->face_n) cudaFree(mesh->face_n);
     delete mesh;
 }
 
@@ -526,7 +670,7 @@ extern "C" int slb_lightmap_create_ex(slb_ctx* ctx, const slb_lightmap_desc* des
             launch_prefilter(lm->d, const_cast<float4*>(lm->h.pre[mip].px), lm->h.pre[mip].size, (float)mip / 4.0f, n_samples, (float)env_size, ctx->stream);
         launch_brdf_lut(lut, lut_size, n_samples, ctx->stream);
         ctx->stats.kernel_launches += 7;
-        cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+        cudaError_t e2 = sync_ctx(ctx);
         if (e2 == cudaSuccess) e2 = cudaGetLastError();
         if (e2 != cudaSuccess) { rc = fail(ctx, SLB_ERR_CUDA, std::string("slb_lightmap_create: ") + cudaGetErrorString(e2)); break; }
     } while (0);
@@ -541,7 +685,7 @@ extern "C" int slb_lightmap_create(slb_ctx* ctx, const slb_lightmap_desc* desc, 
 extern "C" int slb_lightmap_read(slb_ctx* ctx, const slb_lightmap* lm, int which, float* host_out, size_t n_floats) {
     if (!ctx || !lm || !host_out) return SLB_ERR_INVALID_ARGUMENT;
     CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(sync_ctx(ctx));
     if (which == 0 || which == 1 || which == 3) {
         const void* src = which == 0 ? (const void*)lm->h.env[0].px : which == 1 ? (const void*)lm->h.irr.px : (const void*)lm->h.lut;
         size_t n = which == 0 ? (size_t)6 * lm->env_size * lm->env_size * 4 : which == 1 ? (size_t)6 * lm->irr_size * lm->irr_size * 4
@@ -570,7 +714,7 @@ extern "C" int slb_lightmap_sizes(const slb_lightmap* lm, int32_t sizes[4]) {
 
 extern "C" void slb_lightmap_destroy(slb_ctx* ctx, slb_lightmap* lm) {
     if (!lm) return;
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx) { cudaSetDevice(ctx->device); sync_ctx(ctx); }
     for (void* p : lm->allocs) cudaFree(p);
     delete lm;
 }
@@ -624,7 +768,7 @@ extern "C" int slb_result_read(slb_ctx* ctx, const slb_result* res, int target, 
     size_t per = (size_t)res->W * res->H * kTargetBpp[target];
     if (host_bytes < per * n_frames) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_result_read: host buffer too small");
     CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(sync_ctx(ctx));
     CU(cudaMemcpy(host_out, (const uint8_t*)res->ptrs[target] + per * first_frame, per * n_frames, cudaMemcpyDeviceToHost));
     ctx->stats.bytes_d2h += per * n_frames;
     return SLB_OK;
@@ -635,14 +779,14 @@ extern "C" int slb_result_read_hdr(slb_ctx* ctx, const slb_result* res, int32_t 
     if (!res->hdr) return fail(ctx, SLB_ERR_RUNTIME, "slb_result_read_hdr: result was created without SLB_OPT_KEEP_HDR");
     if (frame < 0 || frame >= res->n_frames || n_floats < (size_t)res->W * res->H * 4) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_result_read_hdr: bad frame / size");
     CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(sync_ctx(ctx));
     CU(cudaMemcpy(host_out, res->hdr + (size_t)frame * res->W * res->H, (size_t)res->W * res->H * sizeof(float4), cudaMemcpyDeviceToHost));
     return SLB_OK;
 }
 
 extern "C" void slb_result_destroy(slb_ctx* ctx, slb_result* res) {
     if (!res) return;
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); }
+    if (ctx) { cudaSetDevice(ctx->device); sync_ctx(ctx); cudaStreamSynchronize(ctx->copy_stream); }
     for (int t = 0; t < SLB_NUM_TARGETS; ++t) if (res->owned[t] && res->ptrs[t]) cudaFree(res->ptrs[t]);
     if (res->hdr) cudaFree(res->hdr);
     delete res;
@@ -978,12 +1122,26 @@ static cudaEvent_t get_event(slb_ctx* ctx) {
     if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
+// completed stage timings -> ctx->time_acc, events back to the pool
+static void drain_events(slb_ctx* ctx) {
+    for (auto& e : ctx->events) {
+        cudaEventSynchronize(e.b);
+        float ms = 0; cudaEventElapsedTime(&ms, e.a, e.b);
+        ctx->time_acc[e.stage] += ms;
+        ctx->event_pool.push_back(e.a); ctx->event_pool.push_back(e.b);
+    }
+    ctx->events.clear();
+}
 struct StageTimer {
     slb_ctx* ctx; cudaStream_t s; int stage; cudaEvent_t a = nullptr, b = nullptr;
     StageTimer(slb_ctx* c, cudaStream_t st, int stage_) : ctx(c), s(st), stage(stage_) {
         if (ctx->time_kernels) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, s); }
     }
-    ~StageTimer() { if (ctx->time_kernels) { cudaEventRecord(b, s); ctx->events.push_back({stage, a, b}); } }
+    ~StageTimer() {
+        if (!ctx->time_kernels) return;
+        cudaEventRecord(b, s); ctx->events.push_back({stage, a, b});
+        if (ctx->events.size() >= 4096) drain_events(ctx);   // bounded even if nobody ever asks for the statistics
+    }
 };
 
 static int subbatch_setup_scan(slb_ctx* ctx, Scratch& S, cudaStream_t s);
@@ -1238,16 +1396,8 @@ static int render_subbatch(slb_ctx* ctx, const slb_scene_desc* scenes, int n, sl
 // Stage times are recorded as events on the stream and only read here, on demand: no synchronisation inside the
 // render calls, so timing a run does not drain the sub-batch pipeline between calls.
 static void collect_times(slb_ctx* ctx) {
-    if (ctx->events.empty()) return;
-    float acc[ST_N] = {0};
-    for (auto& e : ctx->events) {
-        cudaEventSynchronize(e.b);
-        float ms = 0; cudaEventElapsedTime(&ms, e.a, e.b);
-        acc[e.stage] += ms;
-        ctx->event_pool.push_back(e.a); ctx->event_pool.push_back(e.b);
-    }
-    ctx->events.clear();
-    for (int i = 0; i < 8; ++i) ctx->stats.last_kernel_ms[i] = i < ST_N ? acc[i] : 0.0f;
+    drain_events(ctx);
+    for (int i = 0; i < 8; ++i) { ctx->stats.last_kernel_ms[i] = i < ST_N ? ctx->time_acc[i] : 0.0f; ctx->time_acc[i] = 0.0f; }
 }
 
 extern "C" int slb_render_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int32_t n_scenes, slb_result* result, int32_t first_frame,
@@ -1261,7 +1411,7 @@ extern "C" int slb_render_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int3
     if (ctx->keep_hdr && !result->hdr) return fail(ctx, SLB_ERR_RUNTIME, "slb_render_batch: SLB_OPT_KEEP_HDR is on but the result was created without it");
     for (int i = 0; i < n_scenes; ++i) { int rc = validate_scene(ctx, scenes[i], result); if (rc != SLB_OK) return rc; }
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = enter_stream(ctx, stream);
     // Software pipeline over the two scratch sets: the first phase of sub-batch k+1 (marshal, upload, clear, set-up,
     // scan) is queued BEFORE the host waits for the scan totals of sub-batch k, so the GPU always has work while the
     // host sizes and queues the second phase (emit, raster, shade). Stream order: P1(0) P1(1) P2(0) P1(2) P2(1) ...
@@ -1326,7 +1476,7 @@ extern "C" int slb_render_batch_host(slb_ctx* ctx, const slb_scene_desc* scenes,
         if (dbg) fprintf(stderr, "[slb] sub-batch %d: render_subbatch host %.2f ms (from %.2f), copies queued at %.2f\n", k, t1 - t0, t0 - t_begin, now() - t_begin);
     }
     if (dbg) fprintf(stderr, "[slb] all queued at %.2f ms\n", now() - t_begin);
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(sync_ctx(ctx));
     CU(cudaStreamSynchronize(ctx->copy_stream));
     if (dbg) fprintf(stderr, "[slb] done at %.2f ms\n", now() - t_begin);
     return SLB_OK;
@@ -1340,7 +1490,7 @@ extern "C" int slb_diff_sobel_valid_mask(slb_ctx* ctx, const int16_t* instance_i
     if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
     if (!instance_index || !depth || !valid_out || height <= 0 || width <= 0) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_diff_sobel_valid_mask: bad arguments");
     CU(cudaSetDevice(ctx->device));
-    launch_sobel_valid_mask(instance_index, depth, valid_out, height, width, stream ? (cudaStream_t)stream : ctx->stream);
+    launch_sobel_valid_mask(instance_index, depth, valid_out, height, width, enter_stream(ctx, stream));
     ctx->stats.kernel_launches += 1;
     CU(cudaGetLastError());
     return SLB_OK;
@@ -1352,7 +1502,7 @@ extern "C" int slb_diff_dilate_object_mask(slb_ctx* ctx, const uint8_t* mask, co
     if (!mask || !valid || !coords || !mask_out || !coords_out || coord_stride < 3 || height <= 0 || width <= 0)
         return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_diff_dilate_object_mask: bad arguments");
     CU(cudaSetDevice(ctx->device));
-    launch_dilate_object_mask(mask, valid, coords, coord_stride, mask_out, coords_out, height, width, stream ? (cudaStream_t)stream : ctx->stream);
+    launch_dilate_object_mask(mask, valid, coords, coord_stride, mask_out, coords_out, height, width, enter_stream(ctx, stream));
     ctx->stats.kernel_launches += 1;
     CU(cudaGetLastError());
     return SLB_OK;
@@ -1367,7 +1517,7 @@ extern "C" int slb_diff_pose_grad(slb_ctx* ctx, const uint8_t* rgb, const int16_
         return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_diff_pose_grad: bad arguments");
     if (n_objects == 0) return SLB_OK;
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = enter_stream(ctx, stream);
     // parameter block: P (row-major), then per object T0 (row-major) + instance id
     const size_t n_par = 16 + (size_t)17 * n_objects;
     std::vector<float> par(n_par);
@@ -1400,7 +1550,7 @@ extern "C" int slb_camera_model(slb_ctx* ctx, const void* in, int32_t in_format,
     if (!in || !out || !params || n_images <= 0 || height <= 0 || width <= 0 || (in_format != 0 && in_format != 1) || (const void*)out == in)
         return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_camera_model: bad arguments");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = enter_stream(ctx, stream);
     const size_t img_floats = (size_t)3 * height * width;
     bool any_post = false;
     for (int i = 0; i < n_images; ++i) any_post |= (params[i].stages & SLB_CAM_POST_BLUR) != 0;
@@ -1438,7 +1588,7 @@ extern "C" int slb_png_encode(slb_ctx* ctx, const void* images, int32_t n_images
     if (out_stride < png_file_bound(height, width, channels, bytes_per_channel))
         return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_png_encode: out_stride is smaller than slb_png_bound()");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = enter_stream(ctx, stream);
     if (!ctx->png_tables) { png_upload_tables(); ctx->png_tables = true; }
     const size_t rows = (size_t)n_images * height * png_segments(width, channels, bytes_per_channel);   // deflate blocks
     CU(ctx->png_rows.reserve(rows * png_seg_bound()));

@@ -28,6 +28,12 @@ def _dev():
     return torch.device("cuda", _sl._cuda_index)
 
 
+def _stream():
+    """The library work is queued on torch's CURRENT stream of the device, i.e. behind the torch ops that produced the input
+    tensors (.to(), .contiguous(), autograd outputs) and ahead of the ones that consume the outputs."""
+    return torch.cuda.current_stream(_dev()).cuda_stream
+
+
 def _check(rc, what):
     if rc != 0:
         ctx = _ctx()
@@ -41,7 +47,7 @@ def generate_sobel_valid_mask(instance_index, depth):
     dep = depth.squeeze().to(_dev(), torch.float32).contiguous()
     H, W = inst.shape
     valid = torch.empty((H, W), dtype=torch.uint8, device=_dev())
-    _check(ctx.lib.slb_diff_sobel_valid_mask(ctx.h, inst.data_ptr(), dep.data_ptr(), valid.data_ptr(), H, W, None), "generate_sobel_valid_mask")
+    _check(ctx.lib.slb_diff_sobel_valid_mask(ctx.h, inst.data_ptr(), dep.data_ptr(), valid.data_ptr(), H, W, _stream()), "generate_sobel_valid_mask")
     ctx.synchronize()
     return valid.bool().to(src)
 
@@ -60,7 +66,7 @@ def dilate_object_mask(object_mask, valid_mask, coordinates):
     mask_out = torch.empty((H, W), dtype=torch.uint8, device=_dev())
     coords_out = torch.empty((H, W, 3), dtype=torch.float32, device=_dev())
     _check(ctx.lib.slb_diff_dilate_object_mask(ctx.h, mask.data_ptr(), valid.data_ptr(), coords.data_ptr(), stride, mask_out.data_ptr(),
-                                               coords_out.data_ptr(), H, W, None), "dilate_object_mask")
+                                               coords_out.data_ptr(), H, W, _stream()), "dilate_object_mask")
     ctx.synchronize()
     return mask_out.bool().to(src), coords_out.to(src)
 
@@ -104,7 +110,7 @@ def backpropagate_gradient_to_poses(scene, render_result, grad_objective_wrt_rnd
     ids = np.asarray([o.instance_index for o in objects], np.int32)
     d_out = torch.empty((len(objects), 6), dtype=torch.float32, device=dev)
     _check(ctx.lib.slb_diff_pose_grad(ctx.h, rgb.data_ptr(), inst.data_ptr(), coord.data_ptr(), g.data_ptr(), P.ctypes.data,
-                                      poses.ctypes.data, ids.ctypes.data, len(objects), d_out.data_ptr(), H, W, None),
+                                      poses.ctypes.data, ids.ctypes.data, len(objects), d_out.data_ptr(), H, W, _stream()),
            "backpropagate_gradient_to_poses")
     ctx.synchronize()
     return d_out.cpu()

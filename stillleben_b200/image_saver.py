@@ -18,6 +18,13 @@ import torch
 from . import sl as _sl
 
 
+def _stream(ctx):
+    """torch's CURRENT stream on the context's device: the library work is ordered after the torch ops that produced the
+    inputs (stack / to / contiguous) instead of racing them on a private stream."""
+    import torch
+    return torch.cuda.current_stream(torch.device("cuda", ctx.device)).cuda_stream
+
+
 def encode_batch(images):
     """images: uint8 [n,H,W], [n,H,W,3], [n,H,W,4] or int16 / uint16 [n,H,W] (any device) -> list of n PNG files (bytes)."""
     ctx = _sl._context()
@@ -42,7 +49,7 @@ def encode_batch(images):
     stride = (bound + 255) // 256 * 256
     out = torch.empty((n, stride), dtype=torch.uint8, device=dev)
     sizes = torch.empty((n,), dtype=torch.int32, device=dev)
-    rc = ctx.lib.slb_png_encode(ctx.h, x.data_ptr(), n, H, W, channels, bpc, out.data_ptr(), stride, sizes.data_ptr(), None)
+    rc = ctx.lib.slb_png_encode(ctx.h, x.data_ptr(), n, H, W, channels, bpc, out.data_ptr(), stride, sizes.data_ptr(), _stream(ctx))
     if rc != 0:
         raise RuntimeError(ctx.lib.slb_last_error(ctx.h).decode())
     ctx.synchronize()
@@ -80,7 +87,7 @@ class ImageSaver:
                 raise ValueError("Grayscale images need to be byte or short type")
         else:
             raise ValueError("Color images need to have shape HxWx3 or HxWx4")
-        self._pending.append((input.detach(), os.fspath(path)))
+        self._pending.append((input.detach().clone(), os.fspath(path)))      # a snapshot, like input.flipud() in py_image_saver.cpp:44
         if len(self._pending) >= self.MAX_PENDING:
             self._flush()
 

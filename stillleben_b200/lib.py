@@ -116,7 +116,8 @@ class Context:
         self.h = h
         self.device = device
         self._handles = {}
-        self._keep = []
+        self._kinds = {}         # id(obj) -> "mesh" | "texture" | "lightmap" (for release / close)
+        self._keep = {}          # id(obj) -> obj: keeps the host arrays alive as long as the device handle exists
         self._pinned = []
         self.lightmap_sizes = (0, 0, 0, 0, 0)
 
@@ -126,16 +127,27 @@ class Context:
         if key in self._handles:
             return self._handles[key]
         if isinstance(obj, MeshData):
-            h = self._upload_mesh(obj)
+            h, kind = self._upload_mesh(obj), "mesh"
         elif isinstance(obj, ImageData):
-            h = self._create_texture(obj)
+            h, kind = self._create_texture(obj), "texture"
         elif isinstance(obj, LightMapData):
-            h = self._create_lightmap(obj)
+            h, kind = self._create_lightmap(obj), "lightmap"
         else:
             raise TypeError(type(obj))
         self._handles[key] = h
-        self._keep.append(obj)
+        self._kinds[key] = kind
+        self._keep[key] = obj
         return h
+
+    def release(self, obj):
+        """Free the device copy of a mesh / texture / light map (it is uploaded again if it is used again)."""
+        key = id(obj)
+        h = self._handles.pop(key, None)
+        if h is None or not self.h:
+            return
+        kind = self._kinds.pop(key)
+        self._keep.pop(key, None)
+        {"mesh": self.lib.slb_mesh_destroy, "texture": self.lib.slb_texture_destroy, "lightmap": self.lib.slb_lightmap_destroy}[kind](self.h, h)
 
     def _upload_mesh(self, m):
         subs = (abi.Submesh * len(m.submeshes))(*[abi.Submesh(o, c, mat, 0) for o, c, mat in m.submeshes])
@@ -156,6 +168,44 @@ class Context:
         rc = self.lib.slb_mesh_update_vertices(self.h, self.handle_of(mesh), v.ctypes.data, len(v))
         if rc != abi.OK:
             _raise(self.lib, self.h, rc, "slb_mesh_update_vertices")
+
+    @staticmethod
+    def _ptr(a):
+        """Device pointer of a CUDA torch tensor, host pointer of a numpy array, None for None."""
+        if a is None:
+            return None
+        return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+
+    def update_positions_and_colors(self, mesh, vertex_ids, position_update=None, color_update=None, stream=None):
+        """Mesh::updateVertexPositionsAndColors on the device copy: ids int32 (one-based), updates float32 n x 3 / n x 4;
+        numpy arrays or CUDA tensors."""
+        rc = self.lib.slb_mesh_update_positions_and_colors(self.h, self.handle_of(mesh), self._ptr(vertex_ids), len(vertex_ids),
+                                                           self._ptr(position_update), self._ptr(color_update), stream)
+        if rc != abi.OK:
+            _raise(self.lib, self.h, rc, "slb_mesh_update_positions_and_colors")
+
+    def set_positions(self, mesh, positions, stream=None):
+        rc = self.lib.slb_mesh_set_positions(self.h, self.handle_of(mesh), self._ptr(positions), len(positions), stream)
+        if rc != abi.OK:
+            _raise(self.lib, self.h, rc, "slb_mesh_set_positions")
+
+    def set_colors(self, mesh, colors, stream=None):
+        rc = self.lib.slb_mesh_set_colors(self.h, self.handle_of(mesh), self._ptr(colors), len(colors), stream)
+        if rc != abi.OK:
+            _raise(self.lib, self.h, rc, "slb_mesh_set_colors")
+
+    def recompute_normals(self, mesh, stream=None):
+        rc = self.lib.slb_mesh_recompute_normals(self.h, self.handle_of(mesh), stream)
+        if rc != abi.OK:
+            _raise(self.lib, self.h, rc, "slb_mesh_recompute_normals")
+
+    def read_vertices(self, mesh):
+        """The device copy's current 68-byte vertex stream as a structured numpy array."""
+        out = np.empty(len(mesh.vertices), abi.VERTEX_DTYPE)
+        rc = self.lib.slb_mesh_read_vertices(self.h, self.handle_of(mesh), out.ctypes.data, len(out))
+        if rc != abi.OK:
+            _raise(self.lib, self.h, rc, "slb_mesh_read_vertices")
+        return out
 
     def _create_texture(self, img):
         ci = img.to_c()
@@ -265,5 +315,7 @@ class Context:
             for p in self._pinned:
                 self.lib.slb_host_free(self.h, p)
             self._pinned = []
+            for obj in list(self._keep.values()):       # meshes, textures, light maps: device memory goes with the context
+                self.release(obj)
             self.lib.slb_ctx_destroy(self.h)
             self.h = None

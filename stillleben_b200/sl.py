@@ -291,42 +291,92 @@ class Mesh:
             raise ValueError("Mesh::setClassIndex(): out of range")    # mesh.cpp:1083-1089
         self._class_index = int(index)
 
-    # ---- geometry access / editing (py_mesh.cpp:409-500) ----
+    # ---- geometry access / editing (py_mesh.cpp:100-260,409-500; src/mesh.cpp:747-885) ----
+    # Edits are applied to the DEVICE copy (slb_mesh_update_positions_and_colors / slb_mesh_set_positions: add, recompute
+    # the area-weighted normals, no re-upload) and mirrored lazily into self.data when an accessor asks for them.
+    def _sync_from_device(self):
+        ctx = _context()
+        if getattr(self, "_device_dirty", False) and id(self.data) in ctx._handles:
+            self.data.vertices[:] = ctx.read_vertices(self.data)
+            self._device_dirty = False
+
     @property
     def points(self):
+        self._sync_from_device()
         return torch.from_numpy(self.data.vertices["position"].copy())
 
     @property
     def normals(self):
+        self._sync_from_device()
         return torch.from_numpy(self.data.vertices["normal"].copy())
 
     @property
     def colors(self):
+        self._sync_from_device()
         return torch.from_numpy(self.data.vertices["color"].copy())
 
     @property
     def faces(self):
         return torch.from_numpy(self.data.indices.astype(np.int32))
 
-    def set_new_positions(self, new_positions):
-        p = new_positions.detach().cpu().numpy().astype(np.float32)
-        if p.shape != self.data.vertices["position"].shape:
-            raise ValueError("new_positions must be N x 3")
-        self.data.vertices["position"] = p
-        self.data.bbox_min, self.data.bbox_max = p.min(axis=0), p.max(axis=0)
-        self._reupload()
+    @staticmethod
+    def _check_update(vertex_indices, update, width, what):
+        # the argument checks of py_mesh.cpp:100-212 (same messages)
+        if vertex_indices.dim() != 1:
+            raise ValueError("vertex_indices (1st argument) should be one dimensional")
+        if update.dim() != 2:
+            raise ValueError(f"{what} (2nd argument) should be two dimensional")
+        if vertex_indices.size(0) != update.size(0):
+            raise ValueError("vertices_index  and vertices_update should be of same size")
+        if update.size(1) != width:
+            raise ValueError(f"{what} should be of shape (N,{width})")
+        if vertex_indices.device.type != "cpu" or update.device.type != "cpu":
+            raise ValueError(f"vertex_indices and {what} should be CPU tensors")
+        if not vertex_indices.is_contiguous():
+            raise ValueError("vertex_indices should be contiguous tensor\n(use vertex_indices.contiguous() before passing vertex_indices as an argument)")
+        if not update.is_contiguous():
+            raise ValueError(f"{what} should be contiguous tensor\n(use {what}.contiguous() before passing {what} as an argument)")
+
+    def _edit(self, ids, dpos, dcol):
+        ctx = _context()
+        ids_np = np.ascontiguousarray(ids.numpy(), np.int32)
+        p = None if dpos is None else np.ascontiguousarray(dpos.numpy(), np.float32)
+        c = None if dcol is None else np.ascontiguousarray(dcol.numpy(), np.float32)
+        ctx.handle_of(self.data)                  # uploads the mesh if this is its first use
+        self._sync_from_device()
+        ctx.update_positions_and_colors(self.data, ids_np, p, c)
+        self._device_dirty = True
 
     def update_positions(self, vertex_indices, position_update):
-        idx = vertex_indices.detach().cpu().numpy().astype(np.int64) - 1      # vertex ids are one-based
-        self.data.vertices["position"][idx] += position_update.detach().cpu().numpy().astype(np.float32)
-        p = self.data.vertices["position"]
-        self.data.bbox_min, self.data.bbox_max = p.min(axis=0), p.max(axis=0)
-        self._reupload()
+        self._check_update(vertex_indices, position_update, 3, "position_update")
+        self._edit(vertex_indices, position_update, None)
 
-    def _reupload(self):
+    def update_colors(self, vertex_indices, color_update):
+        self._check_update(vertex_indices, color_update, 4, "color_update")
+        self._edit(vertex_indices, None, color_update)
+
+    def update_positions_and_colors(self, vertex_indices, position_update, color_update):
+        self._check_update(vertex_indices, position_update, 3, "position_update")
+        self._check_update(vertex_indices, color_update, 4, "color_update")
+        self._edit(vertex_indices, position_update, color_update)
+
+    def set_new_positions(self, new_positions):
+        if not new_positions.is_contiguous():
+            raise ValueError("new_positions should be contiguous tensor\n(use new_positions.contiguous() before passing new_positions as an argument)")
+        p = np.ascontiguousarray(new_positions.detach().cpu().numpy(), np.float32).reshape(-1, 3)
         ctx = _context()
-        if id(self.data) in ctx._handles:
-            ctx.update_vertices(self.data)
+        ctx.handle_of(self.data)
+        ctx.set_positions(self.data, p)           # ValueError on a size mismatch, as Mesh::setVertexPositions
+        self._device_dirty = True
+
+    def set_new_colors(self, new_colors):
+        if not new_colors.is_contiguous():
+            raise ValueError("new_colors should be contiguous tensor \n(use new_colors.contiguous() before passing new_colors as an argument)")
+        c = np.ascontiguousarray(new_colors.detach().cpu().numpy(), np.float32).reshape(-1, 4)
+        ctx = _context()
+        ctx.handle_of(self.data)
+        ctx.set_colors(self.data, c)
+        self._device_dirty = True
 
 
 # ---------------------------------------------------------------------------------------------

@@ -194,10 +194,63 @@ def variant(name, width=320, height=240):
             o.pose = np.eye(4, dtype=np.float32)
             o.pose[:3, 3] = (0.15 * k, -0.1 * k, 0.35 + 0.2 * k)
         return sc
+    if name == "pbr_textures":
+        # normal map + tangent frame, metallic-roughness, emissive and occlusion textures (render_shader.frag:259-298) on the
+        # reference-consolidated assets: pbr_patch (all five textures, computed tangents) and kitchen_sink (four sub-meshes,
+        # nested node transforms, an RGBA base colour -> alpha test, a sub-mesh without material, non-default samplers)
+        sc = synth.tabletop_scene(pool, 28, n_lights=2, **base)
+        for k, mesh_name in ((0, "pbr_patch_mesh"), (1, "kitchen_sink_mesh"), (2, "pbr_patch_mesh"), (3, "kitchen_sink_mesh")):
+            m = load_mesh(mesh_name)
+            o = sc.objects[k]
+            o.mesh = m
+            o.pretransform = synth.normalising_pretransform(m, 0.35 if mesh_name == "pbr_patch_mesh" else 0.9)
+            o.pose = np.array(o.pose, np.float32)
+            o.pose[2, 3] += 0.12                        # lift the open patches off the table so both faces are seen
+            o.metallic = o.roughness = -1.0             # material factors x textures (no per-object override)
+        sc.objects[2].metallic, sc.objects[2].roughness = 0.9, 0.3      # per-object overrides on top of the textures
+        return sc
+    if name == "pbr_textures_ibl":
+        sc = variant("pbr_textures", width, height)
+        sc.light_map = light_map_data()
+        sc.ssao_enabled = True
+        return sc
+    if name == "projective":
+        # non-affine transformation chains: a pretransform and a pose with a projective last row, and a general projection
+        # matrix (Scene::setCameraProjection accepts any 4x4, scene.cpp:255-258) -> the per-vertex vertex-stage path
+        sc = synth.tabletop_scene(pool, 29, **base)
+        for k in (0, 2):
+            pre = np.array(sc.objects[k].pretransform, np.float32)
+            pre[3, :3] = (0.15, -0.1, 0.2)
+            sc.objects[k].pretransform = pre
+        pose = np.array(sc.objects[1].pose, np.float32)
+        pose[3, :3] = (0.02, 0.03, -0.02)
+        sc.objects[1].pose = pose
+        P = np.array(sc.projection, np.float32)
+        P[0, 1] = 0.05; P[1, 0] = -0.03                 # skew
+        sc.projection = P
+        return sc
+    if name == "c2_shape":
+        # config C2 at its real shape: 10 objects incl. the bunny, 640x480, the ycb.py intrinsics, IBL + SSAO +
+        # auto exposure, metallic / roughness ~ U(0,1)
+        rng = np.random.RandomState(1234)
+        sc = synth.tabletop_scene(pool, 30, n_objects=10, width=640, height=480, intrinsics=(1066.778, 1067.487, 312.9869, 241.3109),
+                                  light_map=light_map_data(), ssao=True, manual_exposure=-1.0)
+        bunny = load_mesh("bunny_mesh")
+        for k, o in enumerate(sc.objects):
+            if k % 3 == 0:
+                o.mesh = bunny
+                o.pretransform = synth.normalising_pretransform(bunny, float(rng.uniform(0.08, 0.30)))
+            o.metallic, o.roughness = float(rng.uniform(0, 1)), float(rng.uniform(0, 1))
+        return sc
+    if name == "c5_shape":
+        # config C5's frame: 1920x1080, 64 objects, IBL + SSAO + 3 shadow lights
+        return synth.tabletop_scene(pool, 31, n_objects=64, width=1920, height=1080, intrinsics=None, n_lights=3, ssao=True,
+                                    light_map=light_map_data())
     if name == "odd_viewport":
         return synth.tabletop_scene(pool, 25, n_objects=5, width=203, height=117, intrinsics=None)
     raise KeyError(name)
 
 
 VARIANTS = ["tabletop", "three_lights", "ssao", "auto_exposure", "no_plane_no_light", "empty", "ibl", "alpha_test", "sticker",
-            "background_image", "plane_texture", "near_clip", "predicate", "id_limits", "odd_viewport", "multi_submesh", "low_poly_closeup"]
+            "background_image", "plane_texture", "near_clip", "predicate", "id_limits", "odd_viewport", "multi_submesh", "low_poly_closeup",
+            "pbr_textures", "pbr_textures_ibl", "projective", "c2_shape", "c5_shape"]

@@ -81,3 +81,36 @@ def test_cpulist_parser_and_numa_binding_are_harmless_without_a_gpu():
     assert dist.bind_to_gpu_numa_node(0) in (None, 0, 1, 2, 3, 4, 5, 6, 7)     # no GPU here: None, and nothing changes
     if dist.bind_to_gpu_numa_node(0) is None:
         assert os.sched_getaffinity(0) == before
+
+
+def test_oracle_recompute_normals_matches_float64_restating():
+    """orc_mesh_recompute_normals (the twin of Mesh::recomputeNormals, src/mesh.cpp:763-816) against a float64 numpy
+    restatement: area-weighted face normals summed per vertex; the position update adds to one-based ids."""
+    import ctypes as C
+    import oracle_util as ou
+    from stillleben_b200 import abi, synth
+    mesh = synth.shape_mesh("blob", 11, nu=16, nv=8, textured=False)
+    assets = ou.OracleAssets()
+    h = assets.handle_of(mesh)
+    L = ou.lib()
+    L.orc_mesh_update_positions_and_colors.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.orc_mesh_read_vertices.argtypes = [C.c_void_p, C.c_void_p]
+    rng = np.random.RandomState(0)
+    n = len(mesh.vertices)
+    ids = np.arange(1, n + 1, dtype=np.int32)[::3].copy()
+    dpos = (rng.normal(size=(len(ids), 3)) * 0.03).astype(np.float32)
+    assert L.orc_mesh_update_positions_and_colors(h, ids.ctypes.data, len(ids), dpos.ctypes.data, None) == 0
+    out = np.empty(n, abi.VERTEX_DTYPE)
+    L.orc_mesh_read_vertices(h, out.ctypes.data)
+    pos = mesh.vertices["position"].astype(np.float64).copy()
+    pos[ids - 1] += dpos
+    np.testing.assert_allclose(out["position"], pos, rtol=0, atol=1e-7)
+    tri = mesh.indices.reshape(-1, 3)
+    fn = np.cross(pos[tri[:, 0]] - pos[tri[:, 1]], pos[tri[:, 0]] - pos[tri[:, 2]])        # normal * area = the cross product itself
+    acc = np.zeros_like(pos)
+    for k in range(3):
+        np.add.at(acc, tri[:, k], fn)
+    ok = np.linalg.norm(acc, axis=1) > 1e-12
+    expect = acc[ok] / np.linalg.norm(acc[ok], axis=1, keepdims=True)
+    np.testing.assert_allclose(out["normal"][ok], expect, atol=2e-5)
+    assert L.orc_mesh_update_positions_and_colors(h, np.array([0], np.int32).ctypes.data, 1, dpos.ctypes.data, None) == -1
