@@ -30,15 +30,17 @@ def compare(gpu, ref):
     return stats
 
 
-def assert_parity(gpu, ref, rgb_outlier_frac=0.0, hdr_outlier_frac=0.0):
+def assert_parity(gpu, ref, rgb_outlier_frac=0.0, hdr_outlier_frac=0.0, rgb_outliers=None):
+    """rgb_outliers: absolute number of RGBA8 pixels allowed beyond 1 LSB (overrides rgb_outlier_frac); hdr_outlier_frac:
+    share of HDR pixels allowed beyond RTOL (at least 4 pixels when non-zero)."""
     st = compare(gpu, ref)
     for name, s in st.items():
         if name in EXACT:
             assert s["mismatch"] == 0, (name, s)
         elif name == "rgb":
-            assert s["over1"] <= rgb_outlier_frac * s["n"], (name, s)
+            assert s["over1"] <= (rgb_outliers if rgb_outliers is not None else rgb_outlier_frac * s["n"]), (name, s)
         elif name == "hdr":
-            assert s["bad"] <= hdr_outlier_frac * s["n"], (name, s)
+            assert s["bad"] <= (max(4, hdr_outlier_frac * s["n"]) if hdr_outlier_frac else 0), (name, s)
         else:
             assert s["bad"] == 0, (name, s)
     return st

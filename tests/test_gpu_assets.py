@@ -56,7 +56,7 @@ def test_vertex_update_path(gpu_ctx):
     assets = ou.OracleAssets()
     ref = ou.render(scene, assets, want_hdr=False)
     import parity
-    parity.assert_parity(after, ref, rgb_outlier_frac=1e-3)
+    parity.assert_parity(after, ref, rgb_outliers=4)
     assert (after["instance_index"] != b0["instance_index"]).any()
 
 
@@ -130,7 +130,7 @@ def test_vertex_edit_path_recomputes_normals_like_the_reference(gpu_ctx):
     assert np.array_equal(got_v["color"][ids - 1], mesh.vertices["color"][ids - 1] + dcol)
     after = gpu_ctx.render([scene], target_mask=abi.TARGETS_ALL).frame_dict(0)
     ref = ou.render(scene, assets, want_hdr=False)
-    parity.assert_parity(after, ref, rgb_outlier_frac=1e-3)
+    parity.assert_parity(after, ref, rgb_outliers=4)
     assert (after["normals"] != before["normals"]).any()
     # setVertexPositions: everything replaced, normals again; device-resident update arrays are accepted as well
     import torch

@@ -1,7 +1,9 @@
 """Parity proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
 inputs and against the committed golden fixtures. ID maps bit-exact; float targets within 1e-3 relative
-(tolerances in tests/parity.py); RGBA8 within 1 LSB. The colour targets may differ in a handful of
-pixels where a 4x4 PCF shadow tap sits exactly on its compare threshold (budget: 0.1 % of the pixels)."""
+(tolerances in tests/parity.py); RGBA8 within 1 LSB. The colour targets may differ in a handful of pixels where
+a 4x4 PCF shadow tap sits exactly on its compare threshold or a texture LOD on a level boundary. Budget = the
+MEASURED bound with a small margin (profiles/r02_parity_stats.json, 22 variants: at most 2 RGBA8 pixels per frame
+beyond 1 LSB, at most 8.5e-5 of the HDR pixels beyond 1e-3): 4 pixels for RGBA8, 2e-4 of the pixels for HDR."""
 import numpy as np
 import pytest
 
@@ -12,7 +14,7 @@ from stillleben_b200 import abi, lib
 
 pytestmark = pytest.mark.gpu
 
-OUTLIERS = dict(rgb_outlier_frac=1e-3, hdr_outlier_frac=1e-3)
+OUTLIERS = dict(rgb_outliers=4, hdr_outlier_frac=2e-4)
 
 
 def render_gpu(ctx, scene, mask=abi.TARGETS_ALL, peel=None):
