@@ -317,7 +317,13 @@ enum {
     /* 1 (default): the first few huge sub-triangles of a camera view (the background plane, close-up faces) are
      * resolved per pixel inside the shade kernel instead of being tile-binned; 0: everything large is tile-binned.
      * Results are bit-identical. */
-    SLB_OPT_HUGE_IN_SHADE = 7
+    SLB_OPT_HUGE_IN_SHADE = 7,
+    /* 1 (default): those huge sub-triangles are shaded from per-frame records holding the vertex stage's outputs
+     * (k_huge_prepare) instead of a per-pixel re-set-up. ID maps identical; float targets equal within rounding. */
+    SLB_OPT_HUGE_PREPARE = 8,
+    /* 1 (default): every shadow map carries a block-occupancy mask (one bit per 8x8 texels); PCF footprints over
+     * untouched blocks skip their 25 taps. Results are bit-identical. */
+    SLB_OPT_SHADOW_MASK = 9
 };
 int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value);
 

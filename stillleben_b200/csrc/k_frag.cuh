@@ -411,7 +411,8 @@ __device__ __forceinline__ uint32_t shadow_threshold(float ref) {
 // 4x4 PCF taps at offsets {-1.5,-0.5,0.5,1.5} texels, each a 2x2 bilinear filter of the comparison: the 16
 // taps share their fractional position, so the sum separates into weights (1-a, 1, 1, 1, a) x (1-b, 1, 1, 1, b)
 // over the 5x5 texel neighbourhood — 25 compares instead of 64 (clamp-to-edge per texel index).
-__device__ __forceinline__ float shadow_pcf16(const uint32_t* __restrict__ map, float u, float v, uint32_t thr, uint32_t tagbits) {
+__device__ __forceinline__ float shadow_pcf16(const uint32_t* __restrict__ map, const uint32_t* __restrict__ mask, float u, float v, uint32_t thr,
+                                              uint32_t tagbits) {
     const int N = SLB_SHADOW_RES;
     float x = u * N - 2.0f, y = v * N - 2.0f;            // (u - 1.5/N) * N - 0.5
     float fx = floorf(x), fy = floorf(y);
@@ -421,14 +422,32 @@ __device__ __forceinline__ float shadow_pcf16(const uint32_t* __restrict__ map, 
     const float wy[5] = {1.0f - b, 1.0f, 1.0f, 1.0f, b};
     const uint32_t thr_t = tagbits | thr;   // texels are generation tag << 24 | d24 (DFrame::shadow_tagbits)
     float sum = 0.0f;
+    bool touched = true;
+    if (mask) {   // the (at most 2 x 2) 8x8 texel blocks under the clamped 5x5 footprint: all clear -> every texel is untouched = lit
+        const int bx0 = min(max(i0, 0), N - 1) >> 3, bx1 = min(max(i0 + 4, 0), N - 1) >> 3;
+        const int by0 = min(max(j0, 0), N - 1) >> 3, by1 = min(max(j0 + 4, 0), N - 1) >> 3;
+        const uint32_t m = ((__ldg(mask + by0 * 8 + (bx0 >> 5)) >> (bx0 & 31)) | (__ldg(mask + by0 * 8 + (bx1 >> 5)) >> (bx1 & 31)) |
+                            (__ldg(mask + by1 * 8 + (bx0 >> 5)) >> (bx0 & 31)) | (__ldg(mask + by1 * 8 + (bx1 >> 5)) >> (bx1 & 31))) & 1u;
+        touched = m != 0u;
+    }
+    if (touched) {
 #pragma unroll
-    for (int jj = 0; jj < 5; ++jj) {
-        const uint32_t* row = map + (size_t)min(max(j0 + jj, 0), N - 1) * N;
-        float r = 0.0f;
+        for (int jj = 0; jj < 5; ++jj) {
+            const uint32_t* row = map + (size_t)min(max(j0 + jj, 0), N - 1) * N;
+            float r = 0.0f;
 #pragma unroll
-        for (int ii = 0; ii < 5; ++ii)
-            r += (__ldg(row + min(max(i0 + ii, 0), N - 1)) >= thr_t) ? wx[ii] : 0.0f;   // stale / untouched texels carry a larger tag: lit
-        sum += r * wy[jj];
+            for (int ii = 0; ii < 5; ++ii)
+                r += (__ldg(row + min(max(i0 + ii, 0), N - 1)) >= thr_t) ? wx[ii] : 0.0f;   // stale / untouched texels carry a larger tag: lit
+            sum += r * wy[jj];
+        }
+    } else {   // the same sums with every comparison true (same operation order: bit-identical to the taps)
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            float r = 0.0f;
+#pragma unroll
+            for (int ii = 0; ii < 5; ++ii) r += wx[ii];
+            sum += r * wy[jj];
+        }
     }
     return thr > 0xFFFFFFu ? 0.0f : sum * (1.0f / 16.0f);   // NaN reference: no tap passes
 }
@@ -490,7 +509,7 @@ __device__ __forceinline__ void fragment_stage(const DFrame& f, const DDraw& d, 
         if (!f.lightActive[i]) continue;
         float4 pc = mul_m4_p(f.shadowMat[i], in.wc.x, in.wc.y, in.wc.z, 1.0f);
         float pcx = 0.5f * (pc.x / pc.w) + 0.5f, pcy = 0.5f * (pc.y / pc.w) + 0.5f, pcz = 0.5f * (pc.z / pc.w) + 0.5f;
-        const float inverseShadow = shadow_pcf16(f.shadowMap[i], pcx, pcy, shadow_threshold(pcz - 0.00003f), f.shadow_tagbits);
+        const float inverseShadow = shadow_pcf16(f.shadowMap[i], f.shadowMask[i], pcx, pcy, shadow_threshold(pcz - 0.00003f), f.shadow_tagbits);
 
         f3 L = normalize3(mk3(-f.lightDir[i][0], -f.lightDir[i][1], -f.lightDir[i][2]));
         f3 H = normalize3(cameraDirection + L);

@@ -250,13 +250,26 @@ __device__ __forceinline__ void red_min_u64(unsigned long long* p, unsigned long
 // G = 1: the thread walks the triangle's pixel box alone.  G = 32: the warp walks it together, lane l taking the
 // box pixels l, l+32, ... in row-major order (mid-size triangles, e.g. a 16k-triangle mesh seen from a 2048^2
 // shadow view), so the cost per triangle is box/32 iterations instead of one iteration per touched tile.
+// shadow views: mark the 8x8 texel blocks a triangle's pixel box touches in the map's block-occupancy mask (a superset of
+// the blocks it really writes; see SLB_SHADOW_MASK_WORDS). Most bits are already set by a neighbour: test before the atomic.
+__device__ __forceinline__ void mark_shadow_blocks(uint32_t* __restrict__ mask, int px0, int py0, int px1, int py1, int first_row, int row_step) {
+    const int bx0 = px0 >> 3, bx1 = px1 >> 3;
+    for (int by = (py0 >> 3) + first_row; by <= (py1 >> 3); by += row_step)
+        for (int w = bx0 >> 5; w <= bx1 >> 5; ++w) {
+            const int lo = max(bx0 - w * 32, 0), hi = min(bx1 - w * 32, 31);
+            const uint32_t bits = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+            uint32_t* p = mask + by * 8 + w;
+            if ((__ldcg(p) & bits) != bits) atomicOr(p, bits);
+        }
+}
 template <bool SHADOW, int G>
 __device__ __forceinline__ void raster_direct(int ax, int ay, int bx, int by, int cx, int cy, float az, float bz, float cz, uint32_t seq,
-                                              void* __restrict__ out, int W, int H, int lane, uint32_t tagbits) {
+                                              void* __restrict__ out, int W, int H, int lane, uint32_t tagbits, uint32_t* __restrict__ mask) {
     const int xmin = min(ax, min(bx, cx)), xmax = max(ax, max(bx, cx));
     const int ymin = min(ay, min(by, cy)), ymax = max(ay, max(by, cy));
     const int px0 = max(0, (xmin - 128 + 255) >> 8), px1 = min(W - 1, (xmax - 128) >> 8);
     const int py0 = max(0, (ymin - 128 + 255) >> 8), py1 = min(H - 1, (ymax - 128) >> 8);
+    if (SHADOW && mask) mark_shadow_blocks(mask, px0, py0, px1, py1, G == 1 ? 0 : lane, G);
     const int rbx = bx - ax, rby = by - ay, rcx = cx - ax, rcy = cy - ay;
     const int twoA = rbx * rcy - rby * rcx;
     const int sg = twoA > 0 ? 1 : -1;
@@ -395,8 +408,8 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 5) k_setup(const DView* __res
                   __int_as_float(s_dq[7][q]), __int_as_float(s_dq[8][q]), (uint32_t)s_dq[9][q]
     if ((int)threadIdx.x < s_ndirect) {
         const int q = threadIdx.x;
-        if (v.shadow) raster_direct<true, 1>(SLB_DQ(q), v.out, v.W, v.H, 0, v.tagbits);
-        else raster_direct<false, 1>(SLB_DQ(q), v.out, v.W, v.H, 0, 0u);
+        if (v.shadow) raster_direct<true, 1>(SLB_DQ(q), v.out, v.W, v.H, 0, v.tagbits, v.mask);
+        else raster_direct<false, 1>(SLB_DQ(q), v.out, v.W, v.H, 0, 0u, nullptr);
     }
     // ... then the mid-size ones, one per warp, handed out dynamically
     const int nmid = s_nmid;
@@ -406,8 +419,8 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 5) k_setup(const DView* __res
         m = __shfl_sync(0xffffffffu, m, 0);
         if (m >= nmid) break;
         const int q = SLB_SETUP_CHUNK - 1 - m;
-        if (v.shadow) raster_direct<true, 32>(SLB_DQ(q), v.out, v.W, v.H, lane, v.tagbits);
-        else raster_direct<false, 32>(SLB_DQ(q), v.out, v.W, v.H, lane, 0u);
+        if (v.shadow) raster_direct<true, 32>(SLB_DQ(q), v.out, v.W, v.H, lane, v.tagbits, v.mask);
+        else raster_direct<false, 32>(SLB_DQ(q), v.out, v.W, v.H, lane, 0u, nullptr);
     }
 #undef SLB_DQ
 }
@@ -770,6 +783,12 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DView* _
         if (v.shadow) {   // depth-only view: the d24 plane the PCF lookup reads (cleared to 0xFFFFFF where nothing was drawn)
             uint32_t* out = reinterpret_cast<uint32_t*>(v.out);
             const unsigned long long k0 = keys[ly * SLB_TILE + lx], k1 = keys[(ly + 4) * SLB_TILE + lx];
+            static_assert(SLB_TILE == 8, "one raster tile == one block of the shadow-map occupancy mask");
+            if (v.mask) {   // one atomic per tile, by the first active lane
+                const unsigned act = __activemask();
+                const unsigned any = __ballot_sync(act, k0 != SLB_KEY_EMPTY || k1 != SLB_KEY_EMPTY);
+                if (any && lane == __ffs(act) - 1) atomicOr(v.mask + ty * 8 + (tx >> 5), 1u << (tx & 31));
+            }
             if (y_lo + ly < H) out[(size_t)(y_lo + ly) * W + px] = v.tagbits | (k0 == SLB_KEY_EMPTY ? 0xFFFFFFu : (uint32_t)(k0 >> 40));
             if (y_lo + ly + 4 < H) out[(size_t)(y_lo + ly + 4) * W + px] = v.tagbits | (k1 == SLB_KEY_EMPTY ? 0xFFFFFFu : (uint32_t)(k1 >> 40));
         } else {
@@ -792,6 +811,46 @@ __device__ __forceinline__ uint32_t find_draw_by_prim(const DDraw* __restrict__ 
     return lo;
 }
 
+// Once per frame and huge sub-triangle (instead of once per pixel of it): the per-pixel re-set-up of k_shade's generic path —
+// index / vertex fetch, clip-space transform or ClipRec read, the vertex stage of the three original vertices
+// (render_shader.vert:57-95) — with the results parked in a HugeShade record for the pixels to interpolate.
+__global__ void __launch_bounds__(32) k_huge_prepare(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws) {
+    const DFrame& f = frames[blockIdx.x];
+    if (!f.huge || !f.huge_shade) return;
+    const int nh = min((int)__ldg(f.huge_n), SLB_HUGE_PER_VIEW);
+    if ((int)threadIdx.x >= nh) return;
+    const HugeRec h = f.huge[threadIdx.x];
+    HugeShade hs;
+    hs.fast = 0u;
+    const uint32_t seq = h.seq;
+    const uint32_t di = f.seq_shift ? f.draw_begin + (seq >> f.seq_shift) : find_draw_by_prim(draws, f.draw_begin, f.draw_end, seq);
+    const DDraw& d = draws[di];
+    const uint32_t tri = seq - d.prim_base;
+    const uint32_t* ip = d.idx + 3 * (size_t)tri;
+    const uint32_t vi[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
+    PolyV va, vb, vc; float4 pm[3];
+    const int how = fetch_subtri(f, d, seq, (int)h.kbyte, vi, pm, va, vb, vc);
+    if (how && (d.flags & DRAW_AFFINE) && !d.sticker) {
+        hs.fast = 1u;
+        hs.invw[0] = va.invw; hs.invw[1] = vb.invw; hs.invw[2] = vc.invw;
+        for (int j = 0; j < 3; ++j) { hs.basis[0][j] = va.b[j]; hs.basis[1][j] = vb.b[j]; hs.basis[2][j] = vc.b[j]; }
+        hs.unit_basis = how == 1 ? 1u : 0u;
+        hs.draw = di;
+        hs.front = h.s < 0 ? 1u : 0u;   // FrontFace = CW (render_pass.cpp:330): twoA < 0
+        for (int j = 0; j < 3; ++j) {
+            VSOut o; uint32_t id;
+            vertex_stage(f, d, vi[j], o, id);
+            hs.vid[j] = id; hs.vi[j] = vi[j];
+            hs.objc[j][0] = o.objc.x; hs.objc[j][1] = o.objc.y; hs.objc[j][2] = o.objc.z;
+            hs.wc[j][0] = o.wc.x; hs.wc[j][1] = o.wc.y; hs.wc[j][2] = o.wc.z;
+            hs.cc[j][0] = o.cc.x; hs.cc[j][1] = o.cc.y; hs.cc[j][2] = o.cc.z;
+            hs.nW[j][0] = o.nW.x; hs.nW[j][1] = o.nW.y; hs.nW[j][2] = o.nW.z;
+            hs.uv[j][0] = o.u; hs.uv[j][1] = o.v;
+        }
+    }
+    f.huge_shade[threadIdx.x] = hs;
+}
+
 template <int THREADS, int MINB, bool LEAN>
 __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restrict__ frames, const DDraw* __restrict__ draws) {
     const DFrame& f = frames[blockIdx.z];
@@ -808,18 +867,28 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
     // huge sub-triangles of this view (resolved per pixel below): staged once per block, only those whose pixel box
     // meets the block's 32x8 pixels
     __shared__ HugeRec s_huge[SLB_HUGE_PER_VIEW];
+    __shared__ __align__(16) HugeShade s_hs[SLB_HUGE_PER_VIEW];
+    __shared__ int s_src[SLB_HUGE_PER_VIEW];
     __shared__ int s_nh;
     if (threadIdx.x == 0) s_nh = 0;
     __syncthreads();
     if (f.huge && threadIdx.x < SLB_HUGE_PER_VIEW && (int)threadIdx.x < min((int)__ldg(f.huge_n), SLB_HUGE_PER_VIEW)) {
         const HugeRec h = f.huge[threadIdx.x];
         const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * 8;
-        if (h.px1 >= bx0 && h.px0 <= bx0 + 31 && h.py1 >= by0 && h.py0 <= by0 + 7) s_huge[atomicAdd(&s_nh, 1)] = h;
+        if (h.px1 >= bx0 && h.px0 <= bx0 + 31 && h.py1 >= by0 && h.py0 <= by0 + 7) { const int at = atomicAdd(&s_nh, 1); s_huge[at] = h; s_src[at] = threadIdx.x; }
     }
     __syncthreads();
+    if (f.huge_shade) {   // the staged records' shading halves: 16 x 128-bit words each, copied by the whole block
+        const int n4 = s_nh * (int)(sizeof(HugeShade) / 16);
+        for (int i = threadIdx.x; i < n4; i += THREADS)
+            reinterpret_cast<float4*>(s_hs)[i] = __ldg(reinterpret_cast<const float4*>(f.huge_shade + s_src[i >> 4]) + (i & 15));
+        __syncthreads();
+    }
     if (px >= W || py >= H) return;
     const size_t p = (size_t)py * W + px;
     unsigned long long key = f.keys[p];
+    int best = -1;                       // the staged huge record that owns this pixel, if one does
+    long long bw0 = 0, bw1 = 0, bw2 = 0;   // its edge-function values here (reused for the barycentrics)
     {   // coverage (C6) and depth (C7) of the staged huge sub-triangles at this pixel, merged by minimum (every covering
         // record is evaluated, exactly as the tiled path would: snapped fan triangles may overlap in degenerate cases)
         const int nh = s_nh;
@@ -834,7 +903,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
             subtri_weights(st, px, py, w0, w1, w2);
             if (!subtri_covers(st, w0, w1, w2)) continue;
             const unsigned long long cand = ((unsigned long long)subtri_depth24(st, w1, w2) << 40) | ((unsigned long long)h.seq << 8) | h.kbyte;
-            key = min(key, cand);
+            if (cand < key) { key = cand; best = i; bw0 = w0; bw1 = w1; bw2 = w2; }
         }
         if (nh && !f.fused_tonemap) f.keys[p] = key;   // the post passes (sky box / background image) test coverage on the keys
     }
@@ -853,20 +922,67 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
     float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
     bool shaded = false;
     if (key != SLB_KEY_EMPTY) {
-        const uint32_t seq = (uint32_t)(key >> 8);
-        const int k = (int)(key & 0xffu);
-        // the draw is encoded in the sequence number when the frame's draws fit (host: build_batch), else searched
-        const DDraw& d = draws[f.seq_shift ? f.draw_begin + (seq >> f.seq_shift) : find_draw_by_prim(draws, f.draw_begin, f.draw_end, seq)];
-        const uint32_t tri = seq - d.prim_base;
-        const uint32_t* ip = d.idx + 3 * (size_t)tri;
-        const uint32_t vi[3] = {__ldg(ip), __ldg(ip + 1), __ldg(ip + 2)};
-        PolyV va, vb, vc;
-        SubTri st;
-        float4 pm[3];
-        const int how = fetch_subtri(f, d, seq, k, vi, pm, va, vb, vc);
-        if (how && make_subtri(va.X, va.Y, vb.X, vb.Y, vc.X, vc.Y, va.z, vb.z, vc.z, st)) {
-            FragIn in; float bary[3]; uint32_t vid[3];
-            shade_inputs<LEAN>(f, d, st, va, vb, vc, vi, pm, how == 1, px, py, LEAN ? d.tex[0] != nullptr : draw_has_textures(d), in, bary, vid);
+        FragIn in; float bary[3]; uint32_t vid[3], vi[3];
+        const DDraw* dp = nullptr;
+        if (best >= 0 && f.huge_shade && s_hs[best].fast) {
+            // huge sub-triangle: interpolate the vertex-stage outputs k_huge_prepare parked for it; the barycentrics come from
+            // the edge-function values the coverage test above already has (same arithmetic as bary_from_weights)
+            const HugeShade& hs = s_hs[best];
+            const HugeRec& h = s_huge[best];
+            dp = &draws[hs.draw];
+            auto bary_at = [&](long long w0, long long w1, long long w2, float out[3]) {
+                const float b0 = __ll2float_rn(w0) * h.inv2A, b1 = __ll2float_rn(w1) * h.inv2A, b2 = __ll2float_rn(w2) * h.inv2A;
+                const float g0 = b0 * hs.invw[0], g1 = b1 * hs.invw[1], g2 = b2 * hs.invw[2];
+                const float sgm = g0 + g1 + g2;
+                const float q0 = g0 / sgm, q1 = g1 / sgm, q2 = g2 / sgm;
+                if (hs.unit_basis) { out[0] = q0; out[1] = q1; out[2] = q2; return; }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) out[j] = q0 * hs.basis[0][j] + q1 * hs.basis[1][j] + q2 * hs.basis[2][j];
+            };
+            bary_at(bw0, bw1, bw2, bary);
+            auto lerp = [&](const float a[3][3], int c) { return a[0][c] * bary[0] + a[1][c] * bary[1] + a[2][c] * bary[2]; };
+            in.objc = make_float4(lerp(hs.objc, 0), lerp(hs.objc, 1), lerp(hs.objc, 2), 0.f);
+            in.wc = mk3(lerp(hs.wc, 0), lerp(hs.wc, 1), lerp(hs.wc, 2));
+            in.cc = mk3(lerp(hs.cc, 0), lerp(hs.cc, 1), lerp(hs.cc, 2));
+            in.objc.w = in.cc.z;
+            in.nW = mk3(lerp(hs.nW, 0), lerp(hs.nW, 1), lerp(hs.nW, 2));
+            in.u = hs.uv[0][0] * bary[0] + hs.uv[1][0] * bary[1] + hs.uv[2][0] * bary[2];
+            in.v = hs.uv[0][1] * bary[0] + hs.uv[1][1] * bary[1] + hs.uv[2][1] * bary[2];
+            in.su = in.sv = -1.0f;
+            in.front = hs.front != 0u;
+            in.u_dx = in.v_dx = in.u_dy = in.v_dy = 0.0f;
+            if (LEAN ? dp->tex[0] != nullptr : draw_has_textures(*dp)) {   // dFdx / dFdy of uv: the quad partner's values on the same primitive
+                const long long sx = (px & 1) ? -256 : 256, sy = (py & 1) ? -256 : 256;
+                float bx[3], by[3];
+                bary_at(bw0 - sx * (h.cy - h.by), bw1 - sx * (h.ay - h.cy), bw2 - sx * (h.by - h.ay), bx);
+                bary_at(bw0 + sy * (h.cx - h.bx), bw1 + sy * (h.ax - h.cx), bw2 + sy * (h.bx - h.ax), by);
+                const float sgx = (px & 1) ? -1.0f : 1.0f, sgy = (py & 1) ? -1.0f : 1.0f;
+                in.u_dx = sgx * (hs.uv[0][0] * bx[0] + hs.uv[1][0] * bx[1] + hs.uv[2][0] * bx[2] - in.u);
+                in.v_dx = sgx * (hs.uv[0][1] * bx[0] + hs.uv[1][1] * bx[1] + hs.uv[2][1] * bx[2] - in.v);
+                in.u_dy = sgy * (hs.uv[0][0] * by[0] + hs.uv[1][0] * by[1] + hs.uv[2][0] * by[2] - in.u);
+                in.v_dy = sgy * (hs.uv[0][1] * by[0] + hs.uv[1][1] * by[1] + hs.uv[2][1] * by[2] - in.v);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { vid[j] = hs.vid[j]; vi[j] = hs.vi[j]; }
+        } else {
+            const uint32_t seq = (uint32_t)(key >> 8);
+            const int k = (int)(key & 0xffu);
+            // the draw is encoded in the sequence number when the frame's draws fit (host: build_batch), else searched
+            const DDraw& d = draws[f.seq_shift ? f.draw_begin + (seq >> f.seq_shift) : find_draw_by_prim(draws, f.draw_begin, f.draw_end, seq)];
+            const uint32_t tri = seq - d.prim_base;
+            const uint32_t* ip = d.idx + 3 * (size_t)tri;
+            vi[0] = __ldg(ip); vi[1] = __ldg(ip + 1); vi[2] = __ldg(ip + 2);
+            PolyV va, vb, vc;
+            SubTri st;
+            float4 pm[3];
+            const int how = fetch_subtri(f, d, seq, k, vi, pm, va, vb, vc);
+            if (how && make_subtri(va.X, va.Y, vb.X, vb.Y, vc.X, vc.Y, va.z, vb.z, vc.z, st)) {
+                shade_inputs<LEAN>(f, d, st, va, vb, vc, vi, pm, how == 1, px, py, LEAN ? d.tex[0] != nullptr : draw_has_textures(d), in, bary, vid);
+                dp = &d;
+            }
+        }
+        if (dp) {
+            const DDraw& d = *dp;
             // geometry targets first: their registers are free before the lighting code runs
             store_geometry(in.objc, (unsigned short)d.class_index, (unsigned short)d.instance_index, make_uint4(vid[0], vid[1], vid[2], 0u),
                            make_float4(bary[0], bary[1], bary[2], 1.0f), make_float4(in.cc.x, in.cc.y, in.cc.z, 1.0f));
@@ -925,6 +1041,7 @@ void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W,
     // (128,5) 96 regs 39.4, (256,3) 80 regs 36.3, (256,4) 64 regs 33.4 — the kernel is latency bound, occupancy wins
     // even with ~150 B of spills.
     // `lean`: no material textures beyond base colour, no stickers, no light map, affine chains only (see fragment_stage)
+    k_huge_prepare<<<n_frames, 32, 0, s>>>(frames, draws);   // no-op for frames without huge records
     if (lean) k_shade<256, 4, true><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
     else k_shade<256, 4, false><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
 }

@@ -87,6 +87,25 @@ struct __align__(16) HugeRec {
 };
 static_assert(sizeof(HugeRec) == 80, "HugeRec must be 80 bytes");
 
+// What the shade kernel needs to shade a pixel of a huge sub-triangle WITHOUT re-doing the triangle's set-up: the vertex
+// stage's outputs of the three ORIGINAL vertices (computed once per frame by k_huge_prepare instead of once per pixel — the
+// background plane alone covers most of a table-top frame) plus the perspective terms of the sub-triangle's vertices.
+struct __align__(16) HugeShade {
+    float invw[3];                 // 1/w of the sub-triangle's vertices a, b, c
+    uint32_t fast;                 // 1: usable (affine chain, no sticker); 0: the pixel takes the generic path
+    float basis[3][3];             // barycentric basis of a, b, c w.r.t. the original triangle (identity if unclipped)
+    uint32_t unit_basis, draw, front;
+    uint32_t vid[3], vi[3];        // one-based vertex ids (the render target) and the three indices into the vertex buffers
+    float objc[3][3], wc[3][3], cc[3][3], nW[3][3];   // per original vertex: object / world / camera position, world normal (normalised)
+    float uv[3][2];
+};
+static_assert(sizeof(HugeShade) == 256, "HugeShade must be 256 bytes");
+
+// Coarse occupancy of a shadow map: one bit per 8x8 texel block, set by every rasteriser that MAY write a texel of the
+// block in this sub-batch. A PCF footprint whose blocks are all clear consists of untouched (= lit) texels only, so the 25
+// taps need no loads (bit-identical result). word = by * 8 + (bx >> 5), bit = bx & 31.
+#define SLB_SHADOW_MASK_WORDS ((SLB_SHADOW_RES / 8) * (SLB_SHADOW_RES / 8) / 32)
+
 struct DView {
     int32_t W, H, tiles_x, tiles_y;
     uint32_t tile_base;            // first tile of this view in the batch-wide tile arrays
@@ -94,6 +113,7 @@ struct DView {
     uint32_t frame;                // DFrame index (camera views)
     uint32_t tagbits;              // shadow views: generation tag << 24, stored above every d24 (see DFrame::shadow_tagbits)
     void* out;                     // uint64 keys[H*W] (camera) or uint32 tag | d24 [H*W] (shadow)
+    uint32_t* mask;                // shadow views: SLB_SHADOW_MASK_WORDS words of block-occupancy bits (null: feature off)
     HugeRec* huge;                 // camera views: SLB_HUGE_PER_VIEW slots (null: feature off / shadow view)
     uint32_t* huge_n;              // how many were claimed (may exceed the capacity: the excess went to the tiled path)
 };
@@ -124,6 +144,7 @@ struct DFrame {
     uint32_t shadow_tagbits;
     float shadowMat[SLB_NUM_LIGHTS][16];
     const uint32_t* shadowMap[SLB_NUM_LIGHTS];
+    const uint32_t* shadowMask[SLB_NUM_LIGHTS];   // block-occupancy bits of each map (null: always take the taps)
     const DLightMap* lm;
     const float* peel;             // previous layer's coord target (HxWx4) or null
     const DTexture* bg_image;
@@ -131,6 +152,7 @@ struct DFrame {
     uint32_t* clip_count;
     const HugeRec* huge;           // this frame's huge sub-triangles, resolved per pixel by the shade kernel
     const uint32_t* huge_n;
+    HugeShade* huge_shade;         // SLB_HUGE_PER_VIEW records, filled by k_huge_prepare between set-up and shading
     uint64_t* keys;                // H*W visibility keys
     float4* hdr;                   // H*W pre-tone-map colour (post-pass path only)
     float4* scratch_normal;        // used by SSAO when the normal / cam-coord targets are not requested

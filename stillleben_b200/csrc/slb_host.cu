@@ -83,7 +83,7 @@ struct Pending {   // a sub-batch whose first phase (clear, set-up, scan) is que
 };
 struct Scratch {
     DevBuf frames_d, draws_d, chunk_base_d, views_d, bdraws_d, scan_sums, active_tiles, scan_totals, survivors;
-    DevBuf clip_recs, clip_counts, huge_recs, huge_counts;
+    DevBuf clip_recs, clip_counts, huge_recs, huge_counts, huge_shade, shadow_mask;
     DevBuf tile_count, tile_off, pairs, keys, hdr, scratch_normal, scratch_cam, zplane, ao, avg, mip_a, mip_b, shadow_maps;
     void* staging = nullptr; size_t staging_cap = 0;   // pinned
     uint32_t* total_pinned = nullptr;                   // mapped pinned: the scan writes its totals here
@@ -94,7 +94,7 @@ struct Scratch {
     Pending pending;
     void release() {
         DevBuf* bufs[] = {&frames_d, &draws_d, &chunk_base_d, &views_d, &bdraws_d, &scan_sums, &active_tiles, &scan_totals, &survivors, &clip_recs,
-                          &clip_counts, &huge_recs, &huge_counts, &tile_count, &tile_off, &pairs, &keys, &hdr, &scratch_normal, &scratch_cam,
+                          &clip_counts, &huge_recs, &huge_counts, &huge_shade, &shadow_mask, &tile_count, &tile_off, &pairs, &keys, &hdr, &scratch_normal, &scratch_cam,
                           &zplane, &ao, &avg, &mip_a, &mip_b, &shadow_maps};
         for (DevBuf* b : bufs) b->release();
         if (staging) cudaFreeHost(staging);
@@ -121,6 +121,8 @@ struct slb_ctx {
     int direct_max = 128, warp_max = 4096;
     bool lean_shade = true;
     bool huge_in_shade = true;   // camera views resolve their first SLB_HUGE_PER_VIEW huge sub-triangles in the shade kernel
+    bool huge_prepare = true;    // ... and shade them from per-frame HugeShade records (k_huge_prepare) instead of a per-pixel re-set-up
+    bool shadow_mask = true;     // block-occupancy masks of the shadow maps: PCF footprints over untouched blocks skip their 25 taps
     slb_stats stats;
     // assets owned by the context
     slb_mesh* plane = nullptr;
@@ -296,6 +298,8 @@ extern "C" int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value) {
             (option == SLB_OPT_DIRECT_MAX ? ctx->direct_max : ctx->warp_max) = (int)value;
             return SLB_OK;
         case SLB_OPT_LEAN_SHADE: ctx->lean_shade = value != 0; return SLB_OK;
+        case SLB_OPT_HUGE_PREPARE: ctx->huge_prepare = value != 0; return SLB_OK;
+        case SLB_OPT_SHADOW_MASK: ctx->shadow_mask = value != 0; return SLB_OK;
         case SLB_OPT_HUGE_IN_SHADE: ctx->huge_in_shade = value != 0; return SLB_OK;
         default: return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "unknown option");
     }
@@ -1180,6 +1184,8 @@ static int subbatch_phase1(slb_ctx* ctx, int set, const slb_scene_desc* scenes, 
     CU(S.huge_recs.reserve((size_t)n * SLB_HUGE_PER_VIEW * sizeof(HugeRec)));
     CU(S.huge_counts.reserve((size_t)n * 4));
     CU(S.shadow_maps.reserve((size_t)b.n_shadow_maps * SLB_SHADOW_RES * SLB_SHADOW_RES * 4));
+    if (ctx->huge_in_shade && ctx->huge_prepare) CU(S.huge_shade.reserve((size_t)n * SLB_HUGE_PER_VIEW * sizeof(HugeShade)));
+    if (ctx->shadow_mask) CU(S.shadow_mask.reserve(((size_t)b.n_shadow_maps + 1) * SLB_SHADOW_MASK_WORDS * 4));
     const bool post = !b.fused;
     if (post) {
         if (!result->hdr) CU(S.hdr.reserve(npx * n * 16));
@@ -1202,10 +1208,14 @@ static int subbatch_phase1(slb_ctx* ctx, int set, const slb_scene_desc* scenes, 
         if (ctx->huge_in_shade) {
             f.huge = S.huge_recs.as<HugeRec>() + (size_t)j * SLB_HUGE_PER_VIEW; f.huge_n = S.huge_counts.as<uint32_t>() + j;
             b.views[j].huge = S.huge_recs.as<HugeRec>() + (size_t)j * SLB_HUGE_PER_VIEW; b.views[j].huge_n = S.huge_counts.as<uint32_t>() + j;
+            if (ctx->huge_prepare) f.huge_shade = S.huge_shade.as<HugeShade>() + (size_t)j * SLB_HUGE_PER_VIEW;
         }
         f.fused_tonemap = b.fused ? 1 : 0;
-        for (int li = 0; li < SLB_NUM_LIGHTS; ++li)
-            f.shadowMap[li] = f.lightActive[li] ? smaps + smap_elems * (uintptr_t)f.shadowMap[li] : nullptr;
+        for (int li = 0; li < SLB_NUM_LIGHTS; ++li) {
+            const uintptr_t slot = (uintptr_t)f.shadowMap[li];
+            f.shadowMask[li] = (f.lightActive[li] && ctx->shadow_mask) ? S.shadow_mask.as<uint32_t>() + (size_t)SLB_SHADOW_MASK_WORDS * slot : nullptr;
+            f.shadowMap[li] = f.lightActive[li] ? smaps + smap_elems * slot : nullptr;
+        }
         f.scratch_normal = (float4*)f.out[SLB_TARGET_NORMAL];
         f.scratch_cam = (float4*)f.out[SLB_TARGET_CAM_COORD];
         if (post) {
@@ -1228,7 +1238,10 @@ static int subbatch_phase1(slb_ctx* ctx, int set, const slb_scene_desc* scenes, 
     }
     const uint32_t shadow_tagbits = (255u - S.shadow_gen) << 24;
     for (int j = 0; j < n; ++j) b.frames[j].shadow_tagbits = shadow_tagbits;
-    for (uint32_t sidx = 0; sidx < b.n_shadow_maps; ++sidx) { b.views[n + sidx].out = smaps + smap_elems * sidx; b.views[n + sidx].tagbits = shadow_tagbits; }
+    for (uint32_t sidx = 0; sidx < b.n_shadow_maps; ++sidx) {
+        b.views[n + sidx].out = smaps + smap_elems * sidx; b.views[n + sidx].tagbits = shadow_tagbits;
+        b.views[n + sidx].mask = ctx->shadow_mask ? S.shadow_mask.as<uint32_t>() + (size_t)SLB_SHADOW_MASK_WORDS * sidx : nullptr;
+    }
 
     // ---- one staged upload ----
     const size_t sz[5] = {b.frames.size() * sizeof(DFrame), b.draws.size() * sizeof(DDraw), b.views.size() * sizeof(DView),
@@ -1258,6 +1271,7 @@ static int subbatch_phase1(slb_ctx* ctx, int set, const slb_scene_desc* scenes, 
         StageTimer t(ctx, s, ST_SHADOW);
         CU(cudaMemsetAsync(S.keys.p, 0xFF, npx * n * 8, s));
         if (clear_shadow_pool) CU(cudaMemsetAsync(S.shadow_maps.p, 0xFF, S.shadow_maps.cap, s));   // whole pool: every slot starts stale
+        if (ctx->shadow_mask && b.n_shadow_maps) CU(cudaMemsetAsync(S.shadow_mask.p, 0, (size_t)b.n_shadow_maps * SLB_SHADOW_MASK_WORDS * 4, s));
     }
     // ---- setup (camera + shadow views together) -> scan ----
     Pending& P = S.pending;

@@ -170,3 +170,56 @@ def test_asset_release_frees_and_reuploads(gpu_ctx):
     b = gpu_ctx.render([scene], target_mask=abi.TARGETS_ALL).frame_dict(0)        # uploaded again on use
     for k in a:
         assert (a[k].view(np.uint8) == b[k].view(np.uint8)).all(), k
+
+
+def _all_face_positions(size):
+    """WorldPos of every texel of a size^2 cube map, [6][size][size][3] (GL cube-face orientation, light_map.cpp:185-192)."""
+    c = (np.arange(size, dtype=np.float64) + 0.5) / size * 2.0 - 1.0
+    a, b = np.meshgrid(c, c, indexing="xy")                     # a along x (s), b along y (t)
+    one = np.ones_like(a)
+    faces = [(one, -b, -a), (-one, -b, a), (a, one, b), (a, -one, -b), (a, -b, one), (-a, -b, -one)]
+    return np.ascontiguousarray(np.stack([np.stack(f, -1) for f in faces]), np.float32)
+
+
+def test_lightmap_precompute_at_the_reference_sizes(gpu_ctx):
+    """LightMap::load at the sizes the reference uses (light_map.cpp:381,451,510,580: environment 512^2 with mips,
+    irradiance 32^2 at 0.02 rad steps, prefilter 128^2 x 5 mips and BRDF LUT 512^2 with 1024 samples each): the full
+    environment, irradiance and prefilter cubes and 20 000 random LUT texels against the oracle's per-texel functions (the ones tests/test_glsl_ref.py holds against the reference's shader text)."""
+    from stillleben_b200.desc import LightMapData
+    src = fixtures.light_map_data()
+    lm = LightMapData(src.equirect.copy(), list(src.light_directions), list(src.light_colors))      # a fresh object: not the cached small one
+    saved = gpu_ctx.lightmap_sizes
+    gpu_ctx.lightmap_sizes = (0, 0, 0, 0, 0)                                                         # the reference's sizes
+    try:
+        env, irr, pre, lut = gpu_ctx.read_lightmap(lm)
+    finally:
+        gpu_ctx.lightmap_sizes = saved
+    assert env.shape == (6, 512, 512, 4) and irr.shape == (6, 32, 32, 4) and lut.shape == (512, 512, 4)
+    L = ou.lib()
+    L.orc_test_lightmap_texels.argtypes = [C.c_int, C.POINTER(abi.LightmapDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]
+    L.orc_test_brdf_lut.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    d, eq = ou.lightmap_desc(lm)
+    h = L.orc_lightmap_create(C.byref(d), 512, 4, 4, 4, 4)           # full environment + mip chain; the small maps are unused
+    n = L.orc_lightmap_read(h, 0, None)
+    env_ref = np.empty(n, np.float32); L.orc_lightmap_read(h, 0, env_ref.ctypes.data)
+    np.testing.assert_allclose(env, env_ref.reshape(env.shape), rtol=1e-4, atol=1e-5)
+    wp = _all_face_positions(32)                                  # EVERY irradiance texel: 6144 x 24 806 environment samples
+    ref = np.zeros((6, 32, 32, 3), np.float32)
+    L.orc_test_lightmap_texels(1, C.byref(d), h, wp.ctypes.data, 6 * 32 * 32, 0.0, 1024, float(np.log2(512 / 32)), ref.ctypes.data)
+    np.testing.assert_allclose(irr[..., :3], ref, rtol=2e-3, atol=2e-4)
+    off = 0
+    for mip in range(5):                                          # every prefilter texel of every roughness level
+        size = 128 >> mip
+        level = pre[off:off + 6 * size * size * 4].reshape(6, size, size, 4); off += level.size
+        wp = _all_face_positions(size)
+        ref = np.zeros((6, size, size, 3), np.float32)
+        L.orc_test_lightmap_texels(2, C.byref(d), h, wp.ctypes.data, 6 * size * size, mip / 4.0, 1024, 0.0, ref.ctypes.data)
+        np.testing.assert_allclose(level[..., :3], ref, rtol=2e-3, atol=2e-4, err_msg=f"prefilter mip {mip}")
+    rng = np.random.RandomState(0)
+    x, y = rng.randint(0, 512, 20000), rng.randint(0, 512, 20000)
+    uv = np.ascontiguousarray(np.stack([(x + 0.5) / 512, (y + 0.5) / 512], 1), np.float32)
+    ref = np.zeros((20000, 2), np.float32)
+    L.orc_test_brdf_lut(uv.ctypes.data, 20000, 1024, ref.ctypes.data)
+    np.testing.assert_allclose(lut[y, x, :2], ref, rtol=2e-3, atol=2e-4)
+    L.orc_lightmap_destroy(h)
+    gpu_ctx.release(lm)

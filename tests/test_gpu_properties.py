@@ -91,9 +91,14 @@ def test_raster_paths_agree_bit_exactly(gpu_ctx, batch):
     """The visibility result is the per-pixel minimum key whichever way a triangle is rasterised: all tiled
     (0/0), all small ones by one thread (4096/4096), all by one warp (0/4096), the default mix — every
     target of every frame must come out byte-identical (SLB_OPT_DIRECT_MAX / SLB_OPT_WARP_MAX)."""
-    pool, scenes, res = batch
-    ref = [digest(res, i) for i in range(6)]
+    pool, scenes, _ = batch
     try:
+        # the per-frame HugeShade records change the ROUNDING of the float targets of huge-triangle pixels (not the ids): this
+        # test is about visibility, so both sides shade through the generic path (the records have their own test below)
+        gpu_ctx.set_option(abi.OPT_HUGE_PREPARE, 0)
+        res = gpu_ctx.render(scenes[:6], target_mask=abi.TARGETS_ALL)
+        gpu_ctx.synchronize()
+        ref = [digest(res, i) for i in range(6)]
         for direct_max, warp_max, huge in ((0, 0, 0), (4096, 4096, 1), (0, 4096, 0), (16, 256, 1), (128, 4096, 0), (0, 0, 1)):
             gpu_ctx.set_option(abi.OPT_DIRECT_MAX, direct_max)
             gpu_ctx.set_option(abi.OPT_WARP_MAX, warp_max)
@@ -105,6 +110,61 @@ def test_raster_paths_agree_bit_exactly(gpu_ctx, batch):
         gpu_ctx.set_option(abi.OPT_DIRECT_MAX, 128)
         gpu_ctx.set_option(abi.OPT_WARP_MAX, 4096)
         gpu_ctx.set_option(abi.OPT_HUGE_IN_SHADE, 1)
+        gpu_ctx.set_option(abi.OPT_HUGE_PREPARE, 1)
+
+
+def test_shadow_block_masks_change_nothing(gpu_ctx, batch):
+    """SLB_OPT_SHADOW_MASK: PCF footprints over untouched 8x8 texel blocks skip their 25 taps — every target of every frame
+    must stay byte-identical, with one and with three shadow lights, whichever raster path fills the maps."""
+    import fixtures
+    pool, scenes, res = batch
+    extra = [fixtures.variant("three_lights"), fixtures.variant("low_poly_closeup"), fixtures.variant("near_clip")]
+    on = [digest(res, i) for i in range(6)]
+    on3 = gpu_ctx.render(extra, target_mask=abi.TARGETS_ALL)
+    gpu_ctx.synchronize()
+    on += [digest(on3, i) for i in range(3)]
+    try:
+        for direct_max, warp_max in ((128, 4096), (0, 0)):
+            gpu_ctx.set_option(abi.OPT_DIRECT_MAX, direct_max)
+            gpu_ctx.set_option(abi.OPT_WARP_MAX, warp_max)
+            for mask in (0, 1):
+                gpu_ctx.set_option(abi.OPT_SHADOW_MASK, mask)
+                a = gpu_ctx.render(scenes[:6], target_mask=abi.TARGETS_ALL)
+                b = gpu_ctx.render(extra, target_mask=abi.TARGETS_ALL)
+                gpu_ctx.synchronize()
+                assert [digest(a, i) for i in range(6)] + [digest(b, i) for i in range(3)] == on, (direct_max, warp_max, mask)
+    finally:
+        gpu_ctx.set_option(abi.OPT_DIRECT_MAX, 128)
+        gpu_ctx.set_option(abi.OPT_WARP_MAX, 4096)
+        gpu_ctx.set_option(abi.OPT_SHADOW_MASK, 1)
+
+
+def test_huge_shade_records_agree_with_the_generic_path(gpu_ctx, batch):
+    """SLB_OPT_HUGE_PREPARE: huge sub-triangles (the background plane, close-up faces) shaded from per-frame records of the
+    vertex stage's outputs instead of a per-pixel re-set-up — ids identical, float targets within rounding, colour within
+    1 LSB; incl. clipped planes, textured planes and triangles that fall back to the generic path."""
+    import fixtures
+    scenes = list(batch[1][:3]) + [fixtures.variant(n) for n in ("near_clip", "plane_texture", "low_poly_closeup", "projective", "sticker")]
+    groups = [scenes[:3], scenes[3:]]
+    outs = {}
+    try:
+        for mode in (1, 0):
+            gpu_ctx.set_option(abi.OPT_HUGE_PREPARE, mode)
+            outs[mode] = [gpu_ctx.render(g, target_mask=abi.TARGETS_ALL) for g in groups]
+            gpu_ctx.synchronize()
+    finally:
+        gpu_ctx.set_option(abi.OPT_HUGE_PREPARE, 1)
+    for gi, g in enumerate(groups):
+        for i in range(len(g)):
+            a, b = outs[1][gi].frame_dict(i), outs[0][gi].frame_dict(i)
+            st = parity.compare(a, b)
+            for name, s_ in st.items():
+                if name in parity.EXACT:
+                    assert s_["mismatch"] == 0, (gi, i, name, s_)
+                elif name == "rgb":
+                    assert s_["over1"] <= 2, (gi, i, s_)
+                else:
+                    assert s_["bad"] == 0, (gi, i, name, s_)
 
 
 def test_lean_and_full_shade_kernels_agree(gpu_ctx, batch):
