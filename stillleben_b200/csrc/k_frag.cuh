@@ -423,11 +423,12 @@ __device__ __forceinline__ float shadow_pcf16(const uint32_t* __restrict__ map, 
     const uint32_t thr_t = tagbits | thr;   // texels are generation tag << 24 | d24 (DFrame::shadow_tagbits)
     float sum = 0.0f;
     bool touched = true;
-    if (mask) {   // the (at most 2 x 2) 8x8 texel blocks under the clamped 5x5 footprint: all clear -> every texel is untouched = lit
-        const int bx0 = min(max(i0, 0), N - 1) >> 3, bx1 = min(max(i0 + 4, 0), N - 1) >> 3;
-        const int by0 = min(max(j0, 0), N - 1) >> 3, by1 = min(max(j0 + 4, 0), N - 1) >> 3;
-        const uint32_t m = ((__ldg(mask + by0 * 8 + (bx0 >> 5)) >> (bx0 & 31)) | (__ldg(mask + by0 * 8 + (bx1 >> 5)) >> (bx1 & 31)) |
-                            (__ldg(mask + by1 * 8 + (bx0 >> 5)) >> (bx0 & 31)) | (__ldg(mask + by1 * 8 + (bx1 >> 5)) >> (bx1 & 31))) & 1u;
+    if (mask) {   // the (at most 2 x 2) texel blocks under the clamped 5x5 footprint: all clear -> every texel is untouched = lit
+        const int SH = SLB_SHADOW_MASK_SHIFT, RW = SLB_SHADOW_MASK_ROW;
+        const int bx0 = min(max(i0, 0), N - 1) >> SH, bx1 = min(max(i0 + 4, 0), N - 1) >> SH;
+        const int by0 = min(max(j0, 0), N - 1) >> SH, by1 = min(max(j0 + 4, 0), N - 1) >> SH;
+        const uint32_t m = ((__ldg(mask + by0 * RW + (bx0 >> 5)) >> (bx0 & 31)) | (__ldg(mask + by0 * RW + (bx1 >> 5)) >> (bx1 & 31)) |
+                            (__ldg(mask + by1 * RW + (bx0 >> 5)) >> (bx0 & 31)) | (__ldg(mask + by1 * RW + (bx1 >> 5)) >> (bx1 & 31))) & 1u;
         touched = m != 0u;
     }
     if (touched) {

@@ -250,16 +250,15 @@ __device__ __forceinline__ void red_min_u64(unsigned long long* p, unsigned long
 // G = 1: the thread walks the triangle's pixel box alone.  G = 32: the warp walks it together, lane l taking the
 // box pixels l, l+32, ... in row-major order (mid-size triangles, e.g. a 16k-triangle mesh seen from a 2048^2
 // shadow view), so the cost per triangle is box/32 iterations instead of one iteration per touched tile.
-// shadow views: mark the 8x8 texel blocks a triangle's pixel box touches in the map's block-occupancy mask (a superset of
-// the blocks it really writes; see SLB_SHADOW_MASK_WORDS). Most bits are already set by a neighbour: test before the atomic.
-__device__ __forceinline__ void mark_shadow_blocks(uint32_t* __restrict__ mask, int px0, int py0, int px1, int py1, int first_row, int row_step) {
-    const int bx0 = px0 >> 3, bx1 = px1 >> 3;
-    for (int by = (py0 >> 3) + first_row; by <= (py1 >> 3); by += row_step)
+// shadow views: mark the texel blocks under a pixel box in the map's block-occupancy mask (see SLB_SHADOW_MASK_WORDS). Called by
+// a whole warp with the bounding box of the triangles its lanes are about to rasterise (a superset of what they write, which
+// is all the mask promises): the l-th participating lane takes block rows l, l + n_lanes, ... of the box, so the marking is a handful of parallel RED.ORs per warp.
+__device__ __forceinline__ void mark_shadow_blocks(uint32_t* __restrict__ mask, int px0, int py0, int px1, int py1, int lane, int n_lanes) {
+    const int bx0 = px0 >> SLB_SHADOW_MASK_SHIFT, bx1 = px1 >> SLB_SHADOW_MASK_SHIFT;
+    for (int by = (py0 >> SLB_SHADOW_MASK_SHIFT) + lane; by <= (py1 >> SLB_SHADOW_MASK_SHIFT); by += n_lanes)
         for (int w = bx0 >> 5; w <= bx1 >> 5; ++w) {
             const int lo = max(bx0 - w * 32, 0), hi = min(bx1 - w * 32, 31);
-            const uint32_t bits = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
-            uint32_t* p = mask + by * 8 + w;
-            if ((__ldcg(p) & bits) != bits) atomicOr(p, bits);
+            atomicOr(mask + by * SLB_SHADOW_MASK_ROW + w, (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo));   // result unused: RED.OR
         }
 }
 template <bool SHADOW, int G>
@@ -269,7 +268,13 @@ __device__ __forceinline__ void raster_direct(int ax, int ay, int bx, int by, in
     const int ymin = min(ay, min(by, cy)), ymax = max(ay, max(by, cy));
     const int px0 = max(0, (xmin - 128 + 255) >> 8), px1 = min(W - 1, (xmax - 128) >> 8);
     const int py0 = max(0, (ymin - 128 + 255) >> 8), py1 = min(H - 1, (ymax - 128) >> 8);
-    if (SHADOW && mask) mark_shadow_blocks(mask, px0, py0, px1, py1, G == 1 ? 0 : lane, G);
+    if (SHADOW && mask) {   // occupancy mask of the map: the box of the warp's triangles, one reduction per bound
+        if (G == 1) {
+            const unsigned act = __activemask();
+            const int wx0 = __reduce_min_sync(act, px0), wy0 = __reduce_min_sync(act, py0), wx1 = __reduce_max_sync(act, px1), wy1 = __reduce_max_sync(act, py1);
+            mark_shadow_blocks(mask, wx0, wy0, wx1, wy1, __popc(act & ((1u << (threadIdx.x & 31)) - 1u)), __popc(act));   // rank among the active lanes
+        } else mark_shadow_blocks(mask, px0, py0, px1, py1, lane, 32);
+    }
     const int rbx = bx - ax, rby = by - ay, rcx = cx - ax, rcy = cy - ay;
     const int twoA = rbx * rcy - rby * rcx;
     const int sg = twoA > 0 ? 1 : -1;
@@ -783,11 +788,12 @@ __global__ void __launch_bounds__(SLB_RASTER_WARPS * 32) k_raster(const DView* _
         if (v.shadow) {   // depth-only view: the d24 plane the PCF lookup reads (cleared to 0xFFFFFF where nothing was drawn)
             uint32_t* out = reinterpret_cast<uint32_t*>(v.out);
             const unsigned long long k0 = keys[ly * SLB_TILE + lx], k1 = keys[(ly + 4) * SLB_TILE + lx];
-            static_assert(SLB_TILE == 8, "one raster tile == one block of the shadow-map occupancy mask");
+            static_assert(SLB_TILE == 8 && SLB_SHADOW_MASK_SHIFT >= 3, "a raster tile lies inside one block of the shadow-map occupancy mask");
             if (v.mask) {   // one atomic per tile, by the first active lane
                 const unsigned act = __activemask();
                 const unsigned any = __ballot_sync(act, k0 != SLB_KEY_EMPTY || k1 != SLB_KEY_EMPTY);
-                if (any && lane == __ffs(act) - 1) atomicOr(v.mask + ty * 8 + (tx >> 5), 1u << (tx & 31));
+                const int bx = tx >> (SLB_SHADOW_MASK_SHIFT - 3), by = ty >> (SLB_SHADOW_MASK_SHIFT - 3);
+                if (any && lane == __ffs(act) - 1) atomicOr(v.mask + by * SLB_SHADOW_MASK_ROW + (bx >> 5), 1u << (bx & 31));
             }
             if (y_lo + ly < H) out[(size_t)(y_lo + ly) * W + px] = v.tagbits | (k0 == SLB_KEY_EMPTY ? 0xFFFFFFu : (uint32_t)(k0 >> 40));
             if (y_lo + ly + 4 < H) out[(size_t)(y_lo + ly + 4) * W + px] = v.tagbits | (k1 == SLB_KEY_EMPTY ? 0xFFFFFFu : (uint32_t)(k1 >> 40));
@@ -867,7 +873,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
     // huge sub-triangles of this view (resolved per pixel below): staged once per block, only those whose pixel box
     // meets the block's 32x8 pixels
     __shared__ HugeRec s_huge[SLB_HUGE_PER_VIEW];
-    __shared__ __align__(16) HugeShade s_hs[SLB_HUGE_PER_VIEW];
     __shared__ int s_src[SLB_HUGE_PER_VIEW];
     __shared__ int s_nh;
     if (threadIdx.x == 0) s_nh = 0;
@@ -878,12 +883,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
         if (h.px1 >= bx0 && h.px0 <= bx0 + 31 && h.py1 >= by0 && h.py0 <= by0 + 7) { const int at = atomicAdd(&s_nh, 1); s_huge[at] = h; s_src[at] = threadIdx.x; }
     }
     __syncthreads();
-    if (f.huge_shade) {   // the staged records' shading halves: 16 x 128-bit words each, copied by the whole block
-        const int n4 = s_nh * (int)(sizeof(HugeShade) / 16);
-        for (int i = threadIdx.x; i < n4; i += THREADS)
-            reinterpret_cast<float4*>(s_hs)[i] = __ldg(reinterpret_cast<const float4*>(f.huge_shade + s_src[i >> 4]) + (i & 15));
-        __syncthreads();
-    }
     if (px >= W || py >= H) return;
     const size_t p = (size_t)py * W + px;
     unsigned long long key = f.keys[p];
@@ -924,10 +923,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
     if (key != SLB_KEY_EMPTY) {
         FragIn in; float bary[3]; uint32_t vid[3], vi[3];
         const DDraw* dp = nullptr;
-        if (best >= 0 && f.huge_shade && s_hs[best].fast) {
+        // (the record is read through the read-only path: every lane of a warp that sits on the plane reads the same 256 bytes,
+        // which stay in L1 for the frame — no staging copy, no block-wide barrier before the first pixel can start)
+        const HugeShade* hsp = (best >= 0 && f.huge_shade) ? f.huge_shade + s_src[best] : nullptr;
+        if (hsp && __ldg(&hsp->fast)) {
             // huge sub-triangle: interpolate the vertex-stage outputs k_huge_prepare parked for it; the barycentrics come from
             // the edge-function values the coverage test above already has (same arithmetic as bary_from_weights)
-            const HugeShade& hs = s_hs[best];
+            const HugeShade& hs = *hsp;      // fields are fetched where they are used
             const HugeRec& h = s_huge[best];
             dp = &draws[hs.draw];
             auto bary_at = [&](long long w0, long long w1, long long w2, float out[3]) {

@@ -101,10 +101,13 @@ struct __align__(16) HugeShade {
 };
 static_assert(sizeof(HugeShade) == 256, "HugeShade must be 256 bytes");
 
-// Coarse occupancy of a shadow map: one bit per 8x8 texel block, set by every rasteriser that MAY write a texel of the
+// Coarse occupancy of a shadow map: one bit per 16x16 texel block, set by every rasteriser that MAY write a texel of the
 // block in this sub-batch. A PCF footprint whose blocks are all clear consists of untouched (= lit) texels only, so the 25
-// taps need no loads (bit-identical result). word = by * 8 + (bx >> 5), bit = bx & 31.
-#define SLB_SHADOW_MASK_WORDS ((SLB_SHADOW_RES / 8) * (SLB_SHADOW_RES / 8) / 32)
+// taps need no loads (bit-identical result). word = by * SLB_SHADOW_MASK_ROW + (bx >> 5), bit = bx & 31. 2 KB per map: a
+// set-up block accumulates its bits in shared memory and flushes the non-zero words with one RED.OR each.
+#define SLB_SHADOW_MASK_SHIFT 4
+#define SLB_SHADOW_MASK_ROW ((SLB_SHADOW_RES >> SLB_SHADOW_MASK_SHIFT) / 32)
+#define SLB_SHADOW_MASK_WORDS ((SLB_SHADOW_RES >> SLB_SHADOW_MASK_SHIFT) * SLB_SHADOW_MASK_ROW)
 
 struct DView {
     int32_t W, H, tiles_x, tiles_y;
