@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """bench.py — multi-target frames/sec of the RenderPass::render hot path (BASELINE.json metric).
 
-Workload (config C3 of SURVEY.md §8d): a FIXED batch of 1024 random table-top scenes, 20 objects each
-from a pool of 21 stand-in meshes (16 384 triangles each), 640x480, six render targets (40 B/px), one
-shadow-casting directional light + ambient, manual exposure 1, SSAO off.  A "step" renders the whole
-batch once; with N GPUs the batch is sharded by scene index (strong scaling, no steady-state collective).
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3|C2|C5]
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+Workloads (`config.workload` in the JSON line names the one that ran, C3 is the default and the headline):
+  C3  a FIXED batch of 1024 random table-top scenes x 20 objects, 640x480, six render targets (40 B/px), one shadow-casting
+      directional light + ambient, manual exposure 1, SSAO off
+  C2  examples/ycb.py's shape: 512 scenes x 10 objects, 640x480, ycb.py intrinsics, PBR + IBL light map (sun from the map),
+      SSAO on, auto exposure
+  C5  256 scenes x 64 objects, 1920x1080, PBR + IBL + SSAO + 3 shadow lights
+Mesh pool for all three: 20 procedural stand-ins of 16 384 triangles (YCB google_16k scale) + the reference's own Stanford
+bunny (69 451 triangles, tests/golden/bunny_mesh.npz), shared by all scenes. A "step" renders the whole batch once; with N
+GPUs the batch is sharded by scene index (strong scaling, no steady-state collective; ONE broadcast of meshes + IBL maps).
 
-`value`  : frames/s with the scene descriptors in host memory and all outputs left in HBM (device-timed).
-`e2e`    : frames/s through slb_render_batch_host — descriptors host->device AND all six targets
-           device->host (pinned) inside the timed region.
-`--impl reference` times the CPU implementation of the same path (the OpenMP oracle: the reference's GL
-path cannot be built here) on all host cores over a bounded sample of the same scenes.
+`value`  : frames/s with the scene descriptors in host memory and all outputs left in HBM (device-timed, max over ranks).
+`e2e`    : frames/s through slb_render_batch_host — descriptors host->device AND all six targets device->host (pinned)
+           inside the timed region; `d2h_link_gbs` is a pinned device->host copy of the same size class measured in the same
+           process right before it (the ceiling of that number).
+`roofline`: the shade + MRT-store kernel against the measured HBM peak; `binner`: the set-up / bin kernel.
+`--impl reference` times the CPU implementation of the same path (the OpenMP oracle, one scene per host thread — the
+reference's GL path cannot be built here) over a bounded sample of the same scenes.
 """
 import argparse
+import concurrent.futures
 import json
 import os
 import subprocess
@@ -27,17 +35,62 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_SCENES = 1024
-N_OBJECTS = 20
-W, H = 640, 480
 POOL = 21
 BYTES_PER_PX = 40
 METRIC = "multi-target frames/sec at 640x480x20obj"
+YCB = (1066.778, 1067.487, 312.9869, 241.3109)
+CONFIGS = {
+    "C3": dict(n_scenes=1024, n_objects=20, W=640, H=480, n_lights=1, ibl=False, ssao=False, exposure=1.0, subbatch=64, seed0=1000,
+               intrinsics=YCB, e2e_chunk=1024, text="1 shadow light + ambient, exposure 1, SSAO off"),
+    "C2": dict(n_scenes=512, n_objects=10, W=640, H=480, n_lights=1, ibl=True, ssao=True, exposure=-1.0, subbatch=64, seed0=2000,
+               intrinsics=YCB, e2e_chunk=512, text="PBR + IBL light map (sun light from the map), SSAO on, auto exposure"),
+    "C5": dict(n_scenes=256, n_objects=64, W=1920, H=1080, n_lights=3, ibl=True, ssao=True, exposure=1.0, subbatch=8, seed0=3000,
+               intrinsics=None, e2e_chunk=32, text="PBR + IBL + SSAO + 3 shadow lights, exposure 1"),
+}
 
 
-def build_scenes(pool, lo, hi):
+def workload_string(name, n_scenes):
+    c = CONFIGS[name]
+    return (f"{name}: fixed batch of {n_scenes} scenes x {c['n_objects']} objects (pool: 20 procedural 16384-triangle stand-ins + the "
+            f"Stanford bunny, 69451 triangles), {c['W']}x{c['H']}, six targets (40 B/px), {c['text']}")
+
+
+def build_pool():
+    from stillleben_b200 import abi, synth
+    from stillleben_b200.desc import ImageData, MaterialData, MeshData
+    pool = synth.mesh_pool(POOL - 1)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bunny_mesh.npz"))     # the reference's tests/stanford_bunny after ITS consolidation
+    mats = [MaterialData(tuple(float(x) for x in r[0:4]), tuple(float(x) for x in r[4:8]), float(r[8]), float(r[9]), int(r[10]), int(r[11]),
+                         int(r[12]), int(r[13]), int(r[14])) for r in z["materials"]]
+    s = z["image0_sampler"]
+    images = [ImageData(np.ascontiguousarray(z["image0"]), int(s[0]), int(s[1]), int(s[2]), int(s[3]))]
+    pool.append(MeshData(np.ascontiguousarray(z["vertices"]).view(abi.VERTEX_DTYPE).reshape(-1), z["indices"],
+                         [tuple(int(x) for x in sm) for sm in z["submeshes"]], mats, images, z["bbox_min"].astype(np.float32),
+                         z["bbox_max"].astype(np.float32), "stanford_bunny"))
+    return pool
+
+
+def build_light_map(name):
     from stillleben_b200 import synth
-    return [synth.tabletop_scene(pool, 1000 + s, n_objects=N_OBJECTS, width=W, height=H) for s in range(lo, hi)]
+    from stillleben_b200.desc import LightMapData
+    c = CONFIGS[name]
+    if not c["ibl"]:
+        return None
+    eq, sun = synth.procedural_equirect()
+    dirs, cols = [sun.tolist()], [[2.0, 1.9, 1.7]]
+    for k in range(1, c["n_lights"]):                  # Light1 / Light2 of an sIBL file (light_map.cpp:104-152)
+        d = np.array([0.5 * (-1) ** k, 0.4 * k - 0.3, -1.0])
+        dirs.append((d / np.linalg.norm(d)).tolist())
+        cols.append([0.8, 0.8, 0.9])
+    return LightMapData(eq, dirs, cols)
+
+
+def build_scenes(name, pool, light_map, lo, hi):
+    from stillleben_b200 import synth
+    c = CONFIGS[name]
+    return [synth.tabletop_scene(pool, c["seed0"] + s, n_objects=c["n_objects"], width=c["W"], height=c["H"], light_map=light_map,
+                                 ssao=c["ssao"], manual_exposure=c["exposure"], n_lights=c["n_lights"], intrinsics=c["intrinsics"])
+            for s in range(lo, hi)]
 
 
 class ClockSampler(threading.Thread):
@@ -70,32 +123,62 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_reference_fps(pool, n_sample, n_threads=0, repeats=1):
-    """Oracle (CPU restatement of the reference path) on `n_sample` scenes of the workload -> frames/s."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_util as ou
-    assets = ou.OracleAssets()
-    scenes = build_scenes(pool, 0, n_sample)
-    ou.render(scenes[0], assets, n_threads=n_threads, want_hdr=False)     # builds oracle textures, warms caches
-    t0 = time.perf_counter()
-    for _ in range(repeats):
-        for sc in scenes:
-            ou.render(sc, assets, n_threads=n_threads, want_hdr=False)
-    dt = time.perf_counter() - t0
-    return n_sample * repeats / dt, dt
+class CpuBaseline:
+    """The CPU restatement of the path (oracle) on the first `n_sample` scenes of the workload, ONE SCENE PER HOST THREAD
+    (scenes are independent, exactly how the work shards across GPUs): descriptors, oracle assets and output arrays are built
+    once, outside the timed calls."""
+
+    def __init__(self, name, pool, n_sample, light_map):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import ctypes as C
+        import oracle_util as ou
+        from stillleben_b200 import abi
+        from stillleben_b200.desc import DescBatch
+        self.ou, self.C, self.abi = ou, C, abi
+        self.assets = ou.OracleAssets()
+        if light_map is not None:          # the light-map precompute is load-time work on both sides: reduced sizes keep the CPU set-up short
+            self.assets.lightmap_sizes = (128, 16, 32, 64, 64)
+        self.scenes = build_scenes(name, pool, light_map, 0, n_sample)
+        self.jobs = []
+        for sc in self.scenes:
+            batch = DescBatch([sc], self.assets.handle_of)
+            ptrs = (C.c_void_p * abi.NUM_TARGETS)()
+            keep = []
+            for t, (dt, ch) in enumerate(abi.TARGET_FORMATS):
+                if abi.TARGETS_SIX & (1 << t):
+                    a = np.zeros((sc.height, sc.width, ch), dt)
+                    keep.append(a)
+                    ptrs[t] = a.ctypes.data
+            self.jobs.append((batch, ptrs, keep))
+        self.L = ou.lib()
+        self.cores = os.cpu_count() or 1
+        self._one(self.jobs[0])                    # warms caches, builds the plane
+
+    def _one(self, job):
+        rc = self.L.orc_render(job[0].ptr, None, job[1], None, 1)      # one OpenMP thread inside: the parallelism is across scenes
+        assert rc == 0
+
+    def run(self):
+        """-> (frames/s, seconds)"""
+        t0 = time.perf_counter()
+        with concurrent.futures.ThreadPoolExecutor(self.cores) as ex:   # ctypes releases the GIL during the call
+            list(ex.map(self._one, self.jobs))
+        dt = time.perf_counter() - t0
+        return len(self.jobs) / dt, dt
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from stillleben_b200 import synth
-    pool = synth.mesh_pool(POOL)
+    c = CONFIGS[args.config]
+    n_scenes = args.scenes or c["n_scenes"]
     cores = os.cpu_count() or 1
-    sample = 4
+    sample = min(n_scenes, max(8, cores if c["W"] <= 640 else cores // 2))
+    base = CpuBaseline(args.config, build_pool(), sample, build_light_map(args.config))
     times = []
     for i in range(args.warmup + args.steps):
-        fps, dt = cpu_reference_fps(pool, sample, n_threads=cores)   # explicit: torchrun exports OMP_NUM_THREADS=1
+        fps, dt = base.run()
         if i >= args.warmup:
             times.append(dt)
     dt = sum(times) / len(times)
@@ -103,11 +186,28 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C3: {N_SCENES} scenes x {N_OBJECTS} objects, {W}x{H}, six targets", "sample_scenes_per_step": sample},
+            "config": {"workload": workload_string(args.config, n_scenes)},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} scenes of the workload per step, OpenMP oracle on all host cores"},
+                             "sample": f"scenes 0..{sample - 1} of the workload per step, OpenMP oracle, one scene per host thread"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def measure_d2h(torch, dev, n_bytes=1 << 28, reps=4):
+    """Pinned device->host copy bandwidth of this process / GPU, GB/s (the ceiling of the end-to-end number)."""
+    src = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+    dst = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, n_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
 
 
 def main():
@@ -116,7 +216,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scenes", type=int, default=N_SCENES)
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--scenes", type=int, default=0, help="batch size (default: the config's)")
     ap.add_argument("--subbatch", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -126,14 +227,20 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from stillleben_b200 import abi, lib, synth
+    from stillleben_b200 import abi, lib
     from stillleben_b200 import dist as sdist
 
+    c = CONFIGS[args.config]
+    W, H = c["W"], c["H"]
+    n_scenes = args.scenes or c["n_scenes"]
+    subbatch = args.subbatch or c["subbatch"]
     rank, world, local = sdist.env_rank_world()
     numa_node = sdist.bind_to_gpu_numa_node(local) if world > 1 else None   # host buffers next to the rank's GPU
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    # ---- load: rank 0 builds the pool, ONE broadcast of the asset arena ----
+    ctx = lib.Context(local)
+    ctx.set_option(abi.OPT_MAX_SUBBATCH, subbatch)
+    # ---- load: rank 0 builds the pool and runs the IBL precompute, ONE broadcast of the asset arena (meshes + IBL maps) ----
     # NCCL logs its version banner to stdout when the first communicator comes up: keep fd 1 pointed at stderr until
     # then, so that rank 0's stdout carries exactly ONE JSON line.
     saved_stdout = os.dup(1)
@@ -141,8 +248,13 @@ def main():
     try:
         if world > 1:
             dist.init_process_group("nccl", device_id=dev)
-        pool = synth.mesh_pool(POOL) if rank == 0 else None
-        pool = sdist.broadcast_meshes(pool, 0, dev)
+        pool, lms = None, None
+        if rank == 0:
+            pool = build_pool()
+            lm = build_light_map(args.config)
+            lms = [sdist.precompute_light_map(ctx, lm)] if (lm is not None and world > 1) else ([lm] if lm is not None else [])
+        pool, lms = sdist.broadcast_assets(pool, lms, 0, dev)
+        light_map = lms[0] if lms else None
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
@@ -150,12 +262,9 @@ def main():
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
-    ctx = lib.Context(local)
-    if args.subbatch:
-        ctx.set_option(abi.OPT_MAX_SUBBATCH, args.subbatch)
-    lo, hi = sdist.shard_range(args.scenes, rank, world)
+    lo, hi = sdist.shard_range(n_scenes, rank, world)
     n_local = hi - lo
-    scenes = build_scenes(pool, lo, hi)
+    scenes = build_scenes(args.config, pool, light_map, lo, hi)
     descs = ctx.descs(scenes)                       # host-side scene descriptors (what a caller hands over)
     result = lib.Result(ctx, W, H, n_local, abi.TARGETS_SIX)
     tstream = torch.cuda.Stream(device=dev)            # work is queued on this (non-default) stream
@@ -195,12 +304,13 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = args.scenes * args.steps / (ms_max * 1e-3)
+    value = n_scenes * args.steps / (ms_max * 1e-3)
 
     # ---- end to end: host descriptors in, all six targets back in pinned host memory ----
     e2e = None
     if not args.no_e2e:
-        chunk = min(1024, n_local)                                          # one call per step and rank
+        d2h_gbs = measure_d2h(torch, dev)                                    # this rank alone (the ranks probe concurrently at N > 1)
+        chunk = min(c["e2e_chunk"], n_local)                                 # scenes per call
         host = {}
         for tgt, (dt_, ch) in enumerate(abi.TARGET_FORMATS):
             if abi.TARGETS_SIX & (1 << tgt):
@@ -222,12 +332,17 @@ def main():
             e2e_step()
         torch.cuda.synchronize()
         dt_e2e = time.perf_counter() - t0
-        t = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
+        t = torch.tensor([dt_e2e, -d2h_gbs], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": args.scenes * args.steps / float(t.item()), "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world,
-               "d2h_bytes_per_step": int(d2h) * world, "note": f"slb_render_batch_host, page-locked host buffers (slb_host_alloc), {chunk}-scene calls; bound by the device->host link "
-                       "(12.29 MB per frame; 57 GB/s measured D2H on this pool = 4660 frames/s per GPU)"}
+        e2e_fps = n_scenes * args.steps / float(t[0].item())
+        link = -float(t[1].item())                                           # the slowest rank's link
+        per_gpu_gbs = e2e_fps / world * W * H * BYTES_PER_PX / 1e9
+        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+               "d2h_link_gbs": link, "d2h_achieved_gbs_per_gpu": per_gpu_gbs, "frac_of_d2h_link": per_gpu_gbs / link if link else None,
+               "note": f"slb_render_batch_host, page-locked host buffers (slb_host_alloc), {chunk}-scene calls; every frame returns "
+                       f"{W * H * BYTES_PER_PX / 1e6:.2f} MB over the device->host link, whose pinned-copy bandwidth (d2h_link_gbs, "
+                       "measured in this process; the minimum over ranks probing at the same time) bounds this number"}
 
     if rank != 0:
         if world > 1:
@@ -240,41 +355,47 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
     sub = ctx.stats()
-    traffic = None                                        # DRAM bytes of one k_shade launch from the committed ncu capture
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic = (tj["dram_read_bytes_per_launch"] + tj["dram_write_bytes_per_launch"]) / tj["frames_per_launch"]
-    n_sub = -(-n_local // (args.subbatch or 64))
-    shade_ms_per_launch = stage_ms[5] / (args.steps * n_sub)
+    ncu = {}
+    mpath = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")          # written by tools/ncu_metrics.py from the committed capture
+    if os.path.exists(mpath):
+        ncu = json.load(open(mpath)).get(args.config, {})
+    n_sub = -(-n_local // subbatch)
     frames_per_launch = n_local / n_sub
+    shade_ms = stage_ms[5] / (args.steps * n_sub)
     alg_bytes = frames_per_launch * W * H * BYTES_PER_PX
-    achieved = alg_bytes / (shade_ms_per_launch * 1e-3) / 1e9 if shade_ms_per_launch > 0 else 0.0
+    achieved = alg_bytes / (shade_ms * 1e-3) / 1e9 if shade_ms > 0 else 0.0
+    setup_ms = stage_ms[1] / (args.steps * n_sub)
+    geom_bytes = sum(sum(o.mesh.geometry_bytes() for o in sc.objects) for sc in scenes[:64]) / min(64, len(scenes)) * (1 + c["n_lights"])
+    setup_gbs = geom_bytes * frames_per_launch / (setup_ms * 1e-3) / 1e9 if setup_ms > 0 else 0.0
     names = ["shadow", "bin_count", "scan", "bin_emit", "raster", "shade_store", "ssao", "post"]
+    ks, kb = ncu.get("k_shade", {}), ncu.get("k_setup", {})
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"C3: fixed batch of {args.scenes} scenes x {N_OBJECTS} objects ({POOL}-mesh pool, 16384 tris each), "
-                                   f"{W}x{H}, six targets (40 B/px), 1 shadow light + ambient, exposure 1, SSAO off",
-                       "scenes_per_gpu": n_local, "subbatch": args.subbatch or 64, "rank0_numa_node": numa_node,
+            "config": {"workload": workload_string(args.config, n_scenes), "scenes_per_gpu": n_local, "subbatch": subbatch,
+                       "rank0_numa_node": numa_node,
                        "l2": "outputs per step (%.1f GB) exceed L2; no flush needed" % (n_local * W * H * BYTES_PER_PX / 1e9)},
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "stage_ms_per_step": {n: float(v / args.steps) for n, v in zip(names, stage_ms)},
             "roofline": {"bound": "hbm", "kernel": "k_shade (shade + MRT store)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic * frames_per_launch if traffic else None,
-                         "traffic_source": "profiles/traffic.json (ncu --set full, dram read + write bytes per k_shade launch, scaled to this launch size)",
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": shade_ms_per_launch},
+                         "frac": achieved / peak,
+                         "traffic": ks["dram_bytes_per_frame"] * frames_per_launch if "dram_bytes_per_frame" in ks else None,
+                         "traffic_source": "profiles/r02_ncu_metrics.json (ncu --set full: dram read + write bytes of one k_shade launch, per frame, scaled to this launch size)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": shade_ms},
+            "binner": {"kernel": "k_setup (triangle set-up, direct raster, tile count)", "achieved": setup_gbs, "unit": "GB/s", "frac": setup_gbs / peak,
+                       "algorithmic_bytes_per_launch": geom_bytes * frames_per_launch, "ms_per_launch": setup_ms,
+                       "algorithmic_bytes": "sum over drawn sub-meshes and views (camera + shadow) of n_verts*68 + n_idx*4 (SURVEY 8d B_geom)",
+                       "l2_hit_rate_pct": kb.get("l2_hit_pct"), "l2_hit_source": "profiles/r02_ncu_metrics.json (ncu lts__t_sector_hit_rate.pct)"},
             "triangles_per_frame": int(sub.triangles_submitted / max(1, sub.frames_rendered))}
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu and world == 1:
-        pool0 = pool
         cores = os.cpu_count() or 1
-        sample = 24
-        fps, dt = cpu_reference_fps(pool0, sample, n_threads=cores)
-        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": f"first {sample} scenes of the workload, OpenMP oracle ({dt:.1f} s)"}
+        sample = min(n_scenes, max(8, (cores if W <= 640 else cores // 2)))
+        base = CpuBaseline(args.config, pool, sample, build_light_map(args.config))
+        best = max(base.run() for _ in range(2))
+        line["cpu_baseline"] = {"value": best[0], "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"scenes 0..{sample - 1} of the workload, OpenMP oracle, one scene per host thread ({best[1]:.1f} s)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

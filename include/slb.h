@@ -202,6 +202,13 @@ int slb_lightmap_create(slb_ctx* ctx, const slb_lightmap_desc* desc, slb_lightma
  * 1024 samples, src/light_map.cpp:381,451,510,580); reduced sizes keep parity tests fast. */
 int slb_lightmap_create_ex(slb_ctx* ctx, const slb_lightmap_desc* desc, int env_size, int irradiance_size, int prefilter_size,
                            int lut_size, int n_samples, slb_lightmap** out);
+/* The same light map from maps precomputed elsewhere (rank 0's slb_lightmap_create read back with slb_lightmap_read and
+ * shipped in the one load-time broadcast of the asset arena): env0 [6][e][e][4], irradiance [6][i][i][4],
+ * prefilter = five levels packed [6][p>>l][p>>l][4], lut [l][l][4] floats, host or device memory. desc supplies the
+ * lights only (equirect_rgb is ignored). */
+int slb_lightmap_create_from_maps(slb_ctx* ctx, const slb_lightmap_desc* desc, const float* env0, int env_size,
+                                  const float* irradiance, int irradiance_size, const float* prefilter, int prefilter_size,
+                                  const float* lut, int lut_size, slb_lightmap** out);
 /* sizes[4] = env, irradiance, prefilter (level 0), LUT edge lengths */
 int slb_lightmap_sizes(const slb_lightmap* lm, int32_t sizes[4]);
 /* Read back the precomputed maps (tests / oracle cross-checks). which: 0 env cube level 0

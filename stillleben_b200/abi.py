@@ -129,6 +129,8 @@ PROTOTYPES = {
     "slb_texture_read_level": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                           C.c_void_p]),
     "slb_lightmap_create": (C.c_int, [C.c_void_p, C.POINTER(LightmapDesc), C.POINTER(C.c_void_p)]),
+    "slb_lightmap_create_from_maps": (C.c_int, [C.c_void_p, C.POINTER(LightmapDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "slb_lightmap_create_ex": (C.c_int, [C.c_void_p, C.POINTER(LightmapDesc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(C.c_void_p)]),
     "slb_lightmap_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),

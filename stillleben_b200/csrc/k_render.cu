@@ -37,6 +37,9 @@ __device__ __forceinline__ bool tile_may_overlap(const SubTri& t, int tx, int ty
 }
 
 struct BigEntry { PairRec rec; int tx0, ty0, ntx, nty; };
+#ifndef SLB_MID_GROUP
+#define SLB_MID_GROUP 8     // lanes that rasterise one mid-size triangle together in the set-up kernel
+#endif
 #define SLB_BIG_QUEUE 48
 #define SLB_BIG_TILES 24   // sub-triangles touching more tiles than this are binned by the whole block
 
@@ -273,7 +276,7 @@ __device__ __forceinline__ void raster_direct(int ax, int ay, int bx, int by, in
             const unsigned act = __activemask();
             const int wx0 = __reduce_min_sync(act, px0), wy0 = __reduce_min_sync(act, py0), wx1 = __reduce_max_sync(act, px1), wy1 = __reduce_max_sync(act, py1);
             mark_shadow_blocks(mask, wx0, wy0, wx1, wy1, __popc(act & ((1u << (threadIdx.x & 31)) - 1u)), __popc(act));   // rank among the active lanes
-        } else mark_shadow_blocks(mask, px0, py0, px1, py1, lane, 32);
+        } else mark_shadow_blocks(mask, px0, py0, px1, py1, lane, G);
     }
     const int rbx = bx - ax, rby = by - ay, rcx = cx - ax, rcy = cy - ay;
     const int twoA = rbx * rcy - rby * rcx;
@@ -416,16 +419,21 @@ __global__ void __launch_bounds__(SLB_SETUP_CHUNK, 5) k_setup(const DView* __res
         if (v.shadow) raster_direct<true, 1>(SLB_DQ(q), v.out, v.W, v.H, 0, v.tagbits, v.mask);
         else raster_direct<false, 1>(SLB_DQ(q), v.out, v.W, v.H, 0, 0u, nullptr);
     }
-    // ... then the mid-size ones, one per warp, handed out dynamically
+    // ... then the mid-size ones, one per GROUP of SLB_MID_GROUP lanes (four triangles in flight per warp), handed out
+    // dynamically. A whole warp per triangle replicates the triangle's set-up 32 times and leaves most lanes idle on boxes of
+    // a few dozen pixels; one thread per triangle makes the warp wait for its largest box. Groups of 8 sit in between.
     const int nmid = s_nmid;
+    constexpr int MG = SLB_MID_GROUP;
+    const int gl = lane & (MG - 1);
+    const unsigned gmask = (MG == 32 ? 0xffffffffu : ((1u << MG) - 1u)) << (lane & ~(MG - 1));
     for (;;) {
         int m = 0;
-        if (lane == 0) m = atomicAdd(&s_mid_next, 1);
-        m = __shfl_sync(0xffffffffu, m, 0);
+        if (gl == 0) m = atomicAdd(&s_mid_next, 1);
+        m = __shfl_sync(gmask, m, 0, MG);
         if (m >= nmid) break;
         const int q = SLB_SETUP_CHUNK - 1 - m;
-        if (v.shadow) raster_direct<true, 32>(SLB_DQ(q), v.out, v.W, v.H, lane, v.tagbits, v.mask);
-        else raster_direct<false, 32>(SLB_DQ(q), v.out, v.W, v.H, lane, 0u, nullptr);
+        if (v.shadow) raster_direct<true, MG>(SLB_DQ(q), v.out, v.W, v.H, gl, v.tagbits, v.mask);
+        else raster_direct<false, MG>(SLB_DQ(q), v.out, v.W, v.H, gl, 0u, nullptr);
     }
 #undef SLB_DQ
 }

@@ -686,6 +686,60 @@ extern "C" int slb_lightmap_create(slb_ctx* ctx, const slb_lightmap_desc* desc, 
     return slb_lightmap_create_ex(ctx, desc, 0, 0, 0, 0, 0, out);
 }
 
+// A light map from maps that were precomputed elsewhere (another rank's slb_lightmap_create, read back with
+// slb_lightmap_read and broadcast in the asset arena): copies them, rebuilds the environment's mip chain.
+extern "C" int slb_lightmap_create_from_maps(slb_ctx* ctx, const slb_lightmap_desc* desc, const float* env0, int env_size, const float* irradiance,
+                                             int irr_size, const float* prefilter, int pre_size, const float* lut, int lut_size, slb_lightmap** out) {
+    if (!ctx || !out) return SLB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!desc || desc->n_lights < 0 || desc->n_lights > SLB_NUM_LIGHTS || !env0 || !irradiance || !prefilter || !lut)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_lightmap_create_from_maps: bad arguments");
+    if (env_size <= 0 || irr_size <= 0 || lut_size <= 0 || (env_size & (env_size - 1)) || (pre_size & (pre_size - 1)) || pre_size < 16)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_lightmap_create_from_maps: cube sizes must be powers of two (prefilter >= 16)");
+    CU(cudaSetDevice(ctx->device));
+    slb_lightmap* lm = new slb_lightmap;
+    std::memset(&lm->h, 0, sizeof lm->h);
+    lm->env_size = env_size; lm->irr_size = irr_size; lm->pre_size = pre_size; lm->lut_size = lut_size;
+    lm->h.n_lights = desc->n_lights;
+    std::memcpy(lm->h.light_directions, desc->light_directions, sizeof lm->h.light_directions);
+    std::memcpy(lm->h.light_colors, desc->light_colors, sizeof lm->h.light_colors);
+    int rc = SLB_OK;
+    do {
+        float4 *e0 = nullptr, *ir = nullptr, *lu = nullptr;
+        const size_t be = (size_t)6 * env_size * env_size * sizeof(float4), bi = (size_t)6 * irr_size * irr_size * sizeof(float4),
+                     bl = (size_t)lut_size * lut_size * sizeof(float4);
+        if ((rc = lm_alloc(ctx, lm, sizeof(DLightMap), (void**)&lm->d)) != SLB_OK) break;
+        if ((rc = lm_alloc(ctx, lm, be, (void**)&e0)) != SLB_OK) break;
+        if ((rc = lm_alloc(ctx, lm, bi, (void**)&ir)) != SLB_OK) break;
+        if ((rc = lm_alloc(ctx, lm, bl, (void**)&lu)) != SLB_OK) break;
+        cudaError_t e = cudaMemcpyAsync(e0, env0, be, cudaMemcpyDefault, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ir, irradiance, bi, cudaMemcpyDefault, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(lu, lut, bl, cudaMemcpyDefault, ctx->stream);
+        if (e != cudaSuccess) { rc = fail(ctx, SLB_ERR_CUDA, cudaGetErrorString(e)); break; }
+        if ((rc = lightmap_build_env_mips(ctx, lm, e0, env_size)) != SLB_OK) break;
+        lm->h.irr.px = ir; lm->h.irr.size = irr_size;
+        lm->h.lut = lu; lm->h.lut_size = lut_size;
+        const float* src = prefilter;
+        for (int mip = 0; mip < 5 && rc == SLB_OK; ++mip) {
+            const int n = pre_size >> mip;
+            float4* p = nullptr;
+            if ((rc = lm_alloc(ctx, lm, (size_t)6 * n * n * sizeof(float4), (void**)&p)) != SLB_OK) break;
+            e = cudaMemcpyAsync(p, src, (size_t)6 * n * n * sizeof(float4), cudaMemcpyDefault, ctx->stream);
+            if (e != cudaSuccess) { rc = fail(ctx, SLB_ERR_CUDA, cudaGetErrorString(e)); break; }
+            lm->h.pre[mip].px = p; lm->h.pre[mip].size = n;
+            src += (size_t)6 * n * n * 4;
+        }
+        if (rc != SLB_OK) break;
+        if ((rc = lightmap_finish(ctx, lm)) != SLB_OK) break;
+        cudaError_t e2 = sync_ctx(ctx);
+        if (e2 == cudaSuccess) e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) { rc = fail(ctx, SLB_ERR_CUDA, std::string("slb_lightmap_create_from_maps: ") + cudaGetErrorString(e2)); break; }
+    } while (0);
+    if (rc != SLB_OK) { std::string keep = ctx->err; slb_lightmap_destroy(ctx, lm); ctx->err = keep; return rc; }
+    *out = lm;
+    return SLB_OK;
+}
+
 extern "C" int slb_lightmap_read(slb_ctx* ctx, const slb_lightmap* lm, int which, float* host_out, size_t n_floats) {
     if (!ctx || !lm || !host_out) return SLB_ERR_INVALID_ARGUMENT;
     CU(cudaSetDevice(ctx->device));

@@ -80,6 +80,9 @@ class LightMapData:
     equirect: np.ndarray  # float32 [H, W, 3], row 0 = GL row 0
     light_directions: list = field(default_factory=list)  # up to 3 (x,y,z)
     light_colors: list = field(default_factory=list)
+    # precomputed (env level 0 [6,e,e,4], irradiance [6,i,i,4], prefilter packed, LUT [l,l,4]) — set on ranks that received the
+    # maps in the asset broadcast instead of running the precompute themselves (dist.broadcast_assets)
+    maps: Optional[tuple] = None
 
 
 @dataclass

@@ -2,7 +2,8 @@
 
 Scenes of a batch are independent (the reference treats GPUs as independent processes:
 python/src/py_context.cpp:12-52), so the only communication is ONE broadcast of the packed
-read-only asset arena (consolidated vertex / index buffers, material tables, texture images) from
+read-only asset arena (consolidated vertex / index buffers, material tables, texture images, and the
+light maps WITH their precomputed IBL maps: environment cube, irradiance, prefilter, BRDF LUT) from
 rank 0 at load time — NCCL over NVLink on the GPU box, gloo in the CPU tests.  There is no
 collective in the steady state.
 """
@@ -12,7 +13,7 @@ import os
 import numpy as np
 
 from . import abi
-from .desc import ImageData, MaterialData, MeshData
+from .desc import ImageData, LightMapData, MaterialData, MeshData
 
 
 def shard_range(n_items, rank, world_size):
@@ -27,8 +28,9 @@ def env_rank_world():
 
 
 # ---- asset arena ------------------------------------------------------------------------------
-def pack_meshes(meshes):
-    """Serialise a list of MeshData into (header bytes, flat uint8 arena)."""
+def pack_meshes(meshes, light_maps=()):
+    """Serialise a list of MeshData (and LightMapData, with their precomputed maps when `maps` is set) into
+    (header bytes, flat uint8 arena)."""
     chunks, metas, off = [], [], 0
 
     def put(a):
@@ -53,12 +55,34 @@ def pack_meshes(meshes):
                                    "wrap_t": im.wrap_t, "min_filter": im.min_filter, "mag_filter": im.mag_filter,
                                    "kind": im.kind})
         metas.append(meta)
+    lms = []
+    for lm in light_maps:
+        eq = np.ascontiguousarray(lm.equirect, np.float32)
+        meta = {"equirect": put(eq), "equirect_shape": list(eq.shape), "light_directions": [list(map(float, d)) for d in lm.light_directions],
+                "light_colors": [list(map(float, c)) for c in lm.light_colors], "maps": None}
+        if lm.maps is not None:
+            meta["maps"] = [{"data": put(np.ascontiguousarray(a, np.float32)), "shape": list(np.shape(a))} for a in lm.maps]
+        lms.append(meta)
     arena = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
-    return json.dumps(metas).encode(), arena
+    return json.dumps({"meshes": metas, "light_maps": lms}).encode(), arena
+
+
+def unpack_assets(header, arena):
+    """-> (list of MeshData, list of LightMapData)."""
+    doc = json.loads(bytes(header).decode())
+    lms = []
+    for meta in doc["light_maps"]:
+        o, n = meta["equirect"]
+        eq = arena[o:o + n].view(np.float32).reshape(meta["equirect_shape"]).copy()
+        maps = None
+        if meta["maps"] is not None:
+            maps = tuple(arena[m["data"][0]:m["data"][0] + m["data"][1]].view(np.float32).reshape(m["shape"]).copy() for m in meta["maps"])
+        lms.append(LightMapData(eq, meta["light_directions"], meta["light_colors"], maps))
+    return unpack_meshes(header, arena), lms
 
 
 def unpack_meshes(header, arena):
-    metas = json.loads(bytes(header).decode())
+    metas = json.loads(bytes(header).decode())["meshes"]
     out = []
     for meta in metas:
         vo, vn = meta["vertices"]
@@ -77,18 +101,32 @@ def unpack_meshes(header, arena):
 
 
 def broadcast_meshes(meshes, src=0, device=None):
-    """Broadcast the mesh pool from rank `src` to every rank (one collective for the arena).
+    """Broadcast the mesh pool from rank `src` to every rank (one collective for the arena)."""
+    return broadcast_assets(meshes, (), src, device)[0]
 
-    `meshes` is only read on `src`; other ranks may pass None.  Works with any initialised
-    torch.distributed backend; with NCCL the arena travels GPU-to-GPU over NVLink."""
+
+def precompute_light_map(ctx, lm):
+    """Run the IBL precompute of `lm` on this rank's GPU (if it has not run yet) and attach the maps to it, so that the
+    asset broadcast carries them and the other ranks skip the precompute (north_star: "one NCCL broadcast of shared
+    mesh/IBL buffers at load time")."""
+    if lm.maps is None:
+        lm.maps = tuple(ctx.read_lightmap(lm))
+    return lm
+
+
+def broadcast_assets(meshes, light_maps=(), src=0, device=None):
+    """Broadcast the mesh pool and the light maps from rank `src` to every rank: ONE collective for the whole arena.
+
+    `meshes` / `light_maps` are only read on `src`; other ranks may pass None.  Works with any initialised
+    torch.distributed backend; with NCCL the arena travels GPU-to-GPU over NVLink. Returns (meshes, light_maps)."""
     import torch
     import torch.distributed as dist
 
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return meshes
+        return meshes, list(light_maps or ())
     rank = dist.get_rank()
     if rank == src:
-        header, arena = pack_meshes(meshes)
+        header, arena = pack_meshes(meshes, light_maps or ())
         sizes = torch.tensor([len(header), len(arena)], dtype=torch.int64)
     else:
         header, arena = b"", None
@@ -103,9 +141,9 @@ def broadcast_meshes(meshes, src=0, device=None):
         payload[hn:] = torch.from_numpy(arena).to(dev)
     dist.broadcast(payload, src)
     if rank == src:
-        return meshes
+        return meshes, list(light_maps or ())
     host = payload.cpu().numpy()
-    return unpack_meshes(host[:hn].tobytes(), host[hn:])
+    return unpack_assets(host[:hn].tobytes(), host[hn:])
 
 
 # ---- host placement ---------------------------------------------------------------------------

@@ -236,7 +236,13 @@ class Context:
                 d.light_directions[i][k] = float(lm.light_directions[i][k])
                 d.light_colors[i][k] = float(lm.light_colors[i][k])
         h = C.c_void_p()
-        rc = self.lib.slb_lightmap_create_ex(self.h, C.byref(d), *self.lightmap_sizes, C.byref(h))
+        if lm.maps is not None:                        # precomputed on another rank, received in the asset broadcast
+            env0, irr, pre, lut = (np.ascontiguousarray(a, np.float32) for a in lm.maps)
+            pre_size = int(round(np.sqrt(pre.size / (6 * 4) / sum(0.25 ** k for k in range(5)))))
+            rc = self.lib.slb_lightmap_create_from_maps(self.h, C.byref(d), env0.ctypes.data, env0.shape[1], irr.ctypes.data, irr.shape[1],
+                                                        pre.ctypes.data, pre_size, lut.ctypes.data, lut.shape[0], C.byref(h))
+        else:
+            rc = self.lib.slb_lightmap_create_ex(self.h, C.byref(d), *self.lightmap_sizes, C.byref(h))
         if rc != abi.OK:
             _raise(self.lib, self.h, rc, "slb_lightmap_create")
         return h.value
