@@ -198,9 +198,14 @@ class LightMap:
 # ---------------------------------------------------------------------------------------------
 # mesh
 # ---------------------------------------------------------------------------------------------
-class _Range3D:
+class Range3D:
+    """Magnum::Range3D as exposed by py_magnum.cpp:52-80 (min, max, center, size, diagonal)."""
+
     def __init__(self, lo, hi):
         self.min, self.max = _t(lo), _t(hi)
+
+    def __repr__(self):
+        return "Range3D(Vector(%g, %g, %g),Vector(%g, %g, %g))" % (*self.min.tolist(), *self.max.tolist())
 
     @property
     def center(self):
@@ -215,6 +220,9 @@ class _Range3D:
         return float(torch.linalg.norm(self.size))
 
 
+_Range3D = Range3D
+
+
 class Mesh:
     def __init__(self, filename, visual=True, physics=True, flags=None):
         _context()
@@ -222,9 +230,13 @@ class Mesh:
             self.data, self.filename = filename, filename.name
         else:
             self.filename = os.fspath(filename)
-            if not self.filename.lower().endswith((".gltf", ".glb")):
-                raise RuntimeError(f"Could not load mesh {self.filename}: only glTF / GLB is supported by this build")
-            self.data = gltf.load(self.filename)
+            if self.filename.lower().endswith(".obj"):
+                from . import objfile
+                self.data = objfile.load(self.filename)
+            elif self.filename.lower().endswith((".gltf", ".glb")):
+                self.data = gltf.load(self.filename)
+            else:
+                raise RuntimeError(f"Could not load mesh {self.filename}: only glTF / GLB / OBJ are supported by this build")
         self._scale = 1.0
         self._rigid = np.eye(4, dtype=np.float32)
         self._class_index = 1                                          # mesh.h:300
@@ -265,7 +277,7 @@ class Mesh:
         p = self._pre_np().astype(np.float64)
         lo = p[:3, :3] @ self.data.bbox_min + p[:3, 3]
         hi = p[:3, :3] @ self.data.bbox_max + p[:3, 3]
-        return _Range3D(lo, hi)
+        return Range3D(lo, hi)                                       # mesh.cpp:1075-1081: corners as transformed, not re-sorted
 
     def center_bbox(self):
         c = (self.data.bbox_min + self.data.bbox_max) / 2
@@ -397,6 +409,11 @@ class Object:
         self.sticker_texture = None
         self.static = False
         self.mass = 1.0
+        # rigid-body state: stored only (PhysX is not part of this build); py_object.cpp:120-197
+        self.density = 500.0
+        self.linear_velocity = torch.zeros(3)
+        self.angular_velocity = torch.zeros(3)
+        self.linear_velocity_limit = 1e3
 
     def pose(self):
         return _t(self._pose)
@@ -539,10 +556,156 @@ class Scene:
     def choose_random_light_position(self):
         warnings.warn("choose_random_light_position() is deprecated", DeprecationWarning)     # py_scene.cpp:350-352: sets nothing
 
-    def simulate_tabletop_scene(self, *a, **k):
+    def _no_physics(self, *a, **k):
         raise RuntimeError("physics is not available in this build (PhysX stays host-side, SURVEY §3.2)")
 
-    simulate = check_collisions = find_noncolliding_pose = load_physics = simulate_tabletop_scene
+    simulate = check_collisions = find_noncolliding_pose = load_physics = _no_physics
+
+    def simulate_tabletop_scene(self, vis_cb=None):
+        """scene.cpp:612-759 drops the objects onto a z = 0.04 table through the origin with PhysX. PhysX is not part of this
+        build: this is a NON-PHYSICAL placement sampler with the same outputs (background_plane_pose set like :650-658,
+        every non-static object given a pose above the table): random orientation, bounding spheres resting on the table,
+        positions rejection-sampled so the spheres do not intersect. Objects do not lean on each other."""
+        warnings.warn("simulate_tabletop_scene(): PhysX is not part of this build; objects are placed by a non-physical "
+                      "sampler (random orientations, non-intersecting bounding spheres on the table)")
+        rng = self._rng
+        top = 0.04
+        a = rng.uniform(-math.pi, math.pi)
+        plane = np.eye(4, dtype=np.float32)
+        plane[:2, :2] = [[math.cos(a), -math.sin(a)], [math.sin(a), math.cos(a)]]
+        plane[2, 3] = top
+        if all(not o.static for o in self._objects):
+            self.background_plane_pose = _t(plane)
+        placed = []
+        for o in self._objects:
+            if o.static:
+                continue
+            bb = o.mesh.bbox
+            r = bb.diagonal / 2.0
+            q = rng.normal(size=4)
+            q /= np.linalg.norm(q)
+            R = quat_to_matrix(torch.tensor([q[0], q[1], q[2], q[3]], dtype=torch.float32)).numpy()
+            spread = r
+            while True:
+                xy = rng.uniform(-spread, spread, size=2)
+                if all(np.hypot(*(xy - pxy)) >= r + pr for pxy, pr in placed):
+                    break
+                spread *= 1.1
+            placed.append((xy, r))
+            centre = np.array([xy[0], xy[1], top + r], np.float32)
+            pose = np.eye(4, dtype=np.float32)
+            pose[:3, :3] = R
+            pose[:3, 3] = centre - R @ bb.center.numpy()               # Matrix4::from(q, pos) * translation(-bbox centre), :676
+            o.set_pose(pose)
+
+    # ---- serialization (scene.cpp:761-868, object.cpp:384-460, mesh.cpp:1091-1115: Corrade configuration text) ----
+    def serialize(self):
+        f = lambda v: " ".join("%.9g" % float(x) for x in np.asarray(v, np.float64).reshape(-1))
+        quat = lambda R: f(matrix_to_quat(_t(R)).numpy())
+        out = ["viewport=%d %d" % (self._W, self._H), "projection=" + f(self._projection),
+               "cameraPosition=" + f(self._camera_pose[:3, 3]), "cameraRotation=" + quat(self._camera_pose[:3, :3]),
+               "ambientLight=" + f(self.ambient_light), "numObjects=%d" % len(self._objects)]
+        if self.light_map is not None and self.light_map.path:
+            out.append("lightMap=" + self.light_map.path)
+        out += ["backgroundPlanePose=" + f(_np44(self.background_plane_pose)), "backgroundPlaneSize=" + f(self.background_plane_size),
+                "manualExposure=%.9g" % float(self.manual_exposure)]
+        for i in range(3):
+            out += ["[light]", "direction=" + f(self._light_directions[i]), "color=" + f(self._light_colors[i])]
+        for o in self._objects:
+            out += ["[object]", "pose=" + f(o._pose), "instanceIndex=%d" % o.instance_index, "specularColor=" + f(o.specular_color),
+                    "shininess=%.9g" % o.shininess, "roughness=%.9g" % float(o.roughness), "metallic=%.9g" % float(o.metallic),
+                    "casts_shadows=%s" % ("true" if o.casts_shadows else "false"), "stickerRange=" + f(o.sticker_range),
+                    "stickerRotation=" + f(o.sticker_rotation), "static=%s" % ("true" if o.static else "false"),
+                    "density=%.9g" % float(o.density), "linear_velocity_limit=%.9g" % float(o.linear_velocity_limit),
+                    "[object/mesh]", "filename=" + str(o.mesh.filename), "classIndex=%d" % o.mesh.class_index,
+                    "scale=%.9g" % o.mesh._scale, "rigidPretransform=" + f(o.mesh._rigid)]
+        return "\n".join(out) + "\n"
+
+    def deserialize(self, text, cache=None):
+        groups, cur = [("", {})], None
+        for line in text.splitlines():
+            line = line.strip()
+            if not line or line.startswith(("#", ";")):
+                continue
+            if line.startswith("[") and line.endswith("]"):
+                groups.append((line[1:-1], {}))
+            elif "=" in line:
+                k, v = line.split("=", 1)
+                groups[-1][1][k.strip()] = v.strip()
+        vec = lambda v: np.array([float(x) for x in v.split()], np.float32)
+        top = groups[0][1]
+        if "viewport" in top:
+            self._W, self._H = (int(x) for x in top["viewport"].split())
+        if "projection" in top:
+            self._projection = vec(top["projection"]).reshape(4, 4)
+        if "cameraPosition" in top and "cameraRotation" in top:
+            pose = np.eye(4, dtype=np.float32)
+            pose[:3, :3] = quat_to_matrix(torch.from_numpy(vec(top["cameraRotation"]))).numpy()
+            pose[:3, 3] = vec(top["cameraPosition"])
+            self._camera_pose = pose
+        lights = [g for n, g in groups if n == "light"]
+        if "lightPosition" in top:                                             # scene.cpp:816-820 (legacy files)
+            p = vec(top["lightPosition"])
+            self._light_directions.zero_()
+            self._light_directions[0] = torch.from_numpy(-p / np.linalg.norm(p))
+            self._light_colors.zero_()
+            self._light_colors[0] = torch.tensor([0.0, 0.8, 0.0])
+        elif lights:
+            self._light_directions.zero_()
+            self._light_colors.zero_()
+            for i, g in enumerate(lights[:3]):
+                self._light_directions[i] = torch.from_numpy(vec(g["direction"]))
+                self._light_colors[i] = torch.from_numpy(vec(g["color"]))
+        if "ambientLight" in top:
+            self.ambient_light = torch.from_numpy(vec(top["ambientLight"]))
+        if "lightMap" in top:
+            self.light_map = LightMap(top["lightMap"])
+        if "backgroundPlanePose" in top:
+            self.background_plane_pose = torch.from_numpy(vec(top["backgroundPlanePose"]).reshape(4, 4))
+        if "backgroundPlaneSize" in top:
+            self.background_plane_size = torch.from_numpy(vec(top["backgroundPlaneSize"]))
+        if "manualExposure" in top:
+            self.manual_exposure = float(top["manualExposure"])
+        self._objects = []
+        meshes = cache if cache is not None else {}
+        it = iter(range(len(groups)))
+        for gi in it:
+            name, g = groups[gi]
+            if name != "object":
+                continue
+            if gi + 1 >= len(groups) or groups[gi + 1][0] != "object/mesh":
+                raise RuntimeError("Did not find mesh subgroup in object")   # object.cpp:410-411
+            mg = groups[gi + 1][1]
+            key = mg["filename"]
+            mesh = Mesh(key) if key not in meshes else meshes[key]
+            if cache is not None:
+                meshes[key] = mesh
+            if "classIndex" in mg:
+                mesh.class_index = int(mg["classIndex"])
+            if "scale" in mg:
+                mesh._scale = float(mg["scale"])
+            if "rigidPretransform" in mg:
+                mesh._rigid = vec(mg["rigidPretransform"]).reshape(4, 4)
+            o = Object(mesh)
+            if "pose" in g:
+                o._pose = vec(g["pose"]).reshape(4, 4)
+            if "instanceIndex" in g:
+                o.instance_index = int(g["instanceIndex"])
+            if "specularColor" in g:
+                o.specular_color = torch.from_numpy(vec(g["specularColor"]))
+            for k, attr in (("shininess", "shininess"), ("roughness", "roughness"), ("metallic", "metallic"), ("density", "density"),
+                            ("linear_velocity_limit", "linear_velocity_limit")):
+                if k in g:
+                    setattr(o, attr, float(g[k]))
+            if "casts_shadows" in g:
+                o.casts_shadows = g["casts_shadows"] == "true"
+            if "static" in g:
+                o.static = g["static"] == "true"
+            if "stickerRange" in g:
+                o.sticker_range = torch.from_numpy(vec(g["stickerRange"]))
+            if "stickerRotation" in g:
+                o.sticker_rotation = torch.from_numpy(vec(g["stickerRotation"]))
+            self.add_object(o)
 
     # ---- marshalling ----
     def _spec(self, ssao_enabled, predicate):
@@ -643,6 +806,58 @@ class RenderPass:
 def view(scene):
     """The reference opens an X11 viewer; headless this returns immediately (SURVEY §3.2 caveat ii)."""
     return None
+
+
+def quat_to_matrix(quat):
+    """py_magnum.cpp:83-99: [x y z w] (normalised first) -> 3x3 rotation matrix."""
+    if quat.dim() != 1 or quat.size(0) != 4:
+        raise ValueError("Quaternion tensor should be one-dimensional tensor of size 4")
+    x, y, z, w = (quat.detach().cpu().double() / quat.detach().cpu().double().norm()).tolist()
+    return torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], dtype=torch.float32)
+
+
+def matrix_to_quat(matrix):
+    """py_magnum.cpp:100-113: 3x3 rotation matrix -> [x y z w] (Magnum's Quaternion::fromMatrix branch order)."""
+    m = matrix.detach().cpu().double().numpy()
+    tr = m[0, 0] + m[1, 1] + m[2, 2]
+    if tr > 0:
+        s = math.sqrt(tr + 1.0) * 2
+        q = [(m[2, 1] - m[1, 2]) / s, (m[0, 2] - m[2, 0]) / s, (m[1, 0] - m[0, 1]) / s, s / 4]
+    else:
+        i = int(np.argmax([m[0, 0], m[1, 1], m[2, 2]]))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = math.sqrt(m[i, i] - m[j, j] - m[k, k] + 1.0) * 2
+        q = [0.0, 0.0, 0.0, (m[k, j] - m[j, k]) / s]
+        q[i], q[j], q[k] = s / 4, (m[j, i] + m[i, j]) / s, (m[k, i] + m[i, k]) / s
+    return torch.tensor(q, dtype=torch.float32)
+
+
+def render_debug_image(scene):
+    """src/debug.cpp:19-58 draws every object's coordinate frame (DebugTools::ObjectRenderer3D: unit x / y / z axes in red /
+    green / blue) over a transparent background into an RGBA8 image. A debugging aid outside the render path: the three axis
+    segments are clipped at the near plane, projected with the scene's camera and drawn on the host."""
+    from PIL import Image, ImageDraw
+    W, H = scene._W, scene._H
+    img = Image.new("RGBA", (W, H), (0, 0, 0, 0))
+    draw = ImageDraw.Draw(img)
+    PV = scene._projection.astype(np.float64) @ inverted_rigid(scene._camera_pose).astype(np.float64)
+    near = 1e-3
+    for o in scene._objects:
+        M = PV @ o._pose.astype(np.float64)
+        for axis, col in ((0, (255, 0, 0, 255)), (1, (0, 255, 0, 255)), (2, (0, 0, 255, 255))):
+            a, b = M[:, 3].copy(), M[:, 3] + M[:, axis]
+            if a[3] < near and b[3] < near:
+                continue
+            if a[3] < near:
+                a = b + (a - b) * ((b[3] - near) / (b[3] - a[3]))
+            if b[3] < near:
+                b = a + (b - a) * ((a[3] - near) / (a[3] - b[3]))
+            pa, pb = a[:2] / a[3], b[:2] / b[3]
+            draw.line([((pa[0] + 1) * W / 2, (pa[1] + 1) * H / 2), ((pb[0] + 1) * W / 2, (pb[1] + 1) * H / 2)], fill=col, width=1)
+    t = torch.from_numpy(np.asarray(img).copy())
+    return t.to(f"cuda:{_cuda_index}") if _use_cuda else t
 
 
 from . import diff  # noqa: E402,F401  (sl.diff.backpropagate_gradient_to_poses etc., as the reference's stillleben.diff)

@@ -9,6 +9,11 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# tests/_ref holds the reference's own unittest files (staged, git-ignored); they run in their own interpreters from
+# test_gpu_reference_suite.py and must not be collected here
+collect_ignore = ["_ref"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -2,6 +2,7 @@
 import ctypes as C
 
 import numpy as np
+import pytest
 
 from stillleben_b200 import abi, desc, dist, synth
 
@@ -114,3 +115,38 @@ def test_oracle_recompute_normals_matches_float64_restating():
     expect = acc[ok] / np.linalg.norm(acc[ok], axis=1, keepdims=True)
     np.testing.assert_allclose(out["normal"][ok], expect, atol=2e-5)
     assert L.orc_mesh_update_positions_and_colors(h, np.array([0], np.int32).ctypes.data, 1, dpos.ctypes.data, None) == -1
+
+
+def test_quaternion_helpers_round_trip():
+    """py_magnum.cpp:83-113: [x y z w] <-> 3x3, every branch of Quaternion::fromMatrix."""
+    import torch
+    from stillleben_b200 import sl
+    rng = np.random.RandomState(3)
+    qs = [rng.normal(size=4) for _ in range(50)] + [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1], [0.7, 0.7, 0.01, 0.01]]
+    for q in qs:
+        q = np.asarray(q, np.float64) / np.linalg.norm(q)
+        R = sl.quat_to_matrix(torch.tensor(q, dtype=torch.float32))
+        assert torch.allclose(R @ R.T, torch.eye(3), atol=1e-5) and abs(float(torch.det(R)) - 1) < 1e-5
+        q2 = sl.matrix_to_quat(R).numpy().astype(np.float64)
+        assert min(np.abs(q2 - q).max(), np.abs(q2 + q).max()) < 1e-5
+    with pytest.raises(ValueError):
+        sl.quat_to_matrix(torch.zeros(3))
+
+
+def test_obj_front_end(tmp_path):
+    """objfile.load: (v, vt, vn) triples joined, quads fanned, negative indices, MTL colour + texture, generated normals."""
+    from PIL import Image
+    from stillleben_b200 import objfile
+    Image.fromarray(np.arange(4 * 4 * 3, dtype=np.uint8).reshape(4, 4, 3)).save(tmp_path / "t.png")
+    (tmp_path / "m.mtl").write_text("newmtl a\nKd 0.5 0.25 1\nmap_Kd t.png\nnewmtl b\nKd 1 0 0\nd 0.5\n")
+    (tmp_path / "m.obj").write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+                                    "usemtl a\nf 1/1/1 2/2/1 3/3/1 4/4/1\nusemtl b\nv 0 0 1\nv 1 0 1\nv 0 1 1\nf -3 -2 -1\n")
+    m = objfile.load(str(tmp_path / "m.obj"))
+    assert len(m.vertices) == 7 and m.submeshes == [(0, 6, 0), (6, 3, 1)]
+    assert m.indices.tolist() == [0, 1, 2, 0, 2, 3, 4, 5, 6]
+    assert m.vertices["vertex_index"].tolist() == list(range(1, 8))
+    assert np.allclose(m.vertices["normal"][:4], [0, 0, 1]) and np.allclose(m.vertices["normal"][4:], [0, 0, 1])     # generated
+    assert np.allclose(m.vertices["tangent"][:4], [1, 0, 0, 1]) and np.allclose(m.vertices["uv"][2], [1, 1])
+    assert m.materials[0].base_color == (0.5, 0.25, 1.0, 1.0) and m.materials[0].tex_base_color == 0
+    assert m.materials[1].base_color == (1.0, 0.0, 0.0, 0.5) and m.materials[1].tex_base_color == -1
+    assert m.images[0].pixels[0, 0].tolist() == [36, 37, 38]            # row 0 = bottom row of the picture

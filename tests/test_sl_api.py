@@ -44,10 +44,64 @@ def test_host_side_mesh_and_object_logic(monkeypatch):
     assert obj.instance_index == 1                                  # tests/basic.cpp:152
     assert scene.light_colors[0].tolist() == [300.0, 300.0, 300.0] and float(scene.light_directions.abs().sum()) == 0.0
     assert scene.manual_exposure < 0
-    with pytest.raises(RuntimeError):
-        scene.simulate_tabletop_scene()
+    with pytest.raises(RuntimeError, match="physics is not available"):
+        scene.simulate(0.002)
     with pytest.raises(ValueError, match="unknown shading"):       # py_render_pass.cpp:244
         sl.RenderPass("toon")
+
+
+def test_tabletop_placement_and_serialization(monkeypatch):
+    """Scene.serialize / deserialize (scene.cpp:761-868, tests/test_python.py:68-88) and the documented NON-physical stand-in
+    for simulate_tabletop_scene (scene.cpp:612-759): poses above the table, bounding spheres disjoint, plane pose set."""
+    import os
+    monkeypatch.setattr(sl, "_ctx", object())
+    path = os.path.join(os.path.dirname(__file__), "golden", "assets", "pbr_patch.glb")
+    scene = sl.Scene((640, 480))
+    scene.set_camera_intrinsics(1066.778, 1067.487, 312.9869, 241.3109)
+    scene.set_camera_look_at(torch.tensor([0.6, 0.1, 0.5]), torch.tensor([0.0, 0.0, 0.05]))
+    scene.ambient_light = torch.tensor([0.1, 0.2, 0.3])
+    scene.light_directions = torch.tensor([[0.1, 0.2, -0.9], [0, 0, 0], [0, 0, 0]])
+    scene.manual_exposure = 1.5
+    for k in range(4):
+        mesh = sl.Mesh(path)
+        mesh.center_bbox()
+        mesh.scale_to_bbox_diagonal(0.1 + 0.05 * k)
+        mesh.class_index = k + 3
+        o = sl.Object(mesh)
+        o.metallic, o.roughness, o.casts_shadows = 0.25 * k, 0.9 - 0.2 * k, bool(k % 2)
+        scene.add_object(o)
+    with pytest.warns(UserWarning, match="non-physical"):
+        scene.simulate_tabletop_scene()
+    spheres = []
+    for o in scene.objects:
+        c = o.pose() @ torch.cat([o.mesh.bbox.center, torch.ones(1)])
+        r = o.mesh.bbox.diagonal / 2
+        assert abs(float(c[2]) - (0.04 + r)) < 1e-5                      # resting on the table top
+        R = o.pose()[:3, :3]
+        assert torch.allclose(R @ R.T, torch.eye(3), atol=1e-5)
+        spheres.append((c[:3], r))
+    for i in range(4):
+        for j in range(i):
+            assert float(torch.linalg.norm(spheres[i][0] - spheres[j][0])) >= spheres[i][1] + spheres[j][1] - 1e-5
+    assert abs(float(scene.background_plane_pose[2, 3]) - 0.04) < 1e-7
+
+    text = scene.serialize()
+    assert "[object/mesh]" in text and text.count("[object]") == 4 and text.count("[light]") == 3
+    scene2 = sl.Scene((320, 240))
+    scene2.deserialize(text)
+    assert scene2.viewport == (640, 480)
+    np.testing.assert_allclose(scene2.projection_matrix().numpy(), scene.projection_matrix().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(scene2.camera_pose().numpy(), scene.camera_pose().numpy(), atol=1e-6)
+    np.testing.assert_allclose(scene2.light_directions.numpy(), scene.light_directions.numpy(), atol=1e-7)
+    np.testing.assert_allclose(scene2.background_plane_pose.numpy(), scene.background_plane_pose.numpy(), atol=1e-7)
+    assert scene2.manual_exposure == 1.5 and np.allclose(scene2.ambient_light.numpy(), [0.1, 0.2, 0.3])
+    for a, b in zip(scene.objects, scene2.objects):
+        assert float((a.pose() - b.pose()).norm()) < 1e-9                # tests/test_python.py:87
+        assert float((a.mesh.pretransform - b.mesh.pretransform).norm()) < 1e-5
+        assert (a.instance_index, a.mesh.class_index, a.casts_shadows) == (b.instance_index, b.mesh.class_index, b.casts_shadows)
+        assert abs(a.metallic - b.metallic) < 1e-7 and abs(a.roughness - b.roughness) < 1e-7
+    with pytest.raises(RuntimeError, match="mesh subgroup"):
+        sl.Scene((8, 8)).deserialize("[object]\npose=1 0 0 0 0 1 0 0 0 0 1 0 0 0 0 1\n")
 
 
 @pytest.mark.gpu
