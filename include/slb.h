@@ -405,6 +405,21 @@ size_t slb_png_bound(int32_t height, int32_t width, int32_t channels, int32_t by
 int slb_png_encode(slb_ctx* ctx, const void* images, int32_t n_images, int32_t height, int32_t width, int32_t channels,
                    int32_t bytes_per_channel, uint8_t* out, size_t out_stride, uint32_t* sizes, void* stream);
 
+/* ---- batched JPEG encoder (reference: src/image_saver.cpp:55-97 -> AnyImageConverter -> JpegImageConverter = libjpeg,
+ * jpeg_set_defaults + jpeg_set_quality(80): baseline, 4:2:0, slow-integer DCT, Annex K Huffman tables) ------------- */
+
+/* Upper bound of one encoded file for an image of the given shape (every block at its longest code, every byte stuffed). */
+size_t slb_jpeg_bound(int32_t height, int32_t width, int32_t channels);
+/* Encodes n images of identical shape into n complete JFIF files in DEVICE memory, byte-identical to what libjpeg writes for
+ * the same pixels and quality. images: n contiguous HxWxC uint8 arrays, C = 1 (grey), 3 (RGB) or 4 (RGBA: alpha ignored, as
+ * JpegImageConverter does); row 0 is the top row of the file. quality: 1..100 (the reference's converter default is 80).
+ * File i is written to out + i * out_stride and its size to sizes[i]. out_stride may be smaller than slb_jpeg_bound() (the
+ * worst case is several times the raw image; real files are a fraction of it): an image whose file does not fit gets
+ * sizes[i] = 0 and nothing is written beyond its stride — the caller retries that image with a larger stride.
+ * images / out / sizes are DEVICE pointers. */
+int slb_jpeg_encode(slb_ctx* ctx, const void* images, int32_t n_images, int32_t height, int32_t width, int32_t channels,
+                    int32_t quality, uint8_t* out, size_t out_stride, uint32_t* sizes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

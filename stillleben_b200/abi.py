@@ -157,6 +157,9 @@ PROTOTYPES = {
     "slb_png_bound": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "slb_png_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.c_void_p]),
+    "slb_jpeg_bound": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "slb_jpeg_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+                                  C.c_void_p, C.c_void_p]),
     "slb_diff_pose_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }

@@ -1,5 +1,6 @@
 // kernels.h — host-callable launchers of the CUDA kernels (one per translation unit below).
 #pragma once
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -67,5 +68,16 @@ size_t png_file_bound(int H, int W, int channels, int bpc);
 size_t png_row_info_bytes();
 void launch_png_encode(const uint8_t* images, int n, int H, int W, int channels, int bpc, uint8_t* rows_scratch, void* row_info,
                        uint32_t* row_offset, uint8_t* out, size_t out_stride, uint32_t* sizes, cudaStream_t s);
+
+
+// k_jpeg.cu
+size_t jpeg_stream_words(int H, int W, int channels);
+size_t jpeg_coef_bytes(int H, int W, int channels);
+size_t jpeg_blocks(int H, int W, int channels);
+size_t jpeg_file_bound(int H, int W, int channels);
+std::vector<uint8_t> jpeg_prepare(int H, int W, int channels, int quality, cudaStream_t s);
+void launch_jpeg_encode(const uint8_t* images, int n, int H, int W, int channels, int16_t* coefs, uint32_t* bit_off, uint32_t* total_bits,
+                        uint32_t* stream, const uint8_t* header_dev, int header_len, uint8_t* out, size_t out_stride, uint32_t* sizes,
+                        cudaStream_t s);
 
 }  // namespace slbk

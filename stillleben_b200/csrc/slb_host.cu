@@ -5,6 +5,7 @@
 // src/cuda_interop.cpp:83-208). No exception crosses the boundary; every entry point returns a status.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <ctime>
 #include <cstdlib>
@@ -128,6 +129,9 @@ struct slb_ctx {
     slb_mesh* plane = nullptr;
     Scratch scr[2];
     DevBuf diff_params, diff_partial, cam_params, cam_mid, png_rows, png_info, png_offsets;
+    DevBuf jpeg_coefs, jpeg_off, jpeg_total, jpeg_stream, jpeg_header;
+    int jpeg_key[4] = {0, 0, 0, 0};   // (H, W, channels, quality) the header / constant tables were built for
+    int jpeg_header_len = 0;
     bool png_tables = false;
     // timing
     struct Ev { int stage; cudaEvent_t a, b; };
@@ -272,7 +276,8 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
         if (ctx->slot_copied[i]) cudaEventDestroy(ctx->slot_copied[i]);
     }
     for (Scratch& S : ctx->scr) S.release();
-    DevBuf* bufs[] = {&ctx->diff_params, &ctx->diff_partial, &ctx->cam_params, &ctx->cam_mid, &ctx->png_rows, &ctx->png_info, &ctx->png_offsets};
+    DevBuf* bufs[] = {&ctx->diff_params, &ctx->diff_partial, &ctx->cam_params, &ctx->cam_mid, &ctx->png_rows, &ctx->png_info, &ctx->png_offsets,
+                      &ctx->jpeg_coefs, &ctx->jpeg_off, &ctx->jpeg_total, &ctx->jpeg_stream, &ctx->jpeg_header};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ctx->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -1665,6 +1670,50 @@ extern "C" int slb_png_encode(slb_ctx* ctx, const void* images, int32_t n_images
     launch_png_encode((const uint8_t*)images, n_images, height, width, channels, bytes_per_channel, ctx->png_rows.as<uint8_t>(), ctx->png_info.p,
                       ctx->png_offsets.as<uint32_t>(), out, out_stride, sizes, s);
     ctx->stats.kernel_launches += 3;
+    CU(cudaGetLastError());
+    return SLB_OK;
+}
+
+// ---- batched JPEG encoder ---------------------------------------------------------------------
+extern "C" size_t slb_jpeg_bound(int32_t height, int32_t width, int32_t channels) {
+    if (height <= 0 || width <= 0 || (channels != 1 && channels != 3 && channels != 4)) return 0;
+    return jpeg_file_bound(height, width, channels);
+}
+extern "C" int slb_jpeg_encode(slb_ctx* ctx, const void* images, int32_t n_images, int32_t height, int32_t width, int32_t channels,
+                               int32_t quality, uint8_t* out, size_t out_stride, uint32_t* sizes, void* stream) {
+    if (!ctx) return SLB_ERR_INVALID_ARGUMENT;
+    if (!images || !out || !sizes || n_images <= 0 || height <= 0 || width <= 0 || out_stride == 0)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_jpeg_encode: bad arguments");
+    if (channels != 1 && channels != 3 && channels != 4)   // JpegImageConverter: R8Unorm / RGB8Unorm (RGBA8Unorm with alpha dropped)
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_jpeg_encode: images must be uint8 HxW, HxWx3 or HxWx4");
+    if (height > 65535 || width > 65535) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_jpeg_encode: JPEG dimensions are limited to 65535");
+    if (quality < 1 || quality > 100) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_jpeg_encode: quality must be in 1..100");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = enter_stream(ctx, stream);
+    const int key[4] = {height, width, channels, quality};
+    if (memcmp(key, ctx->jpeg_key, sizeof(key)) != 0) {   // quantisation / Huffman tables in constant memory + the file header of this shape
+        const std::vector<uint8_t> header = jpeg_prepare(height, width, channels, quality, s);
+        CU(ctx->jpeg_header.reserve(header.size()));
+        CU(cudaMemcpyAsync(ctx->jpeg_header.p, header.data(), header.size(), cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));   // `header` is a local
+        ctx->jpeg_header_len = (int)header.size();
+        memcpy(ctx->jpeg_key, key, sizeof(key));
+    }
+    // scratch per image: coefficients (2 B each) + worst-case bit stream; batches are cut so the scratch stays below 512 MB
+    const size_t per_image = jpeg_coef_bytes(height, width, channels) + jpeg_stream_words(height, width, channels) * 4;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_images, ((size_t)512 << 20) / per_image));
+    CU(ctx->jpeg_coefs.reserve((size_t)chunk * jpeg_coef_bytes(height, width, channels)));
+    CU(ctx->jpeg_stream.reserve((size_t)chunk * jpeg_stream_words(height, width, channels) * 4));
+    CU(ctx->jpeg_off.reserve((size_t)chunk * jpeg_blocks(height, width, channels) * 4));
+    CU(ctx->jpeg_total.reserve((size_t)chunk * 4));
+    const size_t image_bytes = (size_t)height * width * channels;
+    for (int at = 0; at < n_images; at += chunk) {
+        const int n = std::min(chunk, n_images - at);
+        launch_jpeg_encode((const uint8_t*)images + (size_t)at * image_bytes, n, height, width, channels, ctx->jpeg_coefs.as<int16_t>(),
+                           ctx->jpeg_off.as<uint32_t>(), ctx->jpeg_total.as<uint32_t>(), ctx->jpeg_stream.as<uint32_t>(),
+                           ctx->jpeg_header.as<uint8_t>(), ctx->jpeg_header_len, out + (size_t)at * out_stride, out_stride, sizes + at, s);
+        ctx->stats.kernel_launches += 4;
+    }
     CU(cudaGetLastError());
     return SLB_OK;
 }

@@ -9,6 +9,9 @@ here the images are ENCODED ON THE GPU in batches (`slb_png_encode`: one standar
 device memory) and only the finished files cross PCIe; a small thread pool writes them to disk. `save()`
 returns immediately; files are complete when the `with` block exits (as in the reference).
 `encode_batch()` is the batched extension: [n, H, W(, C)] tensor -> list of `bytes`.
+File names ending in .jpg / .jpeg are written as baseline JPEG (`slb_jpeg_encode`: the bytes libjpeg writes at the reference's
+converter default, quality 80), everything else as PNG — the choice AnyImageConverter makes from the extension
+(src/image_saver.cpp:55-97).
 """
 import os
 from concurrent.futures import ThreadPoolExecutor
@@ -59,6 +62,43 @@ def encode_batch(images):
     return [host[i, :sz[i]].tobytes() for i in range(n)]
 
 
+def encode_batch_jpeg(images, quality=80):
+    """images: uint8 [n,H,W], [n,H,W,3] or [n,H,W,4] (alpha ignored), any device -> list of n JFIF files (bytes)."""
+    ctx = _sl._context()
+    dev = torch.device("cuda", _sl._cuda_index)
+    if images.dtype != torch.uint8:
+        raise ValueError("JPEG images need to have type uint8")          # JpegImageConverter: R8Unorm / RGB8Unorm only
+    if images.dim() == 3:
+        channels = 1
+    elif images.dim() == 4 and images.size(3) in (3, 4):
+        channels = images.size(3)
+    else:
+        raise ValueError("Color images need to have shape HxWx3 or HxWx4")
+    x = images.to(dev).contiguous()
+    n, H, W = x.shape[0], x.shape[1], x.shape[2]
+    bound = ctx.lib.slb_jpeg_bound(H, W, channels)
+    stride = min(bound, H * W * channels // 2 + 4096)      # real files are a fraction of the raw image; the bound is the retry size
+    while True:
+        stride = (stride + 255) // 256 * 256
+        out = torch.empty((n, stride), dtype=torch.uint8, device=dev)
+        sizes = torch.empty((n,), dtype=torch.int32, device=dev)
+        rc = ctx.lib.slb_jpeg_encode(ctx.h, x.data_ptr(), n, H, W, channels, int(quality), out.data_ptr(), stride, sizes.data_ptr(), _stream(ctx))
+        if rc != 0:
+            raise RuntimeError(ctx.lib.slb_last_error(ctx.h).decode())
+        ctx.synchronize()
+        sz = sizes.cpu().tolist()
+        if min(sz) > 0 or stride >= bound:
+            break
+        stride = bound                                     # some file did not fit (sizes[i] == 0): once more with the worst case
+    top = max(sz)
+    host = out[:, :top].cpu().numpy()
+    return [host[i, :sz[i]].tobytes() for i in range(n)]
+
+
+def _is_jpeg(path):
+    return path.lower().endswith((".jpg", ".jpeg"))
+
+
 class ImageSaver:
     MAX_PENDING = 64
 
@@ -87,6 +127,8 @@ class ImageSaver:
                 raise ValueError("Grayscale images need to be byte or short type")
         else:
             raise ValueError("Color images need to have shape HxWx3 or HxWx4")
+        if _is_jpeg(os.fspath(path)) and input.dtype != torch.uint8:
+            raise ValueError("JPEG images need to have type uint8")
         self._pending.append((input.detach().clone(), os.fspath(path)))      # a snapshot, like input.flipud() in py_image_saver.cpp:44
         if len(self._pending) >= self.MAX_PENDING:
             self._flush()
@@ -94,10 +136,11 @@ class ImageSaver:
     def _flush(self):
         groups = {}
         for t, p in self._pending:
-            groups.setdefault((tuple(t.shape), t.dtype), []).append((t, p))
+            groups.setdefault((tuple(t.shape), t.dtype, _is_jpeg(p)), []).append((t, p))
         self._pending = []
-        for items in groups.values():
-            files = encode_batch(torch.stack([t for t, _ in items]))
+        for (_, _, jpeg), items in groups.items():
+            batch = torch.stack([t for t, _ in items])
+            files = encode_batch_jpeg(batch) if jpeg else encode_batch(batch)
             for data, (_, p) in zip(files, items):
                 self._futures.append(self._pool.submit(_write, p, data))
 
