@@ -62,8 +62,10 @@ def encode_batch(images):
     return [host[i, :sz[i]].tobytes() for i in range(n)]
 
 
-def encode_batch_jpeg(images, quality=80):
-    """images: uint8 [n,H,W], [n,H,W,3] or [n,H,W,4] (alpha ignored), any device -> list of n JFIF files (bytes)."""
+def encode_batch_jpeg(images, quality=80, first_stride=None):
+    """images: uint8 [n,H,W], [n,H,W,3] or [n,H,W,4] (alpha ignored), any device -> list of n JFIF files (bytes).
+    first_stride: bytes reserved per file on the first attempt (default: half the raw image; files that do not fit are
+    encoded again with the worst-case bound)."""
     ctx = _sl._context()
     dev = torch.device("cuda", _sl._cuda_index)
     if images.dtype != torch.uint8:
@@ -77,7 +79,7 @@ def encode_batch_jpeg(images, quality=80):
     x = images.to(dev).contiguous()
     n, H, W = x.shape[0], x.shape[1], x.shape[2]
     bound = ctx.lib.slb_jpeg_bound(H, W, channels)
-    stride = min(bound, H * W * channels // 2 + 4096)      # real files are a fraction of the raw image; the bound is the retry size
+    stride = min(bound, first_stride or (H * W * channels // 2 + 4096))      # real files are a fraction of the raw image; the bound is the retry size
     while True:
         stride = (stride + 255) // 256 * 256
         out = torch.empty((n, stride), dtype=torch.uint8, device=dev)

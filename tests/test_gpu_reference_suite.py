@@ -29,12 +29,23 @@ def _run(args, cwd):
 @pytest.mark.parametrize("name", ["test_render", "test_serialization", "test_image_saver"])
 def test_reference_test_python(name):
     r = _run(["-m", "unittest", "-v", f"test_python.PythonTest.{name}"], REF)
+    if name == "test_image_saver" and r.returncode != 0:
+        # test_python.py:109 expects PIL to open a 16-bit PNG as int32 (Pillow < 10 reported mode "I"); Pillow >= 10 reports
+        # "I;16" = uint16 for the same file, so with this image's Pillow 12 that one line fails for the reference as well.
+        # Everything before it (three files written, 8-bit shapes / dtypes, 16-bit shape) must have passed.
+        assert "dtype('uint16') != <class 'numpy.int32'>" in r.stderr and r.stderr.count("Error") == 1, r.stdout + r.stderr
+        from PIL import Image
+        g16 = np.asarray(Image.open("/tmp/test_gray16.png"))
+        assert g16.shape == (640, 480) and g16.dtype == np.uint16 and not g16.any()
+        return
     assert r.returncode == 0, r.stdout + r.stderr
     if name == "test_render":
         from PIL import Image
         img = np.asarray(Image.open("/tmp/stillleben.png"))
         assert img.shape == (480, 640, 4)
-        assert (img[..., 3] == 255).sum() > 5000 and img[..., :3].std() > 5       # the bunny is there (alpha 255 where it covers)
+        # the scene of test_render has no light (Scene defaults: all light directions zero) and a white background that the
+        # reference clears with alpha 0: the bunny shows as alpha 255 (black), the background as alpha 0
+        assert 20000 < (img[..., 3] == 255).sum() < 200000 and ((img[..., 3] == 0) | (img[..., 3] == 255)).all()
         dbg = np.asarray(Image.open("/tmp/stillleben_debug.png"))
         assert dbg.shape == (480, 640, 4) and dbg[..., 3].max() == 255 and dbg[0, 0, 3] == 0
 
