@@ -10,13 +10,15 @@ from stillleben_b200 import abi, lib, synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--scenes", type=int, default=256)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--config", default="C3")
 ap.add_argument("configs", nargs="*", default=["default="])
 a = ap.parse_args()
 ctx = lib.Context(0)
-pool = synth.mesh_pool(bench.POOL)
-scenes = bench.build_scenes(pool, 0, a.scenes)
+pool = bench.build_pool()
+cfg = bench.CONFIGS[a.config]
+scenes = bench.build_scenes(a.config, pool, bench.build_light_map(a.config), 0, a.scenes)
 descs = ctx.descs(scenes)
-res = lib.Result(ctx, bench.W, bench.H, a.scenes, abi.TARGETS_SIX)
+res = lib.Result(ctx, cfg["W"], cfg["H"], a.scenes, abi.TARGETS_SIX)
 ctx.set_option(abi.OPT_TIME_KERNELS, 1)
 names = ["clear", "bin_count", "scan", "emit", "raster", "shade", "ssao", "post"]
 OPTS = {n[4:].lower(): getattr(abi, n) for n in dir(abi) if n.startswith("OPT_")}
