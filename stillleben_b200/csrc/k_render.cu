@@ -326,7 +326,7 @@ __device__ __forceinline__ void raster_direct(int ax, int ay, int bx, int by, in
 // PASS 1 — triangle setup: one thread per triangle, one block per 256-triangle chunk of one draw (camera or
 // shadow view). Transforms, clips, snaps (contract C1-C6), counts the (tile, sub-triangle) pairs per tile and
 // appends every surviving sub-triangle, already snapped, to the compact survivors[] array.
-__global__ void __launch_bounds__(SLB_SETUP_CHUNK, 5) k_setup(const DView* __restrict__ views, const DFrame* __restrict__ frames,
+__global__ void __launch_bounds__(SLB_SETUP_CHUNK, SLB_SETUP_MINB) k_setup(const DView* __restrict__ views, const DFrame* __restrict__ frames,
                                                               const DBinDraw* __restrict__ bdraws, const uint32_t* __restrict__ chunk_draw,
                                                               uint32_t* __restrict__ tile_count, const SurvOut so, int direct_max, int warp_max) {
     __shared__ float s_mvp[16];

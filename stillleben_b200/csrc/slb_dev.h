@@ -12,7 +12,12 @@
 #include "../../include/slb.h"
 
 #define SLB_TILE 8                 // fine-raster tile: 8x8 pixels, one warp, two pixels per lane
+#ifndef SLB_SETUP_CHUNK
 #define SLB_SETUP_CHUNK 256        // triangles per block in the setup/bin kernels
+#endif
+#ifndef SLB_SETUP_MINB
+#define SLB_SETUP_MINB 5           // resident set-up blocks per SM the register budget is chosen for (48 registers at 256 threads)
+#endif
 #define SLB_MAX_LEVELS 16
 
 struct DTexture {
