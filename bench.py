@@ -210,6 +210,22 @@ def measure_d2h(torch, dev, n_bytes=1 << 28, reps=4):
     return best
 
 
+def measure_d2h_sustained(torch, dev, barrier, n_bytes=1 << 28, reps=8):
+    """Pinned device->host bandwidth of this rank WHILE every rank copies (barrier, then `reps` back-to-back copies timed as
+    one interval): what a rank's link delivers under the contention the end-to-end path sees. GB/s."""
+    src = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+    dst = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+    dst.copy_(src, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return reps * n_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -309,15 +325,30 @@ def main():
     # ---- end to end: host descriptors in, all six targets back in pinned host memory ----
     e2e = None
     if not args.no_e2e:
-        d2h_gbs = measure_d2h(torch, dev)                                    # this rank alone (the ranks probe concurrently at N > 1)
-        chunk = min(c["e2e_chunk"], n_local)                                 # scenes per call
+        # The host-buffer path is bound by each rank's device->host link, and on a multi-GPU box the links are NOT equal while all
+        # ranks copy (profiles/r02_multi_gpu.md: 11.6 vs 18.2 GB/s at 8 GPUs): the fixed batch is sharded in proportion to the
+        # sustained bandwidth every rank measures under that contention, so that all ranks finish together.
+        e2e_scenes, shard_sizes = scenes, [n_local]
+        if world > 1:
+            d2h_gbs = measure_d2h_sustained(torch, dev, barrier)
+            bw = torch.tensor([d2h_gbs], dtype=torch.float64, device=dev)
+            allbw = [torch.zeros_like(bw) for _ in range(world)]
+            dist.all_gather(allbw, bw)
+            weights = [float(x.item()) for x in allbw]
+            shard_sizes = sdist.shard_sizes_weighted(n_scenes, weights)
+            lo_e, hi_e = sdist.shard_range_weighted(n_scenes, rank, weights)
+            e2e_scenes = build_scenes(args.config, pool, light_map, lo_e, hi_e)
+        else:
+            d2h_gbs = measure_d2h(torch, dev)
+        n_e2e = len(e2e_scenes)                                              # (the device-resident leg above keeps the equal shards)
+        chunk = max(1, min(c["e2e_chunk"], n_e2e))                         # scenes per call
         host = {}
         for tgt, (dt_, ch) in enumerate(abi.TARGET_FORMATS):
             if abi.TARGETS_SIX & (1 << tgt):
                 host[tgt] = ctx.host_alloc((chunk, H, W, ch), dt_)          # page-locked (slb_host_alloc)
         host_ptrs = {k: v.ctypes.data for k, v in host.items()}
-        chunk_descs = [ctx.descs(scenes[a:a + chunk]) for a in range(0, n_local, chunk)]
-        d2h = n_local * W * H * BYTES_PER_PX
+        chunk_descs = [ctx.descs(e2e_scenes[a:a + chunk]) for a in range(0, n_e2e, chunk)]
+        d2h = n_e2e * W * H * BYTES_PER_PX
         h2d0 = ctx.stats().bytes_h2d
 
         def e2e_step():
@@ -333,13 +364,16 @@ def main():
         torch.cuda.synchronize()
         dt_e2e = time.perf_counter() - t0
         t = torch.tensor([dt_e2e, -d2h_gbs], dtype=torch.float64, device=dev)
+        tot = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         e2e_fps = n_scenes * args.steps / float(t[0].item())
         link = -float(t[1].item())                                           # the slowest rank's link
         per_gpu_gbs = e2e_fps / world * W * H * BYTES_PER_PX / 1e9
-        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
                "d2h_link_gbs": link, "d2h_achieved_gbs_per_gpu": per_gpu_gbs, "frac_of_d2h_link": per_gpu_gbs / link if link else None,
+               "shard_sizes": shard_sizes, "sharding": "equal" if world == 1 else "proportional to each rank's sustained D2H bandwidth measured while all ranks copy",
                "note": f"slb_render_batch_host, page-locked host buffers (slb_host_alloc), {chunk}-scene calls; every frame returns "
                        f"{W * H * BYTES_PER_PX / 1e6:.2f} MB over the device->host link, whose pinned-copy bandwidth (d2h_link_gbs, "
                        "measured in this process; the minimum over ranks probing at the same time) bounds this number"}

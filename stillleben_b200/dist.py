@@ -23,6 +23,30 @@ def shard_range(n_items, rank, world_size):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def shard_sizes_weighted(n_items, weights):
+    """Shard sizes proportional to `weights` (largest-remainder rounding, every rank with a positive weight gets at least one
+    item when there are enough). For the host-buffer path on a box whose GPUs do not see the same device->host bandwidth
+    (PCIe switches shared by different numbers of GPUs): a shard's wall time is its bytes over its link, so equal TIME per
+    rank means sizes proportional to the links."""
+    w = [max(float(x), 0.0) for x in weights]
+    total = sum(w)
+    if total <= 0.0:
+        w, total = [1.0] * len(w), float(len(w))
+    exact = [n_items * x / total for x in w]
+    sizes = [int(e) for e in exact]
+    order = sorted(range(len(w)), key=lambda i: (exact[i] - sizes[i], w[i]), reverse=True)
+    for i in order[:n_items - sum(sizes)]:
+        sizes[i] += 1
+    return sizes
+
+
+def shard_range_weighted(n_items, rank, weights):
+    """Contiguous block of scene indices owned by `rank` when the blocks are sized by shard_sizes_weighted()."""
+    sizes = shard_sizes_weighted(n_items, weights)
+    start = sum(sizes[:rank])
+    return start, start + sizes[rank]
+
+
 def env_rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 

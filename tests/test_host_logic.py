@@ -150,3 +150,23 @@ def test_obj_front_end(tmp_path):
     assert m.materials[0].base_color == (0.5, 0.25, 1.0, 1.0) and m.materials[0].tex_base_color == 0
     assert m.materials[1].base_color == (1.0, 0.0, 0.0, 0.5) and m.materials[1].tex_base_color == -1
     assert m.images[0].pixels[0, 0].tolist() == [36, 37, 38]            # row 0 = bottom row of the picture
+
+
+def test_weighted_sharding():
+    """dist.shard_sizes_weighted / shard_range_weighted: sizes proportional to the ranks' link bandwidths, exact total,
+    contiguous and disjoint ranges; equal weights reproduce shard_range."""
+    w8 = [11.58, 11.59, 11.59, 11.61, 18.15, 18.2, 18.23, 18.26]          # profiles/r02_d2h_probe_n8.json
+    sizes = dist.shard_sizes_weighted(1024, w8)
+    assert sum(sizes) == 1024 and all(abs(s - 1024 * w / sum(w8)) < 1.0 for s, w in zip(sizes, w8))
+    # equal time per rank: bytes over bandwidth within one scene of each other
+    t = [s / w for s, w in zip(sizes, w8)]
+    assert max(t) - min(t) <= 1.0 / min(w8) + 1e-9
+    ranges = [dist.shard_range_weighted(1024, r, w8) for r in range(8)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == 1024 and all(ranges[r][1] == ranges[r + 1][0] for r in range(7))
+    for n, world in ((1024, 8), (10, 4), (3, 8), (0, 2)):
+        assert [dist.shard_range_weighted(n, r, [1.0] * world) for r in range(world)] != [] and \
+            sum(dist.shard_sizes_weighted(n, [1.0] * world)) == n
+        assert sorted(dist.shard_sizes_weighted(n, [1.0] * world), reverse=True) == sorted((dist.shard_range(n, r, world)[1] - dist.shard_range(n, r, world)[0]
+                                                                                            for r in range(world)), reverse=True)
+    assert dist.shard_sizes_weighted(7, [0.0, 0.0]) in ([4, 3], [3, 4])                                # degenerate weights: equal shards
+    assert dist.shard_sizes_weighted(5, [1.0, 0.0, 3.0]) == [1, 0, 4]
