@@ -8,6 +8,8 @@
 #include <stdint.h>
 
 #include "k_frag.cuh"
+#include <type_traits>
+
 #include "kernels.h"
 
 using namespace slbk;
@@ -22,10 +24,14 @@ __device__ __forceinline__ float rect_linear_z(const float* __restrict__ img, in
     float fx = floorf(x), fy = floorf(y);
     float a = x - fx, b = y - fy;
     int i0 = (int)fx, j0 = (int)fy;
-    int i1 = min(max(i0 + 1, 0), W - 1), j1 = min(max(j0 + 1, 0), H - 1);
-    i0 = min(max(i0, 0), W - 1); j0 = min(max(j0, 0), H - 1);
-    float z00 = __ldg(&img[(size_t)j0 * W + i0]), z10 = __ldg(&img[(size_t)j0 * W + i1]);
-    float z01 = __ldg(&img[(size_t)j1 * W + i0]), z11 = __ldg(&img[(size_t)j1 * W + i1]);
+    // clamp-to-edge: min(max(i, 0), n - 1) as ONE instruction each (VIMNMX with the relu modifier)
+    const int i1 = __vimin_s32_relu(i0 + 1, W - 1), j1 = __vimin_s32_relu(j0 + 1, H - 1);
+    i0 = __vimin_s32_relu(i0, W - 1); j0 = __vimin_s32_relu(j0, H - 1);
+    // texel offsets as UNSIGNED 32-bit values (a frame is far below 2^32 pixels): one IMAD.WIDE.U32 per address instead of a
+    // sign-extended 64-bit add chain
+    const unsigned r0 = (unsigned)(j0 * W), r1 = (unsigned)(j1 * W);
+    float z00 = __ldg(img + (r0 + (unsigned)i0)), z10 = __ldg(img + (r0 + (unsigned)i1));
+    float z01 = __ldg(img + (r1 + (unsigned)i0)), z11 = __ldg(img + (r1 + (unsigned)i1));
     return z00 * ((1 - a) * (1 - b)) + z10 * (a * (1 - b)) + z01 * ((1 - a) * b) + z11 * (a * b);
 }
 
@@ -83,6 +89,9 @@ __global__ void k_downsample(const float4* __restrict__ src, int sw, int sh, flo
     dst[blockIdx.z * dst_stride + (size_t)y * dw + x] = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
 }
 
+// 1 / y as ONE MUFU.RCP (flush-to-zero approximate reciprocal, the instruction the compiler's fast division is built around,
+// without its range fix-up for denormal or > 2^126 operands: there the SSAO results are clamped / irrelevant)
+__device__ __forceinline__ float rcp_fast(float y) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y)); return r; }
 __device__ __forceinline__ float smoothstep01(float x) { float t = clampf(x, 0.0f, 1.0f); return t * t * (3.0f - 2.0f * t); }
 
 __global__ void __launch_bounds__(256) k_ssao(const DFrame* __restrict__ frames) {
@@ -116,18 +125,24 @@ __global__ void __launch_bounds__(256) k_ssao(const DFrame* __restrict__ frames)
     }
     const float zt = 0.1f * tangent.z, zb = 0.1f * bitangent.z, zn = 0.1f * normal.z;
     const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+    // A pinhole projection has the last row (0, 0, 1, 0): then w of the projected sample IS its camera z (base[2] = fragPos.z,
+    // ct[2] = zt, ... bit for bit: multiplications by 0 and 1), and its three FMAs per tap are dropped. Uniform per frame.
+    const bool pinhole_w = P[3] == 0.0f && P[7] == 0.0f && P[11] == 1.0f && P[15] == 0.0f;
     float occlusion = 0.0f;
+    auto taps = [&](auto pinhole) {
 #pragma unroll 4
-    for (int i = 0; i < 64; ++i) {
-        const float sx = c_ssao_kernel[i * 3], sy = c_ssao_kernel[i * 3 + 1], sz = c_ssao_kernel[i * 3 + 2];
-        const float ox = base[0] + ct[0] * sx + cb[0] * sy + cn[0] * sz, oy = base[1] + ct[1] * sx + cb[1] * sy + cn[1] * sz;
-        const float ow = base[2] + ct[2] * sx + cb[2] * sy + cn[2] * sz;
-        const float sample_z = fragPos.z + zt * sx + zb * sy + zn * sz;
-        const float inv = 1.0f / ow;
-        float sampleDepth = rect_linear_z(f.zplane, W, H, ox * inv * hw + hw, oy * inv * hh + hh);
-        float rangeCheck = smoothstep01(0.1f / fabsf(fragPos.z - sampleDepth));
-        occlusion += (sampleDepth <= sample_z - 0.0025f ? 1.0f : 0.0f) * rangeCheck;
-    }
+        for (int i = 0; i < 64; ++i) {
+            const float sx = c_ssao_kernel[i * 3], sy = c_ssao_kernel[i * 3 + 1], sz = c_ssao_kernel[i * 3 + 2];
+            const float ox = base[0] + ct[0] * sx + cb[0] * sy + cn[0] * sz, oy = base[1] + ct[1] * sx + cb[1] * sy + cn[1] * sz;
+            const float sample_z = fragPos.z + zt * sx + zb * sy + zn * sz;
+            const float ow = decltype(pinhole)::value ? sample_z : base[2] + ct[2] * sx + cb[2] * sy + cn[2] * sz;
+            const float inv = rcp_fast(ow);
+            float sampleDepth = rect_linear_z(f.zplane, W, H, ox * inv * hw + hw, oy * inv * hh + hh);
+            float rangeCheck = smoothstep01(0.1f * rcp_fast(fabsf(fragPos.z - sampleDepth)));
+            occlusion += (sampleDepth <= sample_z - 0.0025f ? 1.0f : 0.0f) * rangeCheck;
+        }
+    };
+    if (pinhole_w) taps(std::true_type{}); else taps(std::false_type{});
     f.ao[p] = 1.0f - (occlusion / 64.0f);
 }
 
@@ -139,14 +154,36 @@ __global__ void __launch_bounds__(256) k_ssao_apply_tonemap(const DFrame* __rest
     const size_t p = (size_t)py * W + px;
     float4 hdr = f.hdr[p];
     if (f.ssao) {
-        float center_d = rect_linear_z(f.zplane, W, H, (float)px, (float)py);
+        // The 16 taps and the centre read the z plane at INTEGER rectangle coordinates, i.e. on texel corners: each is the
+        // bilinear mean (weights exactly 1/4) of a 2x2 texel block, and the 17 blocks share a 5x5 neighbourhood. Load those
+        // 25 clamped texels once (instead of 68 loads with their own clamps) and form every depth with the summation order of
+        // rect_linear_z — bit-identical.
+        float z[5][5];
+        {
+            unsigned col[5], row[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                col[k] = (unsigned)__vimin_s32_relu(px - 3 + k, W - 1);
+                row[k] = (unsigned)(__vimin_s32_relu(py - 3 + k, H - 1) * W);
+            }
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+#pragma unroll
+                for (int i = 0; i < 5; ++i) z[j][i] = __ldg(f.zplane + (row[j] + col[i]));
+        }
+        auto corner_z = [&](int x, int y) {   // rect_linear_z(px + x, py + y): texels (px+x-1 .. px+x) x (py+y-1 .. py+y)
+            return __fmaf_rn(z[y + 3][x + 3], 0.25f, __fmaf_rn(z[y + 3][x + 2], 0.25f, __fmaf_rn(z[y + 2][x + 3], 0.25f, z[y + 2][x + 2] * 0.25f)));
+        };
+        const float center_d = corner_z(0, 0);
         float result = 0.0f, w_total = 0.0f;
         const float BlurSigma = 3.0f * 0.5f, BlurFalloff = 1.0f / (2.0f * BlurSigma * BlurSigma);
+#pragma unroll
         for (int x = -2; x < 2; ++x)
+#pragma unroll
             for (int y = -2; y < 2; ++y) {
                 int ux = px + x, uy = py + y;
                 float c = (ux >= 0 && ux < W && uy >= 0 && uy < H) ? f.ao[(size_t)uy * W + ux] : 0.0f;
-                float dd = rect_linear_z(f.zplane, W, H, (float)ux, (float)uy);
+                float dd = corner_z(x, y);
                 float r = sqrtf((float)(x * x + y * y));
                 float ddiff = (dd - center_d) * 300.0f;
                 float w = exp2f(-r * r * BlurFalloff - ddiff * ddiff);
