@@ -1052,8 +1052,11 @@ void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W,
     // even with ~150 B of spills.
     // `lean`: no material textures beyond base colour, no stickers, no light map, affine chains only (see fragment_stage)
     k_huge_prepare<<<n_frames, 32, 0, s>>>(frames, draws);   // no-op for frames without huge records
-    if (lean) k_shade<256, 4, true><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
-    else k_shade<256, 4, false><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
+#ifndef SLB_SHADE_MINB
+#define SLB_SHADE_MINB 4
+#endif
+    if (lean) k_shade<256, SLB_SHADE_MINB, true><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
+    else k_shade<256, SLB_SHADE_MINB, false><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
 }
 
 }  // namespace slbk
