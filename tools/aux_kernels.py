@@ -43,6 +43,10 @@ if os.environ.get("SLB_AUX_TIMING", "1") == "1" and "--no-timing" not in sys.arg
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
+    # a NON-default stream: the legacy default stream's handle is 0, which the ABI reads as "the context's own stream" —
+    # the kernels would then not run on the stream the timing events are recorded on
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
     n = rgb.shape[0]
     # device-side encode only (the files stay in HBM): the ABI calls behind encode_batch / encode_batch_jpeg
     png_out = torch.empty((n, ctx.lib.slb_png_bound(480, 640, 4, 1)), dtype=torch.uint8, device="cuda")
