@@ -88,7 +88,8 @@ struct JpegGeom {
     int n_blocks;         // blocks per image in scan order
 };
 
-__constant__ uint16_t c_div[2][64];      // 8 * Q in NATURAL order (jcdctmgr.c divisors)
+// (the quantisation divisors depend on the quality and travel as a kernel PARAMETER, JpegQuant: contexts / streams encoding at
+// different qualities never share state; the Huffman tables below are the same for every call)
 __constant__ uint32_t c_huff[4][256];    // DC luma, AC luma, DC chroma, AC chroma: code << 8 | length
 
 #define DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
@@ -123,7 +124,8 @@ __device__ __forceinline__ void block_pos(const JpegGeom& g, int b, int& comp, i
     else { comp = k - 3; bx = mx; by = my; }
 }
 
-__global__ void __launch_bounds__(128) k_jpeg_blocks(const uint8_t* __restrict__ images, JpegGeom g, int n_images, int16_t* __restrict__ coefs) {
+__global__ void __launch_bounds__(128) k_jpeg_blocks(const uint8_t* __restrict__ images, JpegGeom g, const JpegQuant q, int n_images,
+                                                     int16_t* __restrict__ coefs) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n_images * g.n_blocks) return;
     const int img = (int)(t / g.n_blocks), b = (int)(t - (long long)img * g.n_blocks);
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(128) k_jpeg_blocks(const uint8_t* __restrict__
     const int qt = comp ? 1 : 0;
     int16_t z[64];
     // zigzag position k <- natural index (static indices: d[] and z[] stay in registers)
-#define Q(k, nat) { const int v = d[nat], dv = c_div[qt][nat]; const int mag = (abs(v) + (dv >> 1)) / dv; z[k] = (int16_t)(v < 0 ? -mag : mag); }
+#define Q(k, nat) { const int v = d[nat], dv = q.div[qt][nat]; const int mag = (abs(v) + (dv >> 1)) / dv; z[k] = (int16_t)(v < 0 ? -mag : mag); }
     Q(0, 0) Q(1, 1) Q(2, 8) Q(3, 16) Q(4, 9) Q(5, 2) Q(6, 3) Q(7, 10)
     Q(8, 17) Q(9, 24) Q(10, 32) Q(11, 25) Q(12, 18) Q(13, 11) Q(14, 4) Q(15, 5)
     Q(16, 12) Q(17, 19) Q(18, 26) Q(19, 33) Q(20, 40) Q(21, 48) Q(22, 41) Q(23, 34)
@@ -391,19 +393,17 @@ size_t jpeg_file_bound(int H, int W, int channels) { return 1024 + jpeg_stream_w
 
 // tables for `quality` into constant memory; returns the file header (jcmarker.c: write_file_header, write_frame_header,
 // write_scan_header) for images of this shape
-std::vector<uint8_t> jpeg_prepare(int H, int W, int channels, int quality, cudaStream_t s) {
+std::vector<uint8_t> jpeg_prepare(int H, int W, int channels, int quality, JpegQuant* quant, cudaStream_t s) {
     const int ncomp = channels == 1 ? 1 : 3;
     uint8_t q[2][64];
     quant_table(kLumaQ, quality, q[0]);
     quant_table(kChromaQ, quality, q[1]);
-    uint16_t div[2][64];
-    for (int t = 0; t < 2; ++t) for (int i = 0; i < 64; ++i) div[t][i] = (uint16_t)(q[t][i] * 8);
-    static uint32_t lut[4][256];
+    for (int t = 0; t < 2; ++t) for (int i = 0; i < 64; ++i) quant->div[t][i] = (uint16_t)(q[t][i] * 8);   // 8 * Q in NATURAL order (jcdctmgr.c divisors)
+    uint32_t lut[4][256];
     derive(kDcLumaBits, kDcVals, lut[0]); derive(kAcLumaBits, kAcLumaVals, lut[1]);
     derive(kDcChromaBits, kDcVals, lut[2]); derive(kAcChromaBits, kAcChromaVals, lut[3]);
-    cudaMemcpyToSymbolAsync(c_div, div, sizeof(div), 0, cudaMemcpyHostToDevice, s);
     cudaMemcpyToSymbolAsync(c_huff, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, s);
-    cudaStreamSynchronize(s);   // the host arrays above are stack / static storage
+    cudaStreamSynchronize(s);   // the host array above is stack storage
 
     std::vector<uint8_t> h = {0xFF, 0xD8};
     put_marker(h, 0xE0, {'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0});
@@ -430,14 +430,14 @@ std::vector<uint8_t> jpeg_prepare(int H, int W, int channels, int quality, cudaS
     return h;
 }
 
-void launch_jpeg_encode(const uint8_t* images, int n, int H, int W, int channels, int16_t* coefs, uint32_t* bit_off, uint32_t* total_bits,
+void launch_jpeg_encode(const uint8_t* images, int n, int H, int W, int channels, const JpegQuant& quant, int16_t* coefs, uint32_t* bit_off, uint32_t* total_bits,
                         uint32_t* stream, const uint8_t* header_dev, int header_len, uint8_t* out, size_t out_stride, uint32_t* sizes,
                         cudaStream_t s) {
     const JpegGeom g = make_geom(H, W, channels);
     const size_t words = jpeg_stream_words(H, W, channels);
     const long long total = (long long)n * g.n_blocks;
     cudaMemsetAsync(stream, 0, (size_t)n * words * 4, s);
-    k_jpeg_blocks<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(images, g, n, coefs);
+    k_jpeg_blocks<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(images, g, quant, n, coefs);
     k_jpeg_scan<<<n, 1024, 0, s>>>(g, coefs, bit_off, total_bits);
     k_jpeg_emit<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(g, n, coefs, bit_off, stream, words);
     k_jpeg_finish<<<n, 1024, 0, s>>>(stream, words, total_bits, header_dev, header_len, out, out_stride, sizes);

@@ -75,8 +75,9 @@ size_t jpeg_stream_words(int H, int W, int channels);
 size_t jpeg_coef_bytes(int H, int W, int channels);
 size_t jpeg_blocks(int H, int W, int channels);
 size_t jpeg_file_bound(int H, int W, int channels);
-std::vector<uint8_t> jpeg_prepare(int H, int W, int channels, int quality, cudaStream_t s);
-void launch_jpeg_encode(const uint8_t* images, int n, int H, int W, int channels, int16_t* coefs, uint32_t* bit_off, uint32_t* total_bits,
+struct JpegQuant { uint16_t div[2][64]; };   // quantisation divisors (8 * Q, natural order) of one quality: a kernel parameter
+std::vector<uint8_t> jpeg_prepare(int H, int W, int channels, int quality, JpegQuant* quant, cudaStream_t s);
+void launch_jpeg_encode(const uint8_t* images, int n, int H, int W, int channels, const JpegQuant& quant, int16_t* coefs, uint32_t* bit_off, uint32_t* total_bits,
                         uint32_t* stream, const uint8_t* header_dev, int header_len, uint8_t* out, size_t out_stride, uint32_t* sizes,
                         cudaStream_t s);
 

@@ -132,6 +132,7 @@ struct slb_ctx {
     DevBuf jpeg_coefs, jpeg_off, jpeg_total, jpeg_stream, jpeg_header;
     int jpeg_key[4] = {0, 0, 0, 0};   // (H, W, channels, quality) the header / constant tables were built for
     int jpeg_header_len = 0;
+    JpegQuant jpeg_quant;
     bool png_tables = false;
     // timing
     struct Ev { int stage; cudaEvent_t a, b; };
@@ -1692,7 +1693,7 @@ extern "C" int slb_jpeg_encode(slb_ctx* ctx, const void* images, int32_t n_image
     cudaStream_t s = enter_stream(ctx, stream);
     const int key[4] = {height, width, channels, quality};
     if (memcmp(key, ctx->jpeg_key, sizeof(key)) != 0) {   // quantisation / Huffman tables in constant memory + the file header of this shape
-        const std::vector<uint8_t> header = jpeg_prepare(height, width, channels, quality, s);
+        const std::vector<uint8_t> header = jpeg_prepare(height, width, channels, quality, &ctx->jpeg_quant, s);
         CU(ctx->jpeg_header.reserve(header.size()));
         CU(cudaMemcpyAsync(ctx->jpeg_header.p, header.data(), header.size(), cudaMemcpyHostToDevice, s));
         CU(cudaStreamSynchronize(s));   // `header` is a local
@@ -1709,7 +1710,7 @@ extern "C" int slb_jpeg_encode(slb_ctx* ctx, const void* images, int32_t n_image
     const size_t image_bytes = (size_t)height * width * channels;
     for (int at = 0; at < n_images; at += chunk) {
         const int n = std::min(chunk, n_images - at);
-        launch_jpeg_encode((const uint8_t*)images + (size_t)at * image_bytes, n, height, width, channels, ctx->jpeg_coefs.as<int16_t>(),
+        launch_jpeg_encode((const uint8_t*)images + (size_t)at * image_bytes, n, height, width, channels, ctx->jpeg_quant, ctx->jpeg_coefs.as<int16_t>(),
                            ctx->jpeg_off.as<uint32_t>(), ctx->jpeg_total.as<uint32_t>(), ctx->jpeg_stream.as<uint32_t>(),
                            ctx->jpeg_header.as<uint8_t>(), ctx->jpeg_header_len, out + (size_t)at * out_stride, out_stride, sizes + at, s);
         ctx->stats.kernel_launches += 4;

@@ -90,3 +90,29 @@ def test_argument_checks():
     assert ctx.lib.slb_jpeg_encode(ctx.h, x.data_ptr(), 1, 8, 8, 3, 80, out.data_ptr(), 100, sizes.data_ptr(), None) == 0      # too small a stride
     ctx.synchronize()
     assert int(sizes[0]) == 0 and int(out[100:].sum()) == 0
+
+
+def test_two_contexts_with_different_qualities_do_not_share_tables():
+    """The quantisation divisors travel as a kernel parameter: a second context encoding at another quality in between
+    must not change what the first one writes (its header / table cache stays valid)."""
+    from stillleben_b200 import lib
+    sl.init_cuda(0)
+    ctx_a = sl._context()
+    ctx_b = lib.Context(0)
+    img = tjo.make_image(48, 64, 3, "smooth", 11)
+    x = torch.from_numpy(img[None]).cuda()
+
+    def encode(ctx, quality):
+        out = torch.zeros((1, 1 << 16), dtype=torch.uint8, device="cuda")
+        sizes = torch.zeros(1, dtype=torch.int32, device="cuda")
+        assert ctx.lib.slb_jpeg_encode(ctx.h, x.data_ptr(), 1, 48, 64, 3, quality, out.data_ptr(), out.shape[1], sizes.data_ptr(), None) == 0
+        ctx.synchronize()
+        return out[0, :int(sizes[0])].cpu().numpy().tobytes()
+
+    try:
+        assert encode(ctx_a, 80) == tjo.libjpeg_bytes(img, 80)
+        assert encode(ctx_b, 35) == tjo.libjpeg_bytes(img, 35)
+        assert encode(ctx_a, 80) == tjo.libjpeg_bytes(img, 80)
+        assert encode(ctx_b, 35) == tjo.libjpeg_bytes(img, 35)
+    finally:
+        ctx_b.close()
