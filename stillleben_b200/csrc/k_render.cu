@@ -883,6 +883,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
     __shared__ HugeRec s_huge[SLB_HUGE_PER_VIEW];
     __shared__ int s_src[SLB_HUGE_PER_VIEW];
     __shared__ int s_nh;
+    // the pixel's visibility key is requested BEFORE the block stages its huge records: its latency overlaps the two barriers
+    const bool in_frame = px < W && py < H;
+    const size_t p = (size_t)py * W + px;
+    unsigned long long key = in_frame ? f.keys[p] : SLB_KEY_EMPTY;
     if (threadIdx.x == 0) s_nh = 0;
     __syncthreads();
     if (f.huge && threadIdx.x < SLB_HUGE_PER_VIEW && (int)threadIdx.x < min((int)__ldg(f.huge_n), SLB_HUGE_PER_VIEW)) {
@@ -891,9 +895,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
         if (h.px1 >= bx0 && h.px0 <= bx0 + 31 && h.py1 >= by0 && h.py0 <= by0 + 7) { const int at = atomicAdd(&s_nh, 1); s_huge[at] = h; s_src[at] = threadIdx.x; }
     }
     __syncthreads();
-    if (px >= W || py >= H) return;
-    const size_t p = (size_t)py * W + px;
-    unsigned long long key = f.keys[p];
+    if (!in_frame) return;
     int best = -1;                       // the staged huge record that owns this pixel, if one does
     long long bw0 = 0, bw1 = 0, bw2 = 0;   // its edge-function values here (reused for the barycentrics)
     {   // coverage (C6) and depth (C7) of the staged huge sub-triangles at this pixel, merged by minimum (every covering
