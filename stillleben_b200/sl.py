@@ -391,6 +391,29 @@ class Mesh:
         self._device_dirty = True
 
 
+class MeshCache:
+    """sl.MeshCache (python/src/py_mesh.cpp:516-530, src/mesh_cache.cpp): meshes by file name, so that Scene.deserialize()
+    re-uses loaded meshes (and their device copies) instead of importing the file again."""
+
+    def __init__(self):
+        _context()
+        self._meshes = {}
+
+    def add(self, meshes):
+        for m in meshes:
+            self._meshes[m.filename] = m
+
+    # mapping protocol used by Scene.deserialize
+    def __contains__(self, filename):
+        return filename in self._meshes
+
+    def __getitem__(self, filename):
+        return self._meshes[filename]
+
+    def __setitem__(self, filename, mesh):
+        self._meshes[filename] = mesh
+
+
 # ---------------------------------------------------------------------------------------------
 # object
 # ---------------------------------------------------------------------------------------------
@@ -677,15 +700,17 @@ class Scene:
                 raise RuntimeError("Did not find mesh subgroup in object")   # object.cpp:410-411
             mg = groups[gi + 1][1]
             key = mg["filename"]
-            mesh = Mesh(key) if key not in meshes else meshes[key]
-            if cache is not None:
-                meshes[key] = mesh
-            if "classIndex" in mg:
-                mesh.class_index = int(mg["classIndex"])
-            if "scale" in mg:
-                mesh._scale = float(mg["scale"])
-            if "rigidPretransform" in mg:
-                mesh._rigid = vec(mg["rigidPretransform"]).reshape(4, 4)
+            if key in meshes:
+                mesh = meshes[key]                                 # mesh_cache.cpp: a cached mesh is used as it is
+            else:
+                mesh = Mesh(key)                                   # Mesh::deserialize (mesh.cpp:1099-1115)
+                if "classIndex" in mg:
+                    mesh.class_index = int(mg["classIndex"])
+                if "scale" in mg:
+                    mesh._scale = float(mg["scale"])
+                if "rigidPretransform" in mg:
+                    mesh._rigid = vec(mg["rigidPretransform"]).reshape(4, 4)
+                meshes[key] = mesh                                 # (without a caller's cache: a local one, scene.cpp:852-857)
             o = Object(mesh)
             if "pose" in g:
                 o._pose = vec(g["pose"]).reshape(4, 4)

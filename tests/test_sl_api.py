@@ -55,19 +55,22 @@ def test_tabletop_placement_and_serialization(monkeypatch):
     for simulate_tabletop_scene (scene.cpp:612-759): poses above the table, bounding spheres disjoint, plane pose set."""
     import os
     monkeypatch.setattr(sl, "_ctx", object())
-    path = os.path.join(os.path.dirname(__file__), "golden", "assets", "pbr_patch.glb")
+    paths = [os.path.join(os.path.dirname(__file__), "golden", "assets", f) for f in ("pbr_patch.glb", "kitchen_sink.glb")]
     scene = sl.Scene((640, 480))
     scene.set_camera_intrinsics(1066.778, 1067.487, 312.9869, 241.3109)
     scene.set_camera_look_at(torch.tensor([0.6, 0.1, 0.5]), torch.tensor([0.0, 0.0, 0.05]))
     scene.ambient_light = torch.tensor([0.1, 0.2, 0.3])
     scene.light_directions = torch.tensor([[0.1, 0.2, -0.9], [0, 0, 0], [0, 0, 0]])
     scene.manual_exposure = 1.5
-    for k in range(4):
+    file_meshes = []
+    for path in paths:                         # (objects of one file share their mesh: the reference's deserialize() loads each file once)
         mesh = sl.Mesh(path)
         mesh.center_bbox()
-        mesh.scale_to_bbox_diagonal(0.1 + 0.05 * k)
-        mesh.class_index = k + 3
-        o = sl.Object(mesh)
+        mesh.scale_to_bbox_diagonal(0.1 + 0.05 * len(file_meshes))
+        mesh.class_index = len(file_meshes) + 3
+        file_meshes.append(mesh)
+    for k in range(4):
+        o = sl.Object(file_meshes[k % 2])
         o.metallic, o.roughness, o.casts_shadows = 0.25 * k, 0.9 - 0.2 * k, bool(k % 2)
         scene.add_object(o)
     with pytest.warns(UserWarning, match="non-physical"):
@@ -100,6 +103,13 @@ def test_tabletop_placement_and_serialization(monkeypatch):
         assert float((a.mesh.pretransform - b.mesh.pretransform).norm()) < 1e-5
         assert (a.instance_index, a.mesh.class_index, a.casts_shadows) == (b.instance_index, b.mesh.class_index, b.casts_shadows)
         assert abs(a.metallic - b.metallic) < 1e-7 and abs(a.roughness - b.roughness) < 1e-7
+    assert scene2.objects[0].mesh is scene2.objects[2].mesh and scene2.objects[0].mesh is not scene2.objects[1].mesh
+    # a MeshCache makes deserialize() re-use meshes that are already loaded (and uploaded)
+    cache = sl.MeshCache()
+    cache.add(file_meshes)
+    scene3 = sl.Scene((640, 480))
+    scene3.deserialize(text, cache)
+    assert all(o.mesh is file_meshes[k % 2] for k, o in enumerate(scene3.objects))
     with pytest.raises(RuntimeError, match="mesh subgroup"):
         sl.Scene((8, 8)).deserialize("[object]\npose=1 0 0 0 0 1 0 0 0 0 1 0 0 0 0 1\n")
 
