@@ -170,3 +170,19 @@ def test_weighted_sharding():
                                                                                             for r in range(world)), reverse=True)
     assert dist.shard_sizes_weighted(7, [0.0, 0.0]) in ([4, 3], [3, 4])                                # degenerate weights: equal shards
     assert dist.shard_sizes_weighted(5, [1.0, 0.0, 3.0]) == [1, 0, 4]
+
+
+def test_neg_iou_loss_matches_its_definition():
+    import torch
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("slb_losses", os.path.join(os.path.dirname(os.path.dirname(__file__)), "stillleben", "losses.py"))
+    losses = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(losses)
+    g = torch.Generator().manual_seed(0)
+    p, t = torch.rand(3, 1, 8, 8, generator=g), (torch.rand(3, 1, 8, 8, generator=g) > 0.5).float()
+    loss, img = losses.neg_iou_loss(p, t)
+    inter, union = (p * t).sum((1, 2, 3)), (p + t - p * t).sum((1, 2, 3)) + 1e-6
+    assert abs(float(loss) - float(1 - (inter / union).mean())) < 1e-6
+    assert img.shape == p.shape and not img.requires_grad
+    assert float(losses.neg_iou_loss(t, t)[0]) < 1e-5
