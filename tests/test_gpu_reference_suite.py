@@ -7,6 +7,8 @@ PYTHONPATH, exactly as a user of the reference would run it (`import stillleben 
     and is expected to fail with the documented RuntimeError.
   * test_grad.py: the gradient-sign test for all six pose parameters (the config-4 path end to end).
   * examples/ycb.py: run on OBJ stand-ins for the YCB models (the dataset cannot be shipped), with and without --ibl.
+  * examples/pbr.py: 20 Stanford bunnies at 1920x1080 under an sIBL light map; the map it would download (no network) is
+    replaced by a synthetic Radiance .hdr + .ibl written where the script looks for it.
 """
 import os
 import subprocess
@@ -119,3 +121,38 @@ def test_reference_example_ycb(tmp_path, ibl):
     assert img.shape == (480, 640, 3)
     if ibl:
         assert img.std() > 1
+
+
+def _write_rgbe(path, img):
+    """Flat (non-RLE) Radiance .hdr, rows top to bottom."""
+    m = img.max(-1)
+    e = np.where(m > 1e-32, np.floor(np.log2(np.maximum(m, 1e-32))) + 1, 0)
+    scale = np.where(m > 1e-32, 256.0 / np.exp2(e), 0.0)
+    rgbe = np.concatenate([np.clip(img * scale[..., None], 0, 255), (e + 128)[..., None] * (m > 1e-32)[..., None]], -1).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (img.shape[0], img.shape[1]))
+        f.write(rgbe.tobytes())
+
+
+def test_reference_example_pbr():
+    from PIL import Image
+    root = os.path.join(REF, "pbr_root")
+    if not os.path.isfile(os.path.join(root, "examples", "pbr.py")):
+        pytest.skip("pbr_root not staged")
+    ibl = os.path.join(root, "examples", "Circus_Backstage")
+    os.makedirs(ibl, exist_ok=True)
+    yy, xx = np.mgrid[0:128, 0:256]
+    env = np.stack([0.8 + 0.6 * np.sin(xx / 30.0), 0.6 + 0.5 * (yy / 128.0), 1.2 * np.ones_like(xx, float)], -1).astype(np.float32)
+    env[20:30, 60:70] = 40.0                                                          # a bright lamp: real HDR range
+    _write_rgbe(os.path.join(ibl, "Circus_Backstage_3k.hdr"), env)
+    open(os.path.join(ibl, "Circus_Backstage.ibl"), "w").write(
+        '[Header]\nName = "Circus Backstage"\n[Reflection]\nREFfile = "Circus_Backstage_3k.hdr"\nREFmap = 1\nREFgamma = 1.0\n'
+        '[Sun]\nSUNcolor = 255,245,231\nSUNmulti = 1.0\nSUNu = 0.3\nSUNv = 0.25\n')
+    out = os.path.join(root, "examples", "rgb.jpeg")
+    if os.path.exists(out):
+        os.remove(out)
+    r = _run([os.path.join(root, "examples", "pbr.py")], os.path.join(root, "examples"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "torch.Size([1080, 1920, 4])" in r.stdout and "torch.Size([1080, 1920, 1])" in r.stdout
+    img = np.asarray(Image.open(out))
+    assert img.shape == (1080, 1920, 3) and img.std() > 2

@@ -2,7 +2,8 @@
 
 /root/reference does not exist on the GPU box and reference sources must not enter the repository, so — like oracle/_ref —
 the files are copied by this recipe into tests/_ref/ (git-ignored, NOT gpurun-ignored: it travels with the snapshot):
-    tests/test_python.py, tests/test_grad.py, tests/stanford_bunny/, tests/cube.glb, examples/ycb.py
+    tests/test_python.py, tests/test_grad.py, tests/stanford_bunny/, tests/cube.glb, examples/ycb.py,
+    pbr_root/examples/pbr.py + pbr_root/tests/stanford_bunny/ (pbr.py finds its assets relative to its own location)
 tests/test_gpu_reference_suite.py runs them against the `stillleben` package of this repository; it skips when the
 directory was never staged.        python tools/stage_ref_tests.py [/root/reference]
 """
@@ -23,6 +24,11 @@ def stage(ref="/root/reference"):
     bunny = os.path.join(dst, "stanford_bunny")
     shutil.rmtree(bunny, ignore_errors=True)
     shutil.copytree(os.path.join(ref, "tests", "stanford_bunny"), bunny)
+    pbr = os.path.join(dst, "pbr_root")
+    shutil.rmtree(pbr, ignore_errors=True)
+    os.makedirs(os.path.join(pbr, "examples"))
+    shutil.copyfile(os.path.join(ref, "examples", "pbr.py"), os.path.join(pbr, "examples", "pbr.py"))
+    shutil.copytree(os.path.join(ref, "tests", "stanford_bunny"), os.path.join(pbr, "tests", "stanford_bunny"))
     return True
 
 
