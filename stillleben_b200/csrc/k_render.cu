@@ -1058,7 +1058,10 @@ void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W,
 #define SLB_SHADE_MINB 4
 #endif
     if (lean) k_shade<256, SLB_SHADE_MINB, true><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
-    else k_shade<256, SLB_SHADE_MINB, false><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
+#ifndef SLB_SHADE_MINB_FULL
+#define SLB_SHADE_MINB_FULL SLB_SHADE_MINB
+#endif
+    else k_shade<256, SLB_SHADE_MINB_FULL, false><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
 }
 
 }  // namespace slbk
