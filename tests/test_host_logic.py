@@ -186,3 +186,31 @@ def test_neg_iou_loss_matches_its_definition():
     assert abs(float(loss) - float(1 - (inter / union).mean())) < 1e-6
     assert img.shape == p.shape and not img.requires_grad
     assert float(losses.neg_iou_loss(t, t)[0]) < 1e-5
+
+
+def test_profiling_timer_context_and_decorator(capsys):
+    """stillleben.profiling.Timer as tests/test_python.py uses it: decorator + nested context manager, silent unless enabled."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("slb_profiling", os.path.join(os.path.dirname(os.path.dirname(__file__)), "stillleben", "profiling.py"))
+    prof = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(prof)
+
+    @prof.Timer("stage")
+    def stage():
+        return 7
+
+    with prof.Timer("quiet"):
+        assert stage() == 7
+    assert capsys.readouterr().out == ""
+    prof.Timer.enabled = True
+    try:
+        with prof.Timer("outer") as t:
+            stage()
+            with prof.Timer("inner"):
+                stage()
+        lines = capsys.readouterr().out.splitlines()
+        assert lines[0] == "Timings:" and [ln.split()[0] for ln in lines[1:]] == ["outer", "stage", "inner", "stage"]
+        assert lines[2].startswith("  stage") and lines[4].startswith("    stage") and t.duration > 0
+    finally:
+        prof.Timer.enabled = False
