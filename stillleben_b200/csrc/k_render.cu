@@ -1048,19 +1048,19 @@ void launch_raster(bool frag_test, const DView* views, const DFrame* frames, con
     if (frag_test) k_raster<true><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(views, frames, draws, active, pairs, g);
     else k_raster<false><<<grid, SLB_RASTER_WARPS * 32, 0, s>>>(views, frames, draws, active, pairs, g);
 }
+#ifndef SLB_SHADE_MINB
+#define SLB_SHADE_MINB 4
+#endif
+#ifndef SLB_SHADE_MINB_FULL
+#define SLB_SHADE_MINB_FULL SLB_SHADE_MINB
+#endif
 void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W, int H, bool lean, cudaStream_t s) {
     // 256 threads = 32 x 8 pixels. Launch bounds measured on B200 (ms per 1024-frame step): (256,2) 118 regs 43.8,
     // (128,5) 96 regs 39.4, (256,3) 80 regs 36.3, (256,4) 64 regs 33.4 — the kernel is latency bound, occupancy wins
     // even with ~150 B of spills.
     // `lean`: no material textures beyond base colour, no stickers, no light map, affine chains only (see fragment_stage)
     k_huge_prepare<<<n_frames, 32, 0, s>>>(frames, draws);   // no-op for frames without huge records
-#ifndef SLB_SHADE_MINB
-#define SLB_SHADE_MINB 4
-#endif
     if (lean) k_shade<256, SLB_SHADE_MINB, true><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
-#ifndef SLB_SHADE_MINB_FULL
-#define SLB_SHADE_MINB_FULL SLB_SHADE_MINB
-#endif
     else k_shade<256, SLB_SHADE_MINB_FULL, false><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
 }
 
