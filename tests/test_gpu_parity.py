@@ -152,3 +152,16 @@ def test_error_convention(gpu_ctx):
         gpu_ctx.render([fixtures.variant("tabletop")], result=res)
     with pytest.raises(ValueError):
         lib.Result(gpu_ctx, 0, 64, 1)
+
+
+@pytest.mark.parametrize("size", [(1, 1), (7, 3), (33, 17), (2560, 1440)])
+def test_extreme_viewports(gpu_ctx, size):
+    """Viewports smaller than a raster tile / a shade block, not multiples of either, and above full HD (the largest the
+    reference's users render): same parity bar as everywhere (the oracle is timed in seconds even at 2560x1440 with 4 objects)."""
+    from stillleben_b200 import synth
+    W, H = size
+    scene = synth.tabletop_scene(fixtures.small_pool(), 77, n_objects=4, width=W, height=H, intrinsics=None, n_lights=1, ssao=W >= 33)
+    gpu, _ = render_gpu(gpu_ctx, scene)
+    ref = ou.render(scene)
+    assert gpu["rgb"].shape[:2] == (H, W)
+    parity.assert_parity(gpu, ref, **OUTLIERS)
