@@ -874,10 +874,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
 #ifndef SLB_WARP_W
 #define SLB_WARP_W 8
 #endif
-    static_assert(THREADS == 256, "the warp layout assumes 32x8 pixel blocks");
+    static_assert(THREADS == 256 || THREADS == 128, "the warp layout assumes 32x8 or 32x4 pixel blocks");
+    constexpr int BH = THREADS / 32;   // block height in pixels (block width is 32)
     constexpr int WW = SLB_WARP_W, WH = 32 / WW, WPR = 32 / WW;   // warp block width / height, warps per block row
     const int wq = threadIdx.x >> 5, lq = threadIdx.x & 31;
-    const int px = blockIdx.x * 32 + (wq % WPR) * WW + (lq % WW), py = blockIdx.y * 8 + (wq / WPR) * WH + (lq / WW);
+    const int px = blockIdx.x * 32 + (wq % WPR) * WW + (lq % WW), py = blockIdx.y * BH + (wq / WPR) * WH + (lq / WW);
     // huge sub-triangles of this view (resolved per pixel below): staged once per block, only those whose pixel box
     // meets the block's 32x8 pixels
     __shared__ HugeRec s_huge[SLB_HUGE_PER_VIEW];
@@ -891,8 +892,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_shade(const DFrame* __restric
     __syncthreads();
     if (f.huge && threadIdx.x < SLB_HUGE_PER_VIEW && (int)threadIdx.x < min((int)__ldg(f.huge_n), SLB_HUGE_PER_VIEW)) {
         const HugeRec h = f.huge[threadIdx.x];
-        const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * 8;
-        if (h.px1 >= bx0 && h.px0 <= bx0 + 31 && h.py1 >= by0 && h.py0 <= by0 + 7) { const int at = atomicAdd(&s_nh, 1); s_huge[at] = h; s_src[at] = threadIdx.x; }
+        const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * BH;
+        if (h.px1 >= bx0 && h.px0 <= bx0 + 31 && h.py1 >= by0 && h.py0 <= by0 + BH - 1) { const int at = atomicAdd(&s_nh, 1); s_huge[at] = h; s_src[at] = threadIdx.x; }
     }
     __syncthreads();
     if (!in_frame) return;
@@ -1060,8 +1061,12 @@ void launch_shade(const DFrame* frames, const DDraw* draws, int n_frames, int W,
     // even with ~150 B of spills.
     // `lean`: no material textures beyond base colour, no stickers, no light map, affine chains only (see fragment_stage)
     k_huge_prepare<<<n_frames, 32, 0, s>>>(frames, draws);   // no-op for frames without huge records
-    if (lean) k_shade<256, SLB_SHADE_MINB, true><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
-    else k_shade<256, SLB_SHADE_MINB_FULL, false><<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, s>>>(frames, draws);
+#ifndef SLB_SHADE_THREADS
+#define SLB_SHADE_THREADS 256
+#endif
+    constexpr int T = SLB_SHADE_THREADS, BH = T / 32, MB = SLB_SHADE_MINB * 256 / T, MBF = SLB_SHADE_MINB_FULL * 256 / T;
+    if (lean) k_shade<T, MB, true><<<dim3((W + 31) / 32, (H + BH - 1) / BH, n_frames), T, 0, s>>>(frames, draws);
+    else k_shade<T, MBF, false><<<dim3((W + 31) / 32, (H + BH - 1) / BH, n_frames), T, 0, s>>>(frames, draws);
 }
 
 }  // namespace slbk
