@@ -415,10 +415,14 @@ def main():
                          "frac": achieved / peak,
                          "traffic": ks["dram_bytes_per_frame"] * frames_per_launch if "dram_bytes_per_frame" in ks else None,
                          "traffic_source": "profiles/r02_ncu_metrics.json (ncu --set full: dram read + write bytes of one k_shade launch, per frame, scaled to this launch size)",
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": shade_ms},
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": shade_ms,
+                         # what actually bounds the kernel: issue slots and memory latency, from the committed ncu capture
+                         "issue_slot_util_pct_ncu": ks.get("issue_pct"), "warp_instructions_per_32_pixels_ncu":
+                             (ks["warp_inst_per_frame"] / (W * H / 32.0)) if "warp_inst_per_frame" in ks else None},
             "binner": {"kernel": "k_setup (triangle set-up, direct raster, tile count)", "achieved": setup_gbs, "unit": "GB/s", "frac": setup_gbs / peak,
                        "algorithmic_bytes_per_launch": geom_bytes * frames_per_launch, "ms_per_launch": setup_ms,
                        "algorithmic_bytes": "sum over drawn sub-meshes and views (camera + shadow) of n_verts*68 + n_idx*4 (SURVEY 8d B_geom)",
+                       "issue_slot_util_pct_ncu": kb.get("issue_pct"), "active_threads_per_instruction_ncu": kb.get("threads_per_inst"),
                        "l2_hit_rate_pct": kb.get("l2_hit_pct"), "l2_hit_source": "profiles/r02_ncu_metrics.json (ncu lts__t_sector_hit_rate.pct)"},
             "triangles_per_frame": int(sub.triangles_submitted / max(1, sub.frames_rendered))}
     if e2e:
