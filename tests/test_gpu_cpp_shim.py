@@ -22,3 +22,90 @@ def test_cpp_client_replays_the_reference_test_cases():
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ALL CHECKS PASSED" in r.stdout, r.stdout + r.stderr
+
+
+def _pymod():
+    import importlib
+    import sys
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "stillleben", "lib")])
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    return importlib.import_module("stillleben.lib.libstillleben_python")
+
+
+def test_pybind11_module_builds_and_keeps_the_error_behaviour():
+    """The pybind11 layer over the C++ shim (stillleben/lib/py_shim.cpp) imports without a GPU; the reference's error behaviour
+    comes through pybind11's exception translation (std::invalid_argument -> ValueError, std::logic_error -> RuntimeError)."""
+    m = _pymod()
+    with pytest.raises(ValueError, match="unknown shading"):                 # py_render_pass.cpp:244
+        m.RenderPass("toon")
+    m._shutdown()
+    with pytest.raises(RuntimeError, match="init"):                          # py_context.cpp:69-75: "Call sl::init() first"
+        m.Scene((64, 48))
+
+
+@pytest.mark.gpu
+def test_pybind11_module_renders_what_the_ctypes_path_renders():
+    import numpy as np
+    import fixtures
+    from stillleben_b200 import abi, sl
+    m = _pymod()
+    md = fixtures.load_mesh("cube_glb_mesh")
+    mats = [(tuple(mt.base_color), float(mt.metallic), float(mt.roughness)) for mt in md.materials]
+    m.init_cuda(0)
+    mesh = m.Mesh.from_data(np.ascontiguousarray(md.vertices).view(np.uint8).reshape(-1), md.indices, [tuple(int(x) for x in s) for s in md.submeshes],
+                            mats, md.bbox_min.tolist(), md.bbox_max.tolist())
+    mesh.center_bbox()
+    mesh.scale_to_bbox_diagonal(0.5)
+    mesh.class_index = 9
+    with pytest.raises(ValueError):
+        mesh.class_index = 70000
+    obj = m.Object(mesh)
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, 3] = [0.05, -0.02, 0.6]
+    pose[:3, :3] = [[0.8, -0.6, 0.0], [0.6, 0.8, 0.0], [0.0, 0.0, 1.0]]
+    obj.set_pose(pose)
+    scene = m.Scene((320, 240))
+    scene.add_object(obj)
+    assert obj.instance_index == 1
+    scene.light_directions = np.array([[0.3, 0.2, 0.93], [0, 0, 0], [0, 0, 0]], np.float32)
+    scene.manual_exposure = 1.0
+    rp = m.RenderPass()
+    rp.ssao_enabled = False
+    res = rp.render(scene)
+
+    # the same scene through the ctypes / Python path
+    sl.init_cuda(0)
+    pmesh = sl.Mesh.from_data(md)
+    pmesh.center_bbox()
+    pmesh.scale_to_bbox_diagonal(0.5)
+    pmesh.class_index = 9
+    pobj = sl.Object(pmesh)
+    import torch
+    pobj.set_pose(torch.from_numpy(pose))
+    pscene = sl.Scene((320, 240))
+    pscene.add_object(pobj)
+    pscene.light_directions = torch.tensor([[0.3, 0.2, 0.93], [0, 0, 0], [0, 0, 0]])
+    pscene.manual_exposure = 1.0
+    prp = sl.RenderPass()
+    prp.ssao_enabled = False
+    pres = prp.render(pscene)
+    np.testing.assert_allclose(mesh.pretransform, pmesh.pretransform.numpy(), rtol=1e-6, atol=1e-7)
+    assert res.rgb().shape == (240, 320, 4) and res.instance_index().dtype == np.int16 and res.coordinates().shape == (240, 320, 3)
+    assert int((res.instance_index() == 1).sum()) > 2000 and set(np.unique(res.class_index())) == {0, 9}
+    # same library underneath; the two host layers build pretransform / projection with their own float32 arithmetic, so a
+    # handful of silhouette pixels may differ: ids equal on all but <= 0.1 % of the pixels, float targets close where they agree
+    same = res.instance_index()[..., 0] == pres.instance_index().cpu().numpy()[..., 0]
+    assert same.mean() > 0.999
+    for name in ("class_index", "instance_index", "vertex_indices"):
+        a, b = getattr(res, name)(), getattr(pres, name)().cpu().numpy()
+        assert a.shape == b.shape and a.dtype == b.dtype and (a[same] == b[same]).mean() > 0.999, name
+    for name in ("coordDepth", "normals", "barycentric_coeffs", "cam_coordinates"):
+        a, b = getattr(res, name)(), getattr(pres, name)().cpu().numpy()
+        assert a.shape == b.shape and a.dtype == b.dtype, name
+        close = np.isclose(a[same], b[same], rtol=1e-3, atol=1e-4).all(-1)
+        assert close.mean() > 0.995, name
+    a, b = res.rgb().astype(int), pres.rgb().cpu().numpy().astype(int)
+    assert (np.abs(a - b)[same].max(-1) <= 1).mean() > 0.995
+    hidden = rp.render(scene, predicate=lambda o: False)
+    assert int(hidden.instance_index().max()) == 0
