@@ -127,7 +127,7 @@ PYBIND11_MODULE(libstillleben_python, m) {
         .def("coordinates", [](sl::RenderPass::Result& r) { return image(r.objectCoordinates, 3); })
         .def("coordDepth", [](sl::RenderPass::Result& r) { return image(r.objectCoordinates, 4); })
         .def("normals", [](sl::RenderPass::Result& r) { return image(r.normals, 4); })
-        .def("vertex_indices", [](sl::RenderPass::Result& r) { return image(r.vertexIndex, 3); })
+        .def("vertex_indices", [](sl::RenderPass::Result& r) { return image(r.vertexIndex, 3).attr("view")("int32"); })   // kInt, as the reference (torch has no uint32)
         .def("barycentric_coeffs", [](sl::RenderPass::Result& r) { return image(r.barycentricCoeffs, 3); })
         .def("cam_coordinates", [](sl::RenderPass::Result& r) { return image(r.camCoordinates, 4); });
 
