@@ -8,8 +8,10 @@ generate the committed golden fixtures (tests/golden/make_ref_golden.py). Test i
             -> oracle/_ref/meshtool (dumps the reference's own consolidated 68-byte vertex stream)
   glsl      src/shaders/*.{vert,frag,glsl} compiled VERBATIM as C++ behind oracle/glsl_compat.h
             -> oracle/_ref/libglslref.so
+  frame     computeFrustumCorners + computeShadowMapMatrix, extracted verbatim from src/render_pass.cpp at build time and
+            compiled against the same GL-less Magnum -> oracle/_ref/libframeref.so
 
-Usage: python oracle/build_ref.py [diff] [meshtool] [glsl]   (no argument = everything that is not built yet)
+Usage: python oracle/build_ref.py [diff] [meshtool] [glsl] [frame]   (no argument = everything that is not built yet)
 Outputs only into oracle/_ref/ (git-ignored, not gpurun-ignored). Needs /root/reference; a no-op without it.
 """
 import os
@@ -96,17 +98,45 @@ def build_glsl(force=False):
     return so
 
 
+def build_frame(force=False):
+    """The two host-side functions of RenderPass::render that are pure Magnum math — computeFrustumCorners and
+    computeShadowMapMatrix (src/render_pass.cpp, between `using FrustumCorners` and the end of the anonymous namespace) — cut out
+    of the reference source at build time (the rest of the file needs GL) and compiled with oracle/ref_frame_harness.cpp."""
+    so = os.path.join(OUT, "libframeref.so")
+    if os.path.exists(so) and not force:
+        return so
+    gen = os.path.join(OUT, "gen")
+    os.makedirs(gen, exist_ok=True)
+    src = os.path.join(REF, "src/render_pass.cpp")
+    lines = open(src).read().splitlines()
+    start = next(i for i, ln in enumerate(lines) if ln.startswith("using FrustumCorners"))
+    end = next(i for i, ln in enumerate(lines) if ln.startswith("RenderPass::Result::Result"))
+    while not lines[end - 1].startswith("}"):          # back over blank lines to the `}` that closes the anonymous namespace
+        end -= 1
+    text = "\n".join(lines[start:end - 1])
+    assert "computeFrustumCorners" in text and "computeShadowMapMatrix" in text and "GL::" not in text
+    with open(os.path.join(gen, "render_pass_frame.inc"), "w") as f:
+        f.write(f"// cut from {src}:{start + 1}-{end - 1} by oracle/build_ref.py - do not commit\n" + text + "\n")
+    prefix = subprocess.check_output(["bash", os.path.join(HERE, "build_magnum.sh")], text=True).strip().splitlines()[-1]
+    libs = [f"{prefix}/lib/lib{n}.a" for n in ("Magnum", "CorradeUtility")]
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", f"-I{prefix}/include", f"-I{HERE}",
+                           os.path.join(HERE, "ref_frame_harness.cpp"), "-o", so] + libs)
+    return so
+
+
 def main(argv):
     if not os.path.isdir(REF):
         print("oracle/build_ref.py: no reference tree at", REF, "- keeping prebuilt oracle/_ref as is")
         return 0
-    want = [a for a in argv if not a.startswith("-")] or ["diff", "meshtool", "glsl"]
+    want = [a for a in argv if not a.startswith("-")] or ["diff", "meshtool", "glsl", "frame"]
     if "diff" in want:
         print("diff ->", build_diff(force="--force" in argv))
     if "meshtool" in want:
         print("meshtool ->", build_meshtool(force="--force" in argv))
     if "glsl" in want:
         print("glsl ->", build_glsl(force="--force" in argv))
+    if "frame" in want:
+        print("frame ->", build_frame(force="--force" in argv))
     return 0
 
 

@@ -1159,6 +1159,27 @@ void orc_test_skybox_dir(const float* projection, const float* world_to_cam, con
     M4 Pinv = inverted(M4::from(projection)), V = M4::from(world_to_cam);
     for (int i = 0; i < n; ++i) { V3 d = skybox_dir(Pinv, V, ndc_xy[2 * i], ndc_xy[2 * i + 1]); dir[3 * i] = d.x; dir[3 * i + 1] = d.y; dir[3 * i + 2] = d.z; }
 }
+// frustum corners + shadow matrix of one scene / light (render_pass.cpp:69-211) from plain arrays (column-major matrices):
+// the same signature as ref_shadow_setup of oracle/ref_frame_harness.cpp, which runs the reference's own two functions
+void orc_test_shadow_setup(const float* projection, const float* world_to_cam, int n_objects, const float* poses, const float* pretransforms,
+                           const float* bbox_min, const float* bbox_max, const float* light_dir, float* corners_out, float* shadow_out) {
+    std::vector<Mesh> meshes(n_objects);
+    std::vector<slb_object_desc> objs(n_objects);
+    for (int i = 0; i < n_objects; ++i) {
+        std::memcpy(meshes[i].bbox_min, bbox_min + 3 * i, 12); std::memcpy(meshes[i].bbox_max, bbox_max + 3 * i, 12);
+        std::memset(&objs[i], 0, sizeof objs[i]);
+        objs[i].mesh = (const slb_mesh*)&meshes[i];
+        std::memcpy(objs[i].pose, poses + 16 * i, 64); std::memcpy(objs[i].pretransform, pretransforms + 16 * i, 64);
+    }
+    slb_scene_desc sc; std::memset(&sc, 0, sizeof sc);
+    std::memcpy(sc.projection, projection, 64); std::memcpy(sc.world_to_cam, world_to_cam, 64);
+    sc.objects = objs.data(); sc.n_objects = n_objects;
+    V3 corners[8];
+    frustum_corners(sc, corners);
+    for (int i = 0; i < 8; ++i) { corners_out[3 * i] = corners[i].x; corners_out[3 * i + 1] = corners[i].y; corners_out[3 * i + 2] = corners[i].z; }
+    const M4 sm = shadow_matrix(sc, corners, V3(light_dir[0], light_dir[1], light_dir[2]));
+    std::memcpy(shadow_out, sm.m, 64);
+}
 void orc_test_background_image(const void* tex, int W, int H, float* out /* HxWx4 */) {
     const Texture& bg = *(const Texture*)tex;
     for (int py = 0; py < H; ++py)

@@ -6,6 +6,8 @@
     /root/reference by oracle/build_ref.py; the prebuilt file travels, the sources do not) on random inputs,
   * the reference's consolidated vertex stream (src/mesh_tools/consolidate.cpp run through oracle/_ref/meshtool ->
     tests/golden/*_ref.npz) against the repo's glTF front end,
+  * the reference's own computeFrustumCorners / computeShadowMapMatrix (src/render_pass.cpp, cut out at build time and compiled with
+    the reference's GL-less Magnum -> oracle/_ref/libframeref.so) against the oracle's frustum_corners / shadow_matrix,
   * the reference's GLSL programs compiled verbatim as C++ (oracle/_ref/libglslref.so) against the oracle's
     vertex / fragment / tone-map / SSAO / background / light-map restatements on random inputs (tests/test_glsl_ref.py).
 
@@ -179,3 +181,65 @@ def test_gltf_without_normals_is_an_error_like_in_the_reference(tmp_path):
         gltf.load(str(p))
     m = gltf.load(str(p), generate_missing_normals=True)
     np.testing.assert_allclose(m.vertices["normal"], [[0, 0, 1]] * 3, atol=1e-6)
+
+
+def _frame_ref():
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_ref", "libframeref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libframeref.so not built (python oracle/build_ref.py frame)")
+    return C.CDLL(so)
+
+
+def test_frustum_corners_and_shadow_matrix_match_the_reference_functions():
+    """oracle/orc_render.cpp:frustum_corners / shadow_matrix against the reference's OWN computeFrustumCorners /
+    computeShadowMapMatrix (src/render_pass.cpp:67-211, cut out at build time and compiled with the reference's Magnum:
+    oracle/_ref/libframeref.so) on random table-top scenes, cameras and light directions — incl. the empty scene
+    (near / far = -1 / 1) and objects partly outside the frustum."""
+    import ctypes as C
+    from stillleben_b200 import desc
+    ref, orc = _frame_ref(), ou.lib()
+    fp = C.POINTER(C.c_float)
+    args = [fp, fp, C.c_int, fp, fp, fp, fp, fp, fp, fp]
+    ref.ref_shadow_setup.argtypes = args
+    orc.orc_test_shadow_setup.argtypes = args
+    rng = np.random.RandomState(5)
+    worst = 0.0
+    for trial in range(300):
+        n = int(rng.choice([0, 1, 2, 5, 20]))
+        W, H = (640, 480) if trial % 2 else (1920, 1080)
+        if trial % 3:
+            P = desc.intrinsics_projection(1066.778 * W / 640, 1067.487 * W / 640, 312.9869 * W / 640, 241.3109 * H / 480, W, H)
+        else:
+            P = desc.fov_projection(W, H, float(rng.uniform(30, 90)))
+        eye = rng.uniform(-1, 1, 3) * [0.8, 0.8, 0.3] + [0, 0, 0.9]
+        V = desc.inverted_rigid(desc.look_at_pose(eye, rng.uniform(-0.2, 0.2, 3)))
+        poses, pres, bmin, bmax = [], [], [], []
+        for _ in range(n):
+            q = rng.normal(size=4); q /= np.linalg.norm(q)
+            x, y, z, w = q
+            R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+            pose = np.eye(4, dtype=np.float32); pose[:3, :3] = R; pose[:3, 3] = rng.uniform(-0.6, 0.6, 3) * [1, 1, 0.3]
+            s = float(rng.uniform(0.02, 3.0))
+            pre = np.eye(4, dtype=np.float32) * s; pre[3, 3] = 1; pre[:3, 3] = rng.uniform(-0.05, 0.05, 3)
+            lo = rng.uniform(-0.1, 0.0, 3) / s
+            hi = lo + rng.uniform(0.02, 0.3, 3) / s
+            poses.append(pose.T.reshape(-1)); pres.append(pre.T.reshape(-1)); bmin.append(lo); bmax.append(hi)      # column-major
+        as_f = lambda a, k: np.ascontiguousarray(np.asarray(a, np.float32).reshape(-1) if len(a) else np.zeros(k, np.float32))
+        poses, pres, bmin, bmax = as_f(poses, 16), as_f(pres, 16), as_f(bmin, 3), as_f(bmax, 3)
+        L = rng.normal(size=3).astype(np.float32)
+        L[2] = -abs(L[2]) - 0.2
+        Pc, Vc = np.ascontiguousarray(P.T.reshape(-1), np.float32), np.ascontiguousarray(V.T.reshape(-1), np.float32)
+        out = {}
+        for name, fn in (("ref", ref.ref_shadow_setup), ("orc", orc.orc_test_shadow_setup)):
+            corners, sm = np.zeros(24, np.float32), np.zeros(16, np.float32)
+            fn(*(a.ctypes.data_as(fp) for a in (Pc, Vc)), n, *(a.ctypes.data_as(fp) for a in (poses, pres, bmin, bmax, L, corners, sm)))
+            out[name] = (corners.copy(), sm.copy())
+        (c_ref, m_ref), (c_orc, m_orc) = out["ref"], out["orc"]
+        assert np.isfinite(c_ref).all() and np.isfinite(m_ref).all()
+        scale_c, scale_m = np.abs(c_ref).max() + 1e-6, np.abs(m_ref).max() + 1e-6
+        worst = max(worst, np.abs(c_orc - c_ref).max() / scale_c, np.abs(m_orc - m_ref).max() / scale_m)
+        np.testing.assert_allclose(c_orc, c_ref, atol=1e-4 * scale_c, rtol=0)       # float32 inverses: Magnum's cofactor expansion vs the oracle's
+        np.testing.assert_allclose(m_orc, m_ref, atol=1e-4 * scale_m, rtol=0)
+    assert worst < 1e-4            # measured: 3.0e-5
