@@ -8,10 +8,13 @@ generate the committed golden fixtures (tests/golden/make_ref_golden.py). Test i
             -> oracle/_ref/meshtool (dumps the reference's own consolidated 68-byte vertex stream)
   glsl      src/shaders/*.{vert,frag,glsl} compiled VERBATIM as C++ behind oracle/glsl_compat.h
             -> oracle/_ref/libglslref.so
+  host      the pure-math member functions behind the render pass's inputs — Scene::setCameraLookAt / setCameraIntrinsics /
+            setCameraFromFOV / setCameraPose, Mesh::centerBBox / scaleToBBoxDiagonal / setPretransform / bbox,
+            Object::stickerViewProjection — cut out of src/{scene,mesh,object}.cpp -> oracle/_ref/libhostref.so
   frame     computeFrustumCorners + computeShadowMapMatrix, extracted verbatim from src/render_pass.cpp at build time and
             compiled against the same GL-less Magnum -> oracle/_ref/libframeref.so
 
-Usage: python oracle/build_ref.py [diff] [meshtool] [glsl] [frame]   (no argument = everything that is not built yet)
+Usage: python oracle/build_ref.py [diff] [meshtool] [glsl] [frame] [host]   (no argument = everything that is not built yet)
 Outputs only into oracle/_ref/ (git-ignored, not gpurun-ignored). Needs /root/reference; a no-op without it.
 """
 import os
@@ -124,11 +127,45 @@ def build_frame(force=False):
     return so
 
 
+def _cut(path, first_prefix, stop_prefix):
+    """Lines of `path` from the first line starting with `first_prefix` up to (not including) the first later line starting
+    with `stop_prefix`, trailing blank lines dropped."""
+    lines = open(path).read().splitlines()
+    a = next(i for i, ln in enumerate(lines) if ln.startswith(first_prefix))
+    b = next(i for i in range(a + 1, len(lines)) if lines[i].startswith(stop_prefix))
+    while not lines[b - 1].strip():
+        b -= 1
+    return f"// cut from {path}:{a + 1}-{b} by oracle/build_ref.py - do not commit\n" + "\n".join(lines[a:b]) + "\n"
+
+
+def build_host(force=False):
+    """Host-side pure-math member functions of Scene / Mesh / Object (see the module docstring), compiled with
+    oracle/ref_host_harness.cpp against the reference's GL-less Magnum."""
+    so = os.path.join(OUT, "libhostref.so")
+    if os.path.exists(so) and not force:
+        return so
+    gen = os.path.join(OUT, "gen")
+    os.makedirs(gen, exist_ok=True)
+    cuts = {"scene_camera.inc": (os.path.join(REF, "src/scene.cpp"), "void Scene::setCameraPose", "Magnum::Matrix4 Scene::projectionMatrix"),
+            "mesh_pretransform.inc": (os.path.join(REF, "src/mesh.cpp"), "void Mesh::centerBBox", "void Mesh::setClassIndex"),
+            "object_sticker.inc": (os.path.join(REF, "src/object.cpp"), "Magnum::Matrix4 Object::stickerViewProjection", "void Object::setStatic")}
+    for name, (path, first, stop) in cuts.items():
+        text = _cut(path, first, stop)
+        assert "GL::" not in text and "physx" not in text.lower()
+        with open(os.path.join(gen, name), "w") as f:
+            f.write(text)
+    prefix = subprocess.check_output(["bash", os.path.join(HERE, "build_magnum.sh")], text=True).strip().splitlines()[-1]
+    libs = [f"{prefix}/lib/lib{n}.a" for n in ("Magnum", "CorradeUtility")]
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", f"-I{prefix}/include", f"-I{HERE}",
+                           os.path.join(HERE, "ref_host_harness.cpp"), "-o", so] + libs)
+    return so
+
+
 def main(argv):
     if not os.path.isdir(REF):
         print("oracle/build_ref.py: no reference tree at", REF, "- keeping prebuilt oracle/_ref as is")
         return 0
-    want = [a for a in argv if not a.startswith("-")] or ["diff", "meshtool", "glsl", "frame"]
+    want = [a for a in argv if not a.startswith("-")] or ["diff", "meshtool", "glsl", "frame", "host"]
     if "diff" in want:
         print("diff ->", build_diff(force="--force" in argv))
     if "meshtool" in want:
@@ -137,6 +174,8 @@ def main(argv):
         print("glsl ->", build_glsl(force="--force" in argv))
     if "frame" in want:
         print("frame ->", build_frame(force="--force" in argv))
+    if "host" in want:
+        print("host ->", build_host(force="--force" in argv))
     return 0
 
 

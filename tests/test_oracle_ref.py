@@ -243,3 +243,105 @@ def test_frustum_corners_and_shadow_matrix_match_the_reference_functions():
         np.testing.assert_allclose(c_orc, c_ref, atol=1e-4 * scale_c, rtol=0)       # float32 inverses: Magnum's cofactor expansion vs the oracle's
         np.testing.assert_allclose(m_orc, m_ref, atol=1e-4 * scale_m, rtol=0)
     assert worst < 1e-4            # measured: 3.0e-5
+
+
+def _host_ref():
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_ref", "libhostref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libhostref.so not built (python oracle/build_ref.py host)")
+    lib = C.CDLL(so)
+    fp = C.POINTER(C.c_float)
+    lib.ref_projection.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, fp]
+    lib.ref_look_at.argtypes = [fp, fp, fp, fp]
+    lib.ref_set_camera_pose.argtypes = [fp]
+    lib.ref_mesh_normalise.argtypes = [fp, fp, C.c_int, C.c_int, C.c_float, fp, fp]
+    lib.ref_mesh_set_pretransform.argtypes = [fp, fp, fp, fp]
+    lib.ref_sticker_projection.argtypes = [fp, fp, fp, fp, fp]
+    return lib, fp
+
+
+def _f(a):
+    return np.ascontiguousarray(np.asarray(a, np.float32).reshape(-1))
+
+
+def test_camera_helpers_match_the_reference_scene_functions():
+    """desc.intrinsics_projection / fov_projection / look_at_pose (what sl.Scene.set_camera_* use) against the reference's own
+    Scene::setCameraIntrinsics / setCameraFromFOV / setCameraLookAt (src/scene.cpp:192-271, compiled from the reference source)."""
+    from stillleben_b200 import desc
+    lib, fp = _host_ref()
+    rng = np.random.RandomState(11)
+    out = np.zeros(16, np.float32)
+    for W, H in ((640, 480), (1920, 1080), (320, 240), (127, 33)):
+        for _ in range(20):
+            fx, fy = rng.uniform(200, 2500, 2)
+            cx, cy = rng.uniform(0.3, 0.7) * W, rng.uniform(0.3, 0.7) * H
+            lib.ref_projection(W, H, 0, fx, fy, cx, cy, out.ctypes.data_as(fp))
+            np.testing.assert_allclose(desc.intrinsics_projection(fx, fy, cx, cy, W, H), out.reshape(4, 4).T, rtol=2e-6, atol=1e-7)
+            fov = float(rng.uniform(20, 110))
+            lib.ref_projection(W, H, 1, np.deg2rad(fov), 0, 0, 0, out.ctypes.data_as(fp))
+            np.testing.assert_allclose(desc.fov_projection(W, H, fov), out.reshape(4, 4).T, rtol=5e-6, atol=1e-7)
+    for _ in range(100):
+        pos, at = rng.uniform(-2, 2, 3), rng.uniform(-0.5, 0.5, 3)
+        up = (0.0, 0.0, 1.0) if rng.rand() < 0.7 else rng.normal(size=3)
+        assert lib.ref_look_at(_f(pos).ctypes.data_as(fp), _f(at).ctypes.data_as(fp), _f(up).ctypes.data_as(fp), out.ctypes.data_as(fp)) == 0
+        np.testing.assert_allclose(desc.look_at_pose(pos, at, up), out.reshape(4, 4).T, atol=2e-6)
+    # setCameraPose rejects non-rigid poses (scene.cpp:192-200); the look-at poses above are rigid by construction
+    bad = np.eye(4, dtype=np.float32); bad[0, 0] = 2.0
+    assert lib.ref_set_camera_pose(_f(bad.T).ctypes.data_as(fp)) == 1
+    assert lib.ref_set_camera_pose(_f(np.eye(4).T).ctypes.data_as(fp)) == 0
+
+
+def test_mesh_pretransform_logic_matches_the_reference_mesh_functions(monkeypatch):
+    """sl.Mesh.center_bbox / scale_to_bbox_diagonal / pretransform setter / bbox against the reference's Mesh::centerBBox /
+    scaleToBBoxDiagonal / setPretransform / bbox (src/mesh.cpp:1019-1081), and sl.Object._sticker_projection against
+    Object::stickerViewProjection (src/object.cpp:494-513) — all compiled from the reference source."""
+    import torch
+    from stillleben_b200 import sl
+    monkeypatch.setattr(sl, "_ctx", object())                         # host logic only
+    lib, fp = _host_ref()
+    rng = np.random.RandomState(12)
+    base = fixtures.load_mesh("cube_glb_mesh")
+    pre_out, bbox_out = np.zeros(16, np.float32), np.zeros(6, np.float32)
+    for trial in range(60):
+        lo = rng.uniform(-3, 0, 3).astype(np.float32)
+        hi = (lo + rng.uniform(0.01, 4, 3)).astype(np.float32)
+        md = type(base)(base.vertices, base.indices, base.submeshes, base.materials, base.images, lo.copy(), hi.copy(), "m")
+        mesh = sl.Mesh.from_data(md)
+        center, mode, target = bool(trial % 2), trial % 3, float(rng.uniform(0.05, 2.0))
+        if center:
+            mesh.center_bbox()
+        if mode:
+            mesh.scale_to_bbox_diagonal(target, "exact" if mode == 1 else "order_of_magnitude")
+        lib.ref_mesh_normalise(_f(lo).ctypes.data_as(fp), _f(hi).ctypes.data_as(fp), int(center), mode, target, pre_out.ctypes.data_as(fp),
+                               bbox_out.ctypes.data_as(fp))
+        ref_pre = pre_out.reshape(4, 4).T
+        np.testing.assert_allclose(mesh.pretransform.numpy(), ref_pre, rtol=2e-6, atol=1e-6 * max(1.0, np.abs(ref_pre).max()))
+        bb = mesh.bbox
+        np.testing.assert_allclose(np.concatenate([bb.min.numpy(), bb.max.numpy()]), bbox_out, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(bbox_out).max()))
+        # sticker projection of an object of this mesh
+        q = rng.normal(size=4).astype(np.float32); q /= np.linalg.norm(q)
+        obj = sl.Object(mesh)
+        obj.sticker_rotation = torch.from_numpy(q)
+        obj.sticker_texture = object()
+        lib.ref_sticker_projection(_f(lo).ctypes.data_as(fp), _f(hi).ctypes.data_as(fp), _f(mesh.pretransform.numpy().T).ctypes.data_as(fp),
+                                   _f(q).ctypes.data_as(fp), pre_out.ctypes.data_as(fp))
+        ref_sp = pre_out.reshape(4, 4).T
+        np.testing.assert_allclose(obj._sticker_projection(), ref_sp, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(ref_sp).max()))
+    # setPretransform: uniform scale x rigid accepted and split like the reference; anisotropic scale rejected
+    scale_out, rigid_out = np.zeros(1, np.float32), np.zeros(16, np.float32)
+    for trial in range(40):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        R = sl.quat_to_matrix(torch.tensor(q, dtype=torch.float32)).numpy()
+        s = float(rng.uniform(0.01, 20))
+        m = np.eye(4, dtype=np.float32); m[:3, :3] = s * R; m[:3, 3] = rng.uniform(-1, 1, 3)
+        mesh = sl.Mesh.from_data(base)
+        mesh.pretransform = torch.from_numpy(m)
+        assert lib.ref_mesh_set_pretransform(_f(m.T).ctypes.data_as(fp), scale_out.ctypes.data_as(fp), rigid_out.ctypes.data_as(fp), pre_out.ctypes.data_as(fp)) == 0
+        assert abs(mesh._scale - float(scale_out[0])) < 3e-6 * s
+        np.testing.assert_allclose(mesh._rigid, rigid_out.reshape(4, 4).T, atol=2e-5 * max(1.0, 1.0 / s))
+        np.testing.assert_allclose(mesh.pretransform.numpy(), pre_out.reshape(4, 4).T, atol=3e-6 * max(1.0, s))
+    m = np.eye(4, dtype=np.float32); m[0, 0] = 2.0
+    assert lib.ref_mesh_set_pretransform(_f(m.T).ctypes.data_as(fp), scale_out.ctypes.data_as(fp), rigid_out.ctypes.data_as(fp), pre_out.ctypes.data_as(fp)) == 1
+    with pytest.raises(ValueError, match="not uniform"):
+        sl.Mesh.from_data(base).pretransform = torch.from_numpy(m)
