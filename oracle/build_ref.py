@@ -148,6 +148,8 @@ def build_host(force=False):
     os.makedirs(gen, exist_ok=True)
     cuts = {"scene_camera.inc": (os.path.join(REF, "src/scene.cpp"), "void Scene::setCameraPose", "Magnum::Matrix4 Scene::projectionMatrix"),
             "mesh_pretransform.inc": (os.path.join(REF, "src/mesh.cpp"), "void Mesh::centerBBox", "void Mesh::setClassIndex"),
+            "mesh_normals.inc": (os.path.join(REF, "src/mesh.cpp"), "void Mesh::recomputeNormals", "void Mesh::recompileMesh"),
+            "mesh_vertex_edit.inc": (os.path.join(REF, "src/mesh.cpp"), "void Mesh::updateVertexPositionsAndColors", "void Mesh::setVertexColors"),
             "object_sticker.inc": (os.path.join(REF, "src/object.cpp"), "Magnum::Matrix4 Object::stickerViewProjection", "void Object::setStatic")}
     for name, (path, first, stop) in cuts.items():
         text = _cut(path, first, stop)

@@ -2,7 +2,8 @@
 // sources at build time (oracle/build_ref.py: build_host -> oracle/_ref/gen/{scene_camera,mesh_pretransform,object_sticker}.inc,
 // never committed) and compiled against the reference's GL-less Magnum:
 //   src/scene.cpp   Scene::setCameraPose / setCameraLookAt / cameraPose / setCameraIntrinsics / setCameraProjection / setCameraFromFOV
-//   src/mesh.cpp    Mesh::centerBBox / scaleToBBoxDiagonal / updatePretransform / setPretransform / bbox
+//   src/mesh.cpp    Mesh::centerBBox / scaleToBBoxDiagonal / updatePretransform / setPretransform / bbox,
+//                   Mesh::recomputeNormals, updateVertexPositionsAndColors, setVertexPositions (the vertex-edit path)
 //   src/object.cpp  Object::stickerViewProjection
 // The classes below declare exactly the members those bodies touch. TEST INFRASTRUCTURE ONLY: tests/test_oracle_ref.py pins the
 // Python host mirror (stillleben_b200/sl.py, desc.py) on these functions.
@@ -14,9 +15,12 @@
 #include <Magnum/Math/Matrix4.h>
 #include <Magnum/Math/Quaternion.h>
 #include <Magnum/Math/Range.h>
+#include <Magnum/Math/Color.h>
 #include <Magnum/Math/Vector3.h>
+#include <Corrade/Containers/ArrayView.h>
 
 #include <cmath>
+#include <vector>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -45,9 +49,29 @@ public:
         Matrix4 absoluteTransformationMatrix() const { return T; }
     } m_cameraObject;
 };
+// what Mesh::meshPoints() / meshNormals() / meshColors() / meshFaces() hand out: a view (copies alias the same storage)
+template <class T> struct View {
+    T* p; std::size_t n;
+    std::size_t size() const { return n; }
+    T& operator[](std::size_t i) const { return p[i]; }
+};
 class Mesh {
 public:
     enum class Scale { Exact, OrderOfMagnitude };
+    // vertex-edit path
+    void recomputeNormals();
+    void recompileMesh() {}                                   // GL buffer upload in the reference
+    void updateVertexPositionsAndColors(const Corrade::Containers::ArrayView<int>& verticesIndex,
+                                        const Corrade::Containers::ArrayView<Magnum::Vector3>& positionsUpdate,
+                                        const Corrade::Containers::ArrayView<Magnum::Color4>& colorsUpdate);
+    void setVertexPositions(const Corrade::Containers::ArrayView<Magnum::Vector3>& newVertices);
+    View<Vector3> meshPoints() { return {points.data(), points.size()}; }
+    View<Vector3> meshNormals() { return {normals.data(), normals.size()}; }
+    View<Color4> meshColors() { return {colors.data(), colors.size()}; }
+    View<UnsignedInt> meshFaces() { return {faces.data(), faces.size()}; }
+    std::vector<Vector3> points, normals;
+    std::vector<Color4> colors;
+    std::vector<UnsignedInt> faces;
     void centerBBox();
     void scaleToBBoxDiagonal(float targetDiagonal, Scale mode);
     void updatePretransform();
@@ -66,6 +90,8 @@ public:
 
 #include "_ref/gen/scene_camera.inc"
 #include "_ref/gen/mesh_pretransform.inc"
+#include "_ref/gen/mesh_normals.inc"
+#include "_ref/gen/mesh_vertex_edit.inc"
 #include "_ref/gen/object_sticker.inc"
 }  // namespace sl
 
@@ -108,6 +134,31 @@ int ref_mesh_set_pretransform(const float* m16, float* scale_out, float* rigid_o
     *scale_out = m.m_scale;
     put(m.m_pretransformRigid, rigid_out);
     put(m.m_pretransform, pre_out);
+    return 0;
+}
+// updateVertexPositionsAndColors (ids one-based; dpos / dcol may be NULL) or, with ids == NULL, setVertexPositions(dpos as the
+// new positions). positions / colors are updated in place, normals_out receives the recomputed normals. Returns 1 on exception.
+int ref_mesh_edit(float* positions, float* normals_out, float* colors, int n_verts, const unsigned* indices, int n_idx, const int* ids, int n_ids,
+                  const float* dpos, const float* dcol) {
+    sl::Mesh m;
+    m.points.resize(n_verts); m.normals.resize(n_verts); m.colors.resize(n_verts);
+    for (int i = 0; i < n_verts; ++i) { m.points[i] = Vector3::from(positions + 3 * i); m.normals[i] = Vector3::from(normals_out + 3 * i); m.colors[i] = Color4::from(colors + 4 * i); }
+    m.faces.assign(indices, indices + n_idx);
+    try {
+        if (ids) {
+            std::vector<int> idv(ids, ids + n_ids);
+            std::vector<Vector3> dp; std::vector<Color4> dc;
+            if (dpos) for (int i = 0; i < n_ids; ++i) dp.push_back(Vector3::from(dpos + 3 * i));
+            if (dcol) for (int i = 0; i < n_ids; ++i) dc.push_back(Color4::from(dcol + 4 * i));
+            m.updateVertexPositionsAndColors({idv.data(), idv.size()}, {dp.data(), dp.size()}, {dc.data(), dc.size()});
+        } else {
+            std::vector<Vector3> np;
+            for (int i = 0; i < n_ids; ++i) np.push_back(Vector3::from(dpos + 3 * i));
+            m.setVertexPositions({np.data(), np.size()});
+        }
+    } catch (const std::invalid_argument&) { return 1; }
+    for (int i = 0; i < n_verts; ++i)
+        for (int k = 0; k < 4; ++k) { if (k < 3) { positions[3 * i + k] = m.points[i][k]; normals_out[3 * i + k] = m.normals[i][k]; } colors[4 * i + k] = m.colors[i][k]; }
     return 0;
 }
 void ref_sticker_projection(const float* bbox_min, const float* bbox_max, const float* pretransform, const float* quat_xyzw, float* out) {

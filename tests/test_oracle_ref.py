@@ -345,3 +345,52 @@ def test_mesh_pretransform_logic_matches_the_reference_mesh_functions(monkeypatc
     assert lib.ref_mesh_set_pretransform(_f(m.T).ctypes.data_as(fp), scale_out.ctypes.data_as(fp), rigid_out.ctypes.data_as(fp), pre_out.ctypes.data_as(fp)) == 1
     with pytest.raises(ValueError, match="not uniform"):
         sl.Mesh.from_data(base).pretransform = torch.from_numpy(m)
+
+
+def test_vertex_edit_twin_matches_the_reference_mesh_functions():
+    """The oracle's vertex-edit twin (orc_mesh_update_positions_and_colors / recompute_normals — which the DEVICE path
+    reproduces bit for bit, tests/test_gpu_assets.py) against the reference's own Mesh::updateVertexPositionsAndColors /
+    setVertexPositions / recomputeNormals (src/mesh.cpp:763-870, compiled from the reference source): positions, colours and the
+    area-weighted normals, incl. the one-based ids and the size check of setVertexPositions."""
+    import ctypes as C
+    from stillleben_b200 import abi, synth
+    lib, fp = _host_ref()
+    ip, up = C.POINTER(C.c_int), C.POINTER(C.c_uint)
+    lib.ref_mesh_edit.argtypes = [fp, fp, fp, C.c_int, up, C.c_int, ip, C.c_int, fp, fp]
+    L = ou.lib()
+    L.orc_mesh_update_positions_and_colors.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.orc_mesh_read_vertices.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_mesh_recompute_normals.argtypes = [C.c_void_p]
+    rng = np.random.RandomState(21)
+    for mesh in (synth.shape_mesh("blob", 9, nu=24, nv=12, textured=True, tex_size=32), fixtures.load_mesh("cube_glb_mesh"), fixtures.load_mesh("kitchen_sink_mesh")):
+        assets = ou.OracleAssets()
+        h = assets.handle_of(mesh)
+        n = len(mesh.vertices)
+        ids = (rng.permutation(n)[: max(1, n // 2)] + 1).astype(np.int32)
+        dpos = (rng.normal(size=(len(ids), 3)) * 0.02).astype(np.float32)
+        dcol = rng.rand(len(ids), 4).astype(np.float32)
+        pos, nrm, col = (np.ascontiguousarray(mesh.vertices[k]).copy() for k in ("position", "normal", "color"))
+        idx = np.ascontiguousarray(mesh.indices, np.uint32)
+        assert lib.ref_mesh_edit(pos.ctypes.data_as(fp), nrm.ctypes.data_as(fp), col.ctypes.data_as(fp), n, idx.ctypes.data_as(up), len(idx),
+                                 ids.ctypes.data_as(ip), len(ids), dpos.ctypes.data_as(fp), dcol.ctypes.data_as(fp)) == 0
+        assert L.orc_mesh_update_positions_and_colors(h, ids.ctypes.data, len(ids), dpos.ctypes.data, dcol.ctypes.data) == 0
+        got = np.empty(n, abi.VERTEX_DTYPE)
+        L.orc_mesh_read_vertices(h, got.ctypes.data)
+        assert np.array_equal(got["position"], pos) and np.array_equal(got["color"], col)
+        ok = np.isfinite(nrm).all(1)                                   # (vertices without faces / zero-area fans: NaN on both sides)
+        assert np.array_equal(np.isfinite(got["normal"]).all(1), ok)
+        np.testing.assert_allclose(got["normal"][ok], nrm[ok], atol=2e-6)
+        assert np.abs(nrm[ok] - mesh.vertices["normal"][ok]).max() > 1e-3    # the edit did change them
+        # setVertexPositions
+        newp = (pos * np.float32(1.07) + np.float32(0.01)).astype(np.float32)
+        assert lib.ref_mesh_edit(pos.ctypes.data_as(fp), nrm.ctypes.data_as(fp), col.ctypes.data_as(fp), n, idx.ctypes.data_as(up), len(idx),
+                                 None, n, newp.ctypes.data_as(fp), None) == 0
+        expect = got.copy(); expect["position"] = newp
+        L.orc_mesh_update_vertices(h, expect.ctypes.data, n)
+        L.orc_mesh_recompute_normals(h)
+        L.orc_mesh_read_vertices(h, got.ctypes.data)
+        assert np.array_equal(pos, newp)
+        np.testing.assert_allclose(got["normal"][ok], nrm[ok], atol=2e-6)
+        # "Number of new vertices should match the existing mesh vertices" (mesh.cpp:861-862)
+        assert lib.ref_mesh_edit(pos.ctypes.data_as(fp), nrm.ctypes.data_as(fp), col.ctypes.data_as(fp), n, idx.ctypes.data_as(up), len(idx),
+                                 None, n - 1, newp.ctypes.data_as(fp), None) == 1
