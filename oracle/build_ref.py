@@ -150,6 +150,8 @@ def build_host(force=False):
             "mesh_pretransform.inc": (os.path.join(REF, "src/mesh.cpp"), "void Mesh::centerBBox", "void Mesh::setClassIndex"),
             "mesh_normals.inc": (os.path.join(REF, "src/mesh.cpp"), "void Mesh::recomputeNormals", "void Mesh::recompileMesh"),
             "mesh_vertex_edit.inc": (os.path.join(REF, "src/mesh.cpp"), "void Mesh::updateVertexPositionsAndColors", "void Mesh::setVertexColors"),
+            "lightmap_specs.inc": (os.path.join(REF, "src/light_map.cpp"), "    struct IBLSpec", "    Containers::Optional<Magnum::GL::Texture2D> loadTexture"),
+            "lightmap_lights.inc": (os.path.join(REF, "src/light_map.cpp"), "        auto addLight = [&]", "    }"),
             "object_sticker.inc": (os.path.join(REF, "src/object.cpp"), "Magnum::Matrix4 Object::stickerViewProjection", "void Object::setStatic")}
     for name, (path, first, stop) in cuts.items():
         text = _cut(path, first, stop)

@@ -5,9 +5,12 @@
 //   src/mesh.cpp    Mesh::centerBBox / scaleToBBoxDiagonal / updatePretransform / setPretransform / bbox,
 //                   Mesh::recomputeNormals, updateVertexPositionsAndColors, setVertexPositions (the vertex-edit path)
 //   src/object.cpp  Object::stickerViewProjection
+//   src/light_map.cpp  the sIBL (.ibl) reader: IBLSpec::load, LightSpec::load and, out of LightMap::load, the addLight lambda +
+//                   the Sun / Light1 / Light2 group handling (the texture upload around them is GL and stays out)
 // The classes below declare exactly the members those bodies touch. TEST INFRASTRUCTURE ONLY: tests/test_oracle_ref.py pins the
 // Python host mirror (stillleben_b200/sl.py, desc.py) on these functions.
 #include <Corrade/Utility/Debug.h>
+#include <Corrade/Utility/DebugStl.h>
 #include <Magnum/Magnum.h>
 #include <Magnum/Math/Algorithms/Svd.h>
 #include <Magnum/Math/Functions.h>
@@ -18,8 +21,17 @@
 #include <Magnum/Math/Color.h>
 #include <Magnum/Math/Vector3.h>
 #include <Corrade/Containers/ArrayView.h>
+#include <Corrade/Containers/GrowableArray.h>
+#include <Corrade/Containers/Optional.h>
+#include <Corrade/Utility/Configuration.h>
+#include <Corrade/Utility/ConfigurationGroup.h>
+#include <Corrade/Utility/String.h>
+#include <Magnum/Math/ConfigurationValue.h>
+#include <Magnum/Math/Constants.h>
+#include <Magnum/Math/Vector2.h>
 
 #include <cmath>
+#include <cstdio>
 #include <vector>
 #include <memory>
 #include <sstream>
@@ -95,9 +107,37 @@ public:
 #include "_ref/gen/object_sticker.inc"
 }  // namespace sl
 
+namespace iblref {
+using namespace Corrade;
+using namespace Magnum;
+#include "_ref/gen/lightmap_specs.inc"
+// REFfile / REFgamma / REFmulti of the [Reflection] group and the directional lights, as LightMap::load derives them.
+// Returns -1 when the reference's load() would fail before touching GL, else the number of lights.
+int lights(const char* path, char* ref_file, int ref_file_cap, float* gamma_multi, float* dirs, float* cols) {
+    using namespace Utility;
+    Containers::Array<Vector3> m_lightDirections;
+    Containers::Array<Color3> m_lightColors;
+    Configuration config{path, Configuration::Flag::ReadOnly};
+    if (config.isEmpty()) return -1;
+    auto reflectionGroup = config.group("Reflection");
+    if (!reflectionGroup) return -1;
+    auto refSpec = IBLSpec::load(*reflectionGroup, "REF");
+    if (!refSpec) return -1;
+    std::snprintf(ref_file, ref_file_cap, "%s", refSpec->file.c_str());
+    gamma_multi[0] = refSpec->gamma; gamma_multi[1] = refSpec->multiplier;
+#include "_ref/gen/lightmap_lights.inc"
+    for (std::size_t i = 0; i < m_lightDirections.size(); ++i)
+        for (int k = 0; k < 3; ++k) { dirs[3 * i + k] = m_lightDirections[i][k]; cols[3 * i + k] = m_lightColors[i][k]; }
+    return (int)m_lightDirections.size();
+}
+}  // namespace iblref
+
 static void put(const Matrix4& m, float* out) { for (int k = 0; k < 16; ++k) out[k] = m.data()[k]; }   // column-major
 
 extern "C" {
+int ref_ibl_lights(const char* path, char* ref_file, int ref_file_cap, float* gamma_multi, float* dirs, float* cols) {
+    return iblref::lights(path, ref_file, ref_file_cap, gamma_multi, dirs, cols);
+}
 // mode 0: setCameraIntrinsics(a, b, c, d); mode 1: setCameraFromFOV(a radians)
 void ref_projection(int W, int H, int mode, float a, float b, float c, float d, float* P_out) {
     sl::Scene s;

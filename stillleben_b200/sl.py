@@ -162,17 +162,27 @@ class LightMap:
                 elif "=" in line and cur is not None:
                     k, v = line.split("=", 1)
                     sections[cur][k.strip()] = v.strip().strip('"')
-            ref = sections.get("Reflection", {})
-            if int(ref.get("REFmap", "1")) != 1:
-                raise RuntimeError("Only lat-long light maps are supported")
+            # LightMap::load + IBLSpec::load + LightSpec::load (light_map.cpp:55-151,266-345); a file the reference refuses makes
+            # its constructor throw "Could not load light map <path>" (:259-262)
+            ref = sections.get("Reflection")
+            if ref is None or "REFfile" not in ref or "REFmap" not in ref or int(ref["REFmap"]) != 1:
+                raise RuntimeError("Could not load light map " + path)
             img_path = os.path.join(os.path.dirname(path), ref["REFfile"])
             for sec, pre in (("Sun", "SUN"), ("Light1", "LIGHT"), ("Light2", "LIGHT")):
                 if sec not in sections:
                     continue
                 s = sections[sec]
-                col = np.array([float(x) for x in s[pre + "color"].split(",")], np.float32) / 255.0 * float(s.get(pre + "multi", 1.0))
-                u, v = float(s[pre + "u"]), float(s[pre + "v"])
-                theta, phi = (u + 0.5) * 2.0 * math.pi, v * math.pi       # light_map.cpp:314-326
+                multi = np.float32(float(s[pre + "multi"])) if pre + "multi" in s else np.float32(1.0)
+                col = np.ones(3, np.float32)                               # Color3{1.0f}: only a present colour is divided by 255
+                if pre + "color" in s:
+                    parts = s[pre + "color"].split(",")
+                    if len(parts) != 3:
+                        continue                                           # "Invalid light spec": this light is skipped
+                    col = np.array([float(x) for x in parts], np.float32) / np.float32(255)
+                col = multi * col
+                u = np.float32(float(s[pre + "u"])) if pre + "u" in s else np.float32(0)
+                v = np.float32(float(s[pre + "v"])) if pre + "v" in s else np.float32(0)
+                theta, phi = float((u + np.float32(0.5)) * np.float32(math.pi) * np.float32(2)), float(v * np.float32(math.pi))
                 lights_d.append((-np.array([math.cos(phi) * math.sin(theta), math.sin(phi) * math.sin(theta), math.cos(theta)])).tolist())
                 lights_c.append(col.tolist())
         if img_path.lower().endswith(".hdr"):

@@ -394,3 +394,52 @@ def test_vertex_edit_twin_matches_the_reference_mesh_functions():
         # "Number of new vertices should match the existing mesh vertices" (mesh.cpp:861-862)
         assert lib.ref_mesh_edit(pos.ctypes.data_as(fp), nrm.ctypes.data_as(fp), col.ctypes.data_as(fp), n, idx.ctypes.data_as(up), len(idx),
                                  None, n - 1, newp.ctypes.data_as(fp), None) == 1
+
+
+def test_ibl_reader_matches_the_reference_light_map_parser(tmp_path, monkeypatch):
+    """sl.LightMap's .ibl reader against the reference's own IBLSpec::load / LightSpec::load / addLight (src/light_map.cpp:55-151,
+    314-345, compiled from the reference source with Corrade's Configuration): the reflection file, and direction + colour of
+    the sun and the two extra lights, over files with quotes, spaces, missing keys and missing groups."""
+    import ctypes as C
+    from stillleben_b200 import sl
+    monkeypatch.setattr(sl, "_ctx", object())
+    lib, fp = _host_ref()
+    lib.ref_ibl_lights.argtypes = [C.c_char_p, C.c_char_p, C.c_int, fp, fp, fp]
+    np.save(tmp_path / "env.npy", np.ones((8, 16, 3), np.float32))
+    rng = np.random.RandomState(4)
+    cases = []
+    for k in range(12):
+        sec = ['[Header]', 'ICOfile = "x.jpg"', '[Reflection]', 'REFfile = "env.npy"' if k % 2 else "REFfile=env.npy", "REFmap = 1",
+               f"REFgamma = {rng.uniform(1, 2.2):.3f}", f"REFmulti = {rng.uniform(0.5, 2):.2f}"]
+        groups = [("Sun", "SUN"), ("Light1", "LIGHT"), ("Light2", "LIGHT")][: 1 + k % 3] if k % 4 != 3 else [("Light1", "LIGHT")]
+        for name, pre in groups:
+            sec.append(f"[{name}]")
+            if k % 5 != 4:
+                r, g, b = rng.randint(0, 256, 3)
+                sec.append(f"{pre}color = {r},{g},{b}" if k % 2 else f"{pre}color={r}, {g} ,{b}")
+            if k % 3 != 2:
+                sec.append(f"{pre}multi = {rng.uniform(0.2, 5):.3f}")
+            sec.append(f"{pre}u = {rng.uniform(-0.5, 0.5):.4f}")
+            if k % 7 != 6:
+                sec.append(f"{pre}v = {rng.uniform(0.05, 0.95):.4f}")
+        cases.append("\n".join(sec) + "\n")
+    for k, text in enumerate(cases):
+        path = tmp_path / f"case{k}.ibl"
+        path.write_text(text)
+        ref_file = C.create_string_buffer(256)
+        gm, dirs, cols = np.zeros(2, np.float32), np.zeros(9, np.float32), np.zeros(9, np.float32)
+        n = lib.ref_ibl_lights(str(path).encode(), ref_file, 256, gm.ctypes.data_as(fp), dirs.ctypes.data_as(fp), cols.ctypes.data_as(fp))
+        assert n >= 1 and ref_file.value == b"env.npy", (k, n, ref_file.value)
+        lm = sl.LightMap(str(path))
+        assert len(lm.data.light_directions) == n, k
+        np.testing.assert_allclose(np.asarray(lm.data.light_directions, np.float32).reshape(-1), dirs[: 3 * n], atol=2e-6, err_msg=text)
+        np.testing.assert_allclose(np.asarray(lm.data.light_colors, np.float32).reshape(-1), cols[: 3 * n], rtol=2e-6, atol=1e-7, err_msg=text)
+    # files the reference refuses: no [Reflection] group, a mapping mode other than 1
+    (tmp_path / "bad1.ibl").write_text("[Sun]\nSUNu = 0.1\nSUNv = 0.2\n")
+    (tmp_path / "bad2.ibl").write_text('[Reflection]\nREFfile = "env.npy"\nREFmap = 2\n')
+    for name in ("bad1.ibl", "bad2.ibl"):
+        gm, dirs, cols = np.zeros(2, np.float32), np.zeros(9, np.float32), np.zeros(9, np.float32)
+        assert lib.ref_ibl_lights(str(tmp_path / name).encode(), C.create_string_buffer(256), 256, gm.ctypes.data_as(fp), dirs.ctypes.data_as(fp),
+                                  cols.ctypes.data_as(fp)) == -1
+        with pytest.raises((RuntimeError, KeyError)):
+            sl.LightMap(str(tmp_path / name))
