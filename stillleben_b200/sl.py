@@ -243,10 +243,13 @@ class Mesh:
             if self.filename.lower().endswith(".obj"):
                 from . import objfile
                 self.data = objfile.load(self.filename)
+            elif self.filename.lower().endswith(".ply"):
+                from . import plyfile
+                self.data = plyfile.load(self.filename)
             elif self.filename.lower().endswith((".gltf", ".glb")):
                 self.data = gltf.load(self.filename)
             else:
-                raise RuntimeError(f"Could not load mesh {self.filename}: only glTF / GLB / OBJ are supported by this build")
+                raise RuntimeError(f"Could not load mesh {self.filename}: only glTF / GLB / OBJ / PLY are supported by this build")
         self._scale = 1.0
         self._rigid = np.eye(4, dtype=np.float32)
         self._class_index = 1                                          # mesh.h:300

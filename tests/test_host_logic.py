@@ -214,3 +214,36 @@ def test_profiling_timer_context_and_decorator(capsys):
         assert lines[2].startswith("  stage") and lines[4].startswith("    stage") and t.duration > 0
     finally:
         prof.Timer.enabled = False
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian", "binary_big_endian"])
+def test_ply_front_end(tmp_path, fmt):
+    """plyfile.load: the three PLY encodings give the same mesh; normals / colours / uv read or generated; quads fanned;
+    TextureFile comment -> base-colour texture (row 0 = bottom row)."""
+    from PIL import Image
+    from stillleben_b200 import plyfile
+    pos = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 0.5, 1]], np.float32)
+    faces = [(0, 1, 2, 3), (0, 1, 4), (1, 2, 4), (2, 3, 4), (3, 0, 4)]
+    nrm = np.tile(np.array([[0, 0, 1]], np.float32), (5, 1))
+    col = np.array([[255, 0, 0], [0, 255, 0], [0, 0, 255], [10, 20, 30], [255, 255, 255]], np.uint8)
+    uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1], [0.5, 0.5]], np.float32)
+    Image.fromarray(np.arange(4 * 4 * 3, dtype=np.uint8).reshape(4, 4, 3)).save(tmp_path / "t.png")
+    plyfile._write_test_ply(tmp_path / "a.ply", pos, faces, fmt, normals=nrm, colors=col, uv=uv, texture_file="t.png")
+    m = plyfile.load(str(tmp_path / "a.ply"))
+    assert len(m.vertices) == 5 and m.indices.tolist() == [0, 1, 2, 0, 2, 3, 0, 1, 4, 1, 2, 4, 2, 3, 4, 3, 0, 4]
+    np.testing.assert_allclose(m.vertices["position"], pos)
+    np.testing.assert_allclose(m.vertices["normal"], nrm)
+    np.testing.assert_allclose(m.vertices["color"][:, :3], col / 255.0, atol=1e-7)
+    assert (m.vertices["color"][:, 3] == 1.0).all() and (m.vertices["tangent"][:, 3] == 1.0).all()
+    np.testing.assert_allclose(m.vertices["uv"], uv)
+    assert m.vertices["vertex_index"].tolist() == [1, 2, 3, 4, 5]
+    assert m.materials[0].tex_base_color == 0 and m.images[0].pixels[0, 0].tolist() == [36, 37, 38]
+    assert m.submeshes == [(0, 18, 0)] and np.allclose(m.bbox_max, [1, 1, 1])
+    # geometry only: normals generated, no texture, no colours
+    plyfile._write_test_ply(tmp_path / "b.ply", pos, faces[1:], fmt)
+    g = plyfile.load(str(tmp_path / "b.ply"))
+    assert np.allclose(np.linalg.norm(g.vertices["normal"], axis=1), 1.0, atol=1e-5) and g.materials[0].tex_base_color == -1 and not g.images
+    assert g.vertices["normal"][4, 2] > 0.5                       # the apex normal points up
+    with pytest.raises(RuntimeError, match="not a PLY"):
+        (tmp_path / "c.ply").write_bytes(b"solid nothing")
+        plyfile.load(str(tmp_path / "c.ply"))
