@@ -1,5 +1,7 @@
-"""Config 4 timing: ms per fused render-and-compare backward (slb_diff_pose_grad) at 640x480 with 21 objects,
-next to the CPU oracle of the same computation.  python tools/bench_diff.py"""
+"""Config 4 timing: ms per fused render-and-compare backward (slb_diff_pose_grad) at 640x480 with 21 objects, next to
+(a) the reference's OWN CUDA kernels for the mask part of the same computation (oracle/_ref/diff: python/src/diff.cu +
+bridge_diff.cpp compiled from the reference — generate_sobel_valid_mask once + dilate_object_mask per object, the calls
+diff.py:355-523 makes before its per-object tensor program) and (b) the CPU oracle.  python tools/bench_diff.py"""
 import os
 import sys
 import time
@@ -38,4 +40,32 @@ t0 = time.perf_counter()
 ref = diff_ref.oracle_pose_grad(*args)
 cpu_ms = (time.perf_counter() - t0) * 1e3
 err = np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max()
+ref_ms = None
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+try:
+    import build_ref
+    ext = build_ref.load_diff()
+except Exception as e:      # noqa: BLE001
+    ext, ref_note = None, f"reference extension not available ({e})"
+if ext is not None:
+    inst_t = t[1]
+    depth_t = t[2][..., 3].contiguous()
+    coord_t = t[2][..., :3].contiguous()
+    masks = [inst_t == int(i) for i in ids]
+
+    def run_ref():
+        valid = ext.generate_sobel_valid_mask(inst_t, depth_t)
+        for m in masks:
+            ext.dilate_object_mask(m, valid, coord_t)
+
+    for _ in range(3):
+        run_ref()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        run_ref()
+    torch.cuda.synchronize()
+    ref_ms = (time.perf_counter() - t0) * 1e3 / 50
+    ref_note = f"{ref_ms:.3f} ms for the reference's own mask kernels alone (1 + {len(ids)} launches of diff.cu, before diff.py's per-object tensor program)"
+print(ref_note)
 print(f"pose_grad 640x480, {len(ids)} objects: {gpu_ms:.3f} ms per backward on the GPU, {cpu_ms:.1f} ms CPU oracle (1 core), max rel err {err:.2e}")
