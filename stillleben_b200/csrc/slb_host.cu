@@ -1689,6 +1689,8 @@ extern "C" int slb_jpeg_encode(slb_ctx* ctx, const void* images, int32_t n_image
         return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_jpeg_encode: images must be uint8 HxW, HxWx3 or HxWx4");
     if (height > 65535 || width > 65535) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_jpeg_encode: JPEG dimensions are limited to 65535");
     if (quality < 1 || quality > 100) return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_jpeg_encode: quality must be in 1..100");
+    if (jpeg_blocks(height, width, channels) > 2500000u)   // bit offsets are 32-bit: 1658 bits per block at most
+        return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "slb_jpeg_encode: image too large (more than 2.5 M blocks, about 100 megapixels in colour)");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = enter_stream(ctx, stream);
     const int key[4] = {height, width, channels, quality};

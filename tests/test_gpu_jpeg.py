@@ -87,6 +87,7 @@ def test_argument_checks():
     sizes = torch.zeros(1, dtype=torch.int32, device="cuda")
     assert ctx.lib.slb_jpeg_encode(ctx.h, x.data_ptr(), 1, 8, 8, 3, 0, out.data_ptr(), 4096, sizes.data_ptr(), None) != 0      # quality 0
     assert ctx.lib.slb_jpeg_encode(ctx.h, x.data_ptr(), 1, 8, 8, 2, 80, out.data_ptr(), 4096, sizes.data_ptr(), None) != 0     # 2 channels
+    assert ctx.lib.slb_jpeg_encode(ctx.h, x.data_ptr(), 1, 20000, 20000, 3, 80, out.data_ptr(), 4096, sizes.data_ptr(), None) != 0   # > 2.5 M blocks
     assert ctx.lib.slb_jpeg_encode(ctx.h, x.data_ptr(), 1, 8, 8, 3, 80, out.data_ptr(), 100, sizes.data_ptr(), None) == 0      # too small a stride
     ctx.synchronize()
     assert int(sizes[0]) == 0 and int(out[100:].sum()) == 0
