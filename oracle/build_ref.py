@@ -152,10 +152,11 @@ def build_host(force=False):
             "mesh_vertex_edit.inc": (os.path.join(REF, "src/mesh.cpp"), "void Mesh::updateVertexPositionsAndColors", "void Mesh::setVertexColors"),
             "lightmap_specs.inc": (os.path.join(REF, "src/light_map.cpp"), "    struct IBLSpec", "    Containers::Optional<Magnum::GL::Texture2D> loadTexture"),
             "lightmap_lights.inc": (os.path.join(REF, "src/light_map.cpp"), "        auto addLight = [&]", "    }"),
+            "ssao_tables.inc": (os.path.join(REF, "src/shaders/ssao_shader.cpp"), "    // Create noise texture", "SSAOShader& SSAOShader::bindCoordinates"),
             "object_sticker.inc": (os.path.join(REF, "src/object.cpp"), "Magnum::Matrix4 Object::stickerViewProjection", "void Object::setStatic")}
     for name, (path, first, stop) in cuts.items():
         text = _cut(path, first, stop)
-        assert "GL::" not in text and "physx" not in text.lower()
+        assert ("GL::" not in text or name == "ssao_tables.inc") and "physx" not in text.lower()
         with open(os.path.join(gen, name), "w") as f:
             f.write(text)
     prefix = subprocess.check_output(["bash", os.path.join(HERE, "build_magnum.sh")], text=True).strip().splitlines()[-1]

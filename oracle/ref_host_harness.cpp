@@ -5,6 +5,8 @@
 //   src/mesh.cpp    Mesh::centerBBox / scaleToBBoxDiagonal / updatePretransform / setPretransform / bbox,
 //                   Mesh::recomputeNormals, updateVertexPositionsAndColors, setVertexPositions (the vertex-edit path)
 //   src/object.cpp  Object::stickerViewProjection
+//   src/shaders/ssao_shader.cpp  the SSAO noise / kernel generator of the SSAOShader constructor (std::mt19937{0xdeadbeef}); the
+//                   texture calls between the two loops run against a do-nothing GL::Texture2D
 //   src/light_map.cpp  the sIBL (.ibl) reader: IBLSpec::load, LightSpec::load and, out of LightMap::load, the addLight lambda +
 //                   the Sun / Light1 / Light2 group handling (the texture upload around them is GL and stays out)
 // The classes below declare exactly the members those bodies touch. TEST INFRASTRUCTURE ONLY: tests/test_oracle_ref.py pins the
@@ -29,9 +31,15 @@
 #include <Magnum/Math/ConfigurationValue.h>
 #include <Magnum/Math/Constants.h>
 #include <Magnum/Math/Vector2.h>
+#include <Magnum/ImageView.h>
+#include <Magnum/PixelFormat.h>
+#include <Magnum/Sampler.h>
+#include <Corrade/Containers/Array.h>
+#include <random>
 
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 #include <memory>
 #include <sstream>
@@ -107,6 +115,36 @@ public:
 #include "_ref/gen/object_sticker.inc"
 }  // namespace sl
 
+namespace ssaoref {
+using namespace Magnum;
+namespace GL {
+enum class TextureFormat { RGB32F };
+struct Wrap2 { Wrap2(std::initializer_list<SamplerWrapping>) {} };
+struct Texture2D {   // the calls the constructor makes on its noise texture: accepted; the uploaded texels are kept
+    float texels[48] = {};
+    Texture2D& setStorage(int, TextureFormat, const Vector2i&) { return *this; }
+    Texture2D& setSubImage(int, const Vector2i&, const ImageView2D& image) {
+        std::memcpy(texels, image.data().data(), sizeof texels);
+        return *this;
+    }
+    Texture2D& setWrapping(const Wrap2&) { return *this; }
+    Texture2D& setMinificationFilter(SamplerFilter, SamplerMipmap) { return *this; }
+    Texture2D& setMagnificationFilter(SamplerFilter) { return *this; }
+};
+}  // namespace GL
+struct Generator {
+    GL::Texture2D m_noiseTexture;
+    Vector3 m_ssaoKernel[64];
+    Generator() {
+#include "_ref/gen/ssao_tables.inc"
+};
+void tables(float* noise16x3, float* kernel64x3) {
+    Generator g;
+    std::memcpy(noise16x3, g.m_noiseTexture.texels, sizeof g.m_noiseTexture.texels);
+    for (int i = 0; i < 64; ++i) for (int k = 0; k < 3; ++k) kernel64x3[3 * i + k] = g.m_ssaoKernel[i][k];
+}
+}  // namespace ssaoref
+
 namespace iblref {
 using namespace Corrade;
 using namespace Magnum;
@@ -135,6 +173,7 @@ int lights(const char* path, char* ref_file, int ref_file_cap, float* gamma_mult
 static void put(const Matrix4& m, float* out) { for (int k = 0; k < 16; ++k) out[k] = m.data()[k]; }   // column-major
 
 extern "C" {
+void ref_ssao_tables(float* noise16x3, float* kernel64x3) { ssaoref::tables(noise16x3, kernel64x3); }
 int ref_ibl_lights(const char* path, char* ref_file, int ref_file_cap, float* gamma_multi, float* dirs, float* cols) {
     return iblref::lights(path, ref_file, ref_file_cap, gamma_multi, dirs, cols);
 }

@@ -443,3 +443,24 @@ def test_ibl_reader_matches_the_reference_light_map_parser(tmp_path, monkeypatch
                                   cols.ctypes.data_as(fp)) == -1
         with pytest.raises((RuntimeError, KeyError)):
             sl.LightMap(str(tmp_path / name))
+
+
+def test_ssao_tables_match_reference_generator():
+    """src/shaders/ssao_shader.cpp:72-112 (the noise / kernel loops of the SSAOShader constructor, std::mt19937{0xdeadbeef}) cut out
+    of the reference and run here (oracle/_ref/libhostref.so:ref_ssao_tables) against the oracle's tables — the ones
+    tests/test_glsl_ref.py feeds to the verbatim ssao_shader.frag and the product's slb_host.cu:ssao_tables restates."""
+    import ctypes as C
+    import oracle_util as ou
+    lib, _ = _host_ref()
+    if not hasattr(lib, "ref_ssao_tables"):
+        pytest.skip("oracle/_ref/libhostref.so predates ref_ssao_tables (python oracle/build_ref.py host --force)")
+    lib.ref_ssao_tables.argtypes = [C.c_void_p, C.c_void_p]
+    n_ref, k_ref = np.zeros((16, 3), np.float32), np.zeros((64, 3), np.float32)
+    lib.ref_ssao_tables(n_ref.ctypes.data, k_ref.ctypes.data)
+    orc = C.CDLL(ou.ORACLE_SO)
+    orc.orc_test_ssao_tables.argtypes = [C.c_void_p, C.c_void_p]
+    n_orc, k_orc = np.zeros((16, 3), np.float32), np.zeros((64, 3), np.float32)
+    orc.orc_test_ssao_tables(n_orc.ctypes.data, k_orc.ctypes.data)
+    assert np.abs(n_ref).max() > 0.5 and np.abs(k_ref).max() > 0.3          # the cut really ran
+    np.testing.assert_array_equal(n_orc, n_ref)
+    np.testing.assert_allclose(k_orc, k_ref, rtol=2e-6, atol=1e-7)          # normalized(): Magnum's 1/sqrt(dot) vs the oracle's
