@@ -14,7 +14,12 @@ generate the committed golden fixtures (tests/golden/make_ref_golden.py). Test i
   frame     computeFrustumCorners + computeShadowMapMatrix, extracted verbatim from src/render_pass.cpp at build time and
             compiled against the same GL-less Magnum -> oracle/_ref/libframeref.so
 
-Usage: python oracle/build_ref.py [diff] [meshtool] [glsl] [frame] [host]   (no argument = everything that is not built yet)
+  gl        the reference's GLSL programs run by a real OpenGL implementation: oracle/glref/glref_harness.cpp (the enums, the #define
+            header and every uniform setter of src/shaders/render_shader.cpp cut out and compiled in; the shader files read from
+            /root/reference/src/shaders at run time) + a do-nothing Xlib (oracle/glref/fake_x11.c) under the Mesa llvmpipe libGL that
+            ships with Nsight Compute in this image -> oracle/_ref/glref, oracle/_ref/glx/libX11.so.6, libXext.so.6
+
+Usage: python oracle/build_ref.py [diff] [meshtool] [glsl] [frame] [host] [gl]   (no argument = everything that is not built yet)
 Outputs only into oracle/_ref/ (git-ignored, not gpurun-ignored). Needs /root/reference; a no-op without it.
 """
 import os
@@ -166,11 +171,51 @@ def build_host(force=False):
     return so
 
 
+MESA_LIBGL_GLOB = "/opt/nvidia/nsight-compute/*/host/linux-desktop-glibc_2_11_3-x64/Mesa/libGL.so.1"
+
+
+def find_mesa_libgl():
+    """The software OpenGL of this image: the Mesa 18.1 llvmpipe libGL bundled with Nsight Compute (needs libX11 / libXext, which the
+    image does not have: oracle/glref/fake_x11.c stands in). None when absent."""
+    import glob
+    hits = sorted(glob.glob(os.environ.get("GLREF_LIBGL", MESA_LIBGL_GLOB)))
+    return hits[-1] if hits else None
+
+
+def build_gl(force=False):
+    """oracle/_ref/glref (see the module docstring). The cuts out of src/shaders/render_shader.cpp: the TextureInput / Uniform enums
+    (:34-75), the statements building the #define header (:95-214), every setter (:233-end)."""
+    exe = os.path.join(OUT, "glref")
+    if os.path.exists(exe) and not force:
+        return exe
+    gen, glx = os.path.join(OUT, "gen"), os.path.join(OUT, "glx")
+    os.makedirs(gen, exist_ok=True)
+    os.makedirs(glx, exist_ok=True)
+    src = os.path.join(REF, "src/shaders/render_shader.cpp")
+    lines = open(src).read().splitlines()
+    first = next(i for i, ln in enumerate(lines) if ln.startswith("RenderShader& RenderShader::setTransformations"))
+    cuts = {"render_shader_enums.inc": "namespace\n{\n" + _cut(src, "    enum class TextureInput", "}") + "}\n",
+            "render_shader_header.inc": _cut(src, "    std::string header = ", "    vert.addSource(header)"),
+            "render_shader_setters.inc": f"// cut from {src}:{first + 1}-{len(lines)} by oracle/build_ref.py - do not commit\n" + "\n".join(lines[first:]) + "\n"}
+    for name, text in cuts.items():
+        assert "physx" not in text.lower()
+        with open(os.path.join(gen, name), "w") as f:
+            f.write(text)
+    gl = os.path.join(HERE, "glref")
+    subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", "-Wl,-soname,libX11.so.6", f"-I{gl}", os.path.join(gl, "fake_x11.c"), "-o", os.path.join(glx, "libX11.so.6")])
+    subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", "-Wl,-soname,libXext.so.6", "-x", "c", "/dev/null", "-o", os.path.join(glx, "libXext.so.6")])
+    prefix = subprocess.check_output(["bash", os.path.join(HERE, "build_magnum.sh")], text=True).strip().splitlines()[-1]
+    libs = [f"{prefix}/lib/lib{n}.a" for n in ("MagnumPrimitives", "MagnumTrade", "Magnum", "CorradePluginManager", "CorradeUtility")]
+    subprocess.check_call(["g++", "-std=c++17", "-O1", f"-I{prefix}/include", f"-I{HERE}", f"-I{gl}", os.path.join(gl, "glref_harness.cpp"), "-o", exe,
+                           f"-L{glx}", "-l:libX11.so.6", "-Wl,-rpath,$ORIGIN/glx"] + libs + ["-ldl"])
+    return exe
+
+
 def main(argv):
     if not os.path.isdir(REF):
         print("oracle/build_ref.py: no reference tree at", REF, "- keeping prebuilt oracle/_ref as is")
         return 0
-    want = [a for a in argv if not a.startswith("-")] or ["diff", "meshtool", "glsl", "frame", "host"]
+    want = [a for a in argv if not a.startswith("-")] or ["diff", "meshtool", "glsl", "frame", "host", "gl"]
     if "diff" in want:
         print("diff ->", build_diff(force="--force" in argv))
     if "meshtool" in want:
@@ -181,6 +226,8 @@ def main(argv):
         print("frame ->", build_frame(force="--force" in argv))
     if "host" in want:
         print("host ->", build_host(force="--force" in argv))
+    if "gl" in want:
+        print("gl ->", build_gl(force="--force" in argv))
     return 0
 
 
