@@ -1,4 +1,5 @@
 """Scenes shared by the CPU and GPU tests, built from the committed fixtures in tests/golden/."""
+import copy
 import os
 
 import numpy as np
@@ -249,6 +250,36 @@ def variant(name, width=320, height=240):
     if name == "odd_viewport":
         return synth.tabletop_scene(pool, 25, n_objects=5, width=203, height=117, intrinsics=None)
     raise KeyError(name)
+
+
+def gl_scene_of(name):
+    """The variant as the OpenGL reference harness takes it (tests/test_gl_ref.py, tests/golden/make_gl_golden.py)."""
+    sc = variant(name)
+    if name == "projective":
+        sc.objects = [copy.copy(o) for o in sc.objects]
+        pose = np.array(sc.objects[1].pose, np.float32)
+        pose[3, :3] = 0.0
+        sc.objects[1].pose = pose
+    return sc
+
+
+def single_level_copy(sc):
+    """The scene with every material / plane texture minified by GL_LINEAR (level 0 only): takes LOD selection out of the comparison."""
+    sc = copy.copy(sc)
+    sc.objects = [copy.copy(o) for o in sc.objects]
+    memo = {}
+    for o in sc.objects:
+        if id(o.mesh) not in memo:
+            m = copy.copy(o.mesh)
+            m.images = [copy.copy(im) for im in m.images]
+            for im in m.images:
+                im.min_filter = abi.FILTER_LINEAR
+            memo[id(o.mesh)] = m
+        o.mesh = memo[id(o.mesh)]
+    if sc.background_plane_texture is not None:
+        sc.background_plane_texture = copy.copy(sc.background_plane_texture)
+        sc.background_plane_texture.min_filter = abi.FILTER_LINEAR
+    return sc
 
 
 VARIANTS = ["tabletop", "three_lights", "ssao", "auto_exposure", "no_plane_no_light", "empty", "ibl", "alpha_test", "sticker",

@@ -36,33 +36,7 @@ GL_VARIANTS = ["tabletop", "three_lights", "no_plane_no_light", "empty", "alpha_
                "id_limits", "odd_viewport", "multi_submesh", "low_poly_closeup", "pbr_textures", "projective"]
 
 
-def scene_of(name):
-    sc = fixtures.variant(name)
-    if name == "projective":
-        sc.objects = [copy.copy(o) for o in sc.objects]
-        pose = np.array(sc.objects[1].pose, np.float32)
-        pose[3, :3] = 0.0
-        sc.objects[1].pose = pose
-    return sc
-
-
-def single_level_copy(sc):
-    """The scene with every material / plane texture minified by GL_LINEAR (level 0 only): takes LOD selection out of the comparison."""
-    sc = copy.copy(sc)
-    sc.objects = [copy.copy(o) for o in sc.objects]
-    memo = {}
-    for o in sc.objects:
-        if id(o.mesh) not in memo:
-            m = copy.copy(o.mesh)
-            m.images = [copy.copy(im) for im in m.images]
-            for im in m.images:
-                im.min_filter = abi.FILTER_LINEAR
-            memo[id(o.mesh)] = m
-        o.mesh = memo[id(o.mesh)]
-    if sc.background_plane_texture is not None:
-        sc.background_plane_texture = copy.copy(sc.background_plane_texture)
-        sc.background_plane_texture.min_filter = abi.FILTER_LINEAR
-    return sc
+scene_of, single_level_copy = fixtures.gl_scene_of, fixtures.single_level_copy
 
 
 def visibility_mismatch(g, o):
