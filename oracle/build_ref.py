@@ -197,6 +197,8 @@ def build_gl(force=False):
     cuts = {"render_shader_enums.inc": "namespace\n{\n" + _cut(src, "    enum class TextureInput", "}") + "}\n",
             "render_shader_header.inc": _cut(src, "    std::string header = ", "    vert.addSource(header)"),
             "render_shader_setters.inc": f"// cut from {src}:{first + 1}-{len(lines)} by oracle/build_ref.py - do not commit\n" + "\n".join(lines[first:]) + "\n"}
+    cuts["ssao_tables.inc"] = _cut(os.path.join(REF, "src/shaders/ssao_shader.cpp"), "    // Create noise texture", "SSAOShader& SSAOShader::bindCoordinates")
+    cuts["lightmap_cube.inc"] = _cut(os.path.join(REF, "src/light_map.cpp"), "    struct CubeMapSide", "}")
     for name, text in cuts.items():
         assert "physx" not in text.lower()
         with open(os.path.join(gen, name), "w") as f:

@@ -23,11 +23,15 @@
 #include <Corrade/Utility/Debug.h>
 #include <Corrade/Utility/FormatStl.h>
 #include <Magnum/Magnum.h>
+#include <Magnum/ImageView.h>
+#include <Magnum/PixelFormat.h>
+#include <Magnum/Sampler.h>
 #include <Magnum/Math/Color.h>
 #include <Magnum/Math/Matrix3.h>
 #include <Magnum/Math/Matrix4.h>
 #include <Magnum/Math/Range.h>
 #include <Magnum/Math/Functions.h>
+#include <Magnum/Primitives/Cube.h>
 #include <Magnum/Primitives/Plane.h>
 #include <Magnum/Primitives/Square.h>
 #include <Magnum/Trade/MaterialData.h>
@@ -36,6 +40,8 @@
 
 #include <dlfcn.h>
 #include <algorithm>
+#include <array>
+#include <random>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -104,6 +110,7 @@ struct Texture2D : TextureBase { Texture2D() { target = GL_TEXTURE_2D; } };
 struct RectangleTexture : TextureBase { RectangleTexture() { target = GL_TEXTURE_RECTANGLE; } };
 struct Texture2DArray : TextureBase { Texture2DArray() { target = GL_TEXTURE_2D_ARRAY; } };
 struct CubeMapTexture : TextureBase { CubeMapTexture() { target = GL_TEXTURE_CUBE_MAP; } };
+enum class CubeMapCoordinate : GLenum { PositiveX = 0x8515, NegativeX = 0x8516, PositiveY = 0x8517, NegativeY = 0x8518, PositiveZ = 0x8519, NegativeZ = 0x851A };
 
 // AbstractShaderProgram::setUniform: the overloads the cut code calls (glUniform* on the bound program == Magnum's glProgramUniform*)
 class AbstractShaderProgram {
@@ -194,6 +201,40 @@ std::string RenderShader::buildHeader() {
 
 #include "_ref/gen/render_shader_setters.inc"   // RenderShader::setTransformations ... setShadowMap, and the closing brace of namespace sl
 
+// The SSAO noise texture + hemisphere kernel: the two loops of SSAOShader::SSAOShader (src/shaders/ssao_shader.cpp:72-112, cut out at
+// build time); the texture calls between them land on this GL-backed stand-in and create the real 4x4 RGB32F noise texture.
+namespace ssaogen {
+namespace GL {
+enum class TextureFormat { RGB32F };
+struct Texture2D : Magnum::GL::Texture2D {
+    Texture2D& setStorage(int, TextureFormat, const Vector2i& size) {
+        glGenTextures(1, &id); glBindTexture(GL_TEXTURE_2D, id); glTexStorage2D(GL_TEXTURE_2D, 1, GL_RGB32F, size.x(), size.y()); return *this;
+    }
+    Texture2D& setSubImage(int, const Vector2i&, const ImageView2D& image) {
+        glBindTexture(GL_TEXTURE_2D, id); glPixelStorei(GL_UNPACK_ALIGNMENT, 1);
+        glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, image.size().x(), image.size().y(), GL_RGB, GL_FLOAT, image.data().data()); return *this;
+    }
+    Texture2D& setWrapping(std::initializer_list<SamplerWrapping>) {
+        glBindTexture(GL_TEXTURE_2D, id); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, GL_REPEAT); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, GL_REPEAT); return *this;
+    }
+    Texture2D& setMinificationFilter(SamplerFilter, SamplerMipmap) { glBindTexture(GL_TEXTURE_2D, id); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_NEAREST); return *this; }
+    Texture2D& setMagnificationFilter(SamplerFilter) { glBindTexture(GL_TEXTURE_2D, id); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_NEAREST); return *this; }
+};
+}  // namespace GL
+struct Tables {
+    GL::Texture2D m_noiseTexture;
+    Vector3 m_ssaoKernel[64];
+    Tables() {
+#include "_ref/gen/ssao_tables.inc"
+};
+}  // namespace ssaogen
+
+// CUBE_MAP_SIDES (face + view matrix) and the inside-out cube of LightMap::load (src/light_map.cpp:178-253, cut out at build time)
+namespace lightmapgen {
+namespace GL { using Magnum::GL::CubeMapCoordinate; }
+#include "_ref/gen/lightmap_cube.inc"
+}  // namespace lightmapgen
+
 // ------------------------------------------------------------------------------------------------------------------------------
 // program construction (what Magnum's GL::Shader / AbstractShaderProgram do for RenderShader::RenderShader)
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -222,7 +263,8 @@ static GLuint link_program(const std::vector<GLuint>& stages, const char* what) 
     if (!ok) { char log[8192]; GLsizei n = 0; glGetProgramInfoLog(p, sizeof log, &n, log); fail(std::string(what) + " does not link:\n" + log); }
     return p;
 }
-static const std::string kVersion = "#version 450\n";   // GL::Shader{GL::Version::GL450, ...} (render_shader.cpp:81,92)
+extern const std::string kVersion;
+const std::string kVersion = "#version 450\n";   // GL::Shader{GL::Version::GL450, ...} (render_shader.cpp:81,92)
 
 // ------------------------------------------------------------------------------------------------------------------------------
 // scene dump
@@ -254,8 +296,18 @@ static void upload_texture(TexIn& t) {
     const GLenum fmt = t.ch == 3 ? GL_RGB : GL_RGBA, ifmt = t.ch == 3 ? GL_RGB8 : GL_RGBA8;
     if (t.kind == 1) {
         glBindTexture(GL_TEXTURE_RECTANGLE, t.id);
-        glTexStorage2D(GL_TEXTURE_RECTANGLE, 1, ifmt, t.w, t.h);
-        glTexSubImage2D(GL_TEXTURE_RECTANGLE, 0, 0, 0, t.w, t.h, fmt, GL_UNSIGNED_BYTE, t.px.data());
+        if (std::getenv("GLREF_FLOAT_TEXTURES")) {   // see below: the same texels, stored as float, take llvmpipe's float filtering path
+            std::vector<float> fl((size_t)t.w * t.h * t.ch);
+            for (size_t i = 0; i < fl.size(); ++i) fl[i] = (float)t.px[i] / 255.0f;
+            glTexStorage2D(GL_TEXTURE_RECTANGLE, 1, t.ch == 3 ? GL_RGB32F : GL_RGBA32F, t.w, t.h);
+            glTexSubImage2D(GL_TEXTURE_RECTANGLE, 0, 0, 0, t.w, t.h, fmt, GL_FLOAT, fl.data());
+        } else {
+            glTexStorage2D(GL_TEXTURE_RECTANGLE, 1, ifmt, t.w, t.h);
+            glTexSubImage2D(GL_TEXTURE_RECTANGLE, 0, 0, 0, t.w, t.h, fmt, GL_UNSIGNED_BYTE, t.px.data());
+        }
+        // wrapping: GL's default for rectangle textures is clamp-to-edge (sl.Texture(tensor), py_magnum.cpp:147-151); Context::loadTexture
+        // (context.cpp:596-598) switches to clamp-to-border with GL's default transparent-black border. REPEAT is not legal on this target.
+        if (t.wrap_s == 3) { glTexParameteri(GL_TEXTURE_RECTANGLE, GL_TEXTURE_WRAP_S, GL_CLAMP_TO_BORDER); glTexParameteri(GL_TEXTURE_RECTANGLE, GL_TEXTURE_WRAP_T, GL_CLAMP_TO_BORDER); }
         glTexParameteri(GL_TEXTURE_RECTANGLE, GL_TEXTURE_MIN_FILTER, (GLint)filter_of(t.min_f > 1 ? 1 : t.min_f));
         glTexParameteri(GL_TEXTURE_RECTANGLE, GL_TEXTURE_MAG_FILTER, (GLint)filter_of(t.mag_f));
     } else {
@@ -353,6 +405,128 @@ static PrimGL upload_primitive(const Trade::MeshData& d, bool three_d) {
     return p;
 }
 
+// MeshTools::compile of an indexed triangle primitive: positions on attribute 0 (the only attribute the cube programs read)
+static PrimGL upload_indexed(const Trade::MeshData& d) {
+    PrimGL p;
+    const Containers::Array<Vector3> pos = d.positions3DAsArray();
+    const Containers::Array<UnsignedInt> idx = d.indicesAsArray();
+    p.count = (GLsizei)idx.size();
+    GLuint vbo, ibo;
+    glGenVertexArrays(1, &p.vao); glBindVertexArray(p.vao);
+    glGenBuffers(1, &vbo); glBindBuffer(GL_ARRAY_BUFFER, vbo); glBufferData(GL_ARRAY_BUFFER, (GLsizeiptr)(pos.size() * 12), pos.data(), GL_STATIC_DRAW);
+    glGenBuffers(1, &ibo); glBindBuffer(GL_ELEMENT_ARRAY_BUFFER, ibo); glBufferData(GL_ELEMENT_ARRAY_BUFFER, (GLsizeiptr)(idx.size() * 4), idx.data(), GL_STATIC_DRAW);
+    glEnableVertexAttribArray(0); glVertexAttribPointer(0, 3, GL_FLOAT, GL_FALSE, 12, (const void*)0);
+    glBindVertexArray(0);
+    check_gl("indexed primitive upload");
+    return p;
+}
+
+// LightMap::load from the equirectangular image on (src/light_map.cpp:355-611): equirect -> cube (+ mips), irradiance convolution,
+// GGX prefilter (5 levels), BRDF LUT, each a draw of the reference's cubemap_shader_* / brdf_shader programs. Sizes are the caller's
+// (the reference's: 512 / 32 / 128 / 512); the sample counts live in the shader text.
+struct LightMapIn { int w = 0, h = 0; std::vector<float> eq; int n_lights = 0; float dirs[9], cols[9]; int sizes[4]; };
+static std::string read_file(const std::string& name);
+static GLuint compile_stage(GLenum type, const std::vector<std::string>& sources, const char* what);
+static GLuint link_program(const std::vector<GLuint>& stages, const char* what);
+extern const std::string kVersion;
+static void cube_params(GLuint id, int levels, int size) {
+    glBindTexture(GL_TEXTURE_CUBE_MAP, id);
+    glTexStorage2D(GL_TEXTURE_CUBE_MAP, levels, GL_RGBA32F, size, size);
+    glTexParameteri(GL_TEXTURE_CUBE_MAP, GL_TEXTURE_WRAP_S, GL_CLAMP_TO_EDGE); glTexParameteri(GL_TEXTURE_CUBE_MAP, GL_TEXTURE_WRAP_T, GL_CLAMP_TO_EDGE);
+    glTexParameteri(GL_TEXTURE_CUBE_MAP, GL_TEXTURE_WRAP_R, GL_CLAMP_TO_EDGE);
+    glTexParameteri(GL_TEXTURE_CUBE_MAP, GL_TEXTURE_MIN_FILTER, GL_LINEAR_MIPMAP_LINEAR); glTexParameteri(GL_TEXTURE_CUBE_MAP, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
+}
+static void load_light_map(const LightMapIn& in, sl::LightMap& lm, const PrimGL& texturedPlane) {
+    const std::string compat = read_file("compatibility.glsl"), common = read_file("common.glsl");
+    GL::Texture2D equirect;                                   // :364-373 (the .hdr branch; loadTexture :166-174 is the same set-up)
+    glGenTextures(1, &equirect.id); glBindTexture(GL_TEXTURE_2D, equirect.id);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_LINEAR); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR_MIPMAP_LINEAR);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, GL_CLAMP_TO_EDGE); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, GL_CLAMP_TO_EDGE);
+    { GLfloat aniso = 1.0f; glGetFloatv(GL_MAX_TEXTURE_MAX_ANISOTROPY, &aniso); if (glGetError() == GL_NO_ERROR && aniso > 1.0f && !std::getenv("GLREF_NO_ANISO")) glTexParameterf(GL_TEXTURE_2D, GL_TEXTURE_MAX_ANISOTROPY, aniso); }
+    glTexStorage2D(GL_TEXTURE_2D, (int)Math::log2((UnsignedInt)in.w) + 1, GL_RGB32F, in.w, in.h);
+    glPixelStorei(GL_UNPACK_ALIGNMENT, 1);
+    glTexSubImage2D(GL_TEXTURE_2D, 0, 0, 0, in.w, in.h, GL_RGB, GL_FLOAT, in.eq.data());
+    glGenerateMipmap(GL_TEXTURE_2D);
+    glEnable(GL_TEXTURE_CUBE_MAP_SEAMLESS);                   // :376
+    const int envSize = in.sizes[0], irrSize = in.sizes[1], preSize = in.sizes[2], lutSize = in.sizes[3];
+    GLuint fb, depth; glGenFramebuffers(1, &fb); glGenRenderbuffers(1, &depth);
+    auto target = [&](int size) {                             // framebuffer.setViewport + depthBuffer.setStorage + attach (:380-384, :462-464, ...)
+        glBindRenderbuffer(GL_RENDERBUFFER, depth); glRenderbufferStorage(GL_RENDERBUFFER, GL_DEPTH_COMPONENT24, size, size);
+        glBindFramebuffer(GL_FRAMEBUFFER, fb); glFramebufferRenderbuffer(GL_FRAMEBUFFER, GL_DEPTH_ATTACHMENT, GL_RENDERBUFFER, depth);
+        glViewport(0, 0, size, size);
+    };
+    const PrimGL cube = upload_indexed(lightmapgen::cubeFromInside());   // :388
+    const Matrix4 perspective = Matrix4::perspectiveProjection(Deg{90.0f}, 1.0f, 0.1f, 10.0f);   // :389
+    auto cube_program = [&](const char* frag) {               // CubeMapShader::CubeMapShader (cubemap_shader.cpp:41-62); uniforms: projection 0, view 1, roughness 2
+        return link_program({compile_stage(GL_VERTEX_SHADER, {kVersion, compat, read_file("cubemap_shader.vert")}, "cubemap_shader.vert"),
+                             compile_stage(GL_FRAGMENT_SHADER, {kVersion, compat, read_file(frag)}, frag)}, frag);
+    };
+    auto draw_faces = [&](GLuint prog, GLuint dst, int level) {
+        for (const auto& side : lightmapgen::CUBE_MAP_SIDES) {
+            glBindFramebuffer(GL_FRAMEBUFFER, fb);
+            glFramebufferTexture2D(GL_FRAMEBUFFER, GL_COLOR_ATTACHMENT0, (GLenum)side.coordinate, dst, level);
+            const GLenum b = GL_COLOR_ATTACHMENT0; glDrawBuffers(1, &b);
+            if (glCheckFramebufferStatus(GL_FRAMEBUFFER) != GL_FRAMEBUFFER_COMPLETE) fail("cube framebuffer incomplete");
+            glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+            glUseProgram(prog); glUniformMatrix4fv(1, 1, GL_FALSE, side.view.data());
+            glBindVertexArray(cube.vao); glDrawElements(GL_TRIANGLES, cube.count, GL_UNSIGNED_INT, nullptr);
+        }
+    };
+    // equirectangular -> cube map (:391-446)
+    glGenTextures(1, &lm.cube.id); cube_params(lm.cube.id, (int)Math::log2((UnsignedInt)envSize) + 1, envSize);
+    target(envSize);
+    {
+        const GLuint prog = cube_program("cubemap_shader_equirectangular.frag");
+        glUseProgram(prog); glUniformMatrix4fv(0, 1, GL_FALSE, perspective.data());
+        equirect.bind(0);
+        draw_faces(prog, lm.cube.id, 0);
+        glBindTexture(GL_TEXTURE_CUBE_MAP, lm.cube.id); glGenerateMipmap(GL_TEXTURE_CUBE_MAP);
+    }
+    // irradiance (:448-509)
+    glGenTextures(1, &lm.irradiance.id); cube_params(lm.irradiance.id, (int)Math::log2((UnsignedInt)irrSize) + 1, irrSize);
+    target(irrSize);
+    {
+        const GLuint prog = cube_program("cubemap_shader_irradiance.frag");
+        glUseProgram(prog); glUniformMatrix4fv(0, 1, GL_FALSE, perspective.data());
+        lm.cube.bind(0);
+        draw_faces(prog, lm.irradiance.id, 0);
+        glBindTexture(GL_TEXTURE_CUBE_MAP, lm.irradiance.id); glGenerateMipmap(GL_TEXTURE_CUBE_MAP);
+    }
+    // prefilter (:511-567): MAX_MIP_LEVELS 5, roughness = mip / 4
+    glGenTextures(1, &lm.prefilter.id); cube_params(lm.prefilter.id, 5, preSize);
+    {
+        const GLuint prog = cube_program("cubemap_shader_prefilter.frag");
+        glUseProgram(prog); glUniformMatrix4fv(0, 1, GL_FALSE, perspective.data());
+        lm.cube.bind(0);
+        for (int mip = 0; mip < 5; ++mip) {
+            const int mipSize = (int)(preSize * Math::pow(0.5f, (float)mip));
+            target(mipSize);
+            glUseProgram(prog); glUniform1f(2, (float)mip / 4.0f);
+            draw_faces(prog, lm.prefilter.id, mip);
+        }
+    }
+    // BRDF LUT (:569-600): the textured plane primitive drawn with brdf_shader
+    glGenTextures(1, &lm.lut.id); glBindTexture(GL_TEXTURE_2D, lm.lut.id);
+    glTexStorage2D(GL_TEXTURE_2D, (int)Math::log2((UnsignedInt)lutSize) + 1, GL_RGBA32F, lutSize, lutSize);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, GL_CLAMP_TO_EDGE); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, GL_CLAMP_TO_EDGE);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR_MIPMAP_LINEAR); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
+    target(lutSize);
+    {
+        glFramebufferTexture2D(GL_FRAMEBUFFER, GL_COLOR_ATTACHMENT0, GL_TEXTURE_2D, lm.lut.id, 0);
+        const GLenum b = GL_COLOR_ATTACHMENT0; glDrawBuffers(1, &b);
+        glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT);
+        const GLuint prog = link_program({compile_stage(GL_VERTEX_SHADER, {kVersion, compat, common, read_file("brdf_shader.vert")}, "brdf_shader.vert"),
+                                          compile_stage(GL_FRAGMENT_SHADER, {kVersion, compat, read_file("brdf_shader.frag")}, "brdf_shader.frag")}, "brdf shader");
+        glUseProgram(prog);
+        glBindVertexArray(texturedPlane.vao); glDrawArrays(GL_TRIANGLE_STRIP, 0, texturedPlane.count);
+        glBindTexture(GL_TEXTURE_2D, lm.lut.id); glGenerateMipmap(GL_TEXTURE_2D);
+    }
+    lm.directions = Containers::Array<Vector3>{(std::size_t)in.n_lights}; lm.colors = Containers::Array<Color3>{(std::size_t)in.n_lights};
+    for (int i = 0; i < in.n_lights; ++i) { lm.directions[i] = Vector3{in.dirs[3 * i], in.dirs[3 * i + 1], in.dirs[3 * i + 2]}; lm.colors[i] = Color3{in.cols[3 * i], in.cols[3 * i + 1], in.cols[3 * i + 2]}; }
+    glBindFramebuffer(GL_FRAMEBUFFER, 0);
+    check_gl("light map");
+}
+
 static GLuint make_rect(GLenum ifmt, int W, int H, bool nearest) {
     GLuint t; glGenTextures(1, &t); glBindTexture(GL_TEXTURE_RECTANGLE, t);
     glTexStorage2D(GL_TEXTURE_RECTANGLE, 1, ifmt, W, H);
@@ -371,7 +545,7 @@ int main(int argc, char** argv) {
         if (!f) fail("cannot read the scene dump");
         r.buf.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
     }
-    if (r.get<UnsignedInt>() != 0x46524C47u || r.get<UnsignedInt>() != 1u) fail("not a glref scene dump");
+    if (r.get<UnsignedInt>() != 0x46524C47u || r.get<UnsignedInt>() != 2u) fail("not a glref scene dump (version 2)");
     const int W = r.get<int>(), H = r.get<int>();
     const Matrix4 P = r.mat4(), V = r.mat4();
     Vector3 lightDir[3]; Color3 lightCol[3]; Color3 ambient;
@@ -382,11 +556,16 @@ int main(int argc, char** argv) {
     Vector2 planeSize; r.take(planeSize.data(), 8);
     const Matrix4 planePose = r.mat4();
     const int planeTex = r.get<int>();
-    const int backgroundImage = r.get<int>(); (void)backgroundImage;
+    const int backgroundImage = r.get<int>();
     const float manualExposure = r.get<float>();
-    const int ssao = r.get<int>(); (void)ssao;
+    const int ssao = r.get<int>();
     const int hasLightMap = r.get<int>();
-    if (hasLightMap) fail("light maps are not part of this harness yet");
+    LightMapIn lmIn;
+    if (hasLightMap) {
+        lmIn.w = r.get<int>(); lmIn.h = r.get<int>();
+        lmIn.eq.resize((size_t)lmIn.w * lmIn.h * 3); r.take(lmIn.eq.data(), lmIn.eq.size() * 4);
+        lmIn.n_lights = r.get<int>(); r.take(lmIn.dirs, 36); r.take(lmIn.cols, 36); r.take(lmIn.sizes, 16);
+    }
     const int hasPeel = r.get<int>();
     std::vector<float> peel((size_t)W * H * 4, 0.0f);   // m_zeroMinDepth (render_pass.cpp:411-419)
     if (hasPeel) r.take(peel.data(), peel.size() * 4);
@@ -414,6 +593,9 @@ int main(int argc, char** argv) {
     for (MeshIn& m : meshes) upload_mesh(m);
     const PrimGL plane = upload_primitive(Primitives::planeSolid(Primitives::PlaneFlag::TextureCoordinates), true);   // render_pass.cpp:268
     const PrimGL quad = upload_primitive(Primitives::squareSolid(), false);                                          // render_pass.cpp:266
+    const PrimGL skyCube = upload_indexed(Primitives::cubeSolid());                                                  // render_pass.cpp:267
+    sl::LightMap lightMap;
+    if (hasLightMap) load_light_map(lmIn, lightMap, plane);
 
     // programs ------------------------------------------------------------------------------------------------------------------
     sl::RenderShader render;
@@ -438,6 +620,17 @@ int main(int argc, char** argv) {
         toneProg = link_program({compile_stage(GL_VERTEX_SHADER, {kVersion, header, read_file("tone_map_shader.vert")}, "tone_map_shader.vert"),
                                  compile_stage(GL_FRAGMENT_SHADER, {kVersion, header, read_file("tone_map_shader.frag")}, "tone_map_shader.frag")}, "tone map shader");
     }
+    // BackgroundShader / BackgroundCubeShader / SSAOShader / SSAOApplyShader constructors: compatibility.glsl [+ common.glsl for the
+    // vertex stage] + the stage source (background_shader.cpp:25-47, background_cube_shader.cpp, ssao_shader.cpp:41-55, ssao_apply_shader.cpp)
+    const std::string compat = read_file("compatibility.glsl"), common = read_file("common.glsl");
+    auto post_program = [&](const char* vert, const char* frag) {
+        return link_program({compile_stage(GL_VERTEX_SHADER, {kVersion, compat, common, read_file(vert)}, vert),
+                             compile_stage(GL_FRAGMENT_SHADER, {kVersion, compat, read_file(frag)}, frag)}, frag);
+    };
+    const GLuint bgProg = backgroundImage >= 0 ? post_program("background_shader.vert", "background_shader.frag") : 0;
+    const GLuint bgCubeProg = hasLightMap ? post_program("background_cube_shader.vert", "background_cube_shader.frag") : 0;
+    const GLuint ssaoProg = ssao ? post_program("ssao_shader.vert", "ssao_shader.frag") : 0;
+    const GLuint ssaoApplyProg = ssao ? post_program("ssao_apply_shader.vert", "ssao_apply_shader.frag") : 0;
     check_gl("programs");
 
     // RenderPass::RenderPass (render_pass.cpp:271-292): 2048 x 2048 x NumLights depth array, linear filter, compare LEQUAL -----------------
@@ -475,6 +668,15 @@ int main(int argc, char** argv) {
     glGenTextures(1, &postprocessInput.id); glBindTexture(GL_TEXTURE_2D, postprocessInput.id);
     glTexStorage2D(GL_TEXTURE_2D, levels, GL_RGBA32F, W, H);
     glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR_MIPMAP_LINEAR); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAX_LEVEL, levels - 1);
+    GL::Texture2D ssaoRGBInput, ssaoTexture;                  // render_pass.cpp:388-397
+    if (ssao) {
+        glGenTextures(1, &ssaoRGBInput.id); glBindTexture(GL_TEXTURE_2D, ssaoRGBInput.id);
+        glTexStorage2D(GL_TEXTURE_2D, levels, GL_RGBA32F, W, H);
+        glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR_MIPMAP_LINEAR); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_NEAREST);
+        glGenTextures(1, &ssaoTexture.id); glBindTexture(GL_TEXTURE_2D, ssaoTexture.id);
+        glTexStorage2D(GL_TEXTURE_2D, 1, GL_R32F, W, H);
+        glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_NEAREST); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_NEAREST);
+    }
     GL::RectangleTexture minDepth;
     glGenTextures(1, &minDepth.id); glBindTexture(GL_TEXTURE_RECTANGLE, minDepth.id);
     glTexParameteri(GL_TEXTURE_RECTANGLE, GL_TEXTURE_MAG_FILTER, GL_LINEAR);
@@ -505,7 +707,7 @@ int main(int argc, char** argv) {
 
     // main framebuffer (render_pass.cpp:468-532)
     GLuint fb; glGenFramebuffers(1, &fb); glBindFramebuffer(GL_FRAMEBUFFER, fb); glViewport(0, 0, W, H);
-    glFramebufferTexture2D(GL_FRAMEBUFFER, GL_COLOR_ATTACHMENT0, GL_TEXTURE_2D, postprocessInput.id, 0);
+    glFramebufferTexture2D(GL_FRAMEBUFFER, GL_COLOR_ATTACHMENT0, GL_TEXTURE_2D, ssao ? ssaoRGBInput.id : postprocessInput.id, 0);   // :469-473
     const GLuint rects[7] = {coordTex, classTex, instTex, normalTex, vidxTex, baryTex, camTex};
     for (int i = 0; i < 7; ++i) glFramebufferTexture2D(GL_FRAMEBUFFER, GL_COLOR_ATTACHMENT0 + 1 + i, GL_TEXTURE_RECTANGLE, rects[i], 0);
     glFramebufferRenderbuffer(GL_FRAMEBUFFER, GL_DEPTH_ATTACHMENT, GL_RENDERBUFFER, depthRB);
@@ -520,7 +722,8 @@ int main(int argc, char** argv) {
     check_gl("clears");
 
     // lighting + per-frame uniforms (render_pass.cpp:534-543)
-    {
+    if (hasLightMap) render.setLightMap(lightMap);
+    else {
         Containers::Array<Vector3> dirs{3}; Containers::Array<Color3> cols{3};
         for (int i = 0; i < 3; ++i) { dirs[i] = lightDir[i]; cols[i] = lightCol[i]; }
         render.setManualLighting(dirs, cols, ambient);
@@ -590,12 +793,51 @@ int main(int argc, char** argv) {
     }
     check_gl("main pass");
     glFrontFace(GL_CCW);                                                        // render_pass.cpp:630
-    glBindTexture(GL_TEXTURE_2D, postprocessInput.id); glGenerateMipmap(GL_TEXTURE_2D);   // :632-635 (SSAO off: m_postprocessInput)
+    glBindTexture(GL_TEXTURE_2D, ssao ? ssaoRGBInput.id : postprocessInput.id); glGenerateMipmap(GL_TEXTURE_2D);   // :632-635
 
-    // the HDR buffer the tone map reads
-    std::vector<float> hdr((size_t)W * H * 4);
-    glPixelStorei(GL_PACK_ALIGNMENT, 1);
-    glBindTexture(GL_TEXTURE_2D, postprocessInput.id); glGetTexImage(GL_TEXTURE_2D, 0, GL_RGBA, GL_FLOAT, hdr.data());
+    // background image or sky box into colour attachment 0 only (render_pass.cpp:637-660)
+    if (backgroundImage >= 0) {
+        const GLenum b = GL_COLOR_ATTACHMENT0; glDrawBuffers(1, &b);
+        glUseProgram(bgProg);
+        GL::RectangleTexture bg; bg.id = tex[backgroundImage].id; bg.bind(0);
+        glBindVertexArray(quad.vao); glDrawArrays(GL_TRIANGLE_STRIP, 0, quad.count);
+    } else if (hasLightMap) {
+        const GLenum b = GL_COLOR_ATTACHMENT0; glDrawBuffers(1, &b);
+        glDepthFunc(GL_LEQUAL);
+        glUseProgram(bgCubeProg);
+        lightMap.cubeMap().bind(0);
+        glUniformMatrix4fv(0, 1, GL_FALSE, V.data());       // setViewMatrix(cameraMatrix): location 0
+        glUniformMatrix4fv(1, 1, GL_FALSE, P.data());       // setProjectionMatrix: location 1
+        glBindVertexArray(skyCube.vao); glDrawElements(GL_TRIANGLES, skyCube.count, GL_UNSIGNED_INT, nullptr);
+        glDepthFunc(GL_LESS);
+    }
+    check_gl("background");
+
+    if (ssao) {   // render_pass.cpp:662-694
+        ssaogen::Tables tables;                              // SSAOShader's constructor data: noise texture + kernel
+        GLuint ssaoFB; glGenFramebuffers(1, &ssaoFB); glBindFramebuffer(GL_FRAMEBUFFER, ssaoFB); glViewport(0, 0, W, H);
+        glFramebufferTexture2D(GL_FRAMEBUFFER, GL_COLOR_ATTACHMENT0, GL_TEXTURE_2D, ssaoTexture.id, 0);
+        { const GLenum b = GL_COLOR_ATTACHMENT0; glDrawBuffers(1, &b); }
+        if (glCheckFramebufferStatus(GL_FRAMEBUFFER) != GL_FRAMEBUFFER_COMPLETE) fail("SSAO framebuffer incomplete");
+        const GLfloat one4[4] = {1, 1, 1, 1}; glClearBufferfv(GL_COLOR, 0, one4);
+        glUseProgram(ssaoProg);
+        glUniformMatrix4fv(65, 1, GL_FALSE, P.data());                                  // setProjection: m_projectionUniform{65} (ssao_shader.h:69)
+        GL::RectangleTexture camR, nrmR; camR.id = camTex; nrmR.id = normalTex;
+        camR.bind(0); nrmR.bind(1);                                                      // CoordinateLayer 0, NormalLayer 1
+        tables.m_noiseTexture.bind(2);                                                   // bindNoise: NoiseLayer 2 + the kernel at m_samplesUniform{0}
+        glUniform3fv(0, 64, tables.m_ssaoKernel[0].data());
+        glBindVertexArray(quad.vao); glDrawArrays(GL_TRIANGLE_STRIP, 0, quad.count);
+
+        GLuint applyFB; glGenFramebuffers(1, &applyFB); glBindFramebuffer(GL_FRAMEBUFFER, applyFB); glViewport(0, 0, W, H);
+        glFramebufferTexture2D(GL_FRAMEBUFFER, GL_COLOR_ATTACHMENT0, GL_TEXTURE_2D, postprocessInput.id, 0);
+        { const GLenum b = GL_COLOR_ATTACHMENT0; glDrawBuffers(1, &b); }
+        if (glCheckFramebufferStatus(GL_FRAMEBUFFER) != GL_FRAMEBUFFER_COMPLETE) fail("SSAO apply framebuffer incomplete");
+        glClearBufferfv(GL_COLOR, 0, zero4);
+        glUseProgram(ssaoApplyProg);
+        ssaoTexture.bind(1); ssaoRGBInput.bind(0); camR.bind(2);                         // bindAO 1, bindColor 0, bindCoordinates 2 (ssao_apply_shader.cpp:24-29)
+        glBindVertexArray(quad.vao); glDrawArrays(GL_TRIANGLE_STRIP, 0, quad.count);
+        check_gl("SSAO");
+    }
 
     // tone map (render_pass.cpp:696-710)
     GLuint postFB; glGenFramebuffers(1, &postFB); glBindFramebuffer(GL_FRAMEBUFFER, postFB); glViewport(0, 0, W, H);
@@ -603,11 +845,17 @@ int main(int argc, char** argv) {
     { const GLenum b = GL_COLOR_ATTACHMENT0; glDrawBuffers(1, &b); }
     if (glCheckFramebufferStatus(GL_FRAMEBUFFER) != GL_FRAMEBUFFER_COMPLETE) fail("post-process framebuffer incomplete");
     glUseProgram(toneProg);
-    postprocessInput.bind(0); postprocessInput.bind(1);
+    postprocessInput.bind(0);                                                            // bindColor(m_postprocessInput)
+    if (ssao) ssaoRGBInput.bind(1); else postprocessInput.bind(1);                       // bindObjectLuminance
     glUniform1f(0, manualExposure);
     glBindVertexArray(quad.vao); glDrawArrays(GL_TRIANGLE_STRIP, 0, quad.count);
     glFinish();
     check_gl("tone map");
+
+    // the HDR buffer the tone map read
+    std::vector<float> hdr((size_t)W * H * 4);
+    glPixelStorei(GL_PACK_ALIGNMENT, 1);
+    glBindTexture(GL_TEXTURE_2D, postprocessInput.id); glGetTexImage(GL_TEXTURE_2D, 0, GL_RGBA, GL_FLOAT, hdr.data());
 
     // read back (row 0 = window y 0, SURVEY 8 preamble: no flip)
     std::vector<unsigned char> rgb((size_t)W * H * 4);
@@ -625,6 +873,19 @@ int main(int argc, char** argv) {
     put(rgb.data(), rgb.size()); put(coord.data(), coord.size() * 4); put(cls.data(), cls.size() * 2); put(inst.data(), inst.size() * 2);
     put(normals.data(), normals.size() * 4); put(vidx.data(), vidx.size() * 4); put(bary.data(), bary.size() * 4); put(cam.data(), cam.size() * 4);
     put(hdr.data(), hdr.size() * 4);
+    if (hasLightMap) {   // the precomputed maps, in the layout of slb_lightmap_read: env level 0, irradiance, prefilter levels, LUT
+        auto put_cube = [&](GLuint id, int level, int size) {
+            std::vector<float> face((size_t)size * size * 4);
+            glBindTexture(GL_TEXTURE_CUBE_MAP, id);
+            for (int f = 0; f < 6; ++f) { glGetTexImage(GL_TEXTURE_CUBE_MAP_POSITIVE_X + f, level, GL_RGBA, GL_FLOAT, face.data()); put(face.data(), face.size() * 4); }
+        };
+        put_cube(lightMap.cube.id, 0, lmIn.sizes[0]);
+        put_cube(lightMap.irradiance.id, 0, lmIn.sizes[1]);
+        for (int mip = 0; mip < 5; ++mip) put_cube(lightMap.prefilter.id, mip, lmIn.sizes[2] >> mip);
+        std::vector<float> lut((size_t)lmIn.sizes[3] * lmIn.sizes[3] * 4);
+        glBindTexture(GL_TEXTURE_2D, lightMap.lut.id); glGetTexImage(GL_TEXTURE_2D, 0, GL_RGBA, GL_FLOAT, lut.data());
+        put(lut.data(), lut.size() * 4);
+    }
     if (std::getenv("GLREF_DUMP_SHADOW")) {   // light 0's depth layer as float, for debugging shadow-edge differences
         std::vector<float> sm((size_t)SR * SR * 3);
         glBindTexture(GL_TEXTURE_2D_ARRAY, shadowMaps.id); glGetTexImage(GL_TEXTURE_2D_ARRAY, 0, GL_DEPTH_COMPONENT, GL_FLOAT, sm.data());

@@ -91,11 +91,15 @@ def _image_from(arg):
 
 
 class Texture:
-    """Rectangle texture (pixel coordinates, clamp-to-border transparent): background image / sticker."""
+    """Rectangle texture (pixel coordinates, linear filter): background image / sticker. Loaded from a file it clamps to a transparent
+    border (Context::loadTexture, src/context.cpp:596-598); built from a tensor it keeps GL's default for rectangle textures,
+    clamp-to-edge (py_magnum.cpp:147-151 sets no wrapping) - the difference shows on the first texel row / column of a background
+    image, which background_shader.frag samples on texel CORNERS (tests/test_gl_ref.py runs that shader on a real GL)."""
 
     def __init__(self, arg):
-        self.image = ImageData(_image_from(arg), wrap_s=abi.WRAP_CLAMP_TO_BORDER, wrap_t=abi.WRAP_CLAMP_TO_BORDER,
-                               min_filter=abi.FILTER_LINEAR, mag_filter=abi.FILTER_LINEAR, kind=abi.TEXTURE_RECT)
+        wrap = abi.WRAP_CLAMP_TO_BORDER if isinstance(arg, (str, os.PathLike)) else abi.WRAP_CLAMP_TO_EDGE
+        self.image = ImageData(_image_from(arg), wrap_s=wrap, wrap_t=wrap, min_filter=abi.FILTER_LINEAR, mag_filter=abi.FILTER_LINEAR,
+                               kind=abi.TEXTURE_RECT)
 
 
 class Texture2D:

@@ -282,6 +282,17 @@ def single_level_copy(sc):
     return sc
 
 
+def gl_post_scene(name):
+    """The two post-pass scenes of the OpenGL goldens (tests/golden/make_gl_golden.py, tests/test_gl_golden.py): 'ssao' = the ssao variant with
+    level-0 texture filtering; 'ibl' = the ibl variant (SSAO on) with level-0 filtering and roughness in quarters (whole prefilter levels)."""
+    sc = single_level_copy(variant(name))
+    if name == "ibl":
+        for k, ob in enumerate(sc.objects):
+            ob.roughness = (0.25, 0.5, 0.75, 1.0)[k % 4]
+        sc.light_map = copy.copy(sc.light_map)
+    return sc
+
+
 VARIANTS = ["tabletop", "three_lights", "ssao", "auto_exposure", "no_plane_no_light", "empty", "ibl", "alpha_test", "sticker",
             "background_image", "plane_texture", "near_clip", "predicate", "id_limits", "odd_viewport", "multi_submesh", "low_poly_closeup",
             "pbr_textures", "pbr_textures_ibl", "projective", "c2_shape", "c5_shape"]

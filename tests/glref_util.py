@@ -38,6 +38,17 @@ def _cm(m):
     return np.ascontiguousarray(np.asarray(m, np.float32).reshape(4, 4).T).tobytes()   # row-major m[r, c] -> column-major
 
 
+def scene_lights(scene):
+    """(directions, colours) the render pass uses: the light map's first three when there is one (render_pass.cpp:426-439), else the scene's."""
+    if scene.light_map is None:
+        return np.asarray(scene.light_directions, np.float32).reshape(3, 3), np.asarray(scene.light_colors, np.float32).reshape(3, 3)
+    ld, lc = np.zeros((3, 3), np.float32), np.zeros((3, 3), np.float32)
+    n = min(3, len(scene.light_map.light_directions))
+    ld[:n] = np.asarray(scene.light_map.light_directions, np.float32).reshape(-1, 3)[:n]
+    lc[:n] = np.asarray(scene.light_map.light_colors, np.float32).reshape(-1, 3)[:n]
+    return ld, lc
+
+
 def oracle_shadow_matrices(scene):
     """The oracle's frustum corners + shadow matrix per active light (render_pass.cpp:69-211; pinned on the reference's own two
     functions by tests/test_oracle_ref.py) — handed to the GL harness so that both sides use the SAME matrices."""
@@ -54,8 +65,7 @@ def oracle_shadow_matrices(scene):
     bmax = as_f([np.asarray(o.mesh.bbox_max, np.float32) for o in objs], 3)
     Pc = np.ascontiguousarray(np.asarray(scene.projection, np.float32).T.reshape(-1))
     Vc = np.ascontiguousarray(np.asarray(scene.world_to_cam, np.float32).T.reshape(-1))
-    ld = np.asarray(scene.light_directions, np.float32).reshape(3, 3)
-    lc = np.asarray(scene.light_colors, np.float32).reshape(3, 3)
+    ld, lc = scene_lights(scene)
     active, mats = [], []
     for i in range(3):
         on = bool(np.any(lc[i] != 0) and np.any(ld[i] != 0))          # render_pass.cpp:433
@@ -68,9 +78,10 @@ def oracle_shadow_matrices(scene):
     return active, mats
 
 
-def dump(scene, path, peel=None):
-    if scene.light_map is not None:
-        raise NotImplementedError("light maps are not part of the GL harness")
+REFERENCE_LIGHTMAP_SIZES = (512, 32, 128, 512)     # environment cube, irradiance, prefilter, BRDF LUT (src/light_map.cpp:378,451,515,572)
+
+
+def dump(scene, path, peel=None, lightmap_sizes=REFERENCE_LIGHTMAP_SIZES):
     textures, tex_index = [], {}
 
     def tex_of(img):
@@ -87,13 +98,24 @@ def dump(scene, path, peel=None):
             mesh_index[id(o.mesh)] = len(meshes)
             meshes.append(o.mesh)
     active, shadow = oracle_shadow_matrices(scene)
-    out = [struct.pack("<IIii", 0x46524C47, 1, scene.width, scene.height), _cm(scene.projection), _cm(scene.world_to_cam),
-           np.asarray(scene.light_directions, np.float32).reshape(9).tobytes(), np.asarray(scene.light_colors, np.float32).reshape(9).tobytes(),
-           np.asarray(scene.ambient_light, np.float32).reshape(3).tobytes(), struct.pack("<3i", *active)]
+    ld, lc = scene_lights(scene)
+    out = [struct.pack("<IIii", 0x46524C47, 2, scene.width, scene.height), _cm(scene.projection), _cm(scene.world_to_cam),
+           ld.reshape(9).tobytes(), lc.reshape(9).tobytes(), np.asarray(scene.ambient_light, np.float32).reshape(3).tobytes(), struct.pack("<3i", *active)]
     out += [m.tobytes() for m in shadow]
     out += [np.asarray(scene.background_plane_size, np.float32).reshape(2).tobytes(), _cm(scene.background_plane_pose),
             struct.pack("<ii", tex_of(scene.background_plane_texture), tex_of(scene.background_image)),
-            struct.pack("<fii", float(scene.manual_exposure), int(bool(scene.ssao_enabled)), 0)]
+            struct.pack("<fi", float(scene.manual_exposure), int(bool(scene.ssao_enabled)))]
+    lm = scene.light_map
+    if lm is None:
+        out.append(struct.pack("<i", 0))
+    else:
+        eq = np.ascontiguousarray(lm.equirect, np.float32)
+        n = min(3, len(lm.light_directions))
+        dirs, cols = np.zeros(9, np.float32), np.zeros(9, np.float32)
+        dirs[:3 * n] = np.asarray(lm.light_directions, np.float32).reshape(-1)[:3 * n]
+        cols[:3 * n] = np.asarray(lm.light_colors, np.float32).reshape(-1)[:3 * n]
+        out += [struct.pack("<iii", 1, eq.shape[1], eq.shape[0]), eq.tobytes(), struct.pack("<i", n), dirs.tobytes(), cols.tobytes(),
+                struct.pack("<4i", *lightmap_sizes)]
     if peel is None:
         out.append(struct.pack("<i", 0))
     else:
@@ -127,15 +149,16 @@ def dump(scene, path, peel=None):
         f.write(b"".join(out))
 
 
-def render(scene, peel=None, env=None):
-    """-> dict named like oracle_util.render's: the eight targets (abi.TARGET_NAMES) + 'hdr'."""
+def render(scene, peel=None, env=None, lightmap_sizes=REFERENCE_LIGHTMAP_SIZES):
+    """-> dict named like oracle_util.render's: the eight targets (abi.TARGET_NAMES) + 'hdr' (+ 'lightmap': env level 0 [6,e,e,4],
+    irradiance [6,i,i,4], prefilter (packed levels), LUT [l,l,4] — the layout of Context.read_lightmap — when the scene has one)."""
     why = available()
     if why:
         raise RuntimeError(why)
     H, W = scene.height, scene.width
     with tempfile.TemporaryDirectory() as tmp:
         src, dst = os.path.join(tmp, "scene.bin"), os.path.join(tmp, "out.bin")
-        dump(scene, src, peel)
+        dump(scene, src, peel, lightmap_sizes)
         e = dict(os.environ, GLREF_LIBGL=build_ref.find_mesa_libgl(), GLREF_SHADER_DIR=SHADER_DIR, MESA_GL_VERSION_OVERRIDE="4.5",
                  MESA_GLSL_VERSION_OVERRIDE="450", LD_LIBRARY_PATH=os.path.join(os.path.dirname(GLREF), "glx") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
         e.update(env or {})
@@ -150,6 +173,18 @@ def render(scene, peel=None, env=None):
         at += n
     outs["hdr"] = raw[at:at + H * W * 16].view(np.float32).reshape(H, W, 4).copy()
     at += H * W * 16
+    if scene.light_map is not None:
+        e, i, pr, l = lightmap_sizes
+        def take(n):
+            nonlocal at
+            a = raw[at:at + 4 * n].view(np.float32).copy()
+            at += 4 * n
+            return a
+        env0 = take(6 * e * e * 4).reshape(6, e, e, 4)
+        irr = take(6 * i * i * 4).reshape(6, i, i, 4)
+        pre = take(sum(6 * (pr >> m) ** 2 * 4 for m in range(5)))
+        lut = take(l * l * 4).reshape(l, l, 4)
+        outs["lightmap"] = (env0, irr, pre, lut)
     if at < raw.size:
         outs["shadow0"] = raw[at:at + 2048 * 2048 * 4].view(np.float32).reshape(2048, 2048).copy()
     outs["stderr"] = p.stderr

@@ -35,6 +35,23 @@ def main():
         np.savez_compressed(path, class_index=g["class_index"], instance_index=g["instance_index"], vertex_index=g["vertex_index"][..., :3].copy(),
                             coord=g["coord"], normals=g["normals"].astype(np.float16), rgb=g["rgb"])
         print(name, os.path.getsize(path) // 1024, "KiB")
+    post_scenes()
+
+
+def post_scenes():
+    """'ssao' and 'ibl' (SSAO + sky box + image-based lighting): the frame plus, for 'ibl', the light maps GL's run of LightMap::load's
+    passes produced at 64 / 16 / 32 / 64 — the tests render with exactly those maps (LightMapData.maps), so the fixtures pin the
+    render path; the precompute is compared in tests/test_gl_ref.py."""
+    for name in ("ssao", "ibl"):
+        sc = fixtures.gl_post_scene(name)
+        g = glref_util.render(sc, env={"GLREF_FLOAT_TEXTURES": "1"}, lightmap_sizes=(64, 16, 32, 64))
+        extra = {}
+        if "lightmap" in g:
+            extra = dict(zip(("lm_env0", "lm_irr", "lm_pre", "lm_lut"), g["lightmap"]))
+        path = os.path.join(HERE, f"gl_ref_post_{name}.npz")
+        np.savez_compressed(path, class_index=g["class_index"], instance_index=g["instance_index"], vertex_index=g["vertex_index"][..., :3].copy(),
+                            coord=g["coord"], normals=g["normals"].astype(np.float16), rgb=g["rgb"], hdr=g["hdr"].astype(np.float16), **extra)
+        print("post", name, os.path.getsize(path) // 1024, "KiB")
 
 
 if __name__ == "__main__":
