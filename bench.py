@@ -169,6 +169,50 @@ class CpuBaseline:
         return len(self.jobs) / dt, dt
 
 
+class GlBaseline:
+    """The reference's own shaders on a CPU OpenGL implementation: oracle/_ref/glref (the reference's GLSL text, #define header and
+    uniform setters compiled in by oracle/build_ref.py; Mesa llvmpipe = the libGL bundled with Nsight Compute in this image) — what
+    SURVEY 8(d) names as the preferred CPU baseline. Scene-parallel like the port: `workers` glref processes, each with llvmpipe's
+    rasteriser in its own thread only (LP_NUM_THREADS=0), render their share of the first `n_sample` scenes of the workload.
+    Timed region = RenderPass::render per frame (shadow passes ... tone map, glFinish) as the harness clocks it; context creation,
+    shader compilation, mesh / texture upload and read-back are outside, as asset building is for the port."""
+
+    def __init__(self, name, pool, n_sample, light_map):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import tempfile
+        import glref_util
+        why = glref_util.available()
+        if why:
+            raise RuntimeError(why)
+        self.g = glref_util
+        self.cores = os.cpu_count() or 1
+        self.tmp = tempfile.TemporaryDirectory()
+        scenes = build_scenes(name, pool, light_map, 0, n_sample)
+        self.n = len(scenes)
+        self.workers = min(self.cores, self.n)
+        self.jobs = [[] for _ in range(self.workers)]
+        for k, sc in enumerate(scenes):
+            src, dst = os.path.join(self.tmp.name, f"s{k}.bin"), os.path.join(self.tmp.name, f"o{k}.bin")
+            glref_util.dump(sc, src, None, (128, 16, 32, 64))          # light-map sizes as the port's baseline (load-time work, untimed)
+            self.jobs[k % self.workers] += [src, dst]
+        self.env = glref_util.gl_env({"GLREF_TIMING": "1", "LP_NUM_THREADS": "0"})
+
+    def _worker(self, files):
+        p = subprocess.run([self.g.GLREF] + files, env=self.env, capture_output=True, text=True, timeout=1800)
+        if p.returncode != 0:
+            raise RuntimeError("glref failed: " + p.stderr[-2000:])
+        ms = [float(ln.split()[-1]) for ln in p.stderr.splitlines() if "render_ms" in ln]
+        assert len(ms) == len(files) // 2, p.stderr[-2000:]
+        return sum(ms) * 1e-3
+
+    def run(self):
+        """-> (frames/s, seconds): the slowest worker's summed render time bounds the step"""
+        with concurrent.futures.ThreadPoolExecutor(self.workers) as ex:
+            busy = list(ex.map(self._worker, self.jobs))
+        dt = max(busy)
+        return self.n / dt, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -177,20 +221,41 @@ def run_reference(args):
     n_scenes = args.scenes or c["n_scenes"]
     cores = os.cpu_count() or 1
     sample = min(n_scenes, max(8, cores if c["W"] <= 640 else cores // 2))
-    base = CpuBaseline(args.config, build_pool(), sample, build_light_map(args.config))
-    times = []
-    for i in range(args.warmup + args.steps):
-        fps, dt = base.run()
-        if i >= args.warmup:
-            times.append(dt)
-    dt = sum(times) / len(times)
-    fps = sample / dt
+    pool, light_map = build_pool(), build_light_map(args.config)
+
+    def timed(base, steps, warmup):
+        times = []
+        for i in range(warmup + steps):
+            _, dt = base.run()
+            if i >= warmup:
+                times.append(dt)
+        dt = sum(times) / len(times)
+        return sample / dt, dt
+
+    # the port (OpenMP oracle): always available
+    port_fps, port_dt = timed(CpuBaseline(args.config, pool, sample, light_map), args.steps, args.warmup)
+    kind, fps, dt = "port", port_fps, port_dt
+    what = f"scenes 0..{sample - 1} of the workload per step, OpenMP oracle, one scene per host thread"
+    extra = {}
+    # the reference's own shaders on Mesa llvmpipe (oracle/_ref/glref), when the image has them: this is then the line's value. A step
+    # costs seconds per frame and core, so it gets fewer steps (the frames are the same every step; there is no noise to average out).
+    if args.ref_arm != "port":
+        try:
+            gl_steps, gl_warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+            fps, dt = timed(GlBaseline(args.config, pool, sample, light_map), gl_steps, gl_warmup)
+            kind = "reference"
+            what = (f"scenes 0..{sample - 1} of the workload per step; the reference's GLSL programs + uniform setters (oracle/_ref/glref) on Mesa llvmpipe, "
+                    f"one process per scene slot, single-threaded rasteriser, RenderPass::render region only ({gl_steps} steps after {gl_warmup} warm-up; "
+                    f"the render loop around the shaders is restated as GL calls, DESIGN 5)")
+            extra = {"port": {"value": port_fps, "unit": "frames/s", "ms_per_step": port_dt * 1e3,
+                              "sample": "same scenes, OpenMP oracle, one scene per host thread"}}
+        except Exception as e:                      # no Mesa libGL / harness on this machine: the port stands
+            extra = {"reference_gl_unavailable": str(e)[:300]}
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_string(args.config, n_scenes)},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"scenes 0..{sample - 1} of the workload per step, OpenMP oracle, one scene per host thread"},
+            "cpu_baseline": dict({"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": what}, **extra),
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -238,6 +303,8 @@ def main():
     ap.add_argument("--scenes", type=int, default=0, help="batch size (default: the config's)")
     ap.add_argument("--subbatch", type=int, default=0)
     ap.add_argument("--targets", default="six", choices=["six", "eight"], help="six (40 B/px, the headline) or all eight targets (88 B/px)")
+    ap.add_argument("--ref-arm", default="auto", choices=["auto", "gl", "port"],
+                    help="--impl reference: the reference's shaders on Mesa llvmpipe when available (auto / gl), or the OpenMP oracle port only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -199,6 +199,14 @@ def build_gl(force=False):
             "render_shader_setters.inc": f"// cut from {src}:{first + 1}-{len(lines)} by oracle/build_ref.py - do not commit\n" + "\n".join(lines[first:]) + "\n"}
     cuts["ssao_tables.inc"] = _cut(os.path.join(REF, "src/shaders/ssao_shader.cpp"), "    // Create noise texture", "SSAOShader& SSAOShader::bindCoordinates")
     cuts["lightmap_cube.inc"] = _cut(os.path.join(REF, "src/light_map.cpp"), "    struct CubeMapSide", "}")
+    shader_dir = os.path.join(REF, "src/shaders")
+    blob = []
+    for fn in sorted(os.listdir(shader_dir)):
+        if fn.endswith((".vert", ".frag", ".geom", ".glsl")):
+            text = open(os.path.join(shader_dir, fn)).read()
+            assert ')GLSLFILE"' not in text
+            blob.append('{"%s", R"GLSLFILE(%s)GLSLFILE"},\n' % (fn, text))
+    cuts["shader_blob.inc"] = f"// {shader_dir}/* as string literals, by oracle/build_ref.py - do not commit\n" + "".join(blob)
     for name, text in cuts.items():
         assert "physx" not in text.lower()
         with open(os.path.join(gen, name), "w") as f:

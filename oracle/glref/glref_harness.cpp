@@ -14,7 +14,7 @@
 // order, pass order; each block below cites its lines), the mesh / texture upload of Mesh::loadVisual (src/mesh.cpp:624-745) and
 // Magnum's MeshTools::compile attribute bindings for the plane / quad primitives.
 //
-// usage: glref <scene dump> <output file>   (format: tests/glref_util.py)
+// usage: glref <scene dump> <output file> [...]   (format: tests/glref_util.py)
 #include <Corrade/Containers/Array.h>
 #include <Corrade/Containers/ArrayView.h>
 #include <Corrade/Containers/GrowableArray.h>
@@ -41,6 +41,7 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <random>
 #include <cstdio>
 #include <cstdlib>
@@ -239,7 +240,18 @@ namespace GL { using Magnum::GL::CubeMapCoordinate; }
 // program construction (what Magnum's GL::Shader / AbstractShaderProgram do for RenderShader::RenderShader)
 // ------------------------------------------------------------------------------------------------------------------------------
 static std::string g_shader_dir;
+// The shader files are compiled into this binary as string literals (oracle/build_ref.py writes _ref/gen/shader_blob.inc from
+// /root/reference/src/shaders — what the reference's own build does with corrade-rc), so that oracle/_ref/glref also runs where the
+// reference tree does not exist (the GPU box: bench.py --impl reference). GLREF_SHADER_DIR reads them from disk instead.
+struct ShaderFile { const char* name; const char* text; };
+static const ShaderFile kShaderFiles[] = {
+#include "_ref/gen/shader_blob.inc"
+};
 static std::string read_file(const std::string& name) {
+    if (g_shader_dir.empty()) {
+        for (const ShaderFile& f : kShaderFiles) if (name == f.name) return f.text;
+        fail("shader " + name + " is not compiled in");
+    }
     std::ifstream f(g_shader_dir + "/" + name, std::ios::binary);
     if (!f) fail("cannot read " + g_shader_dir + "/" + name);
     std::stringstream ss; ss << f.rdbuf();
@@ -534,14 +546,10 @@ static GLuint make_rect(GLenum ifmt, int W, int H, bool nearest) {
     return t;
 }
 
-int main(int argc, char** argv) {
-    if (argc < 3) fail("usage: glref <scene dump> <output file>");
-    const char* sd = std::getenv("GLREF_SHADER_DIR");
-    if (!sd) fail("GLREF_SHADER_DIR not set (the reference's src/shaders)");
-    g_shader_dir = sd;
+static int render_scene(const char* dump_path, const char* out_path, bool first) {
     Reader r;
     {
-        std::ifstream f(argv[1], std::ios::binary);
+        std::ifstream f(dump_path, std::ios::binary);
         if (!f) fail("cannot read the scene dump");
         r.buf.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
     }
@@ -586,8 +594,8 @@ int main(int argc, char** argv) {
         o.sticker_proj = r.mat4(); r.take(o.sticker_range, 16);
     }
 
-    create_context();
-    if (std::getenv("GLREF_VERBOSE")) std::fprintf(stderr, "glref: %s | %s | GLSL %s\n", glGetString(GL_RENDERER), glGetString(GL_VERSION), glGetString(GL_SHADING_LANGUAGE_VERSION));
+    if (first) create_context();
+    if (first && std::getenv("GLREF_VERBOSE")) std::fprintf(stderr, "glref: %s | %s | GLSL %s\n", glGetString(GL_RENDERER), glGetString(GL_VERSION), glGetString(GL_SHADING_LANGUAGE_VERSION));
     glEnable(GL_TEXTURE_CUBE_MAP_SEAMLESS);   // Magnum's context set-up (contrib/magnum/src/Magnum/GL/Context.cpp: seamless cube maps on desktop GL)
     for (TexIn& t : tex) upload_texture(t);
     for (MeshIn& m : meshes) upload_mesh(m);
@@ -685,6 +693,8 @@ int main(int argc, char** argv) {
     glTexSubImage2D(GL_TEXTURE_RECTANGLE, 0, 0, 0, W, H, GL_RGBA, GL_FLOAT, peel.data());
     check_gl("result textures");
 
+    glFinish();
+    const auto t_render0 = std::chrono::steady_clock::now();   // RenderPass::render proper starts here (assets and result buffers exist)
     // shadow pass (render_pass.cpp:423-460): front faces culled, every shadow caster's sub-meshes with shadowMatrix * meshToWorld
     glEnable(GL_CULL_FACE); glCullFace(GL_FRONT);
     for (int i = 0; i < 3; ++i) {
@@ -851,6 +861,8 @@ int main(int argc, char** argv) {
     glBindVertexArray(quad.vao); glDrawArrays(GL_TRIANGLE_STRIP, 0, quad.count);
     glFinish();
     check_gl("tone map");
+    const double render_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_render0).count();
+    if (std::getenv("GLREF_VERBOSE") || std::getenv("GLREF_TIMING")) std::fprintf(stderr, "glref: render_ms %.3f\n", render_ms);
 
     // the HDR buffer the tone map read
     std::vector<float> hdr((size_t)W * H * 4);
@@ -868,7 +880,7 @@ int main(int argc, char** argv) {
     get(normalTex, GL_RGBA, GL_FLOAT, normals.data()); get(vidxTex, GL_RGBA_INTEGER, GL_UNSIGNED_INT, vidx.data());
     get(baryTex, GL_RGBA, GL_FLOAT, bary.data()); get(camTex, GL_RGBA, GL_FLOAT, cam.data());
     check_gl("read back");
-    std::ofstream out(argv[2], std::ios::binary);
+    std::ofstream out(out_path, std::ios::binary);
     auto put = [&](const void* p, size_t n) { out.write((const char*)p, (std::streamsize)n); };
     put(rgb.data(), rgb.size()); put(coord.data(), coord.size() * 4); put(cls.data(), cls.size() * 2); put(inst.data(), inst.size() * 2);
     put(normals.data(), normals.size() * 4); put(vidx.data(), vidx.size() * 4); put(bary.data(), bary.size() * 4); put(cam.data(), cam.size() * 4);
@@ -899,5 +911,13 @@ int main(int argc, char** argv) {
         }
     }
     if (!out) fail("cannot write the output");
+    return 0;
+}
+
+// usage: glref <scene dump> <output file> [<scene dump> <output file> ...]   — one context, the scenes rendered one after the other
+int main(int argc, char** argv) {
+    if (argc < 3 || (argc - 1) % 2) fail("usage: glref <scene dump> <output file> [<scene dump> <output file> ...]");
+    if (const char* sd = std::getenv("GLREF_SHADER_DIR")) g_shader_dir = sd;
+    for (int i = 1; i + 1 < argc; i += 2) render_scene(argv[i], argv[i + 1], i == 1);
     return 0;
 }

@@ -29,8 +29,6 @@ def available():
         return "oracle/_ref/glref not built (python oracle/build_ref.py gl)"
     if build_ref.find_mesa_libgl() is None:
         return "no Mesa libGL in this image (" + build_ref.MESA_LIBGL_GLOB + ")"
-    if not os.path.isdir(SHADER_DIR):
-        return "the reference's shader sources are not here (" + SHADER_DIR + ")"
     return None
 
 
@@ -149,6 +147,18 @@ def dump(scene, path, peel=None, lightmap_sizes=REFERENCE_LIGHTMAP_SIZES):
         f.write(b"".join(out))
 
 
+def gl_env(extra=None):
+    """Environment of a glref process: the Mesa libGL, the fake Xlib next to the binary, the advertised GL / GLSL version; the shader
+    files are read from the reference tree when it is here (a harness built earlier stays current) and from the copy compiled into
+    the binary otherwise."""
+    e = dict(os.environ, GLREF_LIBGL=build_ref.find_mesa_libgl(), MESA_GL_VERSION_OVERRIDE="4.5", MESA_GLSL_VERSION_OVERRIDE="450",
+             LD_LIBRARY_PATH=os.path.join(os.path.dirname(GLREF), "glx") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    if os.path.isdir(SHADER_DIR):
+        e["GLREF_SHADER_DIR"] = SHADER_DIR
+    e.update(extra or {})
+    return e
+
+
 def render(scene, peel=None, env=None, lightmap_sizes=REFERENCE_LIGHTMAP_SIZES):
     """-> dict named like oracle_util.render's: the eight targets (abi.TARGET_NAMES) + 'hdr' (+ 'lightmap': env level 0 [6,e,e,4],
     irradiance [6,i,i,4], prefilter (packed levels), LUT [l,l,4] — the layout of Context.read_lightmap — when the scene has one)."""
@@ -159,9 +169,7 @@ def render(scene, peel=None, env=None, lightmap_sizes=REFERENCE_LIGHTMAP_SIZES):
     with tempfile.TemporaryDirectory() as tmp:
         src, dst = os.path.join(tmp, "scene.bin"), os.path.join(tmp, "out.bin")
         dump(scene, src, peel, lightmap_sizes)
-        e = dict(os.environ, GLREF_LIBGL=build_ref.find_mesa_libgl(), GLREF_SHADER_DIR=SHADER_DIR, MESA_GL_VERSION_OVERRIDE="4.5",
-                 MESA_GLSL_VERSION_OVERRIDE="450", LD_LIBRARY_PATH=os.path.join(os.path.dirname(GLREF), "glx") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-        e.update(env or {})
+        e = gl_env(env)
         p = subprocess.run([GLREF, src, dst], env=e, capture_output=True, text=True, timeout=600)
         if p.returncode != 0:
             raise RuntimeError("glref failed (%d): %s" % (p.returncode, p.stderr[-4000:]))
