@@ -36,6 +36,7 @@ def main():
                             coord=g["coord"], normals=g["normals"].astype(np.float16), rgb=g["rgb"])
         print(name, os.path.getsize(path) // 1024, "KiB")
     post_scenes()
+    bench_frame()
 
 
 def post_scenes():
@@ -52,6 +53,17 @@ def post_scenes():
         np.savez_compressed(path, class_index=g["class_index"], instance_index=g["instance_index"], vertex_index=g["vertex_index"][..., :3].copy(),
                             coord=g["coord"], normals=g["normals"].astype(np.float16), rgb=g["rgb"], hdr=g["hdr"].astype(np.float16), **extra)
         print("post", name, os.path.getsize(path) // 1024, "KiB")
+
+
+def bench_frame():
+    """Scene 1 of the headline workload (bench.py C3, 640x480, 20 objects, 328 k triangles): ids, depth and colour only (file size)."""
+    import bench
+    sc = bench.build_scenes("C3", bench.build_pool(), None, 1, 2)[0]
+    g = glref_util.render(sc, env={"GLREF_FLOAT_TEXTURES": "1"})
+    path = os.path.join(HERE, "gl_ref_bench_c3.npz")
+    np.savez_compressed(path, class_index=g["class_index"], instance_index=g["instance_index"], vertex_index=g["vertex_index"][..., :3].copy(),
+                        depth=g["coord"][..., 3].copy(), rgb=g["rgb"])
+    print("bench_c3", os.path.getsize(path) // 1024, "KiB")
 
 
 if __name__ == "__main__":

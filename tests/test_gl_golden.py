@@ -74,3 +74,35 @@ def test_cuda_post_passes_match_opengl_golden(gpu_ctx, name):
     res = gpu_ctx.render([sc], target_mask=abi.TARGETS_ALL)
     gpu_ctx.synchronize()
     check_against_gl(res.frame_dict(0), name, prefix="gl_ref_post_", rgb_budget=60 if name == "ssao" else 900)
+
+
+def check_bench_frame(out):
+    """The headline workload's own frame (bench.py C3, scene 1) against GL: ids / coverage, depth, colour (mip-mapped 8-bit textures on
+    the CUDA / oracle side, float texels on GL's: the colour budget is the LOD approximation's, tests/test_gl_ref.py)."""
+    z = np.load(os.path.join(fixtures.GOLDEN, "gl_ref_bench_c3.npz"))
+    bad = (((z["depth"] == abi.INVALID_COORD) != (out["coord"][..., 3] == abi.INVALID_COORD))
+           | np.any(z["instance_index"] != out["instance_index"], axis=-1) | np.any(z["class_index"] != out["class_index"], axis=-1)
+           | np.any(z["vertex_index"] != out["vertex_index"][..., :3], axis=-1))
+    assert int(bad.sum()) <= 40, int(bad.sum())                     # measured: 6 of 307 200
+    assert np.abs(z["depth"] - out["coord"][..., 3])[~bad].max() <= 1e-3
+    d8 = np.abs(z["rgb"].astype(int) - out["rgb"].astype(int)).max(-1)[~bad]
+    assert int((d8 > 8).sum()) <= 3000, int((d8 > 8).sum())
+
+
+def bench_scene():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    return bench.build_scenes("C3", bench.build_pool(), None, 1, 2)[0]
+
+
+def test_oracle_bench_frame_matches_opengl_golden():
+    import oracle_util as ou
+    check_bench_frame(ou.render(bench_scene()))
+
+
+@pytest.mark.gpu
+def test_cuda_bench_frame_matches_opengl_golden(gpu_ctx):
+    res = gpu_ctx.render([bench_scene()], target_mask=abi.TARGETS_ALL)
+    gpu_ctx.synchronize()
+    check_bench_frame(res.frame_dict(0))
