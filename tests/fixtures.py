@@ -293,6 +293,34 @@ def gl_post_scene(name):
     return sc
 
 
+def fuzz_scene(seed):
+    """Random corner cases of the fixed-function stage: viewports from 1x1 to 333x77, 1 - 8 objects, 0 - 3 shadow lights, with / without the
+    plane, hidden objects / non-casters, and five camera set-ups — inside the heap (geometry crossing the near plane and behind the camera),
+    a 100 - 150 degree field of view, 6 m away (sub-pixel triangles), grazing 1 - 5 cm above the plane, and the generator's own."""
+    from stillleben_b200.desc import fov_projection
+    rng = np.random.RandomState(seed)
+    W, H = [(320, 240), (64, 48), (17, 13), (200, 120), (3, 2), (1, 1), (333, 77)][rng.randint(7)]
+    sc = synth.tabletop_scene(small_pool(), seed, n_objects=int(rng.randint(1, 9)), width=W, height=H, intrinsics=None,
+                              n_lights=int(rng.randint(0, 4)), plane=bool(rng.randint(2)))
+    mode = rng.randint(5)
+    if mode == 0:
+        pos = rng.uniform(-0.3, 0.3, 3) * [1, 1, 0.3] + [0, 0, 0.15]
+        sc.world_to_cam = inverted_rigid(look_at_pose(pos, rng.uniform(-0.3, 0.3, 3) + [0, 0, 0.1]))
+    elif mode == 1:
+        sc.projection = fov_projection(W, H, float(rng.uniform(100, 150)))
+    elif mode == 2:
+        sc.world_to_cam = inverted_rigid(look_at_pose(np.array([5.0 * np.cos(seed), 5.0 * np.sin(seed), 3.0]), (0, 0, 0.1)))
+    elif mode == 3:
+        pos = np.array([rng.uniform(0.5, 1.2), rng.uniform(-0.3, 0.3), rng.uniform(0.01, 0.05)])
+        sc.world_to_cam = inverted_rigid(look_at_pose(pos, (0, 0, 0.05)))
+    for ob in sc.objects:
+        if rng.rand() < 0.2:
+            ob.casts_shadows = False
+        if rng.rand() < 0.1:
+            ob.visible = False
+    return single_level_copy(sc)
+
+
 VARIANTS = ["tabletop", "three_lights", "ssao", "auto_exposure", "no_plane_no_light", "empty", "ibl", "alpha_test", "sticker",
             "background_image", "plane_texture", "near_clip", "predicate", "id_limits", "odd_viewport", "multi_submesh", "low_poly_closeup",
             "pbr_textures", "pbr_textures_ibl", "projective", "c2_shape", "c5_shape"]
