@@ -54,7 +54,7 @@ def oracle_shadow_matrices(scene):
     L = C.CDLL(ou.ORACLE_SO)
     fp = C.POINTER(C.c_float)
     L.orc_test_shadow_setup.argtypes = [fp, fp, C.c_int, fp, fp, fp, fp, fp, fp, fp]
-    objs = [o for o in scene.objects if o.visible]       # computeShadowMapMatrix walks scene.objects() (no predicate)
+    objs = list(scene.objects)        # computeFrustumCorners / computeShadowMapMatrix walk scene.objects(): the draw predicate does not apply
     n = len(objs)
     as_f = lambda rows, k: np.ascontiguousarray(np.concatenate(rows).astype(np.float32) if rows else np.zeros(k, np.float32))
     poses = as_f([np.asarray(o.pose, np.float32).T.reshape(-1) for o in objs], 16)
