@@ -604,6 +604,10 @@ static int render_scene(const char* dump_path, const char* out_path, bool first)
     const PrimGL skyCube = upload_indexed(Primitives::cubeSolid());                                                  // render_pass.cpp:267
     sl::LightMap lightMap;
     if (hasLightMap) load_light_map(lmIn, lightMap, plane);
+    if (hasLightMap && std::getenv("GLREF_IBL_LEVEL0")) {   // experiment knob: irradiance map and LUT read at level 0 only (what the oracle does)
+        glBindTexture(GL_TEXTURE_CUBE_MAP, lightMap.irradiance.id); glTexParameteri(GL_TEXTURE_CUBE_MAP, GL_TEXTURE_MIN_FILTER, GL_LINEAR);
+        glBindTexture(GL_TEXTURE_2D, lightMap.lut.id); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR);
+    }
 
     // programs ------------------------------------------------------------------------------------------------------------------
     sl::RenderShader render;
