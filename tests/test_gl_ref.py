@@ -160,8 +160,7 @@ def test_depth_peel_matches_opengl():
     g = glref_util.render(sc, peel=first_g["coord"], env={"GLREF_FLOAT_TEXTURES": "1"})
     o = ou.render(sc, peel=first_o["coord"])
     bad = visibility_mismatch(g, o)
-    # the peel threshold (1e-5 m) sits inside the 3e-5 m agreement of the two depth buffers on grazing surfaces: a few dozen pixels flip
-    assert int(bad.sum()) <= 400, int(bad.sum())
+    assert int(bad.sum()) <= 40, int(bad.sum())                 # measured: 0 of 76 800 (5 280 second-layer pixels)
     second_layer = (o["coord"][..., 3] != abi.INVALID_COORD) & (first_o["coord"][..., 3] != abi.INVALID_COORD)
     assert second_layer.sum() > 1000 and np.all(o["coord"][..., 3][second_layer] > first_o["coord"][..., 3][second_layer])
 
@@ -221,6 +220,11 @@ def test_background_image_matches_opengl(wrap):
     rel = hdr_rel(g, o)
     assert background.sum() > 40000 and int((rel[background] > 1e-3).sum()) <= 20, int((rel[background] > 1e-3).sum())
     assert np.all(o["hdr"][..., 3][background] == 0.0) and np.all(g["hdr"][..., 3][background] == 0.0)      # alpha 0: not an object pixel
+    # Q1 of DESIGN §5, now observed instead of read: the quad sits at window depth 0.5 with the depth test still LESS, so GL lets the image
+    # replace the colour of every object pixel farther than about 0.2 m as well — here all of them (measured: 2 289 of 2 289, both sides)
+    objects = o["instance_index"][..., 0] > 0
+    assert objects.sum() > 1000 and np.all(g["hdr"][..., 3][objects] == 0.0) and np.all(o["hdr"][..., 3][objects] == 0.0)
+    assert int((rel[objects & ~tie_rows[:, None]] > 1e-3).sum()) <= 20
 
 
 def test_sky_box_and_image_based_lighting_match_opengl():
