@@ -220,7 +220,8 @@ def run_reference(args):
     c = CONFIGS[args.config]
     n_scenes = args.scenes or c["n_scenes"]
     cores = os.cpu_count() or 1
-    sample = min(n_scenes, max(8, cores if c["W"] <= 640 else cores // 2))
+    used = min(cores, 64)            # one scene per host thread / glref process; bounded so a very wide host does not need 100+ GL contexts
+    sample = min(n_scenes, max(8, used if c["W"] <= 640 else used // 2))
     pool, light_map = build_pool(), build_light_map(args.config)
 
     def timed(base, steps, warmup):
