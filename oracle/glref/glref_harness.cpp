@@ -605,8 +605,9 @@ static int render_scene(const char* dump_path, const char* out_path, bool first)
     sl::LightMap lightMap;
     if (hasLightMap) load_light_map(lmIn, lightMap, plane);
     if (hasLightMap && std::getenv("GLREF_IBL_LEVEL0")) {   // experiment knob: irradiance map and LUT read at level 0 only (what the oracle does)
-        glBindTexture(GL_TEXTURE_CUBE_MAP, lightMap.irradiance.id); glTexParameteri(GL_TEXTURE_CUBE_MAP, GL_TEXTURE_MIN_FILTER, GL_LINEAR);
-        glBindTexture(GL_TEXTURE_2D, lightMap.lut.id); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR);
+        const std::string which = std::getenv("GLREF_IBL_LEVEL0");   // "1" = both, "irr" / "lut" = one of them
+        if (which != "lut") { glBindTexture(GL_TEXTURE_CUBE_MAP, lightMap.irradiance.id); glTexParameteri(GL_TEXTURE_CUBE_MAP, GL_TEXTURE_MIN_FILTER, GL_LINEAR); }
+        if (which != "irr") { glBindTexture(GL_TEXTURE_2D, lightMap.lut.id); glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_LINEAR); }
     }
 
     // programs ------------------------------------------------------------------------------------------------------------------

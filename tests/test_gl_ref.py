@@ -252,7 +252,8 @@ def test_image_based_lighting_matches_opengl_at_level_zero():
     """The IBL branch of render_shader.frag isolated from the one place the oracle knowingly departs from GL: texture(irradianceMap, N) and
     texture(brdfLUT, ...) take an implicit LOD in GL (both textures carry mip chains), the oracle and the kernels read level 0. With GL told
     to do the same (GLREF_IBL_LEVEL0: minification filter LINEAR on those two textures, nothing else changed) the lit pixels agree —
-    measured: 25 of 76 800 beyond 1e-3, none beyond 1e-2 (without the knob: 728 / 103, all on silhouettes of small objects)."""
+    measured: 25 of 76 800 beyond 1e-3, none beyond 1e-2 (without the knob: 728 / 103, all at grazing incidence on silhouettes; forcing level 0 on
+    the LUT alone gives the same 25 / 0, on the irradiance map alone changes nothing: the whole difference is the LUT's implicit LOD)."""
     sc = single_level_copy(fixtures.variant("ibl"))
     sc.ssao_enabled = False
     for k, ob in enumerate(sc.objects):
