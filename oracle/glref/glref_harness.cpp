@@ -903,10 +903,10 @@ static int render_scene(const char* dump_path, const char* out_path, bool first)
         glBindTexture(GL_TEXTURE_2D, lightMap.lut.id); glGetTexImage(GL_TEXTURE_2D, 0, GL_RGBA, GL_FLOAT, lut.data());
         put(lut.data(), lut.size() * 4);
     }
-    if (std::getenv("GLREF_DUMP_SHADOW")) {   // light 0's depth layer as float, for debugging shadow-edge differences
+    if (std::getenv("GLREF_DUMP_SHADOW")) {   // the three depth layers of the shadow-map array as float (tests compare them with the oracle's d24 maps)
         std::vector<float> sm((size_t)SR * SR * 3);
         glBindTexture(GL_TEXTURE_2D_ARRAY, shadowMaps.id); glGetTexImage(GL_TEXTURE_2D_ARRAY, 0, GL_DEPTH_COMPONENT, GL_FLOAT, sm.data());
-        put(sm.data(), (size_t)SR * SR * 4);
+        put(sm.data(), sm.size() * 4);
     }
     if (const char* mp = std::getenv("GLREF_DUMP_MIPS")) {   // every 2-D texture's generated chain: i32 n_levels, then RGBA8 levels
         std::ofstream mo(mp, std::ios::binary);

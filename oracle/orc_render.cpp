@@ -790,6 +790,16 @@ int orc_texture_level(const void* tex, int level, int* w, int* h, uint8_t* out) 
     return (int)t->levels.size();
 }
 
+// test hook: the d24 shadow maps of the last orc_render call (tests/test_gl_ref.py compares them with GL's depth layers)
+static bool g_keep_shadow_maps = false;
+static std::vector<uint32_t> g_kept_shadow_map[SLB_NUM_LIGHTS];
+void orc_test_keep_shadow_maps(int on) { g_keep_shadow_maps = on != 0; if (!on) for (auto& m : g_kept_shadow_map) m.clear(); }
+size_t orc_test_shadow_map(int light, uint32_t* out) {   // -> number of texels (0: that light was inactive); out may be NULL
+    if (light < 0 || light >= SLB_NUM_LIGHTS) return 0;
+    const std::vector<uint32_t>& m = g_kept_shadow_map[light];
+    if (out && !m.empty()) std::memcpy(out, m.data(), m.size() * sizeof(uint32_t));
+    return m.size();
+}
 // Render one scene. The handles inside `sc` (mesh, textures, light map) are ORACLE handles.
 // out[t]: host arrays in the layouts of slb.h (NULL to skip); hdr_out: HxWx4 float pre-tone-map
 // colour (after background + SSAO), may be NULL; peel: HxWx4 float coord buffer of the previous
@@ -913,6 +923,7 @@ int orc_render(const slb_scene_desc* scp, const float* peel, void* const out[SLB
                 }
             }
         }
+        if (g_keep_shadow_maps) for (int li = 0; li < SLB_NUM_LIGHTS; ++li) g_kept_shadow_map[li] = f.lightActive[li] ? f.shadowMap[li] : std::vector<uint32_t>();
     }
 
     // ---- main pass: visibility (key = depth24 << 32 | primitive sequence number) ----

@@ -193,7 +193,7 @@ def render(scene, peel=None, env=None, lightmap_sizes=REFERENCE_LIGHTMAP_SIZES):
         pre = take(sum(6 * (pr >> m) ** 2 * 4 for m in range(5)))
         lut = take(l * l * 4).reshape(l, l, 4)
         outs["lightmap"] = (env0, irr, pre, lut)
-    if at < raw.size:
-        outs["shadow0"] = raw[at:at + 2048 * 2048 * 4].view(np.float32).reshape(2048, 2048).copy()
+    if at < raw.size:                   # GLREF_DUMP_SHADOW: the shadow-map array, float depth
+        outs["shadow"] = raw[at:at + 3 * 2048 * 2048 * 4].view(np.float32).reshape(3, 2048, 2048).copy()
     outs["stderr"] = p.stderr
     return outs
