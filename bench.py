@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--targets", default="six", choices=["six", "eight"], help="six (40 B/px, the headline) or all eight targets (88 B/px)")
     ap.add_argument("--ref-arm", default="auto", choices=["auto", "gl", "port"],
                     help="--impl reference: the reference's shaders on Mesa llvmpipe when available (auto / gl), or the OpenMP oracle port only")
+    ap.add_argument("--overlap", default="on", choices=["on", "off"], help="two-stream sub-batch pipeline in the timed region (SLB_OPT_OVERLAP)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -370,26 +371,44 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    two_streams = args.overlap == "on"
+    ctx.set_option(abi.OPT_OVERLAP, 1 if two_streams else 0)
     for _ in range(args.warmup):
         step()
-    ctx.set_option(abi.OPT_TIME_KERNELS, 1)
     st0 = ctx.stats()
     launches0 = st0.kernel_launches
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = np.zeros(8)
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
-    stage_ms += np.array(list(ctx.stats().last_kernel_ms))    # stage events of the whole timed region, read after it
     sampler.stop_flag = True
     ms = ev0.elapsed_time(ev1)
     launches = ctx.stats().kernel_launches - launches0
+    # ---- stage pass: the same steps again on ONE stream with a CUDA event pair around every stage. With the two-stream pipeline
+    # (SLB_OPT_OVERLAP) a stage's event interval on its stream also contains the other stream's kernels (the block dispatcher drains one
+    # grid before the next), so per-kernel durations - stage_ms_per_step, roofline, binner - are taken here, right after the timed
+    # region, same process, same inputs, same clocks; `pipeline.ms_per_step_single_stream` is this pass's own step time.
+    stage_steps = max(1, min(args.steps, 5))
+    ctx.set_option(abi.OPT_OVERLAP, 0)
+    ctx.set_option(abi.OPT_TIME_KERNELS, 1)
+    step()
+    torch.cuda.synchronize()
+    ctx.stats()                                               # drains the events of the settling step
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es0.record()
+    for _ in range(stage_steps):
+        step()
+    es1.record()
+    torch.cuda.synchronize()
+    stage_ms = np.array(list(ctx.stats().last_kernel_ms))     # stage events of the stage pass, read after it
+    serial_ms_per_step = es0.elapsed_time(es1) / stage_steps
     ctx.set_option(abi.OPT_TIME_KERNELS, 0)
+    ctx.set_option(abi.OPT_OVERLAP, 1 if two_streams else 0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -469,10 +488,10 @@ def main():
         ncu = json.load(open(mpath)).get(args.config, {})
     n_sub = -(-n_local // subbatch)
     frames_per_launch = n_local / n_sub
-    shade_ms = stage_ms[5] / (args.steps * n_sub)
+    shade_ms = stage_ms[5] / (stage_steps * n_sub)
     alg_bytes = frames_per_launch * W * H * BYTES_PER_PX
     achieved = alg_bytes / (shade_ms * 1e-3) / 1e9 if shade_ms > 0 else 0.0
-    setup_ms = stage_ms[1] / (args.steps * n_sub)
+    setup_ms = stage_ms[1] / (stage_steps * n_sub)
     geom_bytes = sum(sum(o.mesh.geometry_bytes() for o in sc.objects) for sc in scenes[:64]) / min(64, len(scenes)) * (1 + c["n_lights"])
     setup_gbs = geom_bytes * frames_per_launch / (setup_ms * 1e-3) / 1e9 if setup_ms > 0 else 0.0
     names = ["shadow", "bin_count", "scan", "bin_emit", "raster", "shade_store", "ssao", "post"]
@@ -484,8 +503,13 @@ def main():
                        "rank0_numa_node": numa_node,
                        "l2": "outputs per step (%.1f GB) exceed L2; no flush needed" % (n_local * W * H * BYTES_PER_PX / 1e9)},
             "clocks": sampler.summary(), "gpu_launches": int(launches),
-            "stage_ms_per_step": {n: float(v / args.steps) for n, v in zip(names, stage_ms)},
+            "pipeline": {"two_streams": two_streams, "ms_per_step_single_stream": serial_ms_per_step, "stage_pass_steps": stage_steps,
+                         "note": "value / ms_per_step: the timed region, sub-batch set-up and shade passes on two streams (SLB_OPT_OVERLAP) unless --overlap off; "
+                                 "stage_ms_per_step, roofline and binner: CUDA events around every stage in a single-stream pass of the same steps "
+                                 "right after it (on two streams a stage's event interval also contains the other stream's kernels)"},
+            "stage_ms_per_step": {n: float(v / stage_steps) for n, v in zip(names, stage_ms)},
             "roofline": {"bound": "hbm", "kernel": "k_shade (shade + MRT store)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "measured": "CUDA events on the launching stream, single-stream stage pass (see pipeline.note)",
                          "frac": achieved / peak,
                          "traffic": ks["dram_bytes_per_frame"] * frames_per_launch if "dram_bytes_per_frame" in ks else None,
                          "traffic_source": "profiles/r02_ncu_metrics.json (ncu --set full: dram read + write bytes of one k_shade launch, per frame, scaled to this launch size)",

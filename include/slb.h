@@ -330,7 +330,10 @@ enum {
     SLB_OPT_HUGE_PREPARE = 8,
     /* 1 (default): every shadow map carries a block-occupancy mask (one bit per 8x8 texels); PCF footprints over
      * untouched blocks skip their 25 taps. Results are bit-identical. */
-    SLB_OPT_SHADOW_MASK = 9
+    SLB_OPT_SHADOW_MASK = 9,
+    /* 1 (default): slb_render_batch queues the first phase of every sub-batch (upload, clear, set-up, scan) on an auxiliary stream of the
+       context, so that it overlaps the shade pass of the previous sub-batch (measured: +4 % on config C3); 0: everything on one stream */
+    SLB_OPT_OVERLAP = 10
 };
 int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value);
 

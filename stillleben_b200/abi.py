@@ -36,7 +36,7 @@ WRAP_REPEAT, WRAP_CLAMP_TO_EDGE, WRAP_MIRRORED_REPEAT, WRAP_CLAMP_TO_BORDER = ra
 TEXTURE_2D, TEXTURE_RECT = 0, 1
 
 OPT_TIME_KERNELS, OPT_KEEP_HDR, OPT_MAX_SUBBATCH, OPT_DIRECT_MAX, OPT_WARP_MAX, OPT_LEAN_SHADE, OPT_HUGE_IN_SHADE = 1, 2, 3, 4, 5, 6, 7
-OPT_HUGE_PREPARE, OPT_SHADOW_MASK = 8, 9
+OPT_HUGE_PREPARE, OPT_SHADOW_MASK, OPT_OVERLAP = 8, 9, 10
 
 # numpy dtype of the 68-byte consolidated vertex (reference: src/mesh_tools/consolidate.cpp:53-61)
 VERTEX_DTYPE = np.dtype([

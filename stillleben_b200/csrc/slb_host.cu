@@ -92,6 +92,8 @@ struct Scratch {
     void* shadow_pool_at = nullptr; size_t shadow_pool_cap = 0;
     void* batch = nullptr; void (*batch_delete)(void*) = nullptr;   // host arrays of the sub-batch (Batch, defined below)
     cudaEvent_t scanned = nullptr;
+    cudaEvent_t p1_done = nullptr, p2_done = nullptr;   // two-stream pipeline: first phase queued (aux stream) / second phase queued (render stream)
+    bool p2_recorded = false;
     Pending pending;
     void release() {
         DevBuf* bufs[] = {&frames_d, &draws_d, &chunk_base_d, &views_d, &bdraws_d, &scan_sums, &active_tiles, &scan_totals, &survivors, &clip_recs,
@@ -102,6 +104,9 @@ struct Scratch {
         if (total_pinned) cudaFreeHost(total_pinned);
         if (batch && batch_delete) batch_delete(batch);
         if (scanned) cudaEventDestroy(scanned);
+        if (p1_done) cudaEventDestroy(p1_done);
+        if (p2_done) cudaEventDestroy(p2_done);
+        p1_done = p2_done = nullptr; p2_recorded = false;
         staging = nullptr; total_pinned = nullptr; batch = nullptr; scanned = nullptr;
     }
 };
@@ -109,6 +114,9 @@ struct Scratch {
 struct slb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // first phases of the sub-batch pipeline when SLB_OPT_OVERLAP is on (slb_render_batch)
+    cudaEvent_t call_start = nullptr;
+    bool overlap = true;
     // All per-context scratch (two Scratch sets, shadow pool + generation tags, staging, diff / camera / PNG buffers) is
     // shared between calls, so calls are ORDERED even when they name different streams: enter_stream() makes the
     // stream of an entry point wait for everything the previous entry point queued. last_stream = where that was.
@@ -159,6 +167,7 @@ static cudaStream_t enter_stream(slb_ctx* ctx, void* stream) {
 static cudaError_t sync_ctx(slb_ctx* ctx) {
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (ctx->last_stream && ctx->last_stream != ctx->stream) { cudaError_t e2 = cudaStreamSynchronize(ctx->last_stream); if (e == cudaSuccess) e = e2; }
+    if (ctx->aux_stream) { cudaError_t e2 = cudaStreamSynchronize(ctx->aux_stream); if (e == cudaSuccess) e = e2; }   // already joined into the render stream; free
     return e;
 }
 
@@ -227,10 +236,14 @@ extern "C" int slb_ctx_create(int device, slb_ctx** out) {
     ctx = c;
     cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&c->call_start, cudaEventDisableTiming);
     cudaError_t e3 = cudaEventCreateWithFlags(&c->order_event, cudaEventDisableTiming);
     for (Scratch& S : c->scr) {
         if (e3 == cudaSuccess) e3 = cudaHostAlloc((void**)&S.total_pinned, 64, cudaHostAllocPortable | cudaHostAllocMapped);
         if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&S.scanned, cudaEventDisableTiming);
+        if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&S.p1_done, cudaEventDisableTiming);
+        if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&S.p2_done, cudaEventDisableTiming);
     }
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { for (Scratch& S : c->scr) S.release(); delete c; ctx = nullptr; return fail(ctx, SLB_ERR_CUDA, "slb_ctx_create: stream/pinned allocation failed"); }
     float noise[48], kernel[192];
@@ -285,6 +298,8 @@ extern "C" void slb_ctx_destroy(slb_ctx* ctx) {
     if (ctx->order_event) cudaEventDestroy(ctx->order_event);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->call_start) cudaEventDestroy(ctx->call_start);
     delete ctx;
 }
 
@@ -306,6 +321,7 @@ extern "C" int slb_ctx_set_option(slb_ctx* ctx, int option, int64_t value) {
         case SLB_OPT_LEAN_SHADE: ctx->lean_shade = value != 0; return SLB_OK;
         case SLB_OPT_HUGE_PREPARE: ctx->huge_prepare = value != 0; return SLB_OK;
         case SLB_OPT_SHADOW_MASK: ctx->shadow_mask = value != 0; return SLB_OK;
+        case SLB_OPT_OVERLAP: ctx->overlap = value != 0; return SLB_OK;
         case SLB_OPT_HUGE_IN_SHADE: ctx->huge_in_shade = value != 0; return SLB_OK;
         default: return fail(ctx, SLB_ERR_INVALID_ARGUMENT, "unknown option");
     }
@@ -1489,14 +1505,37 @@ extern "C" int slb_render_batch(slb_ctx* ctx, const slb_scene_desc* scenes, int3
     // Software pipeline over the two scratch sets: the first phase of sub-batch k+1 (marshal, upload, clear, set-up,
     // scan) is queued BEFORE the host waits for the scan totals of sub-batch k, so the GPU always has work while the
     // host sizes and queues the second phase (emit, raster, shade). Stream order: P1(0) P1(1) P2(0) P1(2) P2(1) ...
+    // SLB_OPT_OVERLAP (default on, more than one sub-batch): the first phases are queued on the context's auxiliary stream, the second
+    // phases on `s`, so that the set-up of sub-batch k+1 can fill the tail and the launch gaps of the shade pass of sub-batch k (the two
+    // touch different scratch sets). Ordering: the auxiliary stream starts after everything `s` holds at the call; P2(k) waits for P1(k)
+    // (p1_done); P1(k+2), which reuses the scratch set of k, waits for P2(k) (p2_done, also across calls). Every P1 is followed by its P2
+    // on `s`, so `s` alone still orders the call for the caller, for enter_stream() and for sync_ctx().
+    const bool two_streams = ctx->overlap && n_scenes > ctx->max_subbatch && ctx->aux_stream;
+    cudaStream_t s1 = two_streams ? ctx->aux_stream : s;
+    if (two_streams) { CU(cudaEventRecord(ctx->call_start, s)); CU(cudaStreamWaitEvent(s1, ctx->call_start, 0)); }
+    auto phase1 = [&](int k, int at, int n) -> int {
+        Scratch& S = ctx->scr[k & 1];
+        if (two_streams && S.p2_recorded) { if (cudaStreamWaitEvent(s1, S.p2_done, 0) != cudaSuccess) return fail(ctx, SLB_ERR_CUDA, "cudaStreamWaitEvent"); }
+        int r = subbatch_phase1(ctx, k & 1, scenes + at, n, result, first_frame + at, depth_peel, s1);
+        if (r == SLB_OK && two_streams && cudaEventRecord(S.p1_done, s1) != cudaSuccess) r = fail(ctx, SLB_ERR_CUDA, "cudaEventRecord");
+        return r;
+    };
+    auto phase2 = [&](int k) -> int {
+        Scratch& S = ctx->scr[k & 1];
+        if (two_streams && cudaStreamWaitEvent(s, S.p1_done, 0) != cudaSuccess) return fail(ctx, SLB_ERR_CUDA, "cudaStreamWaitEvent");
+        int r = subbatch_phase2(ctx, k & 1, s);
+        if (r == SLB_OK) { if (cudaEventRecord(S.p2_done, s) != cudaSuccess) r = fail(ctx, SLB_ERR_CUDA, "cudaEventRecord"); else S.p2_recorded = true; }
+        return r;
+    };
     int k = 0, rc = SLB_OK;
     for (int at = 0; at < n_scenes && rc == SLB_OK; at += ctx->max_subbatch, ++k) {
         const int n = std::min(ctx->max_subbatch, n_scenes - at);
-        rc = subbatch_phase1(ctx, k & 1, scenes + at, n, result, first_frame + at, depth_peel, s);
-        if (rc == SLB_OK && k > 0) rc = subbatch_phase2(ctx, (k - 1) & 1, s);
+        rc = phase1(k, at, n);
+        if (rc == SLB_OK && k > 0) rc = phase2(k - 1);
     }
-    if (rc == SLB_OK && k > 0) rc = subbatch_phase2(ctx, (k - 1) & 1, s);
+    if (rc == SLB_OK && k > 0) rc = phase2(k - 1);
     if (rc != SLB_OK) {   // leave no half-issued sub-batch behind
+        cudaStreamSynchronize(s1);
         cudaStreamSynchronize(s);
         ctx->scr[0].pending.active = ctx->scr[1].pending.active = false;
         return rc;

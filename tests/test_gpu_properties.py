@@ -222,3 +222,34 @@ def test_shadow_map_generations_wrap(gpu_ctx):
                 assert got == want, it
     finally:
         gpu_ctx.set_option(abi.OPT_MAX_SUBBATCH, 64)
+
+
+def test_two_stream_pipeline_changes_nothing(gpu_ctx, batch):
+    """SLB_OPT_OVERLAP: first phases of the sub-batches on the auxiliary stream, second phases on the render stream. Every target of every
+    frame must stay byte-identical — with sub-batches of two frames (six frames = three sub-batches: both scratch sets are reused inside
+    one call), over repeated calls (the reuse is also ordered ACROSS calls), and with work queued on a caller's stream around it."""
+    import torch
+    pool, scenes, _ = batch
+    try:
+        gpu_ctx.set_option(abi.OPT_MAX_SUBBATCH, 2)
+        gpu_ctx.set_option(abi.OPT_OVERLAP, 0)
+        res = gpu_ctx.render(scenes[:6], target_mask=abi.TARGETS_ALL)
+        gpu_ctx.synchronize()
+        ref = [digest(res, i) for i in range(6)]
+        gpu_ctx.set_option(abi.OPT_OVERLAP, 1)
+        stream = torch.cuda.Stream()
+        for attempt in range(4):
+            if attempt % 2:      # on a caller's stream, back to back with another render whose result is read after both
+                with torch.cuda.stream(stream):
+                    other = gpu_ctx.render(scenes[3:6] + scenes[:3], target_mask=abi.TARGETS_ALL, stream=stream.cuda_stream)
+                    again = gpu_ctx.render(scenes[:6], target_mask=abi.TARGETS_ALL, stream=stream.cuda_stream)
+                stream.synchronize()
+                gpu_ctx.synchronize()
+                assert [digest(other, i) for i in range(6)] == ref[3:] + ref[:3], attempt
+            else:
+                again = gpu_ctx.render(scenes[:6], target_mask=abi.TARGETS_ALL)
+                gpu_ctx.synchronize()
+            assert [digest(again, i) for i in range(6)] == ref, attempt
+    finally:
+        gpu_ctx.set_option(abi.OPT_MAX_SUBBATCH, 64)
+        gpu_ctx.set_option(abi.OPT_OVERLAP, 1)

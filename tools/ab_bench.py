@@ -22,7 +22,7 @@ res = lib.Result(ctx, cfg["W"], cfg["H"], a.scenes, abi.TARGETS_SIX)
 ctx.set_option(abi.OPT_TIME_KERNELS, 1)
 names = ["clear", "bin_count", "scan", "emit", "raster", "shade", "ssao", "post"]
 OPTS = {n[4:].lower(): getattr(abi, n) for n in dir(abi) if n.startswith("OPT_")}
-defaults = {"huge_prepare": 1, "shadow_mask": 1, "direct_max": 128, "warp_max": 4096, "lean_shade": 1, "huge_in_shade": 1}
+defaults = {"overlap": 1, "huge_prepare": 1, "shadow_mask": 1, "direct_max": 128, "warp_max": 4096, "lean_shade": 1, "huge_in_shade": 1}
 out = {}
 for cfg in a.configs:
     name, _, spec = cfg.partition("=")
